@@ -1,0 +1,180 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz from the UNMODIFIED reference.
+
+Run here (authoring container, CPU), where /root/reference exists:
+
+    python oracle/make_golden.py
+
+It imports the reference's own files through oracle/refshim.py, loads deterministic synthetic
+weights (oracle.ldmae_oracle.synth_*; the seed is stored, not the weights) into the reference's
+own nn.Modules and records inputs + outputs.  tests/test_oracle_golden.py then asserts the oracle
+restatement reproduces every output.  The GPU box has no /root/reference; it only reads the npz.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import refshim  # noqa: E402
+
+refshim.install()
+
+from oracle import ldmae_oracle as O  # noqa: E402
+
+from models.lightningdit import LightningDiT, LightningDiT_models  # noqa: E402  (reference)
+from transport import create_transport, Sampler  # noqa: E402               (reference)
+import tokenizer.models_mae as ref_mae  # noqa: E402                         (reference)
+
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+torch.set_grad_enabled(False)
+
+
+def load_into(module, sd):
+    missing, unexpected = module.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    return missing
+
+
+def tiny_dit(patch, **flags):
+    spec = O.DiTSpec(depth=2, hidden_size=128, patch_size=patch, num_heads=2, input_size=8, in_channels=16,
+                     num_classes=10, **flags)
+    ref = LightningDiT(input_size=8, patch_size=patch, in_channels=16, hidden_size=128, depth=2, num_heads=2,
+                       num_classes=10, use_qknorm=spec.use_qknorm, use_swiglu=spec.use_swiglu,
+                       use_rope=spec.use_rope, use_rmsnorm=spec.use_rmsnorm, wo_shift=spec.wo_shift)
+    # the reference's own state_dict must have exactly the keys/shapes the oracle lists
+    ref_shapes = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    assert ref_shapes == O.dit_param_shapes(spec), set(ref_shapes) ^ set(O.dit_param_shapes(spec))
+    sd = O.synth_dit_state(spec, seed=11 + patch)
+    # constant tables must equal the reference's own
+    assert torch.equal(sd["pos_embed"], ref.state_dict()["pos_embed"])
+    if spec.use_rope:
+        assert torch.equal(sd["feat_rope.freqs_cos"], ref.state_dict()["feat_rope.freqs_cos"])
+        assert torch.equal(sd["feat_rope.freqs_sin"], ref.state_dict()["feat_rope.freqs_sin"])
+    assert not load_into(ref, sd)
+    return spec, ref.eval(), sd
+
+
+def gen_dit_tiny():
+    for patch in (1, 2):
+        spec, ref, sd = tiny_dit(patch)
+        g = torch.Generator().manual_seed(100 + patch)
+        n = 3
+        x = torch.randn(2 * n, 16, 8, 8, generator=g)
+        t = torch.rand(2 * n, generator=g)
+        y = torch.randint(0, 10, (2 * n,), generator=g)
+        out = ref(x, t, y)
+        ycfg = torch.cat([y[:n], torch.full((n,), 10)])
+        tc = torch.full((2 * n,), 0.37)
+        cfg_hi = ref.forward_with_cfg(x, tc, ycfg, 4.0, cfg_interval=True, cfg_interval_start=0.10)
+        tl = torch.full((2 * n,), 0.05)
+        cfg_lo = ref.forward_with_cfg(x, tl, ycfg, 4.0, cfg_interval=True, cfg_interval_start=0.10)
+        # sampler through the reference's own transport (Euler + shift, and Heun)
+        tr = create_transport("Linear", "velocity", None, None, None, use_cosine_loss=False, use_lognorm=True)
+        smp = Sampler(tr)
+        z = torch.cat([x[:n], x[:n]], 0)
+        kw = dict(y=ycfg, cfg_scale=4.0, cfg_interval=True, cfg_interval_start=0.10)
+        fn_e = smp.sample_ode(sampling_method="euler", num_steps=7, atol=1e-6, rtol=1e-3, reverse=False, timestep_shift=0.3)
+        traj_e = fn_e(z, ref.forward_with_cfg, **kw)
+        fn_h = smp.sample_ode(sampling_method="heun2", num_steps=4, atol=1e-6, rtol=1e-3, reverse=False, timestep_shift=0.0)
+        traj_h = fn_h(z, ref.forward_with_cfg, **kw)
+        fn_n = smp.sample_ode(sampling_method="euler", num_steps=5, atol=1e-6, rtol=1e-3, reverse=False, timestep_shift=0.3)
+        traj_n = fn_n(x[:n], ref.forward, y=y[:n])
+        # training loss with the reference's random draws captured (not replaced)
+        torch.manual_seed(7); np.random.seed(7)
+        cap = {}
+        orig = tr.sample
+
+        def spy(x1, *a, **k):
+            r = orig(x1, *a, **k)
+            cap["t"], cap["x0"] = r[0].clone(), r[1].clone()
+            return r
+
+        tr.sample = spy
+        terms = tr.training_losses(ref, x, dict(y=y))       # eval mode: no label dropout
+        np.savez_compressed(
+            os.path.join(OUT, f"dit_tiny_p{patch}.npz"),
+            seed=11 + patch, checksum=O.state_checksum(sd), x=x.numpy(), t=t.numpy(), y=y.numpy(), out=out.numpy(),
+            ycfg=ycfg.numpy(), cfg_hi=cfg_hi.numpy(), cfg_lo=cfg_lo.numpy(),
+            traj_euler=traj_e.numpy(), traj_heun=traj_h.numpy(), traj_nocfg=traj_n.numpy(),
+            grid_euler=fn_e.__self__.t.numpy(), loss=terms["loss"].numpy(), pred=terms["pred"].numpy(),
+            loss_t=cap["t"].numpy(), loss_x0=cap["x0"].numpy())
+        print("dit tiny patch", patch, "out absmax", out.abs().max().item(), "loss", terms["loss"].mean().item())
+
+
+def gen_dit_variants():
+    """Config flags the API must accept (SURVEY section 8a tail): celeba (no qk-norm, 1 class -> no cfg
+    embedding is NOT the case: class_dropout_prob stays 0.1 unless num_classes==1), wo_shift."""
+    for tag, flags in (("noqk", dict(use_qknorm=False)), ("woshift", dict(wo_shift=True))):
+        spec, ref, sd = tiny_dit(1, **flags)
+        g = torch.Generator().manual_seed(55)
+        x = torch.randn(2, 16, 8, 8, generator=g); t = torch.rand(2, generator=g); y = torch.randint(0, 10, (2,), generator=g)
+        out = ref(x, t, y)
+        np.savez_compressed(os.path.join(OUT, f"dit_tiny_{tag}.npz"), seed=12, checksum=O.state_checksum(sd),
+                            x=x.numpy(), t=t.numpy(), y=y.numpy(), out=out.numpy())
+        print("dit variant", tag, out.abs().max().item())
+
+
+def gen_dit_b1():
+    spec = O.DiTSpec.named("LightningDiT-B/1", input_size=32, in_channels=16)
+    ref = LightningDiT_models["LightningDiT-B/1"](input_size=32, in_channels=16, use_qknorm=True, use_swiglu=True,
+                                                  use_rope=True, use_rmsnorm=True)
+    ref_shapes = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    assert ref_shapes == O.dit_param_shapes(spec)
+    sd = O.synth_dit_state(spec, seed=1234)
+    assert torch.equal(sd["pos_embed"], ref.state_dict()["pos_embed"])
+    assert torch.equal(sd["feat_rope.freqs_cos"], ref.state_dict()["feat_rope.freqs_cos"])
+    assert not load_into(ref, sd)
+    ref.eval()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 16, 32, 32, generator=g)
+    t = torch.tensor([0.0316, 0.7312])
+    y = torch.tensor([207, 1000])
+    out = ref(x, t, y)
+    np.savez_compressed(os.path.join(OUT, "dit_b1_forward.npz"), seed=1234, checksum=O.state_checksum(sd),
+                        x=x.numpy(), t=t.numpy(), y=y.numpy(), out=out.numpy())
+    # key list: the drop-in contract for checkpoints
+    with open(os.path.join(OUT, "dit_b1_keys.txt"), "w") as f:
+        for k, v in ref.state_dict().items():
+            f.write(f"{k} {list(v.shape)}\n")
+    print("dit B/1 out absmax", out.abs().max().item(), "std", out.std().item())
+
+
+def gen_vmae():
+    for img_size, bs, tag in ((32, 2, "small"), (256, 1, "full")):
+        spec = O.VMAESpec(img_size=img_size)
+        ref = ref_mae.mae_for_ldmae_f8d16_prev(ldmae_mode=True, no_cls=True, kl_loss_weight=True, smooth_output=True,
+                                               img_size=img_size).eval()
+        sd = O.synth_vmae_state(spec, seed=77, encoder=True)
+        ref_shapes = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+        mine = dict(O.vmae_decoder_param_shapes(spec)); mine.update(O.vmae_encoder_param_shapes(spec))
+        assert ref_shapes == mine, set(ref_shapes) ^ set(mine)
+        assert torch.allclose(sd["decoder_pos_embed"], ref.state_dict()["decoder_pos_embed"])
+        assert torch.equal(sd["decoder_pos_embed"], ref.state_dict()["decoder_pos_embed"])
+        assert not load_into(ref, sd)
+        g = torch.Generator().manual_seed(5)
+        z = torch.randn(bs, 16, spec.grid, spec.grid, generator=g)
+        img = ref.decode(z, return_dict=False)[0]
+        u8 = torch.clamp(127.5 * img + 128.0, 0, 255).permute(0, 2, 3, 1).to(torch.uint8).numpy()  # models_mae.py:972
+        pix = torch.randn(bs, 3, img_size, img_size, generator=g) * 0.5
+        mom = ref._encode(pix)
+        np.savez_compressed(os.path.join(OUT, f"vmae_{tag}.npz"), seed=77, checksum=O.state_checksum(sd), z=z.numpy(),
+                            img=img.numpy(), u8=u8, pix=pix.numpy(), moments=mom.numpy())
+        if tag == "full":
+            with open(os.path.join(OUT, "vmae_keys.txt"), "w") as f:
+                for k, v in ref.state_dict().items():
+                    f.write(f"{k} {list(v.shape)}\n")
+        print("vmae", tag, "img absmax", img.abs().max().item(), "u8 mean", u8.mean())
+
+
+if __name__ == "__main__":
+    gen_dit_tiny()
+    gen_dit_variants()
+    gen_dit_b1()
+    gen_vmae()
+    print("golden fixtures written to", OUT)

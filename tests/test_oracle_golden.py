@@ -1,0 +1,117 @@
+"""Pins the CPU oracle (oracle/ldmae_oracle.py) against outputs of the unmodified reference
+(tests/golden/*.npz, produced by oracle/make_golden.py in the authoring container)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ldmae_oracle as O
+
+torch.set_grad_enabled(False)
+TOL = dict(rtol=2e-4, atol=2e-5)   # fp32 CPU vs fp32 CPU, different op order (e.g. conv vs linear)
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def _tiny_spec(patch, **flags):
+    return O.DiTSpec(depth=2, hidden_size=128, patch_size=patch, num_heads=2, input_size=8, in_channels=16,
+                     num_classes=10, **flags)
+
+
+@pytest.mark.parametrize("patch", [1, 2])
+def test_dit_tiny_forward_cfg_and_sampler(golden_dir, patch):
+    g = _load(golden_dir, f"dit_tiny_p{patch}.npz")
+    spec = _tiny_spec(patch)
+    sd = O.synth_dit_state(spec, int(g["seed"]))
+    assert O.state_checksum(sd) == pytest.approx(float(g["checksum"]), rel=1e-9), "synthetic-weight RNG drifted"
+    x, t, y = _t(g["x"]), _t(g["t"]), _t(g["y"])
+    torch.testing.assert_close(O.dit_forward(sd, spec, x, t, y), _t(g["out"]), **TOL)
+    n = x.shape[0] // 2
+    ycfg = _t(g["ycfg"])
+    hi = O.dit_forward_with_cfg(sd, spec, x, torch.full((2 * n,), 0.37), ycfg, 4.0, True, 0.10)
+    lo = O.dit_forward_with_cfg(sd, spec, x, torch.full((2 * n,), 0.05), ycfg, 4.0, True, 0.10)
+    torch.testing.assert_close(hi, _t(g["cfg_hi"]), **TOL)
+    torch.testing.assert_close(lo, _t(g["cfg_lo"]), **TOL)
+    # guided channels are duplicated in both halves; below the interval start they equal cond
+    assert torch.equal(hi[:n, :3], hi[n:, :3]) and torch.equal(lo[:n, :3], lo[n:, :3])
+    # sampler: time grid bit-exact, trajectories close
+    assert np.array_equal(O.ode_time_grid(7, 0.3).numpy(), g["grid_euler"])
+    z = torch.cat([x[:n], x[:n]], 0)
+    kw = dict(y=ycfg, cfg_scale=4.0, cfg_interval=True, cfg_interval_start=0.10)
+    fn = lambda xx, tt, **k: O.dit_forward_with_cfg(sd, spec, xx, tt, **k)
+    te = O.sample_ode(fn, z, sampling_method="euler", num_steps=7, timestep_shift=0.3, **kw)
+    th = O.sample_ode(fn, z, sampling_method="heun2", num_steps=4, timestep_shift=0.0, **kw)
+    assert te.shape == g["traj_euler"].shape == (7, 2 * n, 16, 8, 8)      # N grid points, N-1 evals
+    torch.testing.assert_close(te, _t(g["traj_euler"]), rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(th, _t(g["traj_heun"]), rtol=1e-3, atol=1e-4)
+    fn2 = lambda xx, tt, **k: O.dit_forward(sd, spec, xx, tt, **k)
+    tn = O.sample_ode(fn2, x[:n], sampling_method="euler", num_steps=5, timestep_shift=0.3, y=y[:n])
+    torch.testing.assert_close(tn, _t(g["traj_nocfg"]), rtol=1e-3, atol=1e-4)
+    # training loss with the reference's own random draws
+    terms = O.training_losses(fn2, x, _t(g["loss_t"]), _t(g["loss_x0"]), y=y)
+    torch.testing.assert_close(terms["pred"], _t(g["pred"]), **TOL)
+    torch.testing.assert_close(terms["loss"], _t(g["loss"]), **TOL)
+
+
+@pytest.mark.parametrize("tag,flags", [("noqk", dict(use_qknorm=False)), ("woshift", dict(wo_shift=True))])
+def test_dit_tiny_variants(golden_dir, tag, flags):
+    g = _load(golden_dir, f"dit_tiny_{tag}.npz")
+    spec = _tiny_spec(1, **flags)
+    sd = O.synth_dit_state(spec, int(g["seed"]))
+    torch.testing.assert_close(O.dit_forward(sd, spec, _t(g["x"]), _t(g["t"]), _t(g["y"])), _t(g["out"]), **TOL)
+
+
+def test_dit_b1_forward(golden_dir):
+    g = _load(golden_dir, "dit_b1_forward.npz")
+    spec = O.DiTSpec.named("LightningDiT-B/1", input_size=32, in_channels=16)
+    sd = O.synth_dit_state(spec, int(g["seed"]))
+    assert O.state_checksum(sd) == pytest.approx(float(g["checksum"]), rel=1e-9)
+    out = O.dit_forward(sd, spec, _t(g["x"]), _t(g["t"]), _t(g["y"]))
+    torch.testing.assert_close(out, _t(g["out"]), rtol=1e-3, atol=1e-4)
+    keys = [l.split(" ", 1)[0] for l in open(os.path.join(golden_dir, "dit_b1_keys.txt"))]
+    assert keys and set(keys) == set(O.dit_param_shapes(spec))
+
+
+@pytest.mark.parametrize("tag,img", [("small", 32), ("full", 256)])
+def test_vmae_decode_encode(golden_dir, tag, img):
+    g = _load(golden_dir, f"vmae_{tag}.npz")
+    spec = O.VMAESpec(img_size=img)
+    sd = O.synth_vmae_state(spec, int(g["seed"]), encoder=True)
+    assert O.state_checksum(sd) == pytest.approx(float(g["checksum"]), rel=1e-9)
+    out = O.vmae_decode(sd, spec, _t(g["z"]))
+    torch.testing.assert_close(out, _t(g["img"]), rtol=1e-3, atol=1e-4)
+    u8 = O.images_to_uint8(out)
+    assert u8.dtype == np.uint8 and u8.shape == g["u8"].shape
+    # truncating cast: allow +-1 only where the fp32 value sits within 1e-3 of an integer boundary
+    diff = np.abs(u8.astype(np.int32) - g["u8"].astype(np.int32))
+    assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
+    mom = O.vmae_encode_moments(sd, spec, _t(g["pix"]))
+    torch.testing.assert_close(mom, _t(g["moments"]), rtol=1e-3, atol=1e-4)
+
+
+def test_unpatchify_bit_exact():
+    x = torch.arange(2 * 16 * 4 * 3, dtype=torch.float32).reshape(2, 16, 12)
+    out = O.unpatchify(x, 2, 3)
+    ref = torch.einsum("nhwpqc->nchpwq", x.reshape(2, 4, 4, 2, 2, 3)).reshape(2, 3, 8, 8)
+    assert torch.equal(out, ref)
+
+
+def test_rope_axis_layout():
+    """dims [0, hd/2) rotate with the row index, [hd/2, hd) with the column index."""
+    cos, sin = O.rope_tables(32, 32)
+    tok = 5 * 32 + 9
+    assert torch.allclose(cos[tok, :32], cos[5 * 32, :32]) and torch.allclose(cos[tok, 32:], cos[9, 32:])
+    assert torch.equal(cos[:, 0], cos[:, 1]) and torch.equal(sin[:, 62], sin[:, 63])
+
+
+def test_time_grid_counts():
+    t = O.ode_time_grid(250, 0.3)
+    assert t.shape == (250,) and t[0] == 0 and t[-1] == 1
+    assert int((t[:-1] < 0.10).sum()) == 68     # evals that skip guidance at cfg_interval_start 0.10
