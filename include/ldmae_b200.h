@@ -1,0 +1,120 @@
+/* ldmae_b200 -- C ABI of the B200-native LDMAE hot path (libldmae_b200.so).
+ *
+ * The reference (isno0907/ldmae) is pure Python/PyTorch and has no FFI; its boundary for this path is
+ * the Python module API that LDMAE/inference.py and LDMAE/train_accum.py import.  Each entry point
+ * below names the reference interface it sits under; ldmae_b200/ (Python) keeps those module names
+ * and signatures and calls this library through ctypes.
+ *
+ * Conventions: every function returns 0 on success and a negative code on failure; the message is
+ * available through ldmae_last_error() (thread-local).  Nothing throws across the boundary.  All
+ * tensor pointers are DEVICE pointers to contiguous memory in the reference's own layouts (NCHW fp32
+ * latents, int64 labels) unless a parameter says "host".  `stream` is a cudaStream_t passed as
+ * void* (PyTorch's current stream).  Handles are not thread-safe; one process per GPU.
+ */
+#ifndef LDMAE_B200_H
+#define LDMAE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDMAE_OK 0
+#define LDMAE_ERR_INVALID (-1)     /* bad argument / unsupported configuration */
+#define LDMAE_ERR_CUDA (-2)        /* a CUDA call or kernel failed */
+#define LDMAE_ERR_STATE (-3)       /* weights missing, workspace too small, ... */
+
+const char* ldmae_last_error(void);
+/* Library / device introspection: writes the SM count and compute capability (e.g. 100). */
+int ldmae_device_info(int* sm_count, int* cc);
+int ldmae_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * LightningDiT denoiser -- reference LDMAE/models/lightningdit.py:275-442 (class LightningDiT)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ldmae_dit_config {
+  int32_t depth, hidden_size, num_heads, patch_size;   /* registry lightningdit.py:498-531 */
+  int32_t input_size, in_channels;                     /* latent side and channels (inference.py:336-347) */
+  int32_t num_embeddings;                              /* rows of y_embedder.embedding_table (num_classes [+1]) */
+  int32_t mlp_hidden;                                  /* SwiGLU hidden = int(2/3 * 4 * hidden) (lightningdit.py:217) */
+  int32_t learn_sigma, use_qknorm, use_swiglu, use_rope, use_rmsnorm, wo_shift;
+  int32_t max_batch;                                   /* largest forward batch (2n with CFG) the workspace is sized for */
+} ldmae_dit_config;
+
+typedef struct ldmae_dit ldmae_dit;
+
+int ldmae_dit_create(const ldmae_dit_config* cfg, ldmae_dit** out);
+void ldmae_dit_destroy(ldmae_dit* h);
+
+/* nn.Module.load_state_dict, one tensor at a time: `name` is the reference state_dict key
+ * (SURVEY.md section 8b), `data` a device pointer to contiguous fp32 with `numel` elements.
+ * The library copies / packs (bf16, SwiGLU row interleave, adaLN concatenation) into its own buffers. */
+int ldmae_dit_load_tensor(ldmae_dit* h, const char* name, const float* data, int64_t numel, void* stream);
+/* Call once after all tensors were loaded (checks completeness). */
+int ldmae_dit_finalize(ldmae_dit* h, void* stream);
+
+/* LightningDiT.forward(x, t, y) in eval mode (lightningdit.py:391-418).
+ *   x [B, C, S, S] fp32, t [B] fp32 (or NULL with t_scalar broadcast), y [B] int64 -> out [B, C, S, S] fp32.
+ *   src_mod: sample b reads x[b % src_mod] (pass B for a plain forward; n for forward_with_cfg's cat[half,half]). */
+int ldmae_dit_forward(ldmae_dit* h, const float* x, const float* t, float t_scalar, const int64_t* y, float* out,
+                      int32_t B, int32_t src_mod, void* stream);
+
+/* LightningDiT.forward_with_cfg (lightningdit.py:420-442): x [2n,...], t [2n], y [2n] (last n = null class);
+ * guidance on channels [:3]; use_guidance = !(cfg_interval && t[0] < cfg_interval_start), decided by the
+ * caller on the host (the reference syncs the device for it). */
+int ldmae_dit_forward_with_cfg(ldmae_dit* h, const float* x, const float* t, float t_scalar, const int64_t* y,
+                               float* out, int32_t n, float cfg_scale, int32_t use_guidance, void* stream);
+
+/* transport Sampler.sample_ode(...)(x, model_fn, **kw) for path Linear / prediction velocity
+ * (transport/transport.py:398-443, integrators.py:77-126) with the fixed-grid solver of torchdiffeq.
+ *   x [Btot, C, S, S] fp32 in/out (Btot = 2n when cfg_scale > 1 and model_fn = forward_with_cfg, else n)
+ *   tgrid: HOST array of npts fp32 time points (npts - 1 model evaluations)
+ *   method: 0 euler, 1 heun2;  use_cfg: model_fn is forward_with_cfg;  cfg_interval_start < 0: no interval
+ *   traj (optional, device, [npts, Btot, C, S, S]): every grid state like torchdiffeq returns; NULL keeps only the last. */
+int ldmae_sample_ode(ldmae_dit* h, float* x, const int64_t* y, int32_t n, int32_t use_cfg, float cfg_scale,
+                     float cfg_interval_start, const float* tgrid, int32_t npts, int32_t method, float* traj,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * VMAE f8d16 ViT decoder -- reference LDMAE/tokenizer/models_mae.py:865-887 (decode), :963-973
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ldmae_vmae_config {
+  int32_t img_size, patch_size, latent_dim;            /* 256, 8, 16 */
+  int32_t embed_dim;                                   /* encoder width = input of decoder_embed (192) */
+  int32_t decoder_embed_dim, decoder_depth, decoder_num_heads;  /* 192, 12, 12 */
+  int32_t mlp_hidden;                                  /* 4 * decoder_embed_dim */
+  float ln_eps;                                        /* 1e-6 (models_mae.py:996) */
+  int32_t max_batch;
+} ldmae_vmae_config;
+
+typedef struct ldmae_vmae ldmae_vmae;
+
+int ldmae_vmae_create(const ldmae_vmae_config* cfg, ldmae_vmae** out);
+void ldmae_vmae_destroy(ldmae_vmae* h);
+int ldmae_vmae_load_tensor(ldmae_vmae* h, const char* name, const float* data, int64_t numel, void* stream);
+int ldmae_vmae_finalize(ldmae_vmae* h, void* stream);
+
+/* decode(z) (+ the latent de-normalisation of inference.py:291 when mean/std are given:
+ * z*std/multiplier + mean, per channel [C]).  Writes whichever outputs are non-NULL:
+ *   img_f32 [B,3,H,W] fp32 (decode(...)[0]) and/or img_u8 [B,H,W,3] uint8 (decode_to_images). */
+int ldmae_vmae_decode(ldmae_vmae* h, const float* z, const float* mean, const float* stdv, float multiplier,
+                      float* img_f32, uint8_t* img_u8, int32_t B, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Building blocks, exported for the parity tests and micro-benchmarks (device pointers).
+ * ---------------------------------------------------------------------------------------------- */
+/* out[M,N] = act(a[M,K] . w[N,K]^T + bias); a,w bf16 (raw uint16 storage), out fp32 or bf16.
+ * act: 0 none, 1 gelu(erf).  cta_group: 1 or 2.  block_n: 128 or 256. */
+int ldmae_gemm_bias(const void* a_bf16, const void* w_bf16, const float* bias, void* out, int32_t out_is_bf16,
+                    int32_t M, int32_t N, int32_t K, int32_t act, int32_t cta_group, int32_t block_n, void* stream);
+/* softmax(q k^T * scale) v over qkv [B*T, 3*H*64] bf16 (columns q|k|v, head-major) -> out [B*T, H*64] bf16. */
+int ldmae_attention(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t T, int32_t H, float scale, void* stream);
+/* float <-> bf16 conversion helpers for tests (device, n elements) */
+int ldmae_f32_to_bf16(const float* in, void* out_bf16, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDMAE_B200_H */

@@ -1,0 +1,108 @@
+// Host-side plumbing shared by the library translation units: error reporting across the C ABI,
+// device buffers, TMA tensor-map construction and the GEMM launcher.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+
+#include "../../include/ldmae_b200.h"
+#include "gemm_sm100.cuh"
+
+namespace ldmae {
+
+std::string& last_error();
+int set_error(int code, const char* fmt, ...);
+
+#define LDMAE_CUDA(expr)                                                                              \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess)                                                                            \
+      return ::ldmae::set_error(LDMAE_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+#define LDMAE_TRY(expr)          \
+  do {                           \
+    int _r = (expr);             \
+    if (_r != LDMAE_OK) return _r; \
+  } while (0)
+#define LDMAE_REQUIRE(cond, ...)                                    \
+  do {                                                              \
+    if (!(cond)) return ::ldmae::set_error(LDMAE_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  int alloc(size_t count, bool zero = false) {
+    release();
+    if (count == 0) return LDMAE_OK;
+    LDMAE_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
+    n = count;
+    if (zero) LDMAE_CUDA(cudaMemset(p, 0, count * sizeof(T)));
+    return LDMAE_OK;
+  }
+};
+
+int device_sm_count();
+
+// 2-D bf16 row-major [rows, cols] (leading dimension ld elements) -> tensor map with a
+// {64 x box_rows} box and 128-byte swizzle.  Cached by (ptr, rows, cols, ld, box_rows).
+int make_tmap_bf16(CUtensorMap* out, const void* ptr, int rows, int cols, int ld, int box_rows);
+
+template <int BN, int CG, class Epi>
+int launch_gemm(const void* a, int lda, const void* w, int ldw, GemmShape g, const typename Epi::Params& ep,
+                cudaStream_t st) {
+  using Cfg = GemmCfg<BN, CG>;
+  LDMAE_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty shape %d %d %d", g.M, g.N, g.K);
+  LDMAE_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, "gemm: leading dimensions must be multiples of 8 (16-byte TMA strides)");
+  CUtensorMap ta, tw;
+  LDMAE_TRY(make_tmap_bf16(&ta, a, g.M, g.K, lda, kBM));
+  LDMAE_TRY(make_tmap_bf16(&tw, w, g.N, g.K, ldw, Cfg::kLoadBN));
+  auto kern = gemm_tn_kernel<BN, CG, Epi>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LDMAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int n_tiles = (g.N + BN - 1) / BN;
+  const int m_tiles = (g.M + kBM * CG - 1) / (kBM * CG);
+  const long long total = static_cast<long long>(n_tiles) * m_tiles;
+  int sms = device_sm_count();
+  long long clusters = sms / CG;
+  if (total < clusters) clusters = total;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(clusters * CG));
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LDMAE_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tw, g, ep));
+  return LDMAE_OK;
+}
+
+// counts kernel launches issued by this library (bench.py reports it as gpu_launches)
+extern long long g_launch_count;
+
+}  // namespace ldmae

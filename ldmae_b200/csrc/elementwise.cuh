@@ -1,0 +1,340 @@
+// HBM-bound / small kernels of the path: conditioning (timestep + label embedding), adaLN operand
+// preparation, patch embedding, CFG-combine + ODE update, LayerNorm (VMAE), VMAE pixel tail, weight
+// packing.  All are coalesced, vectorised where the layout allows, with warp-shuffle reductions.
+#pragma once
+#include "ptx.cuh"
+
+namespace ldmae {
+
+__device__ __forceinline__ float warp_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weight packing (run once at load time)
+// ---------------------------------------------------------------------------------------------
+// dst[r, 0:Kd] = bf16(src[map(r), 0:Ks]) zero-padded to Kd; row map: 0 identity,
+// 1 SwiGLU interleave: dst row 64g+j holds hidden unit u = 32g + (j & 31): its x1 row (src row u) for
+// j < 32, its x2 row (src row H+u) otherwise; units u >= H (padding of H to a multiple of 32) are zero.
+__device__ __forceinline__ int swiglu_src_row(int r, int H) {
+  const int g = r >> 6, j = r & 63;
+  const int u = 32 * g + (j & 31);
+  if (u >= H) return -1;
+  return (j < 32) ? u : H + u;
+}
+__global__ void pack_rows_bf16_kernel(__nv_bfloat16* __restrict__ dst, const float* __restrict__ src, int rows, int Ks,
+                                      int Kd, int mode, int H) {
+  const int r = blockIdx.x;
+  const int sr = (mode == 1) ? swiglu_src_row(r, H) : r;
+  for (int k = threadIdx.x; k < Kd; k += blockDim.x)
+    dst[static_cast<size_t>(r) * Kd + k] =
+        __float2bfloat16((k < Ks && sr >= 0) ? src[static_cast<size_t>(sr) * Ks + k] : 0.f);
+}
+__global__ void pack_vec_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, int n, int mode, int H) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int sr = (mode == 1) ? swiglu_src_row(r, H) : r;
+  dst[r] = sr >= 0 ? src[sr] : 0.f;
+}
+// VMAE head padding hd -> 64:  qkv weight [3*nh*hd, K] -> [3*nh*64, K] (zero rows), bias likewise;
+// proj weight [D, nh*hd] -> [D, nh*64] (zero columns).
+__global__ void pad_heads_rows_kernel(__nv_bfloat16* __restrict__ dstw, float* __restrict__ dstb,
+                                      const float* __restrict__ w, const float* __restrict__ bias, int nh, int hd, int K) {
+  const int r = blockIdx.x;                       // dst row in [0, 3*nh*64)
+  const int sec = r / (nh * 64), h = (r / 64) % nh, d = r % 64;
+  const bool real = d < hd;
+  const int sr = sec * nh * hd + h * hd + d;
+  for (int k = threadIdx.x; k < K; k += blockDim.x)
+    dstw[static_cast<size_t>(r) * K + k] = __float2bfloat16(real ? w[static_cast<size_t>(sr) * K + k] : 0.f);
+  if (threadIdx.x == 0 && dstb != nullptr) dstb[r] = real ? bias[sr] : 0.f;
+}
+__global__ void pad_heads_cols_kernel(__nv_bfloat16* __restrict__ dstw, const float* __restrict__ w, int nh, int hd) {
+  const int r = blockIdx.x;                       // output row, D rows; dst row length nh*64
+  for (int c = threadIdx.x; c < nh * 64; c += blockDim.x) {
+    const int h = c / 64, d = c % 64;
+    dstw[static_cast<size_t>(r) * nh * 64 + c] = __float2bfloat16(d < hd ? w[static_cast<size_t>(r) * nh * hd + h * hd + d] : 0.f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Conditioning: c = t_embedder(t) + y_embedder(y)       (lightningdit.py:108-137,163-169,403-405)
+// ---------------------------------------------------------------------------------------------
+// out[b, n] = act(in[b, :] . W[n, :] + bias[n]) (+ add[idx[b], n]); fp32 on CUDA cores.  One block =
+// 16 samples (inputs staged in smem) x 64 outputs (8 warps x 8 outputs, weights streamed once per block).
+// in_mode 1: the input row is the sinusoidal timestep embedding of t[b] (dim K, not scaled by 1000).
+template <int ACT /*0 none, 1 silu*/>
+__global__ void __launch_bounds__(256)
+small_linear_kernel(float* __restrict__ out, const float* __restrict__ in, const float* __restrict__ tvals, float tscalar,
+                    const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ add_table,
+                    const long long* __restrict__ add_idx, int B, int K, int N, int in_mode, int in_ld) {
+  extern __shared__ float s_in[];                 // [16][K]
+  const int b0 = blockIdx.y * 16;
+  const int nb = min(16, B - b0);
+  for (int i = threadIdx.x; i < 16 * K; i += blockDim.x) {
+    const int bb = i / K, k = i % K;
+    float v = 0.f;
+    if (bb < nb) {
+      if (in_mode == 1) {
+        const int half = K / 2;
+        const float t = tvals ? tvals[b0 + bb] : tscalar;
+        const int f = k % half;
+        const float freq = expf(-9.210340371976184f * static_cast<float>(f) / static_cast<float>(half));
+        const float a = t * freq;
+        v = (k < half) ? cosf(a) : sinf(a);
+      } else {
+        v = in[static_cast<size_t>(b0 + bb) * in_ld + k];
+      }
+    }
+    s_in[i] = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int o = 0; o < 8; ++o) {
+    const int n = blockIdx.x * 64 + warp * 8 + o;
+    if (n >= N) break;
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float w = __ldg(W + static_cast<size_t>(n) * K + k);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = fmaf(w, s_in[i * K + k], acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = warp_sum(acc[i]);
+    if (lane < nb) {
+      float v = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) if (i == lane) v = acc[i];
+      v += bias[n];
+      if (ACT == 1) v = silu_f(v);
+      if (add_table != nullptr) v += add_table[static_cast<size_t>(add_idx[b0 + lane]) * N + n];
+      out[static_cast<size_t>(b0 + lane) * N + n] = v;
+    }
+  }
+}
+
+// sc = bf16(silu(c))  -- operand of every adaLN_modulation Linear (lightningdit.py:228-236,263-266)
+__global__ void silu_to_bf16_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ in, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16(silu_f(in[i]));
+}
+
+// From the adaLN outputs mods[B, Ntot] build, for norm slot s (2 per block + final):
+//   shift_bf16[s][b][:] = bf16(shift)            (A operand of the per-sample shift . W^T GEMM)
+//   gmul[s][b][:]       = norm_weight[s][:] * (1 + scale)
+// slot_shift_off[s] < 0 means wo_shift (shift = 0).
+__global__ void adaln_prep_kernel(__nv_bfloat16* __restrict__ shift_bf16, float* __restrict__ gmul,
+                                  const float* __restrict__ mods, const float* __restrict__ norm_w /*[S][D]*/,
+                                  const int* __restrict__ slot_shift_off, const int* __restrict__ slot_scale_off, int B,
+                                  int D, int Ntot, int S) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(S) * B * D;
+  if (i >= total) return;
+  const int d = i % D;
+  const int b = (i / D) % B;
+  const int s = i / (static_cast<size_t>(D) * B);
+  const float* row = mods + static_cast<size_t>(b) * Ntot;
+  const int so = slot_shift_off[s];
+  shift_bf16[i] = __float2bfloat16(so >= 0 ? row[so + d] : 0.f);
+  gmul[i] = norm_w[s * D + d] * (1.f + row[slot_scale_off[s] + d]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Patch embedding + positional embedding (timm PatchEmbed = Conv2d k=stride=p; lightningdit.py:402)
+// fused with the first norm's operand preparation (see EpiResidual).  One block = 32 tokens of a sample.
+//   x[row, n]   = W[n, :] . patch(row) + bias[n] + pos[tok, n]
+//   anext[row,n]= bf16(x * gnext[b, n]);  ssq[row] = sum_n x^2
+// src_mod: sample b reads latent (b % src_mod) -- forward_with_cfg feeds cat[half, half] (lightningdit.py:425-426).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+patch_embed_kernel(float* __restrict__ x, __nv_bfloat16* __restrict__ anext, float* __restrict__ ssq,
+                   const float* __restrict__ lat /*[Bsrc, C, S, S]*/, const float* __restrict__ W /*[D, C*p*p]*/,
+                   const float* __restrict__ bias, const float* __restrict__ pos /*[T, D]*/,
+                   const float* __restrict__ gnext /*[B, D]*/, int C, int S, int p, int D, int src_mod) {
+  extern __shared__ float sm[];
+  const int G = S / p, T = G * G, Kp = C * p * p;
+  float* s_in = sm;                               // [32][Kp]
+  float* s_red = sm + 32 * Kp;                    // [32] per-token sum of squares
+  const int b = blockIdx.y;
+  const int tok0 = blockIdx.x * 32;
+  const float* src = lat + static_cast<size_t>(b % src_mod) * C * S * S;
+  for (int i = threadIdx.x; i < 32 * Kp; i += blockDim.x) {
+    const int k = i / 32, tl = i % 32;            // tokens fastest -> coalesced for p == 1
+    const int tok = tok0 + tl;
+    float v = 0.f;
+    if (tok < T) {
+      const int c = k / (p * p), pi = (k / p) % p, qi = k % p;     // conv weight layout [D, C, p, p]
+      const int th = tok / G, tw = tok % G;
+      v = src[(static_cast<size_t>(c) * S + th * p + pi) * S + tw * p + qi];
+    }
+    s_in[tl * Kp + k] = v;
+  }
+  if (threadIdx.x < 32) s_red[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  for (int n = threadIdx.x; n < D; n += blockDim.x) {          // D % 32 == 0: warp-uniform trip count
+    const float bn = bias[n];
+    const float gn = gnext ? gnext[static_cast<size_t>(b) * D + n] : 1.f;
+#pragma unroll 1
+    for (int hf = 0; hf < 2; ++hf) {
+      float acc[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = bn;
+#pragma unroll 1
+      for (int k0 = 0; k0 < Kp; k0 += 4) {
+        const float4 w = *reinterpret_cast<const float4*>(W + static_cast<size_t>(n) * Kp + k0);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float4 a = *reinterpret_cast<const float4*>(s_in + (hf * 16 + i) * Kp + k0);
+          acc[i] = fmaf(w.x, a.x, fmaf(w.y, a.y, fmaf(w.z, a.z, fmaf(w.w, a.w, acc[i]))));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int tok = tok0 + hf * 16 + i;
+        float sq = 0.f;
+        if (tok < T) {
+          const float v = acc[i] + pos[static_cast<size_t>(tok) * D + n];
+          const size_t off = (static_cast<size_t>(b) * T + tok) * D + n;
+          x[off] = v;
+          if (anext) anext[off] = __float2bfloat16(v * gn);
+          sq = v * v;
+        }
+        sq = warp_sum(sq);
+        if (lane == 0) atomicAdd(&s_red[hf * 16 + i], sq);
+      }
+    }
+  }
+  __syncthreads();
+  if (ssq != nullptr && threadIdx.x < 32 && tok0 + threadIdx.x < T)
+    ssq[static_cast<size_t>(b) * T + tok0 + threadIdx.x] = s_red[threadIdx.x];
+}
+
+// ---------------------------------------------------------------------------------------------
+// CFG combine + ODE update (lightningdit.py:432-442 + torchdiffeq fixed-grid step), one pass:
+//   g = guided velocity:  channels < cfg_ch: use_guidance ? vu + s*(vc - vu) : vc   (both halves)
+//                         other channels   : the half's own prediction
+//   xout = xin + a*g + b*kprev ;  optionally gout = g
+// With n_half == 0 there is no CFG pairing (plain forward): g = v.
+// ---------------------------------------------------------------------------------------------
+__global__ void cfg_ode_update_kernel(float* __restrict__ xout, const float* __restrict__ xin,
+                                      const float* __restrict__ v, const float* __restrict__ kprev,
+                                      float* __restrict__ gout, int n_half, int C, int HW, int cfg_ch, float cfg_scale,
+                                      int use_guidance, float a, float bcoef, size_t total /* elements of [Btot,C,HW] */) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float g = v[i];
+  if (n_half > 0) {
+    const size_t per = static_cast<size_t>(C) * HW;
+    const int bidx = i / per;
+    const int c = (i % per) / HW;
+    if (c < cfg_ch) {
+      const size_t j = i - static_cast<size_t>(bidx >= n_half ? n_half : 0) * per;   // cond element
+      const float vc = v[j], vu = v[j + static_cast<size_t>(n_half) * per];
+      g = use_guidance ? (vu + cfg_scale * (vc - vu)) : vc;
+    }
+  }
+  if (gout) gout[i] = g;
+  if (xout) {
+    float xn = xin[i] + a * g;
+    if (kprev) xn += bcoef * kprev[i];
+    xout[i] = xn;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// VMAE: LayerNorm (affine, eps) fp32 -> bf16, one warp per row.   (tokenizer/models_mae.py:177-181,880)
+// ---------------------------------------------------------------------------------------------
+__global__ void layernorm_bf16_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ x,
+                                      const float* __restrict__ w, const float* __restrict__ bvec, int M, int D, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* xr = x + static_cast<size_t>(row) * D;
+  float s = 0.f;
+  for (int k = lane; k < D; k += 32) s += xr[k];
+  const float mean = warp_sum(s) / D;
+  float q = 0.f;
+  for (int k = lane; k < D; k += 32) { const float d = xr[k] - mean; q = fmaf(d, d, q); }
+  const float rstd = rsqrtf(warp_sum(q) / D + eps);
+  for (int k = lane; k < D; k += 32)
+    out[static_cast<size_t>(row) * D + k] = __float2bfloat16((xr[k] - mean) * rstd * w[k] + bvec[k]);
+}
+
+// latent [B,C,g,g] fp32 -> de-normalised tokens [B*g*g, Kpad] bf16 (zero padded):
+//   z' = z * std[c] / multiplier + mean[c]   (inference.py:291), 'b c h w -> b (h w) c' (models_mae.py:868)
+__global__ void latent_to_tokens_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ z,
+                                        const float* __restrict__ mean, const float* __restrict__ stdv, float inv_mult,
+                                        int B, int C, int L, int Kpad) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(B) * L * Kpad;
+  if (i >= total) return;
+  const int k = i % Kpad;
+  const size_t row = i / Kpad;
+  float v = 0.f;
+  if (k < C) {
+    const size_t b = row / L, t = row % L;
+    v = z[(b * C + k) * L + t];
+    if (mean != nullptr) v = v * stdv[k] * inv_mult + mean[k];
+  }
+  out[i] = __float2bfloat16(v);
+}
+
+// x[row, :] = pos[row % L, :]   (the residual epilogue then adds decoder_embed(.) + bias; models_mae.py:871-877)
+__global__ void broadcast_rows_kernel(float* __restrict__ x, const float* __restrict__ pos, size_t M, int L, int D) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= M * D) return;
+  const size_t row = i / D;
+  x[i] = pos[(row % L) * D + (i % D)];
+}
+
+// Pixel tail: pred [B*L, p*p*3] (token-major, column = (pi*p+qi)*3 + c) -> unpatchify -> Conv2d(3,3,3x3,pad 1)
+// (conv_decoder_pred, models_mae.py:271-279) -> either fp32 NCHW or uint8 NHWC via
+// clamp(127.5*x + 128, 0, 255) truncated (models_mae.py:972).  One thread = one pixel, all 3 channels.
+__global__ void vmae_pixel_tail_kernel(float* __restrict__ out_f32, uint8_t* __restrict__ out_u8,
+                                       const float* __restrict__ pred, const float* __restrict__ cw /*[3,3,3,3]*/,
+                                       const float* __restrict__ cb, int B, int G, int p) {
+  const int HW = G * p;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(B) * HW * HW;
+  if (i >= total) return;
+  const int X = i % HW, Y = (i / HW) % HW;
+  const size_t b = i / (static_cast<size_t>(HW) * HW);
+  const int ld = p * p * 3;
+  float acc[3] = {cb[0], cb[1], cb[2]};
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int yy = Y + dy;
+    if (yy < 0 || yy >= HW) continue;
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int xx = X + dx;
+      if (xx < 0 || xx >= HW) continue;
+      const float* px = pred + (b * G * G + static_cast<size_t>(yy / p) * G + xx / p) * ld + ((yy % p) * p + xx % p) * 3;
+      const float i0 = px[0], i1 = px[1], i2 = px[2];
+      const int kk = (dy + 1) * 3 + (dx + 1);
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        acc[c] = fmaf(cw[(c * 3 + 0) * 9 + kk], i0, fmaf(cw[(c * 3 + 1) * 9 + kk], i1, fmaf(cw[(c * 3 + 2) * 9 + kk], i2, acc[c])));
+    }
+  }
+  if (out_f32) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out_f32[((b * 3 + c) * HW + Y) * HW + X] = acc[c];
+  }
+  if (out_u8) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = fminf(fmaxf(127.5f * acc[c] + 128.0f, 0.f), 255.f);
+      out_u8[(((b * HW) + Y) * HW + X) * 3 + c] = static_cast<uint8_t>(v);
+    }
+  }
+}
+
+}  // namespace ldmae

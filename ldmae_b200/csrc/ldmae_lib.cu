@@ -1,0 +1,777 @@
+// libldmae_b200: C ABI (include/ldmae_b200.h) over the sm_100a kernels.
+//   * ldmae_dit_*      LightningDiT forward / forward_with_cfg (reference models/lightningdit.py:391-442)
+//   * ldmae_sample_ode transport ODE sampler loop (reference transport/integrators.py:77-126)
+//   * ldmae_vmae_*     VMAE ViT decoder (reference tokenizer/models_mae.py:865-887,963-973)
+// Host orchestration only: every FLOP and byte of the path runs in the CUDA kernels of this directory.
+#include <algorithm>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "attention_sm100.cuh"
+#include "common.cuh"
+#include "elementwise.cuh"
+
+namespace ldmae {
+
+// ------------------------------------------------------------------------------------------- plumbing
+std::string& last_error() {
+  static thread_local std::string e;
+  return e;
+}
+int set_error(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  last_error() = buf;
+  return code;
+}
+long long g_launch_count = 0;
+
+int device_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* ptr, int rows, int cols, int ld, int box_rows) {
+  typedef std::tuple<const void*, int, int, int, int> Key;
+  static thread_local std::map<Key, CUtensorMap> cache;
+  Key key(ptr, rows, cols, ld, box_rows);
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return LDMAE_OK;
+  }
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return set_error(LDMAE_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  LDMAE_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "tensor map: base pointer must be 16-byte aligned");
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(LDMAE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d box_rows=%d", (int)r, rows,
+                     cols, ld, box_rows);
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = *out;
+  return LDMAE_OK;
+}
+
+static inline unsigned cdiv(size_t a, size_t b) { return static_cast<unsigned>((a + b - 1) / b); }
+#define LDMAE_LAUNCH_CHECK()                                                                      \
+  do {                                                                                            \
+    ++::ldmae::g_launch_count;                                                                    \
+    cudaError_t _e = cudaGetLastError();                                                          \
+    if (_e != cudaSuccess)                                                                        \
+      return ::ldmae::set_error(LDMAE_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+// GEMM tile configuration: big token GEMMs use CTA pairs with 256x256 cluster tiles; LDMAE_GEMM_CG=1
+// switches the whole library to single-CTA 128x128 tiles (debug / A-B measurements).
+static int gemm_cg() {
+  static int cg = 0;
+  if (cg == 0) {
+    const char* e = getenv("LDMAE_GEMM_CG");
+    cg = (e && atoi(e) == 1) ? 1 : 2;
+  }
+  return cg;
+}
+template <class Epi>
+static int gemm_auto(const void* a, int lda, const void* w, int ldw, GemmShape g, const typename Epi::Params& ep,
+                     cudaStream_t st) {
+  ++g_launch_count;
+  if (gemm_cg() == 2 && g.M > 128) return launch_gemm<256, 2, Epi>(a, lda, w, ldw, g, ep, st);
+  return launch_gemm<128, 1, Epi>(a, lda, w, ldw, g, ep, st);
+}
+
+static int run_attention(const void* qkv, int ldq, void* out, int ldo, int B, int T, int H, int q_col, int k_col,
+                         int v_col, float scale, cudaStream_t st) {
+  CUtensorMap tm;
+  LDMAE_TRY(make_tmap_bf16(&tm, qkv, B * T, ldq, ldq, 128));
+  static bool attr = false;
+  if (!attr) {
+    LDMAE_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+    attr = true;
+  }
+  AttnParams p;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.T = T; p.H = H; p.ldo = ldo;
+  p.q_col = q_col; p.k_col = k_col; p.v_col = v_col;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid(cdiv(T, 256), H, B);
+  attn_fwd_kernel<<<grid, kAttnThreads, kAttnSmemBytes, st>>>(tm, p);
+  LDMAE_LAUNCH_CHECK();
+  return LDMAE_OK;
+}
+
+// ------------------------------------------------------------------------------------------- LightningDiT
+struct DitBlockW {
+  DevBuf<__nv_bfloat16> w_qkv, w_proj, w12, w3;
+  DevBuf<float> b_qkv, b_proj, b12, b3, qw, kw;
+};
+
+}  // namespace ldmae
+
+using namespace ldmae;
+
+struct ldmae_dit {
+  ldmae_dit_config c;
+  int D, T, G, Kp, H, Hp, nmod, Ntot, S /*norm slots*/, Nf, maxB;
+  // weights
+  DevBuf<float> pos, patch_w, patch_b, t_w0, t_b0, t_w2, t_b2, emb, rope_cos, rope_sin, norm_w, b_ada, b_f, w_f32;
+  DevBuf<__nv_bfloat16> w_ada, w_f;
+  std::vector<DitBlockW> blk;
+  DevBuf<int> slot_shift_off, slot_scale_off;
+  std::vector<std::string> loaded;
+  bool finalized = false;
+  // workspace (sized for maxB)
+  DevBuf<float> xres, ssq, cvec_c, th1, mods, gmul, cvec_qkv, cvec_12, cvec_f, vbuf, k1buf, xtmp;
+  DevBuf<__nv_bfloat16> abuf, qkv, obuf, hbuf, sc, shift_bf16;
+};
+
+static int dit_alloc_ws(ldmae_dit* h, int B) {
+  const size_t M = static_cast<size_t>(B) * h->T;
+  const int D = h->D;
+  LDMAE_TRY(h->xres.alloc(M * D));
+  LDMAE_TRY(h->abuf.alloc(M * D));
+  LDMAE_TRY(h->qkv.alloc(M * 3 * D));
+  LDMAE_TRY(h->obuf.alloc(M * D));
+  LDMAE_TRY(h->hbuf.alloc(M * h->Hp));
+  LDMAE_TRY(h->ssq.alloc(M));
+  LDMAE_TRY(h->cvec_c.alloc(static_cast<size_t>(B) * D));
+  LDMAE_TRY(h->th1.alloc(static_cast<size_t>(B) * D));
+  LDMAE_TRY(h->sc.alloc(static_cast<size_t>(B) * D));
+  LDMAE_TRY(h->mods.alloc(static_cast<size_t>(B) * h->Ntot));
+  LDMAE_TRY(h->shift_bf16.alloc(static_cast<size_t>(h->S) * B * D));
+  LDMAE_TRY(h->gmul.alloc(static_cast<size_t>(h->S) * B * D));
+  LDMAE_TRY(h->cvec_qkv.alloc(static_cast<size_t>(h->c.depth) * B * 3 * D));
+  LDMAE_TRY(h->cvec_12.alloc(static_cast<size_t>(h->c.depth) * B * 2 * h->Hp));
+  LDMAE_TRY(h->cvec_f.alloc(static_cast<size_t>(B) * h->Nf));
+  const size_t lat = static_cast<size_t>(B) * h->c.in_channels * h->c.input_size * h->c.input_size;
+  LDMAE_TRY(h->vbuf.alloc(lat));
+  LDMAE_TRY(h->k1buf.alloc(lat));
+  LDMAE_TRY(h->xtmp.alloc(lat));
+  h->maxB = B;
+  return LDMAE_OK;
+}
+
+extern "C" const char* ldmae_last_error(void) { return last_error().c_str(); }
+extern "C" int ldmae_version(void) { return 100; }
+extern "C" long long ldmae_launch_count(void) { return g_launch_count; }
+
+extern "C" int ldmae_device_info(int* sm_count, int* cc) {
+  int dev = 0, major = 0, minor = 0, sms = 0;
+  LDMAE_CUDA(cudaGetDevice(&dev));
+  LDMAE_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  LDMAE_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  LDMAE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (sm_count) *sm_count = sms;
+  if (cc) *cc = major * 10 + minor;
+  return LDMAE_OK;
+}
+
+static int require_sm100() {
+  int cc = 0;
+  LDMAE_TRY(ldmae_device_info(nullptr, &cc));
+  if (cc / 10 != 10) return set_error(LDMAE_ERR_INVALID, "ldmae_b200 needs an sm_100 (B200) device, found sm_%d", cc);
+  return LDMAE_OK;
+}
+
+extern "C" int ldmae_dit_create(const ldmae_dit_config* cfg, ldmae_dit** out) {
+  LDMAE_REQUIRE(cfg && out, "null argument");
+  LDMAE_TRY(require_sm100());
+  const ldmae_dit_config& c = *cfg;
+  LDMAE_REQUIRE(c.use_rmsnorm == 1, "LightningDiT without use_rmsnorm (LayerNorm variant) is not built yet");
+  LDMAE_REQUIRE(c.use_swiglu == 1, "LightningDiT without use_swiglu (GELU Mlp variant) is not built yet");
+  LDMAE_REQUIRE(c.hidden_size % c.num_heads == 0 && c.hidden_size / c.num_heads == 64,
+                "attention kernel is built for head_dim 64 (got %d); XL (head_dim 72) is a next-round item",
+                c.num_heads ? c.hidden_size / c.num_heads : 0);
+  LDMAE_REQUIRE(c.input_size % c.patch_size == 0, "input_size %% patch_size != 0");
+  LDMAE_REQUIRE((c.in_channels * c.patch_size * c.patch_size) % 4 == 0, "C*p*p must be a multiple of 4");
+  ldmae_dit* h = new ldmae_dit();
+  h->c = c;
+  h->D = c.hidden_size;
+  h->G = c.input_size / c.patch_size;
+  h->T = h->G * h->G;
+  h->Kp = c.in_channels * c.patch_size * c.patch_size;
+  h->H = c.mlp_hidden;
+  h->Hp = (c.mlp_hidden + 31) / 32 * 32;
+  h->nmod = c.wo_shift ? 4 : 6;
+  h->Ntot = (c.depth * h->nmod + 2) * h->D;
+  h->S = 2 * c.depth + 1;
+  h->Nf = c.patch_size * c.patch_size * c.in_channels * (c.learn_sigma ? 2 : 1);
+  const int D = h->D;
+  h->blk.resize(c.depth);
+  int r = LDMAE_OK;
+  auto A = [&](int rc) { if (r == LDMAE_OK) r = rc; };
+  A(h->pos.alloc(static_cast<size_t>(h->T) * D));
+  A(h->patch_w.alloc(static_cast<size_t>(D) * h->Kp));
+  A(h->patch_b.alloc(D));
+  A(h->t_w0.alloc(static_cast<size_t>(D) * 256)); A(h->t_b0.alloc(D));
+  A(h->t_w2.alloc(static_cast<size_t>(D) * D)); A(h->t_b2.alloc(D));
+  A(h->emb.alloc(static_cast<size_t>(c.num_embeddings) * D));
+  A(h->rope_cos.alloc(static_cast<size_t>(h->T) * 64)); A(h->rope_sin.alloc(static_cast<size_t>(h->T) * 64));
+  A(h->norm_w.alloc(static_cast<size_t>(h->S) * D));
+  A(h->w_ada.alloc(static_cast<size_t>(h->Ntot) * D)); A(h->b_ada.alloc(h->Ntot));
+  A(h->w_f.alloc(static_cast<size_t>(h->Nf) * D)); A(h->b_f.alloc(h->Nf)); A(h->w_f32.alloc(static_cast<size_t>(h->Nf) * D));
+  for (auto& b : h->blk) {
+    A(b.w_qkv.alloc(static_cast<size_t>(3 * D) * D)); A(b.b_qkv.alloc(3 * D));
+    A(b.w_proj.alloc(static_cast<size_t>(D) * D)); A(b.b_proj.alloc(D));
+    A(b.w12.alloc(static_cast<size_t>(2 * h->Hp) * D)); A(b.b12.alloc(2 * h->Hp));
+    A(b.w3.alloc(static_cast<size_t>(D) * h->Hp)); A(b.b3.alloc(D));
+    A(b.qw.alloc(64)); A(b.kw.alloc(64));
+  }
+  // adaLN slot -> column offsets inside a mods row
+  std::vector<int> so(h->S), sco(h->S);
+  for (int i = 0; i < c.depth; ++i) {
+    const int base = i * h->nmod * D;
+    if (c.wo_shift) {
+      so[2 * i] = -1; sco[2 * i] = base;                // scale_msa, gate_msa, scale_mlp, gate_mlp
+      so[2 * i + 1] = -1; sco[2 * i + 1] = base + 2 * D;
+    } else {
+      so[2 * i] = base; sco[2 * i] = base + D;          // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
+      so[2 * i + 1] = base + 3 * D; sco[2 * i + 1] = base + 4 * D;
+    }
+  }
+  so[2 * c.depth] = c.depth * h->nmod * D;
+  sco[2 * c.depth] = c.depth * h->nmod * D + D;
+  A(h->slot_shift_off.alloc(h->S)); A(h->slot_scale_off.alloc(h->S));
+  if (r == LDMAE_OK && cudaMemcpy(h->slot_shift_off.p, so.data(), h->S * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess)
+    r = set_error(LDMAE_ERR_CUDA, "memcpy slot offsets");
+  if (r == LDMAE_OK && cudaMemcpy(h->slot_scale_off.p, sco.data(), h->S * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess)
+    r = set_error(LDMAE_ERR_CUDA, "memcpy slot offsets");
+  if (r == LDMAE_OK) r = dit_alloc_ws(h, std::max(1, c.max_batch));
+  if (r != LDMAE_OK) { delete h; return r; }
+  *out = h;
+  return LDMAE_OK;
+}
+
+extern "C" void ldmae_dit_destroy(ldmae_dit* h) { delete h; }
+
+static int copy_f32(float* dst, const float* src, int64_t n, int64_t expect, const char* name, cudaStream_t st) {
+  LDMAE_REQUIRE(n == expect, "%s: expected %lld elements, got %lld", name, (long long)expect, (long long)n);
+  LDMAE_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return LDMAE_OK;
+}
+static int pack_bf16(__nv_bfloat16* dst, const float* src, int rows, int Ks, int Kd, int64_t n, const char* name,
+                     cudaStream_t st, int mode = 0, int H = 0, int src_rows = -1) {
+  const int64_t expect = static_cast<int64_t>(src_rows < 0 ? rows : src_rows) * Ks;
+  LDMAE_REQUIRE(n == expect, "%s: expected %lld elements, got %lld", name, (long long)expect, (long long)n);
+  pack_rows_bf16_kernel<<<rows, 256, 0, st>>>(dst, src, rows, Ks, Kd, mode, H);
+  LDMAE_LAUNCH_CHECK();
+  return LDMAE_OK;
+}
+
+extern "C" int ldmae_dit_load_tensor(ldmae_dit* h, const char* name, const float* data, int64_t numel, void* stream) {
+  LDMAE_REQUIRE(h && name && data, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int D = h->D;
+  const std::string k(name);
+  int rc = LDMAE_OK;
+  int bi = -1;
+  std::string sub;
+  if (k.rfind("blocks.", 0) == 0) {
+    const size_t dot = k.find('.', 7);
+    LDMAE_REQUIRE(dot != std::string::npos, "bad key %s", name);
+    bi = atoi(k.substr(7, dot - 7).c_str());
+    sub = k.substr(dot + 1);
+    LDMAE_REQUIRE(bi >= 0 && bi < h->c.depth, "block index out of range in %s", name);
+  }
+  if (k == "pos_embed") rc = copy_f32(h->pos.p, data, numel, (int64_t)h->T * D, name, st);
+  else if (k == "x_embedder.proj.weight") rc = copy_f32(h->patch_w.p, data, numel, (int64_t)D * h->Kp, name, st);
+  else if (k == "x_embedder.proj.bias") rc = copy_f32(h->patch_b.p, data, numel, D, name, st);
+  else if (k == "t_embedder.mlp.0.weight") rc = copy_f32(h->t_w0.p, data, numel, (int64_t)D * 256, name, st);
+  else if (k == "t_embedder.mlp.0.bias") rc = copy_f32(h->t_b0.p, data, numel, D, name, st);
+  else if (k == "t_embedder.mlp.2.weight") rc = copy_f32(h->t_w2.p, data, numel, (int64_t)D * D, name, st);
+  else if (k == "t_embedder.mlp.2.bias") rc = copy_f32(h->t_b2.p, data, numel, D, name, st);
+  else if (k == "y_embedder.embedding_table.weight") rc = copy_f32(h->emb.p, data, numel, (int64_t)h->c.num_embeddings * D, name, st);
+  else if (k == "feat_rope.freqs_cos") rc = copy_f32(h->rope_cos.p, data, numel, (int64_t)h->T * 64, name, st);
+  else if (k == "feat_rope.freqs_sin") rc = copy_f32(h->rope_sin.p, data, numel, (int64_t)h->T * 64, name, st);
+  else if (k == "final_layer.norm_final.weight") rc = copy_f32(h->norm_w.p + (size_t)(2 * h->c.depth) * D, data, numel, D, name, st);
+  else if (k == "final_layer.linear.weight") {
+    rc = pack_bf16(h->w_f.p, data, h->Nf, D, D, numel, name, st);
+    if (rc == LDMAE_OK) rc = copy_f32(h->w_f32.p, data, numel, (int64_t)h->Nf * D, name, st);
+  }
+  else if (k == "final_layer.linear.bias") rc = copy_f32(h->b_f.p, data, numel, h->Nf, name, st);
+  else if (k == "final_layer.adaLN_modulation.1.weight")
+    rc = pack_bf16(h->w_ada.p + (size_t)h->c.depth * h->nmod * D * D, data, 2 * D, D, D, numel, name, st);
+  else if (k == "final_layer.adaLN_modulation.1.bias")
+    rc = copy_f32(h->b_ada.p + (size_t)h->c.depth * h->nmod * D, data, numel, 2 * D, name, st);
+  else if (bi >= 0) {
+    DitBlockW& b = h->blk[bi];
+    if (sub == "norm1.weight") rc = copy_f32(h->norm_w.p + (size_t)(2 * bi) * D, data, numel, D, name, st);
+    else if (sub == "norm2.weight") rc = copy_f32(h->norm_w.p + (size_t)(2 * bi + 1) * D, data, numel, D, name, st);
+    else if (sub == "attn.qkv.weight") rc = pack_bf16(b.w_qkv.p, data, 3 * D, D, D, numel, name, st);
+    else if (sub == "attn.qkv.bias") rc = copy_f32(b.b_qkv.p, data, numel, 3 * D, name, st);
+    else if (sub == "attn.q_norm.weight") rc = copy_f32(b.qw.p, data, numel, 64, name, st);
+    else if (sub == "attn.k_norm.weight") rc = copy_f32(b.kw.p, data, numel, 64, name, st);
+    else if (sub == "attn.proj.weight") rc = pack_bf16(b.w_proj.p, data, D, D, D, numel, name, st);
+    else if (sub == "attn.proj.bias") rc = copy_f32(b.b_proj.p, data, numel, D, name, st);
+    else if (sub == "mlp.w12.weight") rc = pack_bf16(b.w12.p, data, 2 * h->Hp, D, D, numel, name, st, 1, h->H, 2 * h->H);
+    else if (sub == "mlp.w12.bias") {
+      LDMAE_REQUIRE(numel == 2 * h->H, "%s: expected %d elements", name, 2 * h->H);
+      pack_vec_f32_kernel<<<cdiv(2 * h->Hp, 256), 256, 0, st>>>(b.b12.p, data, 2 * h->Hp, 1, h->H);
+      LDMAE_LAUNCH_CHECK();
+    } else if (sub == "mlp.w3.weight") rc = pack_bf16(b.w3.p, data, D, h->H, h->Hp, numel, name, st);
+    else if (sub == "mlp.w3.bias") rc = copy_f32(b.b3.p, data, numel, D, name, st);
+    else if (sub == "adaLN_modulation.1.weight")
+      rc = pack_bf16(h->w_ada.p + (size_t)bi * h->nmod * D * D, data, h->nmod * D, D, D, numel, name, st);
+    else if (sub == "adaLN_modulation.1.bias") rc = copy_f32(h->b_ada.p + (size_t)bi * h->nmod * D, data, numel, h->nmod * D, name, st);
+    else return set_error(LDMAE_ERR_INVALID, "unknown LightningDiT state_dict key %s", name);
+  } else {
+    return set_error(LDMAE_ERR_INVALID, "unknown LightningDiT state_dict key %s", name);
+  }
+  if (rc == LDMAE_OK && std::find(h->loaded.begin(), h->loaded.end(), k) == h->loaded.end()) h->loaded.push_back(k);
+  return rc;
+}
+
+extern "C" int ldmae_dit_finalize(ldmae_dit* h, void* stream) {
+  LDMAE_REQUIRE(h, "null handle");
+  (void)stream;
+  int expect = 8 + 5 + 12 * h->c.depth;   // without qk-norm / rope keys
+  if (h->c.use_qknorm) expect += 2 * h->c.depth;
+  if (h->c.use_rope) expect += 2;
+  if ((int)h->loaded.size() != expect)
+    return set_error(LDMAE_ERR_STATE, "LightningDiT weights incomplete: %d of %d tensors loaded", (int)h->loaded.size(), expect);
+  h->finalized = true;
+  return LDMAE_OK;
+}
+
+// One forward pass of cat-batch B (see header).  out: [B, Cstore, S, S].
+static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float t_scalar, const int64_t* y, float* out,
+                            int B, int src_mod, cudaStream_t st) {
+  LDMAE_REQUIRE(h && h->finalized, "LightningDiT handle not finalized (load all weights, then ldmae_dit_finalize)");
+  LDMAE_REQUIRE(B >= 1 && src_mod >= 1, "bad batch");
+  if (B > h->maxB) {
+    LDMAE_CUDA(cudaStreamSynchronize(st));
+    LDMAE_TRY(dit_alloc_ws(h, B));
+  }
+  const ldmae_dit_config& c = h->c;
+  const int D = h->D, T = h->T, depth = c.depth;
+  const int M = B * T;
+  const float eps = 1e-6f;
+  // 1. conditioning c = t_emb + y_emb ; sc = bf16(silu(c))
+  {
+    dim3 grid(cdiv(D, 64), cdiv(B, 16));
+    const size_t sm0 = 16 * 256 * sizeof(float), sm2 = 16 * static_cast<size_t>(D) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+      LDMAE_CUDA(cudaFuncSetAttribute(small_linear_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      LDMAE_CUDA(cudaFuncSetAttribute(small_linear_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr = true;
+    }
+    small_linear_kernel<1><<<grid, 256, sm0, st>>>(h->th1.p, nullptr, t, t_scalar, h->t_w0.p, h->t_b0.p, nullptr, nullptr, B, 256, D, 1, 256);
+    LDMAE_LAUNCH_CHECK();
+    small_linear_kernel<0><<<grid, 256, sm2, st>>>(h->cvec_c.p, h->th1.p, nullptr, 0.f, h->t_w2.p, h->t_b2.p, h->emb.p,
+                                                   reinterpret_cast<const long long*>(y), B, D, D, 0, D);
+    LDMAE_LAUNCH_CHECK();
+    silu_to_bf16_kernel<<<cdiv(static_cast<size_t>(B) * D, 256), 256, 0, st>>>(h->sc.p, h->cvec_c.p, static_cast<size_t>(B) * D);
+    LDMAE_LAUNCH_CHECK();
+  }
+  // 2. all adaLN modulations at once: mods[B, Ntot] = sc . W_ada^T + b_ada
+  {
+    EpiStore<float, 0>::Params ep{h->mods.p, h->b_ada.p, h->Ntot};
+    LDMAE_TRY((gemm_auto<EpiStore<float, 0>>(h->sc.p, D, h->w_ada.p, D, GemmShape{B, h->Ntot, D}, ep, st)));
+    const size_t tot = static_cast<size_t>(h->S) * B * D;
+    adaln_prep_kernel<<<cdiv(tot, 256), 256, 0, st>>>(h->shift_bf16.p, h->gmul.p, h->mods.p, h->norm_w.p,
+                                                      h->slot_shift_off.p, h->slot_scale_off.p, B, D, h->Ntot, h->S);
+    LDMAE_LAUNCH_CHECK();
+  }
+  // 3. per-sample vectors  shift_b . W^T + bias  for every modulated Linear
+  for (int i = 0; i < depth; ++i) {
+    DitBlockW& b = h->blk[i];
+    float* cq = h->cvec_qkv.p + static_cast<size_t>(i) * B * 3 * D;
+    float* c12 = h->cvec_12.p + static_cast<size_t>(i) * B * 2 * h->Hp;
+    EpiStore<float, 0>::Params e1{cq, b.b_qkv.p, 3 * D};
+    LDMAE_TRY((gemm_auto<EpiStore<float, 0>>(h->shift_bf16.p + static_cast<size_t>(2 * i) * B * D, D, b.w_qkv.p, D,
+                                              GemmShape{B, 3 * D, D}, e1, st)));
+    EpiStore<float, 0>::Params e2{c12, b.b12.p, 2 * h->Hp};
+    LDMAE_TRY((gemm_auto<EpiStore<float, 0>>(h->shift_bf16.p + static_cast<size_t>(2 * i + 1) * B * D, D, b.w12.p, D,
+                                              GemmShape{B, 2 * h->Hp, D}, e2, st)));
+  }
+  {
+    // final linear (N = p*p*C_out, e.g. 16): fp32 on CUDA cores straight from the shift columns of mods
+    dim3 grid(cdiv(h->Nf, 64), cdiv(B, 16));
+    const size_t sm2 = 16 * static_cast<size_t>(D) * sizeof(float);
+    small_linear_kernel<0><<<grid, 256, sm2, st>>>(h->cvec_f.p, h->mods.p + static_cast<size_t>(depth) * h->nmod * D, nullptr, 0.f,
+                                                   h->w_f32.p, h->b_f.p, nullptr, nullptr, B, D, h->Nf, 0, h->Ntot);
+    LDMAE_LAUNCH_CHECK();
+  }
+  // 4. patch embed + pos embed -> residual stream, first operand, first row statistics
+  {
+    dim3 grid(cdiv(T, 32), B);
+    const size_t sm = (32 * static_cast<size_t>(h->Kp) + 256) * sizeof(float);
+    patch_embed_kernel<<<grid, 256, sm, st>>>(h->xres.p, h->abuf.p, h->ssq.p, x, h->patch_w.p, h->patch_b.p, h->pos.p,
+                                              h->gmul.p, c.in_channels, c.input_size, c.patch_size, D, src_mod);
+    LDMAE_LAUNCH_CHECK();
+  }
+  // 5. blocks
+  for (int i = 0; i < depth; ++i) {
+    DitBlockW& b = h->blk[i];
+    const float* mods_i = h->mods.p + static_cast<size_t>(i) * h->nmod * D;
+    const float* gate_msa = mods_i + (c.wo_shift ? 1 : 2) * D;
+    const float* gate_mlp = mods_i + (c.wo_shift ? 3 : 5) * D;
+    EpiQKV::Params eq;
+    eq.out = h->qkv.p; eq.ssq = h->ssq.p; eq.cvec = h->cvec_qkv.p + static_cast<size_t>(i) * B * 3 * D;
+    eq.qw = c.use_qknorm ? b.qw.p : nullptr; eq.kw = c.use_qknorm ? b.kw.p : nullptr;
+    eq.rope_cos = c.use_rope ? h->rope_cos.p : nullptr; eq.rope_sin = c.use_rope ? h->rope_sin.p : nullptr;
+    eq.D = D; eq.rows_per_sample = T; eq.inv_D = 1.f / D; eq.eps_row = eps; eq.eps_head = eps;
+    LDMAE_TRY((gemm_auto<EpiQKV>(h->abuf.p, D, b.w_qkv.p, D, GemmShape{M, 3 * D, D}, eq, st)));
+    LDMAE_TRY(run_attention(h->qkv.p, 3 * D, h->obuf.p, D, B, T, c.num_heads, 0, D, 2 * D, 0.125f, st));
+    LDMAE_CUDA(cudaMemsetAsync(h->ssq.p, 0, static_cast<size_t>(M) * sizeof(float), st));
+    EpiResidual::Params ep;
+    ep.x = h->xres.p; ep.bias = b.b_proj.p; ep.gate = gate_msa; ep.gnext = h->gmul.p + static_cast<size_t>(2 * i + 1) * B * D;
+    ep.anext = h->abuf.p; ep.ssq = h->ssq.p; ep.ldx = D; ep.gate_ld = h->Ntot; ep.gnext_ld = D; ep.rows_per_sample = T;
+    LDMAE_TRY((gemm_auto<EpiResidual>(h->obuf.p, D, b.w_proj.p, D, GemmShape{M, D, D}, ep, st)));
+    EpiSwiGLU::Params es;
+    es.out = h->hbuf.p; es.ssq = h->ssq.p; es.cvec = h->cvec_12.p + static_cast<size_t>(i) * B * 2 * h->Hp;
+    es.H = h->Hp; es.rows_per_sample = T; es.inv_D = 1.f / D; es.eps_row = eps;
+    LDMAE_TRY((gemm_auto<EpiSwiGLU>(h->abuf.p, D, b.w12.p, D, GemmShape{M, 2 * h->Hp, D}, es, st)));
+    // NOTE: the w12 GEMM reads ssq; the w3 epilogue accumulates the next statistics into it, so it
+    // is cleared in between (stream order makes this safe).
+    LDMAE_CUDA(cudaMemsetAsync(h->ssq.p, 0, static_cast<size_t>(M) * sizeof(float), st));
+    EpiResidual::Params e3;
+    e3.x = h->xres.p; e3.bias = b.b3.p; e3.gate = gate_mlp; e3.gnext = h->gmul.p + static_cast<size_t>(2 * i + 2) * B * D;
+    e3.anext = h->abuf.p; e3.ssq = h->ssq.p; e3.ldx = D; e3.gate_ld = h->Ntot; e3.gnext_ld = D; e3.rows_per_sample = T;
+    LDMAE_TRY((gemm_auto<EpiResidual>(h->hbuf.p, h->Hp, b.w3.p, h->Hp, GemmShape{M, D, h->Hp}, e3, st)));
+  }
+  // 6. final layer + unpatchify
+  {
+    EpiFinal::Params ef;
+    ef.out = out; ef.ssq = h->ssq.p; ef.cvec = h->cvec_f.p; ef.grid = h->G; ef.patch = c.patch_size;
+    ef.cout = c.in_channels * (c.learn_sigma ? 2 : 1); ef.cstore = c.in_channels; ef.rows_per_sample = T;
+    ef.inv_D = 1.f / D; ef.eps_row = eps;
+    LDMAE_TRY((launch_gemm<16, 1, EpiFinal>(h->abuf.p, D, h->w_f.p, D, GemmShape{M, h->Nf, D}, ef, st)));
+    ++g_launch_count;
+  }
+  return LDMAE_OK;
+}
+
+extern "C" int ldmae_dit_forward(ldmae_dit* h, const float* x, const float* t, float t_scalar, const int64_t* y,
+                                 float* out, int32_t B, int32_t src_mod, void* stream) {
+  LDMAE_REQUIRE(x && y && out, "null tensor");
+  return dit_forward_impl(h, x, t, t_scalar, y, out, B, src_mod, static_cast<cudaStream_t>(stream));
+}
+
+static int launch_update(float* xout, const float* xin, const float* v, const float* kprev, float* gout, int n_half,
+                         int C, int HW, float cfg_scale, int use_guidance, float a, float bcoef, size_t total,
+                         cudaStream_t st) {
+  cfg_ode_update_kernel<<<cdiv(total, 256), 256, 0, st>>>(xout, xin, v, kprev, gout, n_half, C, HW, 3, cfg_scale,
+                                                          use_guidance, a, bcoef, total);
+  LDMAE_LAUNCH_CHECK();
+  return LDMAE_OK;
+}
+
+extern "C" int ldmae_dit_forward_with_cfg(ldmae_dit* h, const float* x, const float* t, float t_scalar,
+                                          const int64_t* y, float* out, int32_t n, float cfg_scale,
+                                          int32_t use_guidance, void* stream) {
+  LDMAE_REQUIRE(h && x && y && out && n >= 1, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int C = h->c.in_channels, HW = h->c.input_size * h->c.input_size;
+  const size_t total = static_cast<size_t>(2 * n) * C * HW;
+  if (2 * n > h->maxB) { LDMAE_CUDA(cudaStreamSynchronize(st)); LDMAE_TRY(dit_alloc_ws(h, 2 * n)); }
+  LDMAE_TRY(dit_forward_impl(h, x, t, t_scalar, y, h->vbuf.p, 2 * n, n, st));
+  return launch_update(nullptr, nullptr, h->vbuf.p, nullptr, out, n, C, HW, cfg_scale, use_guidance, 0.f, 0.f, total, st);
+}
+
+extern "C" int ldmae_sample_ode(ldmae_dit* h, float* x, const int64_t* y, int32_t n, int32_t use_cfg, float cfg_scale,
+                                float cfg_interval_start, const float* tgrid, int32_t npts, int32_t method, float* traj,
+                                void* stream) {
+  LDMAE_REQUIRE(h && x && y && tgrid && n >= 1 && npts >= 2, "bad argument");
+  LDMAE_REQUIRE(method == 0 || method == 1, "method must be 0 (euler) or 1 (heun2)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int C = h->c.in_channels, HW = h->c.input_size * h->c.input_size;
+  const int Btot = use_cfg ? 2 * n : n;
+  const int src_mod = n;
+  const int n_half = use_cfg ? n : 0;
+  const size_t total = static_cast<size_t>(Btot) * C * HW;
+  if (Btot > h->maxB) { LDMAE_CUDA(cudaStreamSynchronize(st)); LDMAE_TRY(dit_alloc_ws(h, Btot)); }
+  if (traj) LDMAE_CUDA(cudaMemcpyAsync(traj, x, total * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  for (int k = 0; k + 1 < npts; ++k) {
+    const float t0 = tgrid[k], t1 = tgrid[k + 1];
+    const float dt = t1 - t0;
+    auto guided = [&](float tt) { return (use_cfg && !(cfg_interval_start >= 0.f && tt < cfg_interval_start)) ? 1 : 0; };
+    LDMAE_TRY(dit_forward_impl(h, x, nullptr, t0, y, h->vbuf.p, Btot, src_mod, st));
+    if (method == 0) {
+      LDMAE_TRY(launch_update(x, x, h->vbuf.p, nullptr, nullptr, n_half, C, HW, cfg_scale, guided(t0), dt, 0.f, total, st));
+    } else {
+      // k1 = f(t0, x); xtmp = x + dt*k1; k2 = f(t0+dt, xtmp); x += dt*(k1/2 + k2/2)
+      LDMAE_TRY(launch_update(h->xtmp.p, x, h->vbuf.p, nullptr, h->k1buf.p, n_half, C, HW, cfg_scale, guided(t0), dt, 0.f, total, st));
+      const float tb = t0 + dt;
+      LDMAE_TRY(dit_forward_impl(h, h->xtmp.p, nullptr, tb, y, h->vbuf.p, Btot, src_mod, st));
+      LDMAE_TRY(launch_update(x, x, h->vbuf.p, h->k1buf.p, nullptr, n_half, C, HW, cfg_scale, guided(tb), 0.5f * dt, 0.5f * dt, total, st));
+    }
+    if (traj)
+      LDMAE_CUDA(cudaMemcpyAsync(traj + static_cast<size_t>(k + 1) * total, x, total * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  return LDMAE_OK;
+}
+
+// ------------------------------------------------------------------------------------------- VMAE decoder
+struct VmaeBlockW {
+  DevBuf<__nv_bfloat16> w_qkv, w_proj, w_fc1, w_fc2;
+  DevBuf<float> b_qkv, b_proj, b_fc1, b_fc2, n1w, n1b, n2w, n2b;
+};
+struct ldmae_vmae {
+  ldmae_vmae_config c;
+  int D, L, G, Hm, HP /*padded heads width nh*64*/, PP, maxB;
+  DevBuf<__nv_bfloat16> w_from, w_embed, w_pred;
+  DevBuf<float> b_from, b_embed, pos, nfw, nfb, b_pred, conv_w, conv_b;
+  std::vector<VmaeBlockW> blk;
+  std::vector<std::string> loaded;
+  bool finalized = false;
+  DevBuf<float> x, pred;
+  DevBuf<__nv_bfloat16> tok, t1, a, qkv, o, hid;
+};
+
+static int vmae_alloc_ws(ldmae_vmae* h, int B) {
+  const size_t M = static_cast<size_t>(B) * h->L;
+  LDMAE_TRY(h->x.alloc(M * h->D));
+  LDMAE_TRY(h->pred.alloc(M * h->PP));
+  LDMAE_TRY(h->tok.alloc(M * 64));
+  LDMAE_TRY(h->t1.alloc(M * h->c.embed_dim));
+  LDMAE_TRY(h->a.alloc(M * h->D));
+  LDMAE_TRY(h->qkv.alloc(M * 3 * h->HP));
+  LDMAE_TRY(h->o.alloc(M * h->HP));
+  LDMAE_TRY(h->hid.alloc(M * h->Hm));
+  h->maxB = B;
+  return LDMAE_OK;
+}
+
+extern "C" int ldmae_vmae_create(const ldmae_vmae_config* cfg, ldmae_vmae** out) {
+  LDMAE_REQUIRE(cfg && out, "null argument");
+  LDMAE_TRY(require_sm100());
+  const ldmae_vmae_config& c = *cfg;
+  LDMAE_REQUIRE(c.decoder_embed_dim % c.decoder_num_heads == 0, "decoder dim %% heads");
+  const int hd = c.decoder_embed_dim / c.decoder_num_heads;
+  LDMAE_REQUIRE(hd <= 64, "VMAE decoder head_dim %d > 64 not supported", hd);
+  LDMAE_REQUIRE(c.latent_dim <= 64, "latent_dim > 64 not supported");
+  LDMAE_REQUIRE(c.decoder_embed_dim % 8 == 0 && c.embed_dim % 8 == 0 && c.mlp_hidden % 8 == 0, "dims must be multiples of 8");
+  ldmae_vmae* h = new ldmae_vmae();
+  h->c = c;
+  h->D = c.decoder_embed_dim;
+  h->G = c.img_size / c.patch_size;
+  h->L = h->G * h->G;
+  h->Hm = c.mlp_hidden;
+  h->HP = c.decoder_num_heads * 64;
+  h->PP = c.patch_size * c.patch_size * 3;
+  const int D = h->D;
+  int r = LDMAE_OK;
+  auto A = [&](int rc) { if (r == LDMAE_OK) r = rc; };
+  A(h->w_from.alloc(static_cast<size_t>(c.embed_dim) * 64)); A(h->b_from.alloc(c.embed_dim));
+  A(h->w_embed.alloc(static_cast<size_t>(D) * c.embed_dim)); A(h->b_embed.alloc(D));
+  A(h->pos.alloc(static_cast<size_t>(h->L) * D));
+  A(h->nfw.alloc(D)); A(h->nfb.alloc(D));
+  A(h->w_pred.alloc(static_cast<size_t>(h->PP) * D)); A(h->b_pred.alloc(h->PP));
+  A(h->conv_w.alloc(81)); A(h->conv_b.alloc(3));
+  h->blk.resize(c.decoder_depth);
+  for (auto& b : h->blk) {
+    A(b.w_qkv.alloc(static_cast<size_t>(3 * h->HP) * D)); A(b.b_qkv.alloc(3 * h->HP, true));
+    A(b.w_proj.alloc(static_cast<size_t>(D) * h->HP)); A(b.b_proj.alloc(D));
+    A(b.w_fc1.alloc(static_cast<size_t>(h->Hm) * D)); A(b.b_fc1.alloc(h->Hm));
+    A(b.w_fc2.alloc(static_cast<size_t>(D) * h->Hm)); A(b.b_fc2.alloc(D));
+    A(b.n1w.alloc(D)); A(b.n1b.alloc(D)); A(b.n2w.alloc(D)); A(b.n2b.alloc(D));
+  }
+  if (r == LDMAE_OK) r = vmae_alloc_ws(h, std::max(1, c.max_batch));
+  if (r != LDMAE_OK) { delete h; return r; }
+  *out = h;
+  return LDMAE_OK;
+}
+extern "C" void ldmae_vmae_destroy(ldmae_vmae* h) { delete h; }
+
+extern "C" int ldmae_vmae_load_tensor(ldmae_vmae* h, const char* name, const float* data, int64_t numel, void* stream) {
+  LDMAE_REQUIRE(h && name && data, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const std::string k(name);
+  const int D = h->D, E = h->c.embed_dim, nh = h->c.decoder_num_heads, hd = D / nh;
+  int rc = LDMAE_OK;
+  int bi = -1;
+  std::string sub;
+  if (k.rfind("decoder_blocks.", 0) == 0) {
+    const size_t dot = k.find('.', 15);
+    LDMAE_REQUIRE(dot != std::string::npos, "bad key %s", name);
+    bi = atoi(k.substr(15, dot - 15).c_str());
+    sub = k.substr(dot + 1);
+    LDMAE_REQUIRE(bi >= 0 && bi < h->c.decoder_depth, "block index out of range in %s", name);
+  }
+  if (k == "from_latent.weight") rc = pack_bf16(h->w_from.p, data, E, h->c.latent_dim, 64, numel, name, st);
+  else if (k == "from_latent.bias") rc = copy_f32(h->b_from.p, data, numel, E, name, st);
+  else if (k == "decoder_embed.weight") rc = pack_bf16(h->w_embed.p, data, D, E, E, numel, name, st);
+  else if (k == "decoder_embed.bias") rc = copy_f32(h->b_embed.p, data, numel, D, name, st);
+  else if (k == "decoder_pos_embed") rc = copy_f32(h->pos.p, data, numel, (int64_t)h->L * D, name, st);
+  else if (k == "decoder_norm.weight") rc = copy_f32(h->nfw.p, data, numel, D, name, st);
+  else if (k == "decoder_norm.bias") rc = copy_f32(h->nfb.p, data, numel, D, name, st);
+  else if (k == "decoder_pred.linear_pred.weight") rc = pack_bf16(h->w_pred.p, data, h->PP, D, D, numel, name, st);
+  else if (k == "decoder_pred.linear_pred.bias") rc = copy_f32(h->b_pred.p, data, numel, h->PP, name, st);
+  else if (k == "decoder_pred.conv_smoother.weight") rc = copy_f32(h->conv_w.p, data, numel, 81, name, st);
+  else if (k == "decoder_pred.conv_smoother.bias") rc = copy_f32(h->conv_b.p, data, numel, 3, name, st);
+  else if (bi >= 0) {
+    VmaeBlockW& b = h->blk[bi];
+    if (sub == "norm1.weight") rc = copy_f32(b.n1w.p, data, numel, D, name, st);
+    else if (sub == "norm1.bias") rc = copy_f32(b.n1b.p, data, numel, D, name, st);
+    else if (sub == "norm2.weight") rc = copy_f32(b.n2w.p, data, numel, D, name, st);
+    else if (sub == "norm2.bias") rc = copy_f32(b.n2b.p, data, numel, D, name, st);
+    else if (sub == "attn.qkv.weight") {
+      LDMAE_REQUIRE(numel == (int64_t)3 * D * D, "%s: bad size", name);
+      pad_heads_rows_kernel<<<3 * h->HP, 128, 0, st>>>(b.w_qkv.p, nullptr, data, nullptr, nh, hd, D);
+      LDMAE_LAUNCH_CHECK();
+    } else if (sub == "attn.qkv.bias") {
+      LDMAE_REQUIRE(numel == 3 * D, "%s: bad size", name);
+      // scatter bias into the padded layout with a strided 2-D copy: [3*nh, hd] -> [3*nh, 64]
+      LDMAE_CUDA(cudaMemsetAsync(b.b_qkv.p, 0, 3 * h->HP * sizeof(float), st));
+      LDMAE_CUDA(cudaMemcpy2DAsync(b.b_qkv.p, 64 * sizeof(float), data, hd * sizeof(float), hd * sizeof(float), 3 * nh,
+                                   cudaMemcpyDeviceToDevice, st));
+    } else if (sub == "attn.proj.weight") {
+      LDMAE_REQUIRE(numel == (int64_t)D * D, "%s: bad size", name);
+      pad_heads_cols_kernel<<<D, 256, 0, st>>>(b.w_proj.p, data, nh, hd);
+      LDMAE_LAUNCH_CHECK();
+    } else if (sub == "attn.proj.bias") rc = copy_f32(b.b_proj.p, data, numel, D, name, st);
+    else if (sub == "mlp.fc1.weight") rc = pack_bf16(b.w_fc1.p, data, h->Hm, D, D, numel, name, st);
+    else if (sub == "mlp.fc1.bias") rc = copy_f32(b.b_fc1.p, data, numel, h->Hm, name, st);
+    else if (sub == "mlp.fc2.weight") rc = pack_bf16(b.w_fc2.p, data, D, h->Hm, h->Hm, numel, name, st);
+    else if (sub == "mlp.fc2.bias") rc = copy_f32(b.b_fc2.p, data, numel, D, name, st);
+    else return set_error(LDMAE_ERR_INVALID, "unknown VMAE decoder key %s", name);
+  } else {
+    return set_error(LDMAE_ERR_INVALID, "unknown VMAE decoder key %s", name);
+  }
+  if (rc == LDMAE_OK && std::find(h->loaded.begin(), h->loaded.end(), k) == h->loaded.end()) h->loaded.push_back(k);
+  return rc;
+}
+
+extern "C" int ldmae_vmae_finalize(ldmae_vmae* h, void* stream) {
+  LDMAE_REQUIRE(h, "null handle");
+  (void)stream;
+  const int expect = 11 + 12 * h->c.decoder_depth;
+  if ((int)h->loaded.size() != expect)
+    return set_error(LDMAE_ERR_STATE, "VMAE decoder weights incomplete: %d of %d tensors loaded", (int)h->loaded.size(), expect);
+  h->finalized = true;
+  return LDMAE_OK;
+}
+
+extern "C" int ldmae_vmae_decode(ldmae_vmae* h, const float* z, const float* mean, const float* stdv, float multiplier,
+                                 float* img_f32, uint8_t* img_u8, int32_t B, void* stream) {
+  LDMAE_REQUIRE(h && h->finalized, "VMAE handle not finalized");
+  LDMAE_REQUIRE(z && (img_f32 || img_u8) && B >= 1, "bad argument");
+  LDMAE_REQUIRE((mean == nullptr) == (stdv == nullptr), "mean/std must be given together");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B > h->maxB) { LDMAE_CUDA(cudaStreamSynchronize(st)); LDMAE_TRY(vmae_alloc_ws(h, B)); }
+  const int D = h->D, L = h->L, E = h->c.embed_dim;
+  const int M = B * L;
+  const int nh = h->c.decoder_num_heads, hd = D / nh;
+  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  latent_to_tokens_kernel<<<cdiv(static_cast<size_t>(M) * 64, 256), 256, 0, st>>>(h->tok.p, z, mean, stdv,
+                                                                                 multiplier != 0.f ? 1.f / multiplier : 1.f,
+                                                                                 B, h->c.latent_dim, L, 64);
+  LDMAE_LAUNCH_CHECK();
+  EpiStore<__nv_bfloat16, 0>::Params e0{h->t1.p, h->b_from.p, E};
+  LDMAE_TRY((gemm_auto<EpiStore<__nv_bfloat16, 0>>(h->tok.p, 64, h->w_from.p, 64, GemmShape{M, E, 64}, e0, st)));
+  broadcast_rows_kernel<<<cdiv(static_cast<size_t>(M) * D, 256), 256, 0, st>>>(h->x.p, h->pos.p, M, L, D);
+  LDMAE_LAUNCH_CHECK();
+  auto resid = [&](const void* a, int lda, const void* w, int ldw, int K, const float* bias) {
+    EpiResidual::Params ep;
+    ep.x = h->x.p; ep.bias = bias; ep.gate = nullptr; ep.gnext = nullptr; ep.anext = nullptr; ep.ssq = nullptr;
+    ep.ldx = D; ep.gate_ld = 0; ep.gnext_ld = 0; ep.rows_per_sample = L;
+    return gemm_auto<EpiResidual>(a, lda, w, ldw, GemmShape{M, D, K}, ep, st);
+  };
+  LDMAE_TRY(resid(h->t1.p, E, h->w_embed.p, E, E, h->b_embed.p));
+  const unsigned ln_grid = cdiv(M, 8);
+  for (int i = 0; i < h->c.decoder_depth; ++i) {
+    VmaeBlockW& b = h->blk[i];
+    layernorm_bf16_kernel<<<ln_grid, 256, 0, st>>>(h->a.p, h->x.p, b.n1w.p, b.n1b.p, M, D, h->c.ln_eps);
+    LDMAE_LAUNCH_CHECK();
+    EpiStore<__nv_bfloat16, 0>::Params eq{h->qkv.p, b.b_qkv.p, 3 * h->HP};
+    LDMAE_TRY((gemm_auto<EpiStore<__nv_bfloat16, 0>>(h->a.p, D, b.w_qkv.p, D, GemmShape{M, 3 * h->HP, D}, eq, st)));
+    LDMAE_TRY(run_attention(h->qkv.p, 3 * h->HP, h->o.p, h->HP, B, L, nh, 0, h->HP, 2 * h->HP, scale, st));
+    LDMAE_TRY(resid(h->o.p, h->HP, b.w_proj.p, h->HP, h->HP, b.b_proj.p));
+    layernorm_bf16_kernel<<<ln_grid, 256, 0, st>>>(h->a.p, h->x.p, b.n2w.p, b.n2b.p, M, D, h->c.ln_eps);
+    LDMAE_LAUNCH_CHECK();
+    EpiStore<__nv_bfloat16, 1>::Params e1{h->hid.p, b.b_fc1.p, h->Hm};
+    LDMAE_TRY((gemm_auto<EpiStore<__nv_bfloat16, 1>>(h->a.p, D, b.w_fc1.p, D, GemmShape{M, h->Hm, D}, e1, st)));
+    LDMAE_TRY(resid(h->hid.p, h->Hm, b.w_fc2.p, h->Hm, h->Hm, b.b_fc2.p));
+  }
+  layernorm_bf16_kernel<<<ln_grid, 256, 0, st>>>(h->a.p, h->x.p, h->nfw.p, h->nfb.p, M, D, h->c.ln_eps);
+  LDMAE_LAUNCH_CHECK();
+  EpiStore<float, 0>::Params epred{h->pred.p, h->b_pred.p, h->PP};
+  LDMAE_TRY((gemm_auto<EpiStore<float, 0>>(h->a.p, D, h->w_pred.p, D, GemmShape{M, h->PP, D}, epred, st)));
+  const size_t npix = static_cast<size_t>(B) * h->c.img_size * h->c.img_size;
+  vmae_pixel_tail_kernel<<<cdiv(npix, 256), 256, 0, st>>>(img_f32, img_u8, h->pred.p, h->conv_w.p, h->conv_b.p, B, h->G,
+                                                          h->c.patch_size);
+  LDMAE_LAUNCH_CHECK();
+  return LDMAE_OK;
+}
+
+// ------------------------------------------------------------------------------------------- building blocks
+extern "C" int ldmae_gemm_bias(const void* a, const void* w, const float* bias, void* out, int32_t out_is_bf16,
+                               int32_t M, int32_t N, int32_t K, int32_t act, int32_t cta_group, int32_t block_n,
+                               void* stream) {
+  LDMAE_TRY(require_sm100());
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LDMAE_REQUIRE(K % 8 == 0, "K must be a multiple of 8");
+  LDMAE_REQUIRE((cta_group == 1 && block_n == 128) || (cta_group == 2 && block_n == 256) || (cta_group == 1 && block_n == 256),
+                "supported tile configs: (cg1,bn128) (cg1,bn256) (cg2,bn256)");
+  ++g_launch_count;
+  const GemmShape g{M, N, K};
+#define LDMAE_DISPATCH(EPI, PARAMS)                                                             \
+  do {                                                                                          \
+    if (cta_group == 2) return launch_gemm<256, 2, EPI>(a, K, w, K, g, PARAMS, st);             \
+    if (block_n == 256) return launch_gemm<256, 1, EPI>(a, K, w, K, g, PARAMS, st);             \
+    return launch_gemm<128, 1, EPI>(a, K, w, K, g, PARAMS, st);                                 \
+  } while (0)
+  using EpiB0 = EpiStore<__nv_bfloat16, 0>;
+  using EpiB1 = EpiStore<__nv_bfloat16, 1>;
+  using EpiF0 = EpiStore<float, 0>;
+  if (out_is_bf16) {
+    if (act == 1) {
+      EpiB1::Params p{static_cast<__nv_bfloat16*>(out), bias, N};
+      LDMAE_DISPATCH(EpiB1, p);
+    }
+    EpiB0::Params p{static_cast<__nv_bfloat16*>(out), bias, N};
+    LDMAE_DISPATCH(EpiB0, p);
+  }
+  LDMAE_REQUIRE(act == 0, "fp32 output supports act 0 only");
+  EpiF0::Params p{static_cast<float*>(out), bias, N};
+  LDMAE_DISPATCH(EpiF0, p);
+#undef LDMAE_DISPATCH
+}
+
+extern "C" int ldmae_attention(const void* qkv, void* out, int32_t B, int32_t T, int32_t H, float scale, void* stream) {
+  LDMAE_TRY(require_sm100());
+  return run_attention(qkv, 3 * H * 64, out, H * 64, B, T, H, 0, H * 64, 2 * H * 64, scale, static_cast<cudaStream_t>(stream));
+}
+
+__global__ void f32_to_bf16_kernel(__nv_bfloat16* out, const float* in, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16(in[i]);
+}
+extern "C" int ldmae_f32_to_bf16(const float* in, void* out, int64_t n, void* stream) {
+  f32_to_bf16_kernel<<<cdiv(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<__nv_bfloat16*>(out), in, n);
+  LDMAE_LAUNCH_CHECK();
+  return LDMAE_OK;
+}

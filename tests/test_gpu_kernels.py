@@ -1,0 +1,78 @@
+"""-m gpu: building-block parity (tcgen05 GEMM, flash attention) through the C ABI, against a CPU fp32
+computation on the same bf16-rounded operands."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    torch.set_grad_enabled(False)
+
+
+GEMM_SHAPES = [
+    (256, 256, 64),      # one cluster tile, one k-block
+    (128, 128, 768),     # single CTA tile
+    (1024, 2304, 768),   # QKV shape (per 1 sample)
+    (1024, 768, 2048),   # w3 shape: long K, ring wraps several times
+    (300, 200, 192),     # ragged M/N tails, short K (VMAE width)
+    (4096, 4096, 768),   # w12 shape, many tiles per CTA (persistent loop, both TMEM stages)
+    (2, 768, 256),       # tiny M (conditioning-sized)
+]
+
+
+@pytest.mark.parametrize("cfg", [(1, 128), (1, 256), (2, 256)])
+@pytest.mark.parametrize("shape", GEMM_SHAPES)
+def test_gemm_bias_fp32_out(shape, cfg):
+    from tests.gpu_util import gemm_bias, rel_err
+    M, N, K = shape
+    cg, bn = cfg
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g)
+    ref = a.float() @ w.float().t() + bias
+    out = gemm_bias(a.cuda(), w.cuda(), bias.cuda(), out_bf16=False, cta_group=cg, block_n=bn).cpu()
+    err = rel_err(out, ref)
+    assert err < 2e-5, f"tcgen05 GEMM {shape} cfg {cfg}: rel err {err}"   # fp32 accumulate of exact bf16 products
+
+
+@pytest.mark.parametrize("act", [0, 1])
+def test_gemm_bias_bf16_out_and_gelu(act):
+    from tests.gpu_util import gemm_bias, rel_err
+    M, N, K = 640, 768, 192
+    g = torch.Generator().manual_seed(5)
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g)
+    ref = a.float() @ w.float().t() + bias
+    if act == 1:
+        ref = torch.nn.functional.gelu(ref)
+    out = gemm_bias(a.cuda(), w.cuda(), bias.cuda(), out_bf16=True, act=act).float().cpu()
+    assert rel_err(out, ref) < 4e-3     # bf16 output rounding (2^-9 relative per element)
+
+
+@pytest.mark.parametrize("B,T,H,scale", [(2, 1024, 3, 0.125), (3, 64, 2, 0.125), (1, 320, 2, 0.25), (2, 256, 1, 0.125)])
+def test_attention_matches_softmax(B, T, H, scale):
+    from tests.gpu_util import attention, rel_err
+    g = torch.Generator().manual_seed(B * 100 + T)
+    qkv = (torch.randn(B * T, 3 * H * 64, generator=g) * 1.5).to(torch.bfloat16)
+    q, k, v = qkv.float().reshape(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    att = torch.softmax((q @ k.transpose(-1, -2)) * scale, dim=-1)
+    ref = (att @ v).transpose(1, 2).reshape(B * T, H * 64)
+    out = attention(qkv.cuda(), B, T, H, scale).float().cpu()
+    err = rel_err(out, ref)
+    assert err < 1e-2, f"attention B{B} T{T} H{H}: rel err {err}"     # P and O are rounded to bf16
+
+
+def test_library_reports_sm100():
+    import ctypes as C
+    from ldmae_b200 import _lib
+    sm, cc = C.c_int(), C.c_int()
+    _lib.check(_lib.lib().ldmae_device_info(C.byref(sm), C.byref(cc)))
+    assert cc.value // 10 == 10 and sm.value >= 100

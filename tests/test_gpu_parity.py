@@ -1,0 +1,169 @@
+"""-m gpu: parity of the CUDA path with the CPU oracle and the committed reference goldens.
+
+Tolerances are the north_star's: per-forward velocity relative error <= 1e-2, final latent / image relative
+error <= 2e-2 (bf16 tensor-core operands, fp32 accumulate / residual stream), uint8 images within one level on
+>= 99% of the pixels.  Index work (patchify / unpatchify / token order) is covered by the same comparisons:
+any permutation error would show as O(1) relative error.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ldmae_oracle as O
+
+pytestmark = pytest.mark.gpu
+FWD_TOL = 1e-2
+FINAL_TOL = 2e-2
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    torch.set_grad_enabled(False)
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).norm() / b.norm())
+
+
+def _tiny_model(patch, seed, **flags):
+    from ldmae_b200.models.lightningdit import LightningDiT
+    spec = O.DiTSpec(depth=2, hidden_size=128, patch_size=patch, num_heads=2, input_size=8, in_channels=16,
+                     num_classes=10, **flags)
+    m = LightningDiT(input_size=8, patch_size=patch, in_channels=16, hidden_size=128, depth=2, num_heads=2, num_classes=10,
+                     use_qknorm=spec.use_qknorm, use_swiglu=True, use_rope=spec.use_rope, use_rmsnorm=True,
+                     wo_shift=spec.wo_shift)
+    sd = O.synth_dit_state(spec, seed)
+    m.load_state_dict(sd, strict=True)
+    return spec, sd, m.cuda().eval()
+
+
+@pytest.mark.parametrize("patch", [1, 2])
+def test_dit_tiny_forward_and_cfg_vs_reference_golden(golden_dir, patch):
+    from tests.gpu_util import load_npz
+    g = load_npz(golden_dir, f"dit_tiny_p{patch}.npz")
+    spec, sd, m = _tiny_model(patch, int(g["seed"]))
+    x, t, y = (torch.from_numpy(g[k]).cuda() for k in ("x", "t", "y"))
+    out = m(x, t, y)
+    assert out.shape == x.shape
+    assert _rel(out, g["out"]) < FWD_TOL
+    n = x.shape[0] // 2
+    ycfg = torch.from_numpy(g["ycfg"]).cuda()
+    hi = m.forward_with_cfg(x, torch.full((2 * n,), 0.37).cuda(), ycfg, 4.0, cfg_interval=True, cfg_interval_start=0.10)
+    lo = m.forward_with_cfg(x, torch.full((2 * n,), 0.05).cuda(), ycfg, 4.0, cfg_interval=True, cfg_interval_start=0.10)
+    assert _rel(hi, g["cfg_hi"]) < 2 * FWD_TOL      # guidance scale 4 amplifies (cond - uncond) error on 3 channels
+    assert _rel(lo, g["cfg_lo"]) < FWD_TOL
+    assert torch.equal(hi[:n, :3], hi[n:, :3])       # guided channels duplicated bit-exactly in both halves
+
+
+@pytest.mark.parametrize("patch", [1, 2])
+def test_sampler_euler_heun_vs_reference_golden(golden_dir, patch):
+    from ldmae_b200.transport import Sampler, create_transport
+    from tests.gpu_util import load_npz
+    g = load_npz(golden_dir, f"dit_tiny_p{patch}.npz")
+    spec, sd, m = _tiny_model(patch, int(g["seed"]))
+    x = torch.from_numpy(g["x"]).cuda()
+    n = x.shape[0] // 2
+    ycfg = torch.from_numpy(g["ycfg"]).cuda()
+    z = torch.cat([x[:n], x[:n]], 0)
+    smp = Sampler(create_transport("Linear", "velocity", None, None, None, use_cosine_loss=False, use_lognorm=True))
+    kw = dict(y=ycfg, cfg_scale=4.0, cfg_interval=True, cfg_interval_start=0.10)
+    fe = smp.sample_ode(sampling_method="euler", num_steps=7, atol=1e-6, rtol=1e-3, reverse=False, timestep_shift=0.3,
+                        keep_trajectory=True)
+    assert np.array_equal(fe.t.numpy(), g["grid_euler"])                 # time grid bit-exact
+    te = fe(z, m.forward_with_cfg, **kw)
+    assert len(te) == 7
+    assert _rel(te[-1], g["traj_euler"][-1]) < FINAL_TOL
+    assert _rel(te[3], g["traj_euler"][3]) < FINAL_TOL
+    fh = smp.sample_ode(sampling_method="heun2", num_steps=4, atol=1e-6, rtol=1e-3, reverse=False, timestep_shift=0.0)
+    th_ = fh(z, m.forward_with_cfg, **kw)
+    assert _rel(th_[-1], g["traj_heun"][-1]) < FINAL_TOL
+    fn = smp.sample_ode(sampling_method="euler", num_steps=5, atol=1e-6, rtol=1e-3, reverse=False, timestep_shift=0.3)
+    tn = fn(x[:n], m.forward, y=torch.from_numpy(g["y"]).cuda()[:n])
+    assert _rel(tn[-1], g["traj_nocfg"][-1]) < FINAL_TOL
+    # z must not be modified in place (the reference's odeint is out-of-place)
+    assert torch.equal(z, torch.cat([x[:n], x[:n]], 0))
+
+
+@pytest.mark.parametrize("tag,flags", [("noqk", dict(use_qknorm=False)), ("woshift", dict(wo_shift=True))])
+def test_dit_tiny_variants(golden_dir, tag, flags):
+    from tests.gpu_util import load_npz
+    g = load_npz(golden_dir, f"dit_tiny_{tag}.npz")
+    spec, sd, m = _tiny_model(1, int(g["seed"]), **flags)
+    out = m(torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["t"]).cuda(), torch.from_numpy(g["y"]).cuda())
+    assert _rel(out, g["out"]) < FWD_TOL
+
+
+def test_dit_b1_forward_vs_reference_golden(golden_dir):
+    from ldmae_b200.models.lightningdit import LightningDiT_models
+    from tests.gpu_util import load_npz
+    g = load_npz(golden_dir, "dit_b1_forward.npz")
+    spec = O.DiTSpec.named("LightningDiT-B/1", input_size=32, in_channels=16)
+    m = LightningDiT_models["LightningDiT-B/1"](input_size=32, in_channels=16, use_qknorm=True, use_swiglu=True,
+                                                use_rope=True, use_rmsnorm=True)
+    m.load_state_dict(O.synth_dit_state(spec, int(g["seed"])), strict=True)
+    m = m.cuda().eval()
+    out = m(torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["t"]).cuda(), torch.from_numpy(g["y"]).cuda())
+    assert _rel(out, g["out"]) < FWD_TOL
+    # linearity-free size-independent property at a larger batch: permuting the batch permutes the output
+    xb = torch.randn(6, 16, 32, 32, device="cuda"); tb = torch.rand(6, device="cuda"); yb = torch.randint(0, 1000, (6,), device="cuda")
+    o1 = m(xb, tb, yb)
+    perm = torch.tensor([3, 0, 5, 1, 4, 2], device="cuda")
+    o2 = m(xb[perm], tb[perm], yb[perm])
+    assert _rel(o2, o1[perm]) < 1e-5
+
+
+@pytest.mark.parametrize("tag,img", [("small", 32), ("full", 256)])
+def test_vmae_decode_vs_reference_golden(golden_dir, tag, img):
+    from ldmae_b200.tokenizer import models_mae
+    from tests.gpu_util import load_npz
+    g = load_npz(golden_dir, f"vmae_{tag}.npz")
+    spec = O.VMAESpec(img_size=img)
+    vae = models_mae.mae_for_ldmae_f8d16_prev(ldmae_mode=True, no_cls=True, kl_loss_weight=True, smooth_output=True, img_size=img)
+    msg = vae.load_state_dict(O.synth_vmae_state(spec, int(g["seed"]), encoder=True), strict=False)
+    assert not msg.missing_keys
+    vae = vae.cuda().eval()
+    z = torch.from_numpy(g["z"]).cuda()
+    imgf = vae.decode(z, return_dict=False)[0]
+    assert imgf.shape == g["img"].shape
+    assert _rel(imgf, g["img"]) < FINAL_TOL
+    assert _rel(vae.decode(z).sample, g["img"]) < FINAL_TOL
+    u8 = vae.decode_to_images(z)
+    assert u8.dtype == np.uint8 and u8.shape == g["u8"].shape
+    diff = np.abs(u8.astype(np.int32) - g["u8"].astype(np.int32))
+    assert (diff <= 1).mean() > 0.99 and diff.mean() < 0.5
+    # fused de-normalisation (inference.py:291) == decoding the de-normalised latent
+    mean = torch.linspace(-0.5, 0.5, 16).view(1, 16, 1, 1).cuda(); std = torch.linspace(0.5, 1.5, 16).view(1, 16, 1, 1).cuda()
+    u8a = vae.decode_to_images(z, mean, std, 2.0)
+    u8b = vae.decode_to_images((z * std) / 2.0 + mean)
+    assert (np.abs(u8a.astype(np.int32) - u8b.astype(np.int32)) <= 1).mean() > 0.999
+
+
+def test_sampling_job_vs_oracle():
+    """BASELINE config-1 shape at a size the oracle finishes in seconds: tiny DiT + small VMAE, CFG, Euler+shift."""
+    from ldmae_b200.models.lightningdit import LightningDiT
+    from ldmae_b200.tokenizer import models_mae
+    from ldmae_b200.transport import Sampler, create_transport
+    ds = O.DiTSpec(depth=2, hidden_size=128, patch_size=1, num_heads=2, input_size=16, in_channels=16, num_classes=10)
+    vs = O.VMAESpec(img_size=128)
+    dsd, vsd = O.synth_dit_state(ds, 3), O.synth_vmae_state(vs, 4)
+    g = torch.Generator().manual_seed(9)
+    n = 4
+    z = torch.randn(n, 16, 16, 16, generator=g); y = torch.randint(0, 10, (n,), generator=g)
+    lat_ref, img_ref, u8_ref = O.sample_images(dsd, ds, vsd, vs, z, y, num_steps=10, cfg_scale=4.0, cfg_interval_start=0.10,
+                                               timestep_shift=0.3)
+    m = LightningDiT(input_size=16, patch_size=1, in_channels=16, hidden_size=128, depth=2, num_heads=2, num_classes=10,
+                     use_qknorm=True, use_swiglu=True, use_rope=True, use_rmsnorm=True)
+    m.load_state_dict(dsd); m = m.cuda().eval()
+    vae = models_mae.mae_for_ldmae_f8d16_prev(ldmae_mode=True, no_cls=True, kl_loss_weight=True, smooth_output=True, img_size=128)
+    vae.load_state_dict(vsd, strict=False); vae = vae.cuda().eval()
+    fn = Sampler(create_transport("Linear", "velocity", None, None, None)).sample_ode(
+        sampling_method="euler", num_steps=10, atol=1e-6, rtol=1e-3, reverse=False, timestep_shift=0.3)
+    zz = torch.cat([z, z], 0).cuda(); yy = torch.cat([y, torch.full((n,), 10)]).cuda()
+    lat = fn(zz, m.forward_with_cfg, y=yy, cfg_scale=4.0, cfg_interval=True, cfg_interval_start=0.10)[-1].chunk(2, dim=0)[0]
+    assert _rel(lat, lat_ref) < FINAL_TOL
+    u8 = vae.decode_to_images(lat)
+    diff = np.abs(u8.astype(np.int32) - u8_ref.astype(np.int32))
+    assert (diff <= 2).mean() > 0.98
