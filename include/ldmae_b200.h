@@ -30,6 +30,14 @@ const char* ldmae_last_error(void);
 /* Library / device introspection: writes the SM count and compute capability (e.g. 100). */
 int ldmae_device_info(int* sm_count, int* cc);
 int ldmae_version(void);
+/* Number of kernel launches issued by the library so far in this process. */
+long long ldmae_launch_count(void);
+/* Per-kernel-class device timing with CUDA events on the launching stream (bench.py roofline).
+ * Classes: 0 qkv GEMM, 1 attention, 2 proj GEMM, 3 w12/SwiGLU GEMM, 4 w3 GEMM, 5 adaLN + shift-vector GEMMs,
+ * 6 final-layer GEMM, 7 conditioning / patch embed / ODE update, 8 VMAE decode. */
+#define LDMAE_PROF_CLASSES 9
+int ldmae_profile_begin(void);
+int ldmae_profile_end(double* ms_per_class, long long* scopes_per_class, int32_t nclasses);
 
 /* ------------------------------------------------------------------------------------------------
  * LightningDiT denoiser -- reference LDMAE/models/lightningdit.py:275-442 (class LightningDiT)
@@ -60,6 +68,13 @@ int ldmae_dit_finalize(ldmae_dit* h, void* stream);
  *   src_mod: sample b reads x[b % src_mod] (pass B for a plain forward; n for forward_with_cfg's cat[half,half]). */
 int ldmae_dit_forward(ldmae_dit* h, const float* x, const float* t, float t_scalar, const int64_t* y, float* out,
                       int32_t B, int32_t src_mod, void* stream);
+
+/* Test hooks: make ldmae_dit_forward return after `stages` launch groups (-1 = run everything; 1 conditioning,
+ * 2 adaLN, 3 shift vectors, 4 patch embed, then 5 per block: qkv, attention, proj, w12, w3), and copy a named
+ * workspace buffer ("xres", "abuf", "qkv", "obuf", "hbuf", "ssq", "mods", ...) to `dst` (device). */
+int ldmae_dit_debug_stop(ldmae_dit* h, int32_t stages);
+int ldmae_dit_debug_poison(ldmae_dit* h, int32_t byte, void* stream);   /* memset every workspace buffer */
+int ldmae_dit_debug_read(ldmae_dit* h, const char* name, void* dst, int64_t nbytes, void* stream);
 
 /* LightningDiT.forward_with_cfg (lightningdit.py:420-442): x [2n,...], t [2n], y [2n] (last n = null class);
  * guidance on channels [:3]; use_guidance = !(cfg_interval && t[0] < cfg_interval_start), decided by the

@@ -39,6 +39,9 @@ SYMBOLS = {
     "ldmae_dit_load_tensor": (C.c_int, [vp, C.c_char_p, vp, i64, vp]),
     "ldmae_dit_finalize": (C.c_int, [vp, vp]),
     "ldmae_dit_forward": (C.c_int, [vp, vp, vp, f32, vp, vp, i32, i32, vp]),
+    "ldmae_dit_debug_stop": (C.c_int, [vp, i32]),
+    "ldmae_dit_debug_poison": (C.c_int, [vp, i32, vp]),
+    "ldmae_dit_debug_read": (C.c_int, [vp, C.c_char_p, vp, i64, vp]),
     "ldmae_dit_forward_with_cfg": (C.c_int, [vp, vp, vp, f32, vp, vp, i32, f32, i32, vp]),
     "ldmae_sample_ode": (C.c_int, [vp, vp, vp, i32, i32, f32, f32, C.POINTER(C.c_float), i32, i32, vp, vp]),
     "ldmae_vmae_create": (C.c_int, [C.POINTER(VmaeConfig), C.POINTER(vp)]),
@@ -50,6 +53,8 @@ SYMBOLS = {
     "ldmae_attention": (C.c_int, [vp, vp, i32, i32, i32, f32, vp]),
     "ldmae_f32_to_bf16": (C.c_int, [vp, vp, i64, vp]),
     "ldmae_launch_count": (C.c_longlong, []),
+    "ldmae_profile_begin": (C.c_int, []),
+    "ldmae_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong), i32]),
 }
 
 
@@ -85,6 +90,22 @@ def ptr(t):
         return C.c_void_p(0)
     assert t.is_cuda and t.is_contiguous(), "ldmae_b200 expects contiguous CUDA tensors"
     return C.c_void_p(t.data_ptr())
+
+
+PROF_CLASSES = ("qkv_gemm", "attention", "proj_gemm", "w12_swiglu_gemm", "w3_gemm", "adaln_shift_gemms", "final_gemm",
+                "cond_embed_update", "vmae_decode")
+
+
+def profile_begin():
+    check(lib().ldmae_profile_begin(), "profile_begin")
+
+
+def profile_end():
+    n = len(PROF_CLASSES)
+    ms = (C.c_double * n)()
+    cnt = (C.c_longlong * n)()
+    check(lib().ldmae_profile_end(ms, cnt, n), "profile_end")
+    return {PROF_CLASSES[i]: (float(ms[i]), int(cnt[i])) for i in range(n)}
 
 
 def launch_count() -> int:

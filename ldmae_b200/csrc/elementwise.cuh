@@ -149,18 +149,19 @@ __global__ void adaln_prep_kernel(__nv_bfloat16* __restrict__ shift_bf16, float*
 // Patch embedding + positional embedding (timm PatchEmbed = Conv2d k=stride=p; lightningdit.py:402)
 // fused with the first norm's operand preparation (see EpiResidual).  One block = 32 tokens of a sample.
 //   x[row, n]   = W[n, :] . patch(row) + bias[n] + pos[tok, n]
-//   anext[row,n]= bf16(x * gnext[b, n]);  ssq[row] = sum_n x^2
+//   anext[row,n]= bf16(x * gnext[b, n]);  ssq[row, 0] = sum_n x^2 (other slots 0)
 // src_mod: sample b reads latent (b % src_mod) -- forward_with_cfg feeds cat[half, half] (lightningdit.py:425-426).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 patch_embed_kernel(float* __restrict__ x, __nv_bfloat16* __restrict__ anext, float* __restrict__ ssq,
                    const float* __restrict__ lat /*[Bsrc, C, S, S]*/, const float* __restrict__ W /*[D, C*p*p]*/,
                    const float* __restrict__ bias, const float* __restrict__ pos /*[T, D]*/,
-                   const float* __restrict__ gnext /*[B, D]*/, int C, int S, int p, int D, int src_mod) {
+                   const float* __restrict__ gnext /*[B, D]*/, int C, int S, int p, int D, int src_mod, int ss_slots) {
   extern __shared__ float sm[];
   const int G = S / p, T = G * G, Kp = C * p * p;
   float* s_in = sm;                               // [32][Kp]
-  float* s_red = sm + 32 * Kp;                    // [32] per-token sum of squares
+  float* s_red = sm + 32 * Kp;                    // [8 warps][32 tokens] partial sums of squares (no atomics:
+                                                  // fixed summation order => bit-reproducible statistics)
   const int b = blockIdx.y;
   const int tok0 = blockIdx.x * 32;
   const float* src = lat + static_cast<size_t>(b % src_mod) * C * S * S;
@@ -175,9 +176,9 @@ patch_embed_kernel(float* __restrict__ x, __nv_bfloat16* __restrict__ anext, flo
     }
     s_in[tl * Kp + k] = v;
   }
-  if (threadIdx.x < 32) s_red[threadIdx.x] = 0.f;
+  s_red[threadIdx.x] = 0.f;
   __syncthreads();
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int n = threadIdx.x; n < D; n += blockDim.x) {          // D % 32 == 0: warp-uniform trip count
     const float bn = bias[n];
     const float gn = gnext ? gnext[static_cast<size_t>(b) * D + n] : 1.f;
@@ -207,13 +208,19 @@ patch_embed_kernel(float* __restrict__ x, __nv_bfloat16* __restrict__ anext, flo
           sq = v * v;
         }
         sq = warp_sum(sq);
-        if (lane == 0) atomicAdd(&s_red[hf * 16 + i], sq);
+        if (lane == 0) s_red[warp * 32 + hf * 16 + i] += sq;
       }
     }
   }
   __syncthreads();
-  if (ssq != nullptr && threadIdx.x < 32 && tok0 + threadIdx.x < T)
-    ssq[static_cast<size_t>(b) * T + tok0 + threadIdx.x] = s_red[threadIdx.x];
+  if (ssq != nullptr && threadIdx.x < 32 && tok0 + threadIdx.x < T) {
+    float* dst = ssq + (static_cast<size_t>(b) * T + tok0 + threadIdx.x) * ss_slots;   // slot 0 = whole row
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += s_red[w * 32 + threadIdx.x];
+    dst[0] = s;
+    for (int j = 1; j < ss_slots; ++j) dst[j] = 0.f;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -114,7 +114,7 @@ struct EpiStore {
 // Residual update of the fp32 token stream, fused with the *next* norm's operand preparation:
 //   x[row,col] += gate[b,col] * (acc + bias[col])                      (lightningdit.py:248-249)
 //   anext[row,col] = bf16( x_new * gnext[b,col] )   with gnext = norm.weight * (1 + scale_b)
-//   ssq[row] += sum_col x_new^2                      (RMSNorm statistics, models/rmsnorm.py:63)
+//   ssq[row, tile] = sum_{col in tile} x_new^2       (RMSNorm statistics, models/rmsnorm.py:63)
 // so that  modulate(RMSNorm(x)) . W^T  ==  rsqrt(ssq/D+eps) * (anext . W^T) + shift_b . W^T  is finished in
 // the next GEMM's epilogue without another pass over x.  gate/gnext/ssq/anext are optional (VMAE
 // uses the plain residual).  b = row / rows_per_sample.
@@ -125,8 +125,9 @@ struct EpiResidual {
     const float* gate;     // [B, gate_ld] or nullptr (=> 1)
     const float* gnext;    // [B, gnext_ld] or nullptr
     __nv_bfloat16* anext;  // [M, ldx] or nullptr
-    float* ssq;            // [M] or nullptr
-    int ldx, gate_ld, gnext_ld, rows_per_sample;
+    float* ssq;            // [M, ss_slots] per-row partial sums of squares, or nullptr.  Slot = column/128 of the
+                           // producing tile: no atomics, so the statistics are bit-reproducible.
+    int ldx, gate_ld, gnext_ld, rows_per_sample, ss_slots;
   };
   template <int BN>
   static __device__ __forceinline__ void run(const Params& p, const GemmShape& g, uint32_t acc, int row0, int n0,
@@ -185,11 +186,23 @@ struct EpiResidual {
         s += __shfl_xor_sync(0xffffffffu, s, 4);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
         s += __shfl_xor_sync(0xffffffffu, s, 1);
-        if (lane == 0 && row0 + r < g.M) atomicAdd(p.ssq + row0 + r, s);
+        if (lane == 0 && row0 + r < g.M) {
+          float* dst = p.ssq + static_cast<size_t>(row0 + r) * p.ss_slots + n0 / 128;
+          dst[0] = s;
+          if (BN > 128 && n0 / 128 + 1 < p.ss_slots) dst[1] = 0.f;
+        }
       }
     }
   }
 };
+
+// rsqrt(mean(x^2) + eps) of a residual-stream row from its per-tile partial sums (fixed summation order)
+__device__ __forceinline__ float row_rinv(const float* ssq, int row, int slots, float inv_D, float eps) {
+  if (ssq == nullptr) return 1.f;
+  float s = 0.f;
+  for (int j = 0; j < slots; ++j) s += __ldg(ssq + static_cast<size_t>(row) * slots + j);
+  return rsqrtf(s * inv_D + eps);
+}
 
 // QKV projection of LightningDiT attention (lightningdit.py:68-74) on the pre-scaled operand:
 //   v = acc * rsqrt(ssq[row]/D + eps) + cvec[b,col]        (= Linear(modulate(RMSNorm(x))) incl. bias)
@@ -199,13 +212,13 @@ struct EpiResidual {
 struct EpiQKV {
   struct Params {
     __nv_bfloat16* out;     // [M, 3D]
-    const float* ssq;       // [M] sum of squares of the residual stream row (or nullptr: no row scale)
+    const float* ssq;       // [M, ss_slots] partial sums of squares of the residual-stream row (nullptr: no row scale)
     const float* cvec;      // [B, 3D]  shift_b . W^T + bias
     const float* qw;        // [64] q_norm.weight or nullptr (no qk-norm)
     const float* kw;        // [64]
     const float* rope_cos;  // [T, 64] or nullptr
     const float* rope_sin;  // [T, 64]
-    int D, rows_per_sample;
+    int D, rows_per_sample, ss_slots;
     float inv_D, eps_row, eps_head;
   };
   template <int BN>
@@ -214,7 +227,7 @@ struct EpiQKV {
     static_assert(BN % 64 == 0, "QKV epilogue works on whole 64-wide heads");
     const int my_row = min(row0 + lane, g.M - 1);
     const int my_b = my_row / p.rows_per_sample;
-    const float rinv = p.ssq ? rsqrtf(__ldg(p.ssq + my_row) * p.inv_D + p.eps_row) : 1.f;
+    const float rinv = row_rinv(p.ssq, my_row, p.ss_slots, p.inv_D, p.eps_row);
     const float* cv = p.cvec + static_cast<size_t>(my_b) * g.N;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 64) {
@@ -270,7 +283,7 @@ struct EpiSwiGLU {
     __nv_bfloat16* out;   // [M, H]
     const float* ssq;     // [M]
     const float* cvec;    // [B, 2H] in the same interleaved column order
-    int H, rows_per_sample;
+    int H, rows_per_sample, ss_slots;
     float inv_D, eps_row;
   };
   template <int BN>
@@ -279,7 +292,7 @@ struct EpiSwiGLU {
     static_assert(BN % 128 == 0, "SwiGLU epilogue consumes 128 accumulator columns per staged block");
     const int my_row = min(row0 + lane, g.M - 1);
     const int my_b = my_row / p.rows_per_sample;
-    const float rinv = p.ssq ? rsqrtf(__ldg(p.ssq + my_row) * p.inv_D + p.eps_row) : 1.f;
+    const float rinv = row_rinv(p.ssq, my_row, p.ss_slots, p.inv_D, p.eps_row);
     const float* cv = p.cvec + static_cast<size_t>(my_b) * g.N;
     uint32_t* sw = reinterpret_cast<uint32_t*>(stage);
 #pragma unroll 1
@@ -321,7 +334,7 @@ struct EpiFinal {
     float* out;          // [B, Cstore, G*p, G*p]
     const float* ssq;    // [M]
     const float* cvec;   // [B, N]
-    int grid, patch, cout, cstore, rows_per_sample;
+    int grid, patch, cout, cstore, rows_per_sample, ss_slots;
     float inv_D, eps_row;
   };
   template <int BN>
@@ -333,7 +346,7 @@ struct EpiFinal {
     const int b = rowc / p.rows_per_sample;
     const int tok = rowc % p.rows_per_sample;
     const int th = tok / p.grid, tw = tok % p.grid;
-    const float rinv = p.ssq ? rsqrtf(__ldg(p.ssq + rowc) * p.inv_D + p.eps_row) : 1.f;
+    const float rinv = row_rinv(p.ssq, rowc, p.ss_slots, p.inv_D, p.eps_row);
     const int HW = p.grid * p.patch;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 16) {

@@ -30,6 +30,23 @@ int set_error(int code, const char* fmt, ...) {
 }
 long long g_launch_count = 0;
 
+// Optional per-kernel-class device timing (CUDA events on the launching stream), used by bench.py for the
+// roofline of the dominant kernel.  Classes: 0 qkv GEMM, 1 attention, 2 proj GEMM, 3 w12 (SwiGLU) GEMM,
+// 4 w3 GEMM, 5 adaLN / shift-vector GEMMs, 6 final-layer GEMM, 7 conditioning + patch embed + ODE update, 8 VMAE decode.
+constexpr int kProfClasses = 9;
+struct ProfRec { int cls; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+struct ProfScope {
+  cudaStream_t st; int cls; cudaEvent_t a = nullptr, b = nullptr; bool on;
+  ProfScope(int c, cudaStream_t s) : st(s), cls(c), on(g_prof_on) {
+    if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
+  }
+  ~ProfScope() {
+    if (on) { cudaEventRecord(b, st); g_prof.push_back(ProfRec{cls, a, b}); }
+  }
+};
+
 int device_sm_count() {
   static int sms = 0;
   if (sms == 0) {
@@ -143,7 +160,7 @@ using namespace ldmae;
 
 struct ldmae_dit {
   ldmae_dit_config c;
-  int D, T, G, Kp, H, Hp, nmod, Ntot, S /*norm slots*/, Nf, maxB;
+  int D, T, G, Kp, H, Hp, nmod, Ntot, S /*norm slots*/, Nf, maxB, SS /*ssq partial slots*/;
   // weights
   DevBuf<float> pos, patch_w, patch_b, t_w0, t_b0, t_w2, t_b2, emb, rope_cos, rope_sin, norm_w, b_ada, b_f, w_f32;
   DevBuf<__nv_bfloat16> w_ada, w_f;
@@ -151,6 +168,7 @@ struct ldmae_dit {
   DevBuf<int> slot_shift_off, slot_scale_off;
   std::vector<std::string> loaded;
   bool finalized = false;
+  int debug_stop = -1;   // >= 0: dit_forward_impl returns after that many launch groups (ldmae_dit_debug_stop)
   // workspace (sized for maxB)
   DevBuf<float> xres, ssq, cvec_c, th1, mods, gmul, cvec_qkv, cvec_12, cvec_f, vbuf, k1buf, xtmp;
   DevBuf<__nv_bfloat16> abuf, qkv, obuf, hbuf, sc, shift_bf16;
@@ -164,7 +182,7 @@ static int dit_alloc_ws(ldmae_dit* h, int B) {
   LDMAE_TRY(h->qkv.alloc(M * 3 * D));
   LDMAE_TRY(h->obuf.alloc(M * D));
   LDMAE_TRY(h->hbuf.alloc(M * h->Hp));
-  LDMAE_TRY(h->ssq.alloc(M));
+  LDMAE_TRY(h->ssq.alloc(M * h->SS));
   LDMAE_TRY(h->cvec_c.alloc(static_cast<size_t>(B) * D));
   LDMAE_TRY(h->th1.alloc(static_cast<size_t>(B) * D));
   LDMAE_TRY(h->sc.alloc(static_cast<size_t>(B) * D));
@@ -185,6 +203,26 @@ static int dit_alloc_ws(ldmae_dit* h, int B) {
 extern "C" const char* ldmae_last_error(void) { return last_error().c_str(); }
 extern "C" int ldmae_version(void) { return 100; }
 extern "C" long long ldmae_launch_count(void) { return g_launch_count; }
+
+extern "C" int ldmae_profile_begin(void) {
+  for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.clear();
+  g_prof_on = true;
+  return LDMAE_OK;
+}
+// Stops profiling; ms[c] = summed device time of class c, launches[c] = number of timed scopes.
+extern "C" int ldmae_profile_end(double* ms, long long* launches, int32_t nclasses) {
+  g_prof_on = false;
+  LDMAE_CUDA(cudaDeviceSynchronize());
+  for (int c = 0; c < nclasses; ++c) { ms[c] = 0.0; launches[c] = 0; }
+  for (auto& r : g_prof) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess && r.cls < nclasses) { ms[r.cls] += t; launches[r.cls] += 1; }
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  return LDMAE_OK;
+}
 
 extern "C" int ldmae_device_info(int* sm_count, int* cc) {
   int dev = 0, major = 0, minor = 0, sms = 0;
@@ -227,6 +265,7 @@ extern "C" int ldmae_dit_create(const ldmae_dit_config* cfg, ldmae_dit** out) {
   h->Ntot = (c.depth * h->nmod + 2) * h->D;
   h->S = 2 * c.depth + 1;
   h->Nf = c.patch_size * c.patch_size * c.in_channels * (c.learn_sigma ? 2 : 1);
+  h->SS = (c.hidden_size + 127) / 128;
   const int D = h->D;
   h->blk.resize(c.depth);
   int r = LDMAE_OK;
@@ -377,8 +416,11 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
   const int D = h->D, T = h->T, depth = c.depth;
   const int M = B * T;
   const float eps = 1e-6f;
+  int dbg_stage = 0;
+#define LDMAE_DBG_STAGE() do { if (h->debug_stop >= 0 && ++dbg_stage > h->debug_stop) return LDMAE_OK; } while (0)
   // 1. conditioning c = t_emb + y_emb ; sc = bf16(silu(c))
   {
+    ProfScope ps(7, st);
     dim3 grid(cdiv(D, 64), cdiv(B, 16));
     const size_t sm0 = 16 * 256 * sizeof(float), sm2 = 16 * static_cast<size_t>(D) * sizeof(float);
     static bool attr = false;
@@ -395,8 +437,10 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
     silu_to_bf16_kernel<<<cdiv(static_cast<size_t>(B) * D, 256), 256, 0, st>>>(h->sc.p, h->cvec_c.p, static_cast<size_t>(B) * D);
     LDMAE_LAUNCH_CHECK();
   }
+  LDMAE_DBG_STAGE();   // 1
   // 2. all adaLN modulations at once: mods[B, Ntot] = sc . W_ada^T + b_ada
   {
+    ProfScope ps(5, st);
     EpiStore<float, 0>::Params ep{h->mods.p, h->b_ada.p, h->Ntot};
     LDMAE_TRY((gemm_auto<EpiStore<float, 0>>(h->sc.p, D, h->w_ada.p, D, GemmShape{B, h->Ntot, D}, ep, st)));
     const size_t tot = static_cast<size_t>(h->S) * B * D;
@@ -404,8 +448,10 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
                                                       h->slot_shift_off.p, h->slot_scale_off.p, B, D, h->Ntot, h->S);
     LDMAE_LAUNCH_CHECK();
   }
+  LDMAE_DBG_STAGE();   // 2
   // 3. per-sample vectors  shift_b . W^T + bias  for every modulated Linear
   for (int i = 0; i < depth; ++i) {
+    ProfScope ps(5, st);
     DitBlockW& b = h->blk[i];
     float* cq = h->cvec_qkv.p + static_cast<size_t>(i) * B * 3 * D;
     float* c12 = h->cvec_12.p + static_cast<size_t>(i) * B * 2 * h->Hp;
@@ -417,6 +463,7 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
                                               GemmShape{B, 2 * h->Hp, D}, e2, st)));
   }
   {
+    ProfScope ps(7, st);
     // final linear (N = p*p*C_out, e.g. 16): fp32 on CUDA cores straight from the shift columns of mods
     dim3 grid(cdiv(h->Nf, 64), cdiv(B, 16));
     const size_t sm2 = 16 * static_cast<size_t>(D) * sizeof(float);
@@ -424,15 +471,18 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
                                                    h->w_f32.p, h->b_f.p, nullptr, nullptr, B, D, h->Nf, 0, h->Ntot);
     LDMAE_LAUNCH_CHECK();
   }
+  LDMAE_DBG_STAGE();   // 3
   // 4. patch embed + pos embed -> residual stream, first operand, first row statistics
   {
+    ProfScope ps(7, st);
     dim3 grid(cdiv(T, 32), B);
     const size_t sm = (32 * static_cast<size_t>(h->Kp) + 256) * sizeof(float);
     patch_embed_kernel<<<grid, 256, sm, st>>>(h->xres.p, h->abuf.p, h->ssq.p, x, h->patch_w.p, h->patch_b.p, h->pos.p,
-                                              h->gmul.p, c.in_channels, c.input_size, c.patch_size, D, src_mod);
+                                              h->gmul.p, c.in_channels, c.input_size, c.patch_size, D, src_mod, h->SS);
     LDMAE_LAUNCH_CHECK();
   }
-  // 5. blocks
+  LDMAE_DBG_STAGE();   // 4
+  // 5. blocks  (debug stages 5 + 5*i + {0 qkv, 1 attention, 2 proj, 3 w12, 4 w3})
   for (int i = 0; i < depth; ++i) {
     DitBlockW& b = h->blk[i];
     const float* mods_i = h->mods.p + static_cast<size_t>(i) * h->nmod * D;
@@ -442,35 +492,71 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
     eq.out = h->qkv.p; eq.ssq = h->ssq.p; eq.cvec = h->cvec_qkv.p + static_cast<size_t>(i) * B * 3 * D;
     eq.qw = c.use_qknorm ? b.qw.p : nullptr; eq.kw = c.use_qknorm ? b.kw.p : nullptr;
     eq.rope_cos = c.use_rope ? h->rope_cos.p : nullptr; eq.rope_sin = c.use_rope ? h->rope_sin.p : nullptr;
-    eq.D = D; eq.rows_per_sample = T; eq.inv_D = 1.f / D; eq.eps_row = eps; eq.eps_head = eps;
-    LDMAE_TRY((gemm_auto<EpiQKV>(h->abuf.p, D, b.w_qkv.p, D, GemmShape{M, 3 * D, D}, eq, st)));
-    LDMAE_TRY(run_attention(h->qkv.p, 3 * D, h->obuf.p, D, B, T, c.num_heads, 0, D, 2 * D, 0.125f, st));
-    LDMAE_CUDA(cudaMemsetAsync(h->ssq.p, 0, static_cast<size_t>(M) * sizeof(float), st));
+    eq.D = D; eq.rows_per_sample = T; eq.ss_slots = h->SS; eq.inv_D = 1.f / D; eq.eps_row = eps; eq.eps_head = eps;
+    { ProfScope ps(0, st); LDMAE_TRY((gemm_auto<EpiQKV>(h->abuf.p, D, b.w_qkv.p, D, GemmShape{M, 3 * D, D}, eq, st))); }
+    LDMAE_DBG_STAGE();
+    { ProfScope ps(1, st); LDMAE_TRY(run_attention(h->qkv.p, 3 * D, h->obuf.p, D, B, T, c.num_heads, 0, D, 2 * D, 0.125f, st)); }
+    LDMAE_DBG_STAGE();
     EpiResidual::Params ep;
     ep.x = h->xres.p; ep.bias = b.b_proj.p; ep.gate = gate_msa; ep.gnext = h->gmul.p + static_cast<size_t>(2 * i + 1) * B * D;
-    ep.anext = h->abuf.p; ep.ssq = h->ssq.p; ep.ldx = D; ep.gate_ld = h->Ntot; ep.gnext_ld = D; ep.rows_per_sample = T;
-    LDMAE_TRY((gemm_auto<EpiResidual>(h->obuf.p, D, b.w_proj.p, D, GemmShape{M, D, D}, ep, st)));
+    ep.anext = h->abuf.p; ep.ssq = h->ssq.p; ep.ldx = D; ep.gate_ld = h->Ntot; ep.gnext_ld = D; ep.rows_per_sample = T; ep.ss_slots = h->SS;
+    { ProfScope ps(2, st); LDMAE_TRY((gemm_auto<EpiResidual>(h->obuf.p, D, b.w_proj.p, D, GemmShape{M, D, D}, ep, st))); }
+    LDMAE_DBG_STAGE();
     EpiSwiGLU::Params es;
     es.out = h->hbuf.p; es.ssq = h->ssq.p; es.cvec = h->cvec_12.p + static_cast<size_t>(i) * B * 2 * h->Hp;
-    es.H = h->Hp; es.rows_per_sample = T; es.inv_D = 1.f / D; es.eps_row = eps;
-    LDMAE_TRY((gemm_auto<EpiSwiGLU>(h->abuf.p, D, b.w12.p, D, GemmShape{M, 2 * h->Hp, D}, es, st)));
-    // NOTE: the w12 GEMM reads ssq; the w3 epilogue accumulates the next statistics into it, so it
-    // is cleared in between (stream order makes this safe).
-    LDMAE_CUDA(cudaMemsetAsync(h->ssq.p, 0, static_cast<size_t>(M) * sizeof(float), st));
+    es.H = h->Hp; es.rows_per_sample = T; es.ss_slots = h->SS; es.inv_D = 1.f / D; es.eps_row = eps;
+    { ProfScope ps(3, st); LDMAE_TRY((gemm_auto<EpiSwiGLU>(h->abuf.p, D, b.w12.p, D, GemmShape{M, 2 * h->Hp, D}, es, st))); }
+    LDMAE_DBG_STAGE();
     EpiResidual::Params e3;
     e3.x = h->xres.p; e3.bias = b.b3.p; e3.gate = gate_mlp; e3.gnext = h->gmul.p + static_cast<size_t>(2 * i + 2) * B * D;
-    e3.anext = h->abuf.p; e3.ssq = h->ssq.p; e3.ldx = D; e3.gate_ld = h->Ntot; e3.gnext_ld = D; e3.rows_per_sample = T;
-    LDMAE_TRY((gemm_auto<EpiResidual>(h->hbuf.p, h->Hp, b.w3.p, h->Hp, GemmShape{M, D, h->Hp}, e3, st)));
+    e3.anext = h->abuf.p; e3.ssq = h->ssq.p; e3.ldx = D; e3.gate_ld = h->Ntot; e3.gnext_ld = D; e3.rows_per_sample = T; e3.ss_slots = h->SS;
+    { ProfScope ps(4, st); LDMAE_TRY((gemm_auto<EpiResidual>(h->hbuf.p, h->Hp, b.w3.p, h->Hp, GemmShape{M, D, h->Hp}, e3, st))); }
+    LDMAE_DBG_STAGE();
   }
   // 6. final layer + unpatchify
   {
     EpiFinal::Params ef;
     ef.out = out; ef.ssq = h->ssq.p; ef.cvec = h->cvec_f.p; ef.grid = h->G; ef.patch = c.patch_size;
-    ef.cout = c.in_channels * (c.learn_sigma ? 2 : 1); ef.cstore = c.in_channels; ef.rows_per_sample = T;
+    ef.cout = c.in_channels * (c.learn_sigma ? 2 : 1); ef.cstore = c.in_channels; ef.rows_per_sample = T; ef.ss_slots = h->SS;
     ef.inv_D = 1.f / D; ef.eps_row = eps;
+    ProfScope ps(6, st);
     LDMAE_TRY((launch_gemm<16, 1, EpiFinal>(h->abuf.p, D, h->w_f.p, D, GemmShape{M, h->Nf, D}, ef, st)));
     ++g_launch_count;
   }
+  return LDMAE_OK;
+}
+
+// Debug hooks for the parity tests: stop the forward after `stages` launch groups / read a workspace buffer.
+extern "C" int ldmae_dit_debug_stop(ldmae_dit* h, int32_t stages) {
+  LDMAE_REQUIRE(h, "null handle");
+  h->debug_stop = stages;
+  return LDMAE_OK;
+}
+// Fills every workspace buffer with `byte` (0xFF = NaN patterns): a read-before-write then shows up as NaNs.
+extern "C" int ldmae_dit_debug_poison(ldmae_dit* h, int32_t byte, void* stream) {
+  LDMAE_REQUIRE(h, "null handle");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define LDMAE_POISON(BUF) if (h->BUF.p) LDMAE_CUDA(cudaMemsetAsync(h->BUF.p, byte, h->BUF.n * sizeof(*h->BUF.p), st));
+  LDMAE_POISON(xres) LDMAE_POISON(ssq) LDMAE_POISON(cvec_c) LDMAE_POISON(th1) LDMAE_POISON(mods) LDMAE_POISON(gmul)
+  LDMAE_POISON(cvec_qkv) LDMAE_POISON(cvec_12) LDMAE_POISON(cvec_f) LDMAE_POISON(vbuf) LDMAE_POISON(k1buf) LDMAE_POISON(xtmp)
+  LDMAE_POISON(abuf) LDMAE_POISON(qkv) LDMAE_POISON(obuf) LDMAE_POISON(hbuf) LDMAE_POISON(sc) LDMAE_POISON(shift_bf16)
+#undef LDMAE_POISON
+  return LDMAE_OK;
+}
+extern "C" int ldmae_dit_debug_read(ldmae_dit* h, const char* name, void* dst, int64_t nbytes, void* stream) {
+  LDMAE_REQUIRE(h && name && dst, "null argument");
+  const std::string k(name);
+  const void* src = nullptr;
+  size_t have = 0;
+#define LDMAE_DBG_BUF(NAME, BUF) if (k == NAME) { src = h->BUF.p; have = h->BUF.n * sizeof(*h->BUF.p); }
+  LDMAE_DBG_BUF("xres", xres) LDMAE_DBG_BUF("abuf", abuf) LDMAE_DBG_BUF("qkv", qkv) LDMAE_DBG_BUF("obuf", obuf)
+  LDMAE_DBG_BUF("hbuf", hbuf) LDMAE_DBG_BUF("ssq", ssq) LDMAE_DBG_BUF("mods", mods) LDMAE_DBG_BUF("cvec_c", cvec_c)
+  LDMAE_DBG_BUF("cvec_qkv", cvec_qkv) LDMAE_DBG_BUF("cvec_12", cvec_12) LDMAE_DBG_BUF("cvec_f", cvec_f)
+  LDMAE_DBG_BUF("gmul", gmul) LDMAE_DBG_BUF("shift_bf16", shift_bf16) LDMAE_DBG_BUF("sc", sc) LDMAE_DBG_BUF("th1", th1)
+#undef LDMAE_DBG_BUF
+  LDMAE_REQUIRE(src != nullptr, "unknown debug buffer %s", name);
+  LDMAE_REQUIRE(nbytes >= 0 && static_cast<size_t>(nbytes) <= have, "debug buffer %s holds %zu bytes, asked for %lld", name, have, (long long)nbytes);
+  LDMAE_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
   return LDMAE_OK;
 }
 
@@ -483,6 +569,7 @@ extern "C" int ldmae_dit_forward(ldmae_dit* h, const float* x, const float* t, f
 static int launch_update(float* xout, const float* xin, const float* v, const float* kprev, float* gout, int n_half,
                          int C, int HW, float cfg_scale, int use_guidance, float a, float bcoef, size_t total,
                          cudaStream_t st) {
+  ProfScope ps(7, st);
   cfg_ode_update_kernel<<<cdiv(total, 256), 256, 0, st>>>(xout, xin, v, kprev, gout, n_half, C, HW, 3, cfg_scale,
                                                           use_guidance, a, bcoef, total);
   LDMAE_LAUNCH_CHECK();
@@ -682,6 +769,7 @@ extern "C" int ldmae_vmae_decode(ldmae_vmae* h, const float* z, const float* mea
   LDMAE_REQUIRE((mean == nullptr) == (stdv == nullptr), "mean/std must be given together");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (B > h->maxB) { LDMAE_CUDA(cudaStreamSynchronize(st)); LDMAE_TRY(vmae_alloc_ws(h, B)); }
+  ProfScope ps(8, st);
   const int D = h->D, L = h->L, E = h->c.embed_dim;
   const int M = B * L;
   const int nh = h->c.decoder_num_heads, hd = D / nh;
@@ -697,7 +785,7 @@ extern "C" int ldmae_vmae_decode(ldmae_vmae* h, const float* z, const float* mea
   auto resid = [&](const void* a, int lda, const void* w, int ldw, int K, const float* bias) {
     EpiResidual::Params ep;
     ep.x = h->x.p; ep.bias = bias; ep.gate = nullptr; ep.gnext = nullptr; ep.anext = nullptr; ep.ssq = nullptr;
-    ep.ldx = D; ep.gate_ld = 0; ep.gnext_ld = 0; ep.rows_per_sample = L;
+    ep.ldx = D; ep.gate_ld = 0; ep.gnext_ld = 0; ep.rows_per_sample = L; ep.ss_slots = 0;
     return gemm_auto<EpiResidual>(a, lda, w, ldw, GemmShape{M, D, K}, ep, st);
   };
   LDMAE_TRY(resid(h->t1.p, E, h->w_embed.p, E, E, h->b_embed.p));

@@ -1,0 +1,94 @@
+"""Batch sampling job: the body of the reference's ``do_sample`` loop (LDMAE/inference.py:264-292) as one call.
+
+    z, y (host or device)  ->  CFG doubling with the null class  ->  transport ODE (``Sampler.sample_ode``)
+    ->  keep the conditional half  ->  latent de-normalisation  ->  VMAE ``decode_to_images``  ->  uint8 NHWC
+
+It only composes the reference-shaped public API of this package (``LightningDiT.forward_with_cfg``,
+``create_transport`` / ``Sampler.sample_ode``, ``MaskedAutoencoderViT.decode_to_images``); every FLOP runs in
+libldmae_b200.so.  ``bench.py`` times this call (device-resident inputs for ``value``; pinned host inputs and
+the uint8 image read-back for ``e2e``); multi-GPU sampling shards the (z, y) batch by rank exactly like
+inference.py:87,266-274 -- one process per GPU, no collective inside the loop.
+"""
+from __future__ import annotations
+
+import torch
+
+from .transport import Sampler, create_transport
+
+
+class SamplingJob:
+    """One rank's sampler + decoder with persistent device / pinned buffers for a fixed batch size."""
+
+    def __init__(self, model, vae, *, num_steps=250, sampling_method="euler", cfg_scale=10.0, cfg_interval_start=0.10,
+                 timestep_shift=0.3, latent_mean=None, latent_std=None, latent_multiplier=1.0, device=None):
+        self.model, self.vae = model, vae
+        self.device = torch.device(device) if device is not None else next(model.parameters()).device
+        self.cfg_scale = float(cfg_scale)
+        self.use_cfg = self.cfg_scale > 1.0                      # inference.py:173,278-285
+        self.cfg_interval_start = cfg_interval_start
+        self.null_class = model.y_embedder.num_classes           # inference.py:279 (hard-coded 1000 there)
+        transport = create_transport("Linear", "velocity", None, None, None, use_cosine_loss=False, use_lognorm=True)
+        self.sample_fn = Sampler(transport).sample_ode(sampling_method=sampling_method, num_steps=num_steps, atol=1e-6,
+                                                       rtol=1e-3, reverse=False, timestep_shift=timestep_shift)
+        C = model.in_channels
+        self.latent_mean = latent_mean if latent_mean is not None else torch.zeros(1, C, 1, 1)
+        self.latent_std = latent_std if latent_std is not None else torch.ones(1, C, 1, 1)
+        self.latent_mean = self.latent_mean.to(self.device)
+        self.latent_std = self.latent_std.to(self.device)
+        self.latent_multiplier = float(latent_multiplier)
+        self.model_evals = num_steps - 1                         # N grid points = N-1 model evaluations (integrators.py:94)
+
+    # -- device-resident path ------------------------------------------------------------------
+    def sample_latents(self, z, y):
+        """z [n,C,S,S] fp32, y [n] int64 on the device -> final normalised latents [n,C,S,S] (inference.py:278-289)."""
+        n = z.shape[0]
+        if self.use_cfg:
+            zz = torch.cat([z, z], 0)
+            yy = torch.cat([y, torch.full((n,), self.null_class, device=y.device, dtype=y.dtype)], 0)
+            kw = dict(y=yy, cfg_scale=self.cfg_scale)
+            if self.cfg_interval_start is not None:
+                kw.update(cfg_interval=True, cfg_interval_start=self.cfg_interval_start)
+            out = self.sample_fn(zz, self.model.forward_with_cfg, **kw)[-1]
+            return out.chunk(2, dim=0)[0]
+        return self.sample_fn(z, self.model.forward, y=y)[-1]
+
+    def decode_u8(self, latents):
+        """normalised latents -> uint8 [n,H,W,3] on the device (inference.py:291-292 without the host copy)."""
+        _, u8 = self.vae._decode(latents, False, True, self.latent_mean, self.latent_std, self.latent_multiplier)
+        return u8
+
+    def run_device(self, z, y):
+        return self.decode_u8(self.sample_latents(z, y))
+
+    # -- host-to-host path (what inference.py does per iteration) --------------------------------
+    def run_host(self, z_host, y_host, out_host=None):
+        """Pinned host z / y in, uint8 images out on the host (pinned ``out_host`` is reused when given)."""
+        z = z_host.to(self.device, non_blocking=True)
+        y = y_host.to(self.device, non_blocking=True)
+        u8 = self.run_device(z, y)
+        if out_host is None:
+            out_host = torch.empty(u8.shape, dtype=torch.uint8, pin_memory=True)
+        out_host.copy_(u8, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return out_host
+
+
+def build_sampling_models(device, *, model_name="LightningDiT-B/1", input_size=32, in_channels=16, img_size=256, seed=0,
+                          num_classes=1000):
+    """Random-init LightningDiT + VMAE decoder of the shipped recipe (configs/imagenet/lightningdit_b_vmae_f8d16_cfg.yaml).
+    The reference zero-initialises final_layer.linear and every adaLN_modulation[-1] (lightningdit.py:365-374), which
+    makes a freshly constructed model output exactly 0; those tensors are re-drawn N(0, 0.02) so the synthetic
+    benchmark exercises non-trivial numerics."""
+    from .models.lightningdit import LightningDiT_models
+    from .tokenizer import models_mae
+    torch.manual_seed(seed)
+    model = LightningDiT_models[model_name](input_size=input_size, num_classes=num_classes, use_qknorm=True, use_swiglu=True,
+                                            use_rope=True, use_rmsnorm=True, wo_shift=False, in_channels=in_channels)
+    g = torch.Generator().manual_seed(1234)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if "adaLN_modulation.1" in name or name.startswith("final_layer.linear"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+    vae = models_mae.mae_for_ldmae_f8d16_prev(ldmae_mode=True, no_cls=True, kl_loss_weight=True, smooth_output=True,
+                                              img_size=img_size)
+    return model.to(device).eval(), vae.to(device).eval()

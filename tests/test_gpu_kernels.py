@@ -29,7 +29,7 @@ GEMM_SHAPES = [
 @pytest.mark.parametrize("cfg", [(1, 128), (1, 256), (2, 256)])
 @pytest.mark.parametrize("shape", GEMM_SHAPES)
 def test_gemm_bias_fp32_out(shape, cfg):
-    from tests.gpu_util import gemm_bias, rel_err
+    from gpu_util import gemm_bias, rel_err
     M, N, K = shape
     cg, bn = cfg
     g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
@@ -44,7 +44,7 @@ def test_gemm_bias_fp32_out(shape, cfg):
 
 @pytest.mark.parametrize("act", [0, 1])
 def test_gemm_bias_bf16_out_and_gelu(act):
-    from tests.gpu_util import gemm_bias, rel_err
+    from gpu_util import gemm_bias, rel_err
     M, N, K = 640, 768, 192
     g = torch.Generator().manual_seed(5)
     a = torch.randn(M, K, generator=g).to(torch.bfloat16)
@@ -59,7 +59,7 @@ def test_gemm_bias_bf16_out_and_gelu(act):
 
 @pytest.mark.parametrize("B,T,H,scale", [(2, 1024, 3, 0.125), (3, 64, 2, 0.125), (1, 320, 2, 0.25), (2, 256, 1, 0.125)])
 def test_attention_matches_softmax(B, T, H, scale):
-    from tests.gpu_util import attention, rel_err
+    from gpu_util import attention, rel_err
     g = torch.Generator().manual_seed(B * 100 + T)
     qkv = (torch.randn(B * T, 3 * H * 64, generator=g) * 1.5).to(torch.bfloat16)
     q, k, v = qkv.float().reshape(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
