@@ -124,6 +124,13 @@ int ldmae_vmae_decode(ldmae_vmae* h, const float* z, const float* mean, const fl
  * act: 0 none, 1 gelu(erf).  cta_group: 1 or 2.  block_n: 128 or 256. */
 int ldmae_gemm_bias(const void* a_bf16, const void* w_bf16, const float* bias, void* out, int32_t out_is_bf16,
                     int32_t M, int32_t N, int32_t K, int32_t act, int32_t cta_group, int32_t block_n, void* stream);
+/* Fused residual GEMM (the LightningDiT block's out-projection / w3 epilogue, models/lightningdit.py:248-249):
+ *   x[M,N] (fp32, in place) += gate[b,:] * (a . w^T + bias),  b = row / rows_per_sample, gate [M/rows_per_sample, N] or NULL;
+ *   optionally anext[M,N] (bf16) = x_new * gnext[b,:] and ssq[M, ceil(N/128)] = partial sums of x_new^2 (slot = 128-column
+ *   group of the producing tile; unused slots are 0).  N must be a multiple of 4. */
+int ldmae_gemm_residual(const void* a_bf16, const void* w_bf16, const float* bias, const float* gate, const float* gnext,
+                        float* x, void* anext_bf16, float* ssq, int32_t M, int32_t N, int32_t K, int32_t rows_per_sample,
+                        void* stream);
 /* softmax(q k^T * scale) v over qkv [B*T, 3*H*64] bf16 (columns q|k|v, head-major) -> out [B*T, H*64] bf16. */
 int ldmae_attention(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t T, int32_t H, float scale, void* stream);
 /* float <-> bf16 conversion helpers for tests (device, n elements) */

@@ -50,6 +50,7 @@ SYMBOLS = {
     "ldmae_vmae_finalize": (C.c_int, [vp, vp]),
     "ldmae_vmae_decode": (C.c_int, [vp, vp, vp, vp, f32, vp, vp, i32, vp]),
     "ldmae_gemm_bias": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "ldmae_gemm_residual": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "ldmae_attention": (C.c_int, [vp, vp, i32, i32, i32, f32, vp]),
     "ldmae_f32_to_bf16": (C.c_int, [vp, vp, i64, vp]),
     "ldmae_launch_count": (C.c_longlong, []),

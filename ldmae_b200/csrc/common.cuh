@@ -61,14 +61,26 @@ struct DevBuf {
 
 int device_sm_count();
 
-// 2-D bf16 row-major [rows, cols] (leading dimension ld elements) -> tensor map with a
-// {64 x box_rows} box and 128-byte swizzle.  Cached by (ptr, rows, cols, ld, box_rows).
-int make_tmap_bf16(CUtensorMap* out, const void* ptr, int rows, int cols, int ld, int box_rows);
+// 2-D row-major [rows, cols] (leading dimension ld elements) tensor map with a {box_cols x box_rows} box.
+// elem_bytes 2 = bf16, 4 = fp32; swizzle_bytes 128 / 64 (box_cols * elem_bytes must not exceed it).  Cached.
+int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, int rows, int cols, int ld, int box_cols, int box_rows,
+                 int swizzle_bytes);
+// bf16 operand tiles: {64 x box_rows} box, 128-byte swizzle
+inline int make_tmap_bf16(CUtensorMap* out, const void* ptr, int rows, int cols, int ld, int box_rows) {
+  return make_tmap_2d(out, ptr, 2, rows, cols, ld, 64, box_rows, 128);
+}
+// epilogue staging tiles (32 rows x 128 bytes, 128-byte swizzle)
+inline int make_tmap_out_bf16(CUtensorMap* out, const void* ptr, int rows, int cols, int ld) {
+  return make_tmap_2d(out, ptr, 2, rows, cols, ld, 64, 32, 128);
+}
+inline int make_tmap_out_f32(CUtensorMap* out, const void* ptr, int rows, int cols, int ld) {
+  return make_tmap_2d(out, ptr, 4, rows, cols, ld, 32, 32, 128);
+}
 
 template <int BN, int CG, class Epi>
 int launch_gemm(const void* a, int lda, const void* w, int ldw, GemmShape g, const typename Epi::Params& ep,
                 cudaStream_t st) {
-  using Cfg = GemmCfg<BN, CG>;
+  using Cfg = GemmCfg<BN, CG, Epi>;
   LDMAE_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty shape %d %d %d", g.M, g.N, g.K);
   LDMAE_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, "gemm: leading dimensions must be multiples of 8 (16-byte TMA strides)");
   CUtensorMap ta, tw;
@@ -88,7 +100,7 @@ int launch_gemm(const void* a, int lda, const void* w, int ldw, GemmShape g, con
   if (total < clusters) clusters = total;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(clusters * CG));
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3(gemm_threads<Epi>());
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

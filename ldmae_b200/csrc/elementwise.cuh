@@ -119,6 +119,29 @@ small_linear_kernel(float* __restrict__ out, const float* __restrict__ in, const
   }
 }
 
+// Compact axial RoPE table for the QKV epilogue, from the reference's persistent buffers freqs_cos / freqs_sin [G*G, 64]
+// (models/pos_embed.py:96-133): dims 0..31 rotate with the token's row h, dims 32..63 with its column w, adjacent
+// pairs share an angle.  tab[axis][pos][0..15] = cos, [16..31] = sin.
+__global__ void rope_compact_kernel(float* __restrict__ tab, const float* __restrict__ cosf_, const float* __restrict__ sinf_, int G) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * G * 32) return;
+  const int f = i % 16, is_sin = (i / 16) % 2, pos = (i / 32) % G, axis = i / (32 * G);
+  const int tok = axis == 0 ? pos * G : pos;
+  const int d = axis * 32 + 2 * f;
+  tab[i] = (is_sin ? sinf_ : cosf_)[static_cast<size_t>(tok) * 64 + d];
+}
+// max |full table - table rebuilt from the compact one| (atomicMax on the bit pattern of a non-negative float)
+__global__ void rope_check_kernel(float* __restrict__ maxdiff, const float* __restrict__ tab, const float* __restrict__ cosf_,
+                                  const float* __restrict__ sinf_, int G) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(G) * G * 64) return;
+  const int d = i % 64, tok = i / 64;
+  const int axis = d / 32, pos = axis == 0 ? tok / G : tok % G, f = (d % 32) / 2;
+  const float* row = tab + (static_cast<size_t>(axis) * G + pos) * 32;
+  const float e = fmaxf(fabsf(cosf_[i] - row[f]), fabsf(sinf_[i] - row[16 + f]));
+  atomicMax(reinterpret_cast<int*>(maxdiff), __float_as_int(e));
+}
+
 // sc = bf16(silu(c))  -- operand of every adaLN_modulation Linear (lightningdit.py:228-236,263-266)
 __global__ void silu_to_bf16_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ in, size_t n) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;

@@ -4,14 +4,18 @@
 //   warp 0      TMA producer: cp.async.bulk.tensor tiles (128B swizzle) into a kStages-deep smem ring
 //   warp 1      MMA issuer:   one elected thread issues tcgen05.mma (kind::f16, fp32 accumulate in TMEM)
 //   warp 2      TMEM allocator
-//   warps 4..7  epilogue:     tcgen05.ld the accumulator (one row per thread), fused epilogue, coalesced stores
+//   warps 4..7  epilogue:     thread = one accumulator row (tcgen05.ld 32x32b), fused math in registers, results
+//                             staged in warp-private 128B-swizzled smem tiles and written with TMA stores
+//                             (operands the epilogue must read, i.e. the fp32 residual stream, arrive by TMA too)
 //
 // kCG = 2 pairs two CTAs (cta_group::2, UMMA M = 256): each CTA loads its own 128 rows of A and half of
 // the W tile, the leader CTA issues the MMAs for both, the accumulator rows of each CTA live in its own
 // TMEM.  Two accumulator stages in TMEM overlap the epilogue of tile i with the main loop of tile i+1.
 //
 // The fused epilogues implement the LightningDiT block algebra (reference models/lightningdit.py:239-250):
-// see struct comments below.
+// see struct comments below.  With a row per thread, a 32-row x 128-byte staging tile in the TMA 128B-swizzle
+// layout is written / read with conflict-free 16-byte shared-memory accesses (chunk index XOR row%8), and all
+// global traffic of the epilogue is full-line TMA bulk traffic.
 #pragma once
 #include "ptx.cuh"
 
@@ -19,182 +23,74 @@ namespace ldmae {
 
 constexpr int kBM = 128;        // rows per CTA
 constexpr int kBK = 64;         // K per stage = one 128-byte swizzle atom of bf16
-constexpr int kGemmThreads = 256;
-constexpr int kStageWords = 32 * 66;   // per-epilogue-warp staging: 32 rows x (64+2) fp32
+// CTA = 4 control warps (TMA, MMA, TMEM alloc, spare) + Epi::kWarps epilogue warps (4 or 8; with 8 the two groups of
+// four split the tile's columns, which doubles the issue slots and the latency hiding of math-heavy epilogues)
+template <class Epi>
+constexpr int gemm_threads() { return 128 + 32 * Epi::kWarps; }
+constexpr int kSmemLimit = 232448;   // 227 KB opt-in shared memory per CTA
 
 struct GemmShape {
   int M, N, K;
 };
 
-template <int BN, int CG>
+// which tiles this CTA works on, and where this epilogue warp's rows are
+struct TileSched {
+  int first, stride, total, n_tiles, cg, cta_rank, wq;
+  template <int BN>
+  __device__ __forceinline__ void coords(int tile, int& row0, int& n0) const {
+    row0 = ((tile / n_tiles) * cg + cta_rank) * kBM + wq * 32;
+    n0 = (tile % n_tiles) * BN;
+  }
+};
+struct EpiCtx {
+  uint8_t* smem;     // this warp's staging area (1024-byte aligned, Epi::kWarpBytes)
+  uint8_t* cta;      // CTA-wide epilogue area (Epi::kCtaBytes), filled by Epi::cta_init before the role split
+  uint64_t* bars;    // this warp's mbarriers (Epi::kBars)
+  int lane;
+};
+
+template <int BN, int CG, class Epi>
 struct GemmCfg {
   static constexpr int kLoadBN = BN / CG;                     // W rows loaded by each CTA
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = kLoadBN * kBK * 2;
   static constexpr int kBBytesPadded = (kBBytes + 1023) / 1024 * 1024;
   static constexpr int kStageBytes = kABytes + kBBytesPadded;
-  static constexpr int kEpiBytes = 4 * kStageWords * 4;
-  static constexpr int kBudget = 225 * 1024 - kEpiBytes - 1024 /*align slack*/ - 512 /*barriers*/;
+  static constexpr int kGroups = (Epi::kWarps == 8 && BN >= 256) ? 2 : 1;   // column groups of epilogue warps at work
+  static constexpr int kGroupCols = BN / kGroups;
+  static constexpr int kEpiBytes = Epi::kWarps * Epi::kWarpBytes + Epi::kCtaBytes;
+  static constexpr int kBarBytes = 1024;
+  static constexpr int kBudget = kSmemLimit - kEpiBytes - 1024 /*align slack*/ - kBarBytes;
   static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kEpiBytes + 512;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kEpiBytes + kBarBytes;
+  static_assert(kStages >= 3, "smem ring too shallow");
+  static_assert((2 * kStages + 4 + Epi::kWarps * Epi::kBars) * 8 + 8 <= kBarBytes, "barrier area");
+  static_assert(Epi::kWarpBytes % 1024 == 0 && Epi::kCtaBytes % 1024 == 0, "staging areas must keep the 1024-byte swizzle alignment");
   static_assert(2 * BN <= 512, "two accumulator stages must fit TMEM");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N");
   static_assert(kLoadBN % 8 == 0, "W rows per CTA");
 };
 
 // ---------------------------------------------------------------------------------------------
-// Epilogues.  Contract:  Epi::run(p, acc_taddr, row0, n0, wq, lane, stage)
-//   acc_taddr : TMEM address of this warp's 32 lanes, column 0 of the accumulator stage
-//   row0      : global row of this warp's lane 0;   n0 : first global column of the tile
-//   stage     : this warp's private smem staging (kStageWords floats)
-// Thread `lane` owns accumulator row (row0 + lane) in the "row phase"; in the "column phase"
-// the warp walks rows and lanes own columns, which makes global accesses 128-byte coalesced.
+// Epilogue building blocks
 // ---------------------------------------------------------------------------------------------
-
-// out[M,N] (bf16 or fp32) = act(acc + bias[col]);  used for adaLN, the per-sample shift vectors,
-// and the VMAE linears (fc1: GELU-erf).
-template <typename OutT, int ACT /*0 none, 1 gelu-erf, 2 gelu-tanh*/>
-struct EpiStore {
-  struct Params {
-    OutT* out;
-    const float* bias;   // [N] or nullptr
-    int ldo;             // leading dimension of out (elements)
-  };
-  template <int BN>
-  static __device__ __forceinline__ void run(const Params& p, const GemmShape& g, uint32_t acc, int row0, int n0,
-                                             int lane, float* stage) {
-    constexpr bool kBf16 = sizeof(OutT) == 2;
-    constexpr int kChunk = kBf16 ? 64 : 32;            // accumulator columns per staged block (32 words/row)
-    static_assert(BN % kChunk == 0, "EpiStore: tile width must be a multiple of the staged chunk");
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += kChunk) {
-      if (n0 + c0 >= g.N) break;
-      float v[kChunk];
-      tmem_ld32(acc + c0, v);
-      if constexpr (kChunk == 64) tmem_ld32(acc + c0 + 32, v + 32);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < kChunk; ++j) {
-        const int col = n0 + c0 + j;
-        float b = (p.bias != nullptr && col < g.N) ? __ldg(p.bias + col) : 0.f;
-        float x = v[j] + b;
-        if constexpr (ACT == 1) x = gelu_erf_f(x);
-        if constexpr (ACT == 2) x = gelu_tanh_f(x);
-        v[j] = x;
-      }
-      uint32_t* sw = reinterpret_cast<uint32_t*>(stage);
-      if constexpr (kBf16) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) sw[lane * 33 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) sw[lane * 33 + j] = __float_as_uint(v[j]);
-      }
-      __syncwarp();
-      // column phase: one row per iteration, lane = word
-      const int colw = n0 + c0 + (kBf16 ? 2 * lane : lane);
-#pragma unroll 4
-      for (int r = 0; r < 32; ++r) {
-        const int row = row0 + r;
-        if (row < g.M && colw < g.N) {
-          uint32_t w = sw[r * 33 + lane];
-          if constexpr (kBf16)
-            *reinterpret_cast<uint32_t*>(p.out + static_cast<size_t>(row) * p.ldo + colw) = w;
-          else
-            p.out[static_cast<size_t>(row) * p.ldo + colw] = __uint_as_float(w);
-        }
-      }
-      __syncwarp();
-    }
-  }
-};
-
-// Residual update of the fp32 token stream, fused with the *next* norm's operand preparation:
-//   x[row,col] += gate[b,col] * (acc + bias[col])                      (lightningdit.py:248-249)
-//   anext[row,col] = bf16( x_new * gnext[b,col] )   with gnext = norm.weight * (1 + scale_b)
-//   ssq[row, tile] = sum_{col in tile} x_new^2       (RMSNorm statistics, models/rmsnorm.py:63)
-// so that  modulate(RMSNorm(x)) . W^T  ==  rsqrt(ssq/D+eps) * (anext . W^T) + shift_b . W^T  is finished in
-// the next GEMM's epilogue without another pass over x.  gate/gnext/ssq/anext are optional (VMAE
-// uses the plain residual).  b = row / rows_per_sample.
-struct EpiResidual {
-  struct Params {
-    float* x;              // [M, ldx] fp32, read-modify-write
-    const float* bias;     // [N]
-    const float* gate;     // [B, gate_ld] or nullptr (=> 1)
-    const float* gnext;    // [B, gnext_ld] or nullptr
-    __nv_bfloat16* anext;  // [M, ldx] or nullptr
-    float* ssq;            // [M, ss_slots] per-row partial sums of squares, or nullptr.  Slot = column/128 of the
-                           // producing tile: no atomics, so the statistics are bit-reproducible.
-    int ldx, gate_ld, gnext_ld, rows_per_sample, ss_slots;
-  };
-  template <int BN>
-  static __device__ __forceinline__ void run(const Params& p, const GemmShape& g, uint32_t acc, int row0, int n0,
-                                             int lane, float* stage) {
-    float ss[32];
-#pragma unroll
-    for (int r = 0; r < 32; ++r) ss[r] = 0.f;
-    const int my_row = row0 + lane;
-    const int my_b = (my_row < g.M ? my_row : g.M - 1) / p.rows_per_sample;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (n0 + c0 >= g.N) break;
-      float v[32];
-      tmem_ld32(acc + c0, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int col = n0 + c0 + j;
-        if (col < g.N) {
-          float y = v[j] + __ldg(p.bias + col);
-          if (p.gate != nullptr) y *= __ldg(p.gate + static_cast<size_t>(my_b) * p.gate_ld + col);
-          v[j] = y;
-        }
-        stage[lane * 33 + j] = v[j];
-      }
-      __syncwarp();
-      const int col = n0 + c0 + lane;
-      const bool col_ok = col < g.N;
-#pragma unroll
-      for (int r = 0; r < 32; ++r) {
-        const int row = row0 + r;
-        if (row >= g.M) break;                                   // warp-uniform
-        const size_t off = static_cast<size_t>(row) * p.ldx + (col_ok ? col : 0);
-        float xn = 0.f;
-        if (col_ok) {
-          xn = p.x[off] + stage[r * 33 + lane];
-          p.x[off] = xn;
-          ss[r] += xn * xn;
-        }
-        if (p.anext != nullptr) {                                // warp-uniform
-          const int b = row / p.rows_per_sample;
-          const float a = col_ok ? xn * __ldg(p.gnext + static_cast<size_t>(b) * p.gnext_ld + col) : 0.f;
-          const float a_hi = __shfl_down_sync(0xffffffffu, a, 1);
-          if (col_ok && (lane & 1) == 0)
-            *reinterpret_cast<uint32_t*>(p.anext + off) = pack_bf16x2(a, a_hi);
-        }
-      }
-      __syncwarp();
-    }
-    if (p.ssq != nullptr) {
-#pragma unroll
-      for (int r = 0; r < 32; ++r) {
-        float s = ss[r];
-        s += __shfl_xor_sync(0xffffffffu, s, 16);
-        s += __shfl_xor_sync(0xffffffffu, s, 8);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        if (lane == 0 && row0 + r < g.M) {
-          float* dst = p.ssq + static_cast<size_t>(row0 + r) * p.ss_slots + n0 / 128;
-          dst[0] = s;
-          if (BN > 128 && n0 / 128 + 1 < p.ss_slots) dst[1] = 0.f;
-        }
-      }
-    }
-  }
-};
+// 4 consecutive entries of a per-column vector (bias, gate, ...); columns >= N read as 0.
+__device__ __forceinline__ float4 ldvec4(const float* __restrict__ base, int col, int N) {
+  const float* p = base + col;
+  if (col + 3 < N && (reinterpret_cast<uintptr_t>(p) & 15) == 0) return __ldg(reinterpret_cast<const float4*>(p));
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < N) r.x = __ldg(p);
+  if (col + 1 < N) r.y = __ldg(p + 1);
+  if (col + 2 < N) r.z = __ldg(p + 2);
+  if (col + 3 < N) r.w = __ldg(p + 3);
+  return r;
+}
+// 16-byte chunk `j` (0..7) of row `r` inside a [32 x 128 B] tile in TMA SWIZZLE_128B layout (tile 1024-B aligned)
+__device__ __forceinline__ uint8_t* sw128_chunk(uint8_t* tile, int r, int j) { return tile + r * 128 + ((j ^ (r & 7)) << 4); }
+// 16-byte chunk `j` (0..3) of row `r` inside a [32 x 64 B] tile in TMA SWIZZLE_64B layout (tile 512-B aligned)
+__device__ __forceinline__ uint8_t* sw64_chunk(uint8_t* tile, int r, int j) { return tile + r * 64 + ((j ^ ((r >> 1) & 3)) << 4); }
 
 // rsqrt(mean(x^2) + eps) of a residual-stream row from its per-tile partial sums (fixed summation order)
 __device__ __forceinline__ float row_rinv(const float* ssq, int row, int slots, float inv_D, float eps) {
@@ -204,100 +100,418 @@ __device__ __forceinline__ float row_rinv(const float* ssq, int row, int slots, 
   return rsqrtf(s * inv_D + eps);
 }
 
+// Per-column vectors (bias, gate, cvec ...) are staged once per tile in this warp's shared memory and read back as
+// broadcasts: with the whole shared-memory carve-out taken, L1 is a few KB and every __ldg would be an L2 round trip.
+// dst[i] = src[col0 + i] for i < ncols (0 beyond N).  ncols is a multiple of 4.
+__device__ __forceinline__ void stage_vec(float* dst, const float* __restrict__ src, int col0, int ncols, int N, int lane) {
+  for (int i = lane * 4; i < ncols; i += 128) *reinterpret_cast<float4*>(dst + i) = ldvec4(src, col0 + i, N);
+}
+__device__ __forceinline__ float4 lds_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// all rows of this warp (row0 .. row0+31, clipped to M) belong to one sample?
+__device__ __forceinline__ bool warp_rows_one_sample(int row0, int M, int rows_per_sample) {
+  const int last = min(row0 + 31, M - 1);
+  return row0 < M && row0 / rows_per_sample == last / rows_per_sample;
+}
+
+// Output staging shared by the store-only epilogues: two 4 KB tiles per warp (one TMA store per 32 rows x 128 B)
+// followed by 2 KB for staged per-column vectors.
+struct StoreRing {
+  static constexpr int kWarpBytes = 2 * 4096 + 2048;
+  static constexpr int kVecOff = 2 * 4096;
+  static constexpr int kBars = 0;
+  static constexpr int kCtaBytes = 0;
+  static constexpr int kWarps = 8;
+  template <class P>
+  static __device__ __forceinline__ void cta_init(const P&, uint8_t*, int, int) {}
+  struct State { int seq; };
+  static __device__ __forceinline__ uint8_t* acquire(const EpiCtx& c, State& st) {
+    if (c.lane == 0) tma_store_wait_read<1>();         // the store issued two chunks ago no longer reads its tile
+    __syncwarp();
+    return c.smem + (st.seq & 1) * 4096;
+  }
+  static __device__ __forceinline__ void release(const EpiCtx& c, State& st, const CUtensorMap* map, uint8_t* tile, int col,
+                                                 int row) {
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (c.lane == 0) {
+      tma_store_2d(map, tile, col, row);
+      tma_store_commit();
+    }
+    ++st.seq;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Epilogues.  Contract (GC = columns of the tile this warp's group works on, cbase = first of them):
+//   cta_init(p, cta_smem, tid, nthreads)                        all threads of the CTA, before the role split
+//   begin<BN>(p, g, sched, ctx, st)                             once per epilogue warp before the first tile
+//   run<BN,GC>(p, g, sched, ctx, st, acc_taddr, row0, n0, cbase) per tile; acc_taddr = TMEM address of this warp's 32
+//                                                               lanes, column 0 of the accumulator stage; thread `lane`
+//                                                               owns row row0+lane
+//   end(ctx, st)                                                once per warp after the last tile (drains TMA stores)
+// ---------------------------------------------------------------------------------------------
+
+// out[M,N] (bf16 or fp32) = act(acc + bias[col]);  used for adaLN, the per-sample shift vectors and the VMAE linears.
+template <typename OutT, int ACT /*0 none, 1 gelu-erf, 2 gelu-tanh*/>
+struct EpiStore : StoreRing {
+  struct Params {
+    CUtensorMap omap;    // out [M, N]: box {64 bf16 | 32 fp32, 32 rows}, SWIZZLE_128B
+    const float* bias;   // [N] or nullptr
+  };
+  static __device__ __forceinline__ void prefetch_maps(const Params& p) { tma_prefetch_desc(&p.omap); }
+  template <int BN>
+  static __device__ __forceinline__ void begin(const Params&, const GemmShape&, const TileSched&, const EpiCtx&, State& st) {
+    st.seq = 0;
+  }
+  template <int BN, int GC>
+  static __device__ __forceinline__ void run(const Params& p, const GemmShape& g, const TileSched&, const EpiCtx& c, State& st,
+                                             uint32_t acc, int row0, int n0, int cbase) {
+    constexpr bool kBf16 = sizeof(OutT) == 2;
+    constexpr int kChunk = kBf16 ? 64 : 32;            // accumulator columns per 128-byte output row
+    static_assert(GC % kChunk == 0 && GC <= 512, "EpiStore: group width must be a multiple of the staged chunk");
+    float* vb = reinterpret_cast<float*>(c.smem + kVecOff);
+    if (p.bias != nullptr) {
+      stage_vec(vb, p.bias, n0 + cbase, GC, g.N, c.lane);
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (int c0 = cbase; c0 < cbase + GC; c0 += kChunk) {
+      if (n0 + c0 >= g.N) break;
+      uint8_t* tile = acquire(c, st);
+      float v[kChunk];
+      tmem_ld32(acc + c0, v);
+      if constexpr (kChunk == 64) tmem_ld32(acc + c0 + 32, v + 32);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < kChunk; j += 4) {
+        if (p.bias != nullptr) {
+          const float4 b = lds_f4(vb + (c0 - cbase) + j);
+          v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        }
+        if constexpr (ACT == 1) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) v[j + q] = gelu_erf_f(v[j + q]);
+        }
+        if constexpr (ACT == 2) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) v[j + q] = gelu_tanh_f(v[j + q]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        uint4 w;
+        if constexpr (kBf16) {
+          w = make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                         pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+        } else {
+          w = make_uint4(__float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]),
+                         __float_as_uint(v[4 * q + 3]));
+        }
+        sts128(sw128_chunk(tile, c.lane, q), w);
+      }
+      release(c, st, &p.omap, tile, n0 + c0, row0);
+    }
+  }
+  static __device__ __forceinline__ void end(const EpiCtx& c, State&) {
+    if (c.lane == 0) tma_store_wait_read<0>();
+  }
+};
+
+// Residual update of the fp32 token stream, fused with the *next* norm's operand preparation:
+//   x[row,col] += gate[b,col] * (acc + bias[col])                      (lightningdit.py:248-249)
+//   anext[row,col] = bf16( x_new * gnext[b,col] )   with gnext = norm.weight * (1 + scale_b)
+//   ssq[row, tile] = sum_{col in tile} x_new^2       (RMSNorm statistics, models/rmsnorm.py:63)
+// so that  modulate(RMSNorm(x)) . W^T  ==  rsqrt(ssq/D+eps) * (anext . W^T) + shift_b . W^T  is finished in
+// the next GEMM's epilogue without another pass over x.  gate/gnext/ssq/anext are optional (VMAE uses the plain
+// residual).  b = row / rows_per_sample.
+// x travels by TMA in 32-row x 32-column fp32 boxes: loaded kPF chunks ahead (across tile boundaries, i.e. while
+// the tensor core still works on the tile), updated in place in shared memory and stored back from the same tile.
+// This epilogue is HBM-bound (12 bytes per accumulator element), so four warps suffice.
+struct EpiResidual {
+  static constexpr int kWarps = 4;
+  static constexpr int kCtaBytes = 0;
+  static constexpr int kNX = 4;     // x tiles in flight per warp
+  static constexpr int kPF = 2;     // prefetch distance (chunks)
+  static constexpr int kXBytes = 4096, kABytesTile = 2048;
+  static constexpr int kVecOff = kNX * kXBytes + 2 * kABytesTile;      // [3][256] floats: bias, gate, gnext of the tile
+  static constexpr int kWarpBytes = kVecOff + 4096;
+  static constexpr int kBars = kNX;
+  struct Params {
+    CUtensorMap xmap;      // x [M, N] fp32: box {32, 32}, SWIZZLE_128B (loads and stores)
+    CUtensorMap amap;      // anext [M, N] bf16: box {32, 32}, SWIZZLE_64B (stores); unused when !has_anext
+    const float* bias;     // [N]
+    const float* gate;     // [B, gate_ld] or nullptr (=> 1)
+    const float* gnext;    // [B, gnext_ld] (has_anext)
+    float* ssq;            // [M, ss_slots] per-row partial sums of squares, or nullptr.  Slot = column/128 of the
+                           // producing tile: no atomics, so the statistics are bit-reproducible.
+    int gate_ld, gnext_ld, rows_per_sample, ss_slots, has_anext;
+  };
+  struct State { int seq, pf_seq, pf_tile, pf_chunk; };
+  template <class P>
+  static __device__ __forceinline__ void cta_init(const P&, uint8_t*, int, int) {}
+  static __device__ __forceinline__ void prefetch_maps(const Params& p) {
+    tma_prefetch_desc(&p.xmap);
+    if (p.has_anext) tma_prefetch_desc(&p.amap);
+  }
+  // issue the x loads of every chunk with sequence number <= upto (lane 0 only; buffers are known to be free)
+  template <int BN>
+  static __device__ __forceinline__ void pump(const Params& p, const GemmShape& g, const TileSched& s, const EpiCtx& c, State& st,
+                                              int upto) {
+    while (st.pf_seq <= upto && st.pf_tile < s.total) {
+      int row0, n0;
+      s.template coords<BN>(st.pf_tile, row0, n0);
+      const int nch = min(BN / 32, (g.N - n0 + 31) / 32);
+      const int b = st.pf_seq % kNX;
+      mbar_expect_tx(&c.bars[b], kXBytes);
+      tma_load_2d(&p.xmap, &c.bars[b], c.smem + b * kXBytes, n0 + st.pf_chunk * 32, row0);
+      ++st.pf_seq;
+      if (++st.pf_chunk == nch) { st.pf_chunk = 0; st.pf_tile += s.stride; }
+    }
+  }
+  template <int BN>
+  static __device__ __forceinline__ void begin(const Params& p, const GemmShape& g, const TileSched& s, const EpiCtx& c, State& st) {
+    st.seq = 0; st.pf_seq = 0; st.pf_tile = s.first; st.pf_chunk = 0;
+    if (c.lane == 0) pump<BN>(p, g, s, c, st, kPF - 1);
+  }
+  template <int BN, int GC>
+  static __device__ __forceinline__ void run(const Params& p, const GemmShape& g, const TileSched& s, const EpiCtx& c, State& st,
+                                             uint32_t acc, int row0, int n0, int /*cbase*/) {
+    static_assert(GC == BN && BN <= 256, "the residual epilogue walks the whole tile width");
+    const int lane = c.lane;
+    const int my_row = row0 + lane;
+    const int my_b = (my_row < g.M ? my_row : g.M - 1) / p.rows_per_sample;
+    const float* gate = p.gate ? p.gate + static_cast<size_t>(my_b) * p.gate_ld : nullptr;
+    const float* gnext = p.has_anext ? p.gnext + static_cast<size_t>(my_b) * p.gnext_ld : nullptr;
+    // one sample per warp (always true when rows_per_sample is a multiple of 32): stage the tile's column vectors
+    const bool staged = warp_rows_one_sample(row0, g.M, p.rows_per_sample);
+    float* vbias = reinterpret_cast<float*>(c.smem + kVecOff);
+    float* vgate = vbias + 256;
+    float* vgnext = vbias + 512;
+    if (staged) {
+      stage_vec(vbias, p.bias, n0, BN, g.N, lane);
+      if (gate != nullptr) stage_vec(vgate, gate, n0, BN, g.N, lane);
+      if (gnext != nullptr) stage_vec(vgnext, gnext, n0, BN, g.N, lane);
+      __syncwarp();
+    }
+    float ss = 0.f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= g.N) break;
+      if (lane == 0) {
+        tma_store_wait_read<1>();                      // stores issued two chunks ago no longer read their tiles
+        pump<BN>(p, g, s, c, st, st.seq + kPF);
+      }
+      __syncwarp();
+      uint8_t* xt = c.smem + (st.seq % kNX) * kXBytes;
+      uint8_t* at = c.smem + kNX * kXBytes + (st.seq & 1) * kABytesTile;
+      mbar_wait(&c.bars[st.seq % kNX], (st.seq / kNX) & 1, 500);
+      __syncwarp();
+      float v[32];
+      tmem_ld32(acc + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int col = n0 + c0 + 4 * q;
+        const float4 bi = staged ? lds_f4(vbias + c0 + 4 * q) : ldvec4(p.bias, col, g.N);
+        float4 gt = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (gate != nullptr) gt = staged ? lds_f4(vgate + c0 + 4 * q) : ldvec4(gate, col, g.N);
+        uint8_t* xp = sw128_chunk(xt, lane, q);
+        const uint4 xr = lds128(xp);
+        float4 xn;
+        xn.x = __uint_as_float(xr.x) + (v[4 * q] + bi.x) * gt.x;
+        xn.y = __uint_as_float(xr.y) + (v[4 * q + 1] + bi.y) * gt.y;
+        xn.z = __uint_as_float(xr.z) + (v[4 * q + 2] + bi.z) * gt.z;
+        xn.w = __uint_as_float(xr.w) + (v[4 * q + 3] + bi.w) * gt.w;
+        sts128(xp, make_uint4(__float_as_uint(xn.x), __float_as_uint(xn.y), __float_as_uint(xn.z), __float_as_uint(xn.w)));
+        // columns >= N hold zeros (TMA zero fill + zero bias/acc), so they do not disturb the statistics
+        ss = fmaf(xn.x, xn.x, ss); ss = fmaf(xn.y, xn.y, ss); ss = fmaf(xn.z, xn.z, ss); ss = fmaf(xn.w, xn.w, ss);
+        v[4 * q] = xn.x; v[4 * q + 1] = xn.y; v[4 * q + 2] = xn.z; v[4 * q + 3] = xn.w;
+      }
+      if (p.has_anext) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int col = n0 + c0 + 8 * q;
+          const float4 g0 = staged ? lds_f4(vgnext + c0 + 8 * q) : ldvec4(gnext, col, g.N);
+          const float4 g1 = staged ? lds_f4(vgnext + c0 + 8 * q + 4) : ldvec4(gnext, col + 4, g.N);
+          sts128(sw64_chunk(at, lane, q),
+                 make_uint4(pack_bf16x2(v[8 * q] * g0.x, v[8 * q + 1] * g0.y), pack_bf16x2(v[8 * q + 2] * g0.z, v[8 * q + 3] * g0.w),
+                            pack_bf16x2(v[8 * q + 4] * g1.x, v[8 * q + 5] * g1.y), pack_bf16x2(v[8 * q + 6] * g1.z, v[8 * q + 7] * g1.w)));
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&p.xmap, xt, n0 + c0, row0);
+        if (p.has_anext) tma_store_2d(&p.amap, at, n0 + c0, row0);
+        tma_store_commit();
+      }
+      ++st.seq;
+    }
+    if (p.ssq != nullptr && my_row < g.M) {
+      float* dst = p.ssq + static_cast<size_t>(my_row) * p.ss_slots + n0 / 128;
+      dst[0] = ss;
+      if (BN > 128 && n0 / 128 + 1 < p.ss_slots) dst[1] = 0.f;
+    }
+  }
+  static __device__ __forceinline__ void end(const EpiCtx& c, State&) {
+    if (c.lane == 0) tma_store_wait_read<0>();
+  }
+};
+
 // QKV projection of LightningDiT attention (lightningdit.py:68-74) on the pre-scaled operand:
 //   v = acc * rsqrt(ssq[row]/D + eps) + cvec[b,col]        (= Linear(modulate(RMSNorm(x))) incl. bias)
 //   q,k heads: RMSNorm over head_dim (fp32) * weight, then 2-D axial RoPE on adjacent pairs
 //   (models/pos_embed.py:38-42,135); v heads pass through.  Output bf16 [M, 3D], column = (which, head, d).
-// Requires head_dim == 64 (one staged chunk = one head).
-struct EpiQKV {
+// Requires head_dim == 64 (one 128-byte output row = one head).  RoPE angles come from a compact table
+// rope[axis][pos][16 cos | 16 sin] (axis 0 = token row h for dims 0..31, axis 1 = token column w for dims 32..63),
+// derived from the reference's [T, 64] buffers at load time and held in shared memory (row pitch 36 floats:
+// conflict-free 16-byte reads when the lanes of a warp walk consecutive positions).
+struct EpiQKV : StoreRing {
+  static constexpr int kCtaBytes = 10240;
+  static constexpr int kRopePitch = 36;
   struct Params {
-    __nv_bfloat16* out;     // [M, 3D]
+    CUtensorMap omap;       // out [M, 3D] bf16: box {64, 32}, SWIZZLE_128B
     const float* ssq;       // [M, ss_slots] partial sums of squares of the residual-stream row (nullptr: no row scale)
     const float* cvec;      // [B, 3D]  shift_b . W^T + bias
     const float* qw;        // [64] q_norm.weight or nullptr (no qk-norm)
     const float* kw;        // [64]
-    const float* rope_cos;  // [T, 64] or nullptr
-    const float* rope_sin;  // [T, 64]
-    int D, rows_per_sample, ss_slots;
+    const float* rope;      // [2, grid, 32] or nullptr
+    int D, rows_per_sample, ss_slots, grid;
     float inv_D, eps_row, eps_head;
   };
+  static __device__ __forceinline__ bool rope_in_smem(const Params& p) {
+    return p.rope != nullptr && 2 * p.grid * kRopePitch * 4 <= kCtaBytes;
+  }
+  static __device__ __forceinline__ void cta_init(const Params& p, uint8_t* cta, int tid, int nthreads) {
+    if (!rope_in_smem(p)) return;
+    float* dst = reinterpret_cast<float*>(cta);
+    for (int i = tid; i < 2 * p.grid * 32; i += nthreads) dst[(i / 32) * kRopePitch + (i % 32)] = __ldg(p.rope + i);
+  }
+  static __device__ __forceinline__ void prefetch_maps(const Params& p) { tma_prefetch_desc(&p.omap); }
   template <int BN>
-  static __device__ __forceinline__ void run(const Params& p, const GemmShape& g, uint32_t acc, int row0, int n0,
-                                             int lane, float* stage) {
-    static_assert(BN % 64 == 0, "QKV epilogue works on whole 64-wide heads");
+  static __device__ __forceinline__ void begin(const Params&, const GemmShape&, const TileSched&, const EpiCtx&, State& st) {
+    st.seq = 0;
+  }
+  template <int BN, int GC>
+  static __device__ __forceinline__ void run(const Params& p, const GemmShape& g, const TileSched&, const EpiCtx& c, State& st,
+                                             uint32_t acc, int row0, int n0, int cbase) {
+    static_assert(GC % 64 == 0 && GC <= 256, "QKV epilogue works on whole 64-wide heads");
+    const int lane = c.lane;
     const int my_row = min(row0 + lane, g.M - 1);
     const int my_b = my_row / p.rows_per_sample;
+    const int tok = my_row % p.rows_per_sample;
     const float rinv = row_rinv(p.ssq, my_row, p.ss_slots, p.inv_D, p.eps_row);
     const float* cv = p.cvec + static_cast<size_t>(my_b) * g.N;
+    const bool staged = warp_rows_one_sample(row0, g.M, p.rows_per_sample);
+    float* vcv = reinterpret_cast<float*>(c.smem + kVecOff);       // [GC] cvec of this tile / group
+    float* vnw = vcv + 256;                                        // [64 q_norm | 64 k_norm]
+    if (staged) stage_vec(vcv, cv, n0 + cbase, GC, g.N, lane);
+    if (p.qw != nullptr) {
+      if (lane < 16) *reinterpret_cast<float4*>(vnw + lane * 4) = __ldg(reinterpret_cast<const float4*>(p.qw) + lane);
+      else *reinterpret_cast<float4*>(vnw + lane * 4) = __ldg(reinterpret_cast<const float4*>(p.kw) + lane - 16);
+    }
+    __syncwarp();
+    const bool rsm = rope_in_smem(p);
+    const float* rbase = rsm ? reinterpret_cast<const float*>(c.cta) : p.rope;
+    const int rpitch = rsm ? kRopePitch : 32;
+    const float* rope_h = p.rope ? rbase + static_cast<size_t>(tok / p.grid) * rpitch : nullptr;
+    const float* rope_w = p.rope ? rbase + static_cast<size_t>(p.grid + tok % p.grid) * rpitch : nullptr;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 64) {
+    for (int c0 = cbase; c0 < cbase + GC; c0 += 64) {
       const int colbase = n0 + c0;
       if (colbase >= g.N) break;
       const int which = colbase / p.D;                 // 0 q, 1 k, 2 v  (D % 64 == 0 => uniform per chunk)
+      uint8_t* tile = acquire(c, st);
       float v[64];
       tmem_ld32(acc + c0, v);
       tmem_ld32(acc + c0 + 32, v + 32);
       tmem_ld_wait();
       float ms = 0.f;
 #pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        v[j] = fmaf(v[j], rinv, __ldg(cv + colbase + j));
-        ms = fmaf(v[j], v[j], ms);
+      for (int j = 0; j < 64; j += 4) {
+        const float4 cc = staged ? lds_f4(vcv + (c0 - cbase) + j) : ldvec4(cv, colbase + j, g.N);
+        v[j] = fmaf(v[j], rinv, cc.x); v[j + 1] = fmaf(v[j + 1], rinv, cc.y);
+        v[j + 2] = fmaf(v[j + 2], rinv, cc.z); v[j + 3] = fmaf(v[j + 3], rinv, cc.w);
+        ms = fmaf(v[j], v[j], ms); ms = fmaf(v[j + 1], v[j + 1], ms);
+        ms = fmaf(v[j + 2], v[j + 2], ms); ms = fmaf(v[j + 3], v[j + 3], ms);
       }
-      const float* nw = which == 0 ? p.qw : (which == 1 ? p.kw : nullptr);
-      const float hs = (nw != nullptr) ? rsqrtf(ms * (1.f / 64.f) + p.eps_head) : 1.f;
+      if (which < 2 && p.qw != nullptr) {
+        const float hs = rsqrtf(ms * (1.f / 64.f) + p.eps_head);
+        const float* nw = vnw + which * 64;
 #pragma unroll
-      for (int j = 0; j < 64; j += 2)
-        *reinterpret_cast<float2*>(stage + lane * 66 + j) = make_float2(v[j] * hs, v[j + 1] * hs);
-      __syncwarp();
-      // column phase: lane owns the adjacent pair (2*lane, 2*lane+1) = one RoPE pair
-      float w0 = 1.f, w1 = 1.f;
-      if (nw != nullptr) { w0 = __ldg(nw + 2 * lane); w1 = __ldg(nw + 2 * lane + 1); }
-      const bool rope = (which < 2) && (p.rope_cos != nullptr);
-#pragma unroll 4
-      for (int r = 0; r < 32; ++r) {
-        const int row = row0 + r;
-        if (row >= g.M) break;
-        float2 a = *reinterpret_cast<const float2*>(stage + r * 66 + 2 * lane);
-        a.x *= w0; a.y *= w1;
-        if (rope) {
-          const int tok = row % p.rows_per_sample;
-          const float2 c = __ldg(reinterpret_cast<const float2*>(p.rope_cos + static_cast<size_t>(tok) * 64) + lane);
-          const float2 s = __ldg(reinterpret_cast<const float2*>(p.rope_sin + static_cast<size_t>(tok) * 64) + lane);
-          const float ox = a.x * c.x - a.y * s.x;      // t*cos + rotate_half(t)*sin, rotate: (x0,x1)->(-x1,x0)
-          const float oy = a.y * c.y + a.x * s.y;
-          a.x = ox; a.y = oy;
+        for (int j = 0; j < 64; j += 4) {
+          const float4 w4 = lds_f4(nw + j);
+          v[j] *= hs * w4.x; v[j + 1] *= hs * w4.y; v[j + 2] *= hs * w4.z; v[j + 3] *= hs * w4.w;
         }
-        *reinterpret_cast<uint32_t*>(p.out + static_cast<size_t>(row) * g.N + colbase + 2 * lane) = pack_bf16x2(a.x, a.y);
       }
-      __syncwarp();
+      if (which < 2 && rope_h != nullptr) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const float* tab = half == 0 ? rope_h : rope_w;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            float4 cs, sn;
+            if (rsm) { cs = lds_f4(tab + i); sn = lds_f4(tab + 16 + i); }
+            else { cs = __ldg(reinterpret_cast<const float4*>(tab + i)); sn = __ldg(reinterpret_cast<const float4*>(tab + 16 + i)); }
+            const float cq[4] = {cs.x, cs.y, cs.z, cs.w}, sq[4] = {sn.x, sn.y, sn.z, sn.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int d = half * 32 + 2 * (i + q);
+              const float a = v[d], b = v[d + 1];
+              v[d] = a * cq[q] - b * sq[q];             // t*cos + rotate_half(t)*sin, rotate: (x0,x1)->(-x1,x0)
+              v[d + 1] = b * cq[q] + a * sq[q];
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        sts128(sw128_chunk(tile, lane, q),
+               make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                          pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7])));
+      release(c, st, &p.omap, tile, colbase, row0);
     }
+  }
+  static __device__ __forceinline__ void end(const EpiCtx& c, State&) {
+    if (c.lane == 0) tma_store_wait_read<0>();
   }
 };
 
 // SwiGLU first projection (models/swiglu_ffn.py:33-35) on the pre-scaled operand.  The packed weight
 // interleaves w12 rows in groups of 64: [32 rows of x1 | the matching 32 rows of x2], so every 64
 // accumulator columns yield 32 hidden values h = silu(x1) * x2 without leaving the thread.
-struct EpiSwiGLU {
+struct EpiSwiGLU : StoreRing {
   struct Params {
-    __nv_bfloat16* out;   // [M, H]
-    const float* ssq;     // [M]
+    CUtensorMap omap;     // out [M, H] bf16: box {64, 32}, SWIZZLE_128B
+    const float* ssq;     // [M, ss_slots]
     const float* cvec;    // [B, 2H] in the same interleaved column order
-    int H, rows_per_sample, ss_slots;
+    int rows_per_sample, ss_slots;
     float inv_D, eps_row;
   };
+  static __device__ __forceinline__ void prefetch_maps(const Params& p) { tma_prefetch_desc(&p.omap); }
   template <int BN>
-  static __device__ __forceinline__ void run(const Params& p, const GemmShape& g, uint32_t acc, int row0, int n0,
-                                             int lane, float* stage) {
-    static_assert(BN % 128 == 0, "SwiGLU epilogue consumes 128 accumulator columns per staged block");
+  static __device__ __forceinline__ void begin(const Params&, const GemmShape&, const TileSched&, const EpiCtx&, State& st) {
+    st.seq = 0;
+  }
+  template <int BN, int GC>
+  static __device__ __forceinline__ void run(const Params& p, const GemmShape& g, const TileSched&, const EpiCtx& c, State& st,
+                                             uint32_t acc, int row0, int n0, int cbase) {
+    static_assert(GC % 128 == 0 && GC <= 512, "SwiGLU epilogue consumes 128 accumulator columns per staged block");
+    const int lane = c.lane;
     const int my_row = min(row0 + lane, g.M - 1);
     const int my_b = my_row / p.rows_per_sample;
     const float rinv = row_rinv(p.ssq, my_row, p.ss_slots, p.inv_D, p.eps_row);
     const float* cv = p.cvec + static_cast<size_t>(my_b) * g.N;
-    uint32_t* sw = reinterpret_cast<uint32_t*>(stage);
+    const bool staged = warp_rows_one_sample(row0, g.M, p.rows_per_sample);
+    float* vcv = reinterpret_cast<float*>(c.smem + kVecOff);
+    if (staged) {
+      stage_vec(vcv, cv, n0 + cbase, GC, g.N, lane);
+      __syncwarp();
+    }
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 128) {
+    for (int c0 = cbase; c0 < cbase + GC; c0 += 128) {
       if (n0 + c0 >= g.N) break;
+      uint8_t* tile = acquire(c, st);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int cb = c0 + half * 64;
@@ -306,42 +520,52 @@ struct EpiSwiGLU {
         tmem_ld32(acc + cb + 32, v + 32);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 64; ++j) v[j] = fmaf(v[j], rinv, __ldg(cv + n0 + cb + j));
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const float h0 = silu_f(v[j]) * v[32 + j];
-          const float h1 = silu_f(v[j + 1]) * v[32 + j + 1];
-          sw[lane * 33 + half * 16 + (j >> 1)] = pack_bf16x2(h0, h1);
+        for (int j = 0; j < 64; j += 4) {
+          const float4 cc = staged ? lds_f4(vcv + (cb - cbase) + j) : ldvec4(cv, n0 + cb + j, g.N);
+          v[j] = fmaf(v[j], rinv, cc.x); v[j + 1] = fmaf(v[j + 1], rinv, cc.y);
+          v[j + 2] = fmaf(v[j + 2], rinv, cc.z); v[j + 3] = fmaf(v[j + 3], rinv, cc.w);
         }
+        uint32_t w[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2)
+          w[j >> 1] = pack_bf16x2(silu_f(v[j]) * v[32 + j], silu_f(v[j + 1]) * v[32 + j + 1]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          sts128(sw128_chunk(tile, lane, half * 4 + q), make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]));
       }
-      __syncwarp();
-      const int hcol = (n0 + c0) / 2 + 2 * lane;
-#pragma unroll 4
-      for (int r = 0; r < 32; ++r) {
-        const int row = row0 + r;
-        if (row < g.M && hcol < p.H)
-          *reinterpret_cast<uint32_t*>(p.out + static_cast<size_t>(row) * p.H + hcol) = sw[r * 33 + lane];
-      }
-      __syncwarp();
+      release(c, st, &p.omap, tile, (n0 + c0) / 2, row0);
     }
+  }
+  static __device__ __forceinline__ void end(const EpiCtx& c, State&) {
+    if (c.lane == 0) tma_store_wait_read<0>();
   }
 };
 
 // Final layer + unpatchify (lightningdit.py:267-272,376-389): out column = (pi*p + qi)*Cout + c,
 // scattered to NCHW [B, Cstore, grid*p, grid*p]; learn_sigma keeps only the first Cstore channels.
+// N is tiny (p*p*C, e.g. 16): plain coalesced stores (for a fixed output column the 32 lanes = 32 consecutive tokens).
 struct EpiFinal {
+  static constexpr int kWarps = 4;
+  static constexpr int kWarpBytes = 0;
+  static constexpr int kCtaBytes = 0;
+  static constexpr int kBars = 0;
+  struct State { int unused; };
   struct Params {
     float* out;          // [B, Cstore, G*p, G*p]
-    const float* ssq;    // [M]
+    const float* ssq;    // [M, ss_slots]
     const float* cvec;   // [B, N]
     int grid, patch, cout, cstore, rows_per_sample, ss_slots;
     float inv_D, eps_row;
   };
+  template <class P>
+  static __device__ __forceinline__ void cta_init(const P&, uint8_t*, int, int) {}
+  static __device__ __forceinline__ void prefetch_maps(const Params&) {}
   template <int BN>
-  static __device__ __forceinline__ void run(const Params& p, const GemmShape& g, uint32_t acc, int row0, int n0,
-                                             int lane, float* stage) {
-    (void)stage;
-    const int row = row0 + lane;
+  static __device__ __forceinline__ void begin(const Params&, const GemmShape&, const TileSched&, const EpiCtx&, State&) {}
+  template <int BN, int GC>
+  static __device__ __forceinline__ void run(const Params& p, const GemmShape& g, const TileSched&, const EpiCtx& c, State&,
+                                             uint32_t acc, int row0, int n0, int /*cbase*/) {
+    const int row = row0 + c.lane;
     const int rowc = min(row, g.M - 1);
     const int b = rowc / p.rows_per_sample;
     const int tok = rowc % p.rows_per_sample;
@@ -358,39 +582,42 @@ struct EpiFinal {
       for (int j = 0; j < 16; ++j) {
         const int col = n0 + c0 + j;
         if (row < g.M && col < g.N) {
-          const int c = col % p.cout;
+          const int ch = col % p.cout;
           const int pq = col / p.cout;
           const int pi = pq / p.patch, qi = pq % p.patch;
-          if (c < p.cstore) {
+          if (ch < p.cstore) {
             const float val = fmaf(v[j], rinv, __ldg(p.cvec + static_cast<size_t>(b) * g.N + col));
-            p.out[((static_cast<size_t>(b) * p.cstore + c) * HW + (th * p.patch + pi)) * HW + tw * p.patch + qi] = val;
+            p.out[((static_cast<size_t>(b) * p.cstore + ch) * HW + (th * p.patch + pi)) * HW + tw * p.patch + qi] = val;
           }
         }
       }
     }
   }
+  static __device__ __forceinline__ void end(const EpiCtx&, State&) {}
 };
 
 // ---------------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------------
 template <int BN, int CG, class Epi>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(gemm_threads<Epi>(), 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-               const GemmShape g, const typename Epi::Params ep) {
-  using Cfg = GemmCfg<BN, CG>;
+               const GemmShape g, const __grid_constant__ typename Epi::Params ep) {
+  using Cfg = GemmCfg<BN, CG, Epi>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * Cfg::kABytes;
-  float* smem_epi = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);
+  uint8_t* smem_epi = smem + kStages * Cfg::kStageBytes;                       // Epi::kWarps x kWarpBytes, then kCtaBytes
+  uint8_t* smem_cta = smem_epi + Epi::kWarps * Epi::kWarpBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + Cfg::kEpiBytes);
   uint64_t* full_bar = bars;                    // [kStages]  TMA -> MMA   (leader CTA's copy is the live one)
   uint64_t* empty_bar = bars + kStages;         // [kStages]  MMA -> TMA   (each CTA's own copy)
   uint64_t* tfull_bar = bars + 2 * kStages;     // [2]        MMA -> epilogue
   uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]      epilogue -> MMA (leader's copy)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* epi_bar = bars + 2 * kStages + 4;   // [Epi::kWarps * Epi::kBars] epilogue operand loads (per warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_bar + Epi::kWarps * Epi::kBars);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -400,6 +627,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_w);
+    Epi::prefetch_maps(ep);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -408,11 +636,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], CG * 4);
+      mbar_init(&tempty_bar[a], CG * 4 * Cfg::kGroups);
     }
+    for (int i = 0; i < Epi::kWarps * Epi::kBars; ++i) mbar_init(&epi_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<CG>(tmem_slot, Cfg::kTmemCols);
+  Epi::cta_init(ep, smem_cta, threadIdx.x, blockDim.x);
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
@@ -488,20 +718,26 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && (warp - 4) / 4 < Cfg::kGroups) {
     // ===================== epilogue =====================
     const int wq = warp & 3;                                         // TMEM lane quarter of this warp
-    float* stage_buf = smem_epi + wq * kStageWords;
+    const int grp = (warp - 4) / 4;                                  // column group of this warp
+    const int ew = warp - 4;
+    const EpiCtx ctx{smem_epi + ew * Epi::kWarpBytes, smem_cta, epi_bar + ew * Epi::kBars, lane};
+    const TileSched sched{cluster_id, num_clusters, total_tiles, n_tiles, CG, static_cast<int>(cta_rank), wq};
+    typename Epi::State est;
+    Epi::template begin<BN>(ep, g, sched, ctx, est);
     int it = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int m_blk = (tile / n_tiles) * CG + static_cast<int>(cta_rank);
-      const int n_blk = tile % n_tiles;
+      int row0, n0;
+      sched.template coords<BN>(tile, row0, n0);
       mbar_wait(&tfull_bar[as], aphase, 400 + as);
+      __syncwarp();
       tc_fence_after();
       const uint32_t acc = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + as * BN;
-      Epi::template run<BN>(ep, g, acc, m_blk * kBM + wq * 32, n_blk * BN, lane, stage_buf);
+      Epi::template run<BN, Cfg::kGroupCols>(ep, g, sched, ctx, est, acc, row0, n0, grp * Cfg::kGroupCols);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -509,6 +745,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         else mbar_arrive_cluster(&tempty_bar[as], 0);
       }
     }
+    Epi::end(ctx, est);
   }
 
   __syncwarp();      // reconverge the single-lane role warps before the aligned barriers below

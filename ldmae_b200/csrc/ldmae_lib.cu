@@ -33,7 +33,7 @@ long long g_launch_count = 0;
 // Optional per-kernel-class device timing (CUDA events on the launching stream), used by bench.py for the
 // roofline of the dominant kernel.  Classes: 0 qkv GEMM, 1 attention, 2 proj GEMM, 3 w12 (SwiGLU) GEMM,
 // 4 w3 GEMM, 5 adaLN / shift-vector GEMMs, 6 final-layer GEMM, 7 conditioning + patch embed + ODE update, 8 VMAE decode.
-constexpr int kProfClasses = 9;
+
 struct ProfRec { int cls; cudaEvent_t a, b; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
@@ -74,10 +74,11 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-int make_tmap_bf16(CUtensorMap* out, const void* ptr, int rows, int cols, int ld, int box_rows) {
-  typedef std::tuple<const void*, int, int, int, int> Key;
+int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, int rows, int cols, int ld, int box_cols, int box_rows,
+                 int swizzle_bytes) {
+  typedef std::tuple<const void*, int, int, int, int, int, int, int> Key;
   static thread_local std::map<Key, CUtensorMap> cache;
-  Key key(ptr, rows, cols, ld, box_rows);
+  Key key(ptr, elem_bytes, rows, cols, ld, box_cols, box_rows, swizzle_bytes);
   auto it = cache.find(key);
   if (it != cache.end()) {
     *out = it->second;
@@ -86,17 +87,20 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, int rows, int cols, int ld
   PFN_encodeTiled enc = get_encode();
   if (!enc) return set_error(LDMAE_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   LDMAE_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "tensor map: base pointer must be 16-byte aligned");
+  LDMAE_REQUIRE((static_cast<long long>(ld) * elem_bytes) % 16 == 0, "tensor map: row pitch %d x %d bytes is not a multiple of 16", ld, elem_bytes);
+  LDMAE_REQUIRE(box_cols * elem_bytes <= swizzle_bytes, "tensor map: box of %d bytes exceeds the %d-byte swizzle span", box_cols * elem_bytes, swizzle_bytes);
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * elem_bytes};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = enc(out, dt, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
-    return set_error(LDMAE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d box_rows=%d", (int)r, rows,
-                     cols, ld, box_rows);
-  if (cache.size() > 4096) cache.clear();
+    return set_error(LDMAE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d box=%dx%d elem=%d", (int)r, rows,
+                     cols, ld, box_cols, box_rows, elem_bytes);
+  if (cache.size() > 8192) cache.clear();
   cache[key] = *out;
   return LDMAE_OK;
 }
@@ -126,6 +130,30 @@ static int gemm_auto(const void* a, int lda, const void* w, int ldw, GemmShape g
   ++g_launch_count;
   if (gemm_cg() == 2 && g.M > 128) return launch_gemm<256, 2, Epi>(a, lda, w, ldw, g, ep, st);
   return launch_gemm<128, 1, Epi>(a, lda, w, ldw, g, ep, st);
+}
+
+// out[M,N] = act(a . w^T + bias) through the TMA-store epilogue (out leading dimension ldo)
+template <typename OutT, int ACT>
+static int gemm_store(const void* a, int lda, const void* w, int ldw, GemmShape g, OutT* out, int ldo, const float* bias,
+                      cudaStream_t st) {
+  typename EpiStore<OutT, ACT>::Params ep;
+  if (sizeof(OutT) == 2) LDMAE_TRY(make_tmap_out_bf16(&ep.omap, out, g.M, g.N, ldo));
+  else LDMAE_TRY(make_tmap_out_f32(&ep.omap, out, g.M, g.N, ldo));
+  ep.bias = bias;
+  return gemm_auto<EpiStore<OutT, ACT>>(a, lda, w, ldw, g, ep, st);
+}
+// x[M,N] (fp32, ld ldx) += gate * (a . w^T + bias); optionally anext = bf16(x * gnext) and row statistics (see EpiResidual)
+static int gemm_residual(const void* a, int lda, const void* w, int ldw, GemmShape g, float* x, int ldx, const float* bias,
+                         const float* gate, int gate_ld, const float* gnext, int gnext_ld, __nv_bfloat16* anext, float* ssq,
+                         int ss_slots, int rows_per_sample, cudaStream_t st) {
+  EpiResidual::Params ep;
+  LDMAE_TRY(make_tmap_out_f32(&ep.xmap, x, g.M, g.N, ldx));
+  ep.has_anext = anext != nullptr;
+  if (anext) LDMAE_TRY(make_tmap_2d(&ep.amap, anext, 2, g.M, g.N, ldx, 32, 32, 64));
+  else ep.amap = ep.xmap;
+  ep.bias = bias; ep.gate = gate; ep.gnext = gnext; ep.ssq = ssq;
+  ep.gate_ld = gate_ld; ep.gnext_ld = gnext_ld; ep.rows_per_sample = rows_per_sample; ep.ss_slots = ss_slots;
+  return gemm_auto<EpiResidual>(a, lda, w, ldw, g, ep, st);
 }
 
 static int run_attention(const void* qkv, int ldq, void* out, int ldo, int B, int T, int H, int q_col, int k_col,
@@ -162,7 +190,7 @@ struct ldmae_dit {
   ldmae_dit_config c;
   int D, T, G, Kp, H, Hp, nmod, Ntot, S /*norm slots*/, Nf, maxB, SS /*ssq partial slots*/;
   // weights
-  DevBuf<float> pos, patch_w, patch_b, t_w0, t_b0, t_w2, t_b2, emb, rope_cos, rope_sin, norm_w, b_ada, b_f, w_f32;
+  DevBuf<float> pos, patch_w, patch_b, t_w0, t_b0, t_w2, t_b2, emb, rope_cos, rope_sin, rope_tab, norm_w, b_ada, b_f, w_f32;
   DevBuf<__nv_bfloat16> w_ada, w_f;
   std::vector<DitBlockW> blk;
   DevBuf<int> slot_shift_off, slot_scale_off;
@@ -277,6 +305,7 @@ extern "C" int ldmae_dit_create(const ldmae_dit_config* cfg, ldmae_dit** out) {
   A(h->t_w2.alloc(static_cast<size_t>(D) * D)); A(h->t_b2.alloc(D));
   A(h->emb.alloc(static_cast<size_t>(c.num_embeddings) * D));
   A(h->rope_cos.alloc(static_cast<size_t>(h->T) * 64)); A(h->rope_sin.alloc(static_cast<size_t>(h->T) * 64));
+  A(h->rope_tab.alloc(static_cast<size_t>(2) * h->G * 32 + 1));
   A(h->norm_w.alloc(static_cast<size_t>(h->S) * D));
   A(h->w_ada.alloc(static_cast<size_t>(h->Ntot) * D)); A(h->b_ada.alloc(h->Ntot));
   A(h->w_f.alloc(static_cast<size_t>(h->Nf) * D)); A(h->b_f.alloc(h->Nf)); A(h->w_f32.alloc(static_cast<size_t>(h->Nf) * D));
@@ -393,12 +422,27 @@ extern "C" int ldmae_dit_load_tensor(ldmae_dit* h, const char* name, const float
 
 extern "C" int ldmae_dit_finalize(ldmae_dit* h, void* stream) {
   LDMAE_REQUIRE(h, "null handle");
-  (void)stream;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   int expect = 8 + 5 + 12 * h->c.depth;   // without qk-norm / rope keys
   if (h->c.use_qknorm) expect += 2 * h->c.depth;
   if (h->c.use_rope) expect += 2;
   if ((int)h->loaded.size() != expect)
     return set_error(LDMAE_ERR_STATE, "LightningDiT weights incomplete: %d of %d tensors loaded", (int)h->loaded.size(), expect);
+  if (h->c.use_rope) {
+    // compact axial table for the QKV epilogue + a check that the loaded [T, 64] buffers really have that structure
+    float* maxdiff = h->rope_tab.p + static_cast<size_t>(2) * h->G * 32;
+    LDMAE_CUDA(cudaMemsetAsync(maxdiff, 0, sizeof(float), st));
+    rope_compact_kernel<<<cdiv(2 * h->G * 32, 128), 128, 0, st>>>(h->rope_tab.p, h->rope_cos.p, h->rope_sin.p, h->G);
+    LDMAE_LAUNCH_CHECK();
+    rope_check_kernel<<<cdiv(static_cast<size_t>(h->T) * 64, 256), 256, 0, st>>>(maxdiff, h->rope_tab.p, h->rope_cos.p, h->rope_sin.p, h->G);
+    LDMAE_LAUNCH_CHECK();
+    float md = 0.f;
+    LDMAE_CUDA(cudaMemcpyAsync(&md, maxdiff, sizeof(float), cudaMemcpyDeviceToHost, st));
+    LDMAE_CUDA(cudaStreamSynchronize(st));
+    if (!(md <= 1e-6f))
+      return set_error(LDMAE_ERR_INVALID, "feat_rope.freqs_cos/sin are not the 2-D axial table of models/pos_embed.py:96-133 "
+                       "(max deviation %g): unsupported RoPE buffers", md);
+  }
   h->finalized = true;
   return LDMAE_OK;
 }
@@ -441,8 +485,7 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
   // 2. all adaLN modulations at once: mods[B, Ntot] = sc . W_ada^T + b_ada
   {
     ProfScope ps(5, st);
-    EpiStore<float, 0>::Params ep{h->mods.p, h->b_ada.p, h->Ntot};
-    LDMAE_TRY((gemm_auto<EpiStore<float, 0>>(h->sc.p, D, h->w_ada.p, D, GemmShape{B, h->Ntot, D}, ep, st)));
+    LDMAE_TRY((gemm_store<float, 0>(h->sc.p, D, h->w_ada.p, D, GemmShape{B, h->Ntot, D}, h->mods.p, h->Ntot, h->b_ada.p, st)));
     const size_t tot = static_cast<size_t>(h->S) * B * D;
     adaln_prep_kernel<<<cdiv(tot, 256), 256, 0, st>>>(h->shift_bf16.p, h->gmul.p, h->mods.p, h->norm_w.p,
                                                       h->slot_shift_off.p, h->slot_scale_off.p, B, D, h->Ntot, h->S);
@@ -455,12 +498,10 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
     DitBlockW& b = h->blk[i];
     float* cq = h->cvec_qkv.p + static_cast<size_t>(i) * B * 3 * D;
     float* c12 = h->cvec_12.p + static_cast<size_t>(i) * B * 2 * h->Hp;
-    EpiStore<float, 0>::Params e1{cq, b.b_qkv.p, 3 * D};
-    LDMAE_TRY((gemm_auto<EpiStore<float, 0>>(h->shift_bf16.p + static_cast<size_t>(2 * i) * B * D, D, b.w_qkv.p, D,
-                                              GemmShape{B, 3 * D, D}, e1, st)));
-    EpiStore<float, 0>::Params e2{c12, b.b12.p, 2 * h->Hp};
-    LDMAE_TRY((gemm_auto<EpiStore<float, 0>>(h->shift_bf16.p + static_cast<size_t>(2 * i + 1) * B * D, D, b.w12.p, D,
-                                              GemmShape{B, 2 * h->Hp, D}, e2, st)));
+    LDMAE_TRY((gemm_store<float, 0>(h->shift_bf16.p + static_cast<size_t>(2 * i) * B * D, D, b.w_qkv.p, D, GemmShape{B, 3 * D, D},
+                                    cq, 3 * D, b.b_qkv.p, st)));
+    LDMAE_TRY((gemm_store<float, 0>(h->shift_bf16.p + static_cast<size_t>(2 * i + 1) * B * D, D, b.w12.p, D,
+                                    GemmShape{B, 2 * h->Hp, D}, c12, 2 * h->Hp, b.b12.p, st)));
   }
   {
     ProfScope ps(7, st);
@@ -489,28 +530,32 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
     const float* gate_msa = mods_i + (c.wo_shift ? 1 : 2) * D;
     const float* gate_mlp = mods_i + (c.wo_shift ? 3 : 5) * D;
     EpiQKV::Params eq;
-    eq.out = h->qkv.p; eq.ssq = h->ssq.p; eq.cvec = h->cvec_qkv.p + static_cast<size_t>(i) * B * 3 * D;
+    LDMAE_TRY(make_tmap_out_bf16(&eq.omap, h->qkv.p, M, 3 * D, 3 * D));
+    eq.ssq = h->ssq.p; eq.cvec = h->cvec_qkv.p + static_cast<size_t>(i) * B * 3 * D;
     eq.qw = c.use_qknorm ? b.qw.p : nullptr; eq.kw = c.use_qknorm ? b.kw.p : nullptr;
-    eq.rope_cos = c.use_rope ? h->rope_cos.p : nullptr; eq.rope_sin = c.use_rope ? h->rope_sin.p : nullptr;
+    eq.rope = c.use_rope ? h->rope_tab.p : nullptr; eq.grid = h->G;
     eq.D = D; eq.rows_per_sample = T; eq.ss_slots = h->SS; eq.inv_D = 1.f / D; eq.eps_row = eps; eq.eps_head = eps;
     { ProfScope ps(0, st); LDMAE_TRY((gemm_auto<EpiQKV>(h->abuf.p, D, b.w_qkv.p, D, GemmShape{M, 3 * D, D}, eq, st))); }
     LDMAE_DBG_STAGE();
     { ProfScope ps(1, st); LDMAE_TRY(run_attention(h->qkv.p, 3 * D, h->obuf.p, D, B, T, c.num_heads, 0, D, 2 * D, 0.125f, st)); }
     LDMAE_DBG_STAGE();
-    EpiResidual::Params ep;
-    ep.x = h->xres.p; ep.bias = b.b_proj.p; ep.gate = gate_msa; ep.gnext = h->gmul.p + static_cast<size_t>(2 * i + 1) * B * D;
-    ep.anext = h->abuf.p; ep.ssq = h->ssq.p; ep.ldx = D; ep.gate_ld = h->Ntot; ep.gnext_ld = D; ep.rows_per_sample = T; ep.ss_slots = h->SS;
-    { ProfScope ps(2, st); LDMAE_TRY((gemm_auto<EpiResidual>(h->obuf.p, D, b.w_proj.p, D, GemmShape{M, D, D}, ep, st))); }
+    {
+      ProfScope ps(2, st);
+      LDMAE_TRY(gemm_residual(h->obuf.p, D, b.w_proj.p, D, GemmShape{M, D, D}, h->xres.p, D, b.b_proj.p, gate_msa, h->Ntot,
+                              h->gmul.p + static_cast<size_t>(2 * i + 1) * B * D, D, h->abuf.p, h->ssq.p, h->SS, T, st));
+    }
     LDMAE_DBG_STAGE();
     EpiSwiGLU::Params es;
-    es.out = h->hbuf.p; es.ssq = h->ssq.p; es.cvec = h->cvec_12.p + static_cast<size_t>(i) * B * 2 * h->Hp;
-    es.H = h->Hp; es.rows_per_sample = T; es.ss_slots = h->SS; es.inv_D = 1.f / D; es.eps_row = eps;
+    LDMAE_TRY(make_tmap_out_bf16(&es.omap, h->hbuf.p, M, h->Hp, h->Hp));
+    es.ssq = h->ssq.p; es.cvec = h->cvec_12.p + static_cast<size_t>(i) * B * 2 * h->Hp;
+    es.rows_per_sample = T; es.ss_slots = h->SS; es.inv_D = 1.f / D; es.eps_row = eps;
     { ProfScope ps(3, st); LDMAE_TRY((gemm_auto<EpiSwiGLU>(h->abuf.p, D, b.w12.p, D, GemmShape{M, 2 * h->Hp, D}, es, st))); }
     LDMAE_DBG_STAGE();
-    EpiResidual::Params e3;
-    e3.x = h->xres.p; e3.bias = b.b3.p; e3.gate = gate_mlp; e3.gnext = h->gmul.p + static_cast<size_t>(2 * i + 2) * B * D;
-    e3.anext = h->abuf.p; e3.ssq = h->ssq.p; e3.ldx = D; e3.gate_ld = h->Ntot; e3.gnext_ld = D; e3.rows_per_sample = T; e3.ss_slots = h->SS;
-    { ProfScope ps(4, st); LDMAE_TRY((gemm_auto<EpiResidual>(h->hbuf.p, h->Hp, b.w3.p, h->Hp, GemmShape{M, D, h->Hp}, e3, st))); }
+    {
+      ProfScope ps(4, st);
+      LDMAE_TRY(gemm_residual(h->hbuf.p, h->Hp, b.w3.p, h->Hp, GemmShape{M, D, h->Hp}, h->xres.p, D, b.b3.p, gate_mlp, h->Ntot,
+                              h->gmul.p + static_cast<size_t>(2 * i + 2) * B * D, D, h->abuf.p, h->ssq.p, h->SS, T, st));
+    }
     LDMAE_DBG_STAGE();
   }
   // 6. final layer + unpatchify
@@ -778,15 +823,11 @@ extern "C" int ldmae_vmae_decode(ldmae_vmae* h, const float* z, const float* mea
                                                                                  multiplier != 0.f ? 1.f / multiplier : 1.f,
                                                                                  B, h->c.latent_dim, L, 64);
   LDMAE_LAUNCH_CHECK();
-  EpiStore<__nv_bfloat16, 0>::Params e0{h->t1.p, h->b_from.p, E};
-  LDMAE_TRY((gemm_auto<EpiStore<__nv_bfloat16, 0>>(h->tok.p, 64, h->w_from.p, 64, GemmShape{M, E, 64}, e0, st)));
+  LDMAE_TRY((gemm_store<__nv_bfloat16, 0>(h->tok.p, 64, h->w_from.p, 64, GemmShape{M, E, 64}, h->t1.p, E, h->b_from.p, st)));
   broadcast_rows_kernel<<<cdiv(static_cast<size_t>(M) * D, 256), 256, 0, st>>>(h->x.p, h->pos.p, M, L, D);
   LDMAE_LAUNCH_CHECK();
   auto resid = [&](const void* a, int lda, const void* w, int ldw, int K, const float* bias) {
-    EpiResidual::Params ep;
-    ep.x = h->x.p; ep.bias = bias; ep.gate = nullptr; ep.gnext = nullptr; ep.anext = nullptr; ep.ssq = nullptr;
-    ep.ldx = D; ep.gate_ld = 0; ep.gnext_ld = 0; ep.rows_per_sample = L; ep.ss_slots = 0;
-    return gemm_auto<EpiResidual>(a, lda, w, ldw, GemmShape{M, D, K}, ep, st);
+    return gemm_residual(a, lda, w, ldw, GemmShape{M, D, K}, h->x.p, D, bias, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, L, st);
   };
   LDMAE_TRY(resid(h->t1.p, E, h->w_embed.p, E, E, h->b_embed.p));
   const unsigned ln_grid = cdiv(M, 8);
@@ -794,20 +835,17 @@ extern "C" int ldmae_vmae_decode(ldmae_vmae* h, const float* z, const float* mea
     VmaeBlockW& b = h->blk[i];
     layernorm_bf16_kernel<<<ln_grid, 256, 0, st>>>(h->a.p, h->x.p, b.n1w.p, b.n1b.p, M, D, h->c.ln_eps);
     LDMAE_LAUNCH_CHECK();
-    EpiStore<__nv_bfloat16, 0>::Params eq{h->qkv.p, b.b_qkv.p, 3 * h->HP};
-    LDMAE_TRY((gemm_auto<EpiStore<__nv_bfloat16, 0>>(h->a.p, D, b.w_qkv.p, D, GemmShape{M, 3 * h->HP, D}, eq, st)));
+    LDMAE_TRY((gemm_store<__nv_bfloat16, 0>(h->a.p, D, b.w_qkv.p, D, GemmShape{M, 3 * h->HP, D}, h->qkv.p, 3 * h->HP, b.b_qkv.p, st)));
     LDMAE_TRY(run_attention(h->qkv.p, 3 * h->HP, h->o.p, h->HP, B, L, nh, 0, h->HP, 2 * h->HP, scale, st));
     LDMAE_TRY(resid(h->o.p, h->HP, b.w_proj.p, h->HP, h->HP, b.b_proj.p));
     layernorm_bf16_kernel<<<ln_grid, 256, 0, st>>>(h->a.p, h->x.p, b.n2w.p, b.n2b.p, M, D, h->c.ln_eps);
     LDMAE_LAUNCH_CHECK();
-    EpiStore<__nv_bfloat16, 1>::Params e1{h->hid.p, b.b_fc1.p, h->Hm};
-    LDMAE_TRY((gemm_auto<EpiStore<__nv_bfloat16, 1>>(h->a.p, D, b.w_fc1.p, D, GemmShape{M, h->Hm, D}, e1, st)));
+    LDMAE_TRY((gemm_store<__nv_bfloat16, 1>(h->a.p, D, b.w_fc1.p, D, GemmShape{M, h->Hm, D}, h->hid.p, h->Hm, b.b_fc1.p, st)));
     LDMAE_TRY(resid(h->hid.p, h->Hm, b.w_fc2.p, h->Hm, h->Hm, b.b_fc2.p));
   }
   layernorm_bf16_kernel<<<ln_grid, 256, 0, st>>>(h->a.p, h->x.p, h->nfw.p, h->nfb.p, M, D, h->c.ln_eps);
   LDMAE_LAUNCH_CHECK();
-  EpiStore<float, 0>::Params epred{h->pred.p, h->b_pred.p, h->PP};
-  LDMAE_TRY((gemm_auto<EpiStore<float, 0>>(h->a.p, D, h->w_pred.p, D, GemmShape{M, h->PP, D}, epred, st)));
+  LDMAE_TRY((gemm_store<float, 0>(h->a.p, D, h->w_pred.p, D, GemmShape{M, h->PP, D}, h->pred.p, h->PP, h->b_pred.p, st)));
   const size_t npix = static_cast<size_t>(B) * h->c.img_size * h->c.img_size;
   vmae_pixel_tail_kernel<<<cdiv(npix, 256), 256, 0, st>>>(img_f32, img_u8, h->pred.p, h->conv_w.p, h->conv_b.p, B, h->G,
                                                           h->c.patch_size);
@@ -837,16 +875,32 @@ extern "C" int ldmae_gemm_bias(const void* a, const void* w, const float* bias, 
   using EpiF0 = EpiStore<float, 0>;
   if (out_is_bf16) {
     if (act == 1) {
-      EpiB1::Params p{static_cast<__nv_bfloat16*>(out), bias, N};
+      EpiB1::Params p;
+      LDMAE_TRY(make_tmap_out_bf16(&p.omap, out, M, N, N));
+      p.bias = bias;
       LDMAE_DISPATCH(EpiB1, p);
     }
-    EpiB0::Params p{static_cast<__nv_bfloat16*>(out), bias, N};
+    EpiB0::Params p;
+    LDMAE_TRY(make_tmap_out_bf16(&p.omap, out, M, N, N));
+    p.bias = bias;
     LDMAE_DISPATCH(EpiB0, p);
   }
   LDMAE_REQUIRE(act == 0, "fp32 output supports act 0 only");
-  EpiF0::Params p{static_cast<float*>(out), bias, N};
+  EpiF0::Params p;
+  LDMAE_TRY(make_tmap_out_f32(&p.omap, out, M, N, N));
+  p.bias = bias;
   LDMAE_DISPATCH(EpiF0, p);
 #undef LDMAE_DISPATCH
+}
+
+extern "C" int ldmae_gemm_residual(const void* a, const void* w, const float* bias, const float* gate, const float* gnext,
+                                   float* x, void* anext, float* ssq, int32_t M, int32_t N, int32_t K, int32_t rows_per_sample,
+                                   void* stream) {
+  LDMAE_TRY(require_sm100());
+  LDMAE_REQUIRE(K % 8 == 0 && N % 4 == 0, "K must be a multiple of 8 and N of 4");
+  LDMAE_REQUIRE((anext == nullptr) == (gnext == nullptr), "anext and gnext go together");
+  return gemm_residual(a, K, w, K, GemmShape{M, N, K}, x, N, bias, gate, N, gnext, N, static_cast<__nv_bfloat16*>(anext), ssq,
+                       (N + 127) / 128, rows_per_sample, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int ldmae_attention(const void* qkv, void* out, int32_t B, int32_t T, int32_t H, float scale, void* stream) {

@@ -36,3 +36,18 @@ def attention(qkv_bf16, B, T, H, scale):
 def load_npz(golden_dir, name):
     import os
     return np.load(os.path.join(golden_dir, name))
+
+
+def gemm_residual(a_bf16, w_bf16, bias, x, gate=None, gnext=None, rows_per_sample=None):
+    """x += gate*(a.w^T + bias) in place; returns (x, anext or None, ssq)."""
+    M, K = a_bf16.shape
+    N = w_bf16.shape[0]
+    rows_per_sample = rows_per_sample or M
+    anext = torch.empty(M, N, device="cuda", dtype=torch.bfloat16) if gnext is not None else None
+    slots = (N + 127) // 128
+    ssq = torch.full((M, slots), float("nan"), device="cuda")
+    _lib.check(_lib.lib().ldmae_gemm_residual(_lib.ptr(a_bf16), _lib.ptr(w_bf16), _lib.ptr(bias), _lib.ptr(gate), _lib.ptr(gnext),
+                                              _lib.ptr(x), _lib.ptr(anext), _lib.ptr(ssq), M, N, K, rows_per_sample,
+                                              _lib.stream_ptr()), "gemm_residual")
+    torch.cuda.synchronize()
+    return x, anext, ssq

@@ -57,6 +57,30 @@ def test_gemm_bias_bf16_out_and_gelu(act):
     assert rel_err(out, ref) < 4e-3     # bf16 output rounding (2^-9 relative per element)
 
 
+@pytest.mark.parametrize("M,N,K,rps,full", [(2048, 768, 768, 1024, True), (1024, 768, 2048, 256, True), (300, 192, 768, 100, False),
+                                              (4096, 768, 768, 1024, True), (96, 128, 64, 32, True)])
+def test_gemm_residual_epilogue(M, N, K, rps, full):
+    """x += gate_b*(a.w^T+bias); anext = bf16(x*gnext_b); ssq = row sums of x^2 -- the TMA load/modify/store epilogue."""
+    from gpu_util import gemm_residual, rel_err
+    g = torch.Generator().manual_seed(M + N + K)
+    nb = (M + rps - 1) // rps
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g)
+    x0 = torch.randn(M, N, generator=g)
+    gate = torch.randn(nb, N, generator=g) if full else None
+    gnext = (1 + 0.1 * torch.randn(nb, N, generator=g)) if full else None
+    y = a.float() @ w.float().t() + bias
+    bidx = torch.arange(M) // rps
+    ref = x0 + (gate[bidx] * y if full else y)
+    x, anext, ssq = gemm_residual(a.cuda(), w.cuda(), bias.cuda(), x0.clone().cuda(), gate.cuda() if full else None,
+                                  gnext.cuda() if full else None, rps)
+    assert rel_err(x, ref) < 1e-5
+    torch.testing.assert_close(ssq.sum(1).cpu(), (ref ** 2).sum(1), rtol=1e-4, atol=1e-4)
+    if full:
+        assert rel_err(anext.float(), ref * gnext[bidx]) < 4e-3     # bf16 rounding of the operand
+
+
 @pytest.mark.parametrize("B,T,H,scale", [(2, 1024, 3, 0.125), (3, 64, 2, 0.125), (1, 320, 2, 0.25), (2, 256, 1, 0.125)])
 def test_attention_matches_softmax(B, T, H, scale):
     from gpu_util import attention, rel_err
