@@ -6,26 +6,30 @@
 // 64 per head) read through ONE 2-D TMA tensor map with a {64 x 128} box, so no head transposes
 // exist anywhere.  Output o is token-major [B*T, H*64] bf16 = the A operand of the out-projection.
 //
-// One CTA = one (sample, head) x 256 queries (two 128-row tiles that ping-pong on the tensor core):
-//   warp 0       TMA loader (Q once; K/V 128-key blocks through a 3-deep ring)
-//   warp 1       MMA issuer: S_t = Q_t K_j^T (128x128x64) and Oblk_t = P_t V_j (128x64x128) in TMEM
+// One CTA = one (sample, head) x 256 queries: two 128-row query tiles that ping-pong on the tensor core
+// (while the softmax warps of one tile work, the tensor core serves the other):
+//   warp 0       TMA loader (Q once; K/V 128-key blocks through a kAttnKVStages-deep ring)
+//   warp 1       MMA issuer: S_t = Q_t K_j^T (128x128x64, SS) and O_t += P_t V_j (128x64x128, A = P from TMEM)
 //   warp 2       TMEM allocator
-//   warps 4-7    softmax + accumulate for tile 0 (one query row per thread, no shuffles)
+//   warps 4-7    softmax for tile 0 (one query row per thread, no shuffles)
 //   warps 8-11   same for tile 1
-// Online softmax keeps the running max / sum / O accumulator in registers; P goes to smem as the
-// K-major A operand (128B swizzle) of the PV MMA; V is consumed MN-major straight from its TMA tile.
+// TMEM columns: S0 [0,128)  S1 [128,256)  O0 [256,320)  O1 [320,384); P_t (bf16, 64 columns) overwrites the first half
+// of S_t once the row has been read into registers, so P never touches shared memory.
+// O accumulates in TMEM over all key blocks.  The running maximum is updated lazily: a row is only rescaled
+// (O_t *= alpha in TMEM, l *= alpha) when its block maximum exceeds the reference by more than 2^8, so exponentials
+// stay <= 256 (exact in fp32 / bf16 range) and the rescale is off the common path.
 #pragma once
 #include "ptx.cuh"
 
 namespace ldmae {
 
 constexpr int kAttnThreads = 384;
-constexpr int kAttnKVStages = 3;
+constexpr int kAttnKVStages = 4;
 constexpr int kAttnTileBytes = 128 * 128;  // 128 rows x 64 bf16
-constexpr int kAttnSmemBytes = 1024 + 2 * kAttnTileBytes            // Q0,Q1
+constexpr int kAttnSmemBytes = 1024 + 2 * kAttnTileBytes            // Q0,Q1 (reused as the output staging tiles)
                                + 2 * kAttnKVStages * kAttnTileBytes  // K,V rings
-                               + 2 * 2 * kAttnTileBytes              // P0,P1 (128 x 128 bf16 each)
                                + 256;
+constexpr float kAttnRescaleLog2 = 8.0f;
 
 struct AttnParams {
   __nv_bfloat16* out;  // [B*T, ldo]
@@ -35,23 +39,22 @@ struct AttnParams {
 };
 
 __global__ void __launch_bounds__(kAttnThreads, 1)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p) {
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + 2 * kAttnTileBytes;
   uint8_t* sV = sK + kAttnKVStages * kAttnTileBytes;
-  uint8_t* sP = sV + kAttnKVStages * kAttnTileBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * kAttnTileBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kAttnKVStages * kAttnTileBytes);
   uint64_t* q_full = bars;                         // [1]
-  uint64_t* k_full = bars + 1;                     // [3]
-  uint64_t* k_empty = k_full + kAttnKVStages;      // [3]
-  uint64_t* v_full = k_empty + kAttnKVStages;      // [3]
-  uint64_t* v_empty = v_full + kAttnKVStages;      // [3]
-  uint64_t* s_full = v_empty + kAttnKVStages;      // [2]
-  uint64_t* p_full = s_full + 2;                   // [2]
-  uint64_t* o_full = p_full + 2;                   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* k_full = bars + 1;                     // [stages]
+  uint64_t* k_empty = k_full + kAttnKVStages;
+  uint64_t* v_full = k_empty + kAttnKVStages;
+  uint64_t* v_empty = v_full + kAttnKVStages;
+  uint64_t* s_full = v_empty + kAttnKVStages;      // [2]  S_t ready (MMA -> softmax)
+  uint64_t* p_full = s_full + 2;                   // [2]  P_t stored in TMEM (softmax -> MMA)
+  uint64_t* o_done = p_full + 2;                   // [2]  O_t += P_t V_j finished (MMA -> softmax)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -59,7 +62,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
   const int nkv = (p.T + 127) / 128;
   const int row_base = b * p.T;                    // first token row of this sample
 
-  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_qkv);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_out);
+  }
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
     for (int s = 0; s < kAttnKVStages; ++s) {
@@ -67,7 +73,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
       mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
     }
     for (int t = 0; t < 2; ++t) {
-      mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 4); mbar_init(&o_full[t], 1);
+      mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 4); mbar_init(&o_done[t], 1);
     }
     fence_mbar_init();
   }
@@ -76,7 +82,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: S0 [0,128)  S1 [128,256)  Oblk0 [256,320)  Oblk1 [320,384)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -106,14 +111,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
           umma_bf16<1>(tmem_base + t * 128, umma_smem_desc_sw128(qa + k * 32, 1024, 0),
                        umma_smem_desc_sw128(ka + k * 32, 1024, 0), idesc_qk, k != 0 ? 1u : 0u);
       };
-      auto issue_pv = [&](int t, int vstage) {
-        const uint32_t pa = smem_u32(sP + t * 2 * kAttnTileBytes);
+      auto issue_pv = [&](int t, int vstage, bool first) {
         const uint32_t va = smem_u32(sV + vstage * kAttnTileBytes);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)   // 8 x 16 keys; P: two 64-key swizzle atoms of 128 rows each
-          umma_bf16<1>(tmem_base + 256 + t * 64,
-                       umma_smem_desc_sw128(pa + (k >> 2) * kAttnTileBytes + (k & 3) * 32, 1024, 0),
-                       umma_smem_desc_sw128(va + k * 2048, 1024, kAttnTileBytes), idesc_pv, k != 0 ? 1u : 0u);
+        for (int k = 0; k < 8; ++k)   // 8 x 16 keys; P: 8 TMEM columns (16 bf16) per step
+          umma_bf16_ts(tmem_base + 256 + t * 64, tmem_base + t * 128 + k * 8,
+                       umma_smem_desc_sw128(va + k * 2048, 1024, kAttnTileBytes), idesc_pv, (first && k == 0) ? 0u : 1u);
       };
       mbar_wait(q_full, 0, 20);
       mbar_wait(&k_full[0], 0, 21);
@@ -129,12 +132,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
           mbar_wait(&p_full[t], j & 1, 22 + t);
           if (t == 0) mbar_wait(&v_full[stage], phase, 24);
           tc_fence_after();
-          issue_pv(t, stage);
-          umma_commit<1>(&o_full[t]);
+          issue_pv(t, stage, j == 0);
+          umma_commit<1>(&o_done[t]);
           if (t == 1) umma_commit<1>(&v_empty[stage]);
           if (j + 1 < nkv) {
             if (t == 0) { mbar_wait(&k_full[nstage], nphase, 25); tc_fence_after(); }
-            issue_qk(t, nstage);
+            issue_qk(t, nstage);                         // executes after P_t V_j: the in-order MMA pipe has read P_t by then
             umma_commit<1>(&s_full[t]);
             if (t == 1) umma_commit<1>(&k_empty[nstage]);
           }
@@ -143,98 +146,117 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
       }
     }
   } else if (warp >= 4) {
-    // ===================== softmax / accumulate: thread = one query row =====================
+    // ===================== softmax: thread = one query row =====================
     const int t = (warp - 4) >> 2;                       // tile 0 / 1
     const int wq = warp & 3;
     const int r = wq * 32 + lane;                        // row inside the tile
     const uint32_t lane_addr = static_cast<uint32_t>(wq * 32) << 16;
     const uint32_t tS = tmem_base + lane_addr + t * 128;
     const uint32_t tO = tmem_base + lane_addr + 256 + t * 64;
-    uint8_t* myP = sP + t * 2 * kAttnTileBytes + r * 128;
-    const int sw = r & 7;
-    float o[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) o[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
+    float m_used = -INFINITY, l_run = 0.f;
+#pragma unroll 1
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(&s_full[t], j & 1, 30 + t);
+      __syncwarp();
       tc_fence_after();
-      const int kvalid = p.T - j * 128;                  // keys of this block that exist (>=1)
-      // pass 1: row max
-      float m_blk = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        float v[32];
-        tmem_ld32(tS + c * 32, v);
-        tmem_ld_wait();
+      float s[128];
+      tmem_ld32(tS, s);
+      tmem_ld32(tS + 32, s + 32);
+      tmem_ld32(tS + 64, s + 64);
+      tmem_ld32(tS + 96, s + 96);
+      tmem_ld_wait();
+      const int kvalid = p.T - j * 128;                  // keys of this block that exist (>= 1)
+      if (kvalid < 128) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < kvalid) m_blk = fmaxf(m_blk, v[i]);
+        for (int i = 0; i < 128; ++i)
+          if (i >= kvalid) s[i] = -INFINITY;
       }
-      const float m_new = fmaxf(m_run, m_blk);
-      const float alpha = exp2f((m_run - m_new) * p.scale_log2);   // 0 on the first block
-      if (j > 0) {
-        // fold in Oblk_{j-1} (frame m_run), then move the accumulator to frame m_new
-        mbar_wait(&o_full[t], (j - 1) & 1, 32 + t);
-        tc_fence_after();
+      float mx[4] = {s[0], s[1], s[2], s[3]};
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          float v[32];
-          tmem_ld32(tO + c * 32, v);
-          tmem_ld_wait();
+      for (int i = 4; i < 128; i += 4) {
+        mx[0] = fmaxf(mx[0], s[i]); mx[1] = fmaxf(mx[1], s[i + 1]);
+        mx[2] = fmaxf(mx[2], s[i + 2]); mx[3] = fmaxf(mx[3], s[i + 3]);
+      }
+      const float m_blk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      if (j == 0) {
+        m_used = m_blk;
+      } else {
+        const bool grow = (m_blk - m_used) * p.scale_log2 > kAttnRescaleLog2;
+        if (__any_sync(0xffffffffu, grow)) {
+          // move this warp's rows to the new reference maximum: O_t *= alpha in TMEM (needs P_t V_{j-1} finished)
+          const float m_new = fmaxf(m_used, m_blk);
+          const float alpha = ex2_approx((m_used - m_new) * p.scale_log2);
+          mbar_wait(&o_done[t], (j - 1) & 1, 32 + t);
+          __syncwarp();
+          tc_fence_after();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[c * 32 + i] = (o[c * 32 + i] + v[i]) * alpha;
+          for (int c = 0; c < 2; ++c) {
+            float o[32];
+            tmem_ld32(tO + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] *= alpha;
+            tmem_st32(tO + c * 32, reinterpret_cast<const uint32_t*>(o));
+          }
+          tmem_st_wait();
+          l_run *= alpha;
+          m_used = m_new;
         }
       }
-      // pass 2: p = exp2((s - m_new) * scale), bf16 -> smem (K-major, 128B swizzle), row sum
-      const float mscaled = m_new * p.scale_log2;
-      float lsum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        float v[32];
-        tmem_ld32(tS + c * 32, v);
-        tmem_ld_wait();
-        uint32_t w[16];
+      // p = exp2((s - m_used) * scale) -> bf16 pairs -> TMEM (A operand of P.V); row sum in fp32
+      const float neg = -m_used * p.scale_log2;
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = (c * 32 + i < kvalid) ? exp2f(fmaf(v[i], p.scale_log2, -mscaled)) : 0.f;
-          float p1 = (c * 32 + i + 1 < kvalid) ? exp2f(fmaf(v[i + 1], p.scale_log2, -mscaled)) : 0.f;
-          lsum += p0 + p1;
+      for (int h = 0; h < 2; ++h) {                      // 64 keys -> 32 packed words -> one tcgen05.st
+        uint32_t w[32];
+#pragma unroll
+        for (int i = 0; i < 64; i += 4) {
+          const float p0 = ex2_approx(fmaf(s[h * 64 + i], p.scale_log2, neg));
+          const float p1 = ex2_approx(fmaf(s[h * 64 + i + 1], p.scale_log2, neg));
+          const float p2 = ex2_approx(fmaf(s[h * 64 + i + 2], p.scale_log2, neg));
+          const float p3 = ex2_approx(fmaf(s[h * 64 + i + 3], p.scale_log2, neg));
+          ls[0] += p0; ls[1] += p1; ls[2] += p2; ls[3] += p3;
           w[i >> 1] = pack_bf16x2(p0, p1);
+          w[(i >> 1) + 1] = pack_bf16x2(p2, p3);
         }
-        uint8_t* dst = myP + (c >> 1) * kAttnTileBytes;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = ((c & 1) * 4 + q) ^ sw;
-          *reinterpret_cast<uint4*>(dst + chunk * 16) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-        }
+        tmem_st32(tS + h * 32, w);
       }
-      l_run = l_run * alpha + lsum;
-      m_run = m_new;
-      fence_proxy_async_smem();
+      l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[t]);
     }
-    // last block's PV
-    mbar_wait(&o_full[t], (nkv - 1) & 1, 34 + t);
+    // epilogue: O_t / l -> bf16 -> global (through this tile's Q slice in smem + one TMA store per warp)
+    mbar_wait(&o_done[t], (nkv - 1) & 1, 34 + t);
+    __syncwarp();
     tc_fence_after();
     const float inv_l = 1.f / l_run;
-    const int q_tok = qpair * 256 + t * 128 + r;
+    const int q_tok0 = qpair * 256 + t * 128 + wq * 32;  // first query token of this warp
+    const bool whole = q_tok0 + 32 <= p.T;               // all 32 rows of the warp exist -> TMA store
+    uint8_t* stage = sQ + t * kAttnTileBytes + wq * 4096;
+    __nv_bfloat16* dst = p.out + static_cast<size_t>(row_base + q_tok0 + lane) * p.ldo + head * 64;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-      float v[32];
-      tmem_ld32(tO + c * 32, v);
+      float o[32];
+      tmem_ld32(tO + c * 32, o);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o[c * 32 + i] = (o[c * 32 + i] + v[i]) * inv_l;
+      for (int q = 0; q < 4; ++q) {
+        const uint4 v = make_uint4(pack_bf16x2(o[8 * q] * inv_l, o[8 * q + 1] * inv_l), pack_bf16x2(o[8 * q + 2] * inv_l, o[8 * q + 3] * inv_l),
+                                   pack_bf16x2(o[8 * q + 4] * inv_l, o[8 * q + 5] * inv_l), pack_bf16x2(o[8 * q + 6] * inv_l, o[8 * q + 7] * inv_l));
+        if (whole) sts128(stage + lane * 128 + (((c * 4 + q) ^ (lane & 7)) << 4), v);
+        else if (q_tok0 + lane < p.T) *reinterpret_cast<uint4*>(dst + c * 32 + q * 8) = v;
+      }
     }
-    if (q_tok < p.T) {
-      __nv_bfloat16* dst = p.out + static_cast<size_t>(row_base + q_tok) * p.ldo + head * 64;
-#pragma unroll
-      for (int i = 0; i < 64; i += 8)
-        *reinterpret_cast<uint4*>(dst + i) = make_uint4(pack_bf16x2(o[i], o[i + 1]), pack_bf16x2(o[i + 2], o[i + 3]),
-                                                        pack_bf16x2(o[i + 4], o[i + 5]), pack_bf16x2(o[i + 6], o[i + 7]));
+    if (whole) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&tmap_out, stage, head * 64, row_base + q_tok0);
+        tma_store_commit();
+        tma_store_wait_read<0>();
+      }
     }
   }
 

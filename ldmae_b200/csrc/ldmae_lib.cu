@@ -158,8 +158,9 @@ static int gemm_residual(const void* a, int lda, const void* w, int ldw, GemmSha
 
 static int run_attention(const void* qkv, int ldq, void* out, int ldo, int B, int T, int H, int q_col, int k_col,
                          int v_col, float scale, cudaStream_t st) {
-  CUtensorMap tm;
+  CUtensorMap tm, tmo;
   LDMAE_TRY(make_tmap_bf16(&tm, qkv, B * T, ldq, ldq, 128));
+  LDMAE_TRY(make_tmap_out_bf16(&tmo, out, B * T, H * 64, ldo));
   static bool attr = false;
   if (!attr) {
     LDMAE_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
@@ -171,7 +172,7 @@ static int run_attention(const void* qkv, int ldq, void* out, int ldo, int B, in
   p.q_col = q_col; p.k_col = k_col; p.v_col = v_col;
   p.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid(cdiv(T, 256), H, B);
-  attn_fwd_kernel<<<grid, kAttnThreads, kAttnSmemBytes, st>>>(tm, p);
+  attn_fwd_kernel<<<grid, kAttnThreads, kAttnSmemBytes, st>>>(tm, tmo, p);
   LDMAE_LAUNCH_CHECK();
   return LDMAE_OK;
 }
