@@ -13,8 +13,9 @@
 //   warp 2       TMEM allocator
 //   warps 4-7    softmax for tile 0 (one query row per thread, no shuffles)
 //   warps 8-11   same for tile 1
-// TMEM columns: S0 [0,128)  S1 [128,256)  O0 [256,320)  O1 [320,384); P_t (bf16, 64 columns) overwrites the first half
-// of S_t once the row has been read into registers, so P never touches shared memory.
+// TMEM columns: S0 [0,128)  S1 [128,256)  P0 [256,320)  P1 [320,384)  O0 [384,448)  O1 [448,512).  P_t (bf16 pairs) has its
+// own columns, so S_t is handed back to the tensor core as soon as the row sits in registers: Q_t K_{j+1}^T runs while
+// the softmax warps still exponentiate block j, and P never touches shared memory.
 // O accumulates in TMEM over all key blocks.  The running maximum is updated lazily: a row is only rescaled
 // (O_t *= alpha in TMEM, l *= alpha) when its block maximum exceeds the reference by more than 2^8, so exponentials
 // stay <= 256 (exact in fp32 / bf16 range) and the rescale is off the common path.
@@ -52,8 +53,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   uint64_t* v_full = k_empty + kAttnKVStages;
   uint64_t* v_empty = v_full + kAttnKVStages;
   uint64_t* s_full = v_empty + kAttnKVStages;      // [2]  S_t ready (MMA -> softmax)
-  uint64_t* p_full = s_full + 2;                   // [2]  P_t stored in TMEM (softmax -> MMA)
-  uint64_t* o_done = p_full + 2;                   // [2]  O_t += P_t V_j finished (MMA -> softmax)
+  uint64_t* s_free = s_full + 2;                   // [2]  S_t copied to registers (softmax -> MMA)
+  uint64_t* p_full = s_free + 2;                   // [2]  P_t stored in TMEM (softmax -> MMA)
+  uint64_t* o_done = p_full + 2;                   // [2]  O_t += P_t V_j finished: P_t free, O_t consistent (MMA -> softmax)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -73,7 +75,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
     }
     for (int t = 0; t < 2; ++t) {
-      mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 4); mbar_init(&o_done[t], 1);
+      mbar_init(&s_full[t], 1); mbar_init(&s_free[t], 4); mbar_init(&p_full[t], 4); mbar_init(&o_done[t], 1);
     }
     fence_mbar_init();
   }
@@ -83,6 +85,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // the eight softmax warps hold a 128-wide score row per thread: they take the registers the control warps do not need
+  // (setmaxnreg sits inside each role's branch so that the register allocator budgets the two regions separately)
+  if (warp < 4) {
+  setmaxnreg_dec<80>();
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(q_full, 2 * kAttnTileBytes);
@@ -115,7 +121,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         const uint32_t va = smem_u32(sV + vstage * kAttnTileBytes);
 #pragma unroll
         for (int k = 0; k < 8; ++k)   // 8 x 16 keys; P: 8 TMEM columns (16 bf16) per step
-          umma_bf16_ts(tmem_base + 256 + t * 64, tmem_base + t * 128 + k * 8,
+          umma_bf16_ts(tmem_base + 384 + t * 64, tmem_base + 256 + t * 64 + k * 8,
                        umma_smem_desc_sw128(va + k * 2048, 1024, kAttnTileBytes), idesc_pv, (first && k == 0) ? 0u : 1u);
       };
       mbar_wait(q_full, 0, 20);
@@ -128,31 +134,40 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       for (int j = 0; j < nkv; ++j) {
         int nstage = stage + 1; uint32_t nphase = phase;
         if (nstage == kAttnKVStages) { nstage = 0; nphase ^= 1; }
+        if (j + 1 < nkv) {
+          // refill S_t with block j+1 as soon as the softmax warps hold block j in registers
+          mbar_wait(&k_full[nstage], nphase, 25);
+          for (int t = 0; t < 2; ++t) {
+            mbar_wait(&s_free[t], j & 1, 26 + t);
+            tc_fence_after();
+            issue_qk(t, nstage);
+            umma_commit<1>(&s_full[t]);
+          }
+          umma_commit<1>(&k_empty[nstage]);
+        }
+        mbar_wait(&v_full[stage], phase, 24);
         for (int t = 0; t < 2; ++t) {
           mbar_wait(&p_full[t], j & 1, 22 + t);
-          if (t == 0) mbar_wait(&v_full[stage], phase, 24);
           tc_fence_after();
           issue_pv(t, stage, j == 0);
           umma_commit<1>(&o_done[t]);
-          if (t == 1) umma_commit<1>(&v_empty[stage]);
-          if (j + 1 < nkv) {
-            if (t == 0) { mbar_wait(&k_full[nstage], nphase, 25); tc_fence_after(); }
-            issue_qk(t, nstage);                         // executes after P_t V_j: the in-order MMA pipe has read P_t by then
-            umma_commit<1>(&s_full[t]);
-            if (t == 1) umma_commit<1>(&k_empty[nstage]);
-          }
         }
+        umma_commit<1>(&v_empty[stage]);
         stage = nstage; phase = nphase;
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    setmaxnreg_inc<208>();
     // ===================== softmax: thread = one query row =====================
     const int t = (warp - 4) >> 2;                       // tile 0 / 1
     const int wq = warp & 3;
     const int r = wq * 32 + lane;                        // row inside the tile
     const uint32_t lane_addr = static_cast<uint32_t>(wq * 32) << 16;
     const uint32_t tS = tmem_base + lane_addr + t * 128;
-    const uint32_t tO = tmem_base + lane_addr + 256 + t * 64;
+    const uint32_t tP = tmem_base + lane_addr + 256 + t * 64;
+    const uint32_t tO = tmem_base + lane_addr + 384 + t * 64;
+    const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
     float m_used = -INFINITY, l_run = 0.f;
 #pragma unroll 1
     for (int j = 0; j < nkv; ++j) {
@@ -165,6 +180,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       tmem_ld32(tS + 64, s + 64);
       tmem_ld32(tS + 96, s + 96);
       tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[t]);            // the tensor core may overwrite S_t with block j+1
       const int kvalid = p.T - j * 128;                  // keys of this block that exist (>= 1)
       if (kvalid < 128) {
 #pragma unroll
@@ -205,23 +223,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       }
       // p = exp2((s - m_used) * scale) -> bf16 pairs -> TMEM (A operand of P.V); row sum in fp32
       const float neg = -m_used * p.scale_log2;
-      float ls[4] = {0.f, 0.f, 0.f, 0.f};
+      const float2 neg2 = make_float2(neg, neg);
+      float2 ls0 = make_float2(0.f, 0.f), ls1 = make_float2(0.f, 0.f);
+      uint32_t w[64];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {                      // 64 keys -> 32 packed words -> one tcgen05.st
-        uint32_t w[32];
-#pragma unroll
-        for (int i = 0; i < 64; i += 4) {
-          const float p0 = ex2_approx(fmaf(s[h * 64 + i], p.scale_log2, neg));
-          const float p1 = ex2_approx(fmaf(s[h * 64 + i + 1], p.scale_log2, neg));
-          const float p2 = ex2_approx(fmaf(s[h * 64 + i + 2], p.scale_log2, neg));
-          const float p3 = ex2_approx(fmaf(s[h * 64 + i + 3], p.scale_log2, neg));
-          ls[0] += p0; ls[1] += p1; ls[2] += p2; ls[3] += p3;
-          w[i >> 1] = pack_bf16x2(p0, p1);
-          w[(i >> 1) + 1] = pack_bf16x2(p2, p3);
-        }
-        tmem_st32(tS + h * 32, w);
+      for (int i = 0; i < 128; i += 4) {
+        const float2 x0 = fma2(make_float2(s[i], s[i + 1]), sc2, neg2);
+        const float2 x1 = fma2(make_float2(s[i + 2], s[i + 3]), sc2, neg2);
+        const float2 p0 = make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
+        const float2 p1 = make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
+        ls0 = add2(ls0, p0);
+        ls1 = add2(ls1, p1);
+        w[i >> 1] = pack_bf16x2(p0.x, p0.y);
+        w[(i >> 1) + 1] = pack_bf16x2(p1.x, p1.y);
       }
-      l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      l_run += (ls0.x + ls0.y) + (ls1.x + ls1.y);
+      if (j > 0) {                                       // P_t is free once P_t V_{j-1} has been read by the tensor core
+        mbar_wait(&o_done[t], (j - 1) & 1, 36 + t);
+        __syncwarp();
+        tc_fence_after();
+      }
+      tmem_st32(tP, w);
+      tmem_st32(tP + 32, w + 32);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
