@@ -156,6 +156,9 @@ static int gemm_residual(const void* a, int lda, const void* w, int ldw, GemmSha
   return gemm_auto<EpiResidual>(a, lda, w, ldw, g, ep, st);
 }
 
+static long long* g_attn_trace = nullptr;   // debug builds (-DLDMAE_ATTN_TRACE): device buffer [2][64][8] of clock64 stamps
+extern "C" int ldmae_attention_trace(long long* dev_buf) { g_attn_trace = dev_buf; return LDMAE_OK; }
+
 static int run_attention(const void* qkv, int ldq, void* out, int ldo, int B, int T, int H, int q_col, int k_col,
                          int v_col, float scale, cudaStream_t st) {
   CUtensorMap tm, tmo;
@@ -167,6 +170,7 @@ static int run_attention(const void* qkv, int ldq, void* out, int ldo, int B, in
     attr = true;
   }
   AttnParams p;
+  p.trace = g_attn_trace;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.T = T; p.H = H; p.ldo = ldo;
   p.q_col = q_col; p.k_col = k_col; p.v_col = v_col;
