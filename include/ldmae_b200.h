@@ -88,9 +88,13 @@ int ldmae_dit_forward_with_cfg(ldmae_dit* h, const float* x, const float* t, flo
  *   tgrid: HOST array of npts fp32 time points (npts - 1 model evaluations)
  *   method: 0 euler, 1 heun2;  use_cfg: model_fn is forward_with_cfg;  cfg_interval_start < 0: no interval
  *   traj (optional, device, [npts, Btot, C, S, S]): every grid state like torchdiffeq returns; NULL keeps only the last. */
+/*   flags: LDMAE_ODE_COND_ONLY_WHEN_UNGUIDED -- on steps with t < cfg_interval_start the guided velocity of the conditional
+ *   half is its own prediction, so only x[:n] is evaluated and advanced; x[n:] is then NOT the reference's second half
+ *   (inference.py:289 discards it: samples.chunk(2)[0]).  Results for x[:n] are identical.  Off by default. */
+#define LDMAE_ODE_COND_ONLY_WHEN_UNGUIDED 1
 int ldmae_sample_ode(ldmae_dit* h, float* x, const int64_t* y, int32_t n, int32_t use_cfg, float cfg_scale,
                      float cfg_interval_start, const float* tgrid, int32_t npts, int32_t method, float* traj,
-                     void* stream);
+                     int32_t flags, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * VMAE f8d16 ViT decoder -- reference LDMAE/tokenizer/models_mae.py:865-887 (decode), :963-973

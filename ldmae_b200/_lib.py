@@ -43,7 +43,7 @@ SYMBOLS = {
     "ldmae_dit_debug_poison": (C.c_int, [vp, i32, vp]),
     "ldmae_dit_debug_read": (C.c_int, [vp, C.c_char_p, vp, i64, vp]),
     "ldmae_dit_forward_with_cfg": (C.c_int, [vp, vp, vp, f32, vp, vp, i32, f32, i32, vp]),
-    "ldmae_sample_ode": (C.c_int, [vp, vp, vp, i32, i32, f32, f32, C.POINTER(C.c_float), i32, i32, vp, vp]),
+    "ldmae_sample_ode": (C.c_int, [vp, vp, vp, i32, i32, f32, f32, C.POINTER(C.c_float), i32, i32, vp, i32, vp]),
     "ldmae_vmae_create": (C.c_int, [C.POINTER(VmaeConfig), C.POINTER(vp)]),
     "ldmae_vmae_destroy": (None, [vp]),
     "ldmae_vmae_load_tensor": (C.c_int, [vp, C.c_char_p, vp, i64, vp]),
@@ -93,6 +93,8 @@ def ptr(t):
     assert t.is_cuda and t.is_contiguous(), "ldmae_b200 expects contiguous CUDA tensors"
     return C.c_void_p(t.data_ptr())
 
+
+ODE_COND_ONLY_WHEN_UNGUIDED = 1
 
 PROF_CLASSES = ("qkv_gemm", "attention", "proj_gemm", "w12_swiglu_gemm", "w3_gemm", "adaln_shift_gemms", "final_gemm",
                 "cond_embed_update", "vmae_decode")

@@ -640,7 +640,7 @@ extern "C" int ldmae_dit_forward_with_cfg(ldmae_dit* h, const float* x, const fl
 
 extern "C" int ldmae_sample_ode(ldmae_dit* h, float* x, const int64_t* y, int32_t n, int32_t use_cfg, float cfg_scale,
                                 float cfg_interval_start, const float* tgrid, int32_t npts, int32_t method, float* traj,
-                                void* stream) {
+                                int32_t flags, void* stream) {
   LDMAE_REQUIRE(h && x && y && tgrid && n >= 1 && npts >= 2, "bad argument");
   LDMAE_REQUIRE(method == 0 || method == 1, "method must be 0 (euler) or 1 (heun2)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -649,21 +649,33 @@ extern "C" int ldmae_sample_ode(ldmae_dit* h, float* x, const int64_t* y, int32_
   const int src_mod = n;
   const int n_half = use_cfg ? n : 0;
   const size_t total = static_cast<size_t>(Btot) * C * HW;
+  const size_t half_total = static_cast<size_t>(n) * C * HW;
+  const bool cond_only = use_cfg && (flags & LDMAE_ODE_COND_ONLY_WHEN_UNGUIDED) != 0;
+  LDMAE_REQUIRE(!(cond_only && traj), "the cond-only shortcut does not keep the unconditional half: no trajectory output");
   if (Btot > h->maxB) { LDMAE_CUDA(cudaStreamSynchronize(st)); LDMAE_TRY(dit_alloc_ws(h, Btot)); }
   if (traj) LDMAE_CUDA(cudaMemcpyAsync(traj, x, total * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  auto guided = [&](float tt) { return (use_cfg && !(cfg_interval_start >= 0.f && tt < cfg_interval_start)) ? 1 : 0; };
+  // One drift evaluation at time tt on state xs, then xout = xin + a*g + b*kprev (g = guided velocity, optionally kept in gout).
+  // Below the guidance interval the guided velocity of the conditional half is its own prediction (lightningdit.py:436-439),
+  // so with LDMAE_ODE_COND_ONLY_WHEN_UNGUIDED only the n conditional samples are evaluated and advanced.
+  auto stage = [&](const float* xs, float tt, float* xout, const float* xin, const float* kprev, float* gout, float a,
+                   float bcoef) -> int {
+    if (cond_only && !guided(tt)) {
+      LDMAE_TRY(dit_forward_impl(h, xs, nullptr, tt, y, h->vbuf.p, n, src_mod, st));
+      return launch_update(xout, xin, h->vbuf.p, kprev, gout, 0, C, HW, cfg_scale, 0, a, bcoef, half_total, st);
+    }
+    LDMAE_TRY(dit_forward_impl(h, xs, nullptr, tt, y, h->vbuf.p, Btot, src_mod, st));
+    return launch_update(xout, xin, h->vbuf.p, kprev, gout, n_half, C, HW, cfg_scale, guided(tt), a, bcoef, total, st);
+  };
   for (int k = 0; k + 1 < npts; ++k) {
     const float t0 = tgrid[k], t1 = tgrid[k + 1];
     const float dt = t1 - t0;
-    auto guided = [&](float tt) { return (use_cfg && !(cfg_interval_start >= 0.f && tt < cfg_interval_start)) ? 1 : 0; };
-    LDMAE_TRY(dit_forward_impl(h, x, nullptr, t0, y, h->vbuf.p, Btot, src_mod, st));
     if (method == 0) {
-      LDMAE_TRY(launch_update(x, x, h->vbuf.p, nullptr, nullptr, n_half, C, HW, cfg_scale, guided(t0), dt, 0.f, total, st));
+      LDMAE_TRY(stage(x, t0, x, x, nullptr, nullptr, dt, 0.f));
     } else {
       // k1 = f(t0, x); xtmp = x + dt*k1; k2 = f(t0+dt, xtmp); x += dt*(k1/2 + k2/2)
-      LDMAE_TRY(launch_update(h->xtmp.p, x, h->vbuf.p, nullptr, h->k1buf.p, n_half, C, HW, cfg_scale, guided(t0), dt, 0.f, total, st));
-      const float tb = t0 + dt;
-      LDMAE_TRY(dit_forward_impl(h, h->xtmp.p, nullptr, tb, y, h->vbuf.p, Btot, src_mod, st));
-      LDMAE_TRY(launch_update(x, x, h->vbuf.p, h->k1buf.p, nullptr, n_half, C, HW, cfg_scale, guided(tb), 0.5f * dt, 0.5f * dt, total, st));
+      LDMAE_TRY(stage(x, t0, h->xtmp.p, x, nullptr, h->k1buf.p, dt, 0.f));
+      LDMAE_TRY(stage(h->xtmp.p, t0 + dt, x, x, h->k1buf.p, nullptr, 0.5f * dt, 0.5f * dt));
     }
     if (traj)
       LDMAE_CUDA(cudaMemcpyAsync(traj + static_cast<size_t>(k + 1) * total, x, total * sizeof(float), cudaMemcpyDeviceToDevice, st));

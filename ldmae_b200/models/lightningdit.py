@@ -312,7 +312,7 @@ class LightningDiT(nn.Module):
         return out
 
     # -- fused sampler entry used by transport.Sampler when model_fn is one of our bound methods
-    def _sample_ode(self, x, y, n, use_cfg, cfg_scale, cfg_interval_start, tgrid, method, keep_trajectory):
+    def _sample_ode(self, x, y, n, use_cfg, cfg_scale, cfg_interval_start, tgrid, method, keep_trajectory, flags=0):
         x = x.detach().float().contiguous().clone()
         y = y.detach().long().contiguous()
         h = self._ensure_handle(x.device, x.shape[0])
@@ -322,7 +322,7 @@ class LightningDiT(nn.Module):
         with torch.cuda.device(x.device):
             _lib.check(_lib.lib().ldmae_sample_ode(h, _lib.ptr(x), _lib.ptr(y), n, int(use_cfg), float(cfg_scale),
                                                    float(cfg_interval_start), grid, npts, int(method), _lib.ptr(traj),
-                                                   _lib.stream_ptr()), "ldmae_sample_ode")
+                                                   int(flags), _lib.stream_ptr()), "ldmae_sample_ode")
         return x, traj
 
 

@@ -20,7 +20,8 @@ class SamplingJob:
     """One rank's sampler + decoder with persistent device / pinned buffers for a fixed batch size."""
 
     def __init__(self, model, vae, *, num_steps=250, sampling_method="euler", cfg_scale=10.0, cfg_interval_start=0.10,
-                 timestep_shift=0.3, latent_mean=None, latent_std=None, latent_multiplier=1.0, device=None):
+                 timestep_shift=0.3, latent_mean=None, latent_std=None, latent_multiplier=1.0, device=None,
+                 cond_only_when_unguided=False):
         self.model, self.vae = model, vae
         self.device = torch.device(device) if device is not None else next(model.parameters()).device
         self.cfg_scale = float(cfg_scale)
@@ -29,7 +30,16 @@ class SamplingJob:
         self.null_class = model.y_embedder.num_classes           # inference.py:279 (hard-coded 1000 there)
         transport = create_transport("Linear", "velocity", None, None, None, use_cosine_loss=False, use_lognorm=True)
         self.sample_fn = Sampler(transport).sample_ode(sampling_method=sampling_method, num_steps=num_steps, atol=1e-6,
-                                                       rtol=1e-3, reverse=False, timestep_shift=timestep_shift)
+                                                       rtol=1e-3, reverse=False, timestep_shift=timestep_shift,
+                                                       cond_only_when_unguided=cond_only_when_unguided)
+        grid = self.sample_fn.t
+        self.cond_only_when_unguided = bool(cond_only_when_unguided and self.use_cfg and cfg_interval_start is not None)
+        # sample-forwards per image actually executed (for FLOP accounting)
+        if self.cond_only_when_unguided:
+            below = int((grid[:-1] < float(cfg_interval_start)).sum())
+            self.sample_forwards_per_image = 2 * (num_steps - 1 - below) + below
+        else:
+            self.sample_forwards_per_image = (2 if self.use_cfg else 1) * (num_steps - 1)
         C = model.in_channels
         self.latent_mean = latent_mean if latent_mean is not None else torch.zeros(1, C, 1, 1)
         self.latent_std = latent_std if latent_std is not None else torch.ones(1, C, 1, 1)

@@ -178,8 +178,13 @@ class Sampler:
         raise NotImplementedError("likelihood ODE is outside the hot path")
 
     def sample_ode(self, *, sampling_method="dopri5", num_steps=50, atol=1e-6, rtol=1e-3, reverse=False,
-                   timestep_shift=0.0, keep_trajectory=None):
-        """Returns ``fn(x, model, **model_kwargs)`` like the reference (transport.py:398-443)."""
+                   timestep_shift=0.0, keep_trajectory=None, cond_only_when_unguided=False):
+        """Returns ``fn(x, model, **model_kwargs)`` like the reference (transport.py:398-443).
+
+        ``cond_only_when_unguided`` (extension, off by default): with ``forward_with_cfg`` and a guidance interval, steps with
+        ``t < cfg_interval_start`` evaluate only the conditional half -- its guided velocity is its own prediction
+        (lightningdit.py:436-439).  The first half of the returned state is identical; the second half is not advanced, so
+        only callers that keep ``chunk(2)[0]`` (inference.py:289) may use it."""
         if reverse:
             raise NotImplementedError("reverse-time ODE is outside the hot path")
         if sampling_method not in _METHODS:
@@ -205,7 +210,8 @@ class Sampler:
                     start = model_kwargs.get("cfg_interval_start", None)
                     start = float(start) if (interval is True and start is not None) else -1.0
                     final, traj = owner._sample_ode(x, y, x.shape[0] // 2, True, model_kwargs["cfg_scale"], start, grid,
-                                                    _METHODS[sampling_method], keep_trajectory)
+                                                    _METHODS[sampling_method], keep_trajectory,
+                                                    flags=1 if (cond_only_when_unguided and start >= 0) else 0)
                 else:
                     final, traj = owner._sample_ode(x, model_kwargs["y"], x.shape[0], False, 1.0, -1.0, grid,
                                                     _METHODS[sampling_method], keep_trajectory)

@@ -144,6 +144,28 @@ def test_vmae_decode_vs_reference_golden(golden_dir, tag, img):
     assert (np.abs(u8a.astype(np.int32) - u8b.astype(np.int32)) <= 1).mean() > 0.999
 
 
+def test_cond_only_shortcut_is_bit_identical_for_the_kept_half(golden_dir):
+    """Below the guidance interval only the conditional half is evaluated; the kept half must not change at all."""
+    from ldmae_b200.transport import Sampler, create_transport
+    from gpu_util import load_npz
+    g = load_npz(golden_dir, "dit_tiny_p1.npz")
+    spec, sd, m = _tiny_model(1, int(g["seed"]))
+    x = torch.from_numpy(g["x"]).cuda()
+    n = x.shape[0] // 2
+    z = torch.cat([x[:n], x[:n]], 0)
+    ycfg = torch.from_numpy(g["ycfg"]).cuda()
+    kw = dict(y=ycfg, cfg_scale=4.0, cfg_interval=True, cfg_interval_start=0.35)
+    smp = Sampler(create_transport("Linear", "velocity", None, None, None))
+    for method, steps in (("euler", 9), ("heun2", 6)):
+        full = smp.sample_ode(sampling_method=method, num_steps=steps, atol=1e-6, rtol=1e-3, reverse=False, timestep_shift=0.3)
+        fast = smp.sample_ode(sampling_method=method, num_steps=steps, atol=1e-6, rtol=1e-3, reverse=False, timestep_shift=0.3,
+                              cond_only_when_unguided=True)
+        assert int((full.t[:-1] < 0.35).sum()) >= 2            # the shortcut is actually exercised
+        a = full(z, m.forward_with_cfg, **kw)[-1]
+        b = fast(z, m.forward_with_cfg, **kw)[-1]
+        assert torch.equal(a[:n], b[:n])
+
+
 def test_sampling_job_vs_oracle():
     """BASELINE config-1 shape at a size the oracle finishes in seconds: tiny DiT + small VMAE, CFG, Euler+shift."""
     from ldmae_b200.models.lightningdit import LightningDiT
