@@ -258,8 +258,14 @@ def run_gpu(args, rank, world, local_rank):
         ms, cnt = gemm_classes[dom]
         flops_per_launch = per_block[dom] * Bf
         achieved = flops_per_launch / (ms / cnt / 1e3) / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp):
+            ent = json.load(open(tp)).get(dom)
+            if ent:
+                traffic = ent["bytes_per_sample_forward"] * Bf          # measured DRAM bytes per launch (ncu capture)
         roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tflops"], "traffic": None, "peak_source": pk["source"],
+                "frac": achieved / pk["tflops"], "traffic": traffic, "peak_source": pk["source"],
                 "flops_per_launch": flops_per_launch, "avg_launch_ms": ms / cnt, "launches_timed": cnt}
     class_ms = {k: round(v[0] / args.steps, 3) for k, v in prof.items()}
     job_flops = fwd_flops * Bf * job.model_evals
