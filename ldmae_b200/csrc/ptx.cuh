@@ -83,7 +83,7 @@ __device__ __forceinline__ uint32_t mbar_probe(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.b32 %0, 1, 0, p;\n\t}\n"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)

@@ -17,7 +17,7 @@ tr = tr.cpu()
 t00 = int(tr[0, 0, 0])
 names = ["wait_S", "ld_S+release", "max(+rescale)", "wait_turn", "exp", "wait_o_done", "st_P"]
 for t in range(2):
-    print(f"tile {t}: block start (rel. cycles) and phase durations")
+    print(f"CTA {t}: block start (rel. cycles) and phase durations")
     for j in range(8):
         st = [int(v) for v in tr[t, j]]
         d = [st[k + 1] - st[k] for k in range(7)]
