@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libldmae_b200.so")
+LIB_PATH = os.environ.get("LDMAE_B200_LIB") or os.path.join(HERE, "libldmae_b200.so")
 
 _lib = None
 

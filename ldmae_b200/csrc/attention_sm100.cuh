@@ -31,6 +31,10 @@ constexpr int kAttnSmemBytes = 1024 + 2 * kAttnTileBytes            // Q0,Q1 (re
                                + 2 * kAttnKVStages * kAttnTileBytes  // K,V rings
                                + 256;
 constexpr float kAttnRescaleLog2 = 8.0f;
+#ifndef LDMAE_ATTN_POLY_EVERY
+#define LDMAE_ATTN_POLY_EVERY 4
+#endif
+constexpr int kAttnPolyEvery = LDMAE_ATTN_POLY_EVERY;   // 1 pair in 2*kAttnPolyEvery uses the polynomial exp2 (1000 = never)
 
 // Optional phase tracing of CTA 0 (debug builds: -DLDMAE_ATTN_TRACE): clock64 stamps per key block and softmax phase.
 #ifdef LDMAE_ATTN_TRACE
@@ -248,7 +252,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         const float2 x0 = fma2(make_float2(s[i], s[i + 1]), sc2, neg2);
         const float2 x1 = fma2(make_float2(s[i + 2], s[i + 3]), sc2, neg2);
         const float2 p0 = make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
-        const float2 p1 = make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
+        // every kAttnPolyEvery-th pair takes the FMA-pipe polynomial instead of the MUFU unit
+        const float2 p1 = ((i / 4) % kAttnPolyEvery == kAttnPolyEvery - 1) ? ex2_poly2(x1) : make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
         ls0 = add2(ls0, p0);
         ls1 = add2(ls1, p1);
         w[i >> 1] = pack_bf16x2(p0.x, p0.y);

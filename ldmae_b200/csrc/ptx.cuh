@@ -336,6 +336,23 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x for a pair of arguments on the FMA / ALU pipes (no MUFU): Cody-Waite split x = n + f, |f| <= 0.5, degree-3
+// polynomial for 2^f (relative error < 7e-4, far below bf16 rounding), exponent added to the result's bit pattern.
+// Used for a fraction of the softmax exponentials, whose MUFU unit is the bottleneck at head_dim 64.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 magic = make_float2(12582912.f, 12582912.f);
+  const float2 t = add2(x, magic);                                   // low mantissa bits = round(x)
+  const float2 fl = add2(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = add2(x, make_float2(-fl.x, -fl.y));
+  float2 r = fma2(f, make_float2(0.0555041f, 0.0555041f), make_float2(0.2402265f, 0.2402265f));
+  r = fma2(r, f, make_float2(0.6931472f, 0.6931472f));
+  r = fma2(r, f, make_float2(1.f, 1.f));
+  r.x = __int_as_float(__float_as_int(r.x) + (__float_as_int(t.x) << 23));
+  r.y = __int_as_float(__float_as_int(r.y) + (__float_as_int(t.y) << 23));
+  return r;
+}
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_tanh_f(float x) {
