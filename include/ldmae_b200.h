@@ -139,6 +139,8 @@ int ldmae_gemm_residual(const void* a_bf16, const void* w_bf16, const float* bia
 int ldmae_attention(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t T, int32_t H, float scale, void* stream);
 /* Debug builds only (-DLDMAE_ATTN_TRACE): device buffer [2][64][8] int64 receiving clock64 phase stamps of CTA 0. */
 int ldmae_attention_trace(long long* dev_buf);
+/* Debug builds only (-DLDMAE_GEMM_TRACE): device buffer [256][8] int64, clock64 stamps of the residual epilogue (CTA 0). */
+int ldmae_gemm_trace(long long* dev_buf);
 /* float <-> bf16 conversion helpers for tests (device, n elements) */
 int ldmae_f32_to_bf16(const float* in, void* out_bf16, int64_t n, void* stream);
 

@@ -53,6 +53,7 @@ SYMBOLS = {
     "ldmae_gemm_residual": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "ldmae_attention": (C.c_int, [vp, vp, i32, i32, i32, f32, vp]),
     "ldmae_attention_trace": (C.c_int, [vp]),
+    "ldmae_gemm_trace": (C.c_int, [vp]),
     "ldmae_f32_to_bf16": (C.c_int, [vp, vp, i64, vp]),
     "ldmae_launch_count": (C.c_longlong, []),
     "ldmae_profile_begin": (C.c_int, []),

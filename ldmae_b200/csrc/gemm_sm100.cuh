@@ -106,7 +106,11 @@ __device__ __forceinline__ float row_rinv(const float* ssq, int row, int slots, 
 __device__ __forceinline__ void stage_vec(float* dst, const float* __restrict__ src, int col0, int ncols, int N, int lane) {
   for (int i = lane * 4; i < ncols; i += 128) *reinterpret_cast<float4*>(dst + i) = ldvec4(src, col0 + i, N);
 }
+// Plain C++ accesses to the staging areas: pointers are derived from the extern __shared__ array without integer casts,
+// so they compile to LDS / STS and -- unlike asm volatile wrappers -- may be overlapped by the scheduler.
 __device__ __forceinline__ float4 lds_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ uint4 ld_tile16(const uint8_t* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void st_tile16(uint8_t* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
 // all rows of this warp (row0 .. row0+31, clipped to M) belong to one sample?
 __device__ __forceinline__ bool warp_rows_one_sample(int row0, int M, int rows_per_sample) {
   const int last = min(row0 + 31, M - 1);
@@ -207,7 +211,7 @@ struct EpiStore : StoreRing {
           w = make_uint4(__float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]),
                          __float_as_uint(v[4 * q + 3]));
         }
-        sts128(sw128_chunk(tile, c.lane, q), w);
+        st_tile16(sw128_chunk(tile, c.lane, q), w);
       }
       release(c, st, &p.omap, tile, n0 + c0, row0);
     }
@@ -227,11 +231,13 @@ struct EpiStore : StoreRing {
 // x travels by TMA in 32-row x 32-column fp32 boxes: loaded kPF chunks ahead (across tile boundaries, i.e. while
 // the tensor core still works on the tile), updated in place in shared memory and stored back from the same tile.
 // This epilogue is HBM-bound (12 bytes per accumulator element), so four warps suffice.
-struct EpiResidual {
+template <int NX /*x tiles per warp*/, int PF /*prefetch distance in chunks*/>
+struct EpiResidualT {
   static constexpr int kWarps = 4;
   static constexpr int kCtaBytes = 0;
-  static constexpr int kNX = 4;     // x tiles in flight per warp
-  static constexpr int kPF = 2;     // prefetch distance (chunks)
+  static constexpr int kNX = NX;
+  static constexpr int kPF = PF;
+  static_assert(PF + 2 <= NX, "a tile is reloaded PF chunks ahead while the stores of the last two chunks may still read theirs");
   static constexpr int kXBytes = 4096, kABytesTile = 2048;
   static constexpr int kVecOff = kNX * kXBytes + 2 * kABytesTile;      // [3][256] floats: bias, gate, gnext of the tile
   static constexpr int kWarpBytes = kVecOff + 4096;
@@ -245,8 +251,14 @@ struct EpiResidual {
     float* ssq;            // [M, ss_slots] per-row partial sums of squares, or nullptr.  Slot = column/128 of the
                            // producing tile: no atomics, so the statistics are bit-reproducible.
     int gate_ld, gnext_ld, rows_per_sample, ss_slots, has_anext;
+    long long* trace;      // debug builds (-DLDMAE_GEMM_TRACE): [256 chunks][8] clock64 stamps of CTA 0, epilogue warp 0
   };
   struct State { int seq, pf_seq, pf_tile, pf_chunk; };
+#ifdef LDMAE_GEMM_TRACE
+#define RES_STAMP(k) do { if (p.trace && blockIdx.x == 0 && s.wq == 0 && lane == 0 && st.seq < 256) p.trace[st.seq * 8 + (k)] = clock64(); } while (0)
+#else
+#define RES_STAMP(k) do { } while (0)
+#endif
   template <class P>
   static __device__ __forceinline__ void cta_init(const P&, uint8_t*, int, int) {}
   static __device__ __forceinline__ void prefetch_maps(const Params& p) {
@@ -273,21 +285,28 @@ struct EpiResidual {
     st.seq = 0; st.pf_seq = 0; st.pf_tile = s.first; st.pf_chunk = 0;
     if (c.lane == 0) pump<BN>(p, g, s, c, st, kPF - 1);
   }
+  // one sample per warp (always true when rows_per_sample is a multiple of 32): the tile's column vectors are staged in
+  // shared memory (kStaged); otherwise every thread reads its own sample's vectors from global memory.  Two
+  // instantiations, so that the hot loop of the common case is branch-free.
   template <int BN, int GC>
   static __device__ __forceinline__ void run(const Params& p, const GemmShape& g, const TileSched& s, const EpiCtx& c, State& st,
-                                             uint32_t acc, int row0, int n0, int /*cbase*/) {
+                                             uint32_t acc, int row0, int n0, int cbase) {
+    if (warp_rows_one_sample(row0, g.M, p.rows_per_sample)) run_t<BN, GC, true>(p, g, s, c, st, acc, row0, n0, cbase);
+    else run_t<BN, GC, false>(p, g, s, c, st, acc, row0, n0, cbase);
+  }
+  template <int BN, int GC, bool kStaged>
+  static __device__ __forceinline__ void run_t(const Params& p, const GemmShape& g, const TileSched& s, const EpiCtx& c, State& st,
+                                               uint32_t acc, int row0, int n0, int /*cbase*/) {
     static_assert(GC == BN && BN <= 256, "the residual epilogue walks the whole tile width");
     const int lane = c.lane;
     const int my_row = row0 + lane;
     const int my_b = (my_row < g.M ? my_row : g.M - 1) / p.rows_per_sample;
     const float* gate = p.gate ? p.gate + static_cast<size_t>(my_b) * p.gate_ld : nullptr;
     const float* gnext = p.has_anext ? p.gnext + static_cast<size_t>(my_b) * p.gnext_ld : nullptr;
-    // one sample per warp (always true when rows_per_sample is a multiple of 32): stage the tile's column vectors
-    const bool staged = warp_rows_one_sample(row0, g.M, p.rows_per_sample);
     float* vbias = reinterpret_cast<float*>(c.smem + kVecOff);
     float* vgate = vbias + 256;
     float* vgnext = vbias + 512;
-    if (staged) {
+    if constexpr (kStaged) {
       stage_vec(vbias, p.bias, n0, BN, g.N, lane);
       if (gate != nullptr) stage_vec(vgate, gate, n0, BN, g.N, lane);
       if (gnext != nullptr) stage_vec(vgnext, gnext, n0, BN, g.N, lane);
@@ -297,32 +316,42 @@ struct EpiResidual {
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= g.N) break;
+      RES_STAMP(0);
       if (lane == 0) {
         tma_store_wait_read<1>();                      // stores issued two chunks ago no longer read their tiles
+        RES_STAMP(1);
         pump<BN>(p, g, s, c, st, st.seq + kPF);
       }
       __syncwarp();
+      RES_STAMP(2);
       uint8_t* xt = c.smem + (st.seq % kNX) * kXBytes;
       uint8_t* at = c.smem + kNX * kXBytes + (st.seq & 1) * kABytesTile;
       mbar_wait(&c.bars[st.seq % kNX], (st.seq / kNX) & 1, 500);
       __syncwarp();
+      RES_STAMP(3);
       float v[32];
       tmem_ld32(acc + c0, v);
       tmem_ld_wait();
+      RES_STAMP(4);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const int col = n0 + c0 + 4 * q;
-        const float4 bi = staged ? lds_f4(vbias + c0 + 4 * q) : ldvec4(p.bias, col, g.N);
-        float4 gt = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (gate != nullptr) gt = staged ? lds_f4(vgate + c0 + 4 * q) : ldvec4(gate, col, g.N);
+        float4 bi, gt = make_float4(1.f, 1.f, 1.f, 1.f);
+        if constexpr (kStaged) {
+          bi = lds_f4(vbias + c0 + 4 * q);
+          if (gate != nullptr) gt = lds_f4(vgate + c0 + 4 * q);
+        } else {
+          bi = ldvec4(p.bias, col, g.N);
+          if (gate != nullptr) gt = ldvec4(gate, col, g.N);
+        }
         uint8_t* xp = sw128_chunk(xt, lane, q);
-        const uint4 xr = lds128(xp);
+        const uint4 xr = ld_tile16(xp);
         float4 xn;
         xn.x = __uint_as_float(xr.x) + (v[4 * q] + bi.x) * gt.x;
         xn.y = __uint_as_float(xr.y) + (v[4 * q + 1] + bi.y) * gt.y;
         xn.z = __uint_as_float(xr.z) + (v[4 * q + 2] + bi.z) * gt.z;
         xn.w = __uint_as_float(xr.w) + (v[4 * q + 3] + bi.w) * gt.w;
-        sts128(xp, make_uint4(__float_as_uint(xn.x), __float_as_uint(xn.y), __float_as_uint(xn.z), __float_as_uint(xn.w)));
+        st_tile16(xp, make_uint4(__float_as_uint(xn.x), __float_as_uint(xn.y), __float_as_uint(xn.z), __float_as_uint(xn.w)));
         // columns >= N hold zeros (TMA zero fill + zero bias/acc), so they do not disturb the statistics
         ss = fmaf(xn.x, xn.x, ss); ss = fmaf(xn.y, xn.y, ss); ss = fmaf(xn.z, xn.z, ss); ss = fmaf(xn.w, xn.w, ss);
         v[4 * q] = xn.x; v[4 * q + 1] = xn.y; v[4 * q + 2] = xn.z; v[4 * q + 3] = xn.w;
@@ -331,13 +360,15 @@ struct EpiResidual {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int col = n0 + c0 + 8 * q;
-          const float4 g0 = staged ? lds_f4(vgnext + c0 + 8 * q) : ldvec4(gnext, col, g.N);
-          const float4 g1 = staged ? lds_f4(vgnext + c0 + 8 * q + 4) : ldvec4(gnext, col + 4, g.N);
-          sts128(sw64_chunk(at, lane, q),
+          float4 g0, g1;
+          if constexpr (kStaged) { g0 = lds_f4(vgnext + c0 + 8 * q); g1 = lds_f4(vgnext + c0 + 8 * q + 4); }
+          else { g0 = ldvec4(gnext, col, g.N); g1 = ldvec4(gnext, col + 4, g.N); }
+          st_tile16(sw64_chunk(at, lane, q),
                  make_uint4(pack_bf16x2(v[8 * q] * g0.x, v[8 * q + 1] * g0.y), pack_bf16x2(v[8 * q + 2] * g0.z, v[8 * q + 3] * g0.w),
                             pack_bf16x2(v[8 * q + 4] * g1.x, v[8 * q + 5] * g1.y), pack_bf16x2(v[8 * q + 6] * g1.z, v[8 * q + 7] * g1.w)));
         }
       }
+      RES_STAMP(5);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
@@ -345,6 +376,7 @@ struct EpiResidual {
         if (p.has_anext) tma_store_2d(&p.amap, at, n0 + c0, row0);
         tma_store_commit();
       }
+      RES_STAMP(6);
       ++st.seq;
     }
     if (p.ssq != nullptr && my_row < g.M) {
@@ -357,6 +389,9 @@ struct EpiResidual {
     if (c.lane == 0) tma_store_wait_read<0>();
   }
 };
+
+using EpiResidual = EpiResidualT<4, 2>;        // w3 (K = 4D/1.5: tensor-bound, keeps a 4-stage operand ring)
+using EpiResidualDeep = EpiResidualT<6, 4>;    // proj (K = D: HBM-bound, deeper residual prefetch, 3-stage operand ring)
 
 // QKV projection of LightningDiT attention (lightningdit.py:68-74) on the pre-scaled operand:
 //   v = acc * rsqrt(ssq[row]/D + eps) + cvec[b,col]        (= Linear(modulate(RMSNorm(x))) incl. bias)
@@ -393,8 +428,16 @@ struct EpiQKV : StoreRing {
     st.seq = 0;
   }
   template <int BN, int GC>
-  static __device__ __forceinline__ void run(const Params& p, const GemmShape& g, const TileSched&, const EpiCtx& c, State& st,
+  static __device__ __forceinline__ void run(const Params& p, const GemmShape& g, const TileSched& s, const EpiCtx& c, State& st,
                                              uint32_t acc, int row0, int n0, int cbase) {
+    // fast instantiation: one sample per warp and the RoPE table in shared memory (branch-free hot loop)
+    if (warp_rows_one_sample(row0, g.M, p.rows_per_sample) && (p.rope == nullptr || rope_in_smem(p)))
+      run_t<BN, GC, true>(p, g, s, c, st, acc, row0, n0, cbase);
+    else run_t<BN, GC, false>(p, g, s, c, st, acc, row0, n0, cbase);
+  }
+  template <int BN, int GC, bool kFast>
+  static __device__ __forceinline__ void run_t(const Params& p, const GemmShape& g, const TileSched&, const EpiCtx& c, State& st,
+                                               uint32_t acc, int row0, int n0, int cbase) {
     static_assert(GC % 64 == 0 && GC <= 256, "QKV epilogue works on whole 64-wide heads");
     const int lane = c.lane;
     const int my_row = min(row0 + lane, g.M - 1);
@@ -402,20 +445,22 @@ struct EpiQKV : StoreRing {
     const int tok = my_row % p.rows_per_sample;
     const float rinv = row_rinv(p.ssq, my_row, p.ss_slots, p.inv_D, p.eps_row);
     const float* cv = p.cvec + static_cast<size_t>(my_b) * g.N;
-    const bool staged = warp_rows_one_sample(row0, g.M, p.rows_per_sample);
+    const bool staged = kFast || warp_rows_one_sample(row0, g.M, p.rows_per_sample);
     float* vcv = reinterpret_cast<float*>(c.smem + kVecOff);       // [GC] cvec of this tile / group
     float* vnw = vcv + 256;                                        // [64 q_norm | 64 k_norm]
     if (staged) stage_vec(vcv, cv, n0 + cbase, GC, g.N, lane);
     if (p.qw != nullptr) {
-      if (lane < 16) *reinterpret_cast<float4*>(vnw + lane * 4) = __ldg(reinterpret_cast<const float4*>(p.qw) + lane);
-      else *reinterpret_cast<float4*>(vnw + lane * 4) = __ldg(reinterpret_cast<const float4*>(p.kw) + lane - 16);
+      *reinterpret_cast<float4*>(vnw + lane * 4) =
+          lane < 16 ? __ldg(reinterpret_cast<const float4*>(p.qw) + lane) : __ldg(reinterpret_cast<const float4*>(p.kw) + lane - 16);
     }
     __syncwarp();
-    const bool rsm = rope_in_smem(p);
-    const float* rbase = rsm ? reinterpret_cast<const float*>(c.cta) : p.rope;
-    const int rpitch = rsm ? kRopePitch : 32;
-    const float* rope_h = p.rope ? rbase + static_cast<size_t>(tok / p.grid) * rpitch : nullptr;
-    const float* rope_w = p.rope ? rbase + static_cast<size_t>(p.grid + tok % p.grid) * rpitch : nullptr;
+    const bool rsm = kFast || rope_in_smem(p);
+    // two pointer pairs so that the shared-memory copy is read with LDS (a pointer that may be either space is generic)
+    const float* cta_tab = reinterpret_cast<const float*>(c.cta);
+    const float* sm_h = cta_tab + (tok / p.grid) * kRopePitch;
+    const float* sm_w = cta_tab + (p.grid + tok % p.grid) * kRopePitch;
+    const float* gl_h = p.rope ? p.rope + static_cast<size_t>(tok / p.grid) * 32 : nullptr;
+    const float* gl_w = p.rope ? p.rope + static_cast<size_t>(p.grid + tok % p.grid) * 32 : nullptr;
 #pragma unroll 1
     for (int c0 = cbase; c0 < cbase + GC; c0 += 64) {
       const int colbase = n0 + c0;
@@ -429,7 +474,9 @@ struct EpiQKV : StoreRing {
       float ms = 0.f;
 #pragma unroll
       for (int j = 0; j < 64; j += 4) {
-        const float4 cc = staged ? lds_f4(vcv + (c0 - cbase) + j) : ldvec4(cv, colbase + j, g.N);
+        float4 cc;
+        if constexpr (kFast) cc = lds_f4(vcv + (c0 - cbase) + j);
+        else cc = staged ? lds_f4(vcv + (c0 - cbase) + j) : ldvec4(cv, colbase + j, g.N);
         v[j] = fmaf(v[j], rinv, cc.x); v[j + 1] = fmaf(v[j + 1], rinv, cc.y);
         v[j + 2] = fmaf(v[j + 2], rinv, cc.z); v[j + 3] = fmaf(v[j + 3], rinv, cc.w);
         ms = fmaf(v[j], v[j], ms); ms = fmaf(v[j + 1], v[j + 1], ms);
@@ -444,15 +491,16 @@ struct EpiQKV : StoreRing {
           v[j] *= hs * w4.x; v[j + 1] *= hs * w4.y; v[j + 2] *= hs * w4.z; v[j + 3] *= hs * w4.w;
         }
       }
-      if (which < 2 && rope_h != nullptr) {
+      if (which < 2 && p.rope != nullptr) {
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-          const float* tab = half == 0 ? rope_h : rope_w;
+          const float* stab = half == 0 ? sm_h : sm_w;
+          const float* gtab = half == 0 ? gl_h : gl_w;
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
             float4 cs, sn;
-            if (rsm) { cs = lds_f4(tab + i); sn = lds_f4(tab + 16 + i); }
-            else { cs = __ldg(reinterpret_cast<const float4*>(tab + i)); sn = __ldg(reinterpret_cast<const float4*>(tab + 16 + i)); }
+            if (kFast || rsm) { cs = lds_f4(stab + i); sn = lds_f4(stab + 16 + i); }
+            else { cs = __ldg(reinterpret_cast<const float4*>(gtab + i)); sn = __ldg(reinterpret_cast<const float4*>(gtab + 16 + i)); }
             const float cq[4] = {cs.x, cs.y, cs.z, cs.w}, sq[4] = {sn.x, sn.y, sn.z, sn.w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -466,7 +514,7 @@ struct EpiQKV : StoreRing {
       }
 #pragma unroll
       for (int q = 0; q < 8; ++q)
-        sts128(sw128_chunk(tile, lane, q),
+        st_tile16(sw128_chunk(tile, lane, q),
                make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
                           pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7])));
       release(c, st, &p.omap, tile, colbase, row0);
@@ -494,17 +542,22 @@ struct EpiSwiGLU : StoreRing {
     st.seq = 0;
   }
   template <int BN, int GC>
-  static __device__ __forceinline__ void run(const Params& p, const GemmShape& g, const TileSched&, const EpiCtx& c, State& st,
+  static __device__ __forceinline__ void run(const Params& p, const GemmShape& g, const TileSched& s, const EpiCtx& c, State& st,
                                              uint32_t acc, int row0, int n0, int cbase) {
+    if (warp_rows_one_sample(row0, g.M, p.rows_per_sample)) run_t<BN, GC, true>(p, g, s, c, st, acc, row0, n0, cbase);
+    else run_t<BN, GC, false>(p, g, s, c, st, acc, row0, n0, cbase);
+  }
+  template <int BN, int GC, bool kStaged>
+  static __device__ __forceinline__ void run_t(const Params& p, const GemmShape& g, const TileSched&, const EpiCtx& c, State& st,
+                                               uint32_t acc, int row0, int n0, int cbase) {
     static_assert(GC % 128 == 0 && GC <= 512, "SwiGLU epilogue consumes 128 accumulator columns per staged block");
     const int lane = c.lane;
     const int my_row = min(row0 + lane, g.M - 1);
     const int my_b = my_row / p.rows_per_sample;
     const float rinv = row_rinv(p.ssq, my_row, p.ss_slots, p.inv_D, p.eps_row);
     const float* cv = p.cvec + static_cast<size_t>(my_b) * g.N;
-    const bool staged = warp_rows_one_sample(row0, g.M, p.rows_per_sample);
     float* vcv = reinterpret_cast<float*>(c.smem + kVecOff);
-    if (staged) {
+    if constexpr (kStaged) {
       stage_vec(vcv, cv, n0 + cbase, GC, g.N, lane);
       __syncwarp();
     }
@@ -521,7 +574,9 @@ struct EpiSwiGLU : StoreRing {
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 64; j += 4) {
-          const float4 cc = staged ? lds_f4(vcv + (cb - cbase) + j) : ldvec4(cv, n0 + cb + j, g.N);
+          float4 cc;
+          if constexpr (kStaged) cc = lds_f4(vcv + (cb - cbase) + j);
+          else cc = ldvec4(cv, n0 + cb + j, g.N);
           v[j] = fmaf(v[j], rinv, cc.x); v[j + 1] = fmaf(v[j + 1], rinv, cc.y);
           v[j + 2] = fmaf(v[j + 2], rinv, cc.z); v[j + 3] = fmaf(v[j + 3], rinv, cc.w);
         }
@@ -531,7 +586,7 @@ struct EpiSwiGLU : StoreRing {
           w[j >> 1] = pack_bf16x2(silu_f(v[j]) * v[32 + j], silu_f(v[j + 1]) * v[32 + j + 1]);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          sts128(sw128_chunk(tile, lane, half * 4 + q), make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]));
+          st_tile16(sw128_chunk(tile, lane, half * 4 + q), make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]));
       }
       release(c, st, &p.omap, tile, (n0 + c0) / 2, row0);
     }
@@ -605,8 +660,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                const GemmShape g, const __grid_constant__ typename Epi::Params ep) {
   using Cfg = GemmCfg<BN, CG, Epi>;
   constexpr int kStages = Cfg::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment comes from the declaration (no integer round trip: the compiler must keep seeing a shared-space
+  // pointer, otherwise every epilogue access becomes a generic LD.E / ST.E); checked once below
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * Cfg::kABytes;
   uint8_t* smem_epi = smem + kStages * Cfg::kStageBytes;                       // Epi::kWarps x kWarpBytes, then kCtaBytes

@@ -29,6 +29,7 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 long long g_launch_count = 0;
+static long long* g_gemm_trace = nullptr;   // debug builds (-DLDMAE_GEMM_TRACE): residual-epilogue clock stamps
 
 // Optional per-kernel-class device timing (CUDA events on the launching stream), used by bench.py for the
 // roofline of the dominant kernel.  Classes: 0 qkv GEMM, 1 attention, 2 proj GEMM, 3 w12 (SwiGLU) GEMM,
@@ -146,16 +147,26 @@ static int gemm_store(const void* a, int lda, const void* w, int ldw, GemmShape 
 static int gemm_residual(const void* a, int lda, const void* w, int ldw, GemmShape g, float* x, int ldx, const float* bias,
                          const float* gate, int gate_ld, const float* gnext, int gnext_ld, __nv_bfloat16* anext, float* ssq,
                          int ss_slots, int rows_per_sample, cudaStream_t st) {
-  EpiResidual::Params ep;
+  typename EpiResidual::Params ep;
   LDMAE_TRY(make_tmap_out_f32(&ep.xmap, x, g.M, g.N, ldx));
   ep.has_anext = anext != nullptr;
   if (anext) LDMAE_TRY(make_tmap_2d(&ep.amap, anext, 2, g.M, g.N, ldx, 32, 32, 64));
   else ep.amap = ep.xmap;
   ep.bias = bias; ep.gate = gate; ep.gnext = gnext; ep.ssq = ssq;
   ep.gate_ld = gate_ld; ep.gnext_ld = gnext_ld; ep.rows_per_sample = rows_per_sample; ep.ss_slots = ss_slots;
+  ep.trace = g_gemm_trace;
+  static int deep = -1;
+  if (deep < 0) { const char* e = getenv("LDMAE_RESID_DEEP"); deep = e ? atoi(e) : 1; }
+  if (deep && g.K <= 1024 && g.M > 128) {
+    // short K: the epilogue's residual traffic, not the tensor core, bounds the kernel
+    EpiResidualDeep::Params ed;
+    memcpy(&ed, &ep, sizeof ed);
+    return gemm_auto<EpiResidualDeep>(a, lda, w, ldw, g, ed, st);
+  }
   return gemm_auto<EpiResidual>(a, lda, w, ldw, g, ep, st);
 }
 
+extern "C" int ldmae_gemm_trace(long long* dev_buf) { g_gemm_trace = dev_buf; return LDMAE_OK; }
 static long long* g_attn_trace = nullptr;   // debug builds (-DLDMAE_ATTN_TRACE): device buffer [2][64][8] of clock64 stamps
 extern "C" int ldmae_attention_trace(long long* dev_buf) { g_attn_trace = dev_buf; return LDMAE_OK; }
 
