@@ -137,6 +137,19 @@ int ldmae_gemm_residual(const void* a_bf16, const void* w_bf16, const float* bia
                         void* stream);
 /* softmax(q k^T * scale) v over qkv [B*T, 3*H*64] bf16 (columns q|k|v, head-major) -> out [B*T, H*64] bf16. */
 int ldmae_attention(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t T, int32_t H, float scale, void* stream);
+/* Training forward of the same attention: additionally writes lse2 [B, H, T (+64 floats of padding at the end)] =
+ * log2(sum_j exp(s_ij * scale)), the row statistic the backward needs. */
+int ldmae_attention_lse(const void* qkv_bf16, void* out_bf16, float* lse2, int32_t B, int32_t T, int32_t H, float scale,
+                        void* stream);
+/* Gradient of ldmae_attention (the backward of F.scaled_dot_product_attention at models/lightningdit.py:77):
+ * dqkv [B*T, 3*H*64] bf16 (dq | dk | dv, same layout as qkv) from dout [B*T, H*64] bf16, the forward's out and lse2;
+ * delta_ws: workspace [B*H*T + 64] fp32.  T must be a multiple of 4. */
+int ldmae_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse2, float* delta_ws,
+                        void* dqkv_bf16, int32_t B, int32_t T, int32_t H, float scale, void* stream);
+/* Weight-gradient GEMM (the dW of every nn.Linear on the path): c[N1,N2] (fp32) += alpha * sum_m p[m,N1] * q[m,N2];
+ * p = gradient of the Linear's output [M,N1] bf16, q = the Linear's input [M,N2] bf16; N1, N2 multiples of 8. */
+int ldmae_gemm_wgrad(const void* p_bf16, const void* q_bf16, float* c, int32_t N1, int32_t N2, int32_t M, float alpha,
+                     void* stream);
 /* Debug builds only (-DLDMAE_ATTN_TRACE): device buffer [2][64][8] int64 receiving clock64 phase stamps of CTA 0. */
 int ldmae_attention_trace(long long* dev_buf);
 /* Debug builds only (-DLDMAE_GEMM_TRACE): device buffer [256][8] int64, clock64 stamps of the residual epilogue (CTA 0). */

@@ -47,6 +47,7 @@ constexpr int kAttnPolyEvery = LDMAE_ATTN_POLY_EVERY;   // 1 pair in 2*kAttnPoly
 struct AttnParams {
   long long* trace;    // [2 tiles][64 blocks][8 stamps] or nullptr (debug builds)
   __nv_bfloat16* out;  // [B*T, ldo]
+  float* lse2;         // [B, H, T] log2-domain log-sum-exp of the scaled scores (training: read by the backward) or nullptr
   int T, H, ldo;
   int q_col, k_col, v_col;  // column offsets of the q / k / v sections inside a QKV row
   float scale_log2;         // softmax scale * log2(e)
@@ -279,6 +280,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     tc_fence_after();
     const float inv_l = 1.f / l_run;
     const int q_tok0 = qpair * 256 + t * 128 + wq * 32;  // first query token of this warp
+    if (p.lse2 != nullptr && q_tok0 + lane < p.T)
+      p.lse2[(static_cast<size_t>(b) * p.H + head) * p.T + q_tok0 + lane] = fmaf(m_used, p.scale_log2, log2f(l_run));
     const bool whole = q_tok0 + 32 <= p.T;               // all 32 rows of the warp exist -> TMA store
     uint8_t* stage = sQ + t * kAttnTileBytes + wq * 4096;
     __nv_bfloat16* dst = p.out + static_cast<size_t>(row_base + q_tok0 + lane) * p.ldo + head * 64;

@@ -8,8 +8,10 @@
 #include <string>
 #include <vector>
 
+#include "attention_bwd_sm100.cuh"
 #include "attention_sm100.cuh"
 #include "common.cuh"
+#include "gemm_wgrad_sm100.cuh"
 #include "elementwise.cuh"
 
 namespace ldmae {
@@ -171,7 +173,7 @@ static long long* g_attn_trace = nullptr;   // debug builds (-DLDMAE_ATTN_TRACE)
 extern "C" int ldmae_attention_trace(long long* dev_buf) { g_attn_trace = dev_buf; return LDMAE_OK; }
 
 static int run_attention(const void* qkv, int ldq, void* out, int ldo, int B, int T, int H, int q_col, int k_col,
-                         int v_col, float scale, cudaStream_t st) {
+                         int v_col, float scale, cudaStream_t st, float* lse2 = nullptr) {
   CUtensorMap tm, tmo;
   LDMAE_TRY(make_tmap_bf16(&tm, qkv, B * T, ldq, ldq, 128));
   LDMAE_TRY(make_tmap_out_bf16(&tmo, out, B * T, H * 64, ldo));
@@ -183,12 +185,88 @@ static int run_attention(const void* qkv, int ldq, void* out, int ldo, int B, in
   AttnParams p;
   p.trace = g_attn_trace;
   p.out = static_cast<__nv_bfloat16*>(out);
+  p.lse2 = lse2;
   p.T = T; p.H = H; p.ldo = ldo;
   p.q_col = q_col; p.k_col = k_col; p.v_col = v_col;
   p.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid(cdiv(T, 256), H, B);
   attn_fwd_kernel<<<grid, kAttnThreads, kAttnSmemBytes, st>>>(tm, tmo, p);
   LDMAE_LAUNCH_CHECK();
+  return LDMAE_OK;
+}
+
+// Backward of run_attention: dqkv [B*T, ldq] (same column layout as qkv) from dO [B*T, ldo], the forward output o,
+// the forward's lse2 [B,H,T] and a delta workspace [B,H,T] (both padded by 64 floats).
+static int run_attention_bwd(const void* qkv, int ldq, const void* o, const void* d_o, int ldo, const float* lse2, float* delta,
+                             void* dqkv, int B, int T, int H, int q_col, int k_col, int v_col, float scale, cudaStream_t st) {
+  LDMAE_REQUIRE(ldo == H * 64, "attention backward expects a dense [B*T, H*64] output gradient");
+  LDMAE_REQUIRE(T % 4 == 0, "attention backward: T must be a multiple of 4 (16-byte aligned statistics rows)");
+  CUtensorMap tqr, tqc, tdr, tdc;
+  LDMAE_TRY(make_tmap_bf16(&tqr, qkv, B * T, ldq, ldq, 128));
+  LDMAE_TRY(make_tmap_bf16(&tqc, qkv, B * T, ldq, ldq, 64));
+  LDMAE_TRY(make_tmap_bf16(&tdr, d_o, B * T, ldo, ldo, 128));
+  LDMAE_TRY(make_tmap_bf16(&tdc, d_o, B * T, ldo, ldo, 64));
+  static bool attr = false;
+  if (!attr) {
+    LDMAE_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAbSmemBytes));
+    LDMAE_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAbSmemBytes));
+    attr = true;
+  }
+  attn_delta_kernel<<<cdiv(static_cast<size_t>(B) * T, 8), 256, 0, st>>>(delta, static_cast<const __nv_bfloat16*>(d_o),
+                                                                         static_cast<const __nv_bfloat16*>(o), B, T, H);
+  LDMAE_LAUNCH_CHECK();
+  AttnBwdParams p;
+  p.lse2 = lse2; p.delta = delta; p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+  p.T = T; p.H = H; p.ld = ldq; p.q_col = q_col; p.k_col = k_col; p.v_col = v_col;
+  p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid(cdiv(T, 128), H, B);
+  attn_bwd_kernel<true><<<grid, kAbThreads, kAbSmemBytes, st>>>(tqr, tqc, tdr, tdc, p);
+  LDMAE_LAUNCH_CHECK();
+  attn_bwd_kernel<false><<<grid, kAbThreads, kAbSmemBytes, st>>>(tqr, tqc, tdr, tdc, p);
+  LDMAE_LAUNCH_CHECK();
+  return LDMAE_OK;
+}
+
+// C[N1,N2] (fp32, leading dimension ldc) += alpha * sum_m p[m,N1] * q[m,N2]   (weight gradients; see gemm_wgrad_sm100.cuh)
+static int gemm_wgrad(const void* pm, int ldp, const void* qm, int ldq, float* c, int ldc, int N1, int N2, int M, float alpha,
+                      cudaStream_t st) {
+  LDMAE_REQUIRE(N1 > 0 && N2 > 0 && M > 0, "wgrad: empty shape %d %d %d", N1, N2, M);
+  LDMAE_REQUIRE(ldp % 8 == 0 && ldq % 8 == 0 && ldc % 4 == 0, "wgrad: leading dimensions must give 16-byte row pitches");
+  constexpr int BN = 256, CG = 2;
+  using Cfg = WgradCfg<BN, CG>;
+  CUtensorMap tp, tq;
+  LDMAE_TRY(make_tmap_2d(&tp, pm, 2, M, N1, ldp, 64, 64, 128));
+  LDMAE_TRY(make_tmap_2d(&tq, qm, 2, M, N2, ldq, 64, 64, 128));
+  EpiAccum::Params ep;
+  LDMAE_TRY(make_tmap_out_f32(&ep.cmap, c, N1, N2, ldc));
+  ep.alpha = alpha;
+  auto kern = gemm_wgrad_kernel<BN, CG>;
+  static bool attr = false;
+  if (!attr) {
+    LDMAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr = true;
+  }
+  const int tiles = ((N1 + kBM * CG - 1) / (kBM * CG)) * ((N2 + BN - 1) / BN);
+  const int num_kb = (M + kBK - 1) / kBK;
+  const int clusters = device_sm_count() / CG;
+  // split the contraction so that every cluster gets work: about two waves of units, at least 8 k-blocks per unit
+  int splits = std::max(1, (2 * clusters + tiles - 1) / tiles);
+  splits = std::min(splits, std::max(1, num_kb / 8));
+  int kb_per = (num_kb + splits - 1) / splits;
+  splits = (num_kb + kb_per - 1) / kb_per;            // no empty unit
+  WgradShape g{N1, N2, M, splits, kb_per};
+  const long long units = static_cast<long long>(tiles) * splits;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(std::min<long long>(units, clusters) * CG));
+  cfg.blockDim = dim3(Cfg::kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  LDMAE_CUDA(cudaLaunchKernelEx(&cfg, kern, tp, tq, g, ep));
+  ++g_launch_count;
   return LDMAE_OK;
 }
 
@@ -934,6 +1012,22 @@ extern "C" int ldmae_gemm_residual(const void* a, const void* w, const float* bi
 extern "C" int ldmae_attention(const void* qkv, void* out, int32_t B, int32_t T, int32_t H, float scale, void* stream) {
   LDMAE_TRY(require_sm100());
   return run_attention(qkv, 3 * H * 64, out, H * 64, B, T, H, 0, H * 64, 2 * H * 64, scale, static_cast<cudaStream_t>(stream));
+}
+extern "C" int ldmae_attention_lse(const void* qkv, void* out, float* lse2, int32_t B, int32_t T, int32_t H, float scale,
+                                   void* stream) {
+  LDMAE_TRY(require_sm100());
+  return run_attention(qkv, 3 * H * 64, out, H * 64, B, T, H, 0, H * 64, 2 * H * 64, scale, static_cast<cudaStream_t>(stream), lse2);
+}
+extern "C" int ldmae_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, float* delta_ws,
+                                   void* dqkv, int32_t B, int32_t T, int32_t H, float scale, void* stream) {
+  LDMAE_TRY(require_sm100());
+  return run_attention_bwd(qkv, 3 * H * 64, out, dout, H * 64, lse2, delta_ws, dqkv, B, T, H, 0, H * 64, 2 * H * 64, scale,
+                           static_cast<cudaStream_t>(stream));
+}
+extern "C" int ldmae_gemm_wgrad(const void* p_bf16, const void* q_bf16, float* c, int32_t N1, int32_t N2, int32_t M, float alpha,
+                                void* stream) {
+  LDMAE_TRY(require_sm100());
+  return gemm_wgrad(p_bf16, N1, q_bf16, N2, c, N2, N1, N2, M, alpha, static_cast<cudaStream_t>(stream));
 }
 
 __global__ void f32_to_bf16_kernel(__nv_bfloat16* out, const float* in, size_t n) {
