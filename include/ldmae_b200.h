@@ -35,7 +35,7 @@ long long ldmae_launch_count(void);
 /* Per-kernel-class device timing with CUDA events on the launching stream (bench.py roofline).
  * Classes: 0 qkv GEMM, 1 attention, 2 proj GEMM, 3 w12/SwiGLU GEMM, 4 w3 GEMM, 5 adaLN + shift-vector GEMMs,
  * 6 final-layer GEMM, 7 conditioning / patch embed / ODE update, 8 VMAE decode. */
-#define LDMAE_PROF_CLASSES 9
+#define LDMAE_PROF_CLASSES 13   /* training adds: 9 data-gradient GEMMs, 10 weight-gradient GEMMs, 11 attention backward, 12 HBM-bound backward kernels */
 int ldmae_profile_begin(void);
 int ldmae_profile_end(double* ms_per_class, long long* scopes_per_class, int32_t nclasses);
 
@@ -68,6 +68,21 @@ int ldmae_dit_finalize(ldmae_dit* h, void* stream);
  *   src_mod: sample b reads x[b % src_mod] (pass B for a plain forward; n for forward_with_cfg's cat[half,half]). */
 int ldmae_dit_forward(ldmae_dit* h, const float* x, const float* t, float t_scalar, const int64_t* y, float* out,
                       int32_t B, int32_t src_mod, void* stream);
+
+/* Training (reference transport/transport.py:169-215 + train_accum.py:215-246): the forward that keeps what the
+ * backward needs, the backward (gradients of every trainable parameter from dL/d(output) [B,C,S,S]), and gradient
+ * read-out in the reference's state_dict layout (`name` = state_dict key; pos_embed and the RoPE buffers have none).
+ * x [B,C,S,S], t [B], y [B] (after the caller's label dropout, lightningdit.py:157-160).  Gradients are valid until the
+ * next ldmae_dit_backward. */
+int ldmae_dit_train_forward(ldmae_dit* h, const float* x, const float* t, const int64_t* y, float* out, int32_t B, void* stream);
+int ldmae_dit_backward(ldmae_dit* h, const float* dout, int32_t B, void* stream);
+int ldmae_dit_grad_read(ldmae_dit* h, const char* name, float* dst, int64_t numel, void* stream);
+/* Fused torch.optim.AdamW step + EMA update (train_accum.py:121,240-246,337-347) on flat fp32 device buffers of n
+ * elements (16-byte aligned); ema may be NULL; grad is multiplied by grad_scale first (1/world_size after an all-reduce);
+ * step counts from 1. */
+int ldmae_adamw_ema_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, int64_t n, float lr,
+                         float beta1, float beta2, float eps, float weight_decay, int32_t step, float ema_decay, float grad_scale,
+                         void* stream);
 
 /* Test hooks: make ldmae_dit_forward return after `stages` launch groups (-1 = run everything; 1 conditioning,
  * 2 adaLN, 3 shift vectors, 4 patch embed, then 5 per block: qkv, attention, proj, w12, w3), and copy a named

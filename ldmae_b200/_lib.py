@@ -39,6 +39,10 @@ SYMBOLS = {
     "ldmae_dit_load_tensor": (C.c_int, [vp, C.c_char_p, vp, i64, vp]),
     "ldmae_dit_finalize": (C.c_int, [vp, vp]),
     "ldmae_dit_forward": (C.c_int, [vp, vp, vp, f32, vp, vp, i32, i32, vp]),
+    "ldmae_dit_train_forward": (C.c_int, [vp, vp, vp, vp, vp, i32, vp]),
+    "ldmae_dit_backward": (C.c_int, [vp, vp, i32, vp]),
+    "ldmae_dit_grad_read": (C.c_int, [vp, C.c_char_p, vp, i64, vp]),
+    "ldmae_adamw_ema_step": (C.c_int, [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, f32, vp]),
     "ldmae_dit_debug_stop": (C.c_int, [vp, i32]),
     "ldmae_dit_debug_poison": (C.c_int, [vp, i32, vp]),
     "ldmae_dit_debug_read": (C.c_int, [vp, C.c_char_p, vp, i64, vp]),
@@ -101,7 +105,7 @@ def ptr(t):
 ODE_COND_ONLY_WHEN_UNGUIDED = 1
 
 PROF_CLASSES = ("qkv_gemm", "attention", "proj_gemm", "w12_swiglu_gemm", "w3_gemm", "adaln_shift_gemms", "final_gemm",
-                "cond_embed_update", "vmae_decode")
+                "cond_embed_update", "vmae_decode", "bwd_dgrad_gemms", "bwd_wgrad_gemms", "bwd_attention", "bwd_hbm_kernels")
 
 
 def profile_begin():

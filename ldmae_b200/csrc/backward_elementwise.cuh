@@ -1,0 +1,401 @@
+// HBM-bound kernels of the training backward (reference: autograd through models/lightningdit.py:239-250, 66-91,
+// models/rmsnorm.py:52-77, models/swiglu_ffn.py:31-36, driven by transport.training_losses / train_accum.py:215-230).
+// They sit between the tensor-core GEMMs of the backward and carry every reduction the parameter gradients need:
+//   * over the columns of a token row (RMSNorm / head-norm Jacobians)      -> warp shuffles
+//   * over the tokens of a sample (adaLN shift / scale / gate gradients)   -> shared-memory accumulators per CTA,
+//                                                                             then one global atomicAdd per column and CTA
+// All global accesses are coalesced and vectorised (a warp walks a token row).
+#pragma once
+#include "elementwise.cuh"
+
+namespace ldmae {
+
+__device__ __forceinline__ float row_rinv_g(const float* __restrict__ ssq, size_t row, int slots, float inv_D, float eps) {
+  float s = 0.f;
+  for (int j = 0; j < slots; ++j) s += __ldg(ssq + row * slots + j);
+  return rsqrtf(s * inv_D + eps);
+}
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __forceinline__ float dsilu_f(float x) {
+  const float s = __fdividef(1.f, 1.f + __expf(-x));
+  return s * (1.f + x * (1.f - s));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward through   a = rsqrt(mean(x^2)+eps) * (x * g_b) + shift_b   (the modulated RMSNorm in front of a Linear) joined
+// with the residual add and the gate of the PREVIOUS branch.  With Gp = r * dL/da (the data-gradient GEMM's output; the
+// row factor r is already folded into the GEMM's other operand):
+//   dx_new  = dx + g_b * Gp - x * (r^2 / D) * sum_col(Gp * x * g_b)                       (dL/dx of this residual point)
+//   dg[b]  += sum_t Gp * x                   (-> dscale = dg * w, dw = sum_b dg * (1 + scale))
+//   dY      = bf16(dx_new * gate_prev[b])    (output gradient of the previous branch's Linear; gate_prev == nullptr: 1)
+//   dgate_prev[b] += sum_t dx_new * m_prev   (m_prev = that branch's output before the gate, saved by the forward)
+//   sdx[b] += sum_t dx_new                   (-> bias gradient of the previous branch's Linear, times the gate)
+// One CTA = 64 token rows of one sample; one warp = one row at a time.
+// ---------------------------------------------------------------------------------------------
+struct ResidBwdParams {
+  float* dx;                    // [M, D] in/out (dx_in == nullptr on entry of the final layer: treated as 0)
+  const __nv_bfloat16* gp;      // [M, D]
+  const float* x;               // [M, D] residual stream at this norm's input
+  const float* ssq;             // [M, slots]
+  const float* g;               // [B, D] norm.weight * (1 + scale)
+  float* dg;                    // [B, D] accumulated
+  __nv_bfloat16* dy;            // [M, D] out
+  const float* gate; int gate_ld;       // [B, gate_ld] or nullptr
+  const __nv_bfloat16* m_prev;  // [M, D] or nullptr
+  float* dgate; int dgate_ld;   // accumulated, or nullptr
+  float* sdx;                   // [B, D] accumulated, or nullptr
+  int T, D, slots, dx_zero;
+  float eps;
+};
+
+__global__ void __launch_bounds__(256)
+resid_bwd_kernel(const ResidBwdParams p) {
+  extern __shared__ float s_acc[];              // [3][D]: dg, dgate, sdx
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * 64;
+  const int nrows = min(64, p.T - t0);
+  const int D = p.D;
+  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* g = p.g + static_cast<size_t>(b) * D;
+  const float* gate = p.gate ? p.gate + static_cast<size_t>(b) * p.gate_ld : nullptr;
+  for (int r = warp; r < nrows; r += 8) {
+    const size_t row = static_cast<size_t>(b) * p.T + t0 + r;
+    const float rinv = row_rinv_g(p.ssq, row, p.slots, 1.f / D, p.eps);
+    const float* xr = p.x + row * D;
+    const __nv_bfloat16* gr = p.gp + row * D;
+    float t = 0.f;
+    for (int c = lane * 4; c < D; c += 128) {
+      const float4 xv = *reinterpret_cast<const float4*>(xr + c);
+      const float4 gv = __ldg(reinterpret_cast<const float4*>(g + c));
+      const uint2 gw = *reinterpret_cast<const uint2*>(gr + c);
+      const float2 a = bf2_to_f2(gw.x), bq = bf2_to_f2(gw.y);
+      t = fmaf(a.x * xv.x, gv.x, t); t = fmaf(a.y * xv.y, gv.y, t);
+      t = fmaf(bq.x * xv.z, gv.z, t); t = fmaf(bq.y * xv.w, gv.w, t);
+    }
+    t = warp_sum(t);
+    const float coef = rinv * rinv * t / D;
+    float* dxr = p.dx + row * D;
+    const __nv_bfloat16* mr = p.m_prev ? p.m_prev + row * D : nullptr;
+    for (int c = lane * 4; c < D; c += 128) {
+      const float4 xv = *reinterpret_cast<const float4*>(xr + c);
+      const float4 gv = __ldg(reinterpret_cast<const float4*>(g + c));
+      const uint2 gw = *reinterpret_cast<const uint2*>(gr + c);
+      const float2 a = bf2_to_f2(gw.x), bq = bf2_to_f2(gw.y);
+      const float gpv[4] = {a.x, a.y, bq.x, bq.y};
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+      const float gs[4] = {gv.x, gv.y, gv.z, gv.w};
+      float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!p.dx_zero) d4 = *reinterpret_cast<const float4*>(dxr + c);
+      float dn[4] = {d4.x, d4.y, d4.z, d4.w};
+      float gt[4] = {1.f, 1.f, 1.f, 1.f};
+      if (gate) { const float4 q = __ldg(reinterpret_cast<const float4*>(gate + c)); gt[0] = q.x; gt[1] = q.y; gt[2] = q.z; gt[3] = q.w; }
+      float mv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (mr) { const uint2 mw = *reinterpret_cast<const uint2*>(mr + c); const float2 m0 = bf2_to_f2(mw.x), m1 = bf2_to_f2(mw.y);
+                mv[0] = m0.x; mv[1] = m0.y; mv[2] = m1.x; mv[3] = m1.y; }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        dn[q] = dn[q] + gs[q] * gpv[q] - xs[q] * coef;
+        atomicAdd(&s_acc[c + q], gpv[q] * xs[q]);
+        if (mr) atomicAdd(&s_acc[D + c + q], dn[q] * mv[q]);
+        if (p.sdx) atomicAdd(&s_acc[2 * D + c + q], dn[q]);
+      }
+      *reinterpret_cast<float4*>(dxr + c) = make_float4(dn[0], dn[1], dn[2], dn[3]);
+      *reinterpret_cast<uint2*>(p.dy + row * D + c) = make_uint2(pack_bf16x2(dn[0] * gt[0], dn[1] * gt[1]), pack_bf16x2(dn[2] * gt[2], dn[3] * gt[3]));
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    atomicAdd(p.dg + static_cast<size_t>(b) * D + c, s_acc[c]);
+    if (p.dgate) atomicAdd(p.dgate + static_cast<size_t>(b) * p.dgate_ld + c, s_acc[D + c]);
+    if (p.sdx) atomicAdd(p.sdx + static_cast<size_t>(b) * D + c, s_acc[2 * D + c]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward through the QKV epilogue (lightningdit.py:68-74): RoPE^T, per-head RMSNorm Jacobian, row factor.
+//   in : dqkv [M, 3D] bf16 = gradients w.r.t. the rotated / normed q, k and v (attention backward output)
+//        raw  [M, 2D] bf16 = q, k before the head norm (saved by the training forward)
+//   out: dqkv in place     = r[row] * dL/d(qkv pre-norm)     (operand of the data- and weight-gradient GEMMs)
+//        dcvec[b, 3D]     += sum_t dL/d(qkv pre-norm)        (-> bias, shift and shift-path weight gradients)
+//        dqw[64], dkw[64] += sum over rows and heads of dy * xhat
+// One warp = one (row, 64-wide head) item, lane = one adjacent pair (= one RoPE pair).  One CTA = 32 rows of a sample.
+// ---------------------------------------------------------------------------------------------
+struct QkvBwdParams {
+  __nv_bfloat16* dqkv;
+  const __nv_bfloat16* raw;
+  const float* ssq;
+  const float* qw; const float* kw;        // nullptr: no qk-norm
+  const float* rope;                        // compact table [2][G][32] or nullptr
+  float* dcvec;                             // [B, 3D]
+  float* dqw; float* dkw;                   // [64] each
+  int T, D, slots, G;
+  float eps_row, eps_head;
+};
+
+__global__ void __launch_bounds__(256)
+qkv_bwd_kernel(const QkvBwdParams p) {
+  extern __shared__ float s_acc[];          // [3D] column sums, then [128] dqw | dkw
+  const int D = p.D, N = 3 * D;
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * 32;
+  const int nrows = min(32, p.T - t0);
+  for (int i = threadIdx.x; i < N + 128; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int heads3 = N / 64;
+  const int items = nrows * heads3;
+  for (int it = warp; it < items; it += 8) {
+    const int r = it / heads3, hc = it % heads3;
+    const int col = hc * 64 + lane * 2;
+    const int which = (hc * 64) / D;                         // 0 q, 1 k, 2 v
+    const int tok = t0 + r;
+    const size_t row = static_cast<size_t>(b) * p.T + tok;
+    const float rinv = row_rinv_g(p.ssq, row, p.slots, 1.f / D, p.eps_row);
+    __nv_bfloat16* dptr = p.dqkv + row * N + col;
+    float2 dy = bf2_to_f2(*reinterpret_cast<const uint32_t*>(dptr));
+    if (which < 2) {
+      if (p.rope != nullptr) {
+        const int axis = lane >> 4, f = lane & 15;
+        const int pos = axis == 0 ? tok / p.G : tok % p.G;
+        const float* tab = p.rope + (static_cast<size_t>(axis) * p.G + pos) * 32;
+        const float cs = __ldg(tab + f), sn = __ldg(tab + 16 + f);
+        const float a = dy.x * cs + dy.y * sn;               // transpose of (a,b) -> (a c - b s, b c + a s)
+        const float bb = dy.y * cs - dy.x * sn;
+        dy = make_float2(a, bb);
+      }
+      if (p.qw != nullptr) {
+        const float2 x = bf2_to_f2(*reinterpret_cast<const uint32_t*>(p.raw + row * 2 * D + col));
+        const float ms = warp_sum(x.x * x.x + x.y * x.y);
+        const float hs = rsqrtf(ms * (1.f / 64.f) + p.eps_head);
+        const float* w = which == 0 ? p.qw : p.kw;
+        const float w0 = __ldg(w + lane * 2), w1 = __ldg(w + lane * 2 + 1);
+        const float xh0 = x.x * hs, xh1 = x.y * hs;
+        const float u0 = dy.x * w0, u1 = dy.y * w1;
+        const float mu = warp_sum(u0 * xh0 + u1 * xh1) * (1.f / 64.f);
+        atomicAdd(&s_acc[N + which * 64 + lane * 2], dy.x * xh0);
+        atomicAdd(&s_acc[N + which * 64 + lane * 2 + 1], dy.y * xh1);
+        dy = make_float2(hs * (u0 - xh0 * mu), hs * (u1 - xh1 * mu));
+      }
+    }
+    atomicAdd(&s_acc[col], dy.x);
+    atomicAdd(&s_acc[col + 1], dy.y);
+    *reinterpret_cast<uint32_t*>(dptr) = pack_bf16x2(dy.x * rinv, dy.y * rinv);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < N; c += blockDim.x) atomicAdd(p.dcvec + static_cast<size_t>(b) * N + c, s_acc[c]);
+  if (p.qw != nullptr && threadIdx.x < 128) atomicAdd((threadIdx.x < 64 ? p.dqw : p.dkw - 64) + threadIdx.x, s_acc[N + threadIdx.x]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward through SwiGLU (swiglu_ffn.py:33-35) in the interleaved column layout of the packed w12
+// (64-column groups = [32 x1 | 32 x2]):   dx1 = dh * x2 * silu'(x1),  dx2 = dh * silu(x1)
+//   out: dh12 [M, 2H] bf16 = r[row] * (dx1 | dx2);   dcvec[b, 2H] += sum_t (dx1 | dx2)
+// Thread = two adjacent hidden units, loops over the 64 rows of the CTA's slab (column sums stay in registers).
+// grid = (ceil(H/512), ceil(T/64), B)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+swiglu_bwd_kernel(__nv_bfloat16* __restrict__ dh12, float* __restrict__ dcvec, const __nv_bfloat16* __restrict__ dh,
+                  const __nv_bfloat16* __restrict__ h12, const float* __restrict__ ssq, int T, int H, int D, int slots, float eps) {
+  __shared__ float s_r[64];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.y * 64;
+  const int nrows = min(64, T - t0);
+  if (threadIdx.x < nrows) s_r[threadIdx.x] = row_rinv_g(ssq, static_cast<size_t>(b) * T + t0 + threadIdx.x, slots, 1.f / D, eps);
+  __syncthreads();
+  const int u = blockIdx.x * 512 + threadIdx.x * 2;          // first hidden unit of this thread
+  if (u >= H) return;
+  const int c1 = (u >> 5) * 64 + (u & 31);                   // column of x1 (x2 at +32)
+  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+  for (int r = 0; r < nrows; ++r) {
+    const size_t row = static_cast<size_t>(b) * T + t0 + r;
+    const float2 g = bf2_to_f2(*reinterpret_cast<const uint32_t*>(dh + row * H + u));
+    const float2 x1 = bf2_to_f2(*reinterpret_cast<const uint32_t*>(h12 + row * 2 * H + c1));
+    const float2 x2 = bf2_to_f2(*reinterpret_cast<const uint32_t*>(h12 + row * 2 * H + c1 + 32));
+    const float d10 = g.x * x2.x * dsilu_f(x1.x), d11 = g.y * x2.y * dsilu_f(x1.y);
+    const float d20 = g.x * silu_f(x1.x), d21 = g.y * silu_f(x1.y);
+    a0 += d10; a1 += d11; b0 += d20; b1 += d21;
+    const float rr = s_r[r];
+    *reinterpret_cast<uint32_t*>(dh12 + row * 2 * H + c1) = pack_bf16x2(d10 * rr, d11 * rr);
+    *reinterpret_cast<uint32_t*>(dh12 + row * 2 * H + c1 + 32) = pack_bf16x2(d20 * rr, d21 * rr);
+  }
+  float* dc = dcvec + static_cast<size_t>(b) * 2 * H;
+  atomicAdd(dc + c1, a0); atomicAdd(dc + c1 + 1, a1);
+  atomicAdd(dc + c1 + 32, b0); atomicAdd(dc + c1 + 33, b1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Final layer (lightningdit.py:267-272 + unpatchify :376-389) backward entry:
+//   dyf[row, col] = bf16(r[row] * dout[b, ch, th*p+pi, tw*p+qi])   (col = (pi*p+qi)*cout + ch; 0 for ch >= cstore)
+//   dcvec[b, col] += sum_t dout(...)
+// ---------------------------------------------------------------------------------------------
+__global__ void final_bwd_prep_kernel(__nv_bfloat16* __restrict__ dyf, float* __restrict__ dcvec, const float* __restrict__ dout,
+                                      const float* __restrict__ ssq, int B, int T, int G, int patch, int cout, int cstore, int Nf,
+                                      int D, int slots, float eps) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(B) * T * Nf) return;
+  const int col = i % Nf;
+  const size_t row = i / Nf;
+  const int b = row / T, tok = row % T;
+  const int ch = col % cout, pq = col / cout, pi = pq / patch, qi = pq % patch;
+  const int th = tok / G, tw = tok % G, HW = G * patch;
+  float v = 0.f;
+  if (ch < cstore) v = dout[((static_cast<size_t>(b) * cstore + ch) * HW + th * patch + pi) * HW + tw * patch + qi];
+  dyf[i] = __float2bfloat16(v * row_rinv_g(ssq, row, slots, 1.f / D, eps));
+  if (v != 0.f) atomicAdd(dcvec + static_cast<size_t>(b) * Nf + col, v);
+}
+
+// latent [B, C, S, S] fp32 -> patch rows [B*T, C*p*p] bf16 in the Conv2d weight's (c, pi, qi) column order
+__global__ void patchify_bf16_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ lat, int B, int C, int S, int p) {
+  const int G = S / p, T = G * G, Kp = C * p * p;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(B) * T * Kp) return;
+  const int k = i % Kp;
+  const size_t row = i / Kp;
+  const int b = row / T, tok = row % T;
+  const int c = k / (p * p), pi = (k / p) % p, qi = k % p;
+  out[i] = __float2bfloat16(lat[((static_cast<size_t>(b) * C + c) * S + (tok / G) * p + pi) * S + (tok % G) * p + qi]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small reductions / fp32 matrix products of the conditioning backward (batch-sized: negligible work)
+// ---------------------------------------------------------------------------------------------
+// out[n] (+)= sum_b in[b*ld_in + n] * (mul ? mul[b*ld_mul + n] : 1)
+__global__ void colsum_kernel(float* __restrict__ out, const float* __restrict__ in, int ld_in, const float* __restrict__ mul,
+                              int ld_mul, int B, int N, int accumulate) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s += in[static_cast<size_t>(b) * ld_in + n] * (mul ? mul[static_cast<size_t>(b) * ld_mul + n] : 1.f);
+  out[n] = accumulate ? out[n] + s : s;
+}
+// adaLN slot gradients: dmods[b, scale_off[s] + d] = dg[s][b][d] * norm_w[s][d];   dnorm_w[s][d] = sum_b dg * (1 + scale)
+__global__ void adaln_bwd_kernel(float* __restrict__ dmods, float* __restrict__ dnorm_w, const float* __restrict__ dg,
+                                 const float* __restrict__ mods, const float* __restrict__ norm_w,
+                                 const int* __restrict__ slot_scale_off, int B, int D, int Ntot, int S) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S * D) return;
+  const int s = i / D, d = i % D;
+  const int so = slot_scale_off[s];
+  const float w = norm_w[i];
+  float acc = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float v = dg[(static_cast<size_t>(s) * B + b) * D + d];
+    dmods[static_cast<size_t>(b) * Ntot + so + d] = v * w;
+    acc = fmaf(v, 1.f + mods[static_cast<size_t>(b) * Ntot + so + d], acc);
+  }
+  dnorm_w[i] = acc;
+}
+// out[i] = in[i] * silu'(pre[i])
+__global__ void dsilu_mul_kernel(float* __restrict__ out, const float* __restrict__ in, const float* __restrict__ pre, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] * dsilu_f(pre[i]);
+}
+__global__ void silu_f32_kernel(float* __restrict__ out, const float* __restrict__ in, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = silu_f(in[i]);
+}
+// sinusoidal timestep features (lightningdit.py:108-128): out[b, 0:half] = cos(t f), [half:] = sin(t f)
+__global__ void timestep_features_kernel(float* __restrict__ out, const float* __restrict__ tvals, float tscalar, int B, int K) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * K) return;
+  const int b = i / K, k = i % K, half = K / 2;
+  const float t = tvals ? tvals[b] : tscalar;
+  const float a = t * expf(-9.210340371976184f * static_cast<float>(k % half) / static_cast<float>(half));
+  out[i] = (k < half) ? cosf(a) : sinf(a);
+}
+// C[n, k] += sum_b A[b, n] * Bm[b, k]   (fp32; one thread per output)
+__global__ void small_wgrad_kernel(float* __restrict__ C, const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
+                                   int B, int N, int K) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(N) * K) return;
+  const int n = i / K, k = i % K;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s = fmaf(A[static_cast<size_t>(b) * lda + n], Bm[static_cast<size_t>(b) * ldb + k], s);
+  C[i] += s;
+}
+// out[b, k] (row pitch ld_out) = sum_n A[b, n] * W[n, k]   (fp32)
+__global__ void small_dgrad_kernel(float* __restrict__ out, int ld_out, const float* __restrict__ A, int lda,
+                                   const float* __restrict__ W, int B, int N, int K) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(B) * K) return;
+  const int b = i / K, k = i % K;
+  float s = 0.f;
+  for (int n = 0; n < N; ++n) s = fmaf(A[static_cast<size_t>(b) * lda + n], W[static_cast<size_t>(n) * K + k], s);
+  out[static_cast<size_t>(b) * ld_out + k] = s;
+}
+// table[idx[b], :] += v[b, :]
+__global__ void embed_bwd_kernel(float* __restrict__ table, const long long* __restrict__ idx, const float* __restrict__ v, int B, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * D) return;
+  atomicAdd(table + static_cast<size_t>(idx[i / D]) * D + (i % D), v[i]);
+}
+// bf16 matrix transpose: dst[c, r] = src[r, c]  (src [R, C]); 32 x 32 tiles through shared memory
+__global__ void transpose_bf16_kernel(__nv_bfloat16* __restrict__ dst, const __nv_bfloat16* __restrict__ src, int R, int C) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (r < R && c < C) ? src[static_cast<size_t>(r) * C + c] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (c < C && r < R) dst[static_cast<size_t>(c) * R + r] = tile[threadIdx.x][j];
+  }
+}
+__global__ void f32_to_bf16_ld_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ in, int rows, int cols, int ld_in) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(rows) * cols) return;
+  out[i] = __float2bfloat16(in[(i / cols) * ld_in + (i % cols)]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused AdamW + EMA over a flat parameter buffer (reference train_accum.py:121,240-246,337-347:
+// torch.optim.AdamW(lr, betas, weight_decay) followed by update_ema(ema, model, decay)).  One pass:
+// 5 reads + 4 writes of 4 bytes per parameter.  grad_scale folds the 1/world_size of the gradient all-reduce.
+// ---------------------------------------------------------------------------------------------
+__global__ void adamw_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                 float* __restrict__ ema, size_t n, float lr, float beta1, float beta2, float eps, float wd,
+                                 float bc1, float bc2, float ema_decay, float grad_scale) {
+  const size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  if (i + 3 < n) {
+    float4 pv = *reinterpret_cast<float4*>(p + i);
+    const float4 gv = *reinterpret_cast<const float4*>(g + i);
+    float4 mv = *reinterpret_cast<float4*>(m + i), vv = *reinterpret_cast<float4*>(v + i);
+    float pp[4] = {pv.x, pv.y, pv.z, pv.w}, gg[4] = {gv.x, gv.y, gv.z, gv.w}, mm[4] = {mv.x, mv.y, mv.z, mv.w}, v2[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float gq = gg[q] * grad_scale;
+      pp[q] *= 1.f - lr * wd;
+      mm[q] = beta1 * mm[q] + (1.f - beta1) * gq;
+      v2[q] = beta2 * v2[q] + (1.f - beta2) * gq * gq;
+      pp[q] -= lr / bc1 * mm[q] / (sqrtf(v2[q]) / sqrtf(bc2) + eps);
+    }
+    *reinterpret_cast<float4*>(p + i) = make_float4(pp[0], pp[1], pp[2], pp[3]);
+    *reinterpret_cast<float4*>(m + i) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    *reinterpret_cast<float4*>(v + i) = make_float4(v2[0], v2[1], v2[2], v2[3]);
+    if (ema) {
+      float4 ev = *reinterpret_cast<float4*>(ema + i);
+      ev.x = ev.x * ema_decay + pp[0] * (1.f - ema_decay); ev.y = ev.y * ema_decay + pp[1] * (1.f - ema_decay);
+      ev.z = ev.z * ema_decay + pp[2] * (1.f - ema_decay); ev.w = ev.w * ema_decay + pp[3] * (1.f - ema_decay);
+      *reinterpret_cast<float4*>(ema + i) = ev;
+    }
+  } else {
+    for (size_t j = i; j < n; ++j) {
+      const float gq = g[j] * grad_scale;
+      float pj = p[j] * (1.f - lr * wd);
+      m[j] = beta1 * m[j] + (1.f - beta1) * gq;
+      v[j] = beta2 * v[j] + (1.f - beta2) * gq * gq;
+      pj -= lr / bc1 * m[j] / (sqrtf(v[j]) / sqrtf(bc2) + eps);
+      p[j] = pj;
+      if (ema) ema[j] = ema[j] * ema_decay + pj * (1.f - ema_decay);
+    }
+  }
+}
+
+}  // namespace ldmae

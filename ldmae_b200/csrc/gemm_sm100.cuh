@@ -231,7 +231,10 @@ struct EpiStore : StoreRing {
 // x travels by TMA in 32-row x 32-column fp32 boxes: loaded kPF chunks ahead (across tile boundaries, i.e. while
 // the tensor core still works on the tile), updated in place in shared memory and stored back from the same tile.
 // This epilogue is HBM-bound (12 bytes per accumulator element), so four warps suffice.
-template <int NX /*x tiles per warp*/, int PF /*prefetch distance in chunks*/>
+// kTrain: the training forward additionally keeps, for the backward, the branch output before the gate
+// (m = acc + bias, bf16 -> dgate = sum_t dx * m) and writes the updated stream to a second buffer (xmap_out), so that
+// the stream at every norm input stays available (RMSNorm Jacobian).
+template <int NX /*x tiles per warp*/, int PF /*prefetch distance in chunks*/, bool kTrain = false>
 struct EpiResidualT {
   static constexpr int kWarps = 4;
   static constexpr int kCtaBytes = 0;
@@ -239,12 +242,15 @@ struct EpiResidualT {
   static constexpr int kPF = PF;
   static_assert(PF + 2 <= NX, "a tile is reloaded PF chunks ahead while the stores of the last two chunks may still read theirs");
   static constexpr int kXBytes = 4096, kABytesTile = 2048;
-  static constexpr int kVecOff = kNX * kXBytes + 2 * kABytesTile;      // [3][256] floats: bias, gate, gnext of the tile
+  static constexpr int kMOff = kNX * kXBytes + 2 * kABytesTile;        // kTrain: two bf16 tiles for m
+  static constexpr int kVecOff = kMOff + (kTrain ? 2 * kABytesTile : 0);   // [3][256] floats: bias, gate, gnext of the tile
   static constexpr int kWarpBytes = kVecOff + 4096;
   static constexpr int kBars = kNX;
   struct Params {
-    CUtensorMap xmap;      // x [M, N] fp32: box {32, 32}, SWIZZLE_128B (loads and stores)
+    CUtensorMap xmap;      // x [M, N] fp32: box {32, 32}, SWIZZLE_128B (loads)
+    CUtensorMap xmap_out;  // where the updated x is stored (= xmap for the in-place inference path)
     CUtensorMap amap;      // anext [M, N] bf16: box {32, 32}, SWIZZLE_64B (stores); unused when !has_anext
+    CUtensorMap mmap;      // kTrain: m [M, N] bf16, box {32, 32}, SWIZZLE_64B
     const float* bias;     // [N]
     const float* gate;     // [B, gate_ld] or nullptr (=> 1)
     const float* gnext;    // [B, gnext_ld] (has_anext)
@@ -263,7 +269,9 @@ struct EpiResidualT {
   static __device__ __forceinline__ void cta_init(const P&, uint8_t*, int, int) {}
   static __device__ __forceinline__ void prefetch_maps(const Params& p) {
     tma_prefetch_desc(&p.xmap);
+    tma_prefetch_desc(&p.xmap_out);
     if (p.has_anext) tma_prefetch_desc(&p.amap);
+    if constexpr (kTrain) tma_prefetch_desc(&p.mmap);
   }
   // issue the x loads of every chunk with sequence number <= upto (lane 0 only; buffers are known to be free)
   template <int BN>
@@ -326,6 +334,7 @@ struct EpiResidualT {
       RES_STAMP(2);
       uint8_t* xt = c.smem + (st.seq % kNX) * kXBytes;
       uint8_t* at = c.smem + kNX * kXBytes + (st.seq & 1) * kABytesTile;
+      uint8_t* mt = c.smem + kMOff + (st.seq & 1) * kABytesTile;
       mbar_wait(&c.bars[st.seq % kNX], (st.seq / kNX) & 1, 500);
       __syncwarp();
       RES_STAMP(3);
@@ -347,10 +356,15 @@ struct EpiResidualT {
         uint8_t* xp = sw128_chunk(xt, lane, q);
         const uint4 xr = ld_tile16(xp);
         float4 xn;
-        xn.x = __uint_as_float(xr.x) + (v[4 * q] + bi.x) * gt.x;
-        xn.y = __uint_as_float(xr.y) + (v[4 * q + 1] + bi.y) * gt.y;
-        xn.z = __uint_as_float(xr.z) + (v[4 * q + 2] + bi.z) * gt.z;
-        xn.w = __uint_as_float(xr.w) + (v[4 * q + 3] + bi.w) * gt.w;
+        const float m0 = v[4 * q] + bi.x, m1 = v[4 * q + 1] + bi.y, m2 = v[4 * q + 2] + bi.z, m3 = v[4 * q + 3] + bi.w;
+        if constexpr (kTrain) {
+          // 4 bf16 = 8 bytes: half of 16-byte chunk q/2 of the SWIZZLE_64B tile
+          *reinterpret_cast<uint2*>(sw64_chunk(mt, lane, q >> 1) + (q & 1) * 8) = make_uint2(pack_bf16x2(m0, m1), pack_bf16x2(m2, m3));
+        }
+        xn.x = __uint_as_float(xr.x) + m0 * gt.x;
+        xn.y = __uint_as_float(xr.y) + m1 * gt.y;
+        xn.z = __uint_as_float(xr.z) + m2 * gt.z;
+        xn.w = __uint_as_float(xr.w) + m3 * gt.w;
         st_tile16(xp, make_uint4(__float_as_uint(xn.x), __float_as_uint(xn.y), __float_as_uint(xn.z), __float_as_uint(xn.w)));
         // columns >= N hold zeros (TMA zero fill + zero bias/acc), so they do not disturb the statistics
         ss = fmaf(xn.x, xn.x, ss); ss = fmaf(xn.y, xn.y, ss); ss = fmaf(xn.z, xn.z, ss); ss = fmaf(xn.w, xn.w, ss);
@@ -372,8 +386,9 @@ struct EpiResidualT {
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        tma_store_2d(&p.xmap, xt, n0 + c0, row0);
+        tma_store_2d(&p.xmap_out, xt, n0 + c0, row0);
         if (p.has_anext) tma_store_2d(&p.amap, at, n0 + c0, row0);
+        if constexpr (kTrain) tma_store_2d(&p.mmap, mt, n0 + c0, row0);
         tma_store_commit();
       }
       RES_STAMP(6);
@@ -392,6 +407,7 @@ struct EpiResidualT {
 
 using EpiResidual = EpiResidualT<4, 2>;        // w3 (K = 4D/1.5: tensor-bound, keeps a 4-stage operand ring)
 using EpiResidualDeep = EpiResidualT<6, 4>;    // proj (K = D: HBM-bound, deeper residual prefetch, 3-stage operand ring)
+using EpiResidualTrain = EpiResidualT<4, 2, true>;   // training forward (keeps m and the per-norm stream copies)
 
 // QKV projection of LightningDiT attention (lightningdit.py:68-74) on the pre-scaled operand:
 //   v = acc * rsqrt(ssq[row]/D + eps) + cvec[b,col]        (= Linear(modulate(RMSNorm(x))) incl. bias)
@@ -406,6 +422,8 @@ struct EpiQKV : StoreRing {
   static constexpr int kRopePitch = 36;
   struct Params {
     CUtensorMap omap;       // out [M, 3D] bf16: box {64, 32}, SWIZZLE_128B
+    CUtensorMap rawmap;     // has_raw (training forward): q, k before the head norm [M, 2D] bf16, same box
+    int has_raw;
     const float* ssq;       // [M, ss_slots] partial sums of squares of the residual-stream row (nullptr: no row scale)
     const float* cvec;      // [B, 3D]  shift_b . W^T + bias
     const float* qw;        // [64] q_norm.weight or nullptr (no qk-norm)
@@ -422,7 +440,10 @@ struct EpiQKV : StoreRing {
     float* dst = reinterpret_cast<float*>(cta);
     for (int i = tid; i < 2 * p.grid * 32; i += nthreads) dst[(i / 32) * kRopePitch + (i % 32)] = __ldg(p.rope + i);
   }
-  static __device__ __forceinline__ void prefetch_maps(const Params& p) { tma_prefetch_desc(&p.omap); }
+  static __device__ __forceinline__ void prefetch_maps(const Params& p) {
+    tma_prefetch_desc(&p.omap);
+    if (p.has_raw) tma_prefetch_desc(&p.rawmap);
+  }
   template <int BN>
   static __device__ __forceinline__ void begin(const Params&, const GemmShape&, const TileSched&, const EpiCtx&, State& st) {
     st.seq = 0;
@@ -482,6 +503,16 @@ struct EpiQKV : StoreRing {
         ms = fmaf(v[j], v[j], ms); ms = fmaf(v[j + 1], v[j + 1], ms);
         ms = fmaf(v[j + 2], v[j + 2], ms); ms = fmaf(v[j + 3], v[j + 3], ms);
       }
+      if (which < 2 && p.has_raw) {
+        // the head-norm Jacobian of the backward needs the un-normed head
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          st_tile16(sw128_chunk(tile, lane, q),
+                 make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                            pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7])));
+        release(c, st, &p.rawmap, tile, colbase, row0);
+        tile = acquire(c, st);
+      }
       if (which < 2 && p.qw != nullptr) {
         const float hs = rsqrtf(ms * (1.f / 64.f) + p.eps_head);
         const float* nw = vnw + which * 64;
@@ -531,12 +562,17 @@ struct EpiQKV : StoreRing {
 struct EpiSwiGLU : StoreRing {
   struct Params {
     CUtensorMap omap;     // out [M, H] bf16: box {64, 32}, SWIZZLE_128B
+    CUtensorMap premap;   // has_pre (training forward): pre-activation [M, 2H] bf16 (interleaved columns), same box
+    int has_pre;
     const float* ssq;     // [M, ss_slots]
     const float* cvec;    // [B, 2H] in the same interleaved column order
     int rows_per_sample, ss_slots;
     float inv_D, eps_row;
   };
-  static __device__ __forceinline__ void prefetch_maps(const Params& p) { tma_prefetch_desc(&p.omap); }
+  static __device__ __forceinline__ void prefetch_maps(const Params& p) {
+    tma_prefetch_desc(&p.omap);
+    if (p.has_pre) tma_prefetch_desc(&p.premap);
+  }
   template <int BN>
   static __device__ __forceinline__ void begin(const Params&, const GemmShape&, const TileSched&, const EpiCtx&, State& st) {
     st.seq = 0;
@@ -564,7 +600,7 @@ struct EpiSwiGLU : StoreRing {
 #pragma unroll 1
     for (int c0 = cbase; c0 < cbase + GC; c0 += 128) {
       if (n0 + c0 >= g.N) break;
-      uint8_t* tile = acquire(c, st);
+      uint32_t w[32];                                  // 64 hidden values of this row (bf16 pairs), staged after both halves
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int cb = c0 + half * 64;
@@ -580,14 +616,24 @@ struct EpiSwiGLU : StoreRing {
           v[j] = fmaf(v[j], rinv, cc.x); v[j + 1] = fmaf(v[j + 1], rinv, cc.y);
           v[j + 2] = fmaf(v[j + 2], rinv, cc.z); v[j + 3] = fmaf(v[j + 3], rinv, cc.w);
         }
-        uint32_t w[16];
+        if (p.has_pre) {
+          // SwiGLU's backward needs x1 and x2: keep the 64 pre-activation columns (own tile, own TMA store)
+          uint8_t* pt = acquire(c, st);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            st_tile16(sw128_chunk(pt, lane, q),
+                   make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                              pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7])));
+          release(c, st, &p.premap, pt, n0 + cb, row0);
+        }
 #pragma unroll
         for (int j = 0; j < 32; j += 2)
-          w[j >> 1] = pack_bf16x2(silu_f(v[j]) * v[32 + j], silu_f(v[j + 1]) * v[32 + j + 1]);
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          st_tile16(sw128_chunk(tile, lane, half * 4 + q), make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]));
+          w[half * 16 + (j >> 1)] = pack_bf16x2(silu_f(v[j]) * v[32 + j], silu_f(v[j + 1]) * v[32 + j + 1]);
       }
+      uint8_t* tile = acquire(c, st);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        st_tile16(sw128_chunk(tile, lane, q), make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]));
       release(c, st, &p.omap, tile, (n0 + c0) / 2, row0);
     }
   }

@@ -12,6 +12,7 @@
 #include "attention_sm100.cuh"
 #include "common.cuh"
 #include "gemm_wgrad_sm100.cuh"
+#include "backward_elementwise.cuh"
 #include "elementwise.cuh"
 
 namespace ldmae {
@@ -151,6 +152,8 @@ static int gemm_residual(const void* a, int lda, const void* w, int ldw, GemmSha
                          int ss_slots, int rows_per_sample, cudaStream_t st) {
   typename EpiResidual::Params ep;
   LDMAE_TRY(make_tmap_out_f32(&ep.xmap, x, g.M, g.N, ldx));
+  ep.xmap_out = ep.xmap;
+  ep.mmap = ep.xmap;
   ep.has_anext = anext != nullptr;
   if (anext) LDMAE_TRY(make_tmap_2d(&ep.amap, anext, 2, g.M, g.N, ldx, 32, 32, 64));
   else ep.amap = ep.xmap;
@@ -166,6 +169,24 @@ static int gemm_residual(const void* a, int lda, const void* w, int ldw, GemmSha
     return gemm_auto<EpiResidualDeep>(a, lda, w, ldw, g, ed, st);
   }
   return gemm_auto<EpiResidual>(a, lda, w, ldw, g, ep, st);
+}
+
+// Training forward of the same epilogue: x_out (a different buffer) = x_in + gate * m, and m = a . w^T + bias is kept (bf16).
+static int gemm_residual_train(const void* a, int lda, const void* w, int ldw, GemmShape g, const float* x_in, float* x_out,
+                               int ldx, const float* bias, const float* gate, int gate_ld, const float* gnext, int gnext_ld,
+                               __nv_bfloat16* anext, float* ssq, int ss_slots, __nv_bfloat16* m_out, int rows_per_sample,
+                               cudaStream_t st) {
+  typename EpiResidualTrain::Params ep;
+  LDMAE_TRY(make_tmap_out_f32(&ep.xmap, x_in, g.M, g.N, ldx));
+  LDMAE_TRY(make_tmap_out_f32(&ep.xmap_out, x_out, g.M, g.N, ldx));
+  LDMAE_TRY(make_tmap_2d(&ep.mmap, m_out, 2, g.M, g.N, ldx, 32, 32, 64));
+  ep.has_anext = anext != nullptr;
+  if (anext) LDMAE_TRY(make_tmap_2d(&ep.amap, anext, 2, g.M, g.N, ldx, 32, 32, 64));
+  else ep.amap = ep.mmap;
+  ep.bias = bias; ep.gate = gate; ep.gnext = gnext; ep.ssq = ssq;
+  ep.gate_ld = gate_ld; ep.gnext_ld = gnext_ld; ep.rows_per_sample = rows_per_sample; ep.ss_slots = ss_slots;
+  ep.trace = nullptr;
+  return gemm_auto<EpiResidualTrain>(a, lda, w, ldw, g, ep, st);
 }
 
 extern "C" int ldmae_gemm_trace(long long* dev_buf) { g_gemm_trace = dev_buf; return LDMAE_OK; }
@@ -280,6 +301,9 @@ struct DitBlockW {
 
 using namespace ldmae;
 
+struct DitTrain;
+static void dit_train_free(DitTrain* t);
+
 struct ldmae_dit {
   ldmae_dit_config c;
   int D, T, G, Kp, H, Hp, nmod, Ntot, S /*norm slots*/, Nf, maxB, SS /*ssq partial slots*/;
@@ -288,12 +312,16 @@ struct ldmae_dit {
   DevBuf<__nv_bfloat16> w_ada, w_f;
   std::vector<DitBlockW> blk;
   DevBuf<int> slot_shift_off, slot_scale_off;
+  std::vector<int> so_host, sco_host;   // host copies of the slot offsets (backward orchestration)
   std::vector<std::string> loaded;
   bool finalized = false;
   int debug_stop = -1;   // >= 0: dit_forward_impl returns after that many launch groups (ldmae_dit_debug_stop)
   // workspace (sized for maxB)
   DevBuf<float> xres, ssq, cvec_c, th1, mods, gmul, cvec_qkv, cvec_12, cvec_f, vbuf, k1buf, xtmp;
   DevBuf<__nv_bfloat16> abuf, qkv, obuf, hbuf, sc, shift_bf16;
+  DitTrain* tr = nullptr;   // activations kept by the training forward, backward workspace, gradients (dit_train.cuh)
+  bool wT_valid = false;    // transposed bf16 weight copies (data-gradient GEMM operands) are current
+  ~ldmae_dit() { dit_train_free(tr); }
 };
 
 static int dit_alloc_ws(ldmae_dit* h, int B) {
@@ -424,6 +452,7 @@ extern "C" int ldmae_dit_create(const ldmae_dit_config* cfg, ldmae_dit** out) {
   }
   so[2 * c.depth] = c.depth * h->nmod * D;
   sco[2 * c.depth] = c.depth * h->nmod * D + D;
+  h->so_host = so; h->sco_host = sco;
   A(h->slot_shift_off.alloc(h->S)); A(h->slot_scale_off.alloc(h->S));
   if (r == LDMAE_OK && cudaMemcpy(h->slot_shift_off.p, so.data(), h->S * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess)
     r = set_error(LDMAE_ERR_CUDA, "memcpy slot offsets");
@@ -511,6 +540,7 @@ extern "C" int ldmae_dit_load_tensor(ldmae_dit* h, const char* name, const float
     return set_error(LDMAE_ERR_INVALID, "unknown LightningDiT state_dict key %s", name);
   }
   if (rc == LDMAE_OK && std::find(h->loaded.begin(), h->loaded.end(), k) == h->loaded.end()) h->loaded.push_back(k);
+  h->wT_valid = false;
   return rc;
 }
 
@@ -541,9 +571,31 @@ extern "C" int ldmae_dit_finalize(ldmae_dit* h, void* stream) {
   return LDMAE_OK;
 }
 
-// One forward pass of cat-batch B (see header).  out: [B, Cstore, S, S].
+// Views of the buffers one forward writes: the shared inference workspace (in place, one block at a time) or, for the
+// training forward, the per-block slices of the activation store (dit_train.cuh).
+struct DitTrain {
+  int B = 0;
+  // kept by the forward
+  DevBuf<float> X, SSQ, LSE, th1pre, tfreq;
+  DevBuf<__nv_bfloat16> A, QKV, QKR, O, MA, MM, H12, HB, XTOK;
+  DevBuf<long long> ykeep;
+  // backward workspace
+  DevBuf<float> dx, delta, dg, sdx, dcv_qkv, dcv_12, dcv_f, dmods, dsc, dcond, dth1, dth1pre, grads;
+  DevBuf<__nv_bfloat16> dY, dO, G, dQKV, dH, dH12, dYf, cv_bf16, dmods_bf16;
+  // transposed weights (operands of the data-gradient GEMMs)
+  std::vector<DevBuf<__nv_bfloat16>> wT_qkv, wT_proj, wT_12, wT_3;
+  DevBuf<__nv_bfloat16> wT_ada, wT_f;
+  // gradient layout inside `grads` (internal packed layouts; ldmae_dit_grad_read converts to the reference's)
+  std::map<std::string, std::pair<size_t, size_t>> goff;
+  size_t gtotal = 0;
+  bool have_forward = false;
+  int lastB = 0;
+};
+static void dit_train_free(DitTrain* t) { delete t; }
+
+// One forward pass of cat-batch B (see header).  out: [B, Cstore, S, S].  tr != nullptr: training forward (keeps activations).
 static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float t_scalar, const int64_t* y, float* out,
-                            int B, int src_mod, cudaStream_t st) {
+                            int B, int src_mod, cudaStream_t st, DitTrain* tr = nullptr) {
   LDMAE_REQUIRE(h && h->finalized, "LightningDiT handle not finalized (load all weights, then ldmae_dit_finalize)");
   LDMAE_REQUIRE(B >= 1 && src_mod >= 1, "bad batch");
   if (B > h->maxB) {
@@ -553,7 +605,12 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
   const ldmae_dit_config& c = h->c;
   const int D = h->D, T = h->T, depth = c.depth;
   const int M = B * T;
+  const size_t MD = static_cast<size_t>(M) * D;
   const float eps = 1e-6f;
+  // slot s = norm index (2 per block + final): stream copy, norm operand and row statistics of that norm's input
+  auto Xs = [&](int s) { return tr ? tr->X.p + s * MD : h->xres.p; };
+  auto As = [&](int s) { return tr ? tr->A.p + s * MD : h->abuf.p; };
+  auto Ss = [&](int s) { return tr ? tr->SSQ.p + static_cast<size_t>(s) * M * h->SS : h->ssq.p; };
   int dbg_stage = 0;
 #define LDMAE_DBG_STAGE() do { if (h->debug_stop >= 0 && ++dbg_stage > h->debug_stop) return LDMAE_OK; } while (0)
   // 1. conditioning c = t_emb + y_emb ; sc = bf16(silu(c))
@@ -567,8 +624,19 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
       LDMAE_CUDA(cudaFuncSetAttribute(small_linear_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr = true;
     }
-    small_linear_kernel<1><<<grid, 256, sm0, st>>>(h->th1.p, nullptr, t, t_scalar, h->t_w0.p, h->t_b0.p, nullptr, nullptr, B, 256, D, 1, 256);
-    LDMAE_LAUNCH_CHECK();
+    if (tr) {
+      // the backward needs the pre-activation of the timestep MLP and its input features
+      timestep_features_kernel<<<cdiv(static_cast<size_t>(B) * 256, 256), 256, 0, st>>>(tr->tfreq.p, t, t_scalar, B, 256);
+      LDMAE_LAUNCH_CHECK();
+      small_linear_kernel<0><<<grid, 256, sm0, st>>>(tr->th1pre.p, nullptr, t, t_scalar, h->t_w0.p, h->t_b0.p, nullptr, nullptr, B, 256, D, 1, 256);
+      LDMAE_LAUNCH_CHECK();
+      silu_f32_kernel<<<cdiv(static_cast<size_t>(B) * D, 256), 256, 0, st>>>(h->th1.p, tr->th1pre.p, static_cast<size_t>(B) * D);
+      LDMAE_LAUNCH_CHECK();
+      LDMAE_CUDA(cudaMemcpyAsync(tr->ykeep.p, y, static_cast<size_t>(B) * sizeof(long long), cudaMemcpyDeviceToDevice, st));
+    } else {
+      small_linear_kernel<1><<<grid, 256, sm0, st>>>(h->th1.p, nullptr, t, t_scalar, h->t_w0.p, h->t_b0.p, nullptr, nullptr, B, 256, D, 1, 256);
+      LDMAE_LAUNCH_CHECK();
+    }
     small_linear_kernel<0><<<grid, 256, sm2, st>>>(h->cvec_c.p, h->th1.p, nullptr, 0.f, h->t_w2.p, h->t_b2.p, h->emb.p,
                                                    reinterpret_cast<const long long*>(y), B, D, D, 0, D);
     LDMAE_LAUNCH_CHECK();
@@ -612,9 +680,14 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
     ProfScope ps(7, st);
     dim3 grid(cdiv(T, 32), B);
     const size_t sm = (32 * static_cast<size_t>(h->Kp) + 256) * sizeof(float);
-    patch_embed_kernel<<<grid, 256, sm, st>>>(h->xres.p, h->abuf.p, h->ssq.p, x, h->patch_w.p, h->patch_b.p, h->pos.p,
+    patch_embed_kernel<<<grid, 256, sm, st>>>(Xs(0), As(0), Ss(0), x, h->patch_w.p, h->patch_b.p, h->pos.p,
                                               h->gmul.p, c.in_channels, c.input_size, c.patch_size, D, src_mod, h->SS);
     LDMAE_LAUNCH_CHECK();
+    if (tr) {
+      LDMAE_REQUIRE(src_mod == B, "training forward takes a plain batch");
+      patchify_bf16_kernel<<<cdiv(static_cast<size_t>(M) * h->Kp, 256), 256, 0, st>>>(tr->XTOK.p, x, B, c.in_channels, c.input_size, c.patch_size);
+      LDMAE_LAUNCH_CHECK();
+    }
   }
   LDMAE_DBG_STAGE();   // 4
   // 5. blocks  (debug stages 5 + 5*i + {0 qkv, 1 attention, 2 proj, 3 w12, 4 w3})
@@ -623,43 +696,70 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
     const float* mods_i = h->mods.p + static_cast<size_t>(i) * h->nmod * D;
     const float* gate_msa = mods_i + (c.wo_shift ? 1 : 2) * D;
     const float* gate_mlp = mods_i + (c.wo_shift ? 3 : 5) * D;
+    __nv_bfloat16* qkv_i = tr ? tr->QKV.p + static_cast<size_t>(i) * M * 3 * D : h->qkv.p;
+    __nv_bfloat16* o_i = tr ? tr->O.p + i * MD : h->obuf.p;
+    __nv_bfloat16* hb_i = tr ? tr->HB.p + static_cast<size_t>(i) * M * h->Hp : h->hbuf.p;
     EpiQKV::Params eq;
-    LDMAE_TRY(make_tmap_out_bf16(&eq.omap, h->qkv.p, M, 3 * D, 3 * D));
-    eq.ssq = h->ssq.p; eq.cvec = h->cvec_qkv.p + static_cast<size_t>(i) * B * 3 * D;
+    LDMAE_TRY(make_tmap_out_bf16(&eq.omap, qkv_i, M, 3 * D, 3 * D));
+    eq.has_raw = 0; eq.rawmap = eq.omap;
+    if (tr) {
+      eq.has_raw = 1;
+      LDMAE_TRY(make_tmap_out_bf16(&eq.rawmap, tr->QKR.p + static_cast<size_t>(i) * M * 2 * D, M, 2 * D, 2 * D));
+    }
+    eq.ssq = Ss(2 * i); eq.cvec = h->cvec_qkv.p + static_cast<size_t>(i) * B * 3 * D;
     eq.qw = c.use_qknorm ? b.qw.p : nullptr; eq.kw = c.use_qknorm ? b.kw.p : nullptr;
     eq.rope = c.use_rope ? h->rope_tab.p : nullptr; eq.grid = h->G;
     eq.D = D; eq.rows_per_sample = T; eq.ss_slots = h->SS; eq.inv_D = 1.f / D; eq.eps_row = eps; eq.eps_head = eps;
-    { ProfScope ps(0, st); LDMAE_TRY((gemm_auto<EpiQKV>(h->abuf.p, D, b.w_qkv.p, D, GemmShape{M, 3 * D, D}, eq, st))); }
+    { ProfScope ps(0, st); LDMAE_TRY((gemm_auto<EpiQKV>(As(2 * i), D, b.w_qkv.p, D, GemmShape{M, 3 * D, D}, eq, st))); }
     LDMAE_DBG_STAGE();
-    { ProfScope ps(1, st); LDMAE_TRY(run_attention(h->qkv.p, 3 * D, h->obuf.p, D, B, T, c.num_heads, 0, D, 2 * D, 0.125f, st)); }
+    {
+      ProfScope ps(1, st);
+      float* lse = tr ? tr->LSE.p + static_cast<size_t>(i) * B * c.num_heads * T : nullptr;
+      LDMAE_TRY(run_attention(qkv_i, 3 * D, o_i, D, B, T, c.num_heads, 0, D, 2 * D, 0.125f, st, lse));
+    }
     LDMAE_DBG_STAGE();
     {
       ProfScope ps(2, st);
-      LDMAE_TRY(gemm_residual(h->obuf.p, D, b.w_proj.p, D, GemmShape{M, D, D}, h->xres.p, D, b.b_proj.p, gate_msa, h->Ntot,
-                              h->gmul.p + static_cast<size_t>(2 * i + 1) * B * D, D, h->abuf.p, h->ssq.p, h->SS, T, st));
+      if (tr)
+        LDMAE_TRY(gemm_residual_train(o_i, D, b.w_proj.p, D, GemmShape{M, D, D}, Xs(2 * i), Xs(2 * i + 1), D, b.b_proj.p, gate_msa,
+                                      h->Ntot, h->gmul.p + static_cast<size_t>(2 * i + 1) * B * D, D, As(2 * i + 1), Ss(2 * i + 1),
+                                      h->SS, tr->MA.p + i * MD, T, st));
+      else
+        LDMAE_TRY(gemm_residual(o_i, D, b.w_proj.p, D, GemmShape{M, D, D}, h->xres.p, D, b.b_proj.p, gate_msa, h->Ntot,
+                                h->gmul.p + static_cast<size_t>(2 * i + 1) * B * D, D, h->abuf.p, h->ssq.p, h->SS, T, st));
     }
     LDMAE_DBG_STAGE();
     EpiSwiGLU::Params es;
-    LDMAE_TRY(make_tmap_out_bf16(&es.omap, h->hbuf.p, M, h->Hp, h->Hp));
-    es.ssq = h->ssq.p; es.cvec = h->cvec_12.p + static_cast<size_t>(i) * B * 2 * h->Hp;
+    LDMAE_TRY(make_tmap_out_bf16(&es.omap, hb_i, M, h->Hp, h->Hp));
+    es.has_pre = 0; es.premap = es.omap;
+    if (tr) {
+      es.has_pre = 1;
+      LDMAE_TRY(make_tmap_out_bf16(&es.premap, tr->H12.p + static_cast<size_t>(i) * M * 2 * h->Hp, M, 2 * h->Hp, 2 * h->Hp));
+    }
+    es.ssq = Ss(2 * i + 1); es.cvec = h->cvec_12.p + static_cast<size_t>(i) * B * 2 * h->Hp;
     es.rows_per_sample = T; es.ss_slots = h->SS; es.inv_D = 1.f / D; es.eps_row = eps;
-    { ProfScope ps(3, st); LDMAE_TRY((gemm_auto<EpiSwiGLU>(h->abuf.p, D, b.w12.p, D, GemmShape{M, 2 * h->Hp, D}, es, st))); }
+    { ProfScope ps(3, st); LDMAE_TRY((gemm_auto<EpiSwiGLU>(As(2 * i + 1), D, b.w12.p, D, GemmShape{M, 2 * h->Hp, D}, es, st))); }
     LDMAE_DBG_STAGE();
     {
       ProfScope ps(4, st);
-      LDMAE_TRY(gemm_residual(h->hbuf.p, h->Hp, b.w3.p, h->Hp, GemmShape{M, D, h->Hp}, h->xres.p, D, b.b3.p, gate_mlp, h->Ntot,
-                              h->gmul.p + static_cast<size_t>(2 * i + 2) * B * D, D, h->abuf.p, h->ssq.p, h->SS, T, st));
+      if (tr)
+        LDMAE_TRY(gemm_residual_train(hb_i, h->Hp, b.w3.p, h->Hp, GemmShape{M, D, h->Hp}, Xs(2 * i + 1), Xs(2 * i + 2), D, b.b3.p,
+                                      gate_mlp, h->Ntot, h->gmul.p + static_cast<size_t>(2 * i + 2) * B * D, D, As(2 * i + 2),
+                                      Ss(2 * i + 2), h->SS, tr->MM.p + i * MD, T, st));
+      else
+        LDMAE_TRY(gemm_residual(h->hbuf.p, h->Hp, b.w3.p, h->Hp, GemmShape{M, D, h->Hp}, h->xres.p, D, b.b3.p, gate_mlp, h->Ntot,
+                                h->gmul.p + static_cast<size_t>(2 * i + 2) * B * D, D, h->abuf.p, h->ssq.p, h->SS, T, st));
     }
     LDMAE_DBG_STAGE();
   }
   // 6. final layer + unpatchify
   {
     EpiFinal::Params ef;
-    ef.out = out; ef.ssq = h->ssq.p; ef.cvec = h->cvec_f.p; ef.grid = h->G; ef.patch = c.patch_size;
+    ef.out = out; ef.ssq = Ss(2 * depth); ef.cvec = h->cvec_f.p; ef.grid = h->G; ef.patch = c.patch_size;
     ef.cout = c.in_channels * (c.learn_sigma ? 2 : 1); ef.cstore = c.in_channels; ef.rows_per_sample = T; ef.ss_slots = h->SS;
     ef.inv_D = 1.f / D; ef.eps_row = eps;
     ProfScope ps(6, st);
-    LDMAE_TRY((launch_gemm<16, 1, EpiFinal>(h->abuf.p, D, h->w_f.p, D, GemmShape{M, h->Nf, D}, ef, st)));
+    LDMAE_TRY((launch_gemm<16, 1, EpiFinal>(As(2 * depth), D, h->w_f.p, D, GemmShape{M, h->Nf, D}, ef, st)));
     ++g_launch_count;
   }
   return LDMAE_OK;
@@ -704,6 +804,10 @@ extern "C" int ldmae_dit_forward(ldmae_dit* h, const float* x, const float* t, f
   LDMAE_REQUIRE(x && y && out, "null tensor");
   return dit_forward_impl(h, x, t, t_scalar, y, out, B, src_mod, static_cast<cudaStream_t>(stream));
 }
+
+// ------------------------------------------------------------------------------------------- LightningDiT training
+// Backward of LightningDiT.forward for transport.training_losses / train_accum.py:215-230.
+#include "dit_train.inc"
 
 static int launch_update(float* xout, const float* xin, const float* v, const float* kprev, float* gout, int n_half,
                          int C, int HW, float cfg_scale, int use_guidance, float a, float bcoef, size_t total,

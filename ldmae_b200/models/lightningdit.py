@@ -280,14 +280,16 @@ class LightningDiT(nn.Module):
 
     # -- forward (reference lightningdit.py:391-418) ------------------------------------------
     def forward(self, x, t=None, y=None):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError("ldmae_b200 round 1 ships the inference path (forward / forward_with_cfg / sampler / "
-                                      "decoder); the backward kernels for train_accum.py are the next milestone")
         if self.training and self.y_embedder.dropout_prob > 0:
             y = self.y_embedder.token_drop(y)             # lightningdit.py:165-167
         x, t, y = self._prep(x, t, y)
         B = x.shape[0]
         h = self._ensure_handle(x.device, B)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # differentiable path (train_accum.py:215-230): the library keeps the activations, autograd sees one node whose
+            # inputs are the trainable parameters, so .grad / DDP hooks / torch optimizers work as with the reference
+            named = [(k, p) for k, p in self.named_parameters() if p.requires_grad]
+            return _DitTrainFunction.apply(self, h, x, t, y, tuple(k for k, _ in named), *[p for _, p in named])
         out = torch.empty(B, self.in_channels, x.shape[2], x.shape[3], device=x.device, dtype=torch.float32)
         with torch.cuda.device(x.device):
             _lib.check(_lib.lib().ldmae_dit_forward(h, _lib.ptr(x), _lib.ptr(t), 0.0, _lib.ptr(y), _lib.ptr(out), B, B,
@@ -324,6 +326,37 @@ class LightningDiT(nn.Module):
                                                    float(cfg_interval_start), grid, npts, int(method), _lib.ptr(traj),
                                                    int(flags), _lib.stream_ptr()), "ldmae_sample_ode")
         return x, traj
+
+
+class _DitTrainFunction(torch.autograd.Function):
+    """LightningDiT.forward as one autograd node: ldmae_dit_train_forward / ldmae_dit_backward (sm_100a kernels).
+    Gradients w.r.t. the latent input are not produced (transport.training_losses never asks for them)."""
+
+    @staticmethod
+    def forward(ctx, model, h, x, t, y, names, *params):
+        B = x.shape[0]
+        out = torch.empty(B, model.in_channels, x.shape[2], x.shape[3], device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().ldmae_dit_train_forward(h, _lib.ptr(x), _lib.ptr(t), _lib.ptr(y), _lib.ptr(out), B,
+                                                          _lib.stream_ptr()), "ldmae_dit_train_forward")
+        ctx.h, ctx.B, ctx.names, ctx.dev = h, B, names, x.device
+        ctx.shapes = [tuple(p.shape) for p in params]
+        ctx.flat = getattr(model, "_flat_grad_views", None)      # ldmae_b200.training: gradients land in one flat buffer
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        L = _lib.lib()
+        dout = dout.detach().float().contiguous()
+        grads = []
+        with torch.cuda.device(ctx.dev):
+            st = _lib.stream_ptr()
+            _lib.check(L.ldmae_dit_backward(ctx.h, _lib.ptr(dout), ctx.B, st), "ldmae_dit_backward")
+            for name, shape in zip(ctx.names, ctx.shapes):
+                g = ctx.flat[name] if ctx.flat is not None else torch.empty(shape, device=ctx.dev, dtype=torch.float32)
+                _lib.check(L.ldmae_dit_grad_read(ctx.h, name.encode(), _lib.ptr(g), g.numel(), st), f"grad {name}")
+                grads.append(g)
+        return (None, None, None, None, None, None, *grads)
 
 
 def get_2d_sincos_pos_embed(embed_dim, grid_size, cls_token=False, extra_tokens=0):

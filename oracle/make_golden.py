@@ -107,6 +107,30 @@ def gen_dit_tiny():
         print("dit tiny patch", patch, "out absmax", out.abs().max().item(), "loss", terms["loss"].mean().item())
 
 
+def gen_dit_grads():
+    """Gradients of the reference's own training loss (transport.training_losses -> loss.mean().backward(),
+    train_accum.py:215-230) for the tiny models, with the random draws (t, x0) fixed; eval mode (no label dropout)."""
+    for patch in (1, 2):
+        spec, ref, sd = tiny_dit(patch)
+        g = torch.Generator().manual_seed(300 + patch)
+        B = 4
+        x1 = torch.randn(B, 16, 8, 8, generator=g)
+        x0 = torch.randn(B, 16, 8, 8, generator=g)
+        t = torch.rand(B, generator=g)
+        y = torch.randint(0, 10, (B,), generator=g)
+        tr = create_transport("Linear", "velocity", None, None, None, use_cosine_loss=False, use_lognorm=True)
+        tr.sample = lambda x1_, *a, **k: (t, x0, x1_)
+        with torch.enable_grad():
+            for p_ in ref.parameters():
+                p_.grad = None
+            terms = tr.training_losses(ref, x1, dict(y=y))
+            terms["loss"].mean().backward()
+        grads = {"grad." + k: p_.grad.numpy() for k, p_ in ref.named_parameters() if p_.grad is not None}
+        np.savez_compressed(os.path.join(OUT, f"dit_tiny_grads_p{patch}.npz"), seed=11 + patch, checksum=O.state_checksum(sd),
+                            x1=x1.numpy(), x0=x0.numpy(), t=t.numpy(), y=y.numpy(), loss=terms["loss"].detach().numpy(), **grads)
+        print("dit tiny grads patch", patch, "loss", terms["loss"].mean().item(), len(grads), "tensors")
+
+
 def gen_dit_variants():
     """Config flags the API must accept (SURVEY section 8a tail): celeba (no qk-norm, 1 class -> no cfg
     embedding is NOT the case: class_dropout_prob stays 0.1 unless num_classes==1), wo_shift."""
@@ -173,7 +197,11 @@ def gen_vmae():
 
 
 if __name__ == "__main__":
+    if "--grads-only" in sys.argv:
+        gen_dit_grads()
+        sys.exit(0)
     gen_dit_tiny()
+    gen_dit_grads()
     gen_dit_variants()
     gen_dit_b1()
     gen_vmae()

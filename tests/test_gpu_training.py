@@ -1,0 +1,145 @@
+"""-m gpu: parity of the training path (forward that keeps activations, backward kernels, fused AdamW + EMA) with
+autograd through the CPU oracle (fp32) on the same seeded inputs and weights, and with the committed gradients of the
+unmodified reference (tests/golden/dit_tiny_grads_p*.npz, written by oracle/make_golden.py).
+
+Tolerance: gradients are products of bf16 tensor-core GEMMs with fp32 accumulation; per-parameter relative error
+(Frobenius) <= 3e-2 against fp32 autograd, loss relative error <= 1e-2 (north_star's per-forward bound).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ldmae_oracle as O
+
+pytestmark = pytest.mark.gpu
+GRAD_TOL = 3e-2
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _oracle_grads(spec, sd, x1, t, x0, y):
+    leaves = {k: v.clone().requires_grad_(v.is_floating_point() and k != "pos_embed" and not k.startswith("feat_rope"))
+              for k, v in sd.items()}
+    terms = O.training_losses(lambda xt, tt, y: O.dit_forward(leaves, spec, xt, tt, y), x1, t, x0, y=y)
+    terms["loss"].mean().backward()
+    return terms, {k: v.grad for k, v in leaves.items() if v.grad is not None}
+
+
+def _our_grads(m, x1, t, x0, y):
+    from ldmae_b200.transport import create_transport
+    tr = create_transport("Linear", "velocity", None, None, None, use_cosine_loss=False, use_lognorm=True)
+    tr.sample = lambda x1_, *a, **k: (t.to(x1_), x0.to(x1_), x1_)       # inject the random draws (SURVEY 8c pitfall 3)
+    m.zero_grad(set_to_none=True)
+    with torch.enable_grad():
+        terms = tr.training_losses(m, x1, dict(y=y))
+        terms["loss"].mean().backward()
+    torch.cuda.synchronize()
+    return terms, {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+
+
+def _compare(ours, ref, tol=GRAD_TOL):
+    assert set(ours) == set(ref), set(ours) ^ set(ref)
+    bad = []
+    worst = ("", 0.0)
+    for k in sorted(ref):
+        e = _rel(ours[k], ref[k])
+        if e > worst[1]:
+            worst = (k, e)
+        if not e < tol:
+            bad.append((k, e, float(ref[k].norm())))
+    print(f"worst gradient rel err {worst[1]:.3e} ({worst[0]})")
+    assert not bad, f"{len(bad)} gradients off: {bad[:12]}"
+
+
+def _tiny(patch, seed, **flags):
+    from ldmae_b200.models.lightningdit import LightningDiT
+    spec = O.DiTSpec(depth=2, hidden_size=128, patch_size=patch, num_heads=2, input_size=8, in_channels=16, num_classes=10, **flags)
+    m = LightningDiT(input_size=8, patch_size=patch, in_channels=16, hidden_size=128, depth=2, num_heads=2, num_classes=10,
+                     use_qknorm=spec.use_qknorm, use_swiglu=True, use_rope=spec.use_rope, use_rmsnorm=True, wo_shift=spec.wo_shift)
+    sd = O.synth_dit_state(spec, seed)
+    m.load_state_dict(sd, strict=True)
+    return spec, sd, m.cuda().eval()        # eval: no label dropout, the draws are injected
+
+
+@pytest.mark.parametrize("patch,flags", [(1, {}), (2, {}), (1, dict(use_qknorm=False)), (1, dict(wo_shift=True)),
+                                         (1, dict(use_rope=False))])
+def test_tiny_backward_matches_oracle_autograd(patch, flags):
+    spec, sd, m = _tiny(patch, 21 + patch, **flags)
+    g = torch.Generator().manual_seed(5 + patch)
+    B = 5
+    x1 = torch.randn(B, 16, 8, 8, generator=g)
+    x0 = torch.randn(B, 16, 8, 8, generator=g)
+    t = torch.rand(B, generator=g)
+    y = torch.randint(0, 10, (B,), generator=g)
+    ref_terms, ref = _oracle_grads(spec, sd, x1, t, x0, y)
+    terms, ours = _our_grads(m, x1.cuda(), t, x0, y.cuda())
+    assert _rel(terms["loss"], ref_terms["loss"].detach()) < 1e-2
+    assert _rel(terms["pred"], ref_terms["pred"].detach()) < 1e-2
+    _compare(ours, ref)
+
+
+@pytest.mark.parametrize("patch", [1, 2])
+def test_tiny_backward_matches_reference_golden(golden_dir, patch):
+    """Gradients of the UNMODIFIED reference (autograd through LDMAE/models/lightningdit.py on CPU, fp32)."""
+    from gpu_util import load_npz
+    g = load_npz(golden_dir, f"dit_tiny_grads_p{patch}.npz")
+    spec, sd, m = _tiny(patch, int(g["seed"]))
+    x1, t, x0, y = (torch.from_numpy(g[k]) for k in ("x1", "t", "x0", "y"))
+    terms, ours = _our_grads(m, x1.cuda(), t, x0, y.cuda())
+    assert _rel(terms["loss"], g["loss"]) < 1e-2
+    ref = {k[len("grad."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("grad.")}
+    _compare(ours, ref)
+
+
+def test_b1_backward_matches_oracle_autograd():
+    """LightningDiT-B/1 at the benchmark shape (T = 1024, D = 768, 12 blocks), batch 2."""
+    from ldmae_b200.models.lightningdit import LightningDiT_models
+    spec = O.DiTSpec.named("LightningDiT-B/1", input_size=32, in_channels=16)
+    sd = O.synth_dit_state(spec, 3)
+    m = LightningDiT_models["LightningDiT-B/1"](input_size=32, in_channels=16, use_qknorm=True, use_swiglu=True, use_rope=True,
+                                                use_rmsnorm=True)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    g = torch.Generator().manual_seed(9)
+    B = 2
+    x1 = torch.randn(B, 16, 32, 32, generator=g)
+    x0 = torch.randn(B, 16, 32, 32, generator=g)
+    t = torch.rand(B, generator=g)
+    y = torch.randint(0, 1000, (B,), generator=g)
+    ref_terms, ref = _oracle_grads(spec, sd, x1, t, x0, y)
+    terms, ours = _our_grads(m, x1.cuda(), t, x0, y.cuda())
+    assert _rel(terms["loss"], ref_terms["loss"].detach()) < 1e-2
+    # the embedding table only has gradient rows for the two drawn labels: compare it as a whole like the others
+    _compare(ours, ref, tol=4e-2)
+
+
+def test_fused_adamw_ema_matches_torch():
+    from ldmae_b200 import _lib
+    n = 100_003 * 4
+    g = torch.Generator().manual_seed(1)
+    p0 = torch.randn(n, generator=g)
+    ema0 = p0.clone()
+    p_ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([p_ref], lr=2e-4, betas=(0.9, 0.95), weight_decay=0.01)
+    ema_ref = ema0.clone()
+    p = p0.clone().cuda(); m = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda"); ema = ema0.clone().cuda()
+    for step in range(1, 4):
+        grad = torch.randn(n, generator=g)
+        p_ref.grad = grad.clone()
+        opt.step()
+        ema_ref.mul_(0.9999).add_(p_ref.data, alpha=1 - 0.9999)
+        gd = (grad * 2).cuda()                              # grad_scale 0.5 undoes the factor (all-reduce average)
+        _lib.check(_lib.lib().ldmae_adamw_ema_step(_lib.ptr(p), _lib.ptr(gd), _lib.ptr(m), _lib.ptr(v), _lib.ptr(ema), n, 2e-4, 0.9,
+                                                   0.95, 1e-8, 0.01, step, 0.9999, 0.5, _lib.stream_ptr()), "adamw")
+    torch.cuda.synchronize()
+    torch.testing.assert_close(p.cpu(), p_ref.data, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(ema.cpu(), ema_ref, rtol=1e-5, atol=1e-6)

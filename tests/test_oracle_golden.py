@@ -115,3 +115,31 @@ def test_time_grid_counts():
     t = O.ode_time_grid(250, 0.3)
     assert t.shape == (250,) and t[0] == 0 and t[-1] == 1
     assert int((t[:-1] < 0.10).sum()) == 68     # evals that skip guidance at cfg_interval_start 0.10
+
+
+@pytest.mark.parametrize("patch", [1, 2])
+def test_oracle_autograd_reproduces_reference_gradients(golden_dir, patch):
+    """The training path's checker: autograd through the oracle restatement equals the reference's own
+    loss.backward() (tests/golden/dit_tiny_grads_p*.npz, oracle/make_golden.py:gen_dit_grads)."""
+    g = np.load(os.path.join(golden_dir, f"dit_tiny_grads_p{patch}.npz"))
+    spec = O.DiTSpec(depth=2, hidden_size=128, patch_size=patch, num_heads=2, input_size=8, in_channels=16, num_classes=10)
+    sd = O.synth_dit_state(spec, int(g["seed"]))
+    assert abs(O.state_checksum(sd) - float(g["checksum"])) < 1e-6 * abs(float(g["checksum"])) + 1e-9
+    leaves = {k: v.clone().requires_grad_(v.is_floating_point() and k != "pos_embed" and not k.startswith("feat_rope"))
+              for k, v in sd.items()}
+    x1, x0, t, y = (torch.from_numpy(g[k]) for k in ("x1", "x0", "t", "y"))
+    with torch.enable_grad():
+        terms = O.training_losses(lambda xt, tt, y: O.dit_forward(leaves, spec, xt, tt, y), x1, t, x0, y=y)
+        terms["loss"].mean().backward()
+    np.testing.assert_allclose(terms["loss"].detach().numpy(), g["loss"], rtol=2e-4)
+    n = 0
+    for k in g.files:
+        if not k.startswith("grad."):
+            continue
+        ref = torch.from_numpy(g[k])
+        got = leaves[k[5:]].grad
+        assert got is not None, k
+        err = float((got - ref).norm() / ref.norm().clamp_min(1e-30))
+        assert err < 2e-4, (k, err)
+        n += 1
+    assert n == 40
