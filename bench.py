@@ -159,6 +159,71 @@ def workload_config(args):
             "l2": "inputs larger than L2: each evaluation streams >6 GB of activations (L2 = 126 MB)"}
 
 
+# ----------------------------------------------------------------------------- training step (BASELINE.json configs[2])
+def measure_train(args, dev, rank, world):
+    """train samples/s: one step = one optimizer step of train_accum.py:203-246 on `--train-batch` synthetic latents per GPU
+    (flow-matching loss, forward + backward, gradient all-reduce across ranks, fused AdamW + EMA, weight re-pack).
+    Inputs come from pinned host memory every step and the per-sample losses are read back (end-to-end by construction)."""
+    import torch
+    import torch.distributed as dist
+    from ldmae_b200 import _lib
+    from ldmae_b200.pipeline import build_sampling_models
+    from ldmae_b200.training import FusedTrainer
+    B = args.train_batch
+    model, _ = build_sampling_models(dev, seed=0)
+    model.train()
+    trainer = FusedTrainer(model, lr=2e-4, betas=(0.9, 0.95), weight_decay=0.0, ema_decay=0.9999)
+    g = torch.Generator().manual_seed(100 + rank)
+    x_host = torch.randn(B, 16, 32, 32, generator=g).pin_memory()
+    y_host = torch.randint(0, 1000, (B,), generator=g).pin_memory()
+    loss_host = torch.empty(B).pin_memory()
+
+    def one_step():
+        x = x_host.to(dev, non_blocking=True)
+        y = y_host.to(dev, non_blocking=True)
+        loss = trainer.step(x, y)
+        loss_host.copy_(loss, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(max(3, args.warmup)):
+            one_step()
+        barrier()
+        launches0 = _lib.launch_count()
+        _lib.profile_begin()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.train_steps):
+            one_step()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        prof = _lib.profile_end()
+    launches = _lib.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    ms_step = ms / args.train_steps
+    _, fwd = dit_flops_per_sample_forward()
+    pk = peaks()
+    tfl = 3 * fwd * B / (ms_step / 1e3) / 1e12
+    del trainer, model
+    torch.cuda.empty_cache()
+    return {"metric": "LightningDiT-B train samples/s", "value": world * B / (ms_step / 1e3), "unit": "samples/s",
+            "batch_per_gpu": B, "global_batch": world * B, "steps": args.train_steps, "ms_per_step": ms_step,
+            "tflops_per_gpu": tfl, "frac_of_bf16_peak": tfl / pk["tflops"], "flops_per_sample": 3 * fwd,
+            "gpu_launches": launches, "final_loss": float(loss_host.mean()),
+            "class_ms_per_step": {k: round(v[0] / args.train_steps, 3) for k, v in prof.items() if v[1] > 0},
+            "includes": "H2D of latents/labels, label dropout, forward, loss, backward, gradient all-reduce (N>1), fused AdamW+EMA, "
+                        "bf16 weight re-pack, D2H of per-sample losses",
+            "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": B * 4}
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def run_gpu(args, rank, world, local_rank):
     import torch
@@ -171,6 +236,13 @@ def run_gpu(args, rank, world, local_rank):
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if args.train_only:
+        tr = measure_train(args, dev, rank, world)
+        if rank == 0:
+            print(json.dumps(tr), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     def barrier():
         if world > 1:
@@ -238,6 +310,11 @@ def run_gpu(args, rank, world, local_rank):
         t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total, ms_e2e = float(t[0]), float(t[1])
+    train = None
+    if not args.no_train:
+        del job, model, vae
+        torch.cuda.empty_cache()
+        train = measure_train(args, dev, rank, world)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -268,7 +345,7 @@ def run_gpu(args, rank, world, local_rank):
                 "frac": achieved / pk["tflops"], "traffic": traffic, "peak_source": pk["source"],
                 "flops_per_launch": flops_per_launch, "avg_launch_ms": ms / cnt, "launches_timed": cnt}
     class_ms = {k: round(v[0] / args.steps, 3) for k, v in prof.items()}
-    job_flops = fwd_flops * Bf * job.model_evals
+    job_flops = fwd_flops * Bf * (args.num_steps - 1)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": workload_config(args), "clocks": clk,
@@ -279,6 +356,8 @@ def run_gpu(args, rank, world, local_rank):
             "dit_tflops_per_gpu": job_flops / (ms_per_step / 1e3) / 1e12,
             "dit_frac_of_bf16_peak": job_flops / (ms_per_step / 1e3) / 1e12 / pk["tflops"],
             "class_ms_per_step": class_ms}
+    if train is not None:
+        line["train"] = train
     if ms_skip is not None:
         line["cond_only_when_unguided"] = {
             "value": world * n / (ms_skip / 1e3), "unit": UNIT, "ms_per_step": ms_skip, "steps": 1,
@@ -307,6 +386,10 @@ def main():
     ap.add_argument("--cpu-images", type=int, default=2)
     ap.add_argument("--cpu-points", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-batch", type=int, default=128, help="training samples per GPU per optimizer step")
+    ap.add_argument("--train-steps", type=int, default=10)
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement (the `train` object)")
+    ap.add_argument("--train-only", action="store_true", help="measure only the training step and print its object")
     ap.add_argument("--no-cond-only-extra", action="store_true", help="skip the extra cond-only-below-interval measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

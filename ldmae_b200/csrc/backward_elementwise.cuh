@@ -50,7 +50,9 @@ struct ResidBwdParams {
   float eps;
 };
 
-__global__ void __launch_bounds__(256)
+// Column sums stay in registers over the 8 rows a warp owns (lane = 4 columns of every 128-column chunk, panels of
+// 6 chunks) and reach shared memory once per warp and panel, global memory once per CTA and column.
+__global__ void __launch_bounds__(256, 2)
 resid_bwd_kernel(const ResidBwdParams p) {
   extern __shared__ float s_acc[];              // [3][D]: dg, dgate, sdx
   const int b = blockIdx.y;
@@ -62,49 +64,90 @@ resid_bwd_kernel(const ResidBwdParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* g = p.g + static_cast<size_t>(b) * D;
   const float* gate = p.gate ? p.gate + static_cast<size_t>(b) * p.gate_ld : nullptr;
-  for (int r = warp; r < nrows; r += 8) {
-    const size_t row = static_cast<size_t>(b) * p.T + t0 + r;
-    const float rinv = row_rinv_g(p.ssq, row, p.slots, 1.f / D, p.eps);
-    const float* xr = p.x + row * D;
-    const __nv_bfloat16* gr = p.gp + row * D;
-    float t = 0.f;
-    for (int c = lane * 4; c < D; c += 128) {
-      const float4 xv = *reinterpret_cast<const float4*>(xr + c);
-      const float4 gv = __ldg(reinterpret_cast<const float4*>(g + c));
-      const uint2 gw = *reinterpret_cast<const uint2*>(gr + c);
-      const float2 a = bf2_to_f2(gw.x), bq = bf2_to_f2(gw.y);
-      t = fmaf(a.x * xv.x, gv.x, t); t = fmaf(a.y * xv.y, gv.y, t);
-      t = fmaf(bq.x * xv.z, gv.z, t); t = fmaf(bq.y * xv.w, gv.w, t);
-    }
-    t = warp_sum(t);
-    const float coef = rinv * rinv * t / D;
-    float* dxr = p.dx + row * D;
-    const __nv_bfloat16* mr = p.m_prev ? p.m_prev + row * D : nullptr;
-    for (int c = lane * 4; c < D; c += 128) {
-      const float4 xv = *reinterpret_cast<const float4*>(xr + c);
-      const float4 gv = __ldg(reinterpret_cast<const float4*>(g + c));
-      const uint2 gw = *reinterpret_cast<const uint2*>(gr + c);
-      const float2 a = bf2_to_f2(gw.x), bq = bf2_to_f2(gw.y);
-      const float gpv[4] = {a.x, a.y, bq.x, bq.y};
-      const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-      const float gs[4] = {gv.x, gv.y, gv.z, gv.w};
-      float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (!p.dx_zero) d4 = *reinterpret_cast<const float4*>(dxr + c);
-      float dn[4] = {d4.x, d4.y, d4.z, d4.w};
-      float gt[4] = {1.f, 1.f, 1.f, 1.f};
-      if (gate) { const float4 q = __ldg(reinterpret_cast<const float4*>(gate + c)); gt[0] = q.x; gt[1] = q.y; gt[2] = q.z; gt[3] = q.w; }
-      float mv[4] = {0.f, 0.f, 0.f, 0.f};
-      if (mr) { const uint2 mw = *reinterpret_cast<const uint2*>(mr + c); const float2 m0 = bf2_to_f2(mw.x), m1 = bf2_to_f2(mw.y);
-                mv[0] = m0.x; mv[1] = m0.y; mv[2] = m1.x; mv[3] = m1.y; }
+  const size_t row0 = static_cast<size_t>(b) * p.T + t0 + warp * 8;
+  const int myrows = max(0, min(8, nrows - warp * 8));
+  // pass A: coef[i] = r^2 / D * sum_col(Gp * x * g) of each of this warp's rows
+  float coef[8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        dn[q] = dn[q] + gs[q] * gpv[q] - xs[q] * coef;
-        atomicAdd(&s_acc[c + q], gpv[q] * xs[q]);
-        if (mr) atomicAdd(&s_acc[D + c + q], dn[q] * mv[q]);
-        if (p.sdx) atomicAdd(&s_acc[2 * D + c + q], dn[q]);
+  for (int i = 0; i < 8; ++i) {
+    coef[i] = 0.f;
+    if (i < myrows) {
+      const size_t row = row0 + i;
+      const float* xr = p.x + row * D;
+      const __nv_bfloat16* gr = p.gp + row * D;
+      float t = 0.f;
+      for (int c = lane * 4; c < D; c += 128) {
+        const float4 xv = *reinterpret_cast<const float4*>(xr + c);
+        const float4 gv = __ldg(reinterpret_cast<const float4*>(g + c));
+        const uint2 gw = *reinterpret_cast<const uint2*>(gr + c);
+        const float2 a = bf2_to_f2(gw.x), bq = bf2_to_f2(gw.y);
+        t = fmaf(a.x * xv.x, gv.x, t); t = fmaf(a.y * xv.y, gv.y, t);
+        t = fmaf(bq.x * xv.z, gv.z, t); t = fmaf(bq.y * xv.w, gv.w, t);
       }
-      *reinterpret_cast<float4*>(dxr + c) = make_float4(dn[0], dn[1], dn[2], dn[3]);
-      *reinterpret_cast<uint2*>(p.dy + row * D + c) = make_uint2(pack_bf16x2(dn[0] * gt[0], dn[1] * gt[1]), pack_bf16x2(dn[2] * gt[2], dn[3] * gt[3]));
+      t = warp_sum(t);
+      const float rinv = row_rinv_g(p.ssq, row, p.slots, 1.f / D, p.eps);
+      coef[i] = rinv * rinv * t / D;
+    }
+  }
+  // pass B, one panel of up to 768 columns at a time
+  for (int p0 = 0; p0 < D; p0 += 768) {
+    float a_dg[6][4], a_gt[6][4], a_sd[6][4];
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { a_dg[k][q] = 0.f; a_gt[k][q] = 0.f; a_sd[k][q] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < myrows) {
+        const size_t row = row0 + i;
+        const float* xr = p.x + row * D;
+        const __nv_bfloat16* gr = p.gp + row * D;
+        float* dxr = p.dx + row * D;
+        const __nv_bfloat16* mr = p.m_prev ? p.m_prev + row * D : nullptr;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          const int c = p0 + k * 128 + lane * 4;
+          if (c < D) {
+            const float4 xv = *reinterpret_cast<const float4*>(xr + c);
+            const float4 gv = __ldg(reinterpret_cast<const float4*>(g + c));
+            const uint2 gw = *reinterpret_cast<const uint2*>(gr + c);
+            const float2 a = bf2_to_f2(gw.x), bq = bf2_to_f2(gw.y);
+            const float gpv[4] = {a.x, a.y, bq.x, bq.y};
+            const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+            const float gs[4] = {gv.x, gv.y, gv.z, gv.w};
+            float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!p.dx_zero) d4 = *reinterpret_cast<const float4*>(dxr + c);
+            float dn[4] = {d4.x, d4.y, d4.z, d4.w};
+            float gt[4] = {1.f, 1.f, 1.f, 1.f};
+            if (gate) { const float4 q4 = __ldg(reinterpret_cast<const float4*>(gate + c)); gt[0] = q4.x; gt[1] = q4.y; gt[2] = q4.z; gt[3] = q4.w; }
+            float mv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (mr) { const uint2 mw = *reinterpret_cast<const uint2*>(mr + c); const float2 m0 = bf2_to_f2(mw.x), m1 = bf2_to_f2(mw.y);
+                      mv[0] = m0.x; mv[1] = m0.y; mv[2] = m1.x; mv[3] = m1.y; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              dn[q] = dn[q] + gs[q] * gpv[q] - xs[q] * coef[i];
+              a_dg[k][q] = fmaf(gpv[q], xs[q], a_dg[k][q]);
+              a_gt[k][q] = fmaf(dn[q], mv[q], a_gt[k][q]);
+              a_sd[k][q] += dn[q];
+            }
+            *reinterpret_cast<float4*>(dxr + c) = make_float4(dn[0], dn[1], dn[2], dn[3]);
+            *reinterpret_cast<uint2*>(p.dy + row * D + c) =
+                make_uint2(pack_bf16x2(dn[0] * gt[0], dn[1] * gt[1]), pack_bf16x2(dn[2] * gt[2], dn[3] * gt[3]));
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const int c = p0 + k * 128 + lane * 4;
+      if (c < D) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          atomicAdd(&s_acc[c + q], a_dg[k][q]);
+          if (p.m_prev) atomicAdd(&s_acc[D + c + q], a_gt[k][q]);
+          if (p.sdx) atomicAdd(&s_acc[2 * D + c + q], a_sd[k][q]);
+        }
+      }
     }
   }
   __syncthreads();
@@ -122,7 +165,7 @@ resid_bwd_kernel(const ResidBwdParams p) {
 //   out: dqkv in place     = r[row] * dL/d(qkv pre-norm)     (operand of the data- and weight-gradient GEMMs)
 //        dcvec[b, 3D]     += sum_t dL/d(qkv pre-norm)        (-> bias, shift and shift-path weight gradients)
 //        dqw[64], dkw[64] += sum over rows and heads of dy * xhat
-// One warp = one (row, 64-wide head) item, lane = one adjacent pair (= one RoPE pair).  One CTA = 32 rows of a sample.
+// One warp = 8 rows x one 64-wide head at a time, lane = one adjacent pair (= one RoPE pair).  One CTA = 64 rows of a sample.
 // ---------------------------------------------------------------------------------------------
 struct QkvBwdParams {
   __nv_bfloat16* dqkv;
@@ -141,49 +184,80 @@ qkv_bwd_kernel(const QkvBwdParams p) {
   extern __shared__ float s_acc[];          // [3D] column sums, then [128] dqw | dkw
   const int D = p.D, N = 3 * D;
   const int b = blockIdx.y;
-  const int t0 = blockIdx.x * 32;
-  const int nrows = min(32, p.T - t0);
+  const int t0 = blockIdx.x * 64;
+  const int nrows = min(64, p.T - t0);
   for (int i = threadIdx.x; i < N + 128; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int heads3 = N / 64;
-  const int items = nrows * heads3;
-  for (int it = warp; it < items; it += 8) {
-    const int r = it / heads3, hc = it % heads3;
-    const int col = hc * 64 + lane * 2;
-    const int which = (hc * 64) / D;                         // 0 q, 1 k, 2 v
-    const int tok = t0 + r;
-    const size_t row = static_cast<size_t>(b) * p.T + tok;
-    const float rinv = row_rinv_g(p.ssq, row, p.slots, 1.f / D, p.eps_row);
-    __nv_bfloat16* dptr = p.dqkv + row * N + col;
-    float2 dy = bf2_to_f2(*reinterpret_cast<const uint32_t*>(dptr));
-    if (which < 2) {
+  const int myrows = max(0, min(8, nrows - warp * 8));       // this warp owns 8 consecutive rows of the slab
+  const int tok0 = t0 + warp * 8;
+  const size_t row0 = static_cast<size_t>(b) * p.T + tok0;
+  float rinv[8], rc[8], rs[8];                               // row factor and this lane's RoPE angle per row
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    rinv[i] = 0.f; rc[i] = 1.f; rs[i] = 0.f;
+    if (i < myrows) {
+      rinv[i] = row_rinv_g(p.ssq, row0 + i, p.slots, 1.f / D, p.eps_row);
       if (p.rope != nullptr) {
-        const int axis = lane >> 4, f = lane & 15;
+        const int axis = lane >> 4, f = lane & 15, tok = tok0 + i;
         const int pos = axis == 0 ? tok / p.G : tok % p.G;
         const float* tab = p.rope + (static_cast<size_t>(axis) * p.G + pos) * 32;
-        const float cs = __ldg(tab + f), sn = __ldg(tab + 16 + f);
-        const float a = dy.x * cs + dy.y * sn;               // transpose of (a,b) -> (a c - b s, b c + a s)
-        const float bb = dy.y * cs - dy.x * sn;
-        dy = make_float2(a, bb);
-      }
-      if (p.qw != nullptr) {
-        const float2 x = bf2_to_f2(*reinterpret_cast<const uint32_t*>(p.raw + row * 2 * D + col));
-        const float ms = warp_sum(x.x * x.x + x.y * x.y);
-        const float hs = rsqrtf(ms * (1.f / 64.f) + p.eps_head);
-        const float* w = which == 0 ? p.qw : p.kw;
-        const float w0 = __ldg(w + lane * 2), w1 = __ldg(w + lane * 2 + 1);
-        const float xh0 = x.x * hs, xh1 = x.y * hs;
-        const float u0 = dy.x * w0, u1 = dy.y * w1;
-        const float mu = warp_sum(u0 * xh0 + u1 * xh1) * (1.f / 64.f);
-        atomicAdd(&s_acc[N + which * 64 + lane * 2], dy.x * xh0);
-        atomicAdd(&s_acc[N + which * 64 + lane * 2 + 1], dy.y * xh1);
-        dy = make_float2(hs * (u0 - xh0 * mu), hs * (u1 - xh1 * mu));
+        rc[i] = __ldg(tab + f); rs[i] = __ldg(tab + 16 + f);
       }
     }
-    atomicAdd(&s_acc[col], dy.x);
-    atomicAdd(&s_acc[col + 1], dy.y);
-    *reinterpret_cast<uint32_t*>(dptr) = pack_bf16x2(dy.x * rinv, dy.y * rinv);
+  }
+  float wacc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};               // dq_norm.weight / dk_norm.weight partial sums of this lane's pair
+  for (int hc = 0; hc < heads3; ++hc) {
+    const int col = hc * 64 + lane * 2;
+    const int which = (hc * 64) / D;                         // 0 q, 1 k, 2 v
+    float w0 = 1.f, w1 = 1.f;
+    if (which < 2 && p.qw != nullptr) { const float* w = which == 0 ? p.qw : p.kw; w0 = __ldg(w + lane * 2); w1 = __ldg(w + lane * 2 + 1); }
+    uint32_t dyw[8], xw[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      dyw[i] = 0u; xw[i] = 0u;
+      if (i < myrows) {
+        dyw[i] = *reinterpret_cast<const uint32_t*>(p.dqkv + (row0 + i) * N + col);
+        if (which < 2 && p.qw != nullptr) xw[i] = *reinterpret_cast<const uint32_t*>(p.raw + (row0 + i) * 2 * D + col);
+      }
+    }
+    float c0 = 0.f, c1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float2 dy = bf2_to_f2(dyw[i]);
+      if (which < 2) {
+        if (p.rope != nullptr) {
+          const float a = dy.x * rc[i] + dy.y * rs[i];       // transpose of (a,b) -> (a c - b s, b c + a s)
+          const float bb = dy.y * rc[i] - dy.x * rs[i];
+          dy = make_float2(a, bb);
+        }
+        if (p.qw != nullptr) {
+          const float2 x = bf2_to_f2(xw[i]);
+          const float ms = warp_sum(x.x * x.x + x.y * x.y);
+          const float hs = rsqrtf(ms * (1.f / 64.f) + p.eps_head);
+          const float xh0 = x.x * hs, xh1 = x.y * hs;
+          const float u0 = dy.x * w0, u1 = dy.y * w1;
+          const float mu = warp_sum(u0 * xh0 + u1 * xh1) * (1.f / 64.f);
+          wacc[which][0] = fmaf(dy.x, xh0, wacc[which][0]);
+          wacc[which][1] = fmaf(dy.y, xh1, wacc[which][1]);
+          dy = make_float2(hs * (u0 - xh0 * mu), hs * (u1 - xh1 * mu));
+        }
+      }
+      if (i < myrows) {
+        c0 += dy.x; c1 += dy.y;
+        *reinterpret_cast<uint32_t*>(p.dqkv + (row0 + i) * N + col) = pack_bf16x2(dy.x * rinv[i], dy.y * rinv[i]);
+      }
+    }
+    atomicAdd(&s_acc[col], c0);
+    atomicAdd(&s_acc[col + 1], c1);
+  }
+  if (p.qw != nullptr) {
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      atomicAdd(&s_acc[N + w * 64 + lane * 2], wacc[w][0]);
+      atomicAdd(&s_acc[N + w * 64 + lane * 2 + 1], wacc[w][1]);
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < N; c += blockDim.x) atomicAdd(p.dcvec + static_cast<size_t>(b) * N + c, s_acc[c]);
