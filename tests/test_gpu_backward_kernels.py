@@ -12,6 +12,10 @@ pytestmark = pytest.mark.gpu
 def _need_cuda():
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
+    prev = torch.is_grad_enabled()          # other test modules switch autograd off process-wide
+    torch.set_grad_enabled(True)
+    yield
+    torch.set_grad_enabled(prev)
 
 
 def _wgrad(p, q, c, alpha=1.0):

@@ -9,7 +9,7 @@ run() {
 }
 run tests python -m pytest -q -m gpu tests -x -s
 run bench_gemm python tools/bench_gemm.py
-run bench_small python bench.py --batch 64 --num-steps 6 --steps 2 --warmup 1 --no-cpu-baseline
+run bench_small python bench.py --batch 64 --num-steps 6 --steps 2 --warmup 1 --no-cpu-baseline --train-batch 64 --train-steps 5
 grep -hE "rel err|Error|error|assert|FAILED|passed|failed|timeout|mbarrier|vmae " gpurun_out/tests.log | head -30
 cat gpurun_out/bench_gemm.log
 python - <<'PY'
