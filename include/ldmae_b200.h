@@ -158,7 +158,7 @@ int ldmae_attention_lse(const void* qkv_bf16, void* out_bf16, float* lse2, int32
                         void* stream);
 /* Gradient of ldmae_attention (the backward of F.scaled_dot_product_attention at models/lightningdit.py:77):
  * dqkv [B*T, 3*H*64] bf16 (dq | dk | dv, same layout as qkv) from dout [B*T, H*64] bf16, the forward's out and lse2;
- * delta_ws: workspace [B*H*T + 64] fp32.  T must be a multiple of 4. */
+ * delta_ws: workspace of 2 * (B*H*T + 64) floats.  T must be a multiple of 4. */
 int ldmae_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse2, float* delta_ws,
                         void* dqkv_bf16, int32_t B, int32_t T, int32_t H, float scale, void* stream);
 /* Weight-gradient GEMM (the dW of every nn.Linear on the path): c[N1,N2] (fp32) += alpha * sum_m p[m,N1] * q[m,N2];

@@ -12,28 +12,42 @@
 // (S is recomputed in both; 7 tensor-core tile products per block pair instead of FlashAttention-2's 5, in exchange for
 // no fp32 atomics on dQ and a single simple pipeline.)
 //
-// Per CTA: warp 0 TMA loader, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 one row per thread.  TMEM (256 columns, so
-// two CTAs share an SM and one CTA's exponentials overlap the other's tensor-core work):
-//   [0,64)   S  (fp32)  -> overwritten in place by P  as bf16 pairs (columns 0..31)   = A operand of  dV += P  C_b
-//   [64,128) dP (fp32)  -> overwritten in place by dS as bf16 pairs (columns 64..95)  = A operand of  dQ|dK += dS C_a
-//   [128,192) accumulator 1 (dQ or dK)     [192,256) accumulator 2 (dV, kKV only)
-// tcgen05.mma instructions of one thread execute in order, so issuing S_{i+1} after the accumulations of block i is
-// all the write-after-read protection the aliasing needs.
+// Per CTA (one per SM): warp 0 TMA loader, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-19 one row per thread and 16 of
+// the 64 columns of a block per warp.  TMEM (512 columns), S / dP double-buffered so that the tensor core computes the scores of
+// block i+1 and the accumulations of block i-1 while the row warps work on block i:
+//   buffer b (b = i & 1) at column 128 b:  [0,64) S (fp32)   [64,128) dP (fp32)
+//       each warp overwrites the first 8 of the 16 S columns it has just read with its P (16 bf16) -- the A operand of
+//       dV += P C_b (K-step k at column 16 k) -- and likewise dS inside dP, the A operand of dQ|dK += dS C_a
+//   [256,320) accumulator 1 (dQ or dK)     [320,384) accumulator 2 (dV, kKV only)
+//   [384,416) row operand a (Q | K rows, bf16)   [416,448) row operand b (dO | V rows): A operands of the score products
+// tcgen05.mma instructions of one thread execute in order: scores(i+1) is issued after the accumulations of block i-1, the
+// previous user of its buffer, which is all the write-after-read protection the aliasing needs.
 #pragma once
 #include "ptx.cuh"
 
 namespace ldmae {
 
-constexpr int kAbThreads = 256;
-constexpr int kAbStages = 3;
+constexpr int kAbThreads = 640;        // 4 control warps + 16 row warps (four 16-column quarters per TMEM lane quarter)
+constexpr int kAbStages = 4;
 constexpr int kAbRTile = 128 * 128;     // 128 rows x 64 bf16
 constexpr int kAbCTile = 64 * 128;      // 64 rows x 64 bf16
 constexpr int kAbStageBytes = 2 * kAbCTile + 512;       // C_a, C_b, lse2[64], delta[64]
 constexpr int kAbSmemBytes = 1024 + 2 * kAbRTile + kAbStages * kAbStageBytes + 256;
 
+// Optional phase tracing of CTA (0,0,0) (debug builds: -DLDMAE_ATTN_TRACE): clock64 stamps per column block;
+// trace[i][0..3] = MMA warp (c_full seen, scores issued, pd_full seen, accumulations issued), [4..7] = row warp 4
+// (sd_full seen, TMEM loaded, math done, P/dS stored).
+#ifdef LDMAE_ATTN_TRACE
+#define ABWD_STAMP(k) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && i < 32) \
+  p.trace[i * 8 + (k)] = clock64(); } while (0)
+#else
+#define ABWD_STAMP(k) do { } while (0)
+#endif
+
 struct AttnBwdParams {
-  const float* lse2;    // [B, H, T] (+ padding)
-  const float* delta;   // [B, H, T]
+  long long* trace;     // [32][8] or nullptr (debug builds)
+  const float* nlse2;   // [B, H, T] (+ padding): -lse2 of the forward
+  const float* delta;   // [B, H, T] (+ padding): scale * sum_d dO * O
   __nv_bfloat16* dqkv;  // [B*T, ld] output, same column layout as qkv
   int T, H, ld;
   int q_col, k_col, v_col;
@@ -47,7 +61,7 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
 }
 
 template <bool kKV>
-__global__ void __launch_bounds__(kAbThreads, 2)
+__global__ void __launch_bounds__(kAbThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_constant__ CUtensorMap tm_qkv_c,
                 const __grid_constant__ CUtensorMap tm_do_r, const __grid_constant__ CUtensorMap tm_do_c, const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -59,10 +73,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
   uint64_t* r_full = bars;
   uint64_t* c_full = bars + 1;               // [stages]
   uint64_t* c_empty = c_full + kAbStages;    // [stages]
-  uint64_t* sd_full = c_empty + kAbStages;   // S and dP of the block are in TMEM (MMA -> rows)
-  uint64_t* pd_full = sd_full + 1;           // P and dS written back (rows -> MMA)
-  uint64_t* acc_done = pd_full + 1;          // all accumulations finished
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+  uint64_t* sd_full = c_empty + kAbStages;   // [2] S and dP of the block are in TMEM buffer b (MMA -> rows)
+  uint64_t* pd_full = sd_full + 2;           // [2] P and dS written back into buffer b (rows -> MMA)
+  uint64_t* acc_done = pd_full + 2;          // all accumulations finished
+  uint64_t* ra_ready = acc_done + 1;         // row operands copied into TMEM (rows -> MMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ra_ready + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -77,10 +92,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
   if (warp == 1 && lane == 0) {
     mbar_init(r_full, 1);
     for (int s = 0; s < kAbStages; ++s) { mbar_init(&c_full[s], 1); mbar_init(&c_empty[s], 1); }
-    mbar_init(sd_full, 1); mbar_init(pd_full, 4); mbar_init(acc_done, 1);
+    for (int q = 0; q < 2; ++q) { mbar_init(&sd_full[q], 1); mbar_init(&pd_full[q], 16); }
+    mbar_init(acc_done, 1); mbar_init(ra_ready, 8);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<1>(tmem_slot, 256);
+  if (warp == 2) tmem_alloc<1>(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -104,7 +120,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
           mbar_expect_tx(&c_full[stage], 2 * kAbCTile + 512);
           tma_load_2d(&tm_qkv_c, &c_full[stage], st, p.q_col + head * 64, row_base + i * 64);
           tma_load_2d(&tm_do_c, &c_full[stage], st + kAbCTile, head * 64, row_base + i * 64);
-          bulk_load_1d(st + 2 * kAbCTile, p.lse2 + vec_base + i * 64, 256, &c_full[stage]);
+          bulk_load_1d(st + 2 * kAbCTile, p.nlse2 + vec_base + i * 64, 256, &c_full[stage]);
           bulk_load_1d(st + 2 * kAbCTile + 256, p.delta + vec_base + i * 64, 256, &c_full[stage]);
         } else {
           mbar_expect_tx(&c_full[stage], 2 * kAbCTile);
@@ -115,127 +131,170 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_ss = umma_idesc_bf16(128, 64, false, false);
-      constexpr uint32_t idesc_ts = umma_idesc_bf16(128, 64, false, true);    // B = column tile read MN-major (d contiguous)
-      const uint32_t ra = smem_u32(sRa), rb = smem_u32(sRb);
-      auto issue_scores = [&](int stage) {
-        const uint32_t ca = smem_u32(sC + stage * kAbStageBytes), cb = ca + kAbCTile;
+    // MMA issuer.  The whole warp runs the control flow (so that descriptors and TMEM addresses stay warp-uniform and live in
+    // uniform registers); only the tcgen05 instructions themselves are issued by one elected lane.
+    constexpr uint32_t idesc_ss = umma_idesc_bf16(128, 64, false, false);
+    constexpr uint32_t idesc_ts = umma_idesc_bf16(128, 64, false, true);    // B = column tile read MN-major (d contiguous)
+    const bool issuer = elect_one();
+    // one descriptor per tile; K-steps advance the 14-bit start-address field: +2 (32 B) K-major, +128 (2 KB) MN-major.
+    // (The leading-dimension offset is unused in both forms: a single 64-wide swizzle atom along the other dimension.)
+    const uint64_t d_c0 = umma_smem_desc_sw128(smem_u32(sC), 1024, 0);
+    auto issue_scores = [&](int stage, int buf) {
+      const uint64_t d_ca = d_c0 + static_cast<uint64_t>((stage * kAbStageBytes) >> 4), d_cb = d_ca + (kAbCTile >> 4);
+      const uint32_t td = tmem_base + buf * 128;
+      if (issuer) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16<1>(tmem_base, umma_smem_desc_sw128(ra + k * 32, 1024, 0), umma_smem_desc_sw128(ca + k * 32, 1024, 0), idesc_ss,
-                       k != 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma_bf16_ts(td, tmem_base + 384 + k * 8, d_ca + 2 * k, idesc_ss, k != 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16<1>(tmem_base + 64, umma_smem_desc_sw128(rb + k * 32, 1024, 0), umma_smem_desc_sw128(cb + k * 32, 1024, 0),
-                       idesc_ss, k != 0 ? 1u : 0u);
-      };
-      mbar_wait(r_full, 0, 20);
-      int stage = 0; uint32_t phase = 0;
-      mbar_wait(&c_full[0], 0, 21);
-      tc_fence_after();
-      issue_scores(0);
-      umma_commit<1>(sd_full);
-      for (int i = 0; i < ncb; ++i) {
-        mbar_wait(pd_full, i & 1, 22);
+        for (int k = 0; k < 4; ++k) umma_bf16_ts(td + 64, tmem_base + 416 + k * 8, d_cb + 2 * k, idesc_ss, k != 0 ? 1u : 0u);
+        umma_commit<1>(&sd_full[buf]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(ra_ready, 0, 20);
+    tc_fence_after();
+    int stage = 0; uint32_t phase = 0;                 // ring position of block i
+    mbar_wait(&c_full[0], 0, 21);
+    tc_fence_after();
+    issue_scores(0, 0);
+    for (int i = 0; i < ncb; ++i) {
+      int nstage = stage + 1; uint32_t nphase = phase;
+      if (nstage == kAbStages) { nstage = 0; nphase ^= 1; }
+      if (i + 1 < ncb) {
+        // scores of block i+1 into the other buffer (its previous user, block i-1, was consumed by MMAs issued earlier)
+        mbar_wait(&c_full[nstage], nphase, 23);
         tc_fence_after();
-        const uint32_t ca = smem_u32(sC + stage * kAbStageBytes), cb = ca + kAbCTile;
+        ABWD_STAMP(0);
+        issue_scores(nstage, (i + 1) & 1);
+        ABWD_STAMP(1);
+      }
+      mbar_wait(&pd_full[i & 1], (i >> 1) & 1, 22);
+      tc_fence_after();
+      ABWD_STAMP(2);
+      const uint64_t d_ca = d_c0 + static_cast<uint64_t>((stage * kAbStageBytes) >> 4), d_cb = d_ca + (kAbCTile >> 4);
+      const uint32_t tb = tmem_base + (i & 1) * 128;
+      const uint32_t acc_first = i != 0 ? 1u : 0u;
+      if (issuer) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)     // 4 x 16 columns of the block; A = dS: 8 TMEM columns (16 bf16) per step
-          umma_bf16_ts(tmem_base + 128, tmem_base + 64 + k * 8, umma_smem_desc_sw128(ca + k * 2048, 1024, kAbCTile), idesc_ts,
-                       (i != 0 || k != 0) ? 1u : 0u);
+        for (int k = 0; k < 4; ++k)     // 4 x 16 columns of the block; A = dS: 16 bf16 = 8 TMEM columns at column 16 k
+          umma_bf16_ts(tmem_base + 256, tb + 64 + k * 16, d_ca + 128 * k, idesc_ts, k != 0 ? 1u : acc_first);
         if constexpr (kKV) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_ts(tmem_base + 192, tmem_base + k * 8, umma_smem_desc_sw128(cb + k * 2048, 1024, kAbCTile), idesc_ts,
-                         (i != 0 || k != 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_bf16_ts(tmem_base + 320, tb + k * 16, d_cb + 128 * k, idesc_ts, k != 0 ? 1u : acc_first);
         }
         umma_commit<1>(&c_empty[stage]);
-        if (++stage == kAbStages) { stage = 0; phase ^= 1; }
-        if (i + 1 < ncb) {
-          mbar_wait(&c_full[stage], phase, 23);
-          tc_fence_after();
-          issue_scores(stage);
-          umma_commit<1>(sd_full);
-        } else {
-          umma_commit<1>(acc_done);
-        }
+        if (i == ncb - 1) umma_commit<1>(acc_done);
       }
+      __syncwarp();
+      ABWD_STAMP(3);
+      stage = nstage; phase = nphase;
     }
   } else if (warp >= 4) {
-    const int wq = warp & 3;
+    const int wq = warp & 3;                           // TMEM lane quarter
+    const int cq = (warp - 4) >> 2;                    // which 16 of the block's 64 columns this warp works on
     const uint32_t lane_addr = static_cast<uint32_t>(wq * 32) << 16;
-    const uint32_t tS = tmem_base + lane_addr, tD = tS + 64;
     const int row = rblk * 128 + wq * 32 + lane;       // token index inside the sample
-    float lse_r = 0.f, delta_r = 0.f;
+    float2 nl_r = make_float2(0.f, 0.f), dl_r = make_float2(0.f, 0.f);
     if constexpr (!kKV) {
-      if (row < p.T) { lse_r = __ldg(p.lse2 + vec_base + row); delta_r = __ldg(p.delta + vec_base + row); }
+      if (row < p.T) {
+        const float a = __ldg(p.nlse2 + vec_base + row), d = __ldg(p.delta + vec_base + row);
+        nl_r = make_float2(a, a); dl_r = make_float2(-d, -d);
+      }
+    }
+    const float2 sl2 = make_float2(p.scale_log2, p.scale_log2), sc2 = make_float2(p.scale, p.scale);
+    if (cq < 2) {
+      // The row operands (Q | K and dO | V rows of this CTA) are the A operand of every score product: copy them once
+      // from their TMA tiles into TMEM (bf16 pairs, one row per lane), so that the score MMAs read only the 2 KB column
+      // tile from shared memory per instruction (an SS product of this shape is shared-memory-bandwidth bound).
+      mbar_wait(r_full, 0, 28);
+      const uint8_t* src = (cq == 0 ? sRa : sRb) + (wq * 32 + lane) * 128;
+      uint32_t w[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint4 v = lds128(src + ((j ^ (lane & 7)) << 4));
+        w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
+      }
+      tmem_st32(tmem_base + lane_addr + 384 + cq * 32, w);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ra_ready);
     }
     int stage = 0;
     uint32_t cphase = 0;
 #pragma unroll 1
     for (int i = 0; i < ncb; ++i) {
-      if constexpr (kKV) mbar_wait(&c_full[stage], cphase, 29);   // this thread reads the stage's lse2 / delta vectors itself
-      mbar_wait(sd_full, i & 1, 30);
+      if constexpr (kKV) mbar_wait(&c_full[stage], cphase, 29);   // this thread reads the stage's statistics vectors itself
+      mbar_wait(&sd_full[i & 1], (i >> 1) & 1, 30);
       __syncwarp();
       tc_fence_after();
-      const float* vl = reinterpret_cast<const float*>(sC + stage * kAbStageBytes + 2 * kAbCTile);
+      if (warp == 4) ABWD_STAMP(4);
+      const uint32_t tS = tmem_base + lane_addr + (i & 1) * 128 + cq * 16, tD = tS + 64;
+      const float* vl = reinterpret_cast<const float*>(sC + stage * kAbStageBytes + 2 * kAbCTile) + cq * 16;
       const float* vd = vl + 64;
-      const int cvalid = p.T - i * 64;                 // columns of this block that exist
+      const int cvalid = p.T - i * 64 - cq * 16;       // columns of this warp's quarter that exist
+      float sv[16], dp[16];
+      tmem_ld16(tS, sv);
+      tmem_ld16(tD, dp);
+      tmem_ld_wait();
+      if (warp == 4) ABWD_STAMP(5);
+      uint32_t wp[8], wd[8];
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        float s[32], dp[32];
-        tmem_ld32(tS + hf * 32, s);
-        tmem_ld32(tD + hf * 32, dp);
-        tmem_ld_wait();
-        uint32_t wp[16], wd[16];
-#pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          float l0, l1, d0, d1;
-          if constexpr (kKV) {
-            const float2 l2 = *reinterpret_cast<const float2*>(vl + hf * 32 + c);
-            const float2 d2 = *reinterpret_cast<const float2*>(vd + hf * 32 + c);
-            l0 = l2.x; l1 = l2.y; d0 = d2.x; d1 = d2.y;
-          } else {
-            l0 = l1 = lse_r; d0 = d1 = delta_r;
-          }
-          const bool ok0 = hf * 32 + c < cvalid, ok1 = hf * 32 + c + 1 < cvalid;   // columns beyond the sample: P = dS = 0
-          const float p0 = ok0 ? ex2_approx(fmaf(s[c], p.scale_log2, -l0)) : 0.f;
-          const float p1 = ok1 ? ex2_approx(fmaf(s[c + 1], p.scale_log2, -l1)) : 0.f;
-          const float e0 = ok0 ? p0 * (dp[c] - d0) * p.scale : 0.f;
-          const float e1 = ok1 ? p1 * (dp[c + 1] - d1) * p.scale : 0.f;
-          wp[c >> 1] = pack_bf16x2(p0, p1);
-          wd[c >> 1] = pack_bf16x2(e0, e1);
+      for (int c = 0; c < 16; c += 4) {
+        float2 nl0 = nl_r, nl1 = nl_r, dl0 = dl_r, dl1 = dl_r;
+        if constexpr (kKV) {
+          const float4 l4 = *reinterpret_cast<const float4*>(vl + c);
+          const float4 d4 = *reinterpret_cast<const float4*>(vd + c);
+          nl0 = make_float2(l4.x, l4.y); nl1 = make_float2(l4.z, l4.w);
+          dl0 = make_float2(-d4.x, -d4.y); dl1 = make_float2(-d4.z, -d4.w);
         }
-        if constexpr (kKV) tmem_st16(tS + hf * 16, wp);
-        tmem_st16(tD + hf * 16, wd);
+        const float2 x0 = fma2(make_float2(sv[c], sv[c + 1]), sl2, nl0);
+        const float2 x1 = fma2(make_float2(sv[c + 2], sv[c + 3]), sl2, nl1);
+        float2 p0 = make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
+        float2 p1 = make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
+        float2 e0 = fma2(make_float2(dp[c], dp[c + 1]), sc2, dl0);      // scale * dP - scale * delta
+        float2 e1 = fma2(make_float2(dp[c + 2], dp[c + 3]), sc2, dl1);
+        if (cvalid < 16) {                              // ragged tail of the sample: P = dS = 0 beyond it
+          if (c >= cvalid) { p0.x = 0.f; e0.x = 0.f; }
+          if (c + 1 >= cvalid) { p0.y = 0.f; e0.y = 0.f; }
+          if (c + 2 >= cvalid) { p1.x = 0.f; e1.x = 0.f; }
+          if (c + 3 >= cvalid) { p1.y = 0.f; e1.y = 0.f; }
+        }
+        e0 = fma2(p0, e0, make_float2(0.f, 0.f));
+        e1 = fma2(p1, e1, make_float2(0.f, 0.f));
+        wp[c >> 1] = pack_bf16x2(p0.x, p0.y);
+        wp[(c >> 1) + 1] = pack_bf16x2(p1.x, p1.y);
+        wd[c >> 1] = pack_bf16x2(e0.x, e0.y);
+        wd[(c >> 1) + 1] = pack_bf16x2(e1.x, e1.y);
       }
+      if (warp == 4) ABWD_STAMP(6);
+      if constexpr (kKV) tmem_st8(tS, wp);
+      tmem_st8(tD, wd);
       tmem_st_wait();
+      if (warp == 4) ABWD_STAMP(7);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(pd_full);
+      if (lane == 0) mbar_arrive(&pd_full[i & 1]);
       if (++stage == kAbStages) { stage = 0; cphase ^= 1; }
     }
-    // epilogue: accumulators -> bf16 rows of dqkv (the tcgen05.ld is warp-collective: only the stores are predicated)
+    // epilogue: accumulators -> bf16 rows of dqkv; this warp stores columns [16 cq, 16 cq + 16) of each accumulator
+    // (the tcgen05.ld is warp-collective: only the stores are predicated)
     mbar_wait(acc_done, 0, 31);
     __syncwarp();
     tc_fence_after();
 #pragma unroll
     for (int a = 0; a < (kKV ? 2 : 1); ++a) {
-      const int col = (kKV ? (a == 0 ? p.k_col : p.v_col) : p.q_col) + head * 64;
+      const int col = (kKV ? (a == 0 ? p.k_col : p.v_col) : p.q_col) + head * 64 + cq * 16;
       __nv_bfloat16* dst = p.dqkv + static_cast<size_t>(row_base + min(row, p.T - 1)) * p.ld + col;
+      float o[16];
+      tmem_ld16(tmem_base + lane_addr + 256 + a * 64 + cq * 16, o);
+      tmem_ld_wait();
+      if (row < p.T) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float o[32];
-        tmem_ld32(tS + 128 + a * 64 + c * 32, o);
-        tmem_ld_wait();
-        if (row < p.T) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<uint4*>(dst + c * 32 + q * 8) =
-                make_uint4(pack_bf16x2(o[8 * q], o[8 * q + 1]), pack_bf16x2(o[8 * q + 2], o[8 * q + 3]),
-                           pack_bf16x2(o[8 * q + 4], o[8 * q + 5]), pack_bf16x2(o[8 * q + 6], o[8 * q + 7]));
-        }
+        for (int q = 0; q < 2; ++q)
+          *reinterpret_cast<uint4*>(dst + q * 8) =
+              make_uint4(pack_bf16x2(o[8 * q], o[8 * q + 1]), pack_bf16x2(o[8 * q + 2], o[8 * q + 3]),
+                         pack_bf16x2(o[8 * q + 4], o[8 * q + 5]), pack_bf16x2(o[8 * q + 6], o[8 * q + 7]));
       }
     }
   }
@@ -243,12 +302,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
   __syncwarp();
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<1>(tmem_base, 256);
+  if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
 }
 
-// delta[b,h,t] = sum_d dO[t,h,d] * O[t,h,d]  (one warp per token row: lanes walk the row, heads are 64 wide)
-__global__ void attn_delta_kernel(float* __restrict__ delta, const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* __restrict__ O,
-                                  int B, int T, int H) {
+// Row statistics of the backward: delta[b,h,t] = scale * sum_d dO[t,h,d] * O[t,h,d] and nlse2 = -lse2 (both in the form the
+// packed fma of the kernels above consumes).  One warp per token row: lanes walk the row, heads are 64 wide.
+__global__ void attn_delta_kernel(float* __restrict__ delta, float* __restrict__ nlse2, const float* __restrict__ lse2,
+                                  const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* __restrict__ O, int B, int T, int H,
+                                  float scale) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= B * T) return;
@@ -260,7 +321,11 @@ __global__ void attn_delta_kernel(float* __restrict__ delta, const __nv_bfloat16
     float s = __bfloat162float(a.x) * __bfloat162float(o.x) + __bfloat162float(a.y) * __bfloat162float(o.y);
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
-    if (lane == 0) delta[(static_cast<size_t>(b) * H + h) * T + t] = s;
+    if (lane == 0) {
+      const size_t i = (static_cast<size_t>(b) * H + h) * T + t;
+      delta[i] = s * scale;
+      nlse2[i] = -lse2[i];
+    }
   }
 }
 

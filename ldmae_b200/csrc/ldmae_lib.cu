@@ -217,7 +217,7 @@ static int run_attention(const void* qkv, int ldq, void* out, int ldo, int B, in
 }
 
 // Backward of run_attention: dqkv [B*T, ldq] (same column layout as qkv) from dO [B*T, ldo], the forward output o,
-// the forward's lse2 [B,H,T] and a delta workspace [B,H,T] (both padded by 64 floats).
+// the forward's lse2 [B,H,T] (padded by 64 floats) and a statistics workspace of 2 * (B*H*T + 64) floats.
 static int run_attention_bwd(const void* qkv, int ldq, const void* o, const void* d_o, int ldo, const float* lse2, float* delta,
                              void* dqkv, int B, int T, int H, int q_col, int k_col, int v_col, float scale, cudaStream_t st) {
   LDMAE_REQUIRE(ldo == H * 64, "attention backward expects a dense [B*T, H*64] output gradient");
@@ -233,11 +233,13 @@ static int run_attention_bwd(const void* qkv, int ldq, const void* o, const void
     LDMAE_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAbSmemBytes));
     attr = true;
   }
-  attn_delta_kernel<<<cdiv(static_cast<size_t>(B) * T, 8), 256, 0, st>>>(delta, static_cast<const __nv_bfloat16*>(d_o),
-                                                                         static_cast<const __nv_bfloat16*>(o), B, T, H);
+  float* nlse2 = delta + static_cast<size_t>(B) * H * T + 64;       // second half of the workspace
+  attn_delta_kernel<<<cdiv(static_cast<size_t>(B) * T, 8), 256, 0, st>>>(delta, nlse2, lse2, static_cast<const __nv_bfloat16*>(d_o),
+                                                                         static_cast<const __nv_bfloat16*>(o), B, T, H, scale);
   LDMAE_LAUNCH_CHECK();
   AttnBwdParams p;
-  p.lse2 = lse2; p.delta = delta; p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+  p.trace = g_attn_trace;
+  p.nlse2 = nlse2; p.delta = delta; p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
   p.T = T; p.H = H; p.ld = ldq; p.q_col = q_col; p.k_col = k_col; p.v_col = v_col;
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid(cdiv(T, 128), H, B);

@@ -79,7 +79,7 @@ def test_attention_backward(B, T, H, scale):
     qkv_d, dout_d = qkv.cuda(), dout.cuda()
     out = torch.empty(B * T, H * 64, device="cuda", dtype=torch.bfloat16)
     lse2 = torch.zeros(B * H * T + 64, device="cuda")
-    delta = torch.zeros(B * H * T + 64, device="cuda")
+    delta = torch.zeros(2 * (B * H * T + 64), device="cuda")
     dqkv = torch.full((B * T, 3 * H * 64), float("nan"), device="cuda").to(torch.bfloat16)
     st = _lib.stream_ptr()
     _lib.check(L.ldmae_attention_lse(_lib.ptr(qkv_d), _lib.ptr(out), _lib.ptr(lse2), B, T, H, float(scale), st), "attn fwd")
