@@ -120,55 +120,70 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, false, false);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, false, true);   // V is MN-major (d contiguous)
-      auto issue_qk = [&](int t, int kstage) {
-        const uint32_t qa = smem_u32(sQ + t * kAttnTileBytes);
-        const uint32_t ka = smem_u32(sK + kstage * kAttnTileBytes);
+    // MMA issuer.  The whole warp runs the control flow, so descriptors and TMEM addresses are warp-uniform values in
+    // uniform registers and every tcgen05.mma is a single instruction (issued by one elected lane); with a single-lane
+    // branch around the whole loop the compiler wraps each MMA in a convergence ("waterfall") loop, which made the issue of
+    // the 24 small MMAs per key block the critical path of the kernel.
+    constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, false, false);
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, false, true);   // V is MN-major (d contiguous)
+    const bool issuer = elect_one();
+    // one descriptor per tile; K-steps advance the start-address field: +2 (32 B) K-major, +128 (2 KB) MN-major
+    const uint64_t d_q0 = umma_smem_desc_sw128(smem_u32(sQ), 1024, 0);
+    const uint64_t d_k0 = umma_smem_desc_sw128(smem_u32(sK), 1024, 0);
+    const uint64_t d_v0 = umma_smem_desc_sw128(smem_u32(sV), 1024, kAttnTileBytes);
+    auto issue_qk = [&](int t, int kstage) {
+      const uint64_t dq = d_q0 + static_cast<uint64_t>(t * (kAttnTileBytes >> 4));
+      const uint64_t dk = d_k0 + static_cast<uint64_t>(kstage * (kAttnTileBytes >> 4));
+      const uint32_t td = tmem_base + t * 128;
+      if (issuer) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16<1>(tmem_base + t * 128, umma_smem_desc_sw128(qa + k * 32, 1024, 0),
-                       umma_smem_desc_sw128(ka + k * 32, 1024, 0), idesc_qk, k != 0 ? 1u : 0u);
-      };
-      auto issue_pv = [&](int t, int vstage, bool first) {
-        const uint32_t va = smem_u32(sV + vstage * kAttnTileBytes);
+        for (int k = 0; k < 4; ++k) umma_bf16<1>(td, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
+        umma_commit<1>(&s_full[t]);
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int t, int vstage, uint32_t accumulate) {
+      const uint64_t dv = d_v0 + static_cast<uint64_t>(vstage * (kAttnTileBytes >> 4));
+      const uint32_t td = tmem_base + 384 + t * 64, ta = tmem_base + 256 + t * 64;
+      if (issuer) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)   // 8 x 16 keys; P: 8 TMEM columns (16 bf16) per step
-          umma_bf16_ts(tmem_base + 384 + t * 64, tmem_base + 256 + t * 64 + k * 8,
-                       umma_smem_desc_sw128(va + k * 2048, 1024, kAttnTileBytes), idesc_pv, (first && k == 0) ? 0u : 1u);
-      };
-      mbar_wait(q_full, 0, 20);
-      mbar_wait(&k_full[0], 0, 21);
-      tc_fence_after();
-      issue_qk(0, 0); umma_commit<1>(&s_full[0]);
-      issue_qk(1, 0); umma_commit<1>(&s_full[1]);
-      umma_commit<1>(&k_empty[0]);
-      int stage = 0; uint32_t phase = 0;                 // ring position of block j
-      for (int j = 0; j < nkv; ++j) {
-        int nstage = stage + 1; uint32_t nphase = phase;
-        if (nstage == kAttnKVStages) { nstage = 0; nphase ^= 1; }
-        if (j + 1 < nkv) {
-          // refill S_t with block j+1 as soon as the softmax warps hold block j in registers
-          mbar_wait(&k_full[nstage], nphase, 25);
-          for (int t = 0; t < 2; ++t) {
-            mbar_wait(&s_free[t], j & 1, 26 + t);
-            tc_fence_after();
-            issue_qk(t, nstage);
-            umma_commit<1>(&s_full[t]);
-          }
-          umma_commit<1>(&k_empty[nstage]);
-        }
-        mbar_wait(&v_full[stage], phase, 24);
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(&p_full[t], j & 1, 22 + t);
-          tc_fence_after();
-          issue_pv(t, stage, j == 0);
-          umma_commit<1>(&o_done[t]);
-        }
-        umma_commit<1>(&v_empty[stage]);
-        stage = nstage; phase = nphase;
+          umma_bf16_ts(td, ta + k * 8, dv + 128 * k, idesc_pv, k != 0 ? 1u : accumulate);
+        umma_commit<1>(&o_done[t]);
       }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0, 20);
+    mbar_wait(&k_full[0], 0, 21);
+    tc_fence_after();
+    issue_qk(0, 0);
+    issue_qk(1, 0);
+    if (issuer) umma_commit<1>(&k_empty[0]);
+    __syncwarp();
+    int stage = 0; uint32_t phase = 0;                 // ring position of block j
+    for (int j = 0; j < nkv; ++j) {
+      int nstage = stage + 1; uint32_t nphase = phase;
+      if (nstage == kAttnKVStages) { nstage = 0; nphase ^= 1; }
+      if (j + 1 < nkv) {
+        // refill S_t with block j+1 as soon as the softmax warps hold block j in registers
+        mbar_wait(&k_full[nstage], nphase, 25);
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&s_free[t], j & 1, 26 + t);
+          tc_fence_after();
+          issue_qk(t, nstage);
+        }
+        if (issuer) umma_commit<1>(&k_empty[nstage]);
+        __syncwarp();
+      }
+      mbar_wait(&v_full[stage], phase, 24);
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(&p_full[t], j & 1, 22 + t);
+        tc_fence_after();
+        issue_pv(t, stage, j == 0 ? 0u : 1u);
+      }
+      if (issuer) umma_commit<1>(&v_empty[stage]);
+      __syncwarp();
+      stage = nstage; phase = nphase;
     }
   }
   } else {
