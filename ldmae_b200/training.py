@@ -22,6 +22,49 @@ from . import _lib
 from .transport import create_transport
 
 
+class FlatLayout:
+    """Host-side layout of the training state: every trainable parameter becomes a view into ONE flat fp32 buffer
+    (16-byte aligned slices, in ``named_parameters`` order), with same-shaped flat buffers for the gradients, the two Adam
+    moments and the EMA copy.  Device-agnostic (the layout logic is covered by the CPU tests)."""
+
+    def __init__(self, model):
+        named = [(k, p) for k, p in model.named_parameters() if p.requires_grad]
+        if not named:
+            raise ValueError("model has no trainable parameters")
+        dev = named[0][1].device
+        sizes = [(p.numel() + 3) // 4 * 4 for _, p in named]
+        total = sum(sizes)
+        self.device = dev
+        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.names, self.slices = [], {}
+        off = 0
+        with torch.no_grad():
+            for (k, p), sz in zip(named, sizes):
+                n = p.numel()
+                self.flat[off:off + n].copy_(p.detach().reshape(-1))
+                p.data = self.flat[off:off + n].view(p.shape)          # parameters become views of the flat buffer
+                self.names.append(k)
+                self.slices[k] = (off, n, tuple(p.shape))
+                off += sz
+
+    def view(self, buf, name):
+        off, n, shape = self.slices[name]
+        return buf[off:off + n].view(shape)
+
+
+def reduce_gradients(grad, group=None):
+    """Data-parallel gradient exchange (the role of DDP's bucketed all-reduce at train_accum.py:105,230): ONE sum all-reduce
+    of the flat gradient buffer; returns the factor (1 / world size) the optimizer kernel folds into its gradient read."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1.0
+    world = dist.get_world_size(group)
+    if world > 1:
+        dist.all_reduce(grad, group=group)
+    return 1.0 / world
+
+
 class FusedTrainer:
     def __init__(self, model, *, lr=2e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.0, ema_decay=0.9999, transport=None,
                  process_group=None):
@@ -33,26 +76,14 @@ class FusedTrainer:
         self.world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(process_group)
-        named = [(k, p) for k, p in model.named_parameters() if p.requires_grad]
-        dev = named[0][1].device
-        if dev.type != "cuda":
+        if next(model.parameters()).device.type != "cuda":
             raise _lib.LdmaeError("FusedTrainer needs the model on a CUDA (B200) device")
-        sizes = [(p.numel() + 3) // 4 * 4 for _, p in named]          # 16-byte aligned slices
-        total = sum(sizes)
-        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
-        self.grad = torch.zeros(total, device=dev, dtype=torch.float32)
-        self.exp_avg = torch.zeros(total, device=dev, dtype=torch.float32)
-        self.exp_avg_sq = torch.zeros(total, device=dev, dtype=torch.float32)
-        self.names, self.slices = [], {}
-        off = 0
-        with torch.no_grad():
-            for (k, p), sz in zip(named, sizes):
-                n = p.numel()
-                self.flat[off:off + n].copy_(p.detach().reshape(-1))
-                p.data = self.flat[off:off + n].view(p.shape)          # parameters become views of the flat buffer
-                self.names.append(k)
-                self.slices[k] = (off, n, tuple(p.shape))
-                off += sz
+        self.layout = FlatLayout(model)
+        self.flat, self.grad = self.layout.flat, self.layout.grad
+        self.names, self.slices = self.layout.names, self.layout.slices
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        dev = self.layout.device
         self.ema = self.flat.clone()                                   # train_accum.py:92 (deepcopy of the fresh model)
         self.step_count = 0
         self.device = dev
@@ -99,14 +130,13 @@ class FusedTrainer:
 
     def optimizer_step(self):
         """all-reduce (mean) + AdamW + EMA on the flat buffers; marks the library's bf16 weight copies stale."""
-        if self.world > 1:
-            torch.distributed.all_reduce(self.grad, group=self.pg)
+        grad_scale = reduce_gradients(self.grad, self.pg)
         self.step_count += 1
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().ldmae_adamw_ema_step(
                 _lib.ptr(self.flat), _lib.ptr(self.grad), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), _lib.ptr(self.ema),
                 self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count,
-                self.ema_decay, 1.0 / self.world, _lib.stream_ptr()), "adamw_ema_step")
+                self.ema_decay, grad_scale, _lib.stream_ptr()), "adamw_ema_step")
         self.model._handle_sig = None                                  # parameters changed behind torch's version counters
 
     def step(self, x1, y, t=None, x0=None):

@@ -126,3 +126,76 @@ def test_two_rank_sharding_over_gloo():
     assert t0 == t1 == 11.0                          # MAX over ranks
     assert s0 != s1 and y0 != y1                     # different shards
     assert g0 == g1 and abs(g0[0] - s0) < 1e-4 and abs(g0[1] - s1) < 1e-4
+
+
+# ----------------------------------------------------------------------------- training host logic (CPU)
+def test_flat_layout_makes_parameters_views_of_one_buffer():
+    from ldmae_b200.models.lightningdit import LightningDiT
+    from ldmae_b200.training import FlatLayout
+    m = LightningDiT(input_size=8, patch_size=1, in_channels=16, hidden_size=128, depth=2, num_heads=2, num_classes=10,
+                     use_qknorm=True, use_swiglu=True, use_rope=True, use_rmsnorm=True)
+    before = {k: p.detach().clone() for k, p in m.named_parameters()}
+    lay = FlatLayout(m)
+    assert "pos_embed" not in lay.slices                       # frozen (requires_grad False, lightningdit.py:314)
+    assert lay.names == [k for k, p in m.named_parameters() if p.requires_grad]
+    end = 0
+    for k in lay.names:
+        off, n, shape = lay.slices[k]
+        assert off % 4 == 0 and off >= end                     # 16-byte aligned, non-overlapping, in order
+        end = off + n
+        p = dict(m.named_parameters())[k]
+        assert p.data_ptr() == lay.flat.data_ptr() + 4 * off   # the parameter IS the slice
+        assert torch.equal(p.detach(), before[k]) and tuple(p.shape) == shape
+    lay.flat.mul_(2.0)                                         # an update of the flat buffer is an update of the model
+    k = "blocks.1.mlp.w12.weight"
+    assert torch.equal(dict(m.named_parameters())[k].detach(), 2 * before[k])
+    assert lay.view(lay.grad, k).shape == before[k].shape
+
+
+def _grad_reduce_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from ldmae_b200.training import reduce_gradients
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(rank)
+    grad = torch.randn(1003, generator=g)
+    mine = grad.clone()
+    scale = reduce_gradients(grad)            # ONE all-reduce (sum) of the flat buffer; the kernel folds in 1/world
+    q.put((rank, scale, mine.tolist(), (grad * scale).tolist()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_reduction_over_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_reduce_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs: p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs: p.join(60)
+    assert all(p.exitcode == 0 for p in procs)
+    (_, s0, m0, a0), (_, s1, m1, a1) = res
+    assert s0 == s1 == 0.5
+    mean = ((torch.tensor(m0) + torch.tensor(m1)) / 2)
+    torch.testing.assert_close(torch.tensor(a0), mean, rtol=1e-6, atol=1e-6)
+    assert a0 == a1                                            # every replica applies the same averaged gradient
+
+
+def test_reduce_gradients_single_process_is_identity():
+    from ldmae_b200.training import reduce_gradients
+    g = torch.arange(8, dtype=torch.float32)
+    assert reduce_gradients(g) == 1.0 and torch.equal(g, torch.arange(8, dtype=torch.float32))
+
+
+def test_training_forward_has_no_cpu_path():
+    """Grad-enabled forward on CPU tensors must raise (no eager fallback), like the inference path."""
+    from ldmae_b200 import _lib
+    from ldmae_b200.models.lightningdit import LightningDiT
+    m = LightningDiT(input_size=8, patch_size=1, in_channels=16, hidden_size=128, depth=2, num_heads=2, num_classes=10,
+                     use_qknorm=True, use_swiglu=True, use_rope=True, use_rmsnorm=True).train()
+    with torch.enable_grad(), pytest.raises(_lib.LdmaeError):
+        m(torch.randn(2, 16, 8, 8), torch.rand(2), torch.zeros(2, dtype=torch.long))
+    from ldmae_b200.training import FusedTrainer
+    with pytest.raises(_lib.LdmaeError):
+        FusedTrainer(m)
