@@ -251,7 +251,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
         const float2 x0 = fma2(make_float2(sv[c], sv[c + 1]), sl2, nl0);
         const float2 x1 = fma2(make_float2(sv[c + 2], sv[c + 3]), sl2, nl1);
         float2 p0 = make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
-        float2 p1 = make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
+        // a quarter of the exponentials takes the FMA-pipe polynomial: the MUFU unit (16 / clk / SM) is the row warps' limit
+        float2 p1 = ((c & 4) != 0) ? ex2_poly2(x1) : make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
         float2 e0 = fma2(make_float2(dp[c], dp[c + 1]), sc2, dl0);      // scale * dP - scale * delta
         float2 e1 = fma2(make_float2(dp[c + 2], dp[c + 3]), sc2, dl1);
         if (cvalid < 16) {                              // ragged tail of the sample: P = dS = 0 beyond it
