@@ -121,6 +121,8 @@ typedef struct ldmae_vmae_config {
   int32_t mlp_hidden;                                  /* 4 * decoder_embed_dim */
   float ln_eps;                                        /* 1e-6 (models_mae.py:996) */
   int32_t max_batch;
+  /* encoder side (0 = decoder only): ViT depth / heads at width embed_dim, outputs of to_latent (2*latent_dim with KL) */
+  int32_t depth, num_heads, to_latent_dim;
 } ldmae_vmae_config;
 
 typedef struct ldmae_vmae ldmae_vmae;
@@ -135,6 +137,11 @@ int ldmae_vmae_finalize(ldmae_vmae* h, void* stream);
  *   img_f32 [B,3,H,W] fp32 (decode(...)[0]) and/or img_u8 [B,H,W,3] uint8 (decode_to_images). */
 int ldmae_vmae_decode(ldmae_vmae* h, const float* z, const float* mean, const float* stdv, float multiplier,
                       float* img_f32, uint8_t* img_u8, int32_t B, void* stream);
+
+/* MaskedAutoencoderViT._encode (tokenizer/models_mae.py:819-836; called by extract_features.py:150-152 and by encode):
+ * img [B,3,H,W] fp32 -> moments [B, to_latent_dim, H/p, W/p] fp32 (mean || logvar of the KL posterior).  Needs the encoder
+ * keys (patch_embed.*, pos_embed, blocks.*, norm.*, to_latent.*) loaded through ldmae_vmae_load_tensor. */
+int ldmae_vmae_encode(ldmae_vmae* h, const float* img, float* moments, int32_t B, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Building blocks, exported for the parity tests and micro-benchmarks (device pointers).

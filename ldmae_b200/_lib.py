@@ -25,7 +25,7 @@ class VmaeConfig(C.Structure):
     _fields_ = [("img_size", C.c_int32), ("patch_size", C.c_int32), ("latent_dim", C.c_int32),
                 ("embed_dim", C.c_int32), ("decoder_embed_dim", C.c_int32), ("decoder_depth", C.c_int32),
                 ("decoder_num_heads", C.c_int32), ("mlp_hidden", C.c_int32), ("ln_eps", C.c_float),
-                ("max_batch", C.c_int32)]
+                ("max_batch", C.c_int32), ("depth", C.c_int32), ("num_heads", C.c_int32), ("to_latent_dim", C.c_int32)]
 
 
 # name -> (restype, argtypes): every symbol include/ldmae_b200.h declares
@@ -53,6 +53,7 @@ SYMBOLS = {
     "ldmae_vmae_load_tensor": (C.c_int, [vp, C.c_char_p, vp, i64, vp]),
     "ldmae_vmae_finalize": (C.c_int, [vp, vp]),
     "ldmae_vmae_decode": (C.c_int, [vp, vp, vp, vp, f32, vp, vp, i32, vp]),
+    "ldmae_vmae_encode": (C.c_int, [vp, vp, vp, i32, vp]),
     "ldmae_gemm_bias": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
     "ldmae_gemm_residual": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "ldmae_attention": (C.c_int, [vp, vp, i32, i32, i32, f32, vp]),

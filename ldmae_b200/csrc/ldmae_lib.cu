@@ -891,6 +891,12 @@ struct ldmae_vmae {
   std::vector<VmaeBlockW> blk;
   std::vector<std::string> loaded;
   bool finalized = false;
+  // encoder (tokenizer/models_mae.py:819-836): patch embed, pos embed, ViT blocks, norm, to_latent
+  int HPe = 0, NL = 0;                       // padded heads width of the encoder, to_latent outputs (2 * latent with KL)
+  DevBuf<__nv_bfloat16> w_patch, w_tolat, etok;
+  DevBuf<float> b_patch, epos, enw, enb, b_tolat;
+  std::vector<VmaeBlockW> eblk;
+  std::vector<std::string> enc_loaded;
   DevBuf<float> x, pred;
   DevBuf<__nv_bfloat16> tok, t1, a, qkv, o, hid;
 };
@@ -902,9 +908,10 @@ static int vmae_alloc_ws(ldmae_vmae* h, int B) {
   LDMAE_TRY(h->tok.alloc(M * 64));
   LDMAE_TRY(h->t1.alloc(M * h->c.embed_dim));
   LDMAE_TRY(h->a.alloc(M * h->D));
-  LDMAE_TRY(h->qkv.alloc(M * 3 * h->HP));
-  LDMAE_TRY(h->o.alloc(M * h->HP));
+  LDMAE_TRY(h->qkv.alloc(M * 3 * std::max(h->HP, h->HPe)));
+  LDMAE_TRY(h->o.alloc(M * std::max(h->HP, h->HPe)));
   LDMAE_TRY(h->hid.alloc(M * h->Hm));
+  if (h->HPe > 0) LDMAE_TRY(h->etok.alloc(M * h->PP));
   h->maxB = B;
   return LDMAE_OK;
 }
@@ -929,6 +936,27 @@ extern "C" int ldmae_vmae_create(const ldmae_vmae_config* cfg, ldmae_vmae** out)
   const int D = h->D;
   int r = LDMAE_OK;
   auto A = [&](int rc) { if (r == LDMAE_OK) r = rc; };
+  if (c.depth > 0) {
+    // encoder side; it shares the decoder's workspace, so the widths must agree (they do in every shipped factory)
+    LDMAE_REQUIRE(c.embed_dim == D && c.num_heads > 0 && c.embed_dim % c.num_heads == 0 && c.embed_dim / c.num_heads <= 64,
+                  "VMAE encoder: embed_dim %d must equal decoder_embed_dim %d with head_dim <= 64", c.embed_dim, D);
+    LDMAE_REQUIRE(h->PP % 8 == 0, "VMAE encoder: patch_size^2 * 3 must be a multiple of 8");
+    h->HPe = c.num_heads * 64;
+    h->NL = c.to_latent_dim;
+    LDMAE_REQUIRE(h->NL > 0 && h->NL % 4 == 0 && h->NL <= h->PP, "VMAE encoder: bad to_latent width %d", h->NL);
+    A(h->w_patch.alloc(static_cast<size_t>(D) * h->PP)); A(h->b_patch.alloc(D));
+    A(h->epos.alloc(static_cast<size_t>(h->L) * D));
+    A(h->enw.alloc(D)); A(h->enb.alloc(D));
+    A(h->w_tolat.alloc(static_cast<size_t>(h->NL) * D)); A(h->b_tolat.alloc(h->NL));
+    h->eblk.resize(c.depth);
+    for (auto& b : h->eblk) {
+      A(b.w_qkv.alloc(static_cast<size_t>(3 * h->HPe) * D)); A(b.b_qkv.alloc(3 * h->HPe, true));
+      A(b.w_proj.alloc(static_cast<size_t>(D) * h->HPe)); A(b.b_proj.alloc(D));
+      A(b.w_fc1.alloc(static_cast<size_t>(h->Hm) * D)); A(b.b_fc1.alloc(h->Hm));
+      A(b.w_fc2.alloc(static_cast<size_t>(D) * h->Hm)); A(b.b_fc2.alloc(D));
+      A(b.n1w.alloc(D)); A(b.n1b.alloc(D)); A(b.n2w.alloc(D)); A(b.n2b.alloc(D));
+    }
+  }
   A(h->w_from.alloc(static_cast<size_t>(c.embed_dim) * 64)); A(h->b_from.alloc(c.embed_dim));
   A(h->w_embed.alloc(static_cast<size_t>(D) * c.embed_dim)); A(h->b_embed.alloc(D));
   A(h->pos.alloc(static_cast<size_t>(h->L) * D));
@@ -957,15 +985,36 @@ extern "C" int ldmae_vmae_load_tensor(ldmae_vmae* h, const char* name, const flo
   const int D = h->D, E = h->c.embed_dim, nh = h->c.decoder_num_heads, hd = D / nh;
   int rc = LDMAE_OK;
   int bi = -1;
+  bool enc = false;
   std::string sub;
+  int nhb = nh, HPb = h->HP;                 // head geometry of the block being loaded
   if (k.rfind("decoder_blocks.", 0) == 0) {
     const size_t dot = k.find('.', 15);
     LDMAE_REQUIRE(dot != std::string::npos, "bad key %s", name);
     bi = atoi(k.substr(15, dot - 15).c_str());
     sub = k.substr(dot + 1);
     LDMAE_REQUIRE(bi >= 0 && bi < h->c.decoder_depth, "block index out of range in %s", name);
+  } else if (k.rfind("blocks.", 0) == 0) {
+    LDMAE_REQUIRE(h->HPe > 0, "VMAE handle was created without an encoder (key %s)", name);
+    const size_t dot = k.find('.', 7);
+    LDMAE_REQUIRE(dot != std::string::npos, "bad key %s", name);
+    bi = atoi(k.substr(7, dot - 7).c_str());
+    sub = k.substr(dot + 1);
+    LDMAE_REQUIRE(bi >= 0 && bi < h->c.depth, "block index out of range in %s", name);
+    enc = true; nhb = h->c.num_heads; HPb = h->HPe;
   }
-  if (k == "from_latent.weight") rc = pack_bf16(h->w_from.p, data, E, h->c.latent_dim, 64, numel, name, st);
+  const int hdb = D / nhb;
+  const bool enc_key = enc || k == "patch_embed.proj.weight" || k == "patch_embed.proj.bias" || k == "pos_embed" ||
+                       k == "norm.weight" || k == "norm.bias" || k == "to_latent.weight" || k == "to_latent.bias";
+  if (enc_key && !enc) LDMAE_REQUIRE(h->HPe > 0, "VMAE handle was created without an encoder (key %s)", name);
+  if (k == "patch_embed.proj.weight") rc = pack_bf16(h->w_patch.p, data, D, h->PP, h->PP, numel, name, st);
+  else if (k == "patch_embed.proj.bias") rc = copy_f32(h->b_patch.p, data, numel, D, name, st);
+  else if (k == "pos_embed") rc = copy_f32(h->epos.p, data, numel, (int64_t)h->L * D, name, st);
+  else if (k == "norm.weight") rc = copy_f32(h->enw.p, data, numel, D, name, st);
+  else if (k == "norm.bias") rc = copy_f32(h->enb.p, data, numel, D, name, st);
+  else if (k == "to_latent.weight") rc = pack_bf16(h->w_tolat.p, data, h->NL, D, D, numel, name, st);
+  else if (k == "to_latent.bias") rc = copy_f32(h->b_tolat.p, data, numel, h->NL, name, st);
+  else if (k == "from_latent.weight") rc = pack_bf16(h->w_from.p, data, E, h->c.latent_dim, 64, numel, name, st);
   else if (k == "from_latent.bias") rc = copy_f32(h->b_from.p, data, numel, E, name, st);
   else if (k == "decoder_embed.weight") rc = pack_bf16(h->w_embed.p, data, D, E, E, numel, name, st);
   else if (k == "decoder_embed.bias") rc = copy_f32(h->b_embed.p, data, numel, D, name, st);
@@ -977,24 +1026,24 @@ extern "C" int ldmae_vmae_load_tensor(ldmae_vmae* h, const char* name, const flo
   else if (k == "decoder_pred.conv_smoother.weight") rc = copy_f32(h->conv_w.p, data, numel, 81, name, st);
   else if (k == "decoder_pred.conv_smoother.bias") rc = copy_f32(h->conv_b.p, data, numel, 3, name, st);
   else if (bi >= 0) {
-    VmaeBlockW& b = h->blk[bi];
+    VmaeBlockW& b = enc ? h->eblk[bi] : h->blk[bi];
     if (sub == "norm1.weight") rc = copy_f32(b.n1w.p, data, numel, D, name, st);
     else if (sub == "norm1.bias") rc = copy_f32(b.n1b.p, data, numel, D, name, st);
     else if (sub == "norm2.weight") rc = copy_f32(b.n2w.p, data, numel, D, name, st);
     else if (sub == "norm2.bias") rc = copy_f32(b.n2b.p, data, numel, D, name, st);
     else if (sub == "attn.qkv.weight") {
       LDMAE_REQUIRE(numel == (int64_t)3 * D * D, "%s: bad size", name);
-      pad_heads_rows_kernel<<<3 * h->HP, 128, 0, st>>>(b.w_qkv.p, nullptr, data, nullptr, nh, hd, D);
+      pad_heads_rows_kernel<<<3 * HPb, 128, 0, st>>>(b.w_qkv.p, nullptr, data, nullptr, nhb, hdb, D);
       LDMAE_LAUNCH_CHECK();
     } else if (sub == "attn.qkv.bias") {
       LDMAE_REQUIRE(numel == 3 * D, "%s: bad size", name);
       // scatter bias into the padded layout with a strided 2-D copy: [3*nh, hd] -> [3*nh, 64]
-      LDMAE_CUDA(cudaMemsetAsync(b.b_qkv.p, 0, 3 * h->HP * sizeof(float), st));
-      LDMAE_CUDA(cudaMemcpy2DAsync(b.b_qkv.p, 64 * sizeof(float), data, hd * sizeof(float), hd * sizeof(float), 3 * nh,
+      LDMAE_CUDA(cudaMemsetAsync(b.b_qkv.p, 0, 3 * HPb * sizeof(float), st));
+      LDMAE_CUDA(cudaMemcpy2DAsync(b.b_qkv.p, 64 * sizeof(float), data, hdb * sizeof(float), hdb * sizeof(float), 3 * nhb,
                                    cudaMemcpyDeviceToDevice, st));
     } else if (sub == "attn.proj.weight") {
       LDMAE_REQUIRE(numel == (int64_t)D * D, "%s: bad size", name);
-      pad_heads_cols_kernel<<<D, 256, 0, st>>>(b.w_proj.p, data, nh, hd);
+      pad_heads_cols_kernel<<<D, 256, 0, st>>>(b.w_proj.p, data, nhb, hdb);
       LDMAE_LAUNCH_CHECK();
     } else if (sub == "attn.proj.bias") rc = copy_f32(b.b_proj.p, data, numel, D, name, st);
     else if (sub == "mlp.fc1.weight") rc = pack_bf16(b.w_fc1.p, data, h->Hm, D, D, numel, name, st);
@@ -1005,7 +1054,8 @@ extern "C" int ldmae_vmae_load_tensor(ldmae_vmae* h, const char* name, const flo
   } else {
     return set_error(LDMAE_ERR_INVALID, "unknown VMAE decoder key %s", name);
   }
-  if (rc == LDMAE_OK && std::find(h->loaded.begin(), h->loaded.end(), k) == h->loaded.end()) h->loaded.push_back(k);
+  std::vector<std::string>& lst = enc_key ? h->enc_loaded : h->loaded;
+  if (rc == LDMAE_OK && std::find(lst.begin(), lst.end(), k) == lst.end()) lst.push_back(k);
   return rc;
 }
 
@@ -1016,6 +1066,65 @@ extern "C" int ldmae_vmae_finalize(ldmae_vmae* h, void* stream) {
   if ((int)h->loaded.size() != expect)
     return set_error(LDMAE_ERR_STATE, "VMAE decoder weights incomplete: %d of %d tensors loaded", (int)h->loaded.size(), expect);
   h->finalized = true;
+  return LDMAE_OK;
+}
+
+// One pre-norm ViT block (tokenizer/models_mae.py:176-187) on the fp32 stream h->x: LN -> qkv -> attention (heads padded
+// to 64) -> proj (+residual) -> LN -> fc1 + exact GELU -> fc2 (+residual).  Shared by the decoder and the encoder.
+static int vmae_vit_block(ldmae_vmae* h, VmaeBlockW& b, int B, int nh, int HP, cudaStream_t st) {
+  const int D = h->D, L = h->L, M = B * L;
+  const float scale = 1.0f / sqrtf(static_cast<float>(D / nh));
+  const unsigned ln_grid = cdiv(M, 8);
+  auto resid = [&](const void* a, int lda, const void* w, int ldw, int K, const float* bias) {
+    return gemm_residual(a, lda, w, ldw, GemmShape{M, D, K}, h->x.p, D, bias, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, L, st);
+  };
+  layernorm_bf16_kernel<<<ln_grid, 256, 0, st>>>(h->a.p, h->x.p, b.n1w.p, b.n1b.p, M, D, h->c.ln_eps);
+  LDMAE_LAUNCH_CHECK();
+  LDMAE_TRY((gemm_store<__nv_bfloat16, 0>(h->a.p, D, b.w_qkv.p, D, GemmShape{M, 3 * HP, D}, h->qkv.p, 3 * HP, b.b_qkv.p, st)));
+  LDMAE_TRY(run_attention(h->qkv.p, 3 * HP, h->o.p, HP, B, L, nh, 0, HP, 2 * HP, scale, st));
+  LDMAE_TRY(resid(h->o.p, HP, b.w_proj.p, HP, HP, b.b_proj.p));
+  layernorm_bf16_kernel<<<ln_grid, 256, 0, st>>>(h->a.p, h->x.p, b.n2w.p, b.n2b.p, M, D, h->c.ln_eps);
+  LDMAE_LAUNCH_CHECK();
+  LDMAE_TRY((gemm_store<__nv_bfloat16, 1>(h->a.p, D, b.w_fc1.p, D, GemmShape{M, h->Hm, D}, h->hid.p, h->Hm, b.b_fc1.p, st)));
+  LDMAE_TRY(resid(h->hid.p, h->Hm, b.w_fc2.p, h->Hm, h->Hm, b.b_fc2.p));
+  return LDMAE_OK;
+}
+
+// out[b, c, t] = in[b*L + t, c]   ('b (h w) c -> b c h w', models_mae.py:835)
+__global__ void tokens_to_nchw_kernel(float* __restrict__ out, const float* __restrict__ in, int B, int L, int C) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(B) * L * C) return;
+  const int t = i % L;
+  const int c = (i / L) % C;
+  const size_t b = i / (static_cast<size_t>(L) * C);
+  out[i] = in[(b * L + t) * C + c];
+}
+
+// MaskedAutoencoderViT._encode (tokenizer/models_mae.py:819-836): img [B,3,H,W] fp32 -> moments [B, NL, g, g] fp32
+// (NL = 2 * latent_dim with the KL bottleneck: mean || logvar, consumed by DiagonalGaussianDistribution).
+extern "C" int ldmae_vmae_encode(ldmae_vmae* h, const float* img, float* moments, int32_t B, void* stream) {
+  LDMAE_REQUIRE(h && h->HPe > 0, "VMAE handle was created without an encoder");
+  LDMAE_REQUIRE(img && moments && B >= 1, "bad argument");
+  const int expect = 7 + 12 * h->c.depth;
+  if ((int)h->enc_loaded.size() != expect)
+    return set_error(LDMAE_ERR_STATE, "VMAE encoder weights incomplete: %d of %d tensors loaded", (int)h->enc_loaded.size(), expect);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B > h->maxB) { LDMAE_CUDA(cudaStreamSynchronize(st)); LDMAE_TRY(vmae_alloc_ws(h, B)); }
+  ProfScope ps(8, st);
+  const int D = h->D, L = h->L, M = B * L;
+  // timm PatchEmbed: Conv2d(3, E, k = stride = p) == GEMM over the (c, pi, qi) patch rows
+  patchify_bf16_kernel<<<cdiv(static_cast<size_t>(M) * h->PP, 256), 256, 0, st>>>(h->etok.p, img, B, 3, h->c.img_size, h->c.patch_size);
+  LDMAE_LAUNCH_CHECK();
+  broadcast_rows_kernel<<<cdiv(static_cast<size_t>(M) * D, 256), 256, 0, st>>>(h->x.p, h->epos.p, M, L, D);
+  LDMAE_LAUNCH_CHECK();
+  LDMAE_TRY(gemm_residual(h->etok.p, h->PP, h->w_patch.p, h->PP, GemmShape{M, D, h->PP}, h->x.p, D, h->b_patch.p, nullptr, 0, nullptr, 0,
+                          nullptr, nullptr, 0, L, st));
+  for (int i = 0; i < h->c.depth; ++i) LDMAE_TRY(vmae_vit_block(h, h->eblk[i], B, h->c.num_heads, h->HPe, st));
+  layernorm_bf16_kernel<<<cdiv(M, 8), 256, 0, st>>>(h->a.p, h->x.p, h->enw.p, h->enb.p, M, D, h->c.ln_eps);
+  LDMAE_LAUNCH_CHECK();
+  LDMAE_TRY((gemm_store<float, 0>(h->a.p, D, h->w_tolat.p, D, GemmShape{M, h->NL, D}, h->pred.p, h->NL, h->b_tolat.p, st)));
+  tokens_to_nchw_kernel<<<cdiv(static_cast<size_t>(M) * h->NL, 256), 256, 0, st>>>(moments, h->pred.p, B, L, h->NL);
+  LDMAE_LAUNCH_CHECK();
   return LDMAE_OK;
 }
 
@@ -1043,18 +1152,7 @@ extern "C" int ldmae_vmae_decode(ldmae_vmae* h, const float* z, const float* mea
   };
   LDMAE_TRY(resid(h->t1.p, E, h->w_embed.p, E, E, h->b_embed.p));
   const unsigned ln_grid = cdiv(M, 8);
-  for (int i = 0; i < h->c.decoder_depth; ++i) {
-    VmaeBlockW& b = h->blk[i];
-    layernorm_bf16_kernel<<<ln_grid, 256, 0, st>>>(h->a.p, h->x.p, b.n1w.p, b.n1b.p, M, D, h->c.ln_eps);
-    LDMAE_LAUNCH_CHECK();
-    LDMAE_TRY((gemm_store<__nv_bfloat16, 0>(h->a.p, D, b.w_qkv.p, D, GemmShape{M, 3 * h->HP, D}, h->qkv.p, 3 * h->HP, b.b_qkv.p, st)));
-    LDMAE_TRY(run_attention(h->qkv.p, 3 * h->HP, h->o.p, h->HP, B, L, nh, 0, h->HP, 2 * h->HP, scale, st));
-    LDMAE_TRY(resid(h->o.p, h->HP, b.w_proj.p, h->HP, h->HP, b.b_proj.p));
-    layernorm_bf16_kernel<<<ln_grid, 256, 0, st>>>(h->a.p, h->x.p, b.n2w.p, b.n2b.p, M, D, h->c.ln_eps);
-    LDMAE_LAUNCH_CHECK();
-    LDMAE_TRY((gemm_store<__nv_bfloat16, 1>(h->a.p, D, b.w_fc1.p, D, GemmShape{M, h->Hm, D}, h->hid.p, h->Hm, b.b_fc1.p, st)));
-    LDMAE_TRY(resid(h->hid.p, h->Hm, b.w_fc2.p, h->Hm, h->Hm, b.b_fc2.p));
-  }
+  for (int i = 0; i < h->c.decoder_depth; ++i) LDMAE_TRY(vmae_vit_block(h, h->blk[i], B, nh, h->HP, st));
   layernorm_bf16_kernel<<<ln_grid, 256, 0, st>>>(h->a.p, h->x.p, h->nfw.p, h->nfb.p, M, D, h->c.ln_eps);
   LDMAE_LAUNCH_CHECK();
   LDMAE_TRY((gemm_store<float, 0>(h->a.p, D, h->w_pred.p, D, GemmShape{M, h->PP, D}, h->pred.p, h->PP, h->b_pred.p, st)));

@@ -1,10 +1,12 @@
-"""Drop-in for the decoder side of the reference's ``tokenizer/models_mae.py`` (VMAE f8d16 tokenizer).
+"""Drop-in for the reference's ``tokenizer/models_mae.py`` (VMAE f8d16 tokenizer), inference-time surface.
 
 Public surface kept: ``mae_for_ldmae_f8d16_prev(**kw)`` (reference models_mae.py:992-997),
 ``MaskedAutoencoderViT.decode(z, return_dict)`` (:865-887), ``decode_to_images(z)`` (:963-973),
-``unpatchify`` (:458-470), ``load_state_dict(ckpt['model'], strict=False)`` with the reference's key names.
-The decoder (from_latent, decoder_embed, 12 ViT blocks, decoder_norm, linear_pred + 3x3 RGB conv, uint8 pack)
-runs in libldmae_b200.so; the encoder (``encode`` / ``_encode``) is SURVEY section 8f item 1 ("next") and raises.
+``unpatchify`` (:458-470), ``_encode(x)`` (:819-836), ``encode(x, return_dict)`` (:838-863), ``encode_images`` (:952-961),
+``load_state_dict(ckpt['model'], strict=False)`` with the reference's key names.
+Decoder (from_latent, decoder_embed, 12 ViT blocks, decoder_norm, linear_pred + 3x3 RGB conv, uint8 pack) and encoder
+(patch embed, 12 ViT blocks, norm, to_latent -> posterior moments) run in libldmae_b200.so; the masked pre-training
+paths (models_mae.py:472-815) are out of scope (tokenizer training).
 """
 from __future__ import annotations
 
@@ -29,6 +31,65 @@ class Config:
 class DecoderOutput:
     sample: torch.Tensor
     commit_loss: Optional[torch.Tensor] = None
+
+
+class DiagonalGaussianDistribution:
+    """reference tokenizer/util/misc.py:74-128 (posterior over latents from the encoder's moments)."""
+
+    def __init__(self, parameters, deterministic=False):
+        self.parameters = parameters
+        self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
+        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
+        self.deterministic = deterministic
+        self.std = torch.exp(0.5 * self.logvar)
+        self.var = torch.exp(self.logvar)
+        if self.deterministic:
+            self.var = self.std = torch.zeros_like(self.mean)
+
+    def sample(self, generator=None):
+        noise = torch.randn(self.mean.shape, generator=generator, device=self.parameters.device, dtype=self.parameters.dtype)
+        return self.mean + self.std * noise
+
+    def kl(self, other=None):
+        if self.deterministic:
+            return torch.Tensor([0.0])
+        dims = list(range(1, self.mean.dim()))
+        if other is None:
+            return 0.5 * torch.sum(torch.pow(self.mean, 2) + self.var - 1.0 - self.logvar, dim=dims)
+        return 0.5 * torch.sum(torch.pow(self.mean - other.mean, 2) / other.var + self.var / other.var - 1.0 - self.logvar
+                               + other.logvar, dim=dims)
+
+    def nll(self, sample, dims=(1, 2, 3)):
+        if self.deterministic:
+            return torch.Tensor([0.0])
+        return 0.5 * torch.sum(np.log(2.0 * np.pi) + self.logvar + torch.pow(sample - self.mean, 2) / self.var, dim=list(dims))
+
+    def mode(self):
+        return self.mean
+
+
+@dataclass
+class EncoderOutput:
+    latent: torch.Tensor
+
+    def sample(self):
+        return self.latent
+
+
+@dataclass
+class MAEOutput:
+    latent_dist: object
+
+
+class _PatchEmbedParams(nn.Module):
+    """timm PatchEmbed as the reference uses it (models_mae.py:330): .proj = Conv2d(k = stride = patch)."""
+
+    def __init__(self, img_size, patch_size, in_chans, embed_dim):
+        super().__init__()
+        self.img_size, self.patch_size = (img_size, img_size), (patch_size, patch_size)
+        self.grid_size = (img_size // patch_size, img_size // patch_size)
+        self.num_patches = self.grid_size[0] * self.grid_size[1]
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size, bias=True)
 
 
 def _sincos_2d_f32(embed_dim, grid_size):
@@ -105,6 +166,13 @@ class MaskedAutoencoderViT(nn.Module):
         ln = norm_layer(decoder_embed_dim)
         self.ln_eps = float(getattr(ln, "eps", 1e-5))
         num_patches = self.latent_resolution ** 2
+        # encoder (models_mae.py:330-352): parameters under the reference's names, arithmetic in the library
+        self.depth, self.num_heads = depth, num_heads
+        self.patch_embed = _PatchEmbedParams(img_size, patch_size, in_chans, embed_dim)
+        self.pos_embed = nn.Parameter(torch.zeros(1, num_patches, embed_dim), requires_grad=False)
+        self.blocks = nn.ModuleList([_BlockParams(embed_dim, num_heads, mlp_ratio, norm_layer) for _ in range(depth)])
+        self.norm = norm_layer(embed_dim)
+        self.to_latent = nn.Linear(embed_dim, latent_dim * 2 if kl_loss_weight is not None else latent_dim)
         self.from_latent = nn.Linear(latent_dim, decoder_embed_dim)
         self.decoder_embed = nn.Linear(embed_dim, decoder_embed_dim, bias=True)
         self.decoder_pos_embed = nn.Parameter(torch.zeros(1, num_patches, decoder_embed_dim), requires_grad=False)
@@ -121,6 +189,8 @@ class MaskedAutoencoderViT(nn.Module):
         """reference models_mae.py:398-435 (decoder side)."""
         pe = _sincos_2d_f32(self.decoder_pos_embed.shape[-1], self.latent_resolution)
         self.decoder_pos_embed.data.copy_(torch.from_numpy(pe).float().unsqueeze(0))
+        pe = _sincos_2d_f32(self.pos_embed.shape[-1], self.latent_resolution)
+        self.pos_embed.data.copy_(torch.from_numpy(pe).float().unsqueeze(0))
 
         def _init(m):
             if isinstance(m, nn.Linear):
@@ -132,18 +202,8 @@ class MaskedAutoencoderViT(nn.Module):
                 nn.init.constant_(m.weight, 1.0)
 
         self.apply(_init)
-
-    def load_state_dict(self, state_dict, strict=True, assign=False):
-        """Encoder-side keys of reference checkpoints are ignored (they belong to ``encode``)."""
-        own = set(self.state_dict().keys())
-        filt = {k: v for k, v in state_dict.items() if k in own}
-        if strict:
-            extra = [k for k in state_dict if k not in own and not k.startswith(("blocks.", "patch_embed.", "pos_embed",
-                                                                                  "norm.", "to_latent.", "mask_token",
-                                                                                  "cls_token"))]
-            if extra:
-                raise RuntimeError(f"unexpected keys: {extra[:5]}")
-        return super().load_state_dict(filt, strict=strict, assign=assign)
+        w = self.patch_embed.proj.weight.data                       # models_mae.py:420-421
+        nn.init.xavier_uniform_(w.view([w.shape[0], -1]))
 
     def unpatchify(self, x):
         """reference models_mae.py:458-470 (index-only)."""
@@ -185,7 +245,8 @@ class MaskedAutoencoderViT(nn.Module):
                                   embed_dim=self.embed_dim, decoder_embed_dim=self.decoder_embed_dim,
                                   decoder_depth=self.decoder_depth, decoder_num_heads=self.decoder_num_heads,
                                   mlp_hidden=int(self.decoder_embed_dim * self.mlp_ratio), ln_eps=self.ln_eps,
-                                  max_batch=max(1, batch))
+                                  max_batch=max(1, batch), depth=self.depth, num_heads=self.num_heads,
+                                  to_latent_dim=self.to_latent.weight.shape[0])
             h = C.c_void_p()
             with torch.cuda.device(device):
                 _lib.check(L.ldmae_vmae_create(C.byref(cfg), C.byref(h)), "ldmae_vmae_create")
@@ -230,11 +291,49 @@ class MaskedAutoencoderViT(nn.Module):
             _, u8 = self._decode(z.cuda(), False, True, latent_mean, latent_std, latent_multiplier)
             return u8.cpu().numpy()
 
-    def encode(self, x, return_dict=True):
-        raise NotImplementedError("VMAE encoder (extract_features.py path) is SURVEY section 8f item 1 -- next round")
+    def _encode(self, x):
+        """reference models_mae.py:819-836: images [B,3,H,W] in [-1,1] -> moments [B, 2*latent, H/p, W/p]."""
+        x = x.detach().float().contiguous()
+        B = x.shape[0]
+        if x.shape[1:] != (3, self.img_size, self.img_size):
+            raise ValueError(f"expected images of shape [B, 3, {self.img_size}, {self.img_size}], got {tuple(x.shape)}")
+        h = self._ensure_handle(x.device, B)
+        out = torch.empty(B, self.to_latent.weight.shape[0], self.latent_resolution, self.latent_resolution, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().ldmae_vmae_encode(h, _lib.ptr(x), _lib.ptr(out), B, _lib.stream_ptr()), "ldmae_vmae_encode")
+        return out
 
-    _encode = encode
-    encode_images = encode
+    def encode(self, x, return_dict=True):
+        """reference models_mae.py:838-863."""
+        m = self._encode(x)
+        p = DiagonalGaussianDistribution(m) if self.kl_loss_weight is not None else EncoderOutput(m)
+        return MAEOutput(latent_dist=p) if return_dict else (p,)
+
+    def encode_images(self, images):
+        """reference models_mae.py:952-961."""
+        with torch.no_grad():
+            return self.encode(images.cuda(), return_dict=False)[0].sample()
+
+    def img_transform(self, p_hflip=0, img_size=None):
+        """reference models_mae.py:935-950 (torchvision pipeline: centre crop, flip, ToTensor, Normalize(0.5, 0.5))."""
+        from torchvision import transforms
+        img_size = img_size if img_size is not None else self.img_size
+        return transforms.Compose([transforms.Lambda(lambda im: center_crop_arr(im, img_size)),
+                                   transforms.RandomHorizontalFlip(p=p_hflip), transforms.ToTensor(),
+                                   transforms.Normalize(mean=[0.5, 0.5, 0.5], std=[0.5, 0.5, 0.5], inplace=True)])
+
+
+def center_crop_arr(pil_image, image_size):
+    """reference models_mae.py:85-103 (ADM centre crop)."""
+    from PIL import Image
+    while min(*pil_image.size) >= 2 * image_size:
+        pil_image = pil_image.resize(tuple(x // 2 for x in pil_image.size), resample=Image.BOX)
+    scale = image_size / min(*pil_image.size)
+    pil_image = pil_image.resize(tuple(round(x * scale) for x in pil_image.size), resample=Image.BICUBIC)
+    arr = np.array(pil_image)
+    crop_y = (arr.shape[0] - image_size) // 2
+    crop_x = (arr.shape[1] - image_size) // 2
+    return Image.fromarray(arr[crop_y: crop_y + image_size, crop_x: crop_x + image_size])
 
 
 def mae_for_ldmae_f8d16_prev(**kwargs):

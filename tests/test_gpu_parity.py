@@ -144,6 +144,34 @@ def test_vmae_decode_vs_reference_golden(golden_dir, tag, img):
     assert (np.abs(u8a.astype(np.int32) - u8b.astype(np.int32)) <= 1).mean() > 0.999
 
 
+@pytest.mark.parametrize("tag,img", [("small", 32), ("full", 256)])
+def test_vmae_encode_vs_reference_golden(golden_dir, tag, img):
+    """_encode / encode (tokenizer/models_mae.py:819-863, the extract_features.py path) against the reference's moments."""
+    from ldmae_b200.tokenizer import models_mae
+    from gpu_util import load_npz
+    g = load_npz(golden_dir, f"vmae_{tag}.npz")
+    spec = O.VMAESpec(img_size=img)
+    vae = models_mae.mae_for_ldmae_f8d16_prev(ldmae_mode=True, no_cls=True, kl_loss_weight=True, smooth_output=True, img_size=img)
+    vae.load_state_dict(O.synth_vmae_state(spec, int(g["seed"]), encoder=True), strict=True)
+    vae = vae.cuda().eval()
+    pix = torch.from_numpy(g["pix"]).cuda()
+    mom = vae._encode(pix)
+    assert mom.shape == g["moments"].shape
+    err = _rel(mom, g["moments"])
+    print(f"vmae encode {tag}: moments rel err {err:.3e}")
+    assert err < FINAL_TOL
+    post = vae.encode(pix).latent_dist
+    assert torch.equal(post.mode(), mom[:, :16])
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    s1 = post.sample(generator=gen)
+    gen.manual_seed(3)
+    s2 = vae.encode(pix, return_dict=False)[0].sample(generator=gen)
+    assert torch.equal(s1, s2) and s1.shape == (pix.shape[0], 16, img // 8, img // 8)
+    # encode -> decode round trip runs through both halves of the tokenizer
+    rec = vae.decode(post.mode(), return_dict=False)[0]
+    assert rec.shape == pix.shape and torch.isfinite(rec).all()
+
+
 def test_cond_only_shortcut_is_bit_identical_for_the_kept_half(golden_dir):
     """Below the guidance interval only the conditional half is evaluated; the kept half must not change at all."""
     from ldmae_b200.transport import Sampler, create_transport

@@ -45,8 +45,9 @@ def test_state_dict_keys_match_reference(golden_dir):
     assert list(m.state_dict().keys()) == want
     vae = models_mae.mae_for_ldmae_f8d16_prev(ldmae_mode=True, no_cls=True, kl_loss_weight=True, smooth_output=True, img_size=256)
     ref_keys = [l.split()[0] for l in open(os.path.join(golden_dir, "vmae_keys.txt")) if l.strip()]
-    dec = [k for k in ref_keys if k.startswith(("from_latent", "decoder_"))]
-    assert sorted(vae.state_dict().keys()) == sorted(dec)
+    assert sorted(vae.state_dict().keys()) == sorted(ref_keys)          # encoder and decoder halves, strict-loadable
+    shapes = {l.split()[0]: eval(" ".join(l.split()[1:])) for l in open(os.path.join(golden_dir, "vmae_keys.txt")) if l.strip()}
+    assert {k: list(v.shape) for k, v in vae.state_dict().items()} == shapes
 
 
 def test_time_grid_matches_oracle_and_counts():
