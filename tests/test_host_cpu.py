@@ -200,3 +200,34 @@ def test_training_forward_has_no_cpu_path():
     from ldmae_b200.training import FusedTrainer
     with pytest.raises(_lib.LdmaeError):
         FusedTrainer(m)
+
+
+def test_img_latent_dataset_reads_the_extract_features_shard_format(tmp_path):
+    """Shards as extract_features.py:168-181 writes them (moments of the image and of its flip + labels), read back through
+    the ImgLatentDataset mirror with posterior sampling and per-channel normalisation (datasets/img_latent_dataset.py:76-94)."""
+    from ldmae_b200.datasets import ImgLatentDataset, write_latent_shard
+    g = torch.Generator().manual_seed(0)
+    n0, n1 = 5, 3
+    mom = [torch.randn(n, 32, 4, 4, generator=g) * 0.5 for n in (n0, n1)]
+    flip = [m.flip(-1) for m in mom]
+    lab = [torch.randint(0, 1000, (n,), generator=g) for n in (n0, n1)]
+    for s in range(2):
+        write_latent_shard(str(tmp_path), 0, s, mom[s], flip[s], lab[s])
+    ds = ImgLatentDataset(str(tmp_path), latent_norm=False, latent_multiplier=1.0, sample=False)
+    assert len(ds) == n0 + n1
+    np.random.seed(1)
+    x, y = ds[6]                                     # second shard, row 1
+    assert x.shape == (32, 4, 4) and int(y) == int(lab[1][1])
+    assert torch.equal(x, mom[1][1]) or torch.equal(x, flip[1][1])
+    # training mode: posterior sample (16 channels), cached statistics, normalisation, multiplier
+    np.random.seed(2); torch.manual_seed(2)
+    ds2 = ImgLatentDataset(str(tmp_path), latent_norm=True, latent_multiplier=2.0, sample=True)
+    assert os.path.exists(os.path.join(str(tmp_path), "latents_stats.pt"))
+    assert ds2._latent_mean.shape == (1, 16, 1, 1) and ds2._latent_std.shape == (1, 16, 1, 1)
+    x2, y2 = ds2[0]
+    assert x2.shape == (16, 4, 4) and int(y2) == int(lab[0][0]) and torch.isfinite(x2).all()
+    # deterministic part of the arithmetic: with sample=False the item is (moments - mean) / std * multiplier
+    ds3 = ImgLatentDataset(str(tmp_path), latent_norm=False, latent_multiplier=3.0, sample=False)
+    np.random.seed(5)
+    x3, _ = ds3[2]
+    assert torch.allclose(x3, 3.0 * mom[0][2]) or torch.allclose(x3, 3.0 * flip[0][2])
