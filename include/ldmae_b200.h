@@ -163,6 +163,11 @@ int ldmae_attention(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t T, 
  * log2(sum_j exp(s_ij * scale)), the row statistic the backward needs. */
 int ldmae_attention_lse(const void* qkv_bf16, void* out_bf16, float* lse2, int32_t B, int32_t T, int32_t H, float scale,
                         void* stream);
+/* The same attention when the scores are known to be bounded, |q.k * scale| * log2(e) <= m0_log2 (qk-normed heads:
+ * 8 * log2(e) * max|q_norm.w| * max|k_norm.w|): the bound replaces the running row maximum (no max pass, no rescale).
+ * lse2 may be NULL. */
+int ldmae_attention_bounded(const void* qkv_bf16, void* out_bf16, float* lse2, int32_t B, int32_t T, int32_t H, float scale,
+                            float m0_log2, void* stream);
 /* Gradient of ldmae_attention (the backward of F.scaled_dot_product_attention at models/lightningdit.py:77):
  * dqkv [B*T, 3*H*64] bf16 (dq | dk | dv, same layout as qkv) from dout [B*T, H*64] bf16, the forward's out and lse2;
  * delta_ws: workspace of 2 * (B*H*T + 64) floats.  T must be a multiple of 4. */

@@ -52,9 +52,20 @@ struct AttnParams {
   int T, H, ldo;
   int q_col, k_col, v_col;  // column offsets of the q / k / v sections inside a QKV row
   float scale_log2;         // softmax scale * log2(e)
+  float m0_log2;            // kFixedMax: upper bound of |score * scale_log2| used as the constant softmax offset
+  int alternate;            // 1: the two query tiles take turns on the exponentials (explicit ping-pong), 0: free running
 };
 
-__global__ void __launch_bounds__(kAttnThreads, 1)
+// kFixedMax: q and k are RMS-normed per head (reference models/lightningdit.py:70), so |q||k| * scale is bounded by a
+// constant known at weight-load time (8 * max|q_norm.w| * max|k_norm.w| for head_dim 64).  Softmax is shift invariant, so
+// that bound replaces the running row maximum: no max pass over the scores, no rescaling of O, ever; exponents lie in
+// [-2*m0, 0], far inside the fp32 / bf16 range for the m0 <= 48 the host admits.  Rows without such a bound (no qk-norm,
+// VMAE) use the tracking instantiation.
+// kWide (requires kFixedMax): without a row maximum the softmax of a row has no cross-thread dependency, so SIXTEEN softmax
+// warps share the work -- two threads per query row, 64 of the 128 scores of a block each -- and keep the MUFU unit fed
+// (four warps per SM sub-partition instead of two); the two partial row sums meet once, in the epilogue.
+template <bool kFixedMax, bool kWide = false>
+__global__ void __launch_bounds__(kWide ? 640 : kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -71,7 +82,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   uint64_t* s_free = s_full + 2;                   // [2]  S_t copied to registers (softmax -> MMA)
   uint64_t* p_full = s_free + 2;                   // [2]  P_t stored in TMEM (softmax -> MMA)
   uint64_t* o_done = p_full + 2;                   // [2]  O_t += P_t V_j finished: P_t free, O_t consistent (MMA -> softmax)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* turn = o_done + 2;                     // [2]  tile t finished the exponentials of a block (softmax t -> softmax 1-t)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(turn + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -90,7 +102,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
     }
     for (int t = 0; t < 2; ++t) {
-      mbar_init(&s_full[t], 1); mbar_init(&s_free[t], 4); mbar_init(&p_full[t], 4); mbar_init(&o_done[t], 1);
+      mbar_init(&s_full[t], 1); mbar_init(&s_free[t], kWide ? 8 : 4); mbar_init(&p_full[t], kWide ? 8 : 4); mbar_init(&o_done[t], 1);
+      mbar_init(&turn[t], kWide ? 8 : 4);
     }
     fence_mbar_init();
   }
@@ -102,8 +115,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
 
   // the eight softmax warps hold a 128-wide score row per thread: they take the registers the control warps do not need
   // (setmaxnreg sits inside each role's branch so that the register allocator budgets the two regions separately)
+  static_assert(!kWide || kFixedMax, "the two-threads-per-row layout needs the constant softmax offset");
   if (warp < 4) {
-  setmaxnreg_dec<80>();
+  if constexpr (!kWide) setmaxnreg_dec<80>();   // (640 threads leave no register pool worth redistributing)
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(q_full, 2 * kAttnTileBytes);
@@ -187,6 +201,94 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       stage = nstage; phase = nphase;
     }
   }
+  } else if constexpr (kWide) {
+    // ===================== softmax, two threads per query row (constant offset) =====================
+    const int g = (warp - 4) >> 2;
+    const int t = g & 1;                                 // tile 0 / 1
+    const int ch = g >> 1;                               // which 64 of the block's 128 keys this thread exponentiates
+    const int wq = warp & 3;
+    const uint32_t lane_addr = static_cast<uint32_t>(wq * 32) << 16;
+    const uint32_t tS = tmem_base + lane_addr + t * 128 + ch * 64;
+    const uint32_t tP = tmem_base + lane_addr + 256 + t * 64 + ch * 32;
+    const uint32_t tO = tmem_base + lane_addr + 384 + t * 64 + ch * 32;
+    const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+    const float2 neg2 = make_float2(-p.m0_log2, -p.m0_log2);
+    float l_run = 0.f;
+#pragma unroll 1
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(&s_full[t], j & 1, 30 + t);
+      __syncwarp();
+      tc_fence_after();
+      float s[64];
+      tmem_ld32(tS, s);
+      tmem_ld32(tS + 32, s + 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[t]);            // the tensor core may overwrite S_t with block j+1
+      const int kvalid = p.T - j * 128 - ch * 64;        // keys of this thread's half that exist
+      if (kvalid < 64) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i >= kvalid) s[i] = -INFINITY;
+      }
+      const uint32_t p_free = (j > 0) ? mbar_probe(&o_done[t], (j - 1) & 1) : 1u;
+      if (p.alternate) {                                 // the two tiles take turns on the MUFU unit (see the 8-warp path)
+        if (t == 1) mbar_wait(&turn[0], j & 1, 38);
+        else if (j > 0) mbar_wait(&turn[1], (j - 1) & 1, 39);
+      }
+      float2 ls0 = make_float2(0.f, 0.f), ls1 = make_float2(0.f, 0.f);
+      uint32_t w[32];
+#pragma unroll
+      for (int i = 0; i < 64; i += 4) {
+        const float2 x0 = fma2(make_float2(s[i], s[i + 1]), sc2, neg2);
+        const float2 x1 = fma2(make_float2(s[i + 2], s[i + 3]), sc2, neg2);
+        const float2 p0 = make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
+        const float2 p1 = ((i / 4) % kAttnPolyEvery == kAttnPolyEvery - 1) ? ex2_poly2(x1) : make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
+        ls0 = add2(ls0, p0);
+        ls1 = add2(ls1, p1);
+        w[i >> 1] = pack_bf16x2(p0.x, p0.y);
+        w[(i >> 1) + 1] = pack_bf16x2(p1.x, p1.y);
+      }
+      l_run += (ls0.x + ls0.y) + (ls1.x + ls1.y);
+      if (p.alternate) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&turn[t]);
+      }
+      if (!p_free) mbar_wait(&o_done[t], (j - 1) & 1, 36 + t);
+      __syncwarp();
+      tc_fence_after();
+      tmem_st32(tP, w);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t]);
+    }
+    // epilogue: the two halves of a row exchange their partial sums through shared memory (the K ring is idle by now),
+    // then each thread normalises and stores 32 of the 64 output columns of its row
+    float* l_x = reinterpret_cast<float*>(sK) + (t * 2) * 128;          // [2 tiles][2 halves][128 rows]
+    const int r = wq * 32 + lane;
+    mbar_wait(&o_done[t], (nkv - 1) & 1, 34 + t);                       // every K / V tile has been consumed
+    __syncwarp();
+    tc_fence_after();
+    l_x[ch * 128 + r] = l_run;
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + t), "r"(256) : "memory");  // the 8 warps of this tile
+    const float l_tot = l_x[r] + l_x[128 + r];
+    const float inv_l = 1.f / l_tot;
+    const int q_tok = qpair * 256 + t * 128 + r;
+    if (ch == 0 && p.lse2 != nullptr && q_tok < p.T)
+      p.lse2[(static_cast<size_t>(b) * p.H + head) * p.T + q_tok] = p.m0_log2 + log2f(l_tot);
+    float o[32];
+    tmem_ld32(tO, o);
+    tmem_ld_wait();
+    if (q_tok < p.T) {
+      __nv_bfloat16* dst = p.out + static_cast<size_t>(row_base + q_tok) * p.ldo + head * 64 + ch * 32;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(dst + q * 8) =
+            make_uint4(pack_bf16x2(o[8 * q] * inv_l, o[8 * q + 1] * inv_l), pack_bf16x2(o[8 * q + 2] * inv_l, o[8 * q + 3] * inv_l),
+                       pack_bf16x2(o[8 * q + 4] * inv_l, o[8 * q + 5] * inv_l), pack_bf16x2(o[8 * q + 6] * inv_l, o[8 * q + 7] * inv_l));
+    }
   } else {
     setmaxnreg_inc<208>();
     // ===================== softmax: thread = one query row =====================
@@ -221,6 +323,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         for (int i = 0; i < 128; ++i)
           if (i >= kvalid) s[i] = -INFINITY;
       }
+      if constexpr (kFixedMax) {
+        if (j == 0) m_used = p.m0_log2 / p.scale_log2;
+      } else {
       float mx[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) mx[i] = s[i];
@@ -255,12 +360,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
           m_used = m_new;
         }
       }
+      }
       // p = exp2((s - m_used) * scale) -> bf16 pairs -> TMEM (A operand of P.V); row sum in fp32
       ATTN_STAMP(3);
       // P_t may only be overwritten after P_t V_{j-1} has been read: non-blocking probe now, consumed after the exponentials
       const uint32_t p_free = (j > 0) ? mbar_probe(&o_done[t], (j - 1) & 1) : 1u;
-      const float neg = -m_used * p.scale_log2;
+      const float neg = kFixedMax ? -p.m0_log2 : -m_used * p.scale_log2;
       const float2 neg2 = make_float2(neg, neg);
+      // Ping-pong: the MUFU unit (16 exp2 / clk / SM) is the bottleneck and the two tiles' warps share SM sub-partitions.
+      // Free running, both tiles fall into lockstep (exponentiate together, then load / max together with the MUFU idle);
+      // taking turns keeps one tile's exponentials under the other tile's loads, maxima and TMEM stores.
+      if (p.alternate) {
+        if (t == 1) mbar_wait(&turn[0], j & 1, 38);
+        else if (j > 0) mbar_wait(&turn[1], (j - 1) & 1, 39);
+      }
       ATTN_STAMP(4);
       float2 ls0 = make_float2(0.f, 0.f), ls1 = make_float2(0.f, 0.f);
       uint32_t w[64];
@@ -277,6 +390,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         w[(i >> 1) + 1] = pack_bf16x2(p1.x, p1.y);
       }
       l_run += (ls0.x + ls0.y) + (ls1.x + ls1.y);
+      if (p.alternate) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&turn[t]);
+      }
       ATTN_STAMP(5);
       if (!p_free) mbar_wait(&o_done[t], (j - 1) & 1, 36 + t);
       __syncwarp();

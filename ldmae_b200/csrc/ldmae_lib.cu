@@ -193,14 +193,17 @@ extern "C" int ldmae_gemm_trace(long long* dev_buf) { g_gemm_trace = dev_buf; re
 static long long* g_attn_trace = nullptr;   // debug builds (-DLDMAE_ATTN_TRACE): device buffer [2][64][8] of clock64 stamps
 extern "C" int ldmae_attention_trace(long long* dev_buf) { g_attn_trace = dev_buf; return LDMAE_OK; }
 
+// m0_log2 > 0: the scores are bounded (|s * scale * log2e| <= m0_log2): constant-offset softmax instantiation
 static int run_attention(const void* qkv, int ldq, void* out, int ldo, int B, int T, int H, int q_col, int k_col,
-                         int v_col, float scale, cudaStream_t st, float* lse2 = nullptr) {
+                         int v_col, float scale, cudaStream_t st, float* lse2 = nullptr, float m0_log2 = -1.f) {
   CUtensorMap tm, tmo;
   LDMAE_TRY(make_tmap_bf16(&tm, qkv, B * T, ldq, ldq, 128));
   LDMAE_TRY(make_tmap_out_bf16(&tmo, out, B * T, H * 64, ldo));
   static bool attr = false;
   if (!attr) {
-    LDMAE_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+    LDMAE_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+    LDMAE_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+    LDMAE_CUDA((cudaFuncSetAttribute(attn_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes)));
     attr = true;
   }
   AttnParams p;
@@ -210,8 +213,18 @@ static int run_attention(const void* qkv, int ldq, void* out, int ldo, int B, in
   p.T = T; p.H = H; p.ldo = ldo;
   p.q_col = q_col; p.k_col = k_col; p.v_col = v_col;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.m0_log2 = m0_log2;
+  // measured (B=128, T=1024, H=12; tools/bench_attn.py): taking turns helps the tracking instantiation (561 -> 594 TFLOP/s)
+  // and is neutral-to-negative for the constant-offset one (605 vs 599); LDMAE_ATTN_ALTERNATE=0/1 forces either
+  static int alt = -2;
+  if (alt == -2) { const char* e = getenv("LDMAE_ATTN_ALTERNATE"); alt = e ? atoi(e) : -1; }
+  p.alternate = alt >= 0 ? alt : (m0_log2 > 0.f ? 0 : 1);
   dim3 grid(cdiv(T, 256), H, B);
-  attn_fwd_kernel<<<grid, kAttnThreads, kAttnSmemBytes, st>>>(tm, tmo, p);
+  static int wide = -1;
+  if (wide < 0) { const char* e = getenv("LDMAE_ATTN_WIDE"); wide = e ? atoi(e) : 0; }
+  if (m0_log2 > 0.f && wide) attn_fwd_kernel<true, true><<<grid, 640, kAttnSmemBytes, st>>>(tm, tmo, p);
+  else if (m0_log2 > 0.f) attn_fwd_kernel<true><<<grid, kAttnThreads, kAttnSmemBytes, st>>>(tm, tmo, p);
+  else attn_fwd_kernel<false><<<grid, kAttnThreads, kAttnSmemBytes, st>>>(tm, tmo, p);
   LDMAE_LAUNCH_CHECK();
   return LDMAE_OK;
 }
@@ -297,6 +310,7 @@ static int gemm_wgrad(const void* pm, int ldp, const void* qm, int ldq, float* c
 struct DitBlockW {
   DevBuf<__nv_bfloat16> w_qkv, w_proj, w12, w3;
   DevBuf<float> b_qkv, b_proj, b12, b3, qw, kw;
+  float attn_m0_log2 = -1.f;   // > 0: bound of |q.k| * scale * log2(e) from the q/k norm weights (constant-offset softmax)
 };
 
 }  // namespace ldmae
@@ -569,6 +583,27 @@ extern "C" int ldmae_dit_finalize(ldmae_dit* h, void* stream) {
       return set_error(LDMAE_ERR_INVALID, "feat_rope.freqs_cos/sin are not the 2-D axial table of models/pos_embed.py:96-133 "
                        "(max deviation %g): unsupported RoPE buffers", md);
   }
+  // Score bound of the qk-normed attention: |q| <= 8 max|q_norm.w|, |k| <= 8 max|k_norm.w| (RMSNorm over 64, RoPE is a
+  // rotation), so |q.k| / 8 * log2(e) <= 8 * log2(e) * max|wq| * max|wk|.  Re-evaluated whenever weights are (re)loaded.
+  for (auto& b : h->blk) b.attn_m0_log2 = -1.f;
+  static int fixed = -1;
+  if (fixed < 0) { const char* e = getenv("LDMAE_ATTN_FIXED_MAX"); fixed = e ? atoi(e) : 1; }
+  if (h->c.use_qknorm && fixed) {
+    const int depth = h->c.depth;
+    std::vector<float> w(static_cast<size_t>(depth) * 128);
+    for (int i = 0; i < depth; ++i) {
+      LDMAE_CUDA(cudaMemcpyAsync(w.data() + i * 128, h->blk[i].qw.p, 64 * sizeof(float), cudaMemcpyDeviceToHost, st));
+      LDMAE_CUDA(cudaMemcpyAsync(w.data() + i * 128 + 64, h->blk[i].kw.p, 64 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    LDMAE_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < depth; ++i) {
+      float mq = 0.f, mk = 0.f;
+      for (int j = 0; j < 64; ++j) { mq = std::max(mq, std::fabs(w[i * 128 + j])); mk = std::max(mk, std::fabs(w[i * 128 + 64 + j])); }
+      // 2 % head-room for the bf16 rounding of q and k; beyond 48 the exponent range [-2 m0, 0] gets uncomfortable
+      const float m0 = 8.f * 1.4426950408889634f * mq * mk * 1.02f;
+      if (m0 > 0.f && m0 <= 48.f) h->blk[i].attn_m0_log2 = m0;
+    }
+  }
   h->finalized = true;
   return LDMAE_OK;
 }
@@ -717,7 +752,7 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
     {
       ProfScope ps(1, st);
       float* lse = tr ? tr->LSE.p + static_cast<size_t>(i) * B * c.num_heads * T : nullptr;
-      LDMAE_TRY(run_attention(qkv_i, 3 * D, o_i, D, B, T, c.num_heads, 0, D, 2 * D, 0.125f, st, lse));
+      LDMAE_TRY(run_attention(qkv_i, 3 * D, o_i, D, B, T, c.num_heads, 0, D, 2 * D, 0.125f, st, lse, b.attn_m0_log2));
     }
     LDMAE_DBG_STAGE();
     {
@@ -1216,6 +1251,13 @@ extern "C" int ldmae_gemm_residual(const void* a, const void* w, const float* bi
 extern "C" int ldmae_attention(const void* qkv, void* out, int32_t B, int32_t T, int32_t H, float scale, void* stream) {
   LDMAE_TRY(require_sm100());
   return run_attention(qkv, 3 * H * 64, out, H * 64, B, T, H, 0, H * 64, 2 * H * 64, scale, static_cast<cudaStream_t>(stream));
+}
+extern "C" int ldmae_attention_bounded(const void* qkv, void* out, float* lse2, int32_t B, int32_t T, int32_t H, float scale,
+                                       float m0_log2, void* stream) {
+  LDMAE_TRY(require_sm100());
+  LDMAE_REQUIRE(m0_log2 > 0.f && m0_log2 <= 48.f, "score bound must be in (0, 48] (log2 units)");
+  return run_attention(qkv, 3 * H * 64, out, H * 64, B, T, H, 0, H * 64, 2 * H * 64, scale, static_cast<cudaStream_t>(stream), lse2,
+                       m0_log2);
 }
 extern "C" int ldmae_attention_lse(const void* qkv, void* out, float* lse2, int32_t B, int32_t T, int32_t H, float scale,
                                    void* stream) {

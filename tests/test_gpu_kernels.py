@@ -100,3 +100,28 @@ def test_library_reports_sm100():
     sm, cc = C.c_int(), C.c_int()
     _lib.check(_lib.lib().ldmae_device_info(C.byref(sm), C.byref(cc)))
     assert cc.value // 10 == 10 and sm.value >= 100
+
+
+@pytest.mark.parametrize("B,T,H,wide", [(2, 1024, 3, 0), (3, 64, 2, 0), (1, 320, 2, 0), (2, 1024, 2, 1), (1, 320, 2, 1)])
+def test_attention_bounded_scores_matches_softmax(B, T, H, wide, monkeypatch):
+    """Constant-offset softmax (qk-normed heads): the score bound replaces the running maximum; lse2 is exported for the
+    backward.  `wide` additionally exercises the two-threads-per-row instantiation (LDMAE_ATTN_WIDE is read once per process,
+    so that case only checks the default unless the variable was set before the library loaded)."""
+    from gpu_util import rel_err
+    from ldmae_b200 import _lib
+    g = torch.Generator().manual_seed(B * 10 + T)
+    x = torch.randn(B * T, 3 * H, 64, generator=g)
+    x[:, : 2 * H] = x[:, : 2 * H] / x[:, : 2 * H].pow(2).mean(-1, keepdim=True).sqrt()       # |q| = |k| = 8
+    qkv = x.reshape(B * T, 3 * H * 64).to(torch.bfloat16)
+    q, k, v = qkv.float().reshape(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    sc = (q @ k.transpose(-1, -2)) * 0.125
+    ref = (torch.softmax(sc, dim=-1) @ v).transpose(1, 2).reshape(B * T, H * 64)
+    out = torch.empty(B * T, H * 64, device="cuda", dtype=torch.bfloat16)
+    lse = torch.zeros(B * H * T + 64, device="cuda")
+    m0 = 8 * 1.4426950408889634 * 1.02
+    assert float(sc.abs().max()) * 1.4426950408889634 <= m0
+    _lib.check(_lib.lib().ldmae_attention_bounded(_lib.ptr(qkv.cuda()), _lib.ptr(out), _lib.ptr(lse), B, T, H, 0.125, m0,
+                                                  _lib.stream_ptr()), "attention_bounded")
+    torch.cuda.synchronize()
+    assert rel_err(out.float().cpu(), ref) < 1e-2
+    torch.testing.assert_close(lse[: B * H * T].cpu().reshape(B, H, T), torch.logsumexp(sc, -1) * 1.4426950408889634, rtol=0, atol=2e-2)

@@ -19,3 +19,19 @@ q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)[:, :2]
 ref = (torch.softmax(q @ k.transpose(-1, -2) * 0.125, -1) @ v).transpose(1, 2).reshape(2 * T, H * 64)
 err = float((o[:2 * T].float() - ref).norm() / ref.norm())
 print(f"{os.environ.get('LDMAE_B200_LIB','default')}: attention fwd {ms:.3f} ms {fl/ms/1e9:.0f} TF/s rel err {err:.2e}")
+
+# bounded-score instantiation on unit-norm-like heads (|q| = |k| = 8 as after RMSNorm(64) with unit weights)
+x = torch.randn(B * T, 3 * H, 64, device=dev)
+x[:, : 2 * H] = x[:, : 2 * H] / x[:, : 2 * H].pow(2).mean(-1, keepdim=True).sqrt()
+qkvn = x.reshape(B * T, 3 * H * 64).to(torch.bfloat16)
+m0 = 8 * 1.4426950408889634 * 1.02
+lse = torch.zeros(B * H * T + 64, device=dev)
+msb = timeit(lambda: _lib.check(_lib.lib().ldmae_attention_bounded(_lib.ptr(qkvn), _lib.ptr(o), _lib.ptr(lse), B, T, H, 0.125, m0, _lib.stream_ptr())))
+mst = timeit(lambda: _lib.check(_lib.lib().ldmae_attention(_lib.ptr(qkvn), _lib.ptr(o), B, T, H, 0.125, _lib.stream_ptr())))
+_lib.check(_lib.lib().ldmae_attention_bounded(_lib.ptr(qkvn), _lib.ptr(o), _lib.ptr(lse), B, T, H, 0.125, m0, _lib.stream_ptr()))
+q, k, v = qkvn.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)[:, :2]
+sc = q @ k.transpose(-1, -2) * 0.125
+ref = (torch.softmax(sc, -1) @ v).transpose(1, 2).reshape(2 * T, H * 64)
+err = float((o[:2 * T].float() - ref).norm() / ref.norm())
+lerr = float((lse[: 2 * H * T].view(2, H, T) - torch.logsumexp(sc, -1) * 1.4426950408889634).abs().max())
+print(f"normed heads: bounded {msb:.3f} ms {fl/msb/1e9:.0f} TF/s | tracking {mst:.3f} ms {fl/mst/1e9:.0f} TF/s | rel err {err:.2e} lse err {lerr:.2e} score absmax {float(sc.abs().max()):.2f}")
