@@ -216,9 +216,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     float l_run = 0.f;
 #pragma unroll 1
     for (int j = 0; j < nkv; ++j) {
+      if (ch == 0) ATTN_STAMP(0);
       mbar_wait(&s_full[t], j & 1, 30 + t);
       __syncwarp();
       tc_fence_after();
+      if (ch == 0) ATTN_STAMP(1);
       float s[64];
       tmem_ld32(tS, s);
       tmem_ld32(tS + 32, s + 32);
@@ -226,6 +228,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[t]);            // the tensor core may overwrite S_t with block j+1
+      if (ch == 0) { ATTN_STAMP(2); ATTN_STAMP(3); }
       const int kvalid = p.T - j * 128 - ch * 64;        // keys of this thread's half that exist
       if (kvalid < 64) {
 #pragma unroll
@@ -237,6 +240,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         if (t == 1) mbar_wait(&turn[0], j & 1, 38);
         else if (j > 0) mbar_wait(&turn[1], (j - 1) & 1, 39);
       }
+      if (ch == 0) ATTN_STAMP(4);
       float2 ls0 = make_float2(0.f, 0.f), ls1 = make_float2(0.f, 0.f);
       uint32_t w[32];
 #pragma unroll
@@ -255,11 +259,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(&turn[t]);
       }
+      if (ch == 0) ATTN_STAMP(5);
       if (!p_free) mbar_wait(&o_done[t], (j - 1) & 1, 36 + t);
       __syncwarp();
       tc_fence_after();
+      if (ch == 0) ATTN_STAMP(6);
       tmem_st32(tP, w);
       tmem_st_wait();
+      if (ch == 0) ATTN_STAMP(7);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[t]);

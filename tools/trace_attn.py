@@ -8,10 +8,14 @@ dev = torch.device("cuda:0")
 qkv = torch.randn(B * T, 3 * H * 64, device=dev).to(torch.bfloat16); o = torch.empty(B * T, H * 64, device=dev, dtype=torch.bfloat16)
 tr = torch.zeros(2, 64, 8, dtype=torch.int64, device=dev)
 L = _lib.lib()
+bounded = len(sys.argv) > 1 and sys.argv[1] == "bounded"
+m0 = 48.0       # (random un-normed scores here: only the timing is of interest)
+run = (lambda: _lib.check(L.ldmae_attention_bounded(_lib.ptr(qkv), _lib.ptr(o), None, B, T, H, 0.125, m0, _lib.stream_ptr()))) if bounded \
+    else (lambda: _lib.check(L.ldmae_attention(_lib.ptr(qkv), _lib.ptr(o), B, T, H, 0.125, _lib.stream_ptr())))
 for _ in range(2):
-    _lib.check(L.ldmae_attention(_lib.ptr(qkv), _lib.ptr(o), B, T, H, 0.125, _lib.stream_ptr()))
+    run()
 _lib.check(L.ldmae_attention_trace(_lib.ptr(tr)))
-_lib.check(L.ldmae_attention(_lib.ptr(qkv), _lib.ptr(o), B, T, H, 0.125, _lib.stream_ptr()))
+run()
 torch.cuda.synchronize()
 tr = tr.cpu()
 t00 = int(tr[0, 0, 0])
