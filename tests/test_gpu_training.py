@@ -104,6 +104,31 @@ def test_tiny_backward_matches_reference_golden(golden_dir, patch):
     _compare(ours, ref)
 
 
+@pytest.mark.parametrize("hidden,heads,patch,inp", [(1024, 16, 2, 16), (1536, 24, 1, 8), (1792, 28, 2, 16)])
+def test_wider_registry_widths_forward_and_backward(hidden, heads, patch, inp):
+    """Widths of the other registry entries with head_dim 64 (L: 1024, 1p0B: 1536, 1p6B: 1792; lightningdit.py:498-531) at
+    depth 2: the row-statistics slots, the column panels of the backward kernels and the GEMM tails all depend on D."""
+    from ldmae_b200.models.lightningdit import LightningDiT
+    spec = O.DiTSpec(depth=2, hidden_size=hidden, patch_size=patch, num_heads=heads, input_size=inp, in_channels=16, num_classes=10)
+    m = LightningDiT(input_size=inp, patch_size=patch, in_channels=16, hidden_size=hidden, depth=2, num_heads=heads, num_classes=10,
+                     use_qknorm=True, use_swiglu=True, use_rope=True, use_rmsnorm=True)
+    sd = O.synth_dit_state(spec, 77)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    g = torch.Generator().manual_seed(hidden)
+    B = 3
+    x1 = torch.randn(B, 16, inp, inp, generator=g); x0 = torch.randn(B, 16, inp, inp, generator=g)
+    t = torch.rand(B, generator=g); y = torch.randint(0, 10, (B,), generator=g)
+    with torch.no_grad():
+        out = m(x1.cuda(), t.cuda(), y.cuda())
+        ref_out = O.dit_forward(sd, spec, x1, t, y)
+    assert _rel(out, ref_out) < 1e-2
+    ref_terms, ref = _oracle_grads(spec, sd, x1, t, x0, y)
+    terms, ours = _our_grads(m, x1.cuda(), t, x0, y.cuda())
+    assert _rel(terms["loss"], ref_terms["loss"].detach()) < 1e-2
+    _compare(ours, ref)
+
+
 def test_b1_backward_matches_oracle_autograd():
     """LightningDiT-B/1 at the benchmark shape (T = 1024, D = 768, 12 blocks), batch 2."""
     from ldmae_b200.models.lightningdit import LightningDiT_models
