@@ -77,6 +77,8 @@ int ldmae_dit_forward(ldmae_dit* h, const float* x, const float* t, float t_scal
 int ldmae_dit_train_forward(ldmae_dit* h, const float* x, const float* t, const int64_t* y, float* out, int32_t B, void* stream);
 int ldmae_dit_backward(ldmae_dit* h, const float* dout, int32_t B, void* stream);
 int ldmae_dit_grad_read(ldmae_dit* h, const char* name, float* dst, int64_t numel, void* stream);
+/* Same, but dst += gradient: micro-batch accumulation between optimizer steps (train_accum.py:220-234). */
+int ldmae_dit_grad_accumulate(ldmae_dit* h, const char* name, float* dst, int64_t numel, void* stream);
 /* Fused torch.optim.AdamW step + EMA update (train_accum.py:121,240-246,337-347) on flat fp32 device buffers of n
  * elements (16-byte aligned); ema may be NULL; grad is multiplied by grad_scale first (1/world_size after an all-reduce);
  * step counts from 1. */

@@ -617,7 +617,7 @@ struct DitTrain {
   DevBuf<__nv_bfloat16> A, QKV, QKR, O, MA, MM, H12, HB, XTOK;
   DevBuf<long long> ykeep;
   // backward workspace
-  DevBuf<float> dx, delta, dg, sdx, dcv_qkv, dcv_12, dcv_f, dmods, dsc, dcond, dth1, dth1pre, grads;
+  DevBuf<float> dx, delta, dg, sdx, dcv_qkv, dcv_12, dcv_f, dmods, dsc, dcond, dth1, dth1pre, grads, gscratch;
   DevBuf<__nv_bfloat16> dY, dO, G, dQKV, dH, dH12, dYf, cv_bf16, dmods_bf16;
   // transposed weights (operands of the data-gradient GEMMs)
   std::vector<DevBuf<__nv_bfloat16>> wT_qkv, wT_proj, wT_12, wT_3;

@@ -101,7 +101,9 @@ class FusedTrainer:
         return sd
 
     # -- one micro-batch: loss + gradients into self.grad ----------------------------------------
-    def loss_and_grad(self, x1, y, t=None, x0=None):
+    def loss_and_grad(self, x1, y, t=None, x0=None, accumulate=False, loss_scale=1.0):
+        """One micro-batch.  accumulate=True adds into the flat gradient buffer instead of overwriting it and loss_scale
+        divides the loss (train_accum.py:220-223: loss / gradient_accumulation_steps)."""
         m, L = self.model, _lib.lib()
         B = x1.shape[0]
         if t is None or x0 is None:
@@ -120,12 +122,13 @@ class FusedTrainer:
             _lib.check(L.ldmae_dit_train_forward(h, _lib.ptr(xt), _lib.ptr(t), _lib.ptr(y), _lib.ptr(out), B, st), "train_forward")
             diff = out - ut
             loss = (diff * diff).mean(dim=(1, 2, 3))                   # mean_flat
-            dout = (diff * (2.0 / (diff[0].numel() * B))).contiguous() # d mean(loss) / d out
+            dout = (diff * (2.0 * loss_scale / (diff[0].numel() * B))).contiguous()   # d (mean(loss) * loss_scale) / d out
             _lib.check(L.ldmae_dit_backward(h, _lib.ptr(dout), B, st), "backward")
             base = self.grad.data_ptr()
             for k in self.names:
                 off, n, _ = self.slices[k]
-                _lib.check(L.ldmae_dit_grad_read(h, k.encode(), C.c_void_p(base + 4 * off), n, st), f"grad {k}")
+                fetch = L.ldmae_dit_grad_accumulate if accumulate else L.ldmae_dit_grad_read
+                _lib.check(fetch(h, k.encode(), C.c_void_p(base + 4 * off), n, st), f"grad {k}")
         return loss, out
 
     def optimizer_step(self):
@@ -139,7 +142,18 @@ class FusedTrainer:
                 self.ema_decay, grad_scale, _lib.stream_ptr()), "adamw_ema_step")
         self.model._handle_sig = None                                  # parameters changed behind torch's version counters
 
-    def step(self, x1, y, t=None, x0=None):
-        loss, _ = self.loss_and_grad(x1, y, t, x0)
+    def step(self, x1, y, t=None, x0=None, micro_batches=1):
+        """One optimizer step; micro_batches > 1 splits the batch and accumulates gradients (train_accum.py's
+        gradient_accumulation_steps) -- one all-reduce per optimizer step, not per micro-batch."""
+        if micro_batches > 1:
+            losses = []
+            for i, (xs, ys) in enumerate(zip(x1.chunk(micro_batches), y.chunk(micro_batches))):
+                ts = t.chunk(micro_batches)[i] if t is not None else None
+                x0s = x0.chunk(micro_batches)[i] if x0 is not None else None
+                l, _ = self.loss_and_grad(xs, ys, ts, x0s, accumulate=i > 0, loss_scale=1.0 / micro_batches)
+                losses.append(l)
+            loss = torch.cat(losses)
+        else:
+            loss, _ = self.loss_and_grad(x1, y, t, x0)
         self.optimizer_step()
         return loss

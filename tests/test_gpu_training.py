@@ -213,3 +213,23 @@ def test_fused_trainer_step_matches_autograd_plus_torch_adamw():
     new_sd = {k_: v.detach().cpu() for k_, v in m.state_dict().items()}
     ref_out = O.dit_forward(new_sd, spec, x1, t, y)
     assert _rel(out, ref_out) < 1e-2
+
+
+def test_gradient_accumulation_equals_the_full_batch():
+    """FusedTrainer micro-batches (train_accum.py gradient_accumulation_steps): the accumulated flat gradient of 2 micro-batches
+    equals the gradient of the full batch (same draws), up to fp32 summation order."""
+    from ldmae_b200.training import FusedTrainer
+    g = torch.Generator().manual_seed(5)
+    B = 6
+    x1 = torch.randn(B, 16, 8, 8, generator=g).cuda(); x0 = torch.randn(B, 16, 8, 8, generator=g).cuda()
+    t = torch.rand(B, generator=g).cuda(); y = torch.randint(0, 10, (B,), generator=g).cuda()
+    _, _, m = _tiny(1, 41)
+    tr = FusedTrainer(m, lr=1e-3)
+    with torch.no_grad():
+        tr.loss_and_grad(x1, y, t, x0)
+        full = tr.grad.clone()
+        for i in range(2):
+            sl = slice(3 * i, 3 * i + 3)
+            tr.loss_and_grad(x1[sl], y[sl], t[sl], x0[sl], accumulate=i > 0, loss_scale=0.5)
+    torch.cuda.synchronize()
+    assert _rel(tr.grad, full) < 2e-3
