@@ -165,6 +165,10 @@ int ldmae_attention(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t T, 
  * log2(sum_j exp(s_ij * scale)), the row statistic the backward needs. */
 int ldmae_attention_lse(const void* qkv_bf16, void* out_bf16, float* lse2, int32_t B, int32_t T, int32_t H, float scale,
                         void* stream);
+/* Heads wider than 64 (LightningDiT-XL: head_dim 72): qkv [B*T, 3*H*128] bf16 with every head in a 128-column slot
+ * (head_dim `hd` real columns, zeros behind), out [B*T, H*hd] bf16 dense.  hd: multiple of 8, <= 128. */
+int ldmae_attention_wide(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t T, int32_t H, int32_t hd, float scale,
+                         void* stream);
 /* The same attention when the scores are known to be bounded, |q.k * scale| * log2(e) <= m0_log2 (qk-normed heads:
  * 8 * log2(e) * max|q_norm.w| * max|k_norm.w|): the bound replaces the running row maximum (no max pass, no rescale).
  * lse2 may be NULL. */

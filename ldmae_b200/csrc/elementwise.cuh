@@ -44,9 +44,10 @@ __global__ void pack_vec_f32_kernel(float* __restrict__ dst, const float* __rest
 // VMAE head padding hd -> 64:  qkv weight [3*nh*hd, K] -> [3*nh*64, K] (zero rows), bias likewise;
 // proj weight [D, nh*hd] -> [D, nh*64] (zero columns).
 __global__ void pad_heads_rows_kernel(__nv_bfloat16* __restrict__ dstw, float* __restrict__ dstb,
-                                      const float* __restrict__ w, const float* __restrict__ bias, int nh, int hd, int K) {
-  const int r = blockIdx.x;                       // dst row in [0, 3*nh*64)
-  const int sec = r / (nh * 64), h = (r / 64) % nh, d = r % 64;
+                                      const float* __restrict__ w, const float* __restrict__ bias, int nh, int hd, int K,
+                                      int hp = 64) {
+  const int r = blockIdx.x;                       // dst row in [0, 3*nh*hp); hp = padded head width (64, or 128 for XL)
+  const int sec = r / (nh * hp), h = (r / hp) % nh, d = r % hp;
   const bool real = d < hd;
   const int sr = sec * nh * hd + h * hd + d;
   for (int k = threadIdx.x; k < K; k += blockDim.x)

@@ -556,6 +556,108 @@ struct EpiQKV : StoreRing {
   }
 };
 
+// The same QKV epilogue for heads wider than 64 (LightningDiT-XL: head_dim 72): every head occupies 128 accumulator /
+// output columns, the real head_dim `hd` first and zeros behind (the packed weight and bias rows of the padding are zero,
+// so the padded accumulators are exactly 0 and take no part in the statistics).  Two passes over the head's two 64-column
+// halves: sum of squares, then normalise + RoPE + store.  RoPE angles come straight from the reference's [T, hd] tables.
+struct EpiQKVWide : StoreRing {
+  struct Params {
+    CUtensorMap omap;       // out [M, 3 * heads * 128] bf16: box {64, 32}, SWIZZLE_128B
+    const float* ssq;       // [M, ss_slots]
+    const float* cvec;      // [B, N]
+    const float* qw;        // [128] q_norm.weight zero-padded, or nullptr
+    const float* kw;        // [128]
+    const float* rope_cos;  // [T, hd] or nullptr
+    const float* rope_sin;
+    int section, hd, rows_per_sample, ss_slots;     // section = heads * 128 = width of each of the q | k | v column ranges
+    float inv_D, eps_row, eps_head;
+  };
+  static __device__ __forceinline__ void prefetch_maps(const Params& p) { tma_prefetch_desc(&p.omap); }
+  template <int BN>
+  static __device__ __forceinline__ void begin(const Params&, const GemmShape&, const TileSched&, const EpiCtx&, State& st) {
+    st.seq = 0;
+  }
+  template <int BN, int GC>
+  static __device__ __forceinline__ void run(const Params& p, const GemmShape& g, const TileSched&, const EpiCtx& c, State& st,
+                                             uint32_t acc, int row0, int n0, int cbase) {
+    static_assert(GC % 128 == 0 && GC <= 256, "wide QKV epilogue works on whole 128-column heads");
+    const int lane = c.lane;
+    const int my_row = min(row0 + lane, g.M - 1);
+    const int my_b = my_row / p.rows_per_sample;
+    const int tok = my_row % p.rows_per_sample;
+    const float rinv = row_rinv(p.ssq, my_row, p.ss_slots, p.inv_D, p.eps_row);
+    const float* cv = p.cvec + static_cast<size_t>(my_b) * g.N;
+    const float inv_hd = 1.f / static_cast<float>(p.hd);
+#pragma unroll 1
+    for (int c0 = cbase; c0 < cbase + GC; c0 += 128) {
+      const int colbase = n0 + c0;
+      if (colbase >= g.N) break;
+      const int which = colbase / p.section;           // 0 q, 1 k, 2 v
+      const bool normed = which < 2 && p.qw != nullptr;
+      float hs = 1.f;
+      if (normed) {
+        float ms = 0.f;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float v[64];
+          tmem_ld32(acc + c0 + half * 64, v);
+          tmem_ld32(acc + c0 + half * 64 + 32, v + 32);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 64; j += 4) {
+            const float4 cc = ldvec4(cv, colbase + half * 64 + j, g.N);
+            const float a0 = fmaf(v[j], rinv, cc.x), a1 = fmaf(v[j + 1], rinv, cc.y), a2 = fmaf(v[j + 2], rinv, cc.z), a3 = fmaf(v[j + 3], rinv, cc.w);
+            ms = fmaf(a0, a0, ms); ms = fmaf(a1, a1, ms); ms = fmaf(a2, a2, ms); ms = fmaf(a3, a3, ms);
+          }
+        }
+        hs = rsqrtf(ms * inv_hd + p.eps_head);
+      }
+      const float* nw = which == 0 ? p.qw : p.kw;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint8_t* tile = acquire(c, st);
+        float v[64];
+        tmem_ld32(acc + c0 + half * 64, v);
+        tmem_ld32(acc + c0 + half * 64 + 32, v + 32);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 64; j += 4) {
+          const float4 cc = ldvec4(cv, colbase + half * 64 + j, g.N);
+          v[j] = fmaf(v[j], rinv, cc.x); v[j + 1] = fmaf(v[j + 1], rinv, cc.y);
+          v[j + 2] = fmaf(v[j + 2], rinv, cc.z); v[j + 3] = fmaf(v[j + 3], rinv, cc.w);
+          if (normed) {
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(nw + half * 64 + j));
+            v[j] *= hs * w4.x; v[j + 1] *= hs * w4.y; v[j + 2] *= hs * w4.z; v[j + 3] *= hs * w4.w;
+          }
+        }
+        if (which < 2 && p.rope_cos != nullptr) {
+          const float* rc = p.rope_cos + static_cast<size_t>(tok) * p.hd;
+          const float* rs = p.rope_sin + static_cast<size_t>(tok) * p.hd;
+#pragma unroll
+          for (int j = 0; j < 64; j += 2) {
+            const int d = half * 64 + j;
+            if (d < p.hd) {                                   // adjacent pairs share an angle (pos_embed.py:38-42,124-133)
+              const float cs = __ldg(rc + d), sn = __ldg(rs + d);
+              const float a = v[j], b2 = v[j + 1];
+              v[j] = a * cs - b2 * sn;
+              v[j + 1] = b2 * cs + a * sn;
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          st_tile16(sw128_chunk(tile, lane, q),
+                 make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                            pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7])));
+        release(c, st, &p.omap, tile, colbase + half * 64, row0);
+      }
+    }
+  }
+  static __device__ __forceinline__ void end(const EpiCtx& c, State&) {
+    if (c.lane == 0) tma_store_wait_read<0>();
+  }
+};
+
 // SwiGLU first projection (models/swiglu_ffn.py:33-35) on the pre-scaled operand.  The packed weight
 // interleaves w12 rows in groups of 64: [32 rows of x1 | the matching 32 rows of x2], so every 64
 // accumulator columns yield 32 hidden values h = silu(x1) * x2 without leaving the thread.

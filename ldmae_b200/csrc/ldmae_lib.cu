@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "attention_bwd_sm100.cuh"
+#include "attention_hd128_sm100.cuh"
 #include "attention_sm100.cuh"
 #include "common.cuh"
 #include "gemm_wgrad_sm100.cuh"
@@ -229,6 +230,27 @@ static int run_attention(const void* qkv, int ldq, void* out, int ldo, int B, in
   return LDMAE_OK;
 }
 
+// Heads stored with a 128-column stride (real head_dim hd <= 128): attention_hd128_sm100.cuh
+static int run_attention_hd128(const void* qkv, int ldq, void* out, int ldo, int B, int T, int H, int hd, int q_col, int k_col,
+                               int v_col, float scale, cudaStream_t st, float* lse2 = nullptr) {
+  LDMAE_REQUIRE(hd > 0 && hd <= 128 && hd % 8 == 0, "wide attention: head_dim %d must be a multiple of 8 up to 128", hd);
+  CUtensorMap tm;
+  LDMAE_TRY(make_tmap_bf16(&tm, qkv, B * T, ldq, ldq, 128));
+  static bool attr = false;
+  if (!attr) {
+    LDMAE_CUDA(cudaFuncSetAttribute(attn_fwd_hd128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kA128SmemBytes));
+    attr = true;
+  }
+  Attn128Params p;
+  p.out = static_cast<__nv_bfloat16*>(out); p.lse2 = lse2;
+  p.T = T; p.H = H; p.ldo = ldo; p.hd = hd; p.q_col = q_col; p.k_col = k_col; p.v_col = v_col;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid(cdiv(T, 128), H, B);
+  attn_fwd_hd128_kernel<<<grid, kA128Threads, kA128SmemBytes, st>>>(tm, p);
+  LDMAE_LAUNCH_CHECK();
+  return LDMAE_OK;
+}
+
 // Backward of run_attention: dqkv [B*T, ldq] (same column layout as qkv) from dO [B*T, ldo], the forward output o,
 // the forward's lse2 [B,H,T] (padded by 64 floats) and a statistics workspace of 2 * (B*H*T + 64) floats.
 static int run_attention_bwd(const void* qkv, int ldq, const void* o, const void* d_o, int ldo, const float* lse2, float* delta,
@@ -323,6 +345,7 @@ static void dit_train_free(DitTrain* t);
 struct ldmae_dit {
   ldmae_dit_config c;
   int D, T, G, Kp, H, Hp, nmod, Ntot, S /*norm slots*/, Nf, maxB, SS /*ssq partial slots*/;
+  int hd /*real head_dim*/, HW /*head stride in the qkv buffer: 64, or 128 for wider heads*/, QW /*heads * HW*/;
   // weights
   DevBuf<float> pos, patch_w, patch_b, t_w0, t_b0, t_w2, t_b2, emb, rope_cos, rope_sin, rope_tab, norm_w, b_ada, b_f, w_f32;
   DevBuf<__nv_bfloat16> w_ada, w_f;
@@ -345,7 +368,7 @@ static int dit_alloc_ws(ldmae_dit* h, int B) {
   const int D = h->D;
   LDMAE_TRY(h->xres.alloc(M * D));
   LDMAE_TRY(h->abuf.alloc(M * D));
-  LDMAE_TRY(h->qkv.alloc(M * 3 * D));
+  LDMAE_TRY(h->qkv.alloc(M * 3 * h->QW));
   LDMAE_TRY(h->obuf.alloc(M * D));
   LDMAE_TRY(h->hbuf.alloc(M * h->Hp));
   LDMAE_TRY(h->ssq.alloc(M * h->SS));
@@ -355,7 +378,7 @@ static int dit_alloc_ws(ldmae_dit* h, int B) {
   LDMAE_TRY(h->mods.alloc(static_cast<size_t>(B) * h->Ntot));
   LDMAE_TRY(h->shift_bf16.alloc(static_cast<size_t>(h->S) * B * D));
   LDMAE_TRY(h->gmul.alloc(static_cast<size_t>(h->S) * B * D));
-  LDMAE_TRY(h->cvec_qkv.alloc(static_cast<size_t>(h->c.depth) * B * 3 * D));
+  LDMAE_TRY(h->cvec_qkv.alloc(static_cast<size_t>(h->c.depth) * B * 3 * h->QW));
   LDMAE_TRY(h->cvec_12.alloc(static_cast<size_t>(h->c.depth) * B * 2 * h->Hp));
   LDMAE_TRY(h->cvec_f.alloc(static_cast<size_t>(B) * h->Nf));
   const size_t lat = static_cast<size_t>(B) * h->c.in_channels * h->c.input_size * h->c.input_size;
@@ -414,9 +437,12 @@ extern "C" int ldmae_dit_create(const ldmae_dit_config* cfg, ldmae_dit** out) {
   const ldmae_dit_config& c = *cfg;
   LDMAE_REQUIRE(c.use_rmsnorm == 1, "LightningDiT without use_rmsnorm (LayerNorm variant) is not built yet");
   LDMAE_REQUIRE(c.use_swiglu == 1, "LightningDiT without use_swiglu (GELU Mlp variant) is not built yet");
-  LDMAE_REQUIRE(c.hidden_size % c.num_heads == 0 && c.hidden_size / c.num_heads == 64,
-                "attention kernel is built for head_dim 64 (got %d); XL (head_dim 72) is a next-round item",
-                c.num_heads ? c.hidden_size / c.num_heads : 0);
+  LDMAE_REQUIRE(c.num_heads > 0 && c.hidden_size % c.num_heads == 0, "hidden_size %% num_heads != 0");
+  {
+    const int hd = c.hidden_size / c.num_heads;
+    LDMAE_REQUIRE(hd == 64 || (hd > 64 && hd <= 128 && hd % 8 == 0),
+                  "head_dim %d: built for 64 (tuned path) and for multiples of 8 in (64, 128] (XL: 72, inference only)", hd);
+  }
   LDMAE_REQUIRE(c.input_size % c.patch_size == 0, "input_size %% patch_size != 0");
   LDMAE_REQUIRE((c.in_channels * c.patch_size * c.patch_size) % 4 == 0, "C*p*p must be a multiple of 4");
   ldmae_dit* h = new ldmae_dit();
@@ -432,6 +458,9 @@ extern "C" int ldmae_dit_create(const ldmae_dit_config* cfg, ldmae_dit** out) {
   h->S = 2 * c.depth + 1;
   h->Nf = c.patch_size * c.patch_size * c.in_channels * (c.learn_sigma ? 2 : 1);
   h->SS = (c.hidden_size + 127) / 128;
+  h->hd = c.hidden_size / c.num_heads;
+  h->HW = h->hd == 64 ? 64 : 128;
+  h->QW = c.num_heads * h->HW;
   const int D = h->D;
   h->blk.resize(c.depth);
   int r = LDMAE_OK;
@@ -442,17 +471,17 @@ extern "C" int ldmae_dit_create(const ldmae_dit_config* cfg, ldmae_dit** out) {
   A(h->t_w0.alloc(static_cast<size_t>(D) * 256)); A(h->t_b0.alloc(D));
   A(h->t_w2.alloc(static_cast<size_t>(D) * D)); A(h->t_b2.alloc(D));
   A(h->emb.alloc(static_cast<size_t>(c.num_embeddings) * D));
-  A(h->rope_cos.alloc(static_cast<size_t>(h->T) * 64)); A(h->rope_sin.alloc(static_cast<size_t>(h->T) * 64));
+  A(h->rope_cos.alloc(static_cast<size_t>(h->T) * h->hd)); A(h->rope_sin.alloc(static_cast<size_t>(h->T) * h->hd));
   A(h->rope_tab.alloc(static_cast<size_t>(2) * h->G * 32 + 1));
   A(h->norm_w.alloc(static_cast<size_t>(h->S) * D));
   A(h->w_ada.alloc(static_cast<size_t>(h->Ntot) * D)); A(h->b_ada.alloc(h->Ntot));
   A(h->w_f.alloc(static_cast<size_t>(h->Nf) * D)); A(h->b_f.alloc(h->Nf)); A(h->w_f32.alloc(static_cast<size_t>(h->Nf) * D));
   for (auto& b : h->blk) {
-    A(b.w_qkv.alloc(static_cast<size_t>(3 * D) * D)); A(b.b_qkv.alloc(3 * D));
+    A(b.w_qkv.alloc(static_cast<size_t>(3 * h->QW) * D)); A(b.b_qkv.alloc(3 * h->QW, true));
     A(b.w_proj.alloc(static_cast<size_t>(D) * D)); A(b.b_proj.alloc(D));
     A(b.w12.alloc(static_cast<size_t>(2 * h->Hp) * D)); A(b.b12.alloc(2 * h->Hp));
     A(b.w3.alloc(static_cast<size_t>(D) * h->Hp)); A(b.b3.alloc(D));
-    A(b.qw.alloc(64)); A(b.kw.alloc(64));
+    A(b.qw.alloc(h->HW, true)); A(b.kw.alloc(h->HW, true));
   }
   // adaLN slot -> column offsets inside a mods row
   std::vector<int> so(h->S), sco(h->S);
@@ -519,8 +548,8 @@ extern "C" int ldmae_dit_load_tensor(ldmae_dit* h, const char* name, const float
   else if (k == "t_embedder.mlp.2.weight") rc = copy_f32(h->t_w2.p, data, numel, (int64_t)D * D, name, st);
   else if (k == "t_embedder.mlp.2.bias") rc = copy_f32(h->t_b2.p, data, numel, D, name, st);
   else if (k == "y_embedder.embedding_table.weight") rc = copy_f32(h->emb.p, data, numel, (int64_t)h->c.num_embeddings * D, name, st);
-  else if (k == "feat_rope.freqs_cos") rc = copy_f32(h->rope_cos.p, data, numel, (int64_t)h->T * 64, name, st);
-  else if (k == "feat_rope.freqs_sin") rc = copy_f32(h->rope_sin.p, data, numel, (int64_t)h->T * 64, name, st);
+  else if (k == "feat_rope.freqs_cos") rc = copy_f32(h->rope_cos.p, data, numel, (int64_t)h->T * h->hd, name, st);
+  else if (k == "feat_rope.freqs_sin") rc = copy_f32(h->rope_sin.p, data, numel, (int64_t)h->T * h->hd, name, st);
   else if (k == "final_layer.norm_final.weight") rc = copy_f32(h->norm_w.p + (size_t)(2 * h->c.depth) * D, data, numel, D, name, st);
   else if (k == "final_layer.linear.weight") {
     rc = pack_bf16(h->w_f.p, data, h->Nf, D, D, numel, name, st);
@@ -535,10 +564,21 @@ extern "C" int ldmae_dit_load_tensor(ldmae_dit* h, const char* name, const float
     DitBlockW& b = h->blk[bi];
     if (sub == "norm1.weight") rc = copy_f32(h->norm_w.p + (size_t)(2 * bi) * D, data, numel, D, name, st);
     else if (sub == "norm2.weight") rc = copy_f32(h->norm_w.p + (size_t)(2 * bi + 1) * D, data, numel, D, name, st);
-    else if (sub == "attn.qkv.weight") rc = pack_bf16(b.w_qkv.p, data, 3 * D, D, D, numel, name, st);
-    else if (sub == "attn.qkv.bias") rc = copy_f32(b.b_qkv.p, data, numel, 3 * D, name, st);
-    else if (sub == "attn.q_norm.weight") rc = copy_f32(b.qw.p, data, numel, 64, name, st);
-    else if (sub == "attn.k_norm.weight") rc = copy_f32(b.kw.p, data, numel, 64, name, st);
+    else if (sub == "attn.qkv.weight" && h->HW == 64) rc = pack_bf16(b.w_qkv.p, data, 3 * D, D, D, numel, name, st);
+    else if (sub == "attn.qkv.bias" && h->HW == 64) rc = copy_f32(b.b_qkv.p, data, numel, 3 * D, name, st);
+    else if (sub == "attn.qkv.weight") {
+      // wider heads: every head gets a 128-row slot, rows beyond head_dim stay zero
+      LDMAE_REQUIRE(numel == (int64_t)3 * D * D, "%s: bad size", name);
+      pad_heads_rows_kernel<<<3 * h->QW, 128, 0, st>>>(b.w_qkv.p, nullptr, data, nullptr, h->c.num_heads, h->hd, D, h->HW);
+      LDMAE_LAUNCH_CHECK();
+    } else if (sub == "attn.qkv.bias") {
+      LDMAE_REQUIRE(numel == 3 * D, "%s: bad size", name);
+      LDMAE_CUDA(cudaMemsetAsync(b.b_qkv.p, 0, 3 * h->QW * sizeof(float), st));
+      LDMAE_CUDA(cudaMemcpy2DAsync(b.b_qkv.p, h->HW * sizeof(float), data, h->hd * sizeof(float), h->hd * sizeof(float),
+                                   3 * h->c.num_heads, cudaMemcpyDeviceToDevice, st));
+    }
+    else if (sub == "attn.q_norm.weight") rc = copy_f32(b.qw.p, data, numel, h->hd, name, st);
+    else if (sub == "attn.k_norm.weight") rc = copy_f32(b.kw.p, data, numel, h->hd, name, st);
     else if (sub == "attn.proj.weight") rc = pack_bf16(b.w_proj.p, data, D, D, D, numel, name, st);
     else if (sub == "attn.proj.bias") rc = copy_f32(b.b_proj.p, data, numel, D, name, st);
     else if (sub == "mlp.w12.weight") rc = pack_bf16(b.w12.p, data, 2 * h->Hp, D, D, numel, name, st, 1, h->H, 2 * h->H);
@@ -568,7 +608,7 @@ extern "C" int ldmae_dit_finalize(ldmae_dit* h, void* stream) {
   if (h->c.use_rope) expect += 2;
   if ((int)h->loaded.size() != expect)
     return set_error(LDMAE_ERR_STATE, "LightningDiT weights incomplete: %d of %d tensors loaded", (int)h->loaded.size(), expect);
-  if (h->c.use_rope) {
+  if (h->c.use_rope && h->HW == 64) {
     // compact axial table for the QKV epilogue + a check that the loaded [T, 64] buffers really have that structure
     float* maxdiff = h->rope_tab.p + static_cast<size_t>(2) * h->G * 32;
     LDMAE_CUDA(cudaMemsetAsync(maxdiff, 0, sizeof(float), st));
@@ -588,7 +628,7 @@ extern "C" int ldmae_dit_finalize(ldmae_dit* h, void* stream) {
   for (auto& b : h->blk) b.attn_m0_log2 = -1.f;
   static int fixed = -1;
   if (fixed < 0) { const char* e = getenv("LDMAE_ATTN_FIXED_MAX"); fixed = e ? atoi(e) : 1; }
-  if (h->c.use_qknorm && fixed) {
+  if (h->c.use_qknorm && fixed && h->HW == 64) {
     const int depth = h->c.depth;
     std::vector<float> w(static_cast<size_t>(depth) * 128);
     for (int i = 0; i < depth; ++i) {
@@ -695,10 +735,10 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
   for (int i = 0; i < depth; ++i) {
     ProfScope ps(5, st);
     DitBlockW& b = h->blk[i];
-    float* cq = h->cvec_qkv.p + static_cast<size_t>(i) * B * 3 * D;
+    float* cq = h->cvec_qkv.p + static_cast<size_t>(i) * B * 3 * h->QW;
     float* c12 = h->cvec_12.p + static_cast<size_t>(i) * B * 2 * h->Hp;
-    LDMAE_TRY((gemm_store<float, 0>(h->shift_bf16.p + static_cast<size_t>(2 * i) * B * D, D, b.w_qkv.p, D, GemmShape{B, 3 * D, D},
-                                    cq, 3 * D, b.b_qkv.p, st)));
+    LDMAE_TRY((gemm_store<float, 0>(h->shift_bf16.p + static_cast<size_t>(2 * i) * B * D, D, b.w_qkv.p, D, GemmShape{B, 3 * h->QW, D},
+                                    cq, 3 * h->QW, b.b_qkv.p, st)));
     LDMAE_TRY((gemm_store<float, 0>(h->shift_bf16.p + static_cast<size_t>(2 * i + 1) * B * D, D, b.w12.p, D,
                                     GemmShape{B, 2 * h->Hp, D}, c12, 2 * h->Hp, b.b12.p, st)));
   }
@@ -736,23 +776,41 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
     __nv_bfloat16* qkv_i = tr ? tr->QKV.p + static_cast<size_t>(i) * M * 3 * D : h->qkv.p;
     __nv_bfloat16* o_i = tr ? tr->O.p + i * MD : h->obuf.p;
     __nv_bfloat16* hb_i = tr ? tr->HB.p + static_cast<size_t>(i) * M * h->Hp : h->hbuf.p;
-    EpiQKV::Params eq;
-    LDMAE_TRY(make_tmap_out_bf16(&eq.omap, qkv_i, M, 3 * D, 3 * D));
-    eq.has_raw = 0; eq.rawmap = eq.omap;
-    if (tr) {
-      eq.has_raw = 1;
-      LDMAE_TRY(make_tmap_out_bf16(&eq.rawmap, tr->QKR.p + static_cast<size_t>(i) * M * 2 * D, M, 2 * D, 2 * D));
-    }
-    eq.ssq = Ss(2 * i); eq.cvec = h->cvec_qkv.p + static_cast<size_t>(i) * B * 3 * D;
-    eq.qw = c.use_qknorm ? b.qw.p : nullptr; eq.kw = c.use_qknorm ? b.kw.p : nullptr;
-    eq.rope = c.use_rope ? h->rope_tab.p : nullptr; eq.grid = h->G;
-    eq.D = D; eq.rows_per_sample = T; eq.ss_slots = h->SS; eq.inv_D = 1.f / D; eq.eps_row = eps; eq.eps_head = eps;
-    { ProfScope ps(0, st); LDMAE_TRY((gemm_auto<EpiQKV>(As(2 * i), D, b.w_qkv.p, D, GemmShape{M, 3 * D, D}, eq, st))); }
-    LDMAE_DBG_STAGE();
-    {
-      ProfScope ps(1, st);
-      float* lse = tr ? tr->LSE.p + static_cast<size_t>(i) * B * c.num_heads * T : nullptr;
-      LDMAE_TRY(run_attention(qkv_i, 3 * D, o_i, D, B, T, c.num_heads, 0, D, 2 * D, 0.125f, st, lse, b.attn_m0_log2));
+    if (h->HW == 64) {
+      EpiQKV::Params eq;
+      LDMAE_TRY(make_tmap_out_bf16(&eq.omap, qkv_i, M, 3 * D, 3 * D));
+      eq.has_raw = 0; eq.rawmap = eq.omap;
+      if (tr) {
+        eq.has_raw = 1;
+        LDMAE_TRY(make_tmap_out_bf16(&eq.rawmap, tr->QKR.p + static_cast<size_t>(i) * M * 2 * D, M, 2 * D, 2 * D));
+      }
+      eq.ssq = Ss(2 * i); eq.cvec = h->cvec_qkv.p + static_cast<size_t>(i) * B * 3 * D;
+      eq.qw = c.use_qknorm ? b.qw.p : nullptr; eq.kw = c.use_qknorm ? b.kw.p : nullptr;
+      eq.rope = c.use_rope ? h->rope_tab.p : nullptr; eq.grid = h->G;
+      eq.D = D; eq.rows_per_sample = T; eq.ss_slots = h->SS; eq.inv_D = 1.f / D; eq.eps_row = eps; eq.eps_head = eps;
+      { ProfScope ps(0, st); LDMAE_TRY((gemm_auto<EpiQKV>(As(2 * i), D, b.w_qkv.p, D, GemmShape{M, 3 * D, D}, eq, st))); }
+      LDMAE_DBG_STAGE();
+      {
+        ProfScope ps(1, st);
+        float* lse = tr ? tr->LSE.p + static_cast<size_t>(i) * B * c.num_heads * T : nullptr;
+        LDMAE_TRY(run_attention(qkv_i, 3 * D, o_i, D, B, T, c.num_heads, 0, D, 2 * D, 0.125f, st, lse, b.attn_m0_log2));
+      }
+    } else {
+      // wider heads (XL, head_dim 72): 128-column head slots, generic epilogue and the one-tile attention kernel
+      EpiQKVWide::Params eq;
+      LDMAE_TRY(make_tmap_out_bf16(&eq.omap, qkv_i, M, 3 * h->QW, 3 * h->QW));
+      eq.ssq = Ss(2 * i); eq.cvec = h->cvec_qkv.p + static_cast<size_t>(i) * B * 3 * h->QW;
+      eq.qw = c.use_qknorm ? b.qw.p : nullptr; eq.kw = c.use_qknorm ? b.kw.p : nullptr;
+      eq.rope_cos = c.use_rope ? h->rope_cos.p : nullptr; eq.rope_sin = c.use_rope ? h->rope_sin.p : nullptr;
+      eq.section = h->QW; eq.hd = h->hd; eq.rows_per_sample = T; eq.ss_slots = h->SS;
+      eq.inv_D = 1.f / D; eq.eps_row = eps; eq.eps_head = eps;
+      { ProfScope ps(0, st); LDMAE_TRY((gemm_auto<EpiQKVWide>(As(2 * i), D, b.w_qkv.p, D, GemmShape{M, 3 * h->QW, D}, eq, st))); }
+      LDMAE_DBG_STAGE();
+      {
+        ProfScope ps(1, st);
+        LDMAE_TRY(run_attention_hd128(qkv_i, 3 * h->QW, o_i, D, B, T, c.num_heads, h->hd, 0, h->QW, 2 * h->QW,
+                                      1.0f / sqrtf(static_cast<float>(h->hd)), st));
+      }
     }
     LDMAE_DBG_STAGE();
     {
@@ -1251,6 +1309,12 @@ extern "C" int ldmae_gemm_residual(const void* a, const void* w, const float* bi
 extern "C" int ldmae_attention(const void* qkv, void* out, int32_t B, int32_t T, int32_t H, float scale, void* stream) {
   LDMAE_TRY(require_sm100());
   return run_attention(qkv, 3 * H * 64, out, H * 64, B, T, H, 0, H * 64, 2 * H * 64, scale, static_cast<cudaStream_t>(stream));
+}
+extern "C" int ldmae_attention_wide(const void* qkv, void* out, int32_t B, int32_t T, int32_t H, int32_t hd, float scale,
+                                    void* stream) {
+  LDMAE_TRY(require_sm100());
+  return run_attention_hd128(qkv, 3 * H * 128, out, H * hd, B, T, H, hd, 0, H * 128, 2 * H * 128, scale,
+                             static_cast<cudaStream_t>(stream));
 }
 extern "C" int ldmae_attention_bounded(const void* qkv, void* out, float* lse2, int32_t B, int32_t T, int32_t H, float scale,
                                        float m0_log2, void* stream) {

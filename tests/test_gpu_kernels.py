@@ -125,3 +125,22 @@ def test_attention_bounded_scores_matches_softmax(B, T, H, wide, monkeypatch):
     torch.cuda.synchronize()
     assert rel_err(out.float().cpu(), ref) < 1e-2
     torch.testing.assert_close(lse[: B * H * T].cpu().reshape(B, H, T), torch.logsumexp(sc, -1) * 1.4426950408889634, rtol=0, atol=2e-2)
+
+
+@pytest.mark.parametrize("B,T,H,hd", [(2, 256, 2, 72), (1, 1024, 3, 72), (2, 200, 2, 128), (1, 64, 1, 80)])
+def test_attention_wide_heads_matches_softmax(B, T, H, hd):
+    """head_dim in (64, 128] (LightningDiT-XL: 72): 128-column head slots, one-tile kernel (attention_hd128_sm100.cuh)."""
+    from gpu_util import rel_err
+    from ldmae_b200 import _lib
+    g = torch.Generator().manual_seed(B * 7 + T + hd)
+    x = torch.zeros(B * T, 3, H, 128)
+    x[..., :hd] = torch.randn(B * T, 3, H, hd, generator=g)
+    qkv = x.reshape(B * T, 3 * H * 128).to(torch.bfloat16)
+    q, k, v = qkv.float().reshape(B, T, 3, H, 128)[..., :hd].permute(2, 0, 3, 1, 4)
+    scale = hd ** -0.5
+    ref = (torch.softmax((q @ k.transpose(-1, -2)) * scale, dim=-1) @ v).transpose(1, 2).reshape(B * T, H * hd)
+    out = torch.empty(B * T, H * hd, device="cuda", dtype=torch.bfloat16)
+    _lib.check(_lib.lib().ldmae_attention_wide(_lib.ptr(qkv.cuda()), _lib.ptr(out), B, T, H, hd, float(scale), _lib.stream_ptr()), "wide")
+    torch.cuda.synchronize()
+    err = rel_err(out.float().cpu(), ref)
+    assert err < 1e-2, f"wide attention hd {hd}: rel err {err}"

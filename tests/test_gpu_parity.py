@@ -220,3 +220,32 @@ def test_sampling_job_vs_oracle():
     u8 = vae.decode_to_images(lat)
     diff = np.abs(u8.astype(np.int32) - u8_ref.astype(np.int32))
     assert (diff <= 2).mean() > 0.98
+
+
+def test_dit_xl_head_dim_72_forward_and_sampler_vs_oracle():
+    """LightningDiT-XL geometry (width 1152, 16 heads, head_dim 72; lightningdit.py:509-515) at depth 2: forward,
+    forward_with_cfg and a short Euler sampler against the CPU oracle (the wide-head kernels; inference path)."""
+    from ldmae_b200.models.lightningdit import LightningDiT
+    from ldmae_b200.transport import Sampler, create_transport
+    spec = O.DiTSpec(depth=2, hidden_size=1152, patch_size=1, num_heads=16, input_size=16, in_channels=16, num_classes=10)
+    m = LightningDiT(input_size=16, patch_size=1, in_channels=16, hidden_size=1152, depth=2, num_heads=16, num_classes=10,
+                     use_qknorm=True, use_swiglu=True, use_rope=True, use_rmsnorm=True)
+    sd = O.synth_dit_state(spec, 91)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    g = torch.Generator().manual_seed(4)
+    n = 3
+    x = torch.randn(2 * n, 16, 16, 16, generator=g); t = torch.rand(2 * n, generator=g); y = torch.randint(0, 10, (2 * n,), generator=g)
+    out = m(x.cuda(), t.cuda(), y.cuda())
+    ref = O.dit_forward(sd, spec, x, t, y)
+    assert _rel(out, ref) < FWD_TOL
+    ycfg = torch.cat([y[:n], torch.full((n,), 10)])
+    z = torch.cat([x[:n], x[:n]], 0)
+    smp = Sampler(create_transport("Linear", "velocity", None, None, None))
+    fn = smp.sample_ode(sampling_method="euler", num_steps=5, atol=1e-6, rtol=1e-3, reverse=False, timestep_shift=0.3)
+    kw = dict(y=ycfg.cuda(), cfg_scale=4.0, cfg_interval=True, cfg_interval_start=0.10)
+    ours = fn(z.cuda(), m.forward_with_cfg, **kw)[-1]
+    ref_fn = lambda xx, tt, **k: O.dit_forward_with_cfg(sd, spec, xx, tt, **k)
+    want = O.sample_ode(ref_fn, z, sampling_method="euler", num_steps=5, timestep_shift=0.3, y=ycfg, cfg_scale=4.0,
+                        cfg_interval=True, cfg_interval_start=0.10)[-1]
+    assert _rel(ours, want) < FINAL_TOL
