@@ -44,6 +44,19 @@ def dit_flops_per_sample_forward(depth=12, D=768, T=1024, H=2048, C=16):
     return per_block, total
 
 
+MODEL_GEOMETRY = {   # registry lightningdit.py:498-531: (depth, width, heads, patch)
+    "LightningDiT-B/1": (12, 768, 12, 1), "LightningDiT-L/2": (24, 1024, 16, 2), "LightningDiT-XL/1": (28, 1152, 16, 1),
+    "LightningDiT-XL/2": (28, 1152, 16, 2), "LightningDiT-1p0B/1": (24, 1536, 24, 1), "LightningDiT-1p6B/1": (28, 1792, 28, 1),
+}
+
+
+def model_flops(args):
+    depth, D, _, patch = MODEL_GEOMETRY[args.model]
+    T = (args.input_size // patch) ** 2
+    H = int(2 / 3 * 4 * D)
+    return dit_flops_per_sample_forward(depth=depth, D=D, T=T, H=H, C=16 * patch * patch)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -151,10 +164,11 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args):
-    return {"workload": f"LightningDiT-B/1 ImageNet-256 class-conditional sampling: {args.num_steps}-point Euler ODE "
+    return {"workload": f"{args.model} ImageNet-{8 * args.input_size} class-conditional sampling: {args.num_steps}-point Euler ODE "
                         f"({args.num_steps - 1} evaluations on the CFG-doubled batch), cfg_scale 10, cfg_interval_start 0.10, "
                         f"timestep_shift 0.3, VMAE f8d16 decode to uint8; batch {args.batch}/GPU",
-            "batch_per_gpu": args.batch, "num_steps": args.num_steps, "latent": "32x32x16", "image": "256x256x3",
+            "batch_per_gpu": args.batch, "num_steps": args.num_steps, "latent": f"{args.input_size}x{args.input_size}x16",
+            "image": f"{8 * args.input_size}x{8 * args.input_size}x3",
             "parallelism": f"batch-sharded x{args.gpus} (no collective in the loop)",
             "l2": "inputs larger than L2: each evaluation streams >6 GB of activations (L2 = 126 MB)"}
 
@@ -170,11 +184,11 @@ def measure_train(args, dev, rank, world):
     from ldmae_b200.pipeline import build_sampling_models
     from ldmae_b200.training import FusedTrainer
     B = args.train_batch
-    model, _ = build_sampling_models(dev, seed=0)
+    model, _ = build_sampling_models(dev, seed=0, model_name=args.model, input_size=args.input_size, img_size=8 * args.input_size)
     model.train()
     trainer = FusedTrainer(model, lr=2e-4, betas=(0.9, 0.95), weight_decay=0.0, ema_decay=0.9999)
     g = torch.Generator().manual_seed(100 + rank)
-    x_host = torch.randn(B, 16, 32, 32, generator=g).pin_memory()
+    x_host = torch.randn(B, 16, args.input_size, args.input_size, generator=g).pin_memory()
     y_host = torch.randint(0, 1000, (B,), generator=g).pin_memory()
     loss_host = torch.empty(B).pin_memory()
 
@@ -209,7 +223,7 @@ def measure_train(args, dev, rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t[0])
     ms_step = ms / args.train_steps
-    _, fwd = dit_flops_per_sample_forward()
+    _, fwd = model_flops(args)
     pk = peaks()
     tfl = 3 * fwd * B / (ms_step / 1e3) / 1e12
     del trainer, model
@@ -249,13 +263,14 @@ def run_gpu(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    model, vae = build_sampling_models(dev, seed=0)
+    model, vae = build_sampling_models(dev, seed=0, model_name=args.model, input_size=args.input_size, img_size=8 * args.input_size)
     job = SamplingJob(model, vae, num_steps=args.num_steps, cfg_scale=10.0, cfg_interval_start=0.10, timestep_shift=0.3)
     n = args.batch
     g = torch.Generator().manual_seed(0 * world + rank)                  # inference.py:87
-    z_host = torch.randn(n, 16, 32, 32, generator=g).pin_memory()
+    S = args.input_size
+    z_host = torch.randn(n, 16, S, S, generator=g).pin_memory()
     y_host = torch.randint(0, 1000, (n,), generator=g).pin_memory()
-    out_host = torch.empty(n, 256, 256, 3, dtype=torch.uint8).pin_memory()
+    out_host = torch.empty(n, 8 * S, 8 * S, 3, dtype=torch.uint8).pin_memory()
     z_dev, y_dev = z_host.to(dev), y_host.to(dev)
 
     for _ in range(args.warmup):
@@ -326,7 +341,7 @@ def run_gpu(args, rank, world, local_rank):
 
     # ---- roofline of the dominant kernel class ----------------------------------------------------------------------
     pk = peaks()
-    per_block, fwd_flops = dit_flops_per_sample_forward()
+    per_block, fwd_flops = model_flops(args)
     Bf = 2 * n
     gemm_classes = {k: v for k, v in prof.items() if k in per_block and v[1] > 0}
     dom = max(gemm_classes, key=lambda k: gemm_classes[k][0]) if gemm_classes else None
@@ -383,6 +398,9 @@ def main():
     ap.add_argument("--impl", default="ldmae_b200", choices=["ldmae_b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step (BASELINE configs[1]: 256)")
     ap.add_argument("--num-steps", type=int, default=250, help="ODE grid points (250 = 249 evaluations)")
+    ap.add_argument("--model", default="LightningDiT-B/1", choices=sorted(MODEL_GEOMETRY),
+                    help="registry entry (headline: B/1; XL/1 with --input-size 64 is BASELINE configs[4], sampling only)")
+    ap.add_argument("--input-size", type=int, default=32, help="latent side (32 = 256 px, 64 = 512 px)")
     ap.add_argument("--cpu-images", type=int, default=2)
     ap.add_argument("--cpu-points", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -169,6 +169,12 @@ int ldmae_attention_lse(const void* qkv_bf16, void* out_bf16, float* lse2, int32
  * (head_dim `hd` real columns, zeros behind), out [B*T, H*hd] bf16 dense.  hd: multiple of 8, <= 128. */
 int ldmae_attention_wide(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t T, int32_t H, int32_t hd, float scale,
                          void* stream);
+/* Training forms of the wide-head attention: forward that also writes lse2 [B,H,T (+64)], and its gradient
+ * (dqkv in the 128-column slot layout, padding columns zero; delta_ws: 2 * (B*H*T + 64) floats; T % 4 == 0). */
+int ldmae_attention_wide_lse(const void* qkv_bf16, void* out_bf16, float* lse2, int32_t B, int32_t T, int32_t H, int32_t hd,
+                             float scale, void* stream);
+int ldmae_attention_wide_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse2, float* delta_ws,
+                             void* dqkv_bf16, int32_t B, int32_t T, int32_t H, int32_t hd, float scale, void* stream);
 /* The same attention when the scores are known to be bounded, |q.k * scale| * log2(e) <= m0_log2 (qk-normed heads:
  * 8 * log2(e) * max|q_norm.w| * max|k_norm.w|): the bound replaces the running row maximum (no max pass, no rescale).
  * lse2 may be NULL. */

@@ -28,11 +28,19 @@
 namespace ldmae {
 
 constexpr int kAbThreads = 640;        // 4 control warps + 16 row warps (four 16-column quarters per TMEM lane quarter)
-constexpr int kAbStages = 4;
-constexpr int kAbRTile = 128 * 128;     // 128 rows x 64 bf16
-constexpr int kAbCTile = 64 * 128;      // 64 rows x 64 bf16
-constexpr int kAbStageBytes = 2 * kAbCTile + 512;       // C_a, C_b, lse2[64], delta[64]
-constexpr int kAbSmemBytes = 1024 + 2 * kAbRTile + kAbStages * kAbStageBytes + 256;
+// HD = head width in the qkv buffer: 64 (tuned path) or 128 (heads wider than 64, zero padded: LightningDiT-XL's 72).
+template <int HD>
+struct AbGeo {
+  static constexpr int kAtoms = HD / 64;                  // 64-column swizzle atoms per tile row
+  static constexpr int kStages = HD == 64 ? 4 : 3;
+  static constexpr int kRAtom = 128 * 128;                // 128 rows x 64 bf16
+  static constexpr int kCAtom = 64 * 128;                 // 64 rows x 64 bf16
+  static constexpr int kRTile = kAtoms * kRAtom;
+  static constexpr int kCTile = kAtoms * kCAtom;
+  static constexpr int kStageBytes = 2 * kCTile + 512;    // C_a, C_b, lse2[64], delta[64]
+  static constexpr int kSmemBytes = 1024 + 2 * kRTile + kStages * kStageBytes + 256;
+  static constexpr int kAcc1 = 256, kAcc2 = 256 + HD;     // TMEM columns of the accumulators
+};
 
 // Optional phase tracing of CTA (0,0,0) (debug builds: -DLDMAE_ATTN_TRACE): clock64 stamps per column block;
 // trace[i][0..3] = MMA warp (c_full seen, scores issued, pd_full seen, accumulations issued), [4..7] = row warp 4
@@ -51,6 +59,7 @@ struct AttnBwdParams {
   __nv_bfloat16* dqkv;  // [B*T, ld] output, same column layout as qkv
   int T, H, ld;
   int q_col, k_col, v_col;
+  int hd;               // real head_dim (<= HD): columns beyond it are stored as zeros
   float scale, scale_log2;
 };
 
@@ -60,10 +69,13 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
                : "memory");
 }
 
-template <bool kKV>
+template <bool kKV, int HD = 64>
 __global__ void __launch_bounds__(kAbThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_constant__ CUtensorMap tm_qkv_c,
                 const __grid_constant__ CUtensorMap tm_do_r, const __grid_constant__ CUtensorMap tm_do_c, const AttnBwdParams p) {
+  using Geo = AbGeo<HD>;
+  constexpr int kAbStages = Geo::kStages, kAbRTile = Geo::kRTile, kAbCTile = Geo::kCTile, kAbStageBytes = Geo::kStageBytes;
+  constexpr int kAtoms = Geo::kAtoms;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sRa = smem;                       // dQ: Q rows    | dKV: K rows
@@ -105,12 +117,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(r_full, 2 * kAbRTile);
-      if constexpr (kKV) {
-        tma_load_2d(&tm_qkv_r, r_full, sRa, p.k_col + head * 64, row_base + rblk * 128);
-        tma_load_2d(&tm_qkv_r, r_full, sRb, p.v_col + head * 64, row_base + rblk * 128);
-      } else {
-        tma_load_2d(&tm_qkv_r, r_full, sRa, p.q_col + head * 64, row_base + rblk * 128);
-        tma_load_2d(&tm_do_r, r_full, sRb, head * 64, row_base + rblk * 128);
+      // (dO is dense [B*T, H*hd]: for hd < HD its second atom runs into the next head's columns -- harmless: those columns
+      //  only meet the zero padding of V in dP, and the matching dV columns are stored as zeros)
+      for (int a = 0; a < kAtoms; ++a) {
+        if constexpr (kKV) {
+          tma_load_2d(&tm_qkv_r, r_full, sRa + a * Geo::kRAtom, p.k_col + head * HD + a * 64, row_base + rblk * 128);
+          tma_load_2d(&tm_qkv_r, r_full, sRb + a * Geo::kRAtom, p.v_col + head * HD + a * 64, row_base + rblk * 128);
+        } else {
+          tma_load_2d(&tm_qkv_r, r_full, sRa + a * Geo::kRAtom, p.q_col + head * HD + a * 64, row_base + rblk * 128);
+          tma_load_2d(&tm_do_r, r_full, sRb + a * Geo::kRAtom, head * p.hd + a * 64, row_base + rblk * 128);
+        }
       }
       int stage = 0; uint32_t phase = 0;
       for (int i = 0; i < ncb; ++i) {
@@ -118,14 +134,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
         uint8_t* st = sC + stage * kAbStageBytes;
         if constexpr (kKV) {
           mbar_expect_tx(&c_full[stage], 2 * kAbCTile + 512);
-          tma_load_2d(&tm_qkv_c, &c_full[stage], st, p.q_col + head * 64, row_base + i * 64);
-          tma_load_2d(&tm_do_c, &c_full[stage], st + kAbCTile, head * 64, row_base + i * 64);
+          for (int a = 0; a < kAtoms; ++a) {
+            tma_load_2d(&tm_qkv_c, &c_full[stage], st + a * Geo::kCAtom, p.q_col + head * HD + a * 64, row_base + i * 64);
+            tma_load_2d(&tm_do_c, &c_full[stage], st + kAbCTile + a * Geo::kCAtom, head * p.hd + a * 64, row_base + i * 64);
+          }
           bulk_load_1d(st + 2 * kAbCTile, p.nlse2 + vec_base + i * 64, 256, &c_full[stage]);
           bulk_load_1d(st + 2 * kAbCTile + 256, p.delta + vec_base + i * 64, 256, &c_full[stage]);
         } else {
           mbar_expect_tx(&c_full[stage], 2 * kAbCTile);
-          tma_load_2d(&tm_qkv_c, &c_full[stage], st, p.k_col + head * 64, row_base + i * 64);
-          tma_load_2d(&tm_qkv_c, &c_full[stage], st + kAbCTile, p.v_col + head * 64, row_base + i * 64);
+          for (int a = 0; a < kAtoms; ++a) {
+            tma_load_2d(&tm_qkv_c, &c_full[stage], st + a * Geo::kCAtom, p.k_col + head * HD + a * 64, row_base + i * 64);
+            tma_load_2d(&tm_qkv_c, &c_full[stage], st + kAbCTile + a * Geo::kCAtom, p.v_col + head * HD + a * 64, row_base + i * 64);
+          }
         }
         if (++stage == kAbStages) { stage = 0; phase ^= 1; }
       }
@@ -134,24 +154,40 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
     // MMA issuer.  The whole warp runs the control flow (so that descriptors and TMEM addresses stay warp-uniform and live in
     // uniform registers); only the tcgen05 instructions themselves are issued by one elected lane.
     constexpr uint32_t idesc_ss = umma_idesc_bf16(128, 64, false, false);
-    constexpr uint32_t idesc_ts = umma_idesc_bf16(128, 64, false, true);    // B = column tile read MN-major (d contiguous)
+    constexpr uint32_t idesc_ts = umma_idesc_bf16(128, HD, false, true);    // B = column tile read MN-major (d contiguous)
     const bool issuer = elect_one();
     // one descriptor per tile; K-steps advance the 14-bit start-address field: +2 (32 B) K-major, +128 (2 KB) MN-major.
     // (The leading-dimension offset is unused in both forms: a single 64-wide swizzle atom along the other dimension.)
-    const uint64_t d_c0 = umma_smem_desc_sw128(smem_u32(sC), 1024, 0);
+    // (MN-major form: LBO = distance between the 64-wide atoms of d; unused when HD = 64)
+    const uint64_t d_c0 = umma_smem_desc_sw128(smem_u32(sC), 1024, Geo::kCAtom);
+    const uint64_t d_ra = umma_smem_desc_sw128(smem_u32(sRa), 1024, 0), d_rb = umma_smem_desc_sw128(smem_u32(sRb), 1024, 0);
     auto issue_scores = [&](int stage, int buf) {
       const uint64_t d_ca = d_c0 + static_cast<uint64_t>((stage * kAbStageBytes) >> 4), d_cb = d_ca + (kAbCTile >> 4);
       const uint32_t td = tmem_base + buf * 128;
       if (issuer) {
+        if constexpr (HD == 64) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ts(td, tmem_base + 384 + k * 8, d_ca + 2 * k, idesc_ss, k != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_bf16_ts(td, tmem_base + 384 + k * 8, d_ca + 2 * k, idesc_ss, k != 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ts(td + 64, tmem_base + 416 + k * 8, d_cb + 2 * k, idesc_ss, k != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_bf16_ts(td + 64, tmem_base + 416 + k * 8, d_cb + 2 * k, idesc_ss, k != 0 ? 1u : 0u);
+        } else {
+          // wide heads: TMEM is full (scores 256 + two 128-wide accumulators), both operands come from shared memory
+#pragma unroll
+          for (int a = 0; a < kAtoms; ++a)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16<1>(td, d_ra + a * (Geo::kRAtom >> 4) + 2 * k, d_ca + a * (Geo::kCAtom >> 4) + 2 * k, idesc_ss, (a | k) != 0 ? 1u : 0u);
+#pragma unroll
+          for (int a = 0; a < kAtoms; ++a)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16<1>(td + 64, d_rb + a * (Geo::kRAtom >> 4) + 2 * k, d_cb + a * (Geo::kCAtom >> 4) + 2 * k, idesc_ss, (a | k) != 0 ? 1u : 0u);
+        }
         umma_commit<1>(&sd_full[buf]);
       }
       __syncwarp();
     };
-    mbar_wait(ra_ready, 0, 20);
+    if constexpr (HD == 64) mbar_wait(ra_ready, 0, 20); else mbar_wait(r_full, 0, 20);
     tc_fence_after();
     int stage = 0; uint32_t phase = 0;                 // ring position of block i
     mbar_wait(&c_full[0], 0, 21);
@@ -177,10 +213,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       if (issuer) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)     // 4 x 16 columns of the block; A = dS: 16 bf16 = 8 TMEM columns at column 16 k
-          umma_bf16_ts(tmem_base + 256, tb + 64 + k * 16, d_ca + 128 * k, idesc_ts, k != 0 ? 1u : acc_first);
+          umma_bf16_ts(tmem_base + Geo::kAcc1, tb + 64 + k * 16, d_ca + 128 * k, idesc_ts, k != 0 ? 1u : acc_first);
         if constexpr (kKV) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ts(tmem_base + 320, tb + k * 16, d_cb + 128 * k, idesc_ts, k != 0 ? 1u : acc_first);
+          for (int k = 0; k < 4; ++k) umma_bf16_ts(tmem_base + Geo::kAcc2, tb + k * 16, d_cb + 128 * k, idesc_ts, k != 0 ? 1u : acc_first);
         }
         umma_commit<1>(&c_empty[stage]);
         if (i == ncb - 1) umma_commit<1>(acc_done);
@@ -202,7 +238,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       }
     }
     const float2 sl2 = make_float2(p.scale_log2, p.scale_log2), sc2 = make_float2(p.scale, p.scale);
-    if (cq < 2) {
+    if (HD == 64 && cq < 2) {
       // The row operands (Q | K and dO | V rows of this CTA) are the A operand of every score product: copy them once
       // from their TMA tiles into TMEM (bf16 pairs, one row per lane), so that the score MMAs read only the 2 KB column
       // tile from shared memory per instruction (an SS product of this shape is shared-memory-bandwidth bound).
@@ -278,24 +314,28 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       if (lane == 0) mbar_arrive(&pd_full[i & 1]);
       if (++stage == kAbStages) { stage = 0; cphase ^= 1; }
     }
-    // epilogue: accumulators -> bf16 rows of dqkv; this warp stores columns [16 cq, 16 cq + 16) of each accumulator
+    // epilogue: accumulators -> bf16 rows of dqkv; this warp stores columns [HD/4 * cq, HD/4 * (cq + 1)) of each accumulator
     // (the tcgen05.ld is warp-collective: only the stores are predicated)
     mbar_wait(acc_done, 0, 31);
     __syncwarp();
     tc_fence_after();
+    constexpr int kEC = HD / 4;                         // columns per warp: 16 or 32
 #pragma unroll
     for (int a = 0; a < (kKV ? 2 : 1); ++a) {
-      const int col = (kKV ? (a == 0 ? p.k_col : p.v_col) : p.q_col) + head * 64 + cq * 16;
+      const int col = (kKV ? (a == 0 ? p.k_col : p.v_col) : p.q_col) + head * HD + cq * kEC;
       __nv_bfloat16* dst = p.dqkv + static_cast<size_t>(row_base + min(row, p.T - 1)) * p.ld + col;
-      float o[16];
-      tmem_ld16(tmem_base + lane_addr + 256 + a * 64 + cq * 16, o);
+      float o[kEC];
+      const uint32_t ta = tmem_base + lane_addr + (a == 0 ? Geo::kAcc1 : Geo::kAcc2) + cq * kEC;
+      if constexpr (kEC == 16) tmem_ld16(ta, o); else tmem_ld32(ta, o);
       tmem_ld_wait();
       if (row < p.T) {
 #pragma unroll
-        for (int q = 0; q < 2; ++q)
-          *reinterpret_cast<uint4*>(dst + q * 8) =
+        for (int q = 0; q < kEC / 8; ++q) {
+          const bool real = cq * kEC + q * 8 < p.hd;    // head_dim is a multiple of 8: whole 16-byte groups are real or padding
+          *reinterpret_cast<uint4*>(dst + q * 8) = real ?
               make_uint4(pack_bf16x2(o[8 * q], o[8 * q + 1]), pack_bf16x2(o[8 * q + 2], o[8 * q + 3]),
-                         pack_bf16x2(o[8 * q + 4], o[8 * q + 5]), pack_bf16x2(o[8 * q + 6], o[8 * q + 7]));
+                         pack_bf16x2(o[8 * q + 4], o[8 * q + 5]), pack_bf16x2(o[8 * q + 6], o[8 * q + 7])) : make_uint4(0u, 0u, 0u, 0u);
+        }
       }
     }
   }
@@ -307,19 +347,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
 }
 
 // Row statistics of the backward: delta[b,h,t] = scale * sum_d dO[t,h,d] * O[t,h,d] and nlse2 = -lse2 (both in the form the
-// packed fma of the kernels above consumes).  One warp per token row: lanes walk the row, heads are 64 wide.
+// packed fma of the kernels above consumes).  One warp per token row: lanes walk a head (hd <= 128, even).
 __global__ void attn_delta_kernel(float* __restrict__ delta, float* __restrict__ nlse2, const float* __restrict__ lse2,
                                   const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* __restrict__ O, int B, int T, int H,
-                                  float scale) {
+                                  int hd, float scale) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= B * T) return;
   const int b = row / T, t = row % T;
-  const size_t base = static_cast<size_t>(row) * H * 64;
+  const size_t base = static_cast<size_t>(row) * H * hd;
   for (int h = 0; h < H; ++h) {
-    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(dO + base + h * 64 + lane * 2);
-    const __nv_bfloat162 o = *reinterpret_cast<const __nv_bfloat162*>(O + base + h * 64 + lane * 2);
-    float s = __bfloat162float(a.x) * __bfloat162float(o.x) + __bfloat162float(a.y) * __bfloat162float(o.y);
+    float s = 0.f;
+    for (int d = lane * 2; d < hd; d += 64) {
+      const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(dO + base + h * hd + d);
+      const __nv_bfloat162 o = *reinterpret_cast<const __nv_bfloat162*>(O + base + h * hd + d);
+      s += __bfloat162float(a.x) * __bfloat162float(o.x) + __bfloat162float(a.y) * __bfloat162float(o.y);
+    }
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
     if (lane == 0) {

@@ -251,38 +251,49 @@ static int run_attention_hd128(const void* qkv, int ldq, void* out, int ldo, int
   return LDMAE_OK;
 }
 
-// Backward of run_attention: dqkv [B*T, ldq] (same column layout as qkv) from dO [B*T, ldo], the forward output o,
-// the forward's lse2 [B,H,T] (padded by 64 floats) and a statistics workspace of 2 * (B*H*T + 64) floats.
-static int run_attention_bwd(const void* qkv, int ldq, const void* o, const void* d_o, int ldo, const float* lse2, float* delta,
-                             void* dqkv, int B, int T, int H, int q_col, int k_col, int v_col, float scale, cudaStream_t st) {
-  LDMAE_REQUIRE(ldo == H * 64, "attention backward expects a dense [B*T, H*64] output gradient");
+// Backward of run_attention / run_attention_hd128: dqkv [B*T, ldq] (same column layout as qkv, head slots of HW columns)
+// from dO [B*T, H*hd] (dense), the forward output o, the forward's lse2 [B,H,T] (padded by 64 floats) and a statistics
+// workspace of 2 * (B*H*T + 64) floats.
+template <int HW>
+static int run_attention_bwd_t(const void* qkv, int ldq, const void* o, const void* d_o, int ldo, const float* lse2, float* delta,
+                               void* dqkv, int B, int T, int H, int hd, int q_col, int k_col, int v_col, float scale,
+                               cudaStream_t st) {
+  LDMAE_REQUIRE(ldo == H * hd, "attention backward expects a dense [B*T, H*head_dim] output gradient");
   LDMAE_REQUIRE(T % 4 == 0, "attention backward: T must be a multiple of 4 (16-byte aligned statistics rows)");
+  LDMAE_REQUIRE(hd <= HW && hd % 8 == 0, "attention backward: head_dim %d does not fit the %d-column head slot", hd, HW);
   CUtensorMap tqr, tqc, tdr, tdc;
   LDMAE_TRY(make_tmap_bf16(&tqr, qkv, B * T, ldq, ldq, 128));
   LDMAE_TRY(make_tmap_bf16(&tqc, qkv, B * T, ldq, ldq, 64));
   LDMAE_TRY(make_tmap_bf16(&tdr, d_o, B * T, ldo, ldo, 128));
   LDMAE_TRY(make_tmap_bf16(&tdc, d_o, B * T, ldo, ldo, 64));
+  constexpr int kSmem = AbGeo<HW>::kSmemBytes;
   static bool attr = false;
   if (!attr) {
-    LDMAE_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAbSmemBytes));
-    LDMAE_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAbSmemBytes));
+    LDMAE_CUDA((cudaFuncSetAttribute(attn_bwd_kernel<false, HW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)));
+    LDMAE_CUDA((cudaFuncSetAttribute(attn_bwd_kernel<true, HW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)));
     attr = true;
   }
   float* nlse2 = delta + static_cast<size_t>(B) * H * T + 64;       // second half of the workspace
   attn_delta_kernel<<<cdiv(static_cast<size_t>(B) * T, 8), 256, 0, st>>>(delta, nlse2, lse2, static_cast<const __nv_bfloat16*>(d_o),
-                                                                         static_cast<const __nv_bfloat16*>(o), B, T, H, scale);
+                                                                         static_cast<const __nv_bfloat16*>(o), B, T, H, hd, scale);
   LDMAE_LAUNCH_CHECK();
   AttnBwdParams p;
   p.trace = g_attn_trace;
   p.nlse2 = nlse2; p.delta = delta; p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
-  p.T = T; p.H = H; p.ld = ldq; p.q_col = q_col; p.k_col = k_col; p.v_col = v_col;
+  p.T = T; p.H = H; p.ld = ldq; p.q_col = q_col; p.k_col = k_col; p.v_col = v_col; p.hd = hd;
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid(cdiv(T, 128), H, B);
-  attn_bwd_kernel<true><<<grid, kAbThreads, kAbSmemBytes, st>>>(tqr, tqc, tdr, tdc, p);
+  attn_bwd_kernel<true, HW><<<grid, kAbThreads, kSmem, st>>>(tqr, tqc, tdr, tdc, p);
   LDMAE_LAUNCH_CHECK();
-  attn_bwd_kernel<false><<<grid, kAbThreads, kAbSmemBytes, st>>>(tqr, tqc, tdr, tdc, p);
+  attn_bwd_kernel<false, HW><<<grid, kAbThreads, kSmem, st>>>(tqr, tqc, tdr, tdc, p);
   LDMAE_LAUNCH_CHECK();
   return LDMAE_OK;
+}
+static int run_attention_bwd(const void* qkv, int ldq, const void* o, const void* d_o, int ldo, const float* lse2, float* delta,
+                             void* dqkv, int B, int T, int H, int q_col, int k_col, int v_col, float scale, cudaStream_t st,
+                             int hd = 64, int HW = 64) {
+  if (HW == 64) return run_attention_bwd_t<64>(qkv, ldq, o, d_o, ldo, lse2, delta, dqkv, B, T, H, hd, q_col, k_col, v_col, scale, st);
+  return run_attention_bwd_t<128>(qkv, ldq, o, d_o, ldo, lse2, delta, dqkv, B, T, H, hd, q_col, k_col, v_col, scale, st);
 }
 
 // C[N1,N2] (fp32, leading dimension ldc) += alpha * sum_m p[m,N1] * q[m,N2]   (weight gradients; see gemm_wgrad_sm100.cuh)
@@ -1309,6 +1320,18 @@ extern "C" int ldmae_gemm_residual(const void* a, const void* w, const float* bi
 extern "C" int ldmae_attention(const void* qkv, void* out, int32_t B, int32_t T, int32_t H, float scale, void* stream) {
   LDMAE_TRY(require_sm100());
   return run_attention(qkv, 3 * H * 64, out, H * 64, B, T, H, 0, H * 64, 2 * H * 64, scale, static_cast<cudaStream_t>(stream));
+}
+extern "C" int ldmae_attention_wide_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, float* delta_ws,
+                                        void* dqkv, int32_t B, int32_t T, int32_t H, int32_t hd, float scale, void* stream) {
+  LDMAE_TRY(require_sm100());
+  return run_attention_bwd(qkv, 3 * H * 128, out, dout, H * hd, lse2, delta_ws, dqkv, B, T, H, 0, H * 128, 2 * H * 128, scale,
+                           static_cast<cudaStream_t>(stream), hd, 128);
+}
+extern "C" int ldmae_attention_wide_lse(const void* qkv, void* out, float* lse2, int32_t B, int32_t T, int32_t H, int32_t hd,
+                                        float scale, void* stream) {
+  LDMAE_TRY(require_sm100());
+  return run_attention_hd128(qkv, 3 * H * 128, out, H * hd, B, T, H, hd, 0, H * 128, 2 * H * 128, scale,
+                             static_cast<cudaStream_t>(stream), lse2);
 }
 extern "C" int ldmae_attention_wide(const void* qkv, void* out, int32_t B, int32_t T, int32_t H, int32_t hd, float scale,
                                     void* stream) {

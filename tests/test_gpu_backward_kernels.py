@@ -92,3 +92,40 @@ def test_attention_backward(B, T, H, scale):
     for i, name in enumerate(("dq", "dk", "dv")):
         err = rel_err(got[:, i], ref_d[:, i])
         assert err < 2e-2, f"attention backward {name} B{B} T{T} H{H}: rel err {err}"
+
+
+@pytest.mark.parametrize("B,T,H,hd", [(2, 256, 2, 72), (1, 1024, 2, 72), (2, 136, 1, 128), (1, 64, 2, 80)])
+def test_attention_backward_wide_heads(B, T, H, hd):
+    """head_dim in (64, 128] (LightningDiT-XL: 72): 128-column head slots in qkv / dqkv, dense [B*T, H*hd] o and do."""
+    from gpu_util import rel_err
+    from ldmae_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(B * 100 + T + hd)
+    x = torch.zeros(B * T, 3, H, 128)
+    x[..., :hd] = torch.randn(B * T, 3, H, hd, generator=g)
+    qkv = x.reshape(B * T, 3 * H * 128).to(torch.bfloat16)
+    dout = torch.randn(B * T, H * hd, generator=g).to(torch.bfloat16)
+    scale = hd ** -0.5
+    xr = qkv.float().reshape(B * T, 3, H, 128)[..., :hd].clone().requires_grad_(True)
+    q, k, v = xr.reshape(B, T, 3, H, hd).permute(2, 0, 3, 1, 4)
+    att = torch.softmax((q @ k.transpose(-1, -2)) * scale, dim=-1)
+    o = (att @ v).transpose(1, 2).reshape(B * T, H * hd)
+    o.backward(dout.float())
+    ref = xr.grad                                        # [B*T, 3, H, hd]
+    qkv_d, dout_d = qkv.cuda(), dout.cuda()
+    out = torch.empty(B * T, H * hd, device="cuda", dtype=torch.bfloat16)
+    lse2 = torch.zeros(B * H * T + 64, device="cuda")
+    ws = torch.zeros(2 * (B * H * T + 64), device="cuda")
+    dqkv = torch.full((B * T, 3 * H * 128), float("nan"), device="cuda").to(torch.bfloat16)
+    st = _lib.stream_ptr()
+    _lib.check(L.ldmae_attention_wide_lse(_lib.ptr(qkv_d), _lib.ptr(out), _lib.ptr(lse2), B, T, H, hd, float(scale), st), "fwd")
+    _lib.check(L.ldmae_attention_wide_bwd(_lib.ptr(qkv_d), _lib.ptr(out), _lib.ptr(dout_d), _lib.ptr(lse2), _lib.ptr(ws), _lib.ptr(dqkv),
+                                          B, T, H, hd, float(scale), st), "bwd")
+    torch.cuda.synchronize()
+    assert rel_err(out.float().cpu(), o.detach()) < 1e-2
+    got = dqkv.float().cpu().reshape(B * T, 3, H, 128)
+    assert torch.isfinite(got).all()
+    assert float(got[..., hd:].abs().max()) == 0.0 if hd < 128 else True        # padding columns are written as zeros
+    for i, name in enumerate(("dq", "dk", "dv")):
+        err = rel_err(got[:, i, :, :hd], ref[:, i])
+        assert err < 2e-2, f"wide attention backward {name} hd {hd}: rel err {err}"
