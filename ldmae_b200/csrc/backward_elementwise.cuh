@@ -264,6 +264,111 @@ qkv_bwd_kernel(const QkvBwdParams p) {
   if (p.qw != nullptr && threadIdx.x < 128) atomicAdd((threadIdx.x < 64 ? p.dqw : p.dkw - 64) + threadIdx.x, s_acc[N + threadIdx.x]);
 }
 
+// The same for heads in 128-column slots (head_dim hd <= 128, LightningDiT-XL: 72): lane = the adjacent pair (2 lane,
+// 2 lane + 1) of each 64-column half of a head; statistics run over the real head_dim (padding columns are zero);
+// RoPE angles come from the reference's [T, hd] tables.
+struct QkvBwdWideParams {
+  __nv_bfloat16* dqkv;                      // [M, 3 * QW]
+  const __nv_bfloat16* raw;                 // [M, 2 * QW]
+  const float* ssq;
+  const float* qw; const float* kw;         // [128] zero padded, or nullptr
+  const float* rope_cos; const float* rope_sin;   // [T, hd] or nullptr
+  float* dcvec;                             // [B, 3 * QW]
+  float* dqw; float* dkw;                   // [128] each
+  int T, D, QW, hd, slots;
+  float eps_row, eps_head;
+};
+
+__global__ void __launch_bounds__(256)
+qkv_bwd_wide_kernel(const QkvBwdWideParams p) {
+  extern __shared__ float s_acc[];          // [3 * QW] column sums, then [256] dqw | dkw
+  const int N = 3 * p.QW;
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * 64;
+  const int nrows = min(64, p.T - t0);
+  for (int i = threadIdx.x; i < N + 256; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int heads3 = N / 128;
+  const int myrows = max(0, min(8, nrows - warp * 8));
+  const int tok0 = t0 + warp * 8;
+  const size_t row0 = static_cast<size_t>(b) * p.T + tok0;
+  const float inv_hd = 1.f / static_cast<float>(p.hd);
+  float wacc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  for (int hc = 0; hc < heads3; ++hc) {
+    const int which = (hc * 128) / p.QW;                     // 0 q, 1 k, 2 v
+    const bool normed = which < 2 && p.qw != nullptr;
+    const float* w = which == 0 ? p.qw : p.kw;
+    float wv[4] = {1.f, 1.f, 1.f, 1.f};
+    if (normed) { wv[0] = __ldg(w + lane * 2); wv[1] = __ldg(w + lane * 2 + 1); wv[2] = __ldg(w + 64 + lane * 2); wv[3] = __ldg(w + 65 + lane * 2); }
+    float cs[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = 0; i < myrows; ++i) {
+      const size_t row = row0 + i;
+      const int tok = tok0 + i;
+      const float rinv = row_rinv_g(p.ssq, row, p.slots, 1.f / p.D, p.eps_row);
+      __nv_bfloat16* dp = p.dqkv + row * N + hc * 128 + lane * 2;
+      const float2 d0 = bf2_to_f2(*reinterpret_cast<const uint32_t*>(dp));
+      const float2 d1 = bf2_to_f2(*reinterpret_cast<const uint32_t*>(dp + 64));
+      float dy[4] = {d0.x, d0.y, d1.x, d1.y};
+      if (which < 2) {
+        if (p.rope_cos != nullptr) {
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int d = hf * 64 + lane * 2;
+            if (d < p.hd) {
+              const float c = __ldg(p.rope_cos + static_cast<size_t>(tok) * p.hd + d), sn = __ldg(p.rope_sin + static_cast<size_t>(tok) * p.hd + d);
+              const float a = dy[2 * hf] * c + dy[2 * hf + 1] * sn;        // transpose of (a,b) -> (a c - b s, b c + a s)
+              const float bb = dy[2 * hf + 1] * c - dy[2 * hf] * sn;
+              dy[2 * hf] = a; dy[2 * hf + 1] = bb;
+            }
+          }
+        }
+        if (normed) {
+          const __nv_bfloat16* xp = p.raw + row * 2 * p.QW + hc * 128 + lane * 2;
+          const float2 x0 = bf2_to_f2(*reinterpret_cast<const uint32_t*>(xp));
+          const float2 x1 = bf2_to_f2(*reinterpret_cast<const uint32_t*>(xp + 64));
+          const float x[4] = {x0.x, x0.y, x1.x, x1.y};
+          const float ms = warp_sum(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
+          const float hs = rsqrtf(ms * inv_hd + p.eps_head);
+          float xh[4], u[4], dot = 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { xh[q] = x[q] * hs; u[q] = dy[q] * wv[q]; dot = fmaf(u[q], xh[q], dot); }
+          const float mu = warp_sum(dot) * inv_hd;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            wacc[which][q] = fmaf(dy[q], xh[q], wacc[which][q]);
+            dy[q] = hs * (u[q] - xh[q] * mu);
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) cs[q] += dy[q];
+      *reinterpret_cast<uint32_t*>(dp) = pack_bf16x2(dy[0] * rinv, dy[1] * rinv);
+      *reinterpret_cast<uint32_t*>(dp + 64) = pack_bf16x2(dy[2] * rinv, dy[3] * rinv);
+    }
+    atomicAdd(&s_acc[hc * 128 + lane * 2], cs[0]); atomicAdd(&s_acc[hc * 128 + lane * 2 + 1], cs[1]);
+    atomicAdd(&s_acc[hc * 128 + 64 + lane * 2], cs[2]); atomicAdd(&s_acc[hc * 128 + 65 + lane * 2], cs[3]);
+  }
+  if (p.qw != nullptr) {
+#pragma unroll
+    for (int wch = 0; wch < 2; ++wch) {
+      atomicAdd(&s_acc[N + wch * 128 + lane * 2], wacc[wch][0]); atomicAdd(&s_acc[N + wch * 128 + lane * 2 + 1], wacc[wch][1]);
+      atomicAdd(&s_acc[N + wch * 128 + 64 + lane * 2], wacc[wch][2]); atomicAdd(&s_acc[N + wch * 128 + 65 + lane * 2], wacc[wch][3]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < N; c += blockDim.x) atomicAdd(p.dcvec + static_cast<size_t>(b) * N + c, s_acc[c]);
+  if (p.qw != nullptr) atomicAdd((threadIdx.x < 128 ? p.dqw : p.dkw - 128) + threadIdx.x, s_acc[N + threadIdx.x]);
+}
+
+// dst[sec*nh*hd + h*hd + d, :] = src[sec*nh*hp + h*hp + d, :]  (gradient of a head-padded weight back to the reference rows)
+__global__ void unpad_heads_rows_kernel(float* __restrict__ dst, const float* __restrict__ src, int nh, int hd, int hp, int K) {
+  const int r = blockIdx.x;                 // reference row in [0, 3*nh*hd)
+  const int sec = r / (nh * hd), h = (r / hd) % nh, d = r % hd;
+  const size_t sr = static_cast<size_t>(sec) * nh * hp + h * hp + d;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) dst[static_cast<size_t>(r) * K + k] = src[sr * K + k];
+}
+
 // ---------------------------------------------------------------------------------------------
 // Backward through SwiGLU (swiglu_ffn.py:33-35) in the interleaved column layout of the packed w12
 // (64-column groups = [32 x1 | 32 x2]):   dx1 = dh * x2 * silu'(x1),  dx2 = dh * silu(x1)

@@ -563,6 +563,8 @@ struct EpiQKV : StoreRing {
 struct EpiQKVWide : StoreRing {
   struct Params {
     CUtensorMap omap;       // out [M, 3 * heads * 128] bf16: box {64, 32}, SWIZZLE_128B
+    CUtensorMap rawmap;     // has_raw (training forward): q, k before the head norm [M, 2 * heads * 128] bf16, same box
+    int has_raw;
     const float* ssq;       // [M, ss_slots]
     const float* cvec;      // [B, N]
     const float* qw;        // [128] q_norm.weight zero-padded, or nullptr
@@ -572,7 +574,10 @@ struct EpiQKVWide : StoreRing {
     int section, hd, rows_per_sample, ss_slots;     // section = heads * 128 = width of each of the q | k | v column ranges
     float inv_D, eps_row, eps_head;
   };
-  static __device__ __forceinline__ void prefetch_maps(const Params& p) { tma_prefetch_desc(&p.omap); }
+  static __device__ __forceinline__ void prefetch_maps(const Params& p) {
+    tma_prefetch_desc(&p.omap);
+    if (p.has_raw) tma_prefetch_desc(&p.rawmap);
+  }
   template <int BN>
   static __device__ __forceinline__ void begin(const Params&, const GemmShape&, const TileSched&, const EpiCtx&, State& st) {
     st.seq = 0;
@@ -625,6 +630,18 @@ struct EpiQKVWide : StoreRing {
           const float4 cc = ldvec4(cv, colbase + half * 64 + j, g.N);
           v[j] = fmaf(v[j], rinv, cc.x); v[j + 1] = fmaf(v[j + 1], rinv, cc.y);
           v[j + 2] = fmaf(v[j + 2], rinv, cc.z); v[j + 3] = fmaf(v[j + 3], rinv, cc.w);
+        }
+        if (which < 2 && p.has_raw) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            st_tile16(sw128_chunk(tile, lane, q),
+                   make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                              pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7])));
+          release(c, st, &p.rawmap, tile, colbase + half * 64, row0);
+          tile = acquire(c, st);
+        }
+#pragma unroll
+        for (int j = 0; j < 64; j += 4) {
           if (normed) {
             const float4 w4 = __ldg(reinterpret_cast<const float4*>(nw + half * 64 + j));
             v[j] *= hs * w4.x; v[j + 1] *= hs * w4.y; v[j + 2] *= hs * w4.z; v[j + 3] *= hs * w4.w;

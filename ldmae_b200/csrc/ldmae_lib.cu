@@ -784,7 +784,7 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
     const float* mods_i = h->mods.p + static_cast<size_t>(i) * h->nmod * D;
     const float* gate_msa = mods_i + (c.wo_shift ? 1 : 2) * D;
     const float* gate_mlp = mods_i + (c.wo_shift ? 3 : 5) * D;
-    __nv_bfloat16* qkv_i = tr ? tr->QKV.p + static_cast<size_t>(i) * M * 3 * D : h->qkv.p;
+    __nv_bfloat16* qkv_i = tr ? tr->QKV.p + static_cast<size_t>(i) * M * 3 * h->QW : h->qkv.p;
     __nv_bfloat16* o_i = tr ? tr->O.p + i * MD : h->obuf.p;
     __nv_bfloat16* hb_i = tr ? tr->HB.p + static_cast<size_t>(i) * M * h->Hp : h->hbuf.p;
     if (h->HW == 64) {
@@ -810,6 +810,11 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
       // wider heads (XL, head_dim 72): 128-column head slots, generic epilogue and the one-tile attention kernel
       EpiQKVWide::Params eq;
       LDMAE_TRY(make_tmap_out_bf16(&eq.omap, qkv_i, M, 3 * h->QW, 3 * h->QW));
+      eq.has_raw = 0; eq.rawmap = eq.omap;
+      if (tr) {
+        eq.has_raw = 1;
+        LDMAE_TRY(make_tmap_out_bf16(&eq.rawmap, tr->QKR.p + static_cast<size_t>(i) * M * 2 * h->QW, M, 2 * h->QW, 2 * h->QW));
+      }
       eq.ssq = Ss(2 * i); eq.cvec = h->cvec_qkv.p + static_cast<size_t>(i) * B * 3 * h->QW;
       eq.qw = c.use_qknorm ? b.qw.p : nullptr; eq.kw = c.use_qknorm ? b.kw.p : nullptr;
       eq.rope_cos = c.use_rope ? h->rope_cos.p : nullptr; eq.rope_sin = c.use_rope ? h->rope_sin.p : nullptr;
@@ -819,8 +824,9 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
       LDMAE_DBG_STAGE();
       {
         ProfScope ps(1, st);
+        float* lse = tr ? tr->LSE.p + static_cast<size_t>(i) * B * c.num_heads * T : nullptr;
         LDMAE_TRY(run_attention_hd128(qkv_i, 3 * h->QW, o_i, D, B, T, c.num_heads, h->hd, 0, h->QW, 2 * h->QW,
-                                      1.0f / sqrtf(static_cast<float>(h->hd)), st));
+                                      1.0f / sqrtf(static_cast<float>(h->hd)), st, lse));
       }
     }
     LDMAE_DBG_STAGE();

@@ -136,8 +136,8 @@ class LightningDiT(nn.Module):
                 "configs/*/lightningdit_b_vmae_f8d16_cfg.yaml:28-34); the LayerNorm / GELU-Mlp fallbacks are not built")
         hd = hidden_size // num_heads
         if not (hd == 64 or (64 < hd <= 128 and hd % 8 == 0)):
-            raise NotImplementedError(f"ldmae_b200 attention is built for head_dim 64 (B, L, 1p0B, 1p6B: tuned kernels, training) "
-                                      f"and for multiples of 8 in (64, 128] (XL, head_dim 72: inference path); got {hd}")
+            raise NotImplementedError(f"ldmae_b200 attention is built for head_dim 64 (B, L, 1p0B, 1p6B: tuned kernels) and for "
+                                      f"multiples of 8 in (64, 128] (XL, head_dim 72: 128-column head slots); got {hd}")
         self.learn_sigma = learn_sigma
         self.in_channels = in_channels
         self.out_channels = in_channels if not learn_sigma else in_channels * 2
@@ -287,9 +287,6 @@ class LightningDiT(nn.Module):
         B = x.shape[0]
         h = self._ensure_handle(x.device, B)
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            if self.hidden_size // self.num_heads != 64:
-                raise NotImplementedError("the backward kernels are built for head_dim 64; XL (head_dim 72) runs inference only -- "
-                                          "call it under torch.no_grad()")
             # differentiable path (train_accum.py:215-230): the library keeps the activations, autograd sees one node whose
             # inputs are the trainable parameters, so .grad / DDP hooks / torch optimizers work as with the reference
             named = [(k, p) for k, p in self.named_parameters() if p.requires_grad]

@@ -129,6 +129,26 @@ def test_wider_registry_widths_forward_and_backward(hidden, heads, patch, inp):
     _compare(ours, ref)
 
 
+def test_xl_head_dim_72_backward_matches_oracle_autograd():
+    """LightningDiT-XL geometry (width 1152, 16 heads of 72) at depth 2: the wide-head training path (128-column head slots,
+    head-norm / RoPE Jacobians over the real head_dim, gradients un-padded into the reference's parameter shapes)."""
+    from ldmae_b200.models.lightningdit import LightningDiT
+    spec = O.DiTSpec(depth=2, hidden_size=1152, patch_size=1, num_heads=16, input_size=16, in_channels=16, num_classes=10)
+    m = LightningDiT(input_size=16, patch_size=1, in_channels=16, hidden_size=1152, depth=2, num_heads=16, num_classes=10,
+                     use_qknorm=True, use_swiglu=True, use_rope=True, use_rmsnorm=True)
+    sd = O.synth_dit_state(spec, 92)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    g = torch.Generator().manual_seed(8)
+    B = 3
+    x1 = torch.randn(B, 16, 16, 16, generator=g); x0 = torch.randn(B, 16, 16, 16, generator=g)
+    t = torch.rand(B, generator=g); y = torch.randint(0, 10, (B,), generator=g)
+    ref_terms, ref = _oracle_grads(spec, sd, x1, t, x0, y)
+    terms, ours = _our_grads(m, x1.cuda(), t, x0, y.cuda())
+    assert _rel(terms["loss"], ref_terms["loss"].detach()) < 1e-2
+    _compare(ours, ref)
+
+
 def test_b1_backward_matches_oracle_autograd():
     """LightningDiT-B/1 at the benchmark shape (T = 1024, D = 768, 12 blocks), batch 2."""
     from ldmae_b200.models.lightningdit import LightningDiT_models
