@@ -64,24 +64,30 @@ def _compare(ours, ref, tol=GRAD_TOL):
     assert not bad, f"{len(bad)} gradients off: {bad[:12]}"
 
 
-def _tiny(patch, seed, **flags):
+def _tiny(patch, seed, input_size=8, **flags):
     from ldmae_b200.models.lightningdit import LightningDiT
-    spec = O.DiTSpec(depth=2, hidden_size=128, patch_size=patch, num_heads=2, input_size=8, in_channels=16, num_classes=10, **flags)
-    m = LightningDiT(input_size=8, patch_size=patch, in_channels=16, hidden_size=128, depth=2, num_heads=2, num_classes=10,
-                     use_qknorm=spec.use_qknorm, use_swiglu=True, use_rope=spec.use_rope, use_rmsnorm=True, wo_shift=spec.wo_shift)
+    spec = O.DiTSpec(depth=2, hidden_size=128, patch_size=patch, num_heads=2, input_size=input_size, in_channels=16, num_classes=10,
+                     **flags)
+    m = LightningDiT(input_size=input_size, patch_size=patch, in_channels=16, hidden_size=128, depth=2, num_heads=2, num_classes=10,
+                     use_qknorm=spec.use_qknorm, use_swiglu=True, use_rope=spec.use_rope, use_rmsnorm=True, wo_shift=spec.wo_shift,
+                     learn_sigma=spec.learn_sigma)
     sd = O.synth_dit_state(spec, seed)
     m.load_state_dict(sd, strict=True)
     return spec, sd, m.cuda().eval()        # eval: no label dropout, the draws are injected
 
 
 @pytest.mark.parametrize("patch,flags", [(1, {}), (2, {}), (1, dict(use_qknorm=False)), (1, dict(wo_shift=True)),
-                                         (1, dict(use_rope=False))])
+                                         (1, dict(use_rope=False)), (1, dict(learn_sigma=True)),
+                                         (1, dict(input_size=6)),      # T = 36: ragged against every tile size (rows, keys, slabs)
+                                         (1, dict(input_size=14))])    # T = 196: several ragged blocks per sample
 def test_tiny_backward_matches_oracle_autograd(patch, flags):
-    spec, sd, m = _tiny(patch, 21 + patch, **flags)
+    flags = dict(flags)
+    S = flags.pop("input_size", 8)
+    spec, sd, m = _tiny(patch, 21 + patch, input_size=S, **flags)
     g = torch.Generator().manual_seed(5 + patch)
     B = 5
-    x1 = torch.randn(B, 16, 8, 8, generator=g)
-    x0 = torch.randn(B, 16, 8, 8, generator=g)
+    x1 = torch.randn(B, 16, S, S, generator=g)
+    x0 = torch.randn(B, 16, S, S, generator=g)
     t = torch.rand(B, generator=g)
     y = torch.randint(0, 10, (B,), generator=g)
     ref_terms, ref = _oracle_grads(spec, sd, x1, t, x0, y)
