@@ -228,7 +228,7 @@ def measure_train(args, dev, rank, world):
     tfl = 3 * fwd * B / (ms_step / 1e3) / 1e12
     del trainer, model
     torch.cuda.empty_cache()
-    return {"metric": "LightningDiT-B train samples/s", "value": world * B / (ms_step / 1e3), "unit": "samples/s",
+    return {"metric": ("LightningDiT-B" if args.model == "LightningDiT-B/1" else args.model) + " train samples/s", "value": world * B / (ms_step / 1e3), "unit": "samples/s",
             "batch_per_gpu": B, "global_batch": world * B, "steps": args.train_steps, "ms_per_step": ms_step,
             "tflops_per_gpu": tfl, "frac_of_bf16_peak": tfl / pk["tflops"], "flops_per_sample": 3 * fwd,
             "gpu_launches": launches, "final_loss": float(loss_host.mean()),
@@ -361,7 +361,7 @@ def run_gpu(args, rank, world, local_rank):
                 "flops_per_launch": flops_per_launch, "avg_launch_ms": ms / cnt, "launches_timed": cnt}
     class_ms = {k: round(v[0] / args.steps, 3) for k, v in prof.items()}
     job_flops = fwd_flops * Bf * (args.num_steps - 1)
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+    line = {"metric": METRIC if args.model == "LightningDiT-B/1" else f"{args.model} sampled img/s", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": workload_config(args), "clocks": clk,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": z_host.numel() * 4 + y_host.numel() * 8,
