@@ -50,8 +50,8 @@ struct ResidBwdParams {
   float eps;
 };
 
-// Column sums stay in registers over the 8 rows a warp owns (lane = 4 columns of every 128-column chunk, panels of
-// 6 chunks) and reach shared memory once per warp and panel, global memory once per CTA and column.
+// Column sums stay in registers over the 8 rows a warp owns (lane = 4 columns of a 128-column chunk) and reach shared
+// memory once per warp and chunk, global memory once per CTA and column.
 __global__ void __launch_bounds__(256, 2)
 resid_bwd_kernel(const ResidBwdParams p) {
   extern __shared__ float s_acc[];              // [3][D]: dg, dgate, sdx
@@ -89,65 +89,46 @@ resid_bwd_kernel(const ResidBwdParams p) {
       coef[i] = rinv * rinv * t / D;
     }
   }
-  // pass B, one panel of up to 768 columns at a time
-  for (int p0 = 0; p0 < D; p0 += 768) {
-    float a_dg[6][4], a_gt[6][4], a_sd[6][4];
-#pragma unroll
-    for (int k = 0; k < 6; ++k)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) { a_dg[k][q] = 0.f; a_gt[k][q] = 0.f; a_sd[k][q] = 0.f; }
+  // pass B, one 128-column chunk at a time (lane = 4 columns) over the warp's 8 rows: the per-sample vectors g / gate are
+  // loaded once per chunk, the 8 rows' loads are independent (deep memory-level parallelism), the column sums of the
+  // chunk stay in 12 registers and reach shared memory once per warp and chunk
+  for (int c = lane * 4; c < D; c += 128) {
+    const float4 gv = __ldg(reinterpret_cast<const float4*>(g + c));
+    const float gs[4] = {gv.x, gv.y, gv.z, gv.w};
+    float gt[4] = {1.f, 1.f, 1.f, 1.f};
+    if (gate) { const float4 q4 = __ldg(reinterpret_cast<const float4*>(gate + c)); gt[0] = q4.x; gt[1] = q4.y; gt[2] = q4.z; gt[3] = q4.w; }
+    float a_dg[4] = {0.f, 0.f, 0.f, 0.f}, a_gt[4] = {0.f, 0.f, 0.f, 0.f}, a_sd[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       if (i < myrows) {
-        const size_t row = row0 + i;
-        const float* xr = p.x + row * D;
-        const __nv_bfloat16* gr = p.gp + row * D;
-        float* dxr = p.dx + row * D;
-        const __nv_bfloat16* mr = p.m_prev ? p.m_prev + row * D : nullptr;
+        const size_t off = (row0 + i) * D + c;
+        const float4 xv = *reinterpret_cast<const float4*>(p.x + off);
+        const uint2 gw = *reinterpret_cast<const uint2*>(p.gp + off);
+        float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!p.dx_zero) d4 = *reinterpret_cast<const float4*>(p.dx + off);
+        uint2 mw = make_uint2(0u, 0u);
+        if (p.m_prev) mw = *reinterpret_cast<const uint2*>(p.m_prev + off);
+        const float2 ga = bf2_to_f2(gw.x), gb = bf2_to_f2(gw.y), m0 = bf2_to_f2(mw.x), m1 = bf2_to_f2(mw.y);
+        const float gpv[4] = {ga.x, ga.y, gb.x, gb.y};
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+        const float mv[4] = {m0.x, m0.y, m1.x, m1.y};
+        float dn[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
-          const int c = p0 + k * 128 + lane * 4;
-          if (c < D) {
-            const float4 xv = *reinterpret_cast<const float4*>(xr + c);
-            const float4 gv = __ldg(reinterpret_cast<const float4*>(g + c));
-            const uint2 gw = *reinterpret_cast<const uint2*>(gr + c);
-            const float2 a = bf2_to_f2(gw.x), bq = bf2_to_f2(gw.y);
-            const float gpv[4] = {a.x, a.y, bq.x, bq.y};
-            const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-            const float gs[4] = {gv.x, gv.y, gv.z, gv.w};
-            float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (!p.dx_zero) d4 = *reinterpret_cast<const float4*>(dxr + c);
-            float dn[4] = {d4.x, d4.y, d4.z, d4.w};
-            float gt[4] = {1.f, 1.f, 1.f, 1.f};
-            if (gate) { const float4 q4 = __ldg(reinterpret_cast<const float4*>(gate + c)); gt[0] = q4.x; gt[1] = q4.y; gt[2] = q4.z; gt[3] = q4.w; }
-            float mv[4] = {0.f, 0.f, 0.f, 0.f};
-            if (mr) { const uint2 mw = *reinterpret_cast<const uint2*>(mr + c); const float2 m0 = bf2_to_f2(mw.x), m1 = bf2_to_f2(mw.y);
-                      mv[0] = m0.x; mv[1] = m0.y; mv[2] = m1.x; mv[3] = m1.y; }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              dn[q] = dn[q] + gs[q] * gpv[q] - xs[q] * coef[i];
-              a_dg[k][q] = fmaf(gpv[q], xs[q], a_dg[k][q]);
-              a_gt[k][q] = fmaf(dn[q], mv[q], a_gt[k][q]);
-              a_sd[k][q] += dn[q];
-            }
-            *reinterpret_cast<float4*>(dxr + c) = make_float4(dn[0], dn[1], dn[2], dn[3]);
-            *reinterpret_cast<uint2*>(p.dy + row * D + c) =
-                make_uint2(pack_bf16x2(dn[0] * gt[0], dn[1] * gt[1]), pack_bf16x2(dn[2] * gt[2], dn[3] * gt[3]));
-          }
+        for (int q = 0; q < 4; ++q) {
+          dn[q] = dn[q] + gs[q] * gpv[q] - xs[q] * coef[i];
+          a_dg[q] = fmaf(gpv[q], xs[q], a_dg[q]);
+          a_gt[q] = fmaf(dn[q], mv[q], a_gt[q]);
+          a_sd[q] += dn[q];
         }
+        *reinterpret_cast<float4*>(p.dx + off) = make_float4(dn[0], dn[1], dn[2], dn[3]);
+        *reinterpret_cast<uint2*>(p.dy + off) = make_uint2(pack_bf16x2(dn[0] * gt[0], dn[1] * gt[1]), pack_bf16x2(dn[2] * gt[2], dn[3] * gt[3]));
       }
     }
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      const int c = p0 + k * 128 + lane * 4;
-      if (c < D) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          atomicAdd(&s_acc[c + q], a_dg[k][q]);
-          if (p.m_prev) atomicAdd(&s_acc[D + c + q], a_gt[k][q]);
-          if (p.sdx) atomicAdd(&s_acc[2 * D + c + q], a_sd[k][q]);
-        }
-      }
+    for (int q = 0; q < 4; ++q) {
+      atomicAdd(&s_acc[c + q], a_dg[q]);
+      if (p.m_prev) atomicAdd(&s_acc[D + c + q], a_gt[q]);
+      if (p.sdx) atomicAdd(&s_acc[2 * D + c + q], a_sd[q]);
     }
   }
   __syncthreads();
@@ -165,7 +146,6 @@ resid_bwd_kernel(const ResidBwdParams p) {
 //   out: dqkv in place     = r[row] * dL/d(qkv pre-norm)     (operand of the data- and weight-gradient GEMMs)
 //        dcvec[b, 3D]     += sum_t dL/d(qkv pre-norm)        (-> bias, shift and shift-path weight gradients)
 //        dqw[64], dkw[64] += sum over rows and heads of dy * xhat
-// One warp = 8 rows x one 64-wide head at a time, lane = one adjacent pair (= one RoPE pair).  One CTA = 64 rows of a sample.
 // ---------------------------------------------------------------------------------------------
 struct QkvBwdParams {
   __nv_bfloat16* dqkv;
@@ -179,7 +159,17 @@ struct QkvBwdParams {
   float eps_row, eps_head;
 };
 
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ float half_warp_sum(float v) {   // sum over the 16 lanes of this half-warp (every lane takes part)
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
+
+// One warp = 8 rows x TWO 64-wide heads at a time: a half-warp per head, lane = 4 consecutive dims (two RoPE pairs, one
+// 8-byte access).  One CTA = 64 rows of a sample.
+__global__ void __launch_bounds__(256, 2)
 qkv_bwd_kernel(const QkvBwdParams p) {
   extern __shared__ float s_acc[];          // [3D] column sums, then [128] dqw | dkw
   const int D = p.D, N = 3 * D;
@@ -189,75 +179,91 @@ qkv_bwd_kernel(const QkvBwdParams p) {
   for (int i = threadIdx.x; i < N + 128; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hh = lane >> 4, l16 = lane & 15;
+  const int d0 = 4 * l16;                                    // first of this lane's 4 dims inside a head
   const int heads3 = N / 64;
   const int myrows = max(0, min(8, nrows - warp * 8));       // this warp owns 8 consecutive rows of the slab
   const int tok0 = t0 + warp * 8;
   const size_t row0 = static_cast<size_t>(b) * p.T + tok0;
-  float rinv[8], rc[8], rs[8];                               // row factor and this lane's RoPE angle per row
+  float rinv[8], rc[8][2], rs[8][2];                         // row factor and this lane's two RoPE angles per row
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    rinv[i] = 0.f; rc[i] = 1.f; rs[i] = 0.f;
+    rinv[i] = 0.f; rc[i][0] = rc[i][1] = 1.f; rs[i][0] = rs[i][1] = 0.f;
     if (i < myrows) {
       rinv[i] = row_rinv_g(p.ssq, row0 + i, p.slots, 1.f / D, p.eps_row);
       if (p.rope != nullptr) {
-        const int axis = lane >> 4, f = lane & 15, tok = tok0 + i;
+        const int axis = d0 >> 5, f = (d0 & 31) >> 1, tok = tok0 + i;     // dims 0..31: token row, 32..63: token column
         const int pos = axis == 0 ? tok / p.G : tok % p.G;
         const float* tab = p.rope + (static_cast<size_t>(axis) * p.G + pos) * 32;
-        rc[i] = __ldg(tab + f); rs[i] = __ldg(tab + 16 + f);
+        rc[i][0] = __ldg(tab + f); rc[i][1] = __ldg(tab + f + 1);
+        rs[i][0] = __ldg(tab + 16 + f); rs[i][1] = __ldg(tab + 16 + f + 1);
       }
     }
   }
-  float wacc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};               // dq_norm.weight / dk_norm.weight partial sums of this lane's pair
-  for (int hc = 0; hc < heads3; ++hc) {
-    const int col = hc * 64 + lane * 2;
-    const int which = (hc * 64) / D;                         // 0 q, 1 k, 2 v
-    float w0 = 1.f, w1 = 1.f;
-    if (which < 2 && p.qw != nullptr) { const float* w = which == 0 ? p.qw : p.kw; w0 = __ldg(w + lane * 2); w1 = __ldg(w + lane * 2 + 1); }
-    uint32_t dyw[8], xw[8];
+  float wacc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};    // dq_norm.weight / dk_norm.weight partial sums (this lane's dims)
+  for (int hp = 0; hp < heads3; hp += 2) {
+    const int hc = hp + hh;                                  // this half-warp's head
+    const bool live = hc < heads3;
+    const int col = hc * 64 + d0;
+    const int which = live ? (hc * 64) / D : 2;              // 0 q, 1 k, 2 v
+    const bool normed = which < 2 && p.qw != nullptr;
+    float wv[4] = {1.f, 1.f, 1.f, 1.f};
+    if (normed) { const float4 w4 = __ldg(reinterpret_cast<const float4*>((which == 0 ? p.qw : p.kw) + d0)); wv[0] = w4.x; wv[1] = w4.y; wv[2] = w4.z; wv[3] = w4.w; }
+    uint2 dyw[8], xw[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      dyw[i] = 0u; xw[i] = 0u;
-      if (i < myrows) {
-        dyw[i] = *reinterpret_cast<const uint32_t*>(p.dqkv + (row0 + i) * N + col);
-        if (which < 2 && p.qw != nullptr) xw[i] = *reinterpret_cast<const uint32_t*>(p.raw + (row0 + i) * 2 * D + col);
+      dyw[i] = make_uint2(0u, 0u); xw[i] = make_uint2(0u, 0u);
+      if (i < myrows && live) {
+        dyw[i] = *reinterpret_cast<const uint2*>(p.dqkv + (row0 + i) * N + col);
+        if (normed) xw[i] = *reinterpret_cast<const uint2*>(p.raw + (row0 + i) * 2 * D + col);
       }
     }
-    float c0 = 0.f, c1 = 0.f;
+    float cs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float2 dy = bf2_to_f2(dyw[i]);
-      if (which < 2) {
-        if (p.rope != nullptr) {
-          const float a = dy.x * rc[i] + dy.y * rs[i];       // transpose of (a,b) -> (a c - b s, b c + a s)
-          const float bb = dy.y * rc[i] - dy.x * rs[i];
-          dy = make_float2(a, bb);
-        }
-        if (p.qw != nullptr) {
-          const float2 x = bf2_to_f2(xw[i]);
-          const float ms = warp_sum(x.x * x.x + x.y * x.y);
-          const float hs = rsqrtf(ms * (1.f / 64.f) + p.eps_head);
-          const float xh0 = x.x * hs, xh1 = x.y * hs;
-          const float u0 = dy.x * w0, u1 = dy.y * w1;
-          const float mu = warp_sum(u0 * xh0 + u1 * xh1) * (1.f / 64.f);
-          wacc[which][0] = fmaf(dy.x, xh0, wacc[which][0]);
-          wacc[which][1] = fmaf(dy.y, xh1, wacc[which][1]);
-          dy = make_float2(hs * (u0 - xh0 * mu), hs * (u1 - xh1 * mu));
+      const float2 a01 = bf2_to_f2(dyw[i].x), a23 = bf2_to_f2(dyw[i].y);
+      float dy[4] = {a01.x, a01.y, a23.x, a23.y};
+      if (which < 2 && p.rope != nullptr) {
+#pragma unroll
+        for (int pr = 0; pr < 2; ++pr) {                     // transpose of (a,b) -> (a c - b s, b c + a s)
+          const float a = dy[2 * pr] * rc[i][pr] + dy[2 * pr + 1] * rs[i][pr];
+          const float bb = dy[2 * pr + 1] * rc[i][pr] - dy[2 * pr] * rs[i][pr];
+          dy[2 * pr] = a; dy[2 * pr + 1] = bb;
         }
       }
-      if (i < myrows) {
-        c0 += dy.x; c1 += dy.y;
-        *reinterpret_cast<uint32_t*>(p.dqkv + (row0 + i) * N + col) = pack_bf16x2(dy.x * rinv[i], dy.y * rinv[i]);
+      // head-norm Jacobian; the reductions run in every lane (the two half-warps may hold a normed and a plain head)
+      const float2 x01 = bf2_to_f2(xw[i].x), x23 = bf2_to_f2(xw[i].y);
+      const float x[4] = {x01.x, x01.y, x23.x, x23.y};
+      const float ms = half_warp_sum(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
+      const float hs = rsqrtf(ms * (1.f / 64.f) + p.eps_head);
+      float xh[4], u[4], dot = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { xh[q] = x[q] * hs; u[q] = dy[q] * wv[q]; dot = fmaf(u[q], xh[q], dot); }
+      const float mu = half_warp_sum(dot) * (1.f / 64.f);
+      if (normed) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          wacc[which][q] = fmaf(dy[q], xh[q], wacc[which][q]);
+          dy[q] = hs * (u[q] - xh[q] * mu);
+        }
+      }
+      if (i < myrows && live) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cs[q] += dy[q];
+        *reinterpret_cast<uint2*>(p.dqkv + (row0 + i) * N + col) =
+            make_uint2(pack_bf16x2(dy[0] * rinv[i], dy[1] * rinv[i]), pack_bf16x2(dy[2] * rinv[i], dy[3] * rinv[i]));
       }
     }
-    atomicAdd(&s_acc[col], c0);
-    atomicAdd(&s_acc[col + 1], c1);
+    if (live) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) atomicAdd(&s_acc[col + q], cs[q]);
+    }
   }
   if (p.qw != nullptr) {
 #pragma unroll
-    for (int w = 0; w < 2; ++w) {
-      atomicAdd(&s_acc[N + w * 64 + lane * 2], wacc[w][0]);
-      atomicAdd(&s_acc[N + w * 64 + lane * 2 + 1], wacc[w][1]);
-    }
+    for (int w = 0; w < 2; ++w)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) atomicAdd(&s_acc[N + w * 64 + d0 + q], wacc[w][q]);
   }
   __syncthreads();
   for (int c = threadIdx.x; c < N; c += blockDim.x) atomicAdd(p.dcvec + static_cast<size_t>(b) * N + c, s_acc[c]);
