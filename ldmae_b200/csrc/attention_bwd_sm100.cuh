@@ -347,30 +347,31 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
 }
 
 // Row statistics of the backward: delta[b,h,t] = scale * sum_d dO[t,h,d] * O[t,h,d] and nlse2 = -lse2 (both in the form the
-// packed fma of the kernels above consumes).  One warp per token row: lanes walk a head (hd <= 128, even).
+// packed fma of the kernels above consumes).  One thread per (token row, head): 16-byte loads along the head, no shuffles;
+// neighbouring threads read neighbouring heads of the same row (coalesced).
 __global__ void attn_delta_kernel(float* __restrict__ delta, float* __restrict__ nlse2, const float* __restrict__ lse2,
                                   const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* __restrict__ O, int B, int T, int H,
                                   int hd, float scale) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= B * T) return;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(B) * T * H) return;
+  const int h = i % H;
+  const size_t row = i / H;
   const int b = row / T, t = row % T;
-  const size_t base = static_cast<size_t>(row) * H * hd;
-  for (int h = 0; h < H; ++h) {
-    float s = 0.f;
-    for (int d = lane * 2; d < hd; d += 64) {
-      const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(dO + base + h * hd + d);
-      const __nv_bfloat162 o = *reinterpret_cast<const __nv_bfloat162*>(O + base + h * hd + d);
-      s += __bfloat162float(a.x) * __bfloat162float(o.x) + __bfloat162float(a.y) * __bfloat162float(o.y);
-    }
+  const uint4* a = reinterpret_cast<const uint4*>(dO + row * H * hd + static_cast<size_t>(h) * hd);
+  const uint4* o = reinterpret_cast<const uint4*>(O + row * H * hd + static_cast<size_t>(h) * hd);
+  float s = 0.f;
+  for (int j = 0; j < hd / 8; ++j) {         // head_dim is a multiple of 8
+    const uint4 x = __ldg(a + j), y = __ldg(o + j);
+    const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
 #pragma unroll
-    for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
-    if (lane == 0) {
-      const size_t i = (static_cast<size_t>(b) * H + h) * T + t;
-      delta[i] = s * scale;
-      nlse2[i] = -lse2[i];
+    for (int q = 0; q < 4; ++q) {
+      s = fmaf(__uint_as_float(xw[q] << 16), __uint_as_float(yw[q] << 16), s);
+      s = fmaf(__uint_as_float(xw[q] & 0xffff0000u), __uint_as_float(yw[q] & 0xffff0000u), s);
     }
   }
+  const size_t k = (static_cast<size_t>(b) * H + h) * T + t;
+  delta[k] = s * scale;
+  nlse2[k] = -lse2[k];
 }
 
 }  // namespace ldmae

@@ -32,7 +32,7 @@ __device__ __forceinline__ float dsilu_f(float x) {
 //   dY      = bf16(dx_new * gate_prev[b])    (output gradient of the previous branch's Linear; gate_prev == nullptr: 1)
 //   dgate_prev[b] += sum_t dx_new * m_prev   (m_prev = that branch's output before the gate, saved by the forward)
 //   sdx[b] += sum_t dx_new                   (-> bias gradient of the previous branch's Linear, times the gate)
-// One CTA = 64 token rows of one sample; one warp = one row at a time.
+// One CTA = 32 token rows of one sample; one warp = 4 rows.
 // ---------------------------------------------------------------------------------------------
 struct ResidBwdParams {
   float* dx;                    // [M, D] in/out (dx_in == nullptr on entry of the final layer: treated as 0)
@@ -52,24 +52,25 @@ struct ResidBwdParams {
 
 // Column sums stay in registers over the 8 rows a warp owns (lane = 4 columns of a 128-column chunk) and reach shared
 // memory once per warp and chunk, global memory once per CTA and column.
-__global__ void __launch_bounds__(256, 2)
+constexpr int kResidRows = 4;   // rows per warp (8 warps per CTA): 4 keeps the kernel at <= 85 registers, three CTAs per SM
+__global__ void __launch_bounds__(256, 3)
 resid_bwd_kernel(const ResidBwdParams p) {
   extern __shared__ float s_acc[];              // [3][D]: dg, dgate, sdx
   const int b = blockIdx.y;
-  const int t0 = blockIdx.x * 64;
-  const int nrows = min(64, p.T - t0);
+  const int t0 = blockIdx.x * (8 * kResidRows);
+  const int nrows = min(8 * kResidRows, p.T - t0);
   const int D = p.D;
   for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* g = p.g + static_cast<size_t>(b) * D;
   const float* gate = p.gate ? p.gate + static_cast<size_t>(b) * p.gate_ld : nullptr;
-  const size_t row0 = static_cast<size_t>(b) * p.T + t0 + warp * 8;
-  const int myrows = max(0, min(8, nrows - warp * 8));
+  const size_t row0 = static_cast<size_t>(b) * p.T + t0 + warp * kResidRows;
+  const int myrows = max(0, min(kResidRows, nrows - warp * kResidRows));
   // pass A: coef[i] = r^2 / D * sum_col(Gp * x * g) of each of this warp's rows
-  float coef[8];
+  float coef[kResidRows];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < kResidRows; ++i) {
     coef[i] = 0.f;
     if (i < myrows) {
       const size_t row = row0 + i;
@@ -99,7 +100,7 @@ resid_bwd_kernel(const ResidBwdParams p) {
     if (gate) { const float4 q4 = __ldg(reinterpret_cast<const float4*>(gate + c)); gt[0] = q4.x; gt[1] = q4.y; gt[2] = q4.z; gt[3] = q4.w; }
     float a_dg[4] = {0.f, 0.f, 0.f, 0.f}, a_gt[4] = {0.f, 0.f, 0.f, 0.f}, a_sd[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < kResidRows; ++i) {
       if (i < myrows) {
         const size_t off = (row0 + i) * D + c;
         const float4 xv = *reinterpret_cast<const float4*>(p.x + off);
@@ -167,27 +168,28 @@ __device__ __forceinline__ float half_warp_sum(float v) {   // sum over the 16 l
   return v;
 }
 
-// One warp = 8 rows x TWO 64-wide heads at a time: a half-warp per head, lane = 4 consecutive dims (two RoPE pairs, one
-// 8-byte access).  One CTA = 64 rows of a sample.
-__global__ void __launch_bounds__(256, 2)
+// One warp = 4 rows x TWO 64-wide heads at a time: a half-warp per head, lane = 4 consecutive dims (two RoPE pairs, one
+// 8-byte access).  One CTA = 32 rows of a sample.
+constexpr int kQkvRows = 4;     // rows per warp of qkv_bwd_kernel (32-row slab per CTA)
+__global__ void __launch_bounds__(256, 3)
 qkv_bwd_kernel(const QkvBwdParams p) {
   extern __shared__ float s_acc[];          // [3D] column sums, then [128] dqw | dkw
   const int D = p.D, N = 3 * D;
   const int b = blockIdx.y;
-  const int t0 = blockIdx.x * 64;
-  const int nrows = min(64, p.T - t0);
+  const int t0 = blockIdx.x * (8 * kQkvRows);
+  const int nrows = min(8 * kQkvRows, p.T - t0);
   for (int i = threadIdx.x; i < N + 128; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int hh = lane >> 4, l16 = lane & 15;
   const int d0 = 4 * l16;                                    // first of this lane's 4 dims inside a head
   const int heads3 = N / 64;
-  const int myrows = max(0, min(8, nrows - warp * 8));       // this warp owns 8 consecutive rows of the slab
-  const int tok0 = t0 + warp * 8;
+  const int myrows = max(0, min(kQkvRows, nrows - warp * kQkvRows));       // this warp owns kQkvRows consecutive rows of the slab
+  const int tok0 = t0 + warp * kQkvRows;
   const size_t row0 = static_cast<size_t>(b) * p.T + tok0;
-  float rinv[8], rc[8][2], rs[8][2];                         // row factor and this lane's two RoPE angles per row
+  float rinv[kQkvRows], rc[kQkvRows][2], rs[kQkvRows][2];                         // row factor and this lane's two RoPE angles per row
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < kQkvRows; ++i) {
     rinv[i] = 0.f; rc[i][0] = rc[i][1] = 1.f; rs[i][0] = rs[i][1] = 0.f;
     if (i < myrows) {
       rinv[i] = row_rinv_g(p.ssq, row0 + i, p.slots, 1.f / D, p.eps_row);
@@ -209,9 +211,9 @@ qkv_bwd_kernel(const QkvBwdParams p) {
     const bool normed = which < 2 && p.qw != nullptr;
     float wv[4] = {1.f, 1.f, 1.f, 1.f};
     if (normed) { const float4 w4 = __ldg(reinterpret_cast<const float4*>((which == 0 ? p.qw : p.kw) + d0)); wv[0] = w4.x; wv[1] = w4.y; wv[2] = w4.z; wv[3] = w4.w; }
-    uint2 dyw[8], xw[8];
+    uint2 dyw[kQkvRows], xw[kQkvRows];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < kQkvRows; ++i) {
       dyw[i] = make_uint2(0u, 0u); xw[i] = make_uint2(0u, 0u);
       if (i < myrows && live) {
         dyw[i] = *reinterpret_cast<const uint2*>(p.dqkv + (row0 + i) * N + col);
@@ -220,7 +222,7 @@ qkv_bwd_kernel(const QkvBwdParams p) {
     }
     float cs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < kQkvRows; ++i) {
       const float2 a01 = bf2_to_f2(dyw[i].x), a23 = bf2_to_f2(dyw[i].y);
       float dy[4] = {a01.x, a01.y, a23.x, a23.y};
       if (which < 2 && p.rope != nullptr) {

@@ -274,7 +274,7 @@ static int run_attention_bwd_t(const void* qkv, int ldq, const void* o, const vo
     attr = true;
   }
   float* nlse2 = delta + static_cast<size_t>(B) * H * T + 64;       // second half of the workspace
-  attn_delta_kernel<<<cdiv(static_cast<size_t>(B) * T, 8), 256, 0, st>>>(delta, nlse2, lse2, static_cast<const __nv_bfloat16*>(d_o),
+  attn_delta_kernel<<<cdiv(static_cast<size_t>(B) * T * H, 256), 256, 0, st>>>(delta, nlse2, lse2, static_cast<const __nv_bfloat16*>(d_o),
                                                                          static_cast<const __nv_bfloat16*>(o), B, T, H, hd, scale);
   LDMAE_LAUNCH_CHECK();
   AttnBwdParams p;
