@@ -23,6 +23,8 @@
 // tcgen05.mma instructions of one thread execute in order: scores(i+1) is issued after the accumulations of block i-1, the
 // previous user of its buffer, which is all the write-after-read protection the aliasing needs.
 #pragma once
+#include <type_traits>
+
 #include "ptx.cuh"
 
 namespace ldmae {
@@ -275,35 +277,41 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       tmem_ld_wait();
       if (warp == 4) ABWD_STAMP(5);
       uint32_t wp[8], wd[8];
+      // The ragged tail of a sample (fewer than 16 live columns in this warp's quarter) is a separate instantiation of
+      // the body behind a warp-uniform branch: as predicated selects inside the common body it cost 48 issue slots per
+      // block in a loop that is issue-bound.
+      auto body = [&](auto ragged) {
+        constexpr bool kRagged = decltype(ragged)::value;
 #pragma unroll
-      for (int c = 0; c < 16; c += 4) {
-        float2 nl0 = nl_r, nl1 = nl_r, dl0 = dl_r, dl1 = dl_r;
-        if constexpr (kKV) {
-          const float4 l4 = *reinterpret_cast<const float4*>(vl + c);
-          const float4 d4 = *reinterpret_cast<const float4*>(vd + c);
-          nl0 = make_float2(l4.x, l4.y); nl1 = make_float2(l4.z, l4.w);
-          dl0 = make_float2(-d4.x, -d4.y); dl1 = make_float2(-d4.z, -d4.w);
+        for (int c = 0; c < 16; c += 4) {
+          float2 nl0 = nl_r, nl1 = nl_r, dl0 = dl_r, dl1 = dl_r;
+          if constexpr (kKV) {
+            const uint4 lw = lds128(vl + c), dw = lds128(vd + c);          // shared-space loads (the pointers are generic)
+            nl0 = make_float2(__uint_as_float(lw.x), __uint_as_float(lw.y)); nl1 = make_float2(__uint_as_float(lw.z), __uint_as_float(lw.w));
+            dl0 = make_float2(-__uint_as_float(dw.x), -__uint_as_float(dw.y)); dl1 = make_float2(-__uint_as_float(dw.z), -__uint_as_float(dw.w));
+          }
+          const float2 x0 = fma2(make_float2(sv[c], sv[c + 1]), sl2, nl0);
+          const float2 x1 = fma2(make_float2(sv[c + 2], sv[c + 3]), sl2, nl1);
+          float2 p0 = make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
+          // a quarter of the exponentials takes the FMA-pipe polynomial: the MUFU unit (16 / clk / SM) is shared by 16 warps
+          float2 p1 = ((c & 4) != 0) ? ex2_poly2(x1) : make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
+          float2 e0 = fma2(make_float2(dp[c], dp[c + 1]), sc2, dl0);      // scale * dP - scale * delta
+          float2 e1 = fma2(make_float2(dp[c + 2], dp[c + 3]), sc2, dl1);
+          if constexpr (kRagged) {                        // P = dS = 0 beyond the sample
+            if (c >= cvalid) { p0.x = 0.f; e0.x = 0.f; }
+            if (c + 1 >= cvalid) { p0.y = 0.f; e0.y = 0.f; }
+            if (c + 2 >= cvalid) { p1.x = 0.f; e1.x = 0.f; }
+            if (c + 3 >= cvalid) { p1.y = 0.f; e1.y = 0.f; }
+          }
+          e0 = fma2(p0, e0, make_float2(0.f, 0.f));
+          e1 = fma2(p1, e1, make_float2(0.f, 0.f));
+          wp[c >> 1] = pack_bf16x2(p0.x, p0.y);
+          wp[(c >> 1) + 1] = pack_bf16x2(p1.x, p1.y);
+          wd[c >> 1] = pack_bf16x2(e0.x, e0.y);
+          wd[(c >> 1) + 1] = pack_bf16x2(e1.x, e1.y);
         }
-        const float2 x0 = fma2(make_float2(sv[c], sv[c + 1]), sl2, nl0);
-        const float2 x1 = fma2(make_float2(sv[c + 2], sv[c + 3]), sl2, nl1);
-        float2 p0 = make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
-        // a quarter of the exponentials takes the FMA-pipe polynomial: the MUFU unit (16 / clk / SM) is the row warps' limit
-        float2 p1 = ((c & 4) != 0) ? ex2_poly2(x1) : make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
-        float2 e0 = fma2(make_float2(dp[c], dp[c + 1]), sc2, dl0);      // scale * dP - scale * delta
-        float2 e1 = fma2(make_float2(dp[c + 2], dp[c + 3]), sc2, dl1);
-        if (cvalid < 16) {                              // ragged tail of the sample: P = dS = 0 beyond it
-          if (c >= cvalid) { p0.x = 0.f; e0.x = 0.f; }
-          if (c + 1 >= cvalid) { p0.y = 0.f; e0.y = 0.f; }
-          if (c + 2 >= cvalid) { p1.x = 0.f; e1.x = 0.f; }
-          if (c + 3 >= cvalid) { p1.y = 0.f; e1.y = 0.f; }
-        }
-        e0 = fma2(p0, e0, make_float2(0.f, 0.f));
-        e1 = fma2(p1, e1, make_float2(0.f, 0.f));
-        wp[c >> 1] = pack_bf16x2(p0.x, p0.y);
-        wp[(c >> 1) + 1] = pack_bf16x2(p1.x, p1.y);
-        wd[c >> 1] = pack_bf16x2(e0.x, e0.y);
-        wd[(c >> 1) + 1] = pack_bf16x2(e1.x, e1.y);
-      }
+      };
+      if (cvalid >= 16) body(std::false_type{}); else body(std::true_type{});
       if (warp == 4) ABWD_STAMP(6);
       if constexpr (kKV) tmem_st8(tS, wp);
       tmem_st8(tD, wd);
