@@ -48,7 +48,7 @@ struct AbGeo {
 // trace[i][0..3] = MMA warp (c_full seen, scores issued, pd_full seen, accumulations issued), [4..7] = row warp 4
 // (sd_full seen, TMEM loaded, math done, P/dS stored).
 #ifdef LDMAE_ATTN_TRACE
-#define ABWD_STAMP(k) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && i < 32) \
+#define ABWD_STAMP(k) do { if (p.trace && blockIdx.x == 0 && it == 0 && lane == 0 && i < 32) \
   p.trace[i * 8 + (k)] = clock64(); } while (0)
 #else
 #define ABWD_STAMP(k) do { } while (0)
@@ -74,7 +74,12 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
 template <bool kKV, int HD = 64>
 __global__ void __launch_bounds__(kAbThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_constant__ CUtensorMap tm_qkv_c,
-                const __grid_constant__ CUtensorMap tm_do_r, const __grid_constant__ CUtensorMap tm_do_c, const AttnBwdParams p) {
+                const __grid_constant__ CUtensorMap tm_do_r, const __grid_constant__ CUtensorMap tm_do_c, const AttnBwdParams p,
+                const int n_rblk, const int n_items) {
+  // Work items (row block, head, sample), row block fastest; CTA c takes items c, c + gridDim.x, ...: with one CTA per SM the
+  // kernel is persistent -- TMEM and barriers are set up once, the loader runs ahead across item boundaries (next row tiles
+  // and column ring in flight under the current item's tail), and barrier phases follow running counters:
+  //   g  column blocks processed so far (buffer g & 1, phase (g >> 1) & 1 of sd_full / pd_full)      it  items so far
   using Geo = AbGeo<HD>;
   constexpr int kAbStages = Geo::kStages, kAbRTile = Geo::kRTile, kAbCTile = Geo::kCTile, kAbStageBytes = Geo::kStageBytes;
   constexpr int kAtoms = Geo::kAtoms;
@@ -91,14 +96,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
   uint64_t* pd_full = sd_full + 2;           // [2] P and dS written back into buffer b (rows -> MMA)
   uint64_t* acc_done = pd_full + 2;          // all accumulations finished
   uint64_t* ra_ready = acc_done + 1;         // row operands copied into TMEM (rows -> MMA)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ra_ready + 1);
+  uint64_t* r_empty = ra_ready + 1;          // the row tiles in shared memory may be reloaded (HD 64: after the TMEM copy, by the
+                                             // copying warps; HD 128: after the item's last score product, by the MMA warp)
+  uint64_t* acc_free = r_empty + 1;          // the epilogue has read the accumulators (rows -> MMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int rblk = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
   const int ncb = (p.T + 63) / 64;           // column blocks
-  const int row_base = b * p.T;
-  const size_t vec_base = (static_cast<size_t>(b) * p.H + head) * p.T;
+  auto item_coords = [&](int w, int& rblk, int& head, int& b) {
+    rblk = w % n_rblk;
+    head = (w / n_rblk) % p.H;
+    b = w / (n_rblk * p.H);
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_qkv_r); tma_prefetch_desc(&tm_qkv_c); tma_prefetch_desc(&tm_do_r); tma_prefetch_desc(&tm_do_c);
@@ -107,7 +117,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
     mbar_init(r_full, 1);
     for (int s = 0; s < kAbStages; ++s) { mbar_init(&c_full[s], 1); mbar_init(&c_empty[s], 1); }
     for (int q = 0; q < 2; ++q) { mbar_init(&sd_full[q], 1); mbar_init(&pd_full[q], 16); }
-    mbar_init(acc_done, 1); mbar_init(ra_ready, 8);
+    mbar_init(acc_done, 1); mbar_init(ra_ready, 8); mbar_init(r_empty, HD == 64 ? 8 : 1); mbar_init(acc_free, 16);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<1>(tmem_slot, 512);
@@ -118,38 +128,46 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(r_full, 2 * kAbRTile);
-      // (dO is dense [B*T, H*hd]: for hd < HD its second atom runs into the next head's columns -- harmless: those columns
-      //  only meet the zero padding of V in dP, and the matching dV columns are stored as zeros)
-      for (int a = 0; a < kAtoms; ++a) {
-        if constexpr (kKV) {
-          tma_load_2d(&tm_qkv_r, r_full, sRa + a * Geo::kRAtom, p.k_col + head * HD + a * 64, row_base + rblk * 128);
-          tma_load_2d(&tm_qkv_r, r_full, sRb + a * Geo::kRAtom, p.v_col + head * HD + a * 64, row_base + rblk * 128);
-        } else {
-          tma_load_2d(&tm_qkv_r, r_full, sRa + a * Geo::kRAtom, p.q_col + head * HD + a * 64, row_base + rblk * 128);
-          tma_load_2d(&tm_do_r, r_full, sRb + a * Geo::kRAtom, head * p.hd + a * 64, row_base + rblk * 128);
-        }
-      }
       int stage = 0; uint32_t phase = 0;
-      for (int i = 0; i < ncb; ++i) {
-        mbar_wait(&c_empty[stage], phase ^ 1, 10);
-        uint8_t* st = sC + stage * kAbStageBytes;
-        if constexpr (kKV) {
-          mbar_expect_tx(&c_full[stage], 2 * kAbCTile + 512);
-          for (int a = 0; a < kAtoms; ++a) {
-            tma_load_2d(&tm_qkv_c, &c_full[stage], st + a * Geo::kCAtom, p.q_col + head * HD + a * 64, row_base + i * 64);
-            tma_load_2d(&tm_do_c, &c_full[stage], st + kAbCTile + a * Geo::kCAtom, head * p.hd + a * 64, row_base + i * 64);
-          }
-          bulk_load_1d(st + 2 * kAbCTile, p.nlse2 + vec_base + i * 64, 256, &c_full[stage]);
-          bulk_load_1d(st + 2 * kAbCTile + 256, p.delta + vec_base + i * 64, 256, &c_full[stage]);
-        } else {
-          mbar_expect_tx(&c_full[stage], 2 * kAbCTile);
-          for (int a = 0; a < kAtoms; ++a) {
-            tma_load_2d(&tm_qkv_c, &c_full[stage], st + a * Geo::kCAtom, p.k_col + head * HD + a * 64, row_base + i * 64);
-            tma_load_2d(&tm_qkv_c, &c_full[stage], st + kAbCTile + a * Geo::kCAtom, p.v_col + head * HD + a * 64, row_base + i * 64);
+      int it = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+        int rblk, head, b;
+        item_coords(w, rblk, head, b);
+        const int row_base = b * p.T;
+        const size_t vec_base = (static_cast<size_t>(b) * p.H + head) * p.T;
+        if (it > 0) mbar_wait(r_empty, (it - 1) & 1, 12);
+        mbar_expect_tx(r_full, 2 * kAbRTile);
+        // (dO is dense [B*T, H*hd]: for hd < HD its second atom runs into the next head's columns -- harmless: those columns
+        //  only meet the zero padding of V in dP, and the matching dV columns are stored as zeros)
+        for (int a = 0; a < kAtoms; ++a) {
+          if constexpr (kKV) {
+            tma_load_2d(&tm_qkv_r, r_full, sRa + a * Geo::kRAtom, p.k_col + head * HD + a * 64, row_base + rblk * 128);
+            tma_load_2d(&tm_qkv_r, r_full, sRb + a * Geo::kRAtom, p.v_col + head * HD + a * 64, row_base + rblk * 128);
+          } else {
+            tma_load_2d(&tm_qkv_r, r_full, sRa + a * Geo::kRAtom, p.q_col + head * HD + a * 64, row_base + rblk * 128);
+            tma_load_2d(&tm_do_r, r_full, sRb + a * Geo::kRAtom, head * p.hd + a * 64, row_base + rblk * 128);
           }
         }
-        if (++stage == kAbStages) { stage = 0; phase ^= 1; }
+        for (int i = 0; i < ncb; ++i) {
+          mbar_wait(&c_empty[stage], phase ^ 1, 10);
+          uint8_t* st = sC + stage * kAbStageBytes;
+          if constexpr (kKV) {
+            mbar_expect_tx(&c_full[stage], 2 * kAbCTile + 512);
+            for (int a = 0; a < kAtoms; ++a) {
+              tma_load_2d(&tm_qkv_c, &c_full[stage], st + a * Geo::kCAtom, p.q_col + head * HD + a * 64, row_base + i * 64);
+              tma_load_2d(&tm_do_c, &c_full[stage], st + kAbCTile + a * Geo::kCAtom, head * p.hd + a * 64, row_base + i * 64);
+            }
+            bulk_load_1d(st + 2 * kAbCTile, p.nlse2 + vec_base + i * 64, 256, &c_full[stage]);
+            bulk_load_1d(st + 2 * kAbCTile + 256, p.delta + vec_base + i * 64, 256, &c_full[stage]);
+          } else {
+            mbar_expect_tx(&c_full[stage], 2 * kAbCTile);
+            for (int a = 0; a < kAtoms; ++a) {
+              tma_load_2d(&tm_qkv_c, &c_full[stage], st + a * Geo::kCAtom, p.k_col + head * HD + a * 64, row_base + i * 64);
+              tma_load_2d(&tm_qkv_c, &c_full[stage], st + kAbCTile + a * Geo::kCAtom, p.v_col + head * HD + a * 64, row_base + i * 64);
+            }
+          }
+          if (++stage == kAbStages) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -189,48 +207,64 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       }
       __syncwarp();
     };
-    if constexpr (HD == 64) mbar_wait(ra_ready, 0, 20); else mbar_wait(r_full, 0, 20);
-    tc_fence_after();
-    int stage = 0; uint32_t phase = 0;                 // ring position of block i
-    mbar_wait(&c_full[0], 0, 21);
-    tc_fence_after();
-    issue_scores(0, 0);
-    for (int i = 0; i < ncb; ++i) {
-      int nstage = stage + 1; uint32_t nphase = phase;
-      if (nstage == kAbStages) { nstage = 0; nphase ^= 1; }
-      if (i + 1 < ncb) {
-        // scores of block i+1 into the other buffer (its previous user, block i-1, was consumed by MMAs issued earlier)
-        mbar_wait(&c_full[nstage], nphase, 23);
-        tc_fence_after();
-        ABWD_STAMP(0);
-        issue_scores(nstage, (i + 1) & 1);
-        ABWD_STAMP(1);
-      }
-      mbar_wait(&pd_full[i & 1], (i >> 1) & 1, 22);
+    int stage = 0; uint32_t phase = 0;                 // ring position of the current block
+    int g = 0, it = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+      if constexpr (HD == 64) mbar_wait(ra_ready, it & 1, 20); else mbar_wait(r_full, it & 1, 20);
+      mbar_wait(&c_full[stage], phase, 21);
       tc_fence_after();
-      ABWD_STAMP(2);
-      const uint64_t d_ca = d_c0 + static_cast<uint64_t>((stage * kAbStageBytes) >> 4), d_cb = d_ca + (kAbCTile >> 4);
-      const uint32_t tb = tmem_base + (i & 1) * 128;
-      const uint32_t acc_first = i != 0 ? 1u : 0u;
-      if (issuer) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)     // 4 x 16 columns of the block; A = dS: 16 bf16 = 8 TMEM columns at column 16 k
-          umma_bf16_ts(tmem_base + Geo::kAcc1, tb + 64 + k * 16, d_ca + 128 * k, idesc_ts, k != 0 ? 1u : acc_first);
-        if constexpr (kKV) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ts(tmem_base + Geo::kAcc2, tb + k * 16, d_cb + 128 * k, idesc_ts, k != 0 ? 1u : acc_first);
+      // (buffer g & 1 was last used by block g - 2, whose accumulations were issued before this point)
+      issue_scores(stage, g & 1);
+      if (HD != 64 && ncb == 1) { if (issuer) umma_commit<1>(r_empty); __syncwarp(); }
+      for (int i = 0; i < ncb; ++i, ++g) {
+        int nstage = stage + 1; uint32_t nphase = phase;
+        if (nstage == kAbStages) { nstage = 0; nphase ^= 1; }
+        if (i + 1 < ncb) {
+          // scores of block i+1 into the other buffer (its previous user, block g-1, was consumed by MMAs issued earlier)
+          mbar_wait(&c_full[nstage], nphase, 23);
+          tc_fence_after();
+          ABWD_STAMP(0);
+          issue_scores(nstage, (g + 1) & 1);
+          if (HD != 64 && i + 2 == ncb) { if (issuer) umma_commit<1>(r_empty); __syncwarp(); }   // last read of the row tiles
+          ABWD_STAMP(1);
         }
-        umma_commit<1>(&c_empty[stage]);
-        if (i == ncb - 1) umma_commit<1>(acc_done);
+        mbar_wait(&pd_full[g & 1], (g >> 1) & 1, 22);
+        // the first accumulation of an item overwrites the accumulators: the previous item's epilogue must have read them
+        if (i == 0 && it > 0) mbar_wait(acc_free, (it - 1) & 1, 27);
+        tc_fence_after();
+        ABWD_STAMP(2);
+        const uint64_t d_ca = d_c0 + static_cast<uint64_t>((stage * kAbStageBytes) >> 4), d_cb = d_ca + (kAbCTile >> 4);
+        const uint32_t tb = tmem_base + (g & 1) * 128;
+        const uint32_t acc_first = i != 0 ? 1u : 0u;
+        if (issuer) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)     // 4 x 16 columns of the block; A = dS: 16 bf16 = 8 TMEM columns at column 16 k
+            umma_bf16_ts(tmem_base + Geo::kAcc1, tb + 64 + k * 16, d_ca + 128 * k, idesc_ts, k != 0 ? 1u : acc_first);
+          if constexpr (kKV) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16_ts(tmem_base + Geo::kAcc2, tb + k * 16, d_cb + 128 * k, idesc_ts, k != 0 ? 1u : acc_first);
+          }
+          umma_commit<1>(&c_empty[stage]);
+          if (i == ncb - 1) umma_commit<1>(acc_done);
+        }
+        __syncwarp();
+        ABWD_STAMP(3);
+        stage = nstage; phase = nphase;
       }
-      __syncwarp();
-      ABWD_STAMP(3);
-      stage = nstage; phase = nphase;
     }
   } else if (warp >= 4) {
     const int wq = warp & 3;                           // TMEM lane quarter
     const int cq = (warp - 4) >> 2;                    // which 16 of the block's 64 columns this warp works on
     const uint32_t lane_addr = static_cast<uint32_t>(wq * 32) << 16;
+    const float2 sl2 = make_float2(p.scale_log2, p.scale_log2), sc2 = make_float2(p.scale, p.scale);
+    int stage = 0;
+    uint32_t cphase = 0;
+    int g = 0, it = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+    int rblk, head, b;
+    item_coords(w, rblk, head, b);
+    const int row_base = b * p.T;
+    const size_t vec_base = (static_cast<size_t>(b) * p.H + head) * p.T;
     const int row = rblk * 128 + wq * 32 + lane;       // token index inside the sample
     float2 nl_r = make_float2(0.f, 0.f), dl_r = make_float2(0.f, 0.f);
     if constexpr (!kKV) {
@@ -239,35 +273,33 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
         nl_r = make_float2(a, a); dl_r = make_float2(-d, -d);
       }
     }
-    const float2 sl2 = make_float2(p.scale_log2, p.scale_log2), sc2 = make_float2(p.scale, p.scale);
     if (HD == 64 && cq < 2) {
-      // The row operands (Q | K and dO | V rows of this CTA) are the A operand of every score product: copy them once
+      // The row operands (Q | K and dO | V rows of this item) are the A operand of every score product: copy them once
       // from their TMA tiles into TMEM (bf16 pairs, one row per lane), so that the score MMAs read only the 2 KB column
       // tile from shared memory per instruction (an SS product of this shape is shared-memory-bandwidth bound).
-      mbar_wait(r_full, 0, 28);
+      // (The previous item's score products are complete: this warp has consumed its last sd_full.)
+      mbar_wait(r_full, it & 1, 28);
       const uint8_t* src = (cq == 0 ? sRa : sRb) + (wq * 32 + lane) * 128;
-      uint32_t w[32];
+      uint32_t wr[32];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const uint4 v = lds128(src + ((j ^ (lane & 7)) << 4));
-        w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
+        wr[4 * j] = v.x; wr[4 * j + 1] = v.y; wr[4 * j + 2] = v.z; wr[4 * j + 3] = v.w;
       }
-      tmem_st32(tmem_base + lane_addr + 384 + cq * 32, w);
+      tmem_st32(tmem_base + lane_addr + 384 + cq * 32, wr);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(ra_ready);
+      if (lane == 0) { mbar_arrive(ra_ready); mbar_arrive(r_empty); }
     }
-    int stage = 0;
-    uint32_t cphase = 0;
 #pragma unroll 1
-    for (int i = 0; i < ncb; ++i) {
+    for (int i = 0; i < ncb; ++i, ++g) {
       if constexpr (kKV) mbar_wait(&c_full[stage], cphase, 29);   // this thread reads the stage's statistics vectors itself
-      mbar_wait(&sd_full[i & 1], (i >> 1) & 1, 30);
+      mbar_wait(&sd_full[g & 1], (g >> 1) & 1, 30);
       __syncwarp();
       tc_fence_after();
       if (warp == 4) ABWD_STAMP(4);
-      const uint32_t tS = tmem_base + lane_addr + (i & 1) * 128 + cq * 16, tD = tS + 64;
+      const uint32_t tS = tmem_base + lane_addr + (g & 1) * 128 + cq * 16, tD = tS + 64;
       const float* vl = reinterpret_cast<const float*>(sC + stage * kAbStageBytes + 2 * kAbCTile) + cq * 16;
       const float* vd = vl + 64;
       const int cvalid = p.T - i * 64 - cq * 16;       // columns of this warp's quarter that exist
@@ -319,33 +351,40 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       if (warp == 4) ABWD_STAMP(7);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&pd_full[i & 1]);
+      if (lane == 0) mbar_arrive(&pd_full[g & 1]);
       if (++stage == kAbStages) { stage = 0; cphase ^= 1; }
     }
     // epilogue: accumulators -> bf16 rows of dqkv; this warp stores columns [HD/4 * cq, HD/4 * (cq + 1)) of each accumulator
     // (the tcgen05.ld is warp-collective: only the stores are predicated)
-    mbar_wait(acc_done, 0, 31);
+    mbar_wait(acc_done, it & 1, 31);
     __syncwarp();
     tc_fence_after();
     constexpr int kEC = HD / 4;                         // columns per warp: 16 or 32
+    float o[kKV ? 2 : 1][kEC];
+#pragma unroll
+    for (int a = 0; a < (kKV ? 2 : 1); ++a) {
+      const uint32_t ta = tmem_base + lane_addr + (a == 0 ? Geo::kAcc1 : Geo::kAcc2) + cq * kEC;
+      if constexpr (kEC == 16) tmem_ld16(ta, o[a]); else tmem_ld32(ta, o[a]);
+    }
+    tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(acc_free);               // the next item's first accumulation may overwrite the accumulators
 #pragma unroll
     for (int a = 0; a < (kKV ? 2 : 1); ++a) {
       const int col = (kKV ? (a == 0 ? p.k_col : p.v_col) : p.q_col) + head * HD + cq * kEC;
       __nv_bfloat16* dst = p.dqkv + static_cast<size_t>(row_base + min(row, p.T - 1)) * p.ld + col;
-      float o[kEC];
-      const uint32_t ta = tmem_base + lane_addr + (a == 0 ? Geo::kAcc1 : Geo::kAcc2) + cq * kEC;
-      if constexpr (kEC == 16) tmem_ld16(ta, o); else tmem_ld32(ta, o);
-      tmem_ld_wait();
       if (row < p.T) {
 #pragma unroll
         for (int q = 0; q < kEC / 8; ++q) {
           const bool real = cq * kEC + q * 8 < p.hd;    // head_dim is a multiple of 8: whole 16-byte groups are real or padding
           *reinterpret_cast<uint4*>(dst + q * 8) = real ?
-              make_uint4(pack_bf16x2(o[8 * q], o[8 * q + 1]), pack_bf16x2(o[8 * q + 2], o[8 * q + 3]),
-                         pack_bf16x2(o[8 * q + 4], o[8 * q + 5]), pack_bf16x2(o[8 * q + 6], o[8 * q + 7])) : make_uint4(0u, 0u, 0u, 0u);
+              make_uint4(pack_bf16x2(o[a][8 * q], o[a][8 * q + 1]), pack_bf16x2(o[a][8 * q + 2], o[a][8 * q + 3]),
+                         pack_bf16x2(o[a][8 * q + 4], o[a][8 * q + 5]), pack_bf16x2(o[a][8 * q + 6], o[a][8 * q + 7])) : make_uint4(0u, 0u, 0u, 0u);
         }
       }
     }
+    }   // work items
   }
 
   __syncwarp();

@@ -298,10 +298,16 @@ static int run_attention_bwd_t(const void* qkv, int ldq, const void* o, const vo
   p.nlse2 = nlse2; p.delta = delta; p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
   p.T = T; p.H = H; p.ld = ldq; p.q_col = q_col; p.k_col = k_col; p.v_col = v_col; p.hd = hd;
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
-  dim3 grid(cdiv(T, 128), H, B);
-  attn_bwd_kernel<true, HW><<<grid, kAbThreads, kSmem, st>>>(tqr, tqc, tdr, tdc, p);
+  // work items = (row block, head, sample); one CTA per SM walks them (persistent) unless LDMAE_ATTN_BWD_PERSIST=0
+  const int n_rblk = static_cast<int>(cdiv(T, 128));
+  const long long items = static_cast<long long>(n_rblk) * H * B;
+  LDMAE_REQUIRE(items < (1ll << 31), "attention backward: too many work items");
+  static int persist = -1;
+  if (persist < 0) { const char* e = getenv("LDMAE_ATTN_BWD_PERSIST"); persist = e ? atoi(e) : 1; }
+  const unsigned ctas = static_cast<unsigned>(persist ? std::min<long long>(items, device_sm_count()) : items);
+  attn_bwd_kernel<true, HW><<<ctas, kAbThreads, kSmem, st>>>(tqr, tqc, tdr, tdc, p, n_rblk, static_cast<int>(items));
   LDMAE_LAUNCH_CHECK();
-  attn_bwd_kernel<false, HW><<<grid, kAbThreads, kSmem, st>>>(tqr, tqc, tdr, tdc, p);
+  attn_bwd_kernel<false, HW><<<ctas, kAbThreads, kSmem, st>>>(tqr, tqc, tdr, tdc, p, n_rblk, static_cast<int>(items));
   LDMAE_LAUNCH_CHECK();
   return LDMAE_OK;
 }
