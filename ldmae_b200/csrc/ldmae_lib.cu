@@ -340,9 +340,18 @@ static int gemm_wgrad(const void* pm, int ldp, const void* qm, int ldq, float* c
   const int tiles = ((N1 + kBM * CG - 1) / (kBM * CG)) * ((N2 + BN - 1) / BN);
   const int num_kb = (M + kBK - 1) / kBK;
   const int clusters = device_sm_count() / CG;
-  // split the contraction so that every cluster gets work: about two waves of units, at least 8 k-blocks per unit
-  int splits = std::max(1, (2 * clusters + tiles - 1) / tiles);
-  splits = std::min(splits, std::max(1, num_kb / 8));
+  // split the contraction so that the units fill whole waves of clusters: among the split counts that keep at least 8
+  // k-blocks per unit and give about two to four waves, take the one with the best last-wave occupancy
+  const int max_splits = std::max(1, num_kb / 8);
+  int splits = 1;
+  double best = -1.0;
+  for (int s = 1; s <= max_splits && static_cast<long long>(tiles) * s <= 4ll * clusters + tiles; ++s) {
+    const long long units = static_cast<long long>(tiles) * s;
+    const long long waves = (units + clusters - 1) / clusters;
+    const double eff = static_cast<double>(units) / static_cast<double>(waves * clusters);
+    const double score = eff - (units < 2ll * clusters ? 0.15 : 0.0) - 1e-4 * s;     // prefer >= 2 waves (tail hiding), then fewer splits
+    if (score > best) { best = score; splits = s; }
+  }
   int kb_per = (num_kb + splits - 1) / splits;
   splits = (num_kb + kb_per - 1) / kb_per;            // no empty unit
   WgradShape g{N1, N2, M, splits, kb_per};
