@@ -180,6 +180,11 @@ int ldmae_attention_wide_bwd(const void* qkv_bf16, const void* out_bf16, const v
  * lse2 may be NULL. */
 int ldmae_attention_bounded(const void* qkv_bf16, void* out_bf16, float* lse2, int32_t B, int32_t T, int32_t H, float scale,
                             float m0_log2, void* stream);
+/* The bounded-score attention for q that already carries scale * log2(e) (the inference forward folds both into
+ * q_norm.weight in the QKV epilogue): probabilities are 2^(q.k) with no per-score multiply-add; |q.k| <= m0_log2 <= 48.
+ * lse2 (log2 units) may be NULL. */
+int ldmae_attention_prescaled(const void* qkv_bf16, void* out_bf16, float* lse2, int32_t B, int32_t T, int32_t H,
+                              float m0_log2, void* stream);
 /* Gradient of ldmae_attention (the backward of F.scaled_dot_product_attention at models/lightningdit.py:77):
  * dqkv [B*T, 3*H*64] bf16 (dq | dk | dv, same layout as qkv) from dout [B*T, H*64] bf16, the forward's out and lse2;
  * delta_ws: workspace of 2 * (B*H*T + 64) floats.  T must be a multiple of 4. */

@@ -63,6 +63,7 @@ SYMBOLS = {
     "ldmae_attention_wide_lse": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, f32, vp]),
     "ldmae_attention_wide_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp]),
     "ldmae_attention_bounded": (C.c_int, [vp, vp, vp, i32, i32, i32, f32, f32, vp]),
+    "ldmae_attention_prescaled": (C.c_int, [vp, vp, vp, i32, i32, i32, f32, vp]),
     "ldmae_attention_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp]),
     "ldmae_gemm_wgrad": (C.c_int, [vp, vp, vp, i32, i32, i32, f32, vp]),
     "ldmae_attention_trace": (C.c_int, [vp]),

@@ -20,7 +20,48 @@ namespace ldmae {
 
 constexpr int kAttnPSmemBytes = kAttnSmemBytes + 2 * kAttnTileBytes;    // + output staging
 
-template <bool kFixedMax>
+// kPipe (requires kFixedMax): the softmax warps software-pipeline their TMEM traffic under the exponentials.  Without a row
+// maximum a thread needs no look at the whole block before its first exponential, so the 128 scores of a step are taken in
+// four 32-column chunks: the loads of chunks 2,3 are in flight under the exponentials of chunk 0 (S_t goes back to the
+// tensor core after chunk 0 instead of before it), every chunk's P columns are stored as soon as they are packed, and the
+// first two chunks of the NEXT step (next key block, or the next item's first block) are fetched under the exponentials of
+// chunk 3 when their scores are already there.  A warp then issues MUFU work almost without gaps, instead of
+// load -> exponentials -> store phases in lockstep with the other tile's warp on the same SM sub-partition.
+#ifndef LDMAE_ATTN_POLY_NUM
+#define LDMAE_ATTN_POLY_NUM 3
+#endif
+#ifndef LDMAE_ATTN_POLY_DEN
+#define LDMAE_ATTN_POLY_DEN 8
+#endif
+// pair q (of 64 per step) takes the FMA-pipe polynomial: kNum of every kDen pairs, evenly spread
+__host__ __device__ constexpr bool attn_pair_is_poly(int q) {
+  return ((q * LDMAE_ATTN_POLY_NUM) % LDMAE_ATTN_POLY_DEN) < LDMAE_ATTN_POLY_NUM;
+}
+// one 32-column chunk of a row: exponentials (MUFU / polynomial), partial row sums, bf16 pack -> 16 packed P columns
+// kRaw: the scores already are the exponents (q pre-multiplied by scale * log2e, no offset: |s| <= m0 <= 48)
+template <int kChunk, bool kRaw = false>
+__device__ __forceinline__ void attn_exp_chunk(const float* s, const float2 sc2, const float2 neg2, float2& ls0, float2& ls1,
+                                               uint32_t* wv) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float2 x0 = kRaw ? make_float2(s[i], s[i + 1]) : fma2(make_float2(s[i], s[i + 1]), sc2, neg2);
+    const float2 x1 = kRaw ? make_float2(s[i + 2], s[i + 3]) : fma2(make_float2(s[i + 2], s[i + 3]), sc2, neg2);
+    const float2 p0 = attn_pair_is_poly(kChunk * 16 + i / 2) ? ex2_poly2_bounded(x0) : make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
+    const float2 p1 = attn_pair_is_poly(kChunk * 16 + i / 2 + 1) ? ex2_poly2_bounded(x1) : make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
+    ls0 = add2(ls0, p0);
+    ls1 = add2(ls1, p1);
+    wv[i >> 1] = pack_bf16x2(p0.x, p0.y);
+    wv[(i >> 1) + 1] = pack_bf16x2(p1.x, p1.y);
+  }
+}
+
+#ifdef LDMAE_ATTN_TRACE
+#define ATTN_PSTAMP(k, v) do { if (p.trace && blockIdx.x == 0 && lane == 0 && wq == 0 && g < 64) p.trace[((t * 64 + g) * 8) + (k)] = (v); } while (0)
+#else
+#define ATTN_PSTAMP(k, v) do { } while (0)
+#endif
+
+template <bool kFixedMax, bool kPipe = false, bool kRaw = false>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out, const AttnParams p,
                         const int n_qpairs, const int n_items) {
@@ -194,12 +235,90 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
     const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
     uint8_t* stage_o = sO + t * kAttnTileBytes + wq * 4096;
     int g = 0, it = 0;
+    float sA[32], sB[32], sC[32], sD[32];                // kPipe: the four score chunks of a step (sA, sB live across steps)
+    bool pre = false;                                    // kPipe: sA, sB already hold the next step's first two chunks
     for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
       int qpair, head, b;
       item_coords(w, qpair, head, b);
       const int row_base = b * p.T;
-      float m_used = kFixedMax ? p.m0_log2 / p.scale_log2 : -INFINITY;
+      float m_used = kRaw ? 0.f : (kFixedMax ? p.m0_log2 / p.scale_log2 : -INFINITY);
       float l_run = 0.f;
+      if constexpr (kPipe) {
+        static_assert(kFixedMax, "the pipelined softmax needs the constant-offset instantiation");
+        static_assert(kPipe || !kRaw, "raw exponents exist only in the pipelined instantiation");
+        const float2 neg2 = make_float2(-p.m0_log2, -p.m0_log2);
+        // (the host selects this instantiation only for T % 128 == 0: no masked keys)
+        float2 ls0 = make_float2(0.f, 0.f), ls1 = make_float2(0.f, 0.f);
+#pragma unroll 1
+        for (int j = 0; j < nkv; ++j, ++g) {
+          bool s_released;
+          ATTN_PSTAMP(0, clock64());
+          ATTN_PSTAMP(7, pre ? 1 : 0);
+          if (!pre) {
+            // nothing fetched ahead (first step of the CTA, or the scores were late): the whole row, then release S_t
+            mbar_wait_quiet(&s_full[t], g & 1);
+            __syncwarp();
+            tc_fence_after();
+            tmem_ld32(tS, sA);
+            tmem_ld32(tS + 32, sB);
+            tmem_ld32(tS + 64, sC);
+            tmem_ld32(tS + 96, sD);
+            tmem_ld_wait();
+            tmem_ld_pin32(sA); tmem_ld_pin32(sB); tmem_ld_pin32(sC); tmem_ld_pin32(sD);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[t]);
+            s_released = true;
+          } else {
+            // chunks 0,1 arrived under the previous step's last exponentials; 2,3 load under chunk 0's
+            tmem_ld32(tS + 64, sC);
+            tmem_ld32(tS + 96, sD);
+            s_released = false;
+          }
+          ATTN_PSTAMP(1, clock64());
+          uint32_t wv[16];
+          attn_exp_chunk<0, kRaw>(sA, sc2, neg2, ls0, ls1, wv);
+          // P_t may only be overwritten after the previous P_t V has been read (the previous block of this CTA, whichever item)
+          if (g > 0) mbar_wait_quiet(&o_done[t], (g - 1) & 1);
+          __syncwarp();
+          tc_fence_after();
+          tmem_st16(tP, wv);
+          ATTN_PSTAMP(2, clock64());
+          if (!s_released) {
+            tmem_ld_wait();
+            tmem_ld_pin32(sC); tmem_ld_pin32(sD);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[t]);          // the tensor core may overwrite S_t with the next block
+          }
+          ATTN_PSTAMP(3, clock64());
+          attn_exp_chunk<1, kRaw>(sB, sc2, neg2, ls0, ls1, wv);
+          tmem_st16(tP + 16, wv);
+          attn_exp_chunk<2, kRaw>(sC, sc2, neg2, ls0, ls1, wv);
+          tmem_st16(tP + 32, wv);
+          // the next step's scores (next key block / next item's first block), if the tensor core has delivered them
+          ATTN_PSTAMP(4, clock64());
+          pre = __all_sync(0xffffffffu, mbar_probe(&s_full[t], (g + 1) & 1) != 0);
+          if (pre) {
+            tc_fence_after();
+            tmem_ld32(tS, sA);
+            tmem_ld32(tS + 32, sB);
+          }
+          ATTN_PSTAMP(5, clock64());
+          attn_exp_chunk<3, kRaw>(sD, sc2, neg2, ls0, ls1, wv);
+          tmem_st16(tP + 48, wv);
+          if (pre) {
+            tmem_ld_wait();
+            tmem_ld_pin32(sA); tmem_ld_pin32(sB);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[t]);
+          ATTN_PSTAMP(6, clock64());
+        }
+        l_run = (ls0.x + ls0.y) + (ls1.x + ls1.y);
+      } else {
 #pragma unroll 1
       for (int j = 0; j < nkv; ++j, ++g) {
         mbar_wait(&s_full[t], g & 1, 30 + t);
@@ -290,6 +409,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[t]);
+      }
       }
       // epilogue of the item: O_t / l -> bf16 -> global (own staging tile + one TMA store per warp)
       mbar_wait(&o_done[t], (g - 1) & 1, 34 + t);

@@ -54,6 +54,8 @@ struct AttnParams {
   float scale_log2;         // softmax scale * log2(e)
   float m0_log2;            // kFixedMax: upper bound of |score * scale_log2| used as the constant softmax offset
   int alternate;            // 1: the two query tiles take turns on the exponentials (explicit ping-pong), 0: free running
+  int raw;                  // 1: q arrives pre-multiplied by scale * log2(e) (scale_log2 == 1); kernels that support it take
+                            //    2^score without scale or offset (|score| <= m0_log2 <= 48 keeps every sum inside fp32 / bf16)
 };
 
 // kFixedMax: q and k are RMS-normed per head (reference models/lightningdit.py:70), so |q||k| * scale is bounded by a

@@ -431,6 +431,8 @@ struct EpiQKV : StoreRing {
     const float* rope;      // [2, grid, 32] or nullptr
     int D, rows_per_sample, ss_slots, grid;
     float inv_D, eps_row, eps_head;
+    float q_mul;            // extra factor on q_norm.weight: 1, or softmax scale * log2(e) when the attention kernel takes
+                            // its exponents straight from the scores (inference forward, run_attention prescaled)
   };
   static __device__ __forceinline__ bool rope_in_smem(const Params& p) {
     return p.rope != nullptr && 2 * p.grid * kRopePitch * 4 <= kCtaBytes;
@@ -471,8 +473,10 @@ struct EpiQKV : StoreRing {
     float* vnw = vcv + 256;                                        // [64 q_norm | 64 k_norm]
     if (staged) stage_vec(vcv, cv, n0 + cbase, GC, g.N, lane);
     if (p.qw != nullptr) {
-      *reinterpret_cast<float4*>(vnw + lane * 4) =
-          lane < 16 ? __ldg(reinterpret_cast<const float4*>(p.qw) + lane) : __ldg(reinterpret_cast<const float4*>(p.kw) + lane - 16);
+      float4 nw4 = lane < 16 ? __ldg(reinterpret_cast<const float4*>(p.qw) + lane) : __ldg(reinterpret_cast<const float4*>(p.kw) + lane - 16);
+      const float mul = lane < 16 ? p.q_mul : 1.f;
+      nw4.x *= mul; nw4.y *= mul; nw4.z *= mul; nw4.w *= mul;
+      *reinterpret_cast<float4*>(vnw + lane * 4) = nw4;
     }
     __syncwarp();
     const bool rsm = kFast || rope_in_smem(p);

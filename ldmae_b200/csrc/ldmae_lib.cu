@@ -197,7 +197,8 @@ extern "C" int ldmae_attention_trace(long long* dev_buf) { g_attn_trace = dev_bu
 
 // m0_log2 > 0: the scores are bounded (|s * scale * log2e| <= m0_log2): constant-offset softmax instantiation
 static int run_attention(const void* qkv, int ldq, void* out, int ldo, int B, int T, int H, int q_col, int k_col,
-                         int v_col, float scale, cudaStream_t st, float* lse2 = nullptr, float m0_log2 = -1.f) {
+                         int v_col, float scale, cudaStream_t st, float* lse2 = nullptr, float m0_log2 = -1.f,
+                         bool prescaled = false) {
   CUtensorMap tm, tmo;
   LDMAE_TRY(make_tmap_bf16(&tm, qkv, B * T, ldq, ldq, 128));
   LDMAE_TRY(make_tmap_out_bf16(&tmo, out, B * T, H * 64, ldo));
@@ -208,6 +209,8 @@ static int run_attention(const void* qkv, int ldq, void* out, int ldo, int B, in
     LDMAE_CUDA((cudaFuncSetAttribute(attn_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes)));
     LDMAE_CUDA(cudaFuncSetAttribute(attn_fwd_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnPSmemBytes));
     LDMAE_CUDA(cudaFuncSetAttribute(attn_fwd_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnPSmemBytes));
+    LDMAE_CUDA((cudaFuncSetAttribute(attn_fwd_persist_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnPSmemBytes)));
+    LDMAE_CUDA((cudaFuncSetAttribute(attn_fwd_persist_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnPSmemBytes)));
     attr = true;
   }
   AttnParams p;
@@ -216,8 +219,10 @@ static int run_attention(const void* qkv, int ldq, void* out, int ldo, int B, in
   p.lse2 = lse2;
   p.T = T; p.H = H; p.ldo = ldo;
   p.q_col = q_col; p.k_col = k_col; p.v_col = v_col;
-  p.scale_log2 = scale * 1.4426950408889634f;
+  // prescaled: q already carries scale * log2(e) (EpiQKV::Params::q_mul), every kernel sees a unit scale
+  p.scale_log2 = prescaled ? 1.f : scale * 1.4426950408889634f;
   p.m0_log2 = m0_log2;
+  p.raw = prescaled ? 1 : 0;
   // measured (B=128, T=1024, H=12; tools/bench_attn.py): taking turns helps the tracking instantiation (561 -> 594 TFLOP/s)
   // and is neutral-to-negative for the constant-offset one (605 vs 599); LDMAE_ATTN_ALTERNATE=0/1 forces either
   static int alt = -2;
@@ -236,7 +241,13 @@ static int run_attention(const void* qkv, int ldq, void* out, int ldo, int B, in
     const long long items = static_cast<long long>(n_qpairs) * H * B;
     LDMAE_REQUIRE(items < (1ll << 31), "attention: too many work items");
     const unsigned ctas = static_cast<unsigned>(std::min<long long>(items, device_sm_count()));
-    if (m0_log2 > 0.f) attn_fwd_persist_kernel<true><<<ctas, kAttnThreads, kAttnPSmemBytes, st>>>(tm, tmo, p, n_qpairs, static_cast<int>(items));
+    // software-pipelined softmax warps (attention_persist_sm100.cuh, kPipe): 644 -> 765 TFLOP/s standalone;
+    // LDMAE_ATTN_PIPE=0 keeps the phase-by-phase loop
+    static int pipe = -1;
+    if (pipe < 0) { const char* e = getenv("LDMAE_ATTN_PIPE"); pipe = e ? atoi(e) : 1; }
+    if (m0_log2 > 0.f && pipe && T % 128 == 0 && prescaled) attn_fwd_persist_kernel<true, true, true><<<ctas, kAttnThreads, kAttnPSmemBytes, st>>>(tm, tmo, p, n_qpairs, static_cast<int>(items));
+    else if (m0_log2 > 0.f && pipe && T % 128 == 0) attn_fwd_persist_kernel<true, true><<<ctas, kAttnThreads, kAttnPSmemBytes, st>>>(tm, tmo, p, n_qpairs, static_cast<int>(items));
+    else if (m0_log2 > 0.f) attn_fwd_persist_kernel<true><<<ctas, kAttnThreads, kAttnPSmemBytes, st>>>(tm, tmo, p, n_qpairs, static_cast<int>(items));
     else attn_fwd_persist_kernel<false><<<ctas, kAttnThreads, kAttnPSmemBytes, st>>>(tm, tmo, p, n_qpairs, static_cast<int>(items));
   }
   else if (m0_log2 > 0.f && wide) attn_fwd_kernel<true, true><<<grid, 640, kAttnSmemBytes, st>>>(tm, tmo, p);
@@ -830,12 +841,16 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
       eq.qw = c.use_qknorm ? b.qw.p : nullptr; eq.kw = c.use_qknorm ? b.kw.p : nullptr;
       eq.rope = c.use_rope ? h->rope_tab.p : nullptr; eq.grid = h->G;
       eq.D = D; eq.rows_per_sample = T; eq.ss_slots = h->SS; eq.inv_D = 1.f / D; eq.eps_row = eps; eq.eps_head = eps;
+      // inference forward of qk-normed heads: the softmax scale and log2(e) ride on q_norm.weight, the attention kernel takes
+      // 2^score directly (no per-score multiply-add); the training forward keeps the plain q the backward kernels expect
+      const bool presc = tr == nullptr && c.use_qknorm && b.attn_m0_log2 > 0.f;
+      eq.q_mul = presc ? 0.125f * 1.4426950408889634f : 1.f;
       { ProfScope ps(0, st); LDMAE_TRY((gemm_auto<EpiQKV>(As(2 * i), D, b.w_qkv.p, D, GemmShape{M, 3 * D, D}, eq, st))); }
       LDMAE_DBG_STAGE();
       {
         ProfScope ps(1, st);
         float* lse = tr ? tr->LSE.p + static_cast<size_t>(i) * B * c.num_heads * T : nullptr;
-        LDMAE_TRY(run_attention(qkv_i, 3 * D, o_i, D, B, T, c.num_heads, 0, D, 2 * D, 0.125f, st, lse, b.attn_m0_log2));
+        LDMAE_TRY(run_attention(qkv_i, 3 * D, o_i, D, B, T, c.num_heads, 0, D, 2 * D, 0.125f, st, lse, b.attn_m0_log2, presc));
       }
     } else {
       // wider heads (XL, head_dim 72): 128-column head slots, generic epilogue and the one-tile attention kernel
@@ -1382,6 +1397,13 @@ extern "C" int ldmae_attention_bounded(const void* qkv, void* out, float* lse2, 
   LDMAE_REQUIRE(m0_log2 > 0.f && m0_log2 <= 48.f, "score bound must be in (0, 48] (log2 units)");
   return run_attention(qkv, 3 * H * 64, out, H * 64, B, T, H, 0, H * 64, 2 * H * 64, scale, static_cast<cudaStream_t>(stream), lse2,
                        m0_log2);
+}
+extern "C" int ldmae_attention_prescaled(const void* qkv, void* out, float* lse2, int32_t B, int32_t T, int32_t H, float m0_log2,
+                                         void* stream) {
+  LDMAE_TRY(require_sm100());
+  LDMAE_REQUIRE(m0_log2 > 0.f && m0_log2 <= 48.f, "score bound must be in (0, 48] (log2 units)");
+  return run_attention(qkv, 3 * H * 64, out, H * 64, B, T, H, 0, H * 64, 2 * H * 64, 1.f, static_cast<cudaStream_t>(stream), lse2,
+                       m0_log2, true);
 }
 extern "C" int ldmae_attention_lse(const void* qkv, void* out, float* lse2, int32_t B, int32_t T, int32_t H, float scale,
                                    void* stream) {

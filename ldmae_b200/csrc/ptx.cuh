@@ -106,6 +106,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   }
 }
 
+// The same without the printf (a call in a register-heavy loop makes ptxas shuffle live registers around the call ABI's
+// argument registers): a protocol bug still traps.
+__device__ __forceinline__ void mbar_wait_quiet(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > LDMAE_MBAR_TIMEOUT_CYCLES) __trap();
+  }
+}
+
 // ------------------------------------------------------------------ fences
 __device__ __forceinline__ void fence_proxy_async_smem() {  // generic-proxy smem writes -> async proxy (UMMA/TMA)
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -349,6 +359,18 @@ __device__ __forceinline__ float2 ex2_poly2(float2 x) {
   x.y = fmaxf(x.y, -125.f);
   const float2 magic = make_float2(12582912.f, 12582912.f);
   const float2 t = add2(x, magic);                                   // low mantissa bits = round(x)
+  const float2 fl = add2(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = add2(x, make_float2(-fl.x, -fl.y));
+  float2 r = fma2(f, make_float2(0.0555041f, 0.0555041f), make_float2(0.2402265f, 0.2402265f));
+  r = fma2(r, f, make_float2(0.6931472f, 0.6931472f));
+  r = fma2(r, f, make_float2(1.f, 1.f));
+  r.x = __int_as_float(__float_as_int(r.x) + (__float_as_int(t.x) << 23));
+  r.y = __int_as_float(__float_as_int(r.y) + (__float_as_int(t.y) << 23));
+  return r;
+}
+// the same for arguments known to lie in [-125, 0] (constant-offset softmax): no clamp
+__device__ __forceinline__ float2 ex2_poly2_bounded(float2 x) {
+  const float2 t = add2(x, make_float2(12582912.f, 12582912.f));
   const float2 fl = add2(t, make_float2(-12582912.f, -12582912.f));
   const float2 f = add2(x, make_float2(-fl.x, -fl.y));
   float2 r = fma2(f, make_float2(0.0555041f, 0.0555041f), make_float2(0.2402265f, 0.2402265f));

@@ -102,11 +102,14 @@ def test_library_reports_sm100():
     assert cc.value // 10 == 10 and sm.value >= 100
 
 
-@pytest.mark.parametrize("B,T,H,wide", [(2, 1024, 3, 0), (3, 64, 2, 0), (1, 320, 2, 0), (2, 1024, 2, 1), (1, 320, 2, 1)])
+@pytest.mark.parametrize("B,T,H,wide", [(2, 1024, 3, 0), (3, 64, 2, 0), (1, 320, 2, 0), (2, 1024, 2, 1), (1, 320, 2, 1),
+                                          (26, 1024, 3, 0), (40, 256, 4, 0), (160, 128, 1, 0)])
 def test_attention_bounded_scores_matches_softmax(B, T, H, wide, monkeypatch):
     """Constant-offset softmax (qk-normed heads): the score bound replaces the running maximum; lse2 is exported for the
     backward.  `wide` additionally exercises the two-threads-per-row instantiation (LDMAE_ATTN_WIDE is read once per process,
-    so that case only checks the default unless the variable was set before the library loaded)."""
+    so that case only checks the default unless the variable was set before the library loaded).  The last three cases give
+    every persistent CTA several work items (more items than SMs; 8, 2 and 1 key blocks per item): the software-pipelined
+    softmax fetches the next item's first scores under the current item's last exponentials."""
     from gpu_util import rel_err
     from ldmae_b200 import _lib
     g = torch.Generator().manual_seed(B * 10 + T)
@@ -125,6 +128,31 @@ def test_attention_bounded_scores_matches_softmax(B, T, H, wide, monkeypatch):
     torch.cuda.synchronize()
     assert rel_err(out.float().cpu(), ref) < 1e-2
     torch.testing.assert_close(lse[: B * H * T].cpu().reshape(B, H, T), torch.logsumexp(sc, -1) * 1.4426950408889634, rtol=0, atol=2e-2)
+
+
+@pytest.mark.parametrize("B,T,H", [(2, 1024, 3), (1, 320, 2), (40, 256, 4), (160, 128, 1)])
+def test_attention_prescaled_matches_softmax(B, T, H):
+    """q pre-multiplied by scale * log2(e) (what the inference QKV epilogue emits): probabilities are 2^(q.k), no offset."""
+    from gpu_util import rel_err
+    from ldmae_b200 import _lib
+    g = torch.Generator().manual_seed(B * 10 + T + 1)
+    x = torch.randn(B * T, 3 * H, 64, generator=g)
+    x[:, : 2 * H] = x[:, : 2 * H] / x[:, : 2 * H].pow(2).mean(-1, keepdim=True).sqrt()       # |q| = |k| = 8
+    x[:, :H] *= 0.125 * 1.4426950408889634
+    qkv = x.reshape(B * T, 3 * H * 64).to(torch.bfloat16)
+    q, k, v = qkv.float().reshape(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    sc2 = q @ k.transpose(-1, -2)                                                            # log2-domain scores
+    ref = (torch.softmax(sc2 * 0.6931471805599453, dim=-1) @ v).transpose(1, 2).reshape(B * T, H * 64)
+    out = torch.empty(B * T, H * 64, device="cuda", dtype=torch.bfloat16)
+    lse = torch.zeros(B * H * T + 64, device="cuda")
+    m0 = 8 * 1.4426950408889634 * 1.02
+    assert float(sc2.abs().max()) <= m0
+    _lib.check(_lib.lib().ldmae_attention_prescaled(_lib.ptr(qkv.cuda()), _lib.ptr(out), _lib.ptr(lse), B, T, H, m0, _lib.stream_ptr()),
+               "attention_prescaled")
+    torch.cuda.synchronize()
+    assert rel_err(out.float().cpu(), ref) < 1e-2
+    torch.testing.assert_close(lse[: B * H * T].cpu().reshape(B, H, T), torch.logsumexp(sc2 * 0.6931471805599453, -1) * 1.4426950408889634,
+                               rtol=0, atol=2e-2)
 
 
 @pytest.mark.parametrize("B,T,H,hd", [(2, 256, 2, 72), (1, 1024, 3, 72), (2, 200, 2, 128), (1, 64, 1, 80)])

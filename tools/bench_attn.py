@@ -35,3 +35,12 @@ ref = (torch.softmax(sc, -1) @ v).transpose(1, 2).reshape(2 * T, H * 64)
 err = float((o[:2 * T].float() - ref).norm() / ref.norm())
 lerr = float((lse[: 2 * H * T].view(2, H, T) - torch.logsumexp(sc, -1) * 1.4426950408889634).abs().max())
 print(f"normed heads: bounded {msb:.3f} ms {fl/msb/1e9:.0f} TF/s | tracking {mst:.3f} ms {fl/mst/1e9:.0f} TF/s | rel err {err:.2e} lse err {lerr:.2e} score absmax {float(sc.abs().max()):.2f}")
+
+# q pre-multiplied by scale * log2(e): exponents straight from the scores (the inference forward's instantiation)
+xs = x.clone(); xs[:, :H] *= 0.125 * 1.4426950408889634
+qkvs = xs.reshape(B * T, 3 * H * 64).to(torch.bfloat16)
+msp = timeit(lambda: _lib.check(_lib.lib().ldmae_attention_prescaled(_lib.ptr(qkvs), _lib.ptr(o), _lib.ptr(lse), B, T, H, m0, _lib.stream_ptr())))
+q, k, v = qkvs.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)[:, :2]
+ref = (torch.softmax(q @ k.transpose(-1, -2) * 0.6931471805599453, -1) @ v).transpose(1, 2).reshape(2 * T, H * 64)
+err = float((o[:2 * T].float() - ref).norm() / ref.norm())
+print(f"prescaled q: {msp:.3f} ms {fl/msp/1e9:.0f} TF/s rel err {err:.2e}")
