@@ -235,7 +235,12 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
     const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
     uint8_t* stage_o = sO + t * kAttnTileBytes + wq * 4096;
     int g = 0, it = 0;
-    float sA[32], sB[32], sC[32], sD[32];                // kPipe: the four score chunks of a step (sA, sB live across steps)
+    // kPipe: shared addresses of this tile's barriers, computed once (a generic -> shared conversion per barrier operation
+    // was ~6 % of the loop's issue slots), and the four score chunks of a step (sA, sB live across steps)
+    uint32_t a_s_full = smem_u32(&s_full[t]), a_s_free = smem_u32(&s_free[t]), a_p_full = smem_u32(&p_full[t]),
+             a_o_done = smem_u32(&o_done[t]);
+    asm volatile("" : "+r"(a_s_full), "+r"(a_s_free), "+r"(a_p_full), "+r"(a_o_done));   // opaque: keep them in registers
+    float sA[32], sB[32], sC[32], sD[32];
     bool pre = false;                                    // kPipe: sA, sB already hold the next step's first two chunks
     for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
       int qpair, head, b;
@@ -256,7 +261,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           ATTN_PSTAMP(7, pre ? 1 : 0);
           if (!pre) {
             // nothing fetched ahead (first step of the CTA, or the scores were late): the whole row, then release S_t
-            mbar_wait_quiet(&s_full[t], g & 1);
+            mbar_wait_quiet_a(a_s_full, g & 1);
             __syncwarp();
             tc_fence_after();
             tmem_ld32(tS, sA);
@@ -267,7 +272,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
             tmem_ld_pin32(sA); tmem_ld_pin32(sB); tmem_ld_pin32(sC); tmem_ld_pin32(sD);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&s_free[t]);
+            if (lane == 0) mbar_arrive_a(a_s_free);
             s_released = true;
           } else {
             // chunks 0,1 arrived under the previous step's last exponentials; 2,3 load under chunk 0's
@@ -276,29 +281,31 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
             s_released = false;
           }
           ATTN_PSTAMP(1, clock64());
-          uint32_t wv[16];
-          attn_exp_chunk<0, kRaw>(sA, sc2, neg2, ls0, ls1, wv);
-          // P_t may only be overwritten after the previous P_t V has been read (the previous block of this CTA, whichever item)
-          if (g > 0) mbar_wait_quiet(&o_done[t], (g - 1) & 1);
-          __syncwarp();
-          tc_fence_after();
-          tmem_st16(tP, wv);
+          uint32_t wv0[16], wv[16];
+          attn_exp_chunk<0, kRaw>(sA, sc2, neg2, ls0, ls1, wv0);
           ATTN_PSTAMP(2, clock64());
           if (!s_released) {
             tmem_ld_wait();
             tmem_ld_pin32(sC); tmem_ld_pin32(sD);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&s_free[t]);          // the tensor core may overwrite S_t with the next block
+            if (lane == 0) mbar_arrive_a(a_s_free);          // the tensor core may overwrite S_t with the next block
           }
           ATTN_PSTAMP(3, clock64());
           attn_exp_chunk<1, kRaw>(sB, sc2, neg2, ls0, ls1, wv);
+          // P_t may only be overwritten after the previous P_t V has been read (the previous block of this CTA, whichever
+          // item): that product was issued at the end of the previous step, so the first store waits until half of this
+          // step's exponentials are done (the first chunk's probabilities sit in registers meanwhile)
+          if (g > 0) mbar_wait_quiet_a(a_o_done, (g - 1) & 1);
+          __syncwarp();
+          tc_fence_after();
+          tmem_st16(tP, wv0);
           tmem_st16(tP + 16, wv);
           attn_exp_chunk<2, kRaw>(sC, sc2, neg2, ls0, ls1, wv);
           tmem_st16(tP + 32, wv);
           // the next step's scores (next key block / next item's first block), if the tensor core has delivered them
           ATTN_PSTAMP(4, clock64());
-          pre = __all_sync(0xffffffffu, mbar_probe(&s_full[t], (g + 1) & 1) != 0);
+          pre = __all_sync(0xffffffffu, mbar_probe_a(a_s_full, (g + 1) & 1) != 0);
           if (pre) {
             tc_fence_after();
             tmem_ld32(tS, sA);
@@ -314,7 +321,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&p_full[t]);
+          if (lane == 0) mbar_arrive_a(a_p_full);
           ATTN_PSTAMP(6, clock64());
         }
         l_run = (ls0.x + ls0.y) + (ls1.x + ls1.y);
