@@ -18,7 +18,9 @@
 
 namespace ldmae {
 
-constexpr int kAttnPSmemBytes = kAttnSmemBytes + 2 * kAttnTileBytes;    // + output staging
+constexpr int kAttnPSmemBytes = kAttnSmemBytes + 2 * kAttnTileBytes     // + output staging
+                                + 2 * 2 * 128 * 4 + 64;                // + row sums handed to the epilogue warps (kPipe), more barriers
+constexpr int kAttnPipeThreads = 512;                                  // kPipe: + four epilogue warps
 
 // kPipe (requires kFixedMax): the softmax warps software-pipeline their TMEM traffic under the exponentials.  Without a row
 // maximum a thread needs no look at the whole block before its first exponential, so the 128 scores of a step are taken in
@@ -39,6 +41,9 @@ __host__ __device__ constexpr bool attn_pair_is_poly(int q) {
 }
 // one 32-column chunk of a row: exponentials (MUFU / polynomial), partial row sums, bf16 pack -> 16 packed P columns
 // kRaw: the scores already are the exponents (q pre-multiplied by scale * log2e, no offset: |s| <= m0 <= 48)
+// (Concentrating the polynomial pairs in alternate chunks, swapped between the two tiles so that one warp of a sub-partition
+// loads the MUFU unit while the other loads the FMA pipe, measured 796-855 vs 876 TFLOP/s: the even spread lets each warp
+// overlap its own MUFU and FMA work, which matters more.)
 template <int kChunk, bool kRaw = false>
 __device__ __forceinline__ void attn_exp_chunk(const float* s, const float2 sc2, const float2 neg2, float2& ls0, float2& ls1,
                                                uint32_t* wv) {
@@ -56,13 +61,15 @@ __device__ __forceinline__ void attn_exp_chunk(const float* s, const float2 sc2,
 }
 
 #ifdef LDMAE_ATTN_TRACE
-#define ATTN_PSTAMP(k, v) do { if (p.trace && blockIdx.x == 0 && lane == 0 && wq == 0 && g < 64) p.trace[((t * 64 + g) * 8) + (k)] = (v); } while (0)
+#define ATTN_PSTAMP(k, v) do { if (p.trace && blockIdx.x == 0 && lane == 0 && wq == 0 && g < 48) p.trace[((t * 64 + g) * 8) + (k)] = (v); } while (0)
+#define ATTN_ESTAMP(k) do { if (p.trace && blockIdx.x == 0 && lane == 0 && wq == 0 && it < 16) p.trace[((t * 64 + 48 + it) * 8) + (k)] = clock64(); } while (0)
 #else
 #define ATTN_PSTAMP(k, v) do { } while (0)
+#define ATTN_ESTAMP(k) do { } while (0)
 #endif
 
 template <bool kFixedMax, bool kPipe = false, bool kRaw = false>
-__global__ void __launch_bounds__(kAttnThreads, 1)
+__global__ void __launch_bounds__(kPipe ? kAttnPipeThreads : kAttnThreads, 1)
 attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out, const AttnParams p,
                         const int n_qpairs, const int n_items) {
   extern __shared__ uint8_t smem_raw[];
@@ -84,7 +91,9 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
   uint64_t* o_done = p_full + 2;                   // [2]
   uint64_t* o_free = o_done + 2;                   // [2]
   uint64_t* turn = o_free + 2;                     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(turn + 2);
+  uint64_t* l_full = turn + 2;                     // [2]  kPipe: the row sums of an item are in shared memory (softmax -> epilogue)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(l_full + 2);
+  float* l_s = reinterpret_cast<float*>(tmem_slot + 2);     // kPipe: [2 item parities][2 tiles][128 rows]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -108,7 +117,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1); mbar_init(&s_free[t], 4); mbar_init(&p_full[t], 4); mbar_init(&o_done[t], 1);
-      mbar_init(&o_free[t], 4); mbar_init(&turn[t], 4);
+      mbar_init(&o_free[t], 4); mbar_init(&turn[t], 4); mbar_init(&l_full[t], 4);
     }
     fence_mbar_init();
   }
@@ -118,8 +127,10 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Register split (setmaxnreg moves registers only through the pool the CTA's own warps release, never the part the launch
+  // left unallocated): 384 threads x 168 -> control 80 / softmax 208;  kPipe: 512 x 128 -> control 64 / epilogue 48 / softmax 200
   if (warp < 4) {
-  setmaxnreg_dec<80>();
+  if constexpr (kPipe) setmaxnreg_dec<64>(); else setmaxnreg_dec<80>();
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
@@ -176,55 +187,118 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       __syncwarp();
     };
     int stage = 0; uint32_t phase = 0;                 // ring position of the block whose P.V comes next
-    int g = 0;                                         // key blocks processed so far (all items)
-    int it = 0;
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
-      // scores of the item's first block: S_t is free once the softmax warps copied the previous block (g - 1) out
-      mbar_wait(q_full, it & 1, 20);
-      mbar_wait(&k_full[stage], phase, 21);
+    // One flat loop over the CTA's key blocks (all items): the scores of block g + 1 are issued before the P.V of block g even
+    // when g + 1 is the NEXT item's first block -- issued after the item's last P.V they reached the softmax warps ~1500 clk
+    // late once the epilogue had moved to its own warps (clock64 trace).
+    const int my_items = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    const int total = my_items * nkv;
+    if (total > 0) {
+      mbar_wait(q_full, 0, 20);
+      mbar_wait(&k_full[0], 0, 21);
       for (int t = 0; t < 2; ++t) {
-        if (g > 0) mbar_wait(&s_free[t], (g - 1) & 1, 26 + t);
         tc_fence_after();
-        issue_qk(t, stage);
+        issue_qk(t, 0);
       }
       if (issuer) {
-        umma_commit<1>(&k_empty[stage]);
+        umma_commit<1>(&k_empty[0]);
         if (nkv == 1) umma_commit<1>(q_empty);
       }
       __syncwarp();
-      for (int j = 0; j < nkv; ++j, ++g) {
-        int nstage = stage + 1; uint32_t nphase = phase;
-        if (nstage == kAttnKVStages) { nstage = 0; nphase ^= 1; }
-        if (j + 1 < nkv) {
-          // refill S_t with block j+1 as soon as the softmax warps hold block j in registers
-          mbar_wait(&k_full[nstage], nphase, 25);
-          for (int t = 0; t < 2; ++t) {
-            mbar_wait(&s_free[t], g & 1, 26 + t);
-            tc_fence_after();
-            issue_qk(t, nstage);
-          }
-          if (issuer) {
-            umma_commit<1>(&k_empty[nstage]);
-            if (j + 2 == nkv) umma_commit<1>(q_empty);   // that was the item's last QK^T: the Q tiles may be reloaded
-          }
-          __syncwarp();
-        }
-        mbar_wait(&v_full[stage], phase, 24);
+    }
+    int it = 0, j = 0;                                 // item / key block of step g
+    for (int g = 0; g < total; ++g) {
+      int nstage = stage + 1; uint32_t nphase = phase;
+      if (nstage == kAttnKVStages) { nstage = 0; nphase ^= 1; }
+      if (g + 1 < total) {
+        // refill S_t with the next block as soon as the softmax warps hold block g in registers
+        const int jn = (j + 1 == nkv) ? 0 : j + 1;
+        if (jn == 0) mbar_wait(q_full, (it + 1) & 1, 20);     // the next item's Q tiles
+        mbar_wait(&k_full[nstage], nphase, 25);
         for (int t = 0; t < 2; ++t) {
-          mbar_wait(&p_full[t], g & 1, 22 + t);
-          // the first P.V of an item overwrites O_t: the previous item's epilogue must have read it
-          if (j == 0 && it > 0) mbar_wait(&o_free[t], (it - 1) & 1, 28 + t);
+          mbar_wait(&s_free[t], g & 1, 26 + t);
           tc_fence_after();
-          issue_pv(t, stage, j == 0 ? 0u : 1u);
+          issue_qk(t, nstage);
         }
-        if (issuer) umma_commit<1>(&v_empty[stage]);
+        if (issuer) {
+          umma_commit<1>(&k_empty[nstage]);
+          if (jn == nkv - 1) umma_commit<1>(q_empty);         // that was an item's last QK^T: the Q tiles may be reloaded
+        }
         __syncwarp();
-        stage = nstage; phase = nphase;
       }
+      mbar_wait(&v_full[stage], phase, 24);
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(&p_full[t], g & 1, 22 + t);
+        // the first P.V of an item overwrites O_t: the previous item's epilogue must have read it
+        if (j == 0 && it > 0) mbar_wait(&o_free[t], (it - 1) & 1, 28 + t);
+        tc_fence_after();
+        issue_pv(t, stage, j == 0 ? 0u : 1u);
+      }
+      if (issuer) umma_commit<1>(&v_empty[stage]);
+      __syncwarp();
+      stage = nstage; phase = nphase;
+      if (++j == nkv) { j = 0; ++it; }
     }
   }
+  } else if (kPipe && warp >= 12) {
+    // ===================== kPipe: epilogue warps (O_t / l -> bf16 -> global), off the softmax warps' critical path =====================
+    // The softmax warps of the eight-warp kernel spent ~3000 of an item's ~22000 clk normalising and storing O with the
+    // tensor core idle (clock64 trace, tools/trace_attn_pipe.py); here they hand the row sums over and go straight on to the
+    // next item's scores, which are already in TMEM.  Warp e serves TMEM lanes 32 (e & 3) .. +31 of tile 0, then of tile 1.
+    setmaxnreg_dec<48>();
+    const int wq = warp & 3;
+    const uint32_t lane_addr = static_cast<uint32_t>(wq * 32) << 16;
+    int it = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+      int qpair, head, b;
+      item_coords(w, qpair, head, b);
+      const int row_base = b * p.T;
+      const int g_last = (it + 1) * nkv - 1;               // the item's last key block in the CTA's running block count
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        const uint32_t tO = tmem_base + lane_addr + 384 + t * 64;
+        uint8_t* stage_o = sO + t * kAttnTileBytes + wq * 4096;
+        mbar_wait(&l_full[t], it & 1, 40 + t);
+        const float l_run = l_s[((it & 1) * 2 + t) * 128 + wq * 32 + lane];
+        const float inv_l = 1.f / l_run;
+        const int q_tok0 = qpair * 256 + t * 128 + wq * 32;
+        if (p.lse2 != nullptr && q_tok0 + lane < p.T)
+          p.lse2[(static_cast<size_t>(b) * p.H + head) * p.T + q_tok0 + lane] = (kRaw ? 0.f : p.m0_log2) + log2f(l_run);
+        // l_full(it) implies o_done(g_last - 1) has completed (the softmax warps waited for it before their last P store),
+        // so the parity wait below cannot be satisfied by an older phase
+        mbar_wait(&o_done[t], g_last & 1, 42 + t);
+        __syncwarp();
+        tc_fence_after();
+        if (lane == 0) tma_store_wait_read<1>();            // this staging tile's previous store (two groups back) has been read
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float o[32];
+          tmem_ld32(tO + c * 32, o);
+          tmem_ld_wait();
+          tmem_ld_pin32(o);
+          if (c == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&o_free[t]);        // O_t is in registers: the next item's first P.V may overwrite it
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 v = make_uint4(pack_bf16x2(o[8 * q] * inv_l, o[8 * q + 1] * inv_l), pack_bf16x2(o[8 * q + 2] * inv_l, o[8 * q + 3] * inv_l),
+                                       pack_bf16x2(o[8 * q + 4] * inv_l, o[8 * q + 5] * inv_l), pack_bf16x2(o[8 * q + 6] * inv_l, o[8 * q + 7] * inv_l));
+            sts128(stage_o + lane * 128 + (((c * 4 + q) ^ (lane & 7)) << 4), v);
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmap_out, stage_o, head * 64, row_base + q_tok0);   // (T % 128 == 0: every 32-row tile is whole)
+          tma_store_commit();
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_read<0>();
   } else {
-    setmaxnreg_inc<208>();
+    if constexpr (kPipe) setmaxnreg_inc<200>(); else setmaxnreg_inc<208>();
     // ===================== softmax: thread = one query row =====================
     const int t = (warp - 4) >> 2;                       // tile 0 / 1
     const int wq = warp & 3;
@@ -324,7 +398,11 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           if (lane == 0) mbar_arrive_a(a_p_full);
           ATTN_PSTAMP(6, clock64());
         }
-        l_run = (ls0.x + ls0.y) + (ls1.x + ls1.y);
+        // hand the row sums to the epilogue warps and go on to the next item
+        l_s[((it & 1) * 2 + t) * 128 + wq * 32 + lane] = (ls0.x + ls0.y) + (ls1.x + ls1.y);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&l_full[t]);
+        continue;
       } else {
 #pragma unroll 1
       for (int j = 0; j < nkv; ++j, ++g) {
@@ -419,7 +497,9 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       }
       }
       // epilogue of the item: O_t / l -> bf16 -> global (own staging tile + one TMA store per warp)
+      ATTN_ESTAMP(0);
       mbar_wait(&o_done[t], (g - 1) & 1, 34 + t);
+      ATTN_ESTAMP(1);
       __syncwarp();
       tc_fence_after();
       const float inv_l = 1.f / l_run;
@@ -430,6 +510,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       __nv_bfloat16* dst = p.out + static_cast<size_t>(row_base + q_tok0 + lane) * p.ldo + head * 64;
       if (lane == 0) tma_store_wait_read<0>();              // the previous item's store has read this staging tile
       __syncwarp();
+      ATTN_ESTAMP(2);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         float o[32];
@@ -449,6 +530,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           else if (q_tok0 + lane < p.T) *reinterpret_cast<uint4*>(dst + c * 32 + q * 8) = v;
         }
       }
+      ATTN_ESTAMP(3);
       if (whole) {
         fence_proxy_async_smem();
         __syncwarp();
@@ -457,8 +539,9 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           tma_store_commit();
         }
       }
+      ATTN_ESTAMP(4);
     }
-    if (lane == 0) tma_store_wait_read<0>();
+    if constexpr (!kPipe) { if (lane == 0) tma_store_wait_read<0>(); }
   }
 
   __syncwarp();

@@ -242,11 +242,12 @@ static int run_attention(const void* qkv, int ldq, void* out, int ldo, int B, in
     LDMAE_REQUIRE(items < (1ll << 31), "attention: too many work items");
     const unsigned ctas = static_cast<unsigned>(std::min<long long>(items, device_sm_count()));
     // software-pipelined softmax warps (attention_persist_sm100.cuh, kPipe): 644 -> 765 TFLOP/s standalone;
-    // LDMAE_ATTN_PIPE=0 keeps the phase-by-phase loop
+    // LDMAE_ATTN_PIPE=0 keeps the phase-by-phase loop.  Needs whole key blocks and at least two per item: with a single block
+    // per item the softmax warps could run a whole item ahead of the epilogue warps and overrun the l_full barrier's parity.
     static int pipe = -1;
     if (pipe < 0) { const char* e = getenv("LDMAE_ATTN_PIPE"); pipe = e ? atoi(e) : 1; }
-    if (m0_log2 > 0.f && pipe && T % 128 == 0 && prescaled) attn_fwd_persist_kernel<true, true, true><<<ctas, kAttnThreads, kAttnPSmemBytes, st>>>(tm, tmo, p, n_qpairs, static_cast<int>(items));
-    else if (m0_log2 > 0.f && pipe && T % 128 == 0) attn_fwd_persist_kernel<true, true><<<ctas, kAttnThreads, kAttnPSmemBytes, st>>>(tm, tmo, p, n_qpairs, static_cast<int>(items));
+    if (m0_log2 > 0.f && pipe && T % 128 == 0 && T >= 256 && prescaled) attn_fwd_persist_kernel<true, true, true><<<ctas, kAttnPipeThreads, kAttnPSmemBytes, st>>>(tm, tmo, p, n_qpairs, static_cast<int>(items));
+    else if (m0_log2 > 0.f && pipe && T % 128 == 0 && T >= 256) attn_fwd_persist_kernel<true, true><<<ctas, kAttnPipeThreads, kAttnPSmemBytes, st>>>(tm, tmo, p, n_qpairs, static_cast<int>(items));
     else if (m0_log2 > 0.f) attn_fwd_persist_kernel<true><<<ctas, kAttnThreads, kAttnPSmemBytes, st>>>(tm, tmo, p, n_qpairs, static_cast<int>(items));
     else attn_fwd_persist_kernel<false><<<ctas, kAttnThreads, kAttnPSmemBytes, st>>>(tm, tmo, p, n_qpairs, static_cast<int>(items));
   }

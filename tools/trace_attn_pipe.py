@@ -9,7 +9,7 @@ dev = torch.device("cuda:0")
 qkv = torch.randn(B * T, 3 * H * 64, device=dev).to(torch.bfloat16); o = torch.empty(B * T, H * 64, device=dev, dtype=torch.bfloat16)
 tr = torch.zeros(2, 64, 8, dtype=torch.int64, device=dev)
 L = _lib.lib()
-run = lambda: _lib.check(L.ldmae_attention_bounded(_lib.ptr(qkv), _lib.ptr(o), None, B, T, H, 0.125, 48.0, _lib.stream_ptr()))
+run = lambda: _lib.check(L.ldmae_attention_prescaled(_lib.ptr(qkv), _lib.ptr(o), None, B, T, H, 48.0, _lib.stream_ptr()))
 for _ in range(2):
     run()
 _lib.check(L.ldmae_attention_trace(_lib.ptr(tr)))
@@ -17,10 +17,10 @@ run()
 torch.cuda.synchronize()
 tr = tr.cpu()
 t00 = int(tr[0, 0, 0])
-names = ["ld/issue", "expA+o_done+st", "release", "expB,C", "probe+prefetch", "expD+st+p_full"]
+names = ["ld/issue", "expA", "release", "expB+o_done+st+expC", "probe+prefetch", "expD+st+p_full"]
 for t in range(2):
     print(f"tile {t}: step start (rel. cycles), phase durations, pre flag")
-    for g in range(40):
+    for g in range(47):
         st = [int(v) for v in tr[t, g]]
         d = [st[k + 1] - st[k] for k in range(6)]
         nxt = int(tr[t, g + 1, 0]) - st[6]
