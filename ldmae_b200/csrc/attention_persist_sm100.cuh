@@ -257,7 +257,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       for (int t = 0; t < 2; ++t) {
         const uint32_t tO = tmem_base + lane_addr + 384 + t * 64;
         uint8_t* stage_o = sO + t * kAttnTileBytes + wq * 4096;
-        mbar_wait(&l_full[t], it & 1, 40 + t);
+        mbar_wait_sleep(&l_full[t], it & 1, 200, 40 + t);
         const float l_run = l_s[((it & 1) * 2 + t) * 128 + wq * 32 + lane];
         const float inv_l = 1.f / l_run;
         const int q_tok0 = qpair * 256 + t * 128 + wq * 32;

@@ -116,6 +116,19 @@ __device__ __forceinline__ void mbar_wait_quiet(uint64_t* bar, uint32_t parity) 
   }
 }
 
+// Latency-tolerant wait (epilogue warps): sleeps between polls so that the spinning warp does not take issue slots from the
+// warps that share its SM sub-partition (ncu: the tight loop was 15 % of the kernel's executed instructions).
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns, int tag = 0) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (clock64() - t0 > LDMAE_MBAR_TIMEOUT_CYCLES) {
+      printf("ldmae: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x, (int)threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
 // Raw shared-address forms for hot loops: the 32-bit shared address is computed once (smem_u32) instead of a
 // generic -> shared conversion (S2UR SR_SWINHI / SR_CgaCtaId, ULEA, ...) in front of every barrier operation.
 __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
