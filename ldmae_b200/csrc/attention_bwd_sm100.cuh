@@ -260,6 +260,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
     int stage = 0;
     uint32_t cphase = 0;
     int g = 0, it = 0;
+    // shared addresses of the loop's barriers, computed once and kept opaque (a generic -> shared conversion in front of every
+    // barrier operation and the printf path of the checked wait were a measurable share of this issue-bound loop; the same
+    // change was worth 10 % in the forward kernel)
+    uint32_t a_c_full = smem_u32(c_full), a_sd_full = smem_u32(sd_full), a_pd_full = smem_u32(pd_full);
+    asm volatile("" : "+r"(a_c_full), "+r"(a_sd_full), "+r"(a_pd_full));
     for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
     int rblk, head, b;
     item_coords(w, rblk, head, b);
@@ -294,8 +299,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
     }
 #pragma unroll 1
     for (int i = 0; i < ncb; ++i, ++g) {
-      if constexpr (kKV) mbar_wait(&c_full[stage], cphase, 29);   // this thread reads the stage's statistics vectors itself
-      mbar_wait(&sd_full[g & 1], (g >> 1) & 1, 30);
+      if constexpr (kKV) mbar_wait_quiet_a(a_c_full + stage * 8, cphase);   // this thread reads the stage's statistics vectors itself
+      mbar_wait_quiet_a(a_sd_full + (g & 1) * 8, (g >> 1) & 1);
       __syncwarp();
       tc_fence_after();
       if (warp == 4) ABWD_STAMP(4);
@@ -351,7 +356,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       if (warp == 4) ABWD_STAMP(7);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&pd_full[g & 1]);
+      if (lane == 0) mbar_arrive_a(a_pd_full + (g & 1) * 8);
       if (++stage == kAbStages) { stage = 0; cphase ^= 1; }
     }
     // epilogue: accumulators -> bf16 rows of dqkv; this warp stores columns [HD/4 * cq, HD/4 * (cq + 1)) of each accumulator
