@@ -44,14 +44,19 @@ struct AbGeo {
   static constexpr int kAcc1 = 256, kAcc2 = 256 + HD;     // TMEM columns of the accumulators
 };
 
-// Optional phase tracing of CTA (0,0,0) (debug builds: -DLDMAE_ATTN_TRACE): clock64 stamps per column block;
+// Optional phase tracing of CTA 0 (debug builds: -DLDMAE_ATTN_TRACE): clock64 stamps per column block of its first two items
+// (rows 0..15 and 16..31 of the buffer: the gap between them is the item boundary);
 // trace[i][0..3] = MMA warp (c_full seen, scores issued, pd_full seen, accumulations issued), [4..7] = row warp 4
 // (sd_full seen, TMEM loaded, math done, P/dS stored).
 #ifdef LDMAE_ATTN_TRACE
-#define ABWD_STAMP(k) do { if (p.trace && blockIdx.x == 0 && it == 0 && lane == 0 && i < 32) \
-  p.trace[i * 8 + (k)] = clock64(); } while (0)
+#define ABWD_STAMP(k) do { if (p.trace && blockIdx.x == 0 && it < 2 && lane == 0 && i < 16) \
+  p.trace[(it * 16 + i) * 8 + (k)] = clock64(); } while (0)
+// epilogue stamps of row warp 4 go into the two MMA slots the item's last block leaves unused
+#define ABWD_ESTAMP(k) do { if (p.trace && blockIdx.x == 0 && it < 2 && lane == 0 && warp == 4) \
+  p.trace[(it * 16 + 15) * 8 + (k)] = clock64(); } while (0)
 #else
 #define ABWD_STAMP(k) do { } while (0)
+#define ABWD_ESTAMP(k) do { } while (0)
 #endif
 
 struct AttnBwdParams {
@@ -135,18 +140,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
         item_coords(w, rblk, head, b);
         const int row_base = b * p.T;
         const size_t vec_base = (static_cast<size_t>(b) * p.H + head) * p.T;
-        if (it > 0) mbar_wait(r_empty, (it - 1) & 1, 12);
-        mbar_expect_tx(r_full, 2 * kAbRTile);
-        // (dO is dense [B*T, H*hd]: for hd < HD its second atom runs into the next head's columns -- harmless: those columns
-        //  only meet the zero padding of V in dP, and the matching dV columns are stored as zeros)
-        for (int a = 0; a < kAtoms; ++a) {
-          if constexpr (kKV) {
-            tma_load_2d(&tm_qkv_r, r_full, sRa + a * Geo::kRAtom, p.k_col + head * HD + a * 64, row_base + rblk * 128);
-            tma_load_2d(&tm_qkv_r, r_full, sRb + a * Geo::kRAtom, p.v_col + head * HD + a * 64, row_base + rblk * 128);
-          } else {
-            tma_load_2d(&tm_qkv_r, r_full, sRa + a * Geo::kRAtom, p.q_col + head * HD + a * 64, row_base + rblk * 128);
-            tma_load_2d(&tm_do_r, r_full, sRb + a * Geo::kRAtom, head * p.hd + a * 64, row_base + rblk * 128);
+        // Row tiles (Q | K and dO | V rows of the item).  HD == 64: the row warps copy them into TMEM at once and hand the
+        // shared-memory tiles back (r_empty), so the NEXT item's tiles are requested early in this item's column loop
+        // (below) -- requested after the last column block they arrived ~2300 clk after the row warps wanted them.
+        auto load_rows = [&](int rblk_, int head_, int row_base_) {
+          mbar_expect_tx(r_full, 2 * kAbRTile);
+          // (dO is dense [B*T, H*hd]: for hd < HD its second atom runs into the next head's columns -- harmless: those columns
+          //  only meet the zero padding of V in dP, and the matching dV columns are stored as zeros)
+          for (int a = 0; a < kAtoms; ++a) {
+            if constexpr (kKV) {
+              tma_load_2d(&tm_qkv_r, r_full, sRa + a * Geo::kRAtom, p.k_col + head_ * HD + a * 64, row_base_ + rblk_ * 128);
+              tma_load_2d(&tm_qkv_r, r_full, sRb + a * Geo::kRAtom, p.v_col + head_ * HD + a * 64, row_base_ + rblk_ * 128);
+            } else {
+              tma_load_2d(&tm_qkv_r, r_full, sRa + a * Geo::kRAtom, p.q_col + head_ * HD + a * 64, row_base_ + rblk_ * 128);
+              tma_load_2d(&tm_do_r, r_full, sRb + a * Geo::kRAtom, head_ * p.hd + a * 64, row_base_ + rblk_ * 128);
+            }
           }
+        };
+        if (HD != 64 || it == 0) {
+          if (it > 0) mbar_wait(r_empty, (it - 1) & 1, 12);
+          load_rows(rblk, head, row_base);
         }
         for (int i = 0; i < ncb; ++i) {
           mbar_wait(&c_empty[stage], phase ^ 1, 10);
@@ -167,6 +180,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
             }
           }
           if (++stage == kAbStages) { stage = 0; phase ^= 1; }
+          // (at the ring depth, this item's first block has been consumed, hence its row tiles were copied long ago: the wait
+          //  below does not hold the column loads up -- at i == 0 it stalled the ring for most of an item)
+          if (HD == 64 && i == min(kAbStages, ncb - 1) && w + static_cast<int>(gridDim.x) < n_items) {
+            int rblk_n, head_n, b_n;
+            item_coords(w + static_cast<int>(gridDim.x), rblk_n, head_n, b_n);
+            mbar_wait(r_empty, it & 1, 12);                  // this item's tiles have been copied into TMEM
+            load_rows(rblk_n, head_n, b_n * p.T);
+          }
         }
       }
     }
@@ -209,12 +230,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
     };
     int stage = 0; uint32_t phase = 0;                 // ring position of the current block
     int g = 0, it = 0;
+    // kAhead (HD == 64): the first scores of the NEXT item are issued during the current item's last block (the row warps copy
+    // the next item's row operands into TMEM as soon as they hold the last scores), so the next item's first block is in
+    // TMEM when the row warps come back from the epilogue.  Issued only after the item's last accumulation, they arrived
+    // 4600 clk after it (clock64 trace: 24 % of an item of 16 blocks).
+    constexpr bool kAhead = HD == 64;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
-      if constexpr (HD == 64) mbar_wait(ra_ready, it & 1, 20); else mbar_wait(r_full, it & 1, 20);
-      mbar_wait(&c_full[stage], phase, 21);
-      tc_fence_after();
-      // (buffer g & 1 was last used by block g - 2, whose accumulations were issued before this point)
-      issue_scores(stage, g & 1);
+      const bool has_next = w + static_cast<int>(gridDim.x) < n_items;
+      if (!kAhead || it == 0) {
+        if constexpr (HD == 64) mbar_wait(ra_ready, it & 1, 20); else mbar_wait(r_full, it & 1, 20);
+        mbar_wait(&c_full[stage], phase, 21);
+        tc_fence_after();
+        // (buffer g & 1 was last used by block g - 2, whose accumulations were issued before this point)
+        issue_scores(stage, g & 1);
+      }
       if (HD != 64 && ncb == 1) { if (issuer) umma_commit<1>(r_empty); __syncwarp(); }
       for (int i = 0; i < ncb; ++i, ++g) {
         int nstage = stage + 1; uint32_t nphase = phase;
@@ -227,6 +256,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
           issue_scores(nstage, (g + 1) & 1);
           if (HD != 64 && i + 2 == ncb) { if (issuer) umma_commit<1>(r_empty); __syncwarp(); }   // last read of the row tiles
           ABWD_STAMP(1);
+        } else if (kAhead && has_next) {
+          // the next item's first block (its row operands are being copied into TMEM by the row warps right now)
+          mbar_wait(ra_ready, (it + 1) & 1, 20);
+          mbar_wait(&c_full[nstage], nphase, 21);
+          tc_fence_after();
+          issue_scores(nstage, (g + 1) & 1);
         }
         mbar_wait(&pd_full[g & 1], (g >> 1) & 1, 22);
         // the first accumulation of an item overwrites the accumulators: the previous item's epilogue must have read them
@@ -265,25 +300,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
     // change was worth 10 % in the forward kernel)
     uint32_t a_c_full = smem_u32(c_full), a_sd_full = smem_u32(sd_full), a_pd_full = smem_u32(pd_full);
     asm volatile("" : "+r"(a_c_full), "+r"(a_sd_full), "+r"(a_pd_full));
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
-    int rblk, head, b;
-    item_coords(w, rblk, head, b);
-    const int row_base = b * p.T;
-    const size_t vec_base = (static_cast<size_t>(b) * p.H + head) * p.T;
-    const int row = rblk * 128 + wq * 32 + lane;       // token index inside the sample
-    float2 nl_r = make_float2(0.f, 0.f), dl_r = make_float2(0.f, 0.f);
-    if constexpr (!kKV) {
-      if (row < p.T) {
-        const float a = __ldg(p.nlse2 + vec_base + row), d = __ldg(p.delta + vec_base + row);
-        nl_r = make_float2(a, a); dl_r = make_float2(-d, -d);
-      }
-    }
-    if (HD == 64 && cq < 2) {
-      // The row operands (Q | K and dO | V rows of this item) are the A operand of every score product: copy them once
-      // from their TMA tiles into TMEM (bf16 pairs, one row per lane), so that the score MMAs read only the 2 KB column
-      // tile from shared memory per instruction (an SS product of this shape is shared-memory-bandwidth bound).
-      // (The previous item's score products are complete: this warp has consumed its last sd_full.)
-      mbar_wait(r_full, it & 1, 28);
+    constexpr bool kAhead = HD == 64;                  // see the MMA warp: the next item's operands are prepared one block early
+    float a_n = 0.f, d_n = 0.f;                        // kAhead: the next item's row statistics, loaded (not yet used) one item early
+    // copies this warp's 32 rows x 64 columns of a row tile (Q | K or dO | V) from its TMA tile into TMEM
+    auto copy_row_operands = [&](int item) {
+      mbar_wait(r_full, item & 1, 28);
       const uint8_t* src = (cq == 0 ? sRa : sRb) + (wq * 32 + lane) * 128;
       uint32_t wr[32];
 #pragma unroll
@@ -296,6 +317,49 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { mbar_arrive(ra_ready); mbar_arrive(r_empty); }
+    };
+    // Item coordinates advance incrementally (w += gridDim.x): the two integer divisions of item_coords, run by sixteen in-order
+    // warps at once, were ~1000 clk of every item boundary (clock64 trace).
+    const int G = static_cast<int>(gridDim.x);
+    const int d_r = G % n_rblk, d_h = (G / n_rblk) % p.H, d_b = G / (n_rblk * p.H);
+    auto advance = [&](int& r_, int& h_, int& b_) {
+      r_ += d_r; if (r_ >= n_rblk) { r_ -= n_rblk; ++h_; }
+      h_ += d_h; if (h_ >= p.H) { h_ -= p.H; ++b_; }
+      b_ += d_b;
+    };
+    int rblk, head, b;
+    item_coords(blockIdx.x, rblk, head, b);
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+    int rblk_n = rblk, head_n = head, b_n = b;
+    advance(rblk_n, head_n, b_n);
+    const bool has_next = w + static_cast<int>(gridDim.x) < n_items;
+    const int row_base = b * p.T;
+    const size_t vec_base = (static_cast<size_t>(b) * p.H + head) * p.T;
+    const int row = rblk * 128 + wq * 32 + lane;       // token index inside the sample
+    float2 nl_r = make_float2(0.f, 0.f), dl_r = make_float2(0.f, 0.f);
+    if constexpr (!kKV) {
+      if (kAhead && it > 0) { nl_r = make_float2(a_n, a_n); dl_r = make_float2(-d_n, -d_n); }
+      else if (row < p.T) {
+        const float a = __ldg(p.nlse2 + vec_base + row), d = __ldg(p.delta + vec_base + row);
+        nl_r = make_float2(a, a); dl_r = make_float2(-d, -d);
+      }
+    }
+    // The row operands (Q | K and dO | V rows of this item) are the A operand of every score product: copy them once
+    // from their TMA tiles into TMEM (bf16 pairs, one row per lane), so that the score MMAs read only the 2 KB column
+    // tile from shared memory per instruction (an SS product of this shape is shared-memory-bandwidth bound).
+    // (kAhead: items after the CTA's first were copied during the previous item's last block, below.)
+    if (HD == 64 && cq < 2 && (!kAhead || it == 0)) copy_row_operands(it);
+    if constexpr (!kKV) {
+      if (kAhead && has_next) {
+        // the next item's row statistics: global loads issued a whole item ahead, first used after this item's epilogue (used
+        // right after the load they stalled every item boundary for a DRAM round trip)
+        const int row_n = rblk_n * 128 + wq * 32 + lane;
+        a_n = 0.f; d_n = 0.f;
+        if (row_n < p.T) {
+          const size_t vb = (static_cast<size_t>(b_n) * p.H + head_n) * p.T + row_n;
+          a_n = __ldg(p.nlse2 + vb); d_n = __ldg(p.delta + vb);
+        }
+      }
     }
 #pragma unroll 1
     for (int i = 0; i < ncb; ++i, ++g) {
@@ -313,6 +377,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       tmem_ld16(tD, dp);
       tmem_ld_wait();
       if (warp == 4) ABWD_STAMP(5);
+      if (kAhead && i == ncb - 1 && has_next) {
+        // this item's last scores are in registers (every score product of the item is complete): hand the next item's row
+        // operands to the tensor core now
+        if (cq < 2) copy_row_operands(it + 1);
+      }
       uint32_t wp[8], wd[8];
       // The ragged tail of a sample (fewer than 16 live columns in this warp's quarter) is a separate instantiation of
       // the body behind a warp-uniform branch: as predicated selects inside the common body it cost 48 issue slots per
@@ -364,6 +433,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
     mbar_wait(acc_done, it & 1, 31);
     __syncwarp();
     tc_fence_after();
+    ABWD_ESTAMP(0);
     constexpr int kEC = HD / 4;                         // columns per warp: 16 or 32
     float o[kKV ? 2 : 1][kEC];
 #pragma unroll
@@ -389,6 +459,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
         }
       }
     }
+    ABWD_ESTAMP(1);
+    rblk = rblk_n; head = head_n; b = b_n;
     }   // work items
   }
 

@@ -55,7 +55,9 @@ def test_wgrad_accumulates(shape):
     assert err < 2e-5, f"wgrad {shape}: rel err {err}"
 
 
-ATTN_SHAPES = [(2, 1024, 3, 0.125), (3, 64, 2, 0.125), (1, 320, 2, 0.25), (2, 256, 1, 0.125), (2, 16, 2, 0.125)]
+ATTN_SHAPES = [(2, 1024, 3, 0.125), (3, 64, 2, 0.125), (1, 320, 2, 0.25), (2, 256, 1, 0.125), (2, 16, 2, 0.125),
+               # more work items than SMs: every persistent CTA walks several items (next-item look-ahead; 16, 4, 1 and a ragged 3 blocks)
+               (30, 1024, 1, 0.125), (80, 256, 2, 0.125), (200, 64, 1, 0.125), (100, 136, 1, 0.125)]
 
 
 @pytest.mark.parametrize("B,T,H,scale", ATTN_SHAPES)

@@ -1,4 +1,4 @@
-"""Phase timing of the attention backward (dKV kernel) -- needs a library built with -DLDMAE_ATTN_TRACE."""
+"""Phase timing of the attention backward (rows 15 / 31, first two columns: row warp 4 saw acc_done / finished the item's epilogue) -- needs a library built with -DLDMAE_ATTN_TRACE."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -20,5 +20,5 @@ tr = tr.cpu()          # holds the stamps of the LAST kernel launched (dQ), CTA 
 t0 = int(tr[0, 4])
 print("dQ kernel, CTA 0: per column block, cycles relative to the first sd_full")
 print(" i | mma: c_full scores_issued pd_full acc_issued | rows: sd_full loaded math_done stored")
-for i in range(16):
+for i in range(32):
     print(f"{i:2d} | " + " ".join(f"{int(tr[i, k]) - t0:7d}" for k in range(4)) + " | " + " ".join(f"{int(tr[i, k]) - t0:7d}" for k in range(4, 8)))
