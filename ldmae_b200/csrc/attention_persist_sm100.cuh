@@ -29,11 +29,14 @@ constexpr int kAttnPipeThreads = 512;                                  // kPipe:
 // first two chunks of the NEXT step (next key block, or the next item's first block) are fetched under the exponentials of
 // chunk 3 when their scores are already there.  A warp then issues MUFU work almost without gaps, instead of
 // load -> exponentials -> store phases in lockstep with the other tile's warp on the same SM sub-partition.
+#ifndef LDMAE_ATTN_SCALAR_SUM
+#define LDMAE_ATTN_SCALAR_SUM 1
+#endif
 #ifndef LDMAE_ATTN_POLY_NUM
-#define LDMAE_ATTN_POLY_NUM 3
+#define LDMAE_ATTN_POLY_NUM 1
 #endif
 #ifndef LDMAE_ATTN_POLY_DEN
-#define LDMAE_ATTN_POLY_DEN 8
+#define LDMAE_ATTN_POLY_DEN 4
 #endif
 // pair q (of 64 per step) takes the FMA-pipe polynomial: kNum of every kDen pairs, evenly spread
 __host__ __device__ constexpr bool attn_pair_is_poly(int q) {
@@ -53,8 +56,12 @@ __device__ __forceinline__ void attn_exp_chunk(const float* s, const float2 sc2,
     const float2 x1 = kRaw ? make_float2(s[i + 2], s[i + 3]) : fma2(make_float2(s[i + 2], s[i + 3]), sc2, neg2);
     const float2 p0 = attn_pair_is_poly(kChunk * 16 + i / 2) ? ex2_poly2_bounded(x0) : make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
     const float2 p1 = attn_pair_is_poly(kChunk * 16 + i / 2 + 1) ? ex2_poly2_bounded(x1) : make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
+#if LDMAE_ATTN_SCALAR_SUM
+    ls0.x += p0.x; ls0.y += p0.y; ls1.x += p1.x; ls1.y += p1.y;        // (A/B: scalar FADDs can use both FMA pipes)
+#else
     ls0 = add2(ls0, p0);
     ls1 = add2(ls1, p1);
+#endif
     wv[i >> 1] = pack_bf16x2(p0.x, p0.y);
     wv[(i >> 1) + 1] = pack_bf16x2(p1.x, p1.y);
   }
