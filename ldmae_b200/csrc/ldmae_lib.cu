@@ -1139,7 +1139,7 @@ extern "C" int ldmae_vmae_load_tensor(ldmae_vmae* h, const char* name, const flo
   LDMAE_REQUIRE(h && name && data, "null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const std::string k(name);
-  const int D = h->D, E = h->c.embed_dim, nh = h->c.decoder_num_heads, hd = D / nh;
+  const int D = h->D, E = h->c.embed_dim, nh = h->c.decoder_num_heads;
   int rc = LDMAE_OK;
   int bi = -1;
   bool enc = false;
