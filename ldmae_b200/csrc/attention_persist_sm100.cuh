@@ -409,7 +409,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
         l_s[((it & 1) * 2 + t) * 128 + wq * 32 + lane] = (ls0.x + ls0.y) + (ls1.x + ls1.y);
         __syncwarp();
         if (lane == 0) mbar_arrive(&l_full[t]);
-        continue;
+        // (kPipe has no in-line epilogue: the guard below)
       } else {
 #pragma unroll 1
       for (int j = 0; j < nkv; ++j, ++g) {
@@ -503,6 +503,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
         if (lane == 0) mbar_arrive(&p_full[t]);
       }
       }
+      if constexpr (!kPipe) {
       // epilogue of the item: O_t / l -> bf16 -> global (own staging tile + one TMA store per warp)
       ATTN_ESTAMP(0);
       mbar_wait(&o_done[t], (g - 1) & 1, 34 + t);
@@ -547,6 +548,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
         }
       }
       ATTN_ESTAMP(4);
+      }   // !kPipe
     }
     if constexpr (!kPipe) { if (lane == 0) tma_store_wait_read<0>(); }
   }
