@@ -13,6 +13,14 @@
 // Extra barriers: q_empty (last QK^T of an item issued -> the Q tile may be reloaded), o_free[t] (the epilogue has read O_t ->
 // the next item's first P.V may overwrite it).  The output is staged in its own shared-memory tiles (the Q tiles are being
 // reloaded during the epilogue).
+//
+// Instantiations (ldmae_lib.cu:run_attention picks one):
+//   <false>              running-maximum softmax (no qk-norm, VMAE), 384 threads, in-line epilogue
+//   <true>               constant-offset softmax, key blocks that may be ragged (T % 128 != 0) or a single block per item
+//   <true, true>         + kPipe: software-pipelined softmax warps, four epilogue warps (512 threads), used by the training forward
+//   <true, true, true>   + kRaw: exponents straight from the scores (inference forward: scale * log2e folded into q_norm.weight)
+// The MMA issuer walks ONE flat loop over the CTA's key blocks (all items) in every instantiation: the scores of block g + 1
+// are issued before the P.V of block g even when g + 1 is the next item's first block.
 #pragma once
 #include "attention_sm100.cuh"
 
@@ -57,7 +65,8 @@ __device__ __forceinline__ void attn_exp_chunk(const float* s, const float2 sc2,
     const float2 p0 = attn_pair_is_poly(kChunk * 16 + i / 2) ? ex2_poly2_bounded(x0) : make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
     const float2 p1 = attn_pair_is_poly(kChunk * 16 + i / 2 + 1) ? ex2_poly2_bounded(x1) : make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
 #if LDMAE_ATTN_SCALAR_SUM
-    ls0.x += p0.x; ls0.y += p0.y; ls1.x += p1.x; ls1.y += p1.y;        // (A/B: scalar FADDs can use both FMA pipes)
+    // scalar FADDs (either FMA pipe) instead of add.f32x2: 876 -> 899 TFLOP/s together with the 1/4 polynomial share
+    ls0.x += p0.x; ls0.y += p0.y; ls1.x += p1.x; ls1.y += p1.y;
 #else
     ls0 = add2(ls0, p0);
     ls1 = add2(ls1, p1);
