@@ -916,7 +916,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (leader && lane == 0) {
+    // The whole warp runs the control flow and only the tcgen05 instructions are issued by one elected lane: behind a
+    // single-lane branch nvcc cannot prove the descriptors / TMEM addresses warp-uniform and wraps EVERY tcgen05.mma in an
+    // ELECT / 5 x R2UR.BROADCAST / BRA.U.ANY convergence loop (~19 SASS instructions per 64-clk MMA: the issue rate sat at the
+    // margin of the tensor pipe's, ncu: 64-70 % active) -- the same finding as in the attention kernels.
+    if (leader) {
+      const bool issuer = elect_one();
       constexpr uint32_t idesc = umma_idesc_bf16(kBM * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -932,14 +937,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::kABytes);
           const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBBytesPadded);
+          if (issuer) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            const uint64_t ad = umma_smem_desc_sw128(a_addr + k * 32, 1024, 0);
-            const uint64_t bd = umma_smem_desc_sw128(b_addr + k * 32, 1024, 0);
-            umma_bf16<CG>(tmem_d, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBK / 16; ++k) {
+              const uint64_t ad = umma_smem_desc_sw128(a_addr + k * 32, 1024, 0);
+              const uint64_t bd = umma_smem_desc_sw128(b_addr + k * 32, 1024, 0);
+              umma_bf16<CG>(tmem_d, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit<CG>(&empty_bar[stage]);                       // frees the smem slot (both CTAs)
+            if (kb == num_k - 1) umma_commit<CG>(&tfull_bar[as]);     // accumulator ready (both CTAs)
           }
-          umma_commit<CG>(&empty_bar[stage]);                       // frees the smem slot (both CTAs)
-          if (kb == num_k - 1) umma_commit<CG>(&tfull_bar[as]);     // accumulator ready (both CTAs)
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
