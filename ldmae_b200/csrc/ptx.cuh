@@ -400,7 +400,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 // 2^x for a pair of arguments on the FMA / ALU pipes (no MUFU): Cody-Waite split x = n + f, |f| <= 0.5, degree-3
-// polynomial for 2^f (relative error < 7e-4, far below bf16 rounding), exponent added to the result's bit pattern.
+// polynomial for 2^f (relative error < 8e-4, below the bf16 rounding of the results; tests/test_host_cpu.py), exponent added to the result's bit pattern.
 // Used for a fraction of the softmax exponentials, whose MUFU unit is the bottleneck at head_dim 64.
 __device__ __forceinline__ float2 ex2_poly2(float2 x) {
   x.x = fmaxf(x.x, -125.f);

@@ -231,3 +231,44 @@ def test_img_latent_dataset_reads_the_extract_features_shard_format(tmp_path):
     np.random.seed(5)
     x3, _ = ds3[2]
     assert torch.allclose(x3, 3.0 * mom[0][2]) or torch.allclose(x3, 3.0 * flip[0][2])
+
+
+def test_prescaled_softmax_algebra_and_score_bound():
+    """The inference forward folds softmax scale * log2(e) into q_norm.weight (EpiQKV::Params::q_mul) and the attention kernel
+    takes p = 2^(q.k) with neither scale nor offset (attention_persist_sm100.cuh, kRaw).  Host-side statement of that algebra
+    on the reference's formulation (models/lightningdit.py:66-91: RMSNorm(64) on q and k, SDPA with scale 1/8), and of the
+    score bound |q.k| * scale * log2e <= 8 * log2e * max|wq| * max|wk| that admits the constant-offset kernels."""
+    g = torch.Generator().manual_seed(7)
+    T, hd = 96, 64
+    q, k, v = (torch.randn(T, hd, generator=g, dtype=torch.float64) for _ in range(3))
+    wq, wk = 1 + 0.3 * torch.randn(hd, generator=g, dtype=torch.float64), 1 + 0.3 * torch.randn(hd, generator=g, dtype=torch.float64)
+    rms = lambda x: x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6)
+    scale, log2e = 0.125, 1.4426950408889634
+    ref = torch.softmax((rms(q) * wq) @ (rms(k) * wk).T * scale, -1) @ v
+    s2 = (rms(q) * (wq * scale * log2e)) @ (rms(k) * wk).T          # what the tensor core produces from the pre-scaled q
+    p = torch.exp2(s2)                                              # no offset
+    out = (p @ v) / p.sum(-1, keepdim=True)
+    torch.testing.assert_close(out, ref, rtol=1e-12, atol=1e-12)
+    m0 = 8 * log2e * float(wq.abs().max()) * float(wk.abs().max())
+    assert float(s2.abs().max()) <= m0
+    # the admitted range m0 <= 48 keeps every probability and every 1024-term row sum inside fp32 / bf16
+    assert 2.0 ** 48 * 1024 < torch.finfo(torch.float32).max and 2.0 ** -48 > torch.finfo(torch.float32).tiny
+
+
+def test_polynomial_exp2_accuracy():
+    """The FMA-pipe exp2 of the attention kernels (csrc/ptx.cuh:ex2_poly2_bounded: Cody-Waite split with the 1.5 * 2^23 magic
+    number, degree-3 Taylor polynomial on |f| <= 0.5, exponent added to the bit pattern), restated in numpy float32: relative
+    error 8e-4, below the bf16 rounding of the probabilities (half an ulp = 2^-9 = 2e-3), over the whole admitted exponent range."""
+    x = np.linspace(-96.0, 48.0, 200001, dtype=np.float32)
+    magic = np.float32(12582912.0)
+    t = x + magic
+    fl = t - magic
+    f = x - fl
+    assert np.abs(f).max() <= 0.5
+    r = f * np.float32(0.0555041) + np.float32(0.2402265)
+    r = r * f + np.float32(0.6931472)
+    r = r * f + np.float32(1.0)
+    bits = r.view(np.int32) + (t.view(np.int32) << 23)
+    y = bits.view(np.float32)
+    rel = np.abs(y.astype(np.float64) / np.exp2(x.astype(np.float64)) - 1.0)
+    assert rel.max() < 1e-3, rel.max()
