@@ -76,6 +76,14 @@ int ldmae_dit_forward(ldmae_dit* h, const float* x, const float* t, float t_scal
  * next ldmae_dit_backward. */
 int ldmae_dit_train_forward(ldmae_dit* h, const float* x, const float* t, const int64_t* y, float* out, int32_t B, void* stream);
 int ldmae_dit_backward(ldmae_dit* h, const float* dout, int32_t B, void* stream);
+/* Only ONE training forward may be pending per handle: the kept activations and the shared conditioning workspace are
+ * overwritten by the next forward of any kind.  ldmae_dit_generation() is bumped by every forward / workspace
+ * re-allocation; ldmae_dit_backward fails with LDMAE_ERR_STATE when its forward is no longer the latest (the reference's
+ * autograd graph would keep both alive, models/lightningdit.py:391-418 under train_accum.py:215-230). */
+long long ldmae_dit_generation(ldmae_dit* h);
+/* Class labels (reference nn.Embedding, lightningdit.py:146-169) outside the table are clamped and flagged on the device;
+ * the flag is reported by the NEXT call on the handle, or right away by this call (which waits for `stream`). */
+int ldmae_dit_check_labels(ldmae_dit* h, void* stream);
 int ldmae_dit_grad_read(ldmae_dit* h, const char* name, float* dst, int64_t numel, void* stream);
 /* Same, but dst += gradient: micro-batch accumulation between optimizer steps (train_accum.py:220-234). */
 int ldmae_dit_grad_accumulate(ldmae_dit* h, const char* name, float* dst, int64_t numel, void* stream);

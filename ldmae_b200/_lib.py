@@ -41,6 +41,8 @@ SYMBOLS = {
     "ldmae_dit_forward": (C.c_int, [vp, vp, vp, f32, vp, vp, i32, i32, vp]),
     "ldmae_dit_train_forward": (C.c_int, [vp, vp, vp, vp, vp, i32, vp]),
     "ldmae_dit_backward": (C.c_int, [vp, vp, i32, vp]),
+    "ldmae_dit_generation": (C.c_longlong, [vp]),
+    "ldmae_dit_check_labels": (C.c_int, [vp, vp]),
     "ldmae_dit_grad_read": (C.c_int, [vp, C.c_char_p, vp, i64, vp]),
     "ldmae_dit_grad_accumulate": (C.c_int, [vp, C.c_char_p, vp, i64, vp]),
     "ldmae_adamw_ema_step": (C.c_int, [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, f32, vp]),

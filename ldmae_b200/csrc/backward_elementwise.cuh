@@ -514,11 +514,14 @@ __global__ void small_dgrad_kernel(float* __restrict__ out, int ld_out, const fl
   for (int n = 0; n < N; ++n) s = fmaf(A[static_cast<size_t>(b) * lda + n], W[static_cast<size_t>(n) * K + k], s);
   out[static_cast<size_t>(b) * ld_out + k] = s;
 }
-// table[idx[b], :] += v[b, :]
-__global__ void embed_bwd_kernel(float* __restrict__ table, const long long* __restrict__ idx, const float* __restrict__ v, int B, int D) {
+// table[idx[b], :] += v[b, :]   (rows outside the table were flagged by the forward's gather and are skipped here)
+__global__ void embed_bwd_kernel(float* __restrict__ table, const long long* __restrict__ idx, const float* __restrict__ v, int B, int D,
+                                 int table_rows) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * D) return;
-  atomicAdd(table + static_cast<size_t>(idx[i / D]) * D + (i % D), v[i]);
+  const long long r = idx[i / D];
+  if (r < 0 || r >= table_rows) return;
+  atomicAdd(table + static_cast<size_t>(r) * D + (i % D), v[i]);
 }
 // bf16 matrix transpose: dst[c, r] = src[r, c]  (src [R, C]); 32 x 32 tiles through shared memory
 __global__ void transpose_bf16_kernel(__nv_bfloat16* __restrict__ dst, const __nv_bfloat16* __restrict__ src, int R, int C) {

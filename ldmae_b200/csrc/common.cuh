@@ -61,6 +61,15 @@ struct DevBuf {
 
 int device_sm_count();
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: one flag per (call site, device ordinal), so a second
+// GPU driven from the same process gets its own opt-in.
+struct PerDeviceOnce {
+  bool done_[64] = {};
+  static int dev() { int d = 0; cudaGetDevice(&d); return d & 63; }
+  bool pending() const { return !done_[dev()]; }
+  void mark() { done_[dev()] = true; }
+};
+
 // 2-D row-major [rows, cols] (leading dimension ld elements) tensor map with a {box_cols x box_rows} box.
 // elem_bytes 2 = bf16, 4 = fp32; swizzle_bytes 128 / 64 (box_cols * elem_bytes must not exceed it).  Cached.
 int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, int rows, int cols, int ld, int box_cols, int box_rows,
@@ -87,10 +96,10 @@ int launch_gemm(const void* a, int lda, const void* w, int ldw, GemmShape g, con
   LDMAE_TRY(make_tmap_bf16(&ta, a, g.M, g.K, lda, kBM));
   LDMAE_TRY(make_tmap_bf16(&tw, w, g.N, g.K, ldw, Cfg::kLoadBN));
   auto kern = gemm_tn_kernel<BN, CG, Epi>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.pending()) {
     LDMAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
+    attr_set.mark();
   }
   const int n_tiles = (g.N + BN - 1) / BN;
   const int m_tiles = (g.M + kBM * CG - 1) / (kBM * CG);

@@ -72,7 +72,8 @@ template <int ACT /*0 none, 1 silu*/>
 __global__ void __launch_bounds__(256)
 small_linear_kernel(float* __restrict__ out, const float* __restrict__ in, const float* __restrict__ tvals, float tscalar,
                     const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ add_table,
-                    const long long* __restrict__ add_idx, int B, int K, int N, int in_mode, int in_ld) {
+                    const long long* __restrict__ add_idx, int B, int K, int N, int in_mode, int in_ld,
+                    int table_rows = 0, int* __restrict__ idx_err = nullptr) {
   extern __shared__ float s_in[];                 // [16][K]
   const int b0 = blockIdx.y * 16;
   const int nb = min(16, B - b0);
@@ -114,7 +115,16 @@ small_linear_kernel(float* __restrict__ out, const float* __restrict__ in, const
       for (int i = 0; i < 16; ++i) if (i == lane) v = acc[i];
       v += bias[n];
       if (ACT == 1) v = silu_f(v);
-      if (add_table != nullptr) v += add_table[static_cast<size_t>(add_idx[b0 + lane]) * N + n];
+      if (add_table != nullptr) {
+        // label gather (y_embedder.embedding_table): an index outside the table is flagged for the host and clamped -- nn.Embedding
+        // would raise a device assert; reading past the table never happens
+        long long idx = add_idx[b0 + lane];
+        if (idx < 0 || idx >= table_rows) {
+          if (idx_err != nullptr) atomicOr(idx_err, 1);
+          idx = idx < 0 ? 0 : table_rows - 1;
+        }
+        v += add_table[static_cast<size_t>(idx) * N + n];
+      }
       out[static_cast<size_t>(b0 + lane) * N + n] = v;
     }
   }
@@ -362,7 +372,9 @@ __global__ void vmae_pixel_tail_kernel(float* __restrict__ out_f32, uint8_t* __r
   if (out_u8) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const float v = fminf(fmaxf(127.5f * acc[c] + 128.0f, 0.f), 255.f);
+      // two roundings (multiply, then add) like the reference's eager `127.5 * x + 128.0`: an fma would truncate to a
+      // different grey level when the sum lands within an ulp of an integer; the pack is tested bit-exactly
+      const float v = fminf(fmaxf(__fadd_rn(__fmul_rn(127.5f, acc[c]), 128.0f), 0.f), 255.f);
       out_u8[(((b * HW) + Y) * HW + X) * 3 + c] = static_cast<uint8_t>(v);
     }
   }

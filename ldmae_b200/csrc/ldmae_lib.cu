@@ -54,14 +54,15 @@ struct ProfScope {
 };
 
 int device_sm_count() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
+  static int sms[64] = {};       // per device ordinal
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& s = sms[dev & 63];
+  if (s == 0) {
+    cudaDeviceGetAttribute(&s, cudaDevAttrMultiProcessorCount, dev);
+    if (s <= 0) s = 148;
   }
-  return sms;
+  return s;
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -202,8 +203,8 @@ static int run_attention(const void* qkv, int ldq, void* out, int ldo, int B, in
   CUtensorMap tm, tmo;
   LDMAE_TRY(make_tmap_bf16(&tm, qkv, B * T, ldq, ldq, 128));
   LDMAE_TRY(make_tmap_out_bf16(&tmo, out, B * T, H * 64, ldo));
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.pending()) {
     LDMAE_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
     LDMAE_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
     LDMAE_CUDA((cudaFuncSetAttribute(attn_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes)));
@@ -211,7 +212,7 @@ static int run_attention(const void* qkv, int ldq, void* out, int ldo, int B, in
     LDMAE_CUDA(cudaFuncSetAttribute(attn_fwd_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnPSmemBytes));
     LDMAE_CUDA((cudaFuncSetAttribute(attn_fwd_persist_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnPSmemBytes)));
     LDMAE_CUDA((cudaFuncSetAttribute(attn_fwd_persist_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnPSmemBytes)));
-    attr = true;
+    attr.mark();
   }
   AttnParams p;
   p.trace = g_attn_trace;
@@ -264,10 +265,10 @@ static int run_attention_hd128(const void* qkv, int ldq, void* out, int ldo, int
   LDMAE_REQUIRE(hd > 0 && hd <= 128 && hd % 8 == 0, "wide attention: head_dim %d must be a multiple of 8 up to 128", hd);
   CUtensorMap tm;
   LDMAE_TRY(make_tmap_bf16(&tm, qkv, B * T, ldq, ldq, 128));
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.pending()) {
     LDMAE_CUDA(cudaFuncSetAttribute(attn_fwd_hd128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kA128SmemBytes));
-    attr = true;
+    attr.mark();
   }
   Attn128Params p;
   p.out = static_cast<__nv_bfloat16*>(out); p.lse2 = lse2;
@@ -295,11 +296,11 @@ static int run_attention_bwd_t(const void* qkv, int ldq, const void* o, const vo
   LDMAE_TRY(make_tmap_bf16(&tdr, d_o, B * T, ldo, ldo, 128));
   LDMAE_TRY(make_tmap_bf16(&tdc, d_o, B * T, ldo, ldo, 64));
   constexpr int kSmem = AbGeo<HW>::kSmemBytes;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.pending()) {
     LDMAE_CUDA((cudaFuncSetAttribute(attn_bwd_kernel<false, HW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)));
     LDMAE_CUDA((cudaFuncSetAttribute(attn_bwd_kernel<true, HW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)));
-    attr = true;
+    attr.mark();
   }
   float* nlse2 = delta + static_cast<size_t>(B) * H * T + 64;       // second half of the workspace
   attn_delta_kernel<<<cdiv(static_cast<size_t>(B) * T * H, 256), 256, 0, st>>>(delta, nlse2, lse2, static_cast<const __nv_bfloat16*>(d_o),
@@ -344,10 +345,10 @@ static int gemm_wgrad(const void* pm, int ldp, const void* qm, int ldq, float* c
   LDMAE_TRY(make_tmap_out_f32(&ep.cmap, c, N1, N2, ldc));
   ep.alpha = alpha;
   auto kern = gemm_wgrad_kernel<BN, CG>;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.pending()) {
     LDMAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr = true;
+    attr.mark();
   }
   const int tiles = ((N1 + kBM * CG - 1) / (kBM * CG)) * ((N2 + BN - 1) / BN);
   const int num_kb = (M + kBK - 1) / kBK;
@@ -414,8 +415,26 @@ struct ldmae_dit {
   DevBuf<__nv_bfloat16> abuf, qkv, obuf, hbuf, sc, shift_bf16;
   DitTrain* tr = nullptr;   // activations kept by the training forward, backward workspace, gradients (dit_train.cuh)
   bool wT_valid = false;    // transposed bf16 weight copies (data-gradient GEMM operands) are current
-  ~ldmae_dit() { dit_train_free(tr); }
+  long long ws_gen = 0;     // bumped by every forward and workspace re-allocation: a backward checks its forward is the latest
+  DevBuf<int> label_err;    // device flag: a class label outside y_embedder.embedding_table was seen (clamped, never read OOB)
+  int* label_err_host = nullptr;   // pinned mirror, refreshed after every conditioning kernel (read without a sync)
+  ~ldmae_dit() {
+    dit_train_free(tr);
+    if (label_err_host) cudaFreeHost(label_err_host);
+  }
 };
+
+// Reports (once) a label that was out of range in an EARLIER call on this handle: the flag travels through a pinned
+// mirror that the stream refreshes after each conditioning kernel, so no call waits for the device here.
+static int dit_label_check(ldmae_dit* h) {
+  if (h->label_err_host && *h->label_err_host != 0) {
+    *h->label_err_host = 0;
+    cudaMemset(h->label_err.p, 0, sizeof(int));
+    return set_error(LDMAE_ERR_INVALID, "class label outside y_embedder.embedding_table (%d rows) in an earlier call on this handle "
+                     "(labels must lie in [0, %d]; the null class needs class_dropout_prob > 0)", h->c.num_embeddings, h->c.num_embeddings - 1);
+  }
+  return LDMAE_OK;
+}
 
 static int dit_alloc_ws(ldmae_dit* h, int B) {
   const size_t M = static_cast<size_t>(B) * h->T;
@@ -440,6 +459,7 @@ static int dit_alloc_ws(ldmae_dit* h, int B) {
   LDMAE_TRY(h->k1buf.alloc(lat));
   LDMAE_TRY(h->xtmp.alloc(lat));
   h->maxB = B;
+  ++h->ws_gen;
   return LDMAE_OK;
 }
 
@@ -558,6 +578,10 @@ extern "C" int ldmae_dit_create(const ldmae_dit_config* cfg, ldmae_dit** out) {
   if (r == LDMAE_OK && cudaMemcpy(h->slot_scale_off.p, sco.data(), h->S * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess)
     r = set_error(LDMAE_ERR_CUDA, "memcpy slot offsets");
   if (r == LDMAE_OK) r = dit_alloc_ws(h, std::max(1, c.max_batch));
+  A(h->label_err.alloc(1, true));
+  if (r == LDMAE_OK && cudaHostAlloc(reinterpret_cast<void**>(&h->label_err_host), sizeof(int), cudaHostAllocDefault) != cudaSuccess)
+    r = set_error(LDMAE_ERR_CUDA, "cudaHostAlloc failed");
+  if (r == LDMAE_OK) *h->label_err_host = 0;
   if (r != LDMAE_OK) { delete h; return r; }
   *out = h;
   return LDMAE_OK;
@@ -721,6 +745,7 @@ struct DitTrain {
   size_t gtotal = 0;
   bool have_forward = false;
   int lastB = 0;
+  long long fwd_gen = -1;   // ldmae_dit::ws_gen when the kept forward ran
 };
 static void dit_train_free(DitTrain* t) { delete t; }
 
@@ -729,6 +754,8 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
                             int B, int src_mod, cudaStream_t st, DitTrain* tr = nullptr) {
   LDMAE_REQUIRE(h && h->finalized, "LightningDiT handle not finalized (load all weights, then ldmae_dit_finalize)");
   LDMAE_REQUIRE(B >= 1 && src_mod >= 1, "bad batch");
+  LDMAE_TRY(dit_label_check(h));
+  ++h->ws_gen;
   if (B > h->maxB) {
     LDMAE_CUDA(cudaStreamSynchronize(st));
     LDMAE_TRY(dit_alloc_ws(h, B));
@@ -749,11 +776,11 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
     ProfScope ps(7, st);
     dim3 grid(cdiv(D, 64), cdiv(B, 16));
     const size_t sm0 = 16 * 256 * sizeof(float), sm2 = 16 * static_cast<size_t>(D) * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.pending()) {
       LDMAE_CUDA(cudaFuncSetAttribute(small_linear_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       LDMAE_CUDA(cudaFuncSetAttribute(small_linear_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr = true;
+      attr.mark();
     }
     if (tr) {
       // the backward needs the pre-activation of the timestep MLP and its input features
@@ -769,8 +796,10 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
       LDMAE_LAUNCH_CHECK();
     }
     small_linear_kernel<0><<<grid, 256, sm2, st>>>(h->cvec_c.p, h->th1.p, nullptr, 0.f, h->t_w2.p, h->t_b2.p, h->emb.p,
-                                                   reinterpret_cast<const long long*>(y), B, D, D, 0, D);
+                                                   reinterpret_cast<const long long*>(y), B, D, D, 0, D, c.num_embeddings,
+                                                   h->label_err.p);
     LDMAE_LAUNCH_CHECK();
+    LDMAE_CUDA(cudaMemcpyAsync(h->label_err_host, h->label_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     silu_to_bf16_kernel<<<cdiv(static_cast<size_t>(B) * D, 256), 256, 0, st>>>(h->sc.p, h->cvec_c.p, static_cast<size_t>(B) * D);
     LDMAE_LAUNCH_CHECK();
   }
@@ -957,6 +986,16 @@ extern "C" int ldmae_dit_debug_read(ldmae_dit* h, const char* name, void* dst, i
   LDMAE_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
   return LDMAE_OK;
 }
+
+// Waits for the stream and reports a class label that fell outside the embedding table in any call since the last check.
+extern "C" int ldmae_dit_check_labels(ldmae_dit* h, void* stream) {
+  LDMAE_REQUIRE(h, "null handle");
+  LDMAE_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  return dit_label_check(h);
+}
+// Generation of the handle's shared workspace: bumped by every forward (inference or training) and every workspace
+// re-allocation.  A caller that keeps a training forward pending (autograd) records it and compares before the backward.
+extern "C" long long ldmae_dit_generation(ldmae_dit* h) { return h ? h->ws_gen : -1; }
 
 extern "C" int ldmae_dit_forward(ldmae_dit* h, const float* x, const float* t, float t_scalar, const int64_t* y,
                                  float* out, int32_t B, int32_t src_mod, void* stream) {

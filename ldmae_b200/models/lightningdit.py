@@ -165,6 +165,8 @@ class LightningDiT(nn.Module):
         self._handle = None
         self._handle_sig = None
         self._handle_dev = None
+        self._sig_items = None
+        self._dirty_names = None
 
     # -- init exactly as the reference (lightningdit.py:340-374)
     def initialize_weights(self):
@@ -208,7 +210,7 @@ class LightningDiT(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k in ("_handle", "_handle_sig", "_handle_dev"):
+            if k in ("_handle", "_handle_sig", "_handle_dev", "_sig_items", "_dirty_names"):
                 new.__dict__[k] = None
             else:
                 new.__dict__[k] = copy.deepcopy(v, memo)
@@ -226,50 +228,80 @@ class LightningDiT(nn.Module):
             self._handle = None
             self._handle_sig = None
 
-    def _weights(self):
-        sd = {}
-        for k, v in self.state_dict().items():
-            sd[k] = v
-        return sd
+    # -- weight cache ------------------------------------------------------------------------
+    def _apply(self, fn, *a, **k):
+        # .to() / .cuda() / .float(): parameters move, the library's packed copies are stale
+        self._sig_items = None
+        return super()._apply(fn, *a, **k)
 
-    def _signature(self, tensors):
-        return tuple((t.data_ptr(), t._version) for t in tensors)
+    def load_state_dict(self, *a, **k):
+        self._sig_items = None
+        return super().load_state_dict(*a, **k)
+
+    def mark_weights_dirty(self, names=None):
+        """Tell the library that parameters changed behind PyTorch's version counters: in-place edits through ``p.data``
+        (custom EMA / clipping / init code), raw-pointer writes (``ldmae_adamw_ema_step``), or re-assigned Parameter
+        objects.  Ordinary edits (optimizer steps on the parameters, ``load_state_dict``, ``.to()``) are picked up
+        automatically.  ``names``: state_dict keys to re-upload (default: everything)."""
+        if names is None:
+            self._sig_items = None
+            self._handle_sig = None
+        else:
+            self._dirty_names = set(getattr(self, "_dirty_names", ())) | set(names)
+
+    refresh_weights = mark_weights_dirty
+
+    def _signature_items(self):
+        """(key, tensor) of everything the library holds a copy of; the list is cached (Parameter objects are stable
+        across .to() and load_state_dict), the per-call check only reads data_ptr / _version of each."""
+        items = getattr(self, "_sig_items", None)
+        if items is None:
+            items = list(self.state_dict(keep_vars=True).items())
+            self._sig_items = items
+        return items
 
     def _ensure_handle(self, device, batch):
-        """Create the library handle on first use and re-upload weights whenever a parameter changed
-        (load_state_dict, optimizer / EMA step, .to())."""
+        """Create the library handle on first use and re-upload the weights that changed since the last call
+        (load_state_dict, optimizer / EMA step, .to(), mark_weights_dirty)."""
         if device.type != "cuda":
             raise _lib.LdmaeError("ldmae_b200.LightningDiT runs on a CUDA (B200) device only; there is no CPU path")
         L = _lib.lib()
-        sd = self._weights()
-        tensors = list(sd.values())
+        items = self._signature_items()
         if self._handle is None or self._handle_dev != device:
             self._release()
             cfg = _lib.DitConfig(
                 depth=self.depth, hidden_size=self.hidden_size, num_heads=self.num_heads, patch_size=self.patch_size,
                 input_size=self.input_size, in_channels=self.in_channels,
                 num_embeddings=self.y_embedder.embedding_table.weight.shape[0],
-                mlp_hidden=self.blocks[0].mlp.w3.weight.shape[1], learn_sigma=int(self.learn_sigma),
-                use_qknorm=int(self.use_qknorm), use_swiglu=1, use_rope=int(self.use_rope), use_rmsnorm=1,
-                wo_shift=int(self.wo_shift), max_batch=max(1, batch))
+                mlp_hidden=self.blocks[0].mlp.w3.weight.shape[1] if self.use_swiglu else self.blocks[0].mlp.fc1.weight.shape[0],
+                learn_sigma=int(self.learn_sigma),
+                use_qknorm=int(self.use_qknorm), use_swiglu=int(self.use_swiglu), use_rope=int(self.use_rope),
+                use_rmsnorm=int(self.use_rmsnorm), wo_shift=int(self.wo_shift), max_batch=max(1, batch))
             h = C.c_void_p()
             with torch.cuda.device(device):
                 _lib.check(L.ldmae_dit_create(C.byref(cfg), C.byref(h)), "ldmae_dit_create")
             self._handle, self._handle_dev, self._handle_sig = h, device, None
-        sig = self._signature(tensors)
-        if sig != self._handle_sig:
-            st = _lib.stream_ptr()
-            for k, v in sd.items():
-                t = v.detach()
-                if t.dtype != torch.float32 or not t.is_contiguous():
-                    t = t.float().contiguous()
-                if t.device != device:
-                    raise _lib.LdmaeError(f"parameter {k} is on {t.device}, expected {device}")
-                _lib.check(L.ldmae_dit_load_tensor(self._handle, k.encode(), _lib.ptr(t), t.numel(), st),
-                           f"load {k}")
-            _lib.check(L.ldmae_dit_finalize(self._handle, st), "ldmae_dit_finalize")
-            torch.cuda.current_stream().synchronize()      # temporaries above may be freed after this
+        sig = {k: (t.data_ptr(), t._version) for k, t in items}
+        old = self._handle_sig
+        dirty = getattr(self, "_dirty_names", None)
+        if old != sig or dirty:
+            changed = [(k, t) for k, t in items if old is None or old.get(k) != sig[k] or (dirty and k in dirty)]
+            with torch.cuda.device(device):          # pack kernels must run on the handle's device and its current stream
+                st = _lib.stream_ptr()
+                keep = []
+                for k, v in changed:
+                    t = v.detach()
+                    if t.device != device:
+                        raise _lib.LdmaeError(f"parameter {k} is on {t.device}, expected {device}")
+                    if t.dtype != torch.float32 or not t.is_contiguous():
+                        t = t.float().contiguous()
+                        keep.append(t)
+                    _lib.check(L.ldmae_dit_load_tensor(self._handle, k.encode(), _lib.ptr(t), t.numel(), st), f"load {k}")
+                _lib.check(L.ldmae_dit_finalize(self._handle, st), "ldmae_dit_finalize")
+                if keep:
+                    torch.cuda.current_stream().synchronize()      # the temporaries above may be freed after this
             self._handle_sig = sig
+            self._dirty_names = None
         return self._handle
 
     @staticmethod
@@ -342,19 +374,27 @@ class _DitTrainFunction(torch.autograd.Function):
                                                           _lib.stream_ptr()), "ldmae_dit_train_forward")
         ctx.h, ctx.B, ctx.names, ctx.dev = h, B, names, x.device
         ctx.shapes = [tuple(p.shape) for p in params]
-        ctx.flat = getattr(model, "_flat_grad_views", None)      # ldmae_b200.training: gradients land in one flat buffer
+        # the library keeps ONE set of activations per handle: remember which forward they belong to
+        ctx.gen = int(_lib.lib().ldmae_dit_generation(h))
         return out
 
     @staticmethod
     def backward(ctx, dout):
         L = _lib.lib()
+        now = int(L.ldmae_dit_generation(ctx.h))
+        if now != ctx.gen:
+            raise _lib.LdmaeError(
+                "LightningDiT backward: the model ran another forward (training, no_grad, forward_with_cfg or a sampler) after "
+                f"the forward this backward belongs to (workspace generation {ctx.gen}, now {now}).  ldmae_b200 keeps the "
+                "activations of ONE training forward per model: call backward() before the next forward; expressions like "
+                "(model(a) + model(b)).backward() and activation checkpointing are not supported -- use gradient accumulation")
         dout = dout.detach().float().contiguous()
         grads = []
         with torch.cuda.device(ctx.dev):
             st = _lib.stream_ptr()
             _lib.check(L.ldmae_dit_backward(ctx.h, _lib.ptr(dout), ctx.B, st), "ldmae_dit_backward")
             for name, shape in zip(ctx.names, ctx.shapes):
-                g = ctx.flat[name] if ctx.flat is not None else torch.empty(shape, device=ctx.dev, dtype=torch.float32)
+                g = torch.empty(shape, device=ctx.dev, dtype=torch.float32)
                 _lib.check(L.ldmae_dit_grad_read(ctx.h, name.encode(), _lib.ptr(g), g.numel(), st), f"grad {name}")
                 grads.append(g)
         return (None, None, None, None, None, None, *grads)

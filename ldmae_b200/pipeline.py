@@ -28,6 +28,12 @@ class SamplingJob:
         self.use_cfg = self.cfg_scale > 1.0                      # inference.py:173,278-285
         self.cfg_interval_start = cfg_interval_start
         self.null_class = model.y_embedder.num_classes           # inference.py:279 (hard-coded 1000 there)
+        if self.use_cfg and model.y_embedder.embedding_table.weight.shape[0] <= self.null_class:
+            # class_dropout_prob == 0 builds the table without the null row (lightningdit.py:146-148); the reference would
+            # hit nn.Embedding's device assert on label num_classes -- fail here, before any kernel reads out of bounds
+            raise ValueError(f"classifier-free guidance (cfg_scale {self.cfg_scale}) needs the null-class row {self.null_class} "
+                             f"of y_embedder.embedding_table, but the model was built with class_dropout_prob=0 "
+                             f"({model.y_embedder.embedding_table.weight.shape[0]} rows)")
         transport = create_transport("Linear", "velocity", None, None, None, use_cosine_loss=False, use_lognorm=True)
         self.sample_fn = Sampler(transport).sample_ode(sampling_method=sampling_method, num_steps=num_steps, atol=1e-6,
                                                        rtol=1e-3, reverse=False, timestep_shift=timestep_shift,
@@ -71,14 +77,27 @@ class SamplingJob:
         return self.decode_u8(self.sample_latents(z, y))
 
     # -- host-to-host path (what inference.py does per iteration) --------------------------------
-    def run_host(self, z_host, y_host, out_host=None):
-        """Pinned host z / y in, uint8 images out on the host (pinned ``out_host`` is reused when given)."""
+    def run_host(self, z_host, y_host, out_host=None, events=None):
+        """Pinned host z / y in, uint8 images out on the host (pinned ``out_host`` is reused when given).
+
+        ``events``: optional 4 ``torch.cuda.Event(enable_timing=True)`` recorded on the current stream -- before the
+        host-to-device copies, after them (= start of the device-resident job), after the decode (= its end) and after
+        the device-to-host copy of the images; bench.py derives ``value`` (inner pair) and ``e2e`` (outer pair) from the
+        same call."""
+        if events is not None:
+            events[0].record()
         z = z_host.to(self.device, non_blocking=True)
         y = y_host.to(self.device, non_blocking=True)
+        if events is not None:
+            events[1].record()
         u8 = self.run_device(z, y)
+        if events is not None:
+            events[2].record()
         if out_host is None:
             out_host = torch.empty(u8.shape, dtype=torch.uint8, pin_memory=True)
         out_host.copy_(u8, non_blocking=True)
+        if events is not None:
+            events[3].record()
         torch.cuda.current_stream(self.device).synchronize()
         return out_host
 

@@ -253,18 +253,24 @@ class MaskedAutoencoderViT(nn.Module):
             self._handle, self._handle_dev, self._handle_sig = h, device, None
         sig = tuple((t.data_ptr(), t._version) for t in sd.values())
         if sig != self._handle_sig:
-            st = _lib.stream_ptr()
-            for k, v in sd.items():
-                t = v.detach()
-                if t.dtype != torch.float32 or not t.is_contiguous():
-                    t = t.float().contiguous()
-                if t.device != device:
-                    raise _lib.LdmaeError(f"parameter {k} is on {t.device}, expected {device}")
-                _lib.check(L.ldmae_vmae_load_tensor(self._handle, k.encode(), _lib.ptr(t), t.numel(), st), f"load {k}")
-            _lib.check(L.ldmae_vmae_finalize(self._handle, st), "ldmae_vmae_finalize")
-            torch.cuda.current_stream().synchronize()
+            with torch.cuda.device(device):          # pack kernels must run on the handle's device and its current stream
+                st = _lib.stream_ptr()
+                for k, v in sd.items():
+                    t = v.detach()
+                    if t.dtype != torch.float32 or not t.is_contiguous():
+                        t = t.float().contiguous()
+                    if t.device != device:
+                        raise _lib.LdmaeError(f"parameter {k} is on {t.device}, expected {device}")
+                    _lib.check(L.ldmae_vmae_load_tensor(self._handle, k.encode(), _lib.ptr(t), t.numel(), st), f"load {k}")
+                _lib.check(L.ldmae_vmae_finalize(self._handle, st), "ldmae_vmae_finalize")
+                torch.cuda.current_stream().synchronize()
             self._handle_sig = sig
         return self._handle
+
+    def mark_weights_dirty(self):
+        """Re-upload the weights on the next call (needed after in-place edits through ``p.data`` or raw pointers, which
+        PyTorch's version counters do not see)."""
+        self._handle_sig = None
 
     def _decode(self, z, want_f32, want_u8, mean=None, std=None, multiplier=1.0):
         z = z.detach().float().contiguous()

@@ -140,7 +140,7 @@ class FusedTrainer:
                 _lib.ptr(self.flat), _lib.ptr(self.grad), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), _lib.ptr(self.ema),
                 self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count,
                 self.ema_decay, grad_scale, _lib.stream_ptr()), "adamw_ema_step")
-        self.model._handle_sig = None                                  # parameters changed behind torch's version counters
+        self.model.mark_weights_dirty(self.names)                      # parameters changed behind torch's version counters
 
     def step(self, x1, y, t=None, x0=None, micro_batches=1):
         """One optimizer step; micro_batches > 1 splits the batch and accumulates gradients (train_accum.py's

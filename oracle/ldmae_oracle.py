@@ -312,7 +312,7 @@ def apply_rope(x: Tensor, cos: Tensor, sin: Tensor) -> Tensor:
 def timestep_embedding(t: Tensor, dim: int = 256, max_period: float = 10000.0) -> Tensor:
     """models/lightningdit.py:108-131 (t is NOT scaled by 1000)."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32, device=t.device) / half)
     args = t[:, None].float() * freqs[None]
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 
@@ -467,7 +467,7 @@ def sample_ode(model_fn: Callable, x: Tensor, *, sampling_method: str = "euler",
     t = ode_time_grid(num_steps, timestep_shift)
 
     def _fn(tk, xk):
-        tv = torch.ones(xk.size(0)) * tk          # integrators.py:111
+        tv = torch.ones(xk.size(0), device=xk.device) * tk          # integrators.py:111
         out = model_fn(xk, tv, **model_kwargs)
         assert out.shape == xk.shape              # transport.py:247
         return out
@@ -560,7 +560,7 @@ def sample_images(dit_sd: SD, ds: DiTSpec, vae_sd: SD, vs: VMAESpec, z: Tensor, 
     n = z.shape[0]
     if cfg_scale > 1.0:
         zz = torch.cat([z, z], 0)
-        yy = torch.cat([y, torch.full((n,), ds.num_classes, dtype=y.dtype)], 0)
+        yy = torch.cat([y, torch.full((n,), ds.num_classes, dtype=y.dtype, device=y.device)], 0)
         fn = lambda x, t, **kw: dit_forward_with_cfg(dit_sd, ds, x, t, **kw)
         kw = dict(y=yy, cfg_scale=cfg_scale, cfg_interval=True, cfg_interval_start=cfg_interval_start)
     else:

@@ -196,7 +196,48 @@ def gen_vmae():
         print("vmae", tag, "img absmax", img.abs().max().item(), "u8 mean", u8.mean())
 
 
+def gen_config1():
+    """BASELINE.json configs[0]: LightningDiT-B/1, batch 8 (16 with CFG), 10-point shifted Euler grid (9 evaluations),
+    cfg_scale 10 with cfg_interval_start 0.10, then VMAE decode -- the body of inference.py:264-292 through the
+    reference's own modules (about 100 s of CPU).  The benchmarked job (configs[1]) is this recipe with 250 points."""
+    spec = O.DiTSpec.named("LightningDiT-B/1", input_size=32, in_channels=16)
+    ref = LightningDiT_models["LightningDiT-B/1"](input_size=32, in_channels=16, use_qknorm=True, use_swiglu=True,
+                                                  use_rope=True, use_rmsnorm=True)
+    sd = O.synth_dit_state(spec, seed=1234)
+    assert not load_into(ref, sd)
+    ref.eval()
+    vspec = O.VMAESpec(img_size=256)
+    vae = ref_mae.mae_for_ldmae_f8d16_prev(ldmae_mode=True, no_cls=True, kl_loss_weight=True, smooth_output=True,
+                                           img_size=256).eval()
+    vsd = O.synth_vmae_state(vspec, seed=77, encoder=True)
+    assert not load_into(vae, vsd)
+    g = torch.Generator().manual_seed(0)
+    n = 8
+    z = torch.randn(n, 16, 32, 32, generator=g)
+    y = torch.randint(0, 1000, (n,), generator=g)
+    zz = torch.cat([z, z], 0)                                               # inference.py:278-282
+    yy = torch.cat([y, torch.full((n,), 1000)], 0)
+    tr = create_transport("Linear", "velocity", None, None, None, use_cosine_loss=False, use_lognorm=True)
+    fn = Sampler(tr).sample_ode(sampling_method="euler", num_steps=10, atol=1e-6, rtol=1e-3, reverse=False, timestep_shift=0.3)
+    traj = fn(zz, ref.forward_with_cfg, y=yy, cfg_scale=10.0, cfg_interval=True, cfg_interval_start=0.10)
+    lat = traj[-1].chunk(2, dim=0)[0]                                       # inference.py:287-289
+    mean = torch.linspace(-0.25, 0.25, 16).view(1, 16, 1, 1)                # synthetic latents_stats (inference.py:291)
+    std = torch.linspace(0.75, 1.25, 16).view(1, 16, 1, 1)
+    mult = 1.0
+    img = vae.decode((lat * std) / mult + mean, return_dict=False)[0]
+    u8 = torch.clamp(127.5 * img + 128.0, 0, 255).permute(0, 2, 3, 1).to(torch.uint8).numpy()
+    np.savez_compressed(os.path.join(OUT, "config1_b1_cfg10.npz"), dit_seed=1234, vmae_seed=77,
+                        dit_checksum=O.state_checksum(sd), vmae_checksum=O.state_checksum(vsd), z=z.numpy(), y=y.numpy(),
+                        grid=fn.__self__.t.numpy(), latents=lat.numpy(), traj_norm=traj.flatten(1).norm(dim=1).numpy(),
+                        mid_state=traj[5][:2].numpy(), latent_mean=mean.numpy(), latent_std=std.numpy(), latent_multiplier=mult,
+                        img_first=img[:1].numpy(), u8=u8[:4])
+    print("config 1: latent absmax", lat.abs().max().item(), "std", lat.std().item(), "u8 mean", u8.mean())
+
+
 if __name__ == "__main__":
+    if "--config1-only" in sys.argv:
+        gen_config1()
+        sys.exit(0)
     if "--grads-only" in sys.argv:
         gen_dit_grads()
         sys.exit(0)
@@ -205,4 +246,5 @@ if __name__ == "__main__":
     gen_dit_variants()
     gen_dit_b1()
     gen_vmae()
+    gen_config1()
     print("golden fixtures written to", OUT)

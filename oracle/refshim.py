@@ -4,8 +4,9 @@ Lets the reference's hot-path files (``/root/reference/LDMAE/models/lightningdit
 ``transport/*``, ``tokenizer/models_mae.py``) import verbatim in this container, where
 ``timm``, ``fairscale``, ``torchdiffeq``, ``diffusers`` and ``taming`` are not installed.
 It is used by ``oracle/make_golden.py`` (here, on CPU) to produce the committed fixtures
-under ``tests/golden/``; it cannot travel to the GPU box (``/root/reference`` is absent
-there) and nothing in the product imports it.
+under ``tests/golden/`` and by ``bench.py``'s reference / cpu_baseline legs.  ``/root/reference`` is absent on
+the GPU box; ``oracle/build_ref.py`` stages the files of the path under ``oracle/_ref/`` (git-ignored, travels with
+the snapshot) and the shim falls back to that copy.  Nothing in the product imports it.
 
 What is restated (third-party arithmetic that is not under /root/reference):
 
@@ -27,7 +28,18 @@ import types
 import torch
 import torch.nn as nn
 
-REF_ROOT = os.environ.get("LDMAE_REFERENCE_ROOT", "/root/reference/LDMAE")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "LDMAE")     # oracle/build_ref.py
+
+
+def _default_root():
+    """The reference tree itself where it exists (authoring container), else the copy staged by oracle/build_ref.py
+    (git-ignored; travels to the GPU box)."""
+    if os.path.isdir("/root/reference/LDMAE/models"):
+        return "/root/reference/LDMAE"
+    return _STAGED
+
+
+REF_ROOT = os.environ.get("LDMAE_REFERENCE_ROOT") or _default_root()
 
 
 # --------------------------------------------------------------------------- timm

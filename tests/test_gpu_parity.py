@@ -249,3 +249,201 @@ def test_dit_xl_head_dim_72_forward_and_sampler_vs_oracle():
     want = O.sample_ode(ref_fn, z, sampling_method="euler", num_steps=5, timestep_shift=0.3, y=ycfg, cfg_scale=4.0,
                         cfg_interval=True, cfg_interval_start=0.10)[-1]
     assert _rel(ours, want) < FINAL_TOL
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The benchmarked configuration itself (BASELINE.json configs[0] / configs[1]): B/1, cfg_scale 10, interval 0.10, shift 0.3
+# ------------------------------------------------------------------------------------------------------------------
+def _b1_and_vmae(dit_seed, vmae_seed):
+    from ldmae_b200.models.lightningdit import LightningDiT_models
+    from ldmae_b200.tokenizer import models_mae
+    ds = O.DiTSpec.named("LightningDiT-B/1", input_size=32, in_channels=16)
+    vs = O.VMAESpec(img_size=256)
+    dsd, vsd = O.synth_dit_state(ds, dit_seed), O.synth_vmae_state(vs, vmae_seed, encoder=True)
+    m = LightningDiT_models["LightningDiT-B/1"](input_size=32, in_channels=16, use_qknorm=True, use_swiglu=True,
+                                                use_rope=True, use_rmsnorm=True)
+    m.load_state_dict(dsd, strict=True)
+    vae = models_mae.mae_for_ldmae_f8d16_prev(ldmae_mode=True, no_cls=True, kl_loss_weight=True, smooth_output=True, img_size=256)
+    vae.load_state_dict(vsd, strict=True)
+    return ds, dsd, m.cuda().eval(), vs, vsd, vae.cuda().eval()
+
+
+def test_config1_b1_cfg10_vs_reference_golden(golden_dir):
+    """BASELINE.json configs[0] through the public job API against the unmodified reference's output: LightningDiT-B/1,
+    batch 8 (16 with CFG), 10-point shifted Euler grid, cfg_scale 10 (x10 on (cond - uncond), channels 0-2), guidance
+    interval 0.10, latent de-normalisation, VMAE decode to uint8 (inference.py:264-292)."""
+    from ldmae_b200.pipeline import SamplingJob
+    from gpu_util import load_npz
+    g = load_npz(golden_dir, "config1_b1_cfg10.npz")
+    ds, dsd, m, vs, vsd, vae = _b1_and_vmae(int(g["dit_seed"]), int(g["vmae_seed"]))
+    job = SamplingJob(m, vae, num_steps=10, cfg_scale=10.0, cfg_interval_start=0.10, timestep_shift=0.3,
+                      latent_mean=torch.from_numpy(g["latent_mean"]), latent_std=torch.from_numpy(g["latent_std"]),
+                      latent_multiplier=float(g["latent_multiplier"]))
+    assert np.array_equal(job.sample_fn.t.numpy(), g["grid"])
+    z, y = torch.from_numpy(g["z"]).cuda(), torch.from_numpy(g["y"]).cuda()
+    lat = job.sample_latents(z, y)
+    err = _rel(lat, g["latents"])
+    per_img = [(_rel(lat[i], g["latents"][i])) for i in range(lat.shape[0])]
+    print(f"config 1: final latent rel err {err:.3e} (per image max {max(per_img):.3e})")
+    assert err < FINAL_TOL and max(per_img) < FINAL_TOL
+    u8 = job.decode_u8(lat).cpu().numpy()
+    img = vae.decode((lat * job.latent_std) / job.latent_multiplier + job.latent_mean, return_dict=False)[0]
+    ierr = _rel(img[:1], g["img_first"])
+    diff = np.abs(u8[:4].astype(np.int32) - g["u8"].astype(np.int32))
+    print(f"config 1: image rel err {ierr:.3e}; uint8 within 1 level {(diff <= 1).mean():.4f}, within 2 {(diff <= 2).mean():.4f}")
+    assert ierr < FINAL_TOL
+    assert (diff <= 2).mean() > 0.99 and diff.mean() < 1.0
+    # run_host (pinned host in, pinned host out) is the same job
+    out = job.run_host(torch.from_numpy(g["z"]).pin_memory(), torch.from_numpy(g["y"]).pin_memory())
+    assert np.array_equal(out.numpy(), u8)
+
+
+def test_b1_250_point_cfg10_sampler_vs_fp32_oracle_on_gpu():
+    """The benchmarked job (BASELINE.json configs[1]: 250-point shifted Euler grid = 249 evaluations, cfg 10, interval 0.10)
+    on 4 images, against the oracle evaluated in strict fp32 on the same GPU (TF32 off).  Records how the bf16-operand
+    error grows along the trajectory; the final latent must stay within the north_star's 2e-2."""
+    from ldmae_b200.transport import Sampler, create_transport
+    ds, dsd, m, vs, vsd, vae = _b1_and_vmae(1234, 77)
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        g = torch.Generator().manual_seed(0)
+        n = 4
+        z = torch.randn(n, 16, 32, 32, generator=g).cuda()
+        y = torch.randint(0, 1000, (n,), generator=g).cuda()
+        zz = torch.cat([z, z], 0)
+        yy = torch.cat([y, torch.full((n,), 1000, device="cuda")], 0)
+        kw = dict(y=yy, cfg_scale=10.0, cfg_interval=True, cfg_interval_start=0.10)
+        fn = Sampler(create_transport("Linear", "velocity", None, None, None)).sample_ode(
+            sampling_method="euler", num_steps=250, atol=1e-6, rtol=1e-3, reverse=False, timestep_shift=0.3, keep_trajectory=True)
+        ours = fn(zz, m.forward_with_cfg, **kw)
+        sd_gpu = {k: v.cuda() for k, v in dsd.items()}
+        ref_fn = lambda xx, tt, **k: O.dit_forward_with_cfg(sd_gpu, ds, xx, tt, **k)
+        want = O.sample_ode(ref_fn, zz, sampling_method="euler", num_steps=250, timestep_shift=0.3, **kw)
+        assert len(ours) == 250 and want.shape[0] == 250
+        growth = {k: _rel(ours[k][:n], want[k][:n]) for k in (1, 50, 100, 150, 200, 249)}
+        print("250-point cfg-10 B/1 sampler, rel err of the kept half vs fp32 oracle by grid index:",
+              ", ".join(f"{k}: {v:.2e}" for k, v in growth.items()))
+        # per-forward velocity error at three points of the trajectory, on the oracle's own states
+        for k in (0, 120, 248):
+            tk = torch.full((2 * n,), float(fn.t[k]), device="cuda")
+            v_ours = m.forward_with_cfg(want[k], tk, **kw)
+            v_ref = O.dit_forward_with_cfg(sd_gpu, ds, want[k], tk, **kw)
+            e = _rel(v_ours[:n], v_ref[:n])
+            print(f"  guided velocity rel err at grid index {k} (t = {float(fn.t[k]):.4f}): {e:.2e}")
+            assert e < 2 * FWD_TOL          # cfg 10 amplifies (cond - uncond) error on channels 0-2
+        assert growth[249] < FINAL_TOL
+        # decode both final latents: images within tolerance too
+        a = vae.decode(ours[-1][:n], return_dict=False)[0]
+        b = O.vmae_decode({k: v.cuda() for k, v in vsd.items()}, vs, want[-1][:n])
+        print(f"  decoded image rel err {_rel(a, b):.2e}")
+        assert _rel(a, b) < FINAL_TOL
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Index work must be bit-exact: patchify / token order / unpatchify (lightningdit.py:376-389,402) and the uint8 NHWC pack
+# ------------------------------------------------------------------------------------------------------------------
+def _index_model(patch):
+    """Tiny model whose forward is an exact function of the indices only: every adaLN matrix is zero (gates = 0: the blocks
+    leave the stream untouched bit for bit; scale = shift = 0), the patch embedding and the final linear are one-hot
+    selections, pos_embed and the biases are zero.  Then  out = unpatchify(patchify(x)) * r = x * r  for a single row factor r
+    as long as every token's patch vector has the same sum of squares."""
+    from ldmae_b200.models.lightningdit import LightningDiT
+    C, S, D = 16, 8, 128
+    m = LightningDiT(input_size=S, patch_size=patch, in_channels=C, hidden_size=D, depth=2, num_heads=2, num_classes=10,
+                     use_qknorm=True, use_swiglu=True, use_rope=True, use_rmsnorm=True)
+    Kp = C * patch * patch
+    assert Kp <= D
+    with torch.no_grad():
+        m.pos_embed.zero_()
+        w = torch.zeros(D, C, patch, patch)
+        for c in range(C):
+            for pi in range(patch):
+                for qi in range(patch):
+                    w[(c * patch + pi) * patch + qi, c, pi, qi] = 1.0       # Conv2d weight order (c, pi, qi)
+        m.x_embedder.proj.weight.copy_(w)
+        m.x_embedder.proj.bias.zero_()
+        wf = torch.zeros(patch * patch * C, D)
+        for pi in range(patch):
+            for qi in range(patch):
+                for c in range(C):
+                    wf[(pi * patch + qi) * C + c, (c * patch + pi) * patch + qi] = 1.0   # unpatchify column order (p, q, c)
+        m.final_layer.linear.weight.copy_(wf)
+        m.final_layer.linear.bias.zero_()
+        # initialize_weights already zeroes every adaLN_modulation[-1] (lightningdit.py:365-372)
+        for blk in m.blocks:
+            assert float(blk.adaLN_modulation[-1].weight.abs().max()) == 0.0
+    return m.cuda().eval(), Kp
+
+
+def _index_input(B, C, S, patch, Kp):
+    """Integer-valued latents (exact in bf16) where each token's patch vector is a distinct signed cyclic shift of 1..Kp:
+    same sum of squares for every token, every (token, column) pair identifiable."""
+    G = S // patch
+    x = torch.zeros(B, C, S, S)
+    for b in range(B):
+        for th in range(G):
+            for tw in range(G):
+                tok = th * G + tw
+                for c in range(C):
+                    for pi in range(patch):
+                        for qi in range(patch):
+                            k = (c * patch + pi) * patch + qi
+                            v = 1 + (k + tok + 7 * b) % Kp
+                            sign = -1.0 if (((tok // Kp) >> (k % 8)) & 1) else 1.0     # tok // Kp in binary over the columns
+                            x[b, c, th * patch + pi, tw * patch + qi] = sign * v
+    return x
+
+
+@pytest.mark.parametrize("patch", [1, 2])
+def test_patchify_token_order_unpatchify_bit_exact(patch):
+    from ldmae_b200 import _lib
+    m, Kp = _index_model(patch)
+    B, C, S, D = 3, 16, 8, 128
+    G = S // patch
+    T = G * G
+    x = _index_input(B, C, S, patch, Kp).cuda()
+    t = torch.tensor([0.1, 0.5, 0.9], device="cuda")
+    y = torch.tensor([1, 5, 10], device="cuda")
+    out = m(x, t, y)
+    # (1) the whole forward is the identity up to ONE row factor: unpatchify(final(patchify(x))) == x * r, bit for bit
+    r = out[0, 0, 0, 0] / x[0, 0, 0, 0]
+    assert 0.0 < float(r) and torch.isfinite(r)
+    assert torch.equal(out, x * r), "patchify -> token order -> unpatchify is not the identity permutation"
+    # (2) patchify + token order alone: the residual stream after the patch embedding holds the patch vectors exactly
+    L, h = _lib.lib(), m._handle
+    _lib.check(L.ldmae_dit_debug_stop(h, 4))
+    try:
+        m(x, t, y)
+        xres = torch.empty(B * T * D, device="cuda")
+        _lib.check(L.ldmae_dit_debug_read(h, b"xres", _lib.ptr(xres), xres.numel() * 4, _lib.stream_ptr()))
+        torch.cuda.synchronize()
+    finally:
+        _lib.check(L.ldmae_dit_debug_stop(h, -1))
+    xres = xres.view(B, T, D)
+    want = torch.nn.functional.unfold(x, kernel_size=patch, stride=patch).transpose(1, 2)     # [B, T, C*p*p], (c, pi, qi) order
+    assert torch.equal(xres[:, :, :Kp], want)
+    assert float(xres[:, :, Kp:].abs().max()) == 0.0 if Kp < D else True
+    # (3) the module's own unpatchify (index-only) equals the reference einsum on an index tensor
+    idx = torch.arange(B * T * patch * patch * C, dtype=torch.float32).view(B, T, patch * patch * C)
+    assert torch.equal(m.unpatchify(idx), O.unpatchify(idx, patch, C))
+
+
+def test_uint8_nhwc_pack_bit_exact():
+    """decode_to_images' tail (models_mae.py:972): clamp(127.5*x + 128, 0, 255), NCHW -> NHWC, truncating cast.  The fused
+    kernel's bytes equal that expression applied to the kernel's own fp32 image, bit for bit."""
+    from ldmae_b200.tokenizer import models_mae
+    vs = O.VMAESpec(img_size=32)
+    vae = models_mae.mae_for_ldmae_f8d16_prev(ldmae_mode=True, no_cls=True, kl_loss_weight=True, smooth_output=True, img_size=32)
+    vae.load_state_dict(O.synth_vmae_state(vs, 5, encoder=True), strict=True)
+    vae = vae.cuda().eval()
+    z = torch.randn(5, 16, 4, 4, generator=torch.Generator().manual_seed(2)).cuda() * 3.0     # saturates some pixels both ways
+    f32, u8 = vae._decode(z, True, True)
+    want = torch.clamp(127.5 * f32 + 128.0, 0, 255).permute(0, 2, 3, 1).to(torch.uint8)
+    assert u8.shape == (5, 32, 32, 3) and u8.dtype == torch.uint8
+    assert torch.equal(u8, want)
+    assert int((want == 0).sum()) > 0 and int((want == 255).sum()) > 0          # both clamps exercised
+    assert np.array_equal(vae.decode_to_images(z), want.cpu().numpy())

@@ -282,3 +282,59 @@ def test_fused_trainer_reduces_the_loss_on_a_fixed_batch():
     ema = tr.ema_state_dict()[k]
     d_live = float((live.cpu() - sd[k]).norm()); d_ema = float((ema.cpu() - sd[k]).norm())
     assert 0 < d_ema < d_live                                # the EMA moved, but less than the live weights
+
+
+def test_second_forward_before_backward_fails_loudly():
+    """The library keeps the activations of ONE training forward per model; a backward whose forward is no longer the latest
+    (two grad-enabled forwards, or any inference call in between) must raise instead of returning wrong gradients."""
+    from ldmae_b200 import _lib
+    spec, sd, m = _tiny(1, 12)
+    g = torch.Generator().manual_seed(1)
+    xa, xb = torch.randn(2, 16, 8, 8, generator=g).cuda(), torch.randn(2, 16, 8, 8, generator=g).cuda()
+    t = torch.rand(2, generator=g).cuda(); y = torch.randint(0, 10, (2,), generator=g).cuda()
+    a = m(xa, t, y)
+    b = m(xb, t, y)
+    with pytest.raises(_lib.LdmaeError, match="ONE training forward"):
+        (a.sum() + b.sum()).backward()
+    m.zero_grad(set_to_none=True)
+    c = m(xa, t, y)
+    with torch.no_grad():
+        m(xb, t, y)                                   # inference call in between overwrites the shared workspace
+    with pytest.raises(_lib.LdmaeError, match="ONE training forward"):
+        c.sum().backward()
+    # the C ABI itself refuses too (callers that bypass the autograd node)
+    L, h = _lib.lib(), m._handle
+    out = torch.empty_like(xa)
+    _lib.check(L.ldmae_dit_train_forward(h, _lib.ptr(xa), _lib.ptr(t), _lib.ptr(y), _lib.ptr(out), 2, _lib.stream_ptr()))
+    _lib.check(L.ldmae_dit_forward(h, _lib.ptr(xb), _lib.ptr(t), 0.0, _lib.ptr(y), _lib.ptr(out), 2, 2, _lib.stream_ptr()))
+    assert L.ldmae_dit_backward(h, _lib.ptr(out), 2, _lib.stream_ptr()) != 0
+    assert b"one training forward" in L.ldmae_last_error()
+    # and the regular order still works afterwards
+    m.zero_grad(set_to_none=True)
+    m(xa, t, y).sum().backward()
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
+
+
+def test_out_of_range_class_label_is_flagged_not_read():
+    """nn.Embedding would device-assert (lightningdit.py:146-169); the library clamps the index, never reads or writes
+    outside the table, and reports the bad label."""
+    from ldmae_b200 import _lib
+    from ldmae_b200.models.lightningdit import LightningDiT
+    from ldmae_b200.pipeline import SamplingJob
+    from ldmae_b200.tokenizer import models_mae
+    m = LightningDiT(input_size=8, patch_size=1, in_channels=16, hidden_size=128, depth=2, num_heads=2, num_classes=10,
+                     class_dropout_prob=0.0, use_qknorm=True, use_swiglu=True, use_rope=True, use_rmsnorm=True).cuda().eval()
+    assert m.y_embedder.embedding_table.weight.shape[0] == 10          # no null row without label dropout
+    x = torch.randn(2, 16, 8, 8).cuda(); t = torch.rand(2).cuda()
+    with torch.no_grad():
+        m(x, t, torch.tensor([3, 9]).cuda())                            # in range: fine
+        L, h = _lib.lib(), m._handle
+        _lib.check(L.ldmae_dit_check_labels(h, _lib.stream_ptr()))
+        m(x, t, torch.tensor([3, 10]).cuda())                           # 10 is outside a 10-row table
+        assert L.ldmae_dit_check_labels(h, _lib.stream_ptr()) != 0
+        assert b"class label outside" in L.ldmae_last_error()
+        m(x, t, torch.tensor([0, 1]).cuda())                            # the flag was reported once and cleared
+        _lib.check(L.ldmae_dit_check_labels(h, _lib.stream_ptr()))
+    vae = models_mae.mae_for_ldmae_f8d16_prev(ldmae_mode=True, no_cls=True, kl_loss_weight=True, smooth_output=True, img_size=64)
+    with pytest.raises(ValueError, match="null-class row"):
+        SamplingJob(m, vae.cuda().eval(), num_steps=4, cfg_scale=4.0)   # CFG needs the null row this model does not have

@@ -143,3 +143,25 @@ def test_oracle_autograd_reproduces_reference_gradients(golden_dir, patch):
         assert err < 2e-4, (k, err)
         n += 1
     assert n == 40
+
+
+def test_config1_b1_cfg10_subset(golden_dir):
+    """BASELINE.json configs[0] (B/1, 10-point shifted Euler grid, cfg 10, interval 0.10, decode): the oracle reproduces
+    the reference's job.  Samples are independent, so the first image of the 8 is enough to pin every stage (the whole
+    job is ~100 s of CPU; the GPU test covers all 8 images)."""
+    g = _load(golden_dir, "config1_b1_cfg10.npz")
+    ds = O.DiTSpec.named("LightningDiT-B/1", input_size=32, in_channels=16)
+    vs = O.VMAESpec(img_size=256)
+    dsd, vsd = O.synth_dit_state(ds, int(g["dit_seed"])), O.synth_vmae_state(vs, int(g["vmae_seed"]), encoder=True)
+    assert O.state_checksum(dsd) == pytest.approx(float(g["dit_checksum"]), rel=1e-9)
+    assert O.state_checksum(vsd) == pytest.approx(float(g["vmae_checksum"]), rel=1e-9)
+    assert np.array_equal(O.ode_time_grid(10, 0.3).numpy(), g["grid"])
+    assert int((g["grid"][:-1] < 0.10).sum()) == 3          # three of the nine evaluations fall below the guidance interval
+    z, y = _t(g["z"])[:1], _t(g["y"])[:1]
+    lat, img, u8 = O.sample_images(dsd, ds, vsd, vs, z, y, num_steps=10, cfg_scale=10.0, cfg_interval_start=0.10,
+                                   timestep_shift=0.3, latent_mean=_t(g["latent_mean"]), latent_std=_t(g["latent_std"]),
+                                   latent_multiplier=float(g["latent_multiplier"]))
+    torch.testing.assert_close(lat, _t(g["latents"])[:1], rtol=2e-3, atol=2e-4)
+    torch.testing.assert_close(img, _t(g["img_first"]), rtol=2e-3, atol=2e-3)
+    d = np.abs(u8.astype(np.int32) - g["u8"][:1].astype(np.int32))
+    assert (d <= 1).mean() > 0.999
