@@ -94,6 +94,18 @@ int ldmae_adamw_ema_step(float* param, const float* grad, float* exp_avg, float*
                          float beta1, float beta2, float eps, float weight_decay, int32_t step, float ema_decay, float grad_scale,
                          void* stream);
 
+/* Trainer input pipeline and loss, one pass each (reference datasets/img_latent_dataset.py:76-94: flip select, posterior
+ * sample, per-channel normalise, multiplier; transport/transport.py:136-166 + path.py:114-136: xt = t*x1 + (1-t)*x0,
+ * ut = x1 - x0; transport.py:195 + train_accum.py:220-223: loss[b] = mean_flat((out-ut)^2), dout = d(mean_b loss * loss_scale)).
+ * moments / moments_flip [B, 2C, HW] (mean || logvar), flip [B] bytes (non-zero = take the flipped row), eps_post [B, C, HW]
+ * (NULL = posterior mode), mean / std [C] (NULL = no normalisation); OR x1_in [B, C, HW] ready latents (moments NULL).
+ * x0 [B, C, HW] noise, t [B]; outputs xt, ut and optionally x1_out.  HW % 4 == 0. */
+int ldmae_flow_prepare(const float* moments, const float* moments_flip, const uint8_t* flip, const float* eps_post,
+                       const float* mean, const float* stdv, float multiplier, const float* x1_in, const float* x0, const float* t,
+                       float* x1_out, float* xt, float* ut, int32_t B, int32_t C, int32_t HW, void* stream);
+int ldmae_flow_loss(const float* out, const float* ut, float* loss, float* dout /* or NULL */, float loss_scale, int32_t B, int32_t n,
+                    void* stream);
+
 /* Test hooks: make ldmae_dit_forward return after `stages` launch groups (-1 = run everything; 1 conditioning,
  * 2 adaLN, 3 shift vectors, 4 patch embed, then 5 per block: qkv, attention, proj, w12, w3), and copy a named
  * workspace buffer ("xres", "abuf", "qkv", "obuf", "hbuf", "ssq", "mods", ...) to `dst` (device). */

@@ -46,6 +46,8 @@ SYMBOLS = {
     "ldmae_dit_grad_read": (C.c_int, [vp, C.c_char_p, vp, i64, vp]),
     "ldmae_dit_grad_accumulate": (C.c_int, [vp, C.c_char_p, vp, i64, vp]),
     "ldmae_adamw_ema_step": (C.c_int, [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, f32, vp]),
+    "ldmae_flow_prepare": (C.c_int, [vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    "ldmae_flow_loss": (C.c_int, [vp, vp, vp, vp, f32, i32, i32, vp]),
     "ldmae_dit_debug_stop": (C.c_int, [vp, i32]),
     "ldmae_dit_debug_poison": (C.c_int, [vp, i32, vp]),
     "ldmae_dit_debug_read": (C.c_int, [vp, C.c_char_p, vp, i64, vp]),

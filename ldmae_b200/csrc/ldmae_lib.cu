@@ -16,6 +16,7 @@
 #include "gemm_wgrad_sm100.cuh"
 #include "backward_elementwise.cuh"
 #include "elementwise.cuh"
+#include "train_io.cuh"
 
 namespace ldmae {
 
@@ -1006,6 +1007,29 @@ extern "C" int ldmae_dit_forward(ldmae_dit* h, const float* x, const float* t, f
 // ------------------------------------------------------------------------------------------- LightningDiT training
 // Backward of LightningDiT.forward for transport.training_losses / train_accum.py:215-230.
 #include "dit_train.inc"
+
+// Trainer input pipeline + loss (see train_io.cuh).  All pointers are device pointers; HW = S*S, n = C*HW.
+extern "C" int ldmae_flow_prepare(const float* moments, const float* moments_flip, const uint8_t* flip, const float* eps_post,
+                                  const float* mean, const float* stdv, float multiplier, const float* x1_in, const float* x0,
+                                  const float* t, float* x1_out, float* xt, float* ut, int32_t B, int32_t C, int32_t HW, void* stream) {
+  LDMAE_REQUIRE((moments != nullptr) != (x1_in != nullptr), "give either the posterior moments or ready latents x1_in");
+  LDMAE_REQUIRE(x0 && t && xt && ut && B >= 1 && C >= 1 && HW >= 4 && HW % 4 == 0, "bad argument");
+  LDMAE_REQUIRE((mean == nullptr) == (stdv == nullptr), "mean/std must be given together");
+  LDMAE_REQUIRE(!(flip != nullptr && moments_flip == nullptr), "a flip mask needs the flipped moments");
+  const size_t total4 = static_cast<size_t>(B) * C * HW / 4;
+  flow_prepare_kernel<<<cdiv(total4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      moments, moments_flip, flip, eps_post, mean, stdv, multiplier, x1_in, x0, t, x1_out, xt, ut, B, C, HW);
+  LDMAE_LAUNCH_CHECK();
+  return LDMAE_OK;
+}
+extern "C" int ldmae_flow_loss(const float* out, const float* ut, float* loss, float* dout, float loss_scale, int32_t B, int32_t n,
+                               void* stream) {
+  LDMAE_REQUIRE(out && ut && loss && B >= 1 && n >= 4 && n % 4 == 0, "bad argument");
+  flow_loss_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, ut, loss, dout,
+                                                                    2.0f * loss_scale / (static_cast<float>(n) * static_cast<float>(B)), n);
+  LDMAE_LAUNCH_CHECK();
+  return LDMAE_OK;
+}
 
 static int launch_update(float* xout, const float* xin, const float* v, const float* kprev, float* gout, int n_half,
                          int C, int HW, float cfg_scale, int use_guidance, float a, float bcoef, size_t total,

@@ -247,7 +247,7 @@ class LightningDiT(nn.Module):
             self._sig_items = None
             self._handle_sig = None
         else:
-            self._dirty_names = set(getattr(self, "_dirty_names", ())) | set(names)
+            self._dirty_names = set(getattr(self, "_dirty_names", None) or ()) | set(names)
 
     refresh_weights = mark_weights_dirty
 

@@ -53,6 +53,38 @@ class FlatLayout:
         return buf[off:off + n].view(shape)
 
 
+def adamw_state_dict(model, layout, exp_avg, exp_avg_sq, step, *, lr, betas, eps, weight_decay):
+    """The flat moment buffers in ``torch.optim.AdamW(model.parameters()).state_dict()`` form -- the 'opt' entry of the
+    reference's checkpoints (train_accum.py:121,278): parameter indices follow ``model.parameters()`` (frozen tensors such
+    as pos_embed keep their index and have no state)."""
+    index = {k: i for i, (k, _) in enumerate(model.named_parameters())}
+    state = {}
+    for k in layout.names:
+        state[index[k]] = {"step": torch.tensor(float(step)), "exp_avg": layout.view(exp_avg, k).detach().clone().cpu(),
+                           "exp_avg_sq": layout.view(exp_avg_sq, k).detach().clone().cpu()}
+    group = {"lr": lr, "betas": tuple(betas), "eps": eps, "weight_decay": weight_decay, "amsgrad": False, "maximize": False,
+             "foreach": None, "capturable": False, "differentiable": False, "fused": None, "decoupled_weight_decay": True,
+             "params": list(range(len(index)))}
+    return {"state": state if step > 0 else {}, "param_groups": [group]}
+
+
+def load_adamw_state_dict(model, layout, exp_avg, exp_avg_sq, opt_state):
+    """Inverse of ``adamw_state_dict`` (also accepts the state of a real ``torch.optim.AdamW`` over ``model.parameters()``);
+    returns the step count.  Parameters without state (fresh optimizer, frozen tensors) keep zero moments."""
+    names = [k for k, _ in model.named_parameters()]
+    steps = 0
+    with torch.no_grad():
+        exp_avg.zero_(); exp_avg_sq.zero_()
+        for idx, st in opt_state.get("state", {}).items():
+            k = names[int(idx)]
+            if k not in layout.slices:
+                continue
+            layout.view(exp_avg, k).copy_(st["exp_avg"].to(exp_avg.device))
+            layout.view(exp_avg_sq, k).copy_(st["exp_avg_sq"].to(exp_avg.device))
+            steps = max(steps, int(float(st["step"])))
+    return steps
+
+
 def reduce_gradients(grad, group=None):
     """Data-parallel gradient exchange (the role of DDP's bucketed all-reduce at train_accum.py:105,230): ONE sum all-reduce
     of the flat gradient buffer; returns the factor (1 / world size) the optimizer kernel folds into its gradient read."""
@@ -100,29 +132,98 @@ class FusedTrainer:
             sd[k] = self.ema[off:off + n].view(shape).clone()
         return sd
 
+    # -- checkpoint contract (train_accum.py:273-284,170-187) ------------------------------------------
+    def opt_state_dict(self):
+        return adamw_state_dict(self.model, self.layout, self.exp_avg, self.exp_avg_sq, self.step_count, lr=self.lr,
+                                betas=self.betas, eps=self.eps, weight_decay=self.weight_decay)
+
+    def load_opt_state_dict(self, opt_state):
+        self.step_count = load_adamw_state_dict(self.model, self.layout, self.exp_avg, self.exp_avg_sq, opt_state)
+        g = (opt_state.get("param_groups") or [{}])[0]
+        self.lr = float(g.get("lr", self.lr)); self.betas = tuple(g.get("betas", self.betas))
+        self.eps = float(g.get("eps", self.eps)); self.weight_decay = float(g.get("weight_decay", self.weight_decay))
+
+    def load_ema_state_dict(self, ema_state):
+        from .checkpoint import strip_module_prefix
+        ema_state = strip_module_prefix(ema_state)
+        with torch.no_grad():
+            for k in self.names:
+                self.layout.view(self.ema, k).copy_(ema_state[k].to(self.ema.device))
+
+    def save_checkpoint(self, checkpoint_dir, train_steps, config=None):
+        """``{model, ema, opt, config}`` as ``<dir>/<steps:07d>.pt`` -- loadable by the reference's resume / inference code."""
+        from .checkpoint import save_checkpoint
+        return save_checkpoint(checkpoint_dir, train_steps, self.model.state_dict(), self.ema_state_dict(), self.opt_state_dict(),
+                               config or {})
+
+    def resume(self, checkpoint_dir, load_opt=True, map_location="cpu"):
+        """Latest checkpoint of ``checkpoint_dir`` into the flat buffers (parameters are views of them, so
+        ``load_state_dict`` writes in place); returns the step count parsed from the file name (0: nothing to resume)."""
+        from .checkpoint import latest_checkpoint, strip_module_prefix
+        path, steps = latest_checkpoint(checkpoint_dir)
+        if path is None:
+            return 0
+        ckpt = torch.load(path, map_location=map_location, weights_only=False)
+        self.model.load_state_dict(strip_module_prefix(ckpt["model"]))
+        self.load_ema_state_dict(ckpt["ema"])
+        if load_opt and ckpt.get("opt"):
+            self.load_opt_state_dict(ckpt["opt"])
+        self.model.mark_weights_dirty(self.names)
+        return steps
+
+    # -- trainer input pipeline on the device --------------------------------------------------------
+    def prepare(self, x1=None, *, t, x0, moments=None, moments_flip=None, flip=None, eps_post=None, latent_mean=None,
+                latent_std=None, latent_multiplier=1.0, want_x1=False):
+        """ONE kernel for everything between the stored features and the model input (ldmae_flow_prepare): flip select +
+        posterior sample + per-channel normalise + multiplier (datasets/img_latent_dataset.py:76-94, when ``moments``
+        [B, 2C, S, S] are given instead of ready latents ``x1``), then xt = t*x1 + (1-t)*x0 and ut = x1 - x0
+        (transport.py:136-166, path.py:114-136).  Returns (xt, ut, x1 or None)."""
+        L = _lib.lib()
+        src = moments if moments is not None else x1
+        B, S = src.shape[0], src.shape[-1]
+        Cc = src.shape[1] // 2 if moments is not None else src.shape[1]
+        dev = src.device
+        f = lambda v: None if v is None else v.detach().to(dev).float().contiguous()
+        x1c, x0c, tc, mo, mf, ep = f(x1) if moments is None else None, f(x0), f(t), f(moments), f(moments_flip), f(eps_post)
+        fl = None if flip is None else flip.detach().to(dev).to(torch.uint8).contiguous()
+        mean = None if latent_mean is None else f(latent_mean).reshape(-1)
+        std = None if latent_std is None else f(latent_std).reshape(-1)
+        xt = torch.empty(B, Cc, S, S, device=dev)
+        ut = torch.empty_like(xt)
+        x1o = torch.empty_like(xt) if want_x1 else None
+        with torch.cuda.device(dev):
+            _lib.check(L.ldmae_flow_prepare(_lib.ptr(mo), _lib.ptr(mf), _lib.ptr(fl), _lib.ptr(ep), _lib.ptr(mean), _lib.ptr(std),
+                                            float(latent_multiplier), _lib.ptr(x1c), _lib.ptr(x0c), _lib.ptr(tc), _lib.ptr(x1o),
+                                            _lib.ptr(xt), _lib.ptr(ut), B, Cc, S * S, _lib.stream_ptr()), "ldmae_flow_prepare")
+        return xt, ut, x1o
+
     # -- one micro-batch: loss + gradients into self.grad ----------------------------------------
-    def loss_and_grad(self, x1, y, t=None, x0=None, accumulate=False, loss_scale=1.0):
+    def loss_and_grad(self, x1, y, t=None, x0=None, accumulate=False, loss_scale=1.0, **pipeline):
         """One micro-batch.  accumulate=True adds into the flat gradient buffer instead of overwriting it and loss_scale
-        divides the loss (train_accum.py:220-223: loss / gradient_accumulation_steps)."""
+        divides the loss (train_accum.py:220-223: loss / gradient_accumulation_steps).  ``pipeline``: keyword arguments of
+        ``prepare`` (moments=..., moments_flip=..., flip=..., eps_post=..., latent_mean/std/multiplier) to start from the
+        stored posterior moments instead of ready latents (then ``x1`` may be None)."""
         m, L = self.model, _lib.lib()
-        B = x1.shape[0]
+        src = pipeline.get("moments") if pipeline.get("moments") is not None else x1
+        B = src.shape[0]
         if t is None or x0 is None:
-            t, x0, x1 = self.transport.sample(x1)                      # reference draws: randn_like + logit-normal t
-        t = t.to(x1).float().contiguous()
-        tt = t.view(B, 1, 1, 1)
-        xt = (tt * x1 + (1 - tt) * x0).float().contiguous()
-        ut = x1 - x0
+            shape_like = src[:, : src.shape[1] // 2] if pipeline.get("moments") is not None else src
+            t, x0, _ = self.transport.sample(shape_like)               # reference draws: randn_like + logit-normal t
+        xt, ut, _ = self.prepare(x1, t=t, x0=x0, **pipeline)
+        t = t.to(xt.device).float().contiguous()
         if m.training and m.y_embedder.dropout_prob > 0:
             y = m.y_embedder.token_drop(y)
         y = y.long().contiguous()
-        h = m._ensure_handle(x1.device, B)
+        h = m._ensure_handle(xt.device, B)
         out = torch.empty_like(xt)
-        with torch.cuda.device(x1.device):
+        loss = torch.empty(B, device=xt.device)
+        dout = torch.empty_like(xt)
+        with torch.cuda.device(xt.device):
             st = _lib.stream_ptr()
             _lib.check(L.ldmae_dit_train_forward(h, _lib.ptr(xt), _lib.ptr(t), _lib.ptr(y), _lib.ptr(out), B, st), "train_forward")
-            diff = out - ut
-            loss = (diff * diff).mean(dim=(1, 2, 3))                   # mean_flat
-            dout = (diff * (2.0 * loss_scale / (diff[0].numel() * B))).contiguous()   # d (mean(loss) * loss_scale) / d out
+            # loss = mean_flat((out - ut)^2); dout = d (mean(loss) * loss_scale) / d out  -- one pass (ldmae_flow_loss)
+            _lib.check(L.ldmae_flow_loss(_lib.ptr(out), _lib.ptr(ut), _lib.ptr(loss), _lib.ptr(dout), float(loss_scale), B,
+                                         out[0].numel(), st), "flow_loss")
             _lib.check(L.ldmae_dit_backward(h, _lib.ptr(dout), B, st), "backward")
             base = self.grad.data_ptr()
             for k in self.names:
@@ -141,6 +242,21 @@ class FusedTrainer:
                 self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count,
                 self.ema_decay, grad_scale, _lib.stream_ptr()), "adamw_ema_step")
         self.model.mark_weights_dirty(self.names)                      # parameters changed behind torch's version counters
+
+    def step_from_moments(self, moments, moments_flip, y, *, latent_mean=None, latent_std=None, latent_multiplier=1.0,
+                          flip=None, eps_post=None, t=None, x0=None):
+        """One optimizer step straight from the stored features of extract_features.py (posterior moments of each image and
+        of its horizontal flip, [B, 2C, S, S]): the dataset's coin flip, posterior sample and normalisation
+        (img_latent_dataset.py:76-94) run inside the same kernel that builds xt / ut.  Random draws can be injected."""
+        B, dev = moments.shape[0], moments.device
+        if flip is None:
+            flip = torch.rand(B, device=dev) <= 0.5                     # "latents" if uniform > 0.5 else "latents_flip"
+        if eps_post is None:
+            eps_post = torch.randn(B, moments.shape[1] // 2, *moments.shape[2:], device=dev)
+        loss, _ = self.loss_and_grad(None, y, t, x0, moments=moments, moments_flip=moments_flip, flip=flip, eps_post=eps_post,
+                                     latent_mean=latent_mean, latent_std=latent_std, latent_multiplier=latent_multiplier)
+        self.optimizer_step()
+        return loss
 
     def step(self, x1, y, t=None, x0=None, micro_batches=1):
         """One optimizer step; micro_batches > 1 splits the batch and accumulates gradients (train_accum.py's

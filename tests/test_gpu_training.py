@@ -338,3 +338,72 @@ def test_out_of_range_class_label_is_flagged_not_read():
     vae = models_mae.mae_for_ldmae_f8d16_prev(ldmae_mode=True, no_cls=True, kl_loss_weight=True, smooth_output=True, img_size=64)
     with pytest.raises(ValueError, match="null-class row"):
         SamplingJob(m, vae.cuda().eval(), num_steps=4, cfg_scale=4.0)   # CFG needs the null row this model does not have
+
+
+def test_flow_prepare_and_loss_kernels_vs_reference_expressions():
+    """The fused trainer-input kernel (flip select, posterior sample, normalise, xt / ut) and the fused loss kernel against the
+    reference's expressions evaluated by PyTorch on the same device (img_latent_dataset.py:76-94, tokenizer/util/misc.py:74-96,
+    transport.py:136-166,195, path.py:114-136)."""
+    from ldmae_b200.tokenizer.models_mae import DiagonalGaussianDistribution
+    from ldmae_b200.training import FusedTrainer
+    spec, sd, m = _tiny(1, 12)
+    tr = FusedTrainer(m)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, C, S = 6, 16, 8
+    mom = torch.randn(B, 2 * C, S, S, device="cuda", generator=g)
+    mom[:, C:] = mom[:, C:] * 3.0 - 1.0
+    mom[0, C] = 45.0; mom[1, C + 1] = -80.0                                   # both clamps of the log-variance
+    momf = torch.randn(B, 2 * C, S, S, device="cuda", generator=g)
+    flip = torch.tensor([0, 1, 1, 0, 1, 0], device="cuda", dtype=torch.bool)
+    eps = torch.randn(B, C, S, S, device="cuda", generator=g)
+    x0 = torch.randn(B, C, S, S, device="cuda", generator=g)
+    t = torch.rand(B, device="cuda", generator=g)
+    mean = torch.linspace(-0.3, 0.4, C, device="cuda").view(1, C, 1, 1); std = torch.linspace(0.6, 1.7, C, device="cuda").view(1, C, 1, 1)
+    mult = 0.75
+    xt, ut, x1 = tr.prepare(None, t=t, x0=x0, moments=mom, moments_flip=momf, flip=flip, eps_post=eps, latent_mean=mean,
+                            latent_std=std, latent_multiplier=mult, want_x1=True)
+    src = torch.where(flip.view(B, 1, 1, 1), momf, mom)
+    post = DiagonalGaussianDistribution(src)
+    feat = ((post.mean + post.std * eps) - mean) / std * mult
+    tt = t.view(B, 1, 1, 1)
+    torch.testing.assert_close(x1, feat, rtol=2e-6, atol=1e-6)
+    assert torch.equal(xt, tt * x1 + (1 - tt) * x0)                           # same roundings as the eager expression
+    assert torch.equal(ut, x1 - x0)
+    # posterior mode + no normalisation; ready latents
+    xt2, ut2, x12 = tr.prepare(None, t=t, x0=x0, moments=mom, want_x1=True)
+    assert torch.equal(x12, mom[:, :C])
+    xt3, ut3, _ = tr.prepare(x12, t=t, x0=x0)
+    assert torch.equal(xt3, xt2) and torch.equal(ut3, ut2)
+    # loss + output gradient
+    from ldmae_b200 import _lib
+    out = torch.randn(B, C, S, S, device="cuda", generator=g)
+    loss = torch.empty(B, device="cuda"); dout = torch.empty_like(out)
+    _lib.check(_lib.lib().ldmae_flow_loss(_lib.ptr(out), _lib.ptr(ut), _lib.ptr(loss), _lib.ptr(dout), 0.5, B, C * S * S, _lib.stream_ptr()))
+    want = ((out - ut) ** 2).mean(dim=(1, 2, 3))
+    torch.testing.assert_close(loss, want, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(dout, (out - ut) * (2.0 * 0.5 / (C * S * S * B)), rtol=1e-6, atol=1e-9)
+
+
+def test_step_from_moments_equals_step_on_prepared_latents():
+    """FusedTrainer.step_from_moments (dataset features in) == FusedTrainer.step on the latents the dataset would have produced."""
+    import copy
+    from ldmae_b200.tokenizer.models_mae import DiagonalGaussianDistribution
+    from ldmae_b200.training import FusedTrainer
+    spec, sd, m = _tiny(1, 12)
+    m2 = copy.deepcopy(m)
+    g = torch.Generator(device="cuda").manual_seed(8)
+    B, C, S = 4, 16, 8
+    mom = torch.randn(B, 2 * C, S, S, device="cuda", generator=g); momf = torch.randn(B, 2 * C, S, S, device="cuda", generator=g)
+    flip = torch.tensor([1, 0, 0, 1], device="cuda", dtype=torch.bool)
+    eps = torch.randn(B, C, S, S, device="cuda", generator=g); x0 = torch.randn(B, C, S, S, device="cuda", generator=g)
+    t = torch.rand(B, device="cuda", generator=g); y = torch.randint(0, 10, (B,), device="cuda", generator=g)
+    mean = torch.full((1, C, 1, 1), 0.1, device="cuda"); std = torch.full((1, C, 1, 1), 1.3, device="cuda")
+    a, b = FusedTrainer(m), FusedTrainer(m2)
+    la = a.step_from_moments(mom, momf, y, latent_mean=mean, latent_std=std, latent_multiplier=1.0, flip=flip, eps_post=eps, t=t, x0=x0)
+    src = torch.where(flip.view(B, 1, 1, 1), momf, mom)
+    post = DiagonalGaussianDistribution(src)
+    x1 = ((post.mean + post.std * eps) - mean) / std * 1.0
+    lb = b.step(x1, y, t=t, x0=x0)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(la, lb, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(a.flat, b.flat, rtol=1e-5, atol=1e-7)

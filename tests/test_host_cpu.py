@@ -272,3 +272,107 @@ def test_polynomial_exp2_accuracy():
     y = bits.view(np.float32)
     rel = np.abs(y.astype(np.float64) / np.exp2(x.astype(np.float64)) - 1.0)
     assert rel.max() < 1e-3, rel.max()
+
+
+# ----------------------------------------------------------------------------- checkpoint contract (train_accum.py)
+def _tiny_cpu_dit(in_channels=16, **kw):
+    from ldmae_b200.models.lightningdit import LightningDiT
+    return LightningDiT(input_size=8, patch_size=1, in_channels=in_channels, hidden_size=128, depth=2, num_heads=2, num_classes=10,
+                        use_qknorm=True, use_swiglu=True, use_rope=True, use_rmsnorm=True, **kw)
+
+
+def test_checkpoint_layout_module_prefix_and_sampling_load(tmp_path):
+    """{model, ema, opt, config} as <steps:07d>.pt (train_accum.py:273-284); resume with / without DDP's 'module.' prefix
+    (:98,172-187,345); the sampler takes 'ema' (inference.py:100-103)."""
+    import copy
+    import torch
+    from ldmae_b200 import checkpoint as ck
+    torch.manual_seed(0)
+    m = _tiny_cpu_dit()
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.requires_grad:
+                p.add_(torch.randn_like(p) * 0.01)
+    ema = copy.deepcopy(m)
+    with torch.no_grad():
+        ema.final_layer.linear.bias.add_(1.0)
+    opt = torch.optim.AdamW(m.parameters(), lr=2e-4, weight_decay=0, betas=(0.9, 0.95))
+    d = str(tmp_path / "checkpoints")
+    p1 = ck.save_checkpoint(d, 50, m.state_dict(), ema.state_dict(), opt.state_dict(), {"train": {"exp_name": "t"}})
+    assert p1.endswith("/0000050.pt")
+    ck.save_checkpoint(d, 100, m.state_dict(), ema.state_dict(), opt.state_dict(), {"train": {"exp_name": "t"}})
+    saved = torch.load(p1, weights_only=False)
+    assert set(saved) == {"model", "ema", "opt", "config"}
+    path, steps = ck.latest_checkpoint(d)
+    assert steps == 100 and path.endswith("0000100.pt")
+    m2, ema2 = _tiny_cpu_dit(), _tiny_cpu_dit()
+    assert ck.resume(d, m2, ema2) == 100
+    for k, v in m.state_dict().items():
+        assert torch.equal(m2.state_dict()[k], v)
+    assert torch.equal(ema2.final_layer.linear.bias, ema.final_layer.linear.bias)
+    # a 'module.'-prefixed checkpoint (what a DDP-wrapped trainer holds) into a plain model, and a plain one into a wrapped model
+    os.remove(path)
+    wrapped = {("module." + k): v for k, v in m.state_dict().items()}
+    ck.save_checkpoint(d, 50, wrapped, ema.state_dict(), opt.state_dict(), {"train": {"exp_name": "t"}})
+    m3 = _tiny_cpu_dit()
+    assert ck.resume(d, m3, None) == 50
+    assert torch.equal(m3.blocks[1].mlp.w3.weight, m.blocks[1].mlp.w3.weight)
+
+    class Wrapped(torch.nn.Module):
+        def __init__(self, mod):
+            super().__init__()
+            self.module = mod
+    w = Wrapped(_tiny_cpu_dit())
+    ck.save_checkpoint(d, 60, m.state_dict(), ema.state_dict(), None, {})
+    os.remove(p1)
+    assert ck.resume(d, w, None) == 60
+    assert torch.equal(w.module.blocks[0].attn.qkv.weight, m.blocks[0].attn.qkv.weight)
+    # sampler: EMA weights win
+    m4 = ck.load_for_sampling(_tiny_cpu_dit(), ck.checkpoint_path(d, 60))
+    assert torch.equal(m4.final_layer.linear.bias, ema.final_layer.linear.bias)
+    assert ck.resume(str(tmp_path / "nothing_here"), m4, None) == 0
+
+
+def test_load_weights_with_shape_check_pads_patch_embedding(tmp_path):
+    """train_accum.py:308-334: matching tensors are copied, x_embedder.proj.weight of a model with MORE latent channels is
+    zero-padded around the first 16, other mismatches / unknown names are skipped."""
+    import torch
+    from ldmae_b200 import checkpoint as ck
+    torch.manual_seed(1)
+    src = _tiny_cpu_dit(in_channels=16)
+    dst = _tiny_cpu_dit(in_channels=32)
+    sd = {("module." + k): v.clone() for k, v in src.state_dict().items()}
+    sd["module.not_a_parameter"] = torch.zeros(3)
+    torch.save({"model": sd}, tmp_path / "init.pt")
+    before_final = dst.final_layer.linear.weight.clone()
+    ck.init_from_pretrained(dst, None, str(tmp_path / "init.pt"))
+    w = dst.x_embedder.proj.weight
+    assert w.shape == (128, 32, 1, 1)
+    assert torch.equal(w[:, :16], src.x_embedder.proj.weight) and float(w[:, 16:].abs().max()) == 0.0
+    assert torch.equal(dst.blocks[0].attn.qkv.weight, src.blocks[0].attn.qkv.weight)
+    assert torch.equal(dst.final_layer.linear.weight, before_final)              # [32, 128] vs [16, 128]: skipped
+    assert set(dst._ldmae_skipped_keys) == {"final_layer.linear.weight", "final_layer.linear.bias", "not_a_parameter"}
+
+
+def test_fused_optimizer_state_round_trips_through_torch_adamw():
+    """The flat moment buffers export to / import from torch.optim.AdamW(model.parameters()).state_dict() -- the 'opt' entry
+    of the reference's checkpoints (frozen pos_embed keeps its parameter index and has no state)."""
+    import torch
+    from ldmae_b200.training import FlatLayout, adamw_state_dict, load_adamw_state_dict
+    torch.manual_seed(2)
+    m = _tiny_cpu_dit()
+    lay = FlatLayout(m)
+    ea, es = torch.rand_like(lay.flat), torch.rand_like(lay.flat)
+    sd = adamw_state_dict(m, lay, ea, es, 7, lr=2e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.0)
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3, weight_decay=0, betas=(0.9, 0.999))
+    opt.load_state_dict(sd)                                                       # torch accepts the layout as its own
+    assert opt.param_groups[0]["lr"] == 2e-4 and tuple(opt.param_groups[0]["betas"]) == (0.9, 0.95)
+    named = dict(m.named_parameters())
+    for k in lay.names:
+        st = opt.state[named[k]]
+        assert torch.equal(st["exp_avg"], lay.view(ea, k)) and torch.equal(st["exp_avg_sq"], lay.view(es, k)) and float(st["step"]) == 7
+    assert named["pos_embed"] not in opt.state
+    ea2, es2 = torch.zeros_like(ea), torch.zeros_like(es)
+    assert load_adamw_state_dict(m, lay, ea2, es2, opt.state_dict()) == 7
+    for k in lay.names:
+        assert torch.equal(lay.view(ea2, k), lay.view(ea, k)) and torch.equal(lay.view(es2, k), lay.view(es, k))
