@@ -186,7 +186,7 @@ __global__ void adaln_prep_kernel(__nv_bfloat16* __restrict__ shift_bf16, float*
 //   anext[row,n]= bf16(x * gnext[b, n]);  ssq[row, 0] = sum_n x^2 (other slots 0)
 // src_mod: sample b reads latent (b % src_mod) -- forward_with_cfg feeds cat[half, half] (lightningdit.py:425-426).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 patch_embed_kernel(float* __restrict__ x, __nv_bfloat16* __restrict__ anext, float* __restrict__ ssq,
                    const float* __restrict__ lat /*[Bsrc, C, S, S]*/, const float* __restrict__ W /*[D, C*p*p]*/,
                    const float* __restrict__ bias, const float* __restrict__ pos /*[T, D]*/,
@@ -213,37 +213,54 @@ patch_embed_kernel(float* __restrict__ x, __nv_bfloat16* __restrict__ anext, flo
   s_red[threadIdx.x] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int n = threadIdx.x; n < D; n += blockDim.x) {          // D % 32 == 0: warp-uniform trip count
-    const float bn = bias[n];
-    const float gn = gnext ? gnext[static_cast<size_t>(b) * D + n] : 1.f;
+  // thread = 4 consecutive output columns (16-byte stores of x, 8-byte stores of the bf16 operand; a warp writes 512
+  // contiguous bytes per token), 8 tokens at a time (32 accumulators: the kernel streams 6 bytes per output element, so it
+  // needs occupancy, not registers); the squares are summed per thread over its columns and reduced with ONE warp
+  // reduction per token (fixed order => bit-reproducible statistics).  D % 128 == 0.
 #pragma unroll 1
-    for (int hf = 0; hf < 2; ++hf) {
-      float acc[16];
+  for (int tg = 0; tg < 4; ++tg) {
+    float sq[8];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) acc[i] = bn;
+    for (int i = 0; i < 8; ++i) sq[i] = 0.f;
+#pragma unroll 1
+    for (int n = threadIdx.x * 4; n < D; n += blockDim.x * 4) {
+      const float4 bn = *reinterpret_cast<const float4*>(bias + n);
+      float4 gn = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (gnext) gn = *reinterpret_cast<const float4*>(gnext + static_cast<size_t>(b) * D + n);
+      float acc[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { acc[i][0] = bn.x; acc[i][1] = bn.y; acc[i][2] = bn.z; acc[i][3] = bn.w; }
 #pragma unroll 1
       for (int k0 = 0; k0 < Kp; k0 += 4) {
-        const float4 w = *reinterpret_cast<const float4*>(W + static_cast<size_t>(n) * Kp + k0);
+        float4 w[4];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float4 a = *reinterpret_cast<const float4*>(s_in + (hf * 16 + i) * Kp + k0);
-          acc[i] = fmaf(w.x, a.x, fmaf(w.y, a.y, fmaf(w.z, a.z, fmaf(w.w, a.w, acc[i]))));
+        for (int j = 0; j < 4; ++j) w[j] = __ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(n + j) * Kp + k0));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 a = *reinterpret_cast<const float4*>(s_in + (tg * 8 + i) * Kp + k0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            acc[i][j] = fmaf(w[j].x, a.x, fmaf(w[j].y, a.y, fmaf(w[j].z, a.z, fmaf(w[j].w, a.w, acc[i][j]))));
         }
       }
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int tok = tok0 + hf * 16 + i;
-        float sq = 0.f;
+      for (int i = 0; i < 8; ++i) {
+        const int tok = tok0 + tg * 8 + i;
         if (tok < T) {
-          const float v = acc[i] + pos[static_cast<size_t>(tok) * D + n];
+          const float4 pe = __ldg(reinterpret_cast<const float4*>(pos + static_cast<size_t>(tok) * D + n));
+          const float4 v = make_float4(acc[i][0] + pe.x, acc[i][1] + pe.y, acc[i][2] + pe.z, acc[i][3] + pe.w);
           const size_t off = (static_cast<size_t>(b) * T + tok) * D + n;
-          x[off] = v;
-          if (anext) anext[off] = __float2bfloat16(v * gn);
-          sq = v * v;
+          *reinterpret_cast<float4*>(x + off) = v;
+          if (anext)
+            *reinterpret_cast<uint2*>(anext + off) = make_uint2(pack_bf16x2(v.x * gn.x, v.y * gn.y), pack_bf16x2(v.z * gn.z, v.w * gn.w));
+          sq[i] = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, sq[i]))));
         }
-        sq = warp_sum(sq);
-        if (lane == 0) s_red[warp * 32 + hf * 16 + i] += sq;
       }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float t = warp_sum(sq[i]);
+      if (lane == 0) s_red[warp * 32 + tg * 8 + i] = t;
     }
   }
   __syncthreads();

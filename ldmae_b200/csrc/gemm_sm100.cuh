@@ -47,6 +47,8 @@ struct EpiCtx {
   uint8_t* cta;      // CTA-wide epilogue area (Epi::kCtaBytes), filled by Epi::cta_init before the role split
   uint64_t* bars;    // this warp's mbarriers (Epi::kBars)
   int lane;
+  bool el;           // this lane is the warp's elected issuer of TMA / bulk-group instructions (same lane for the whole kernel:
+                     // bulk async-groups are per thread).  Every lane runs the control flow; only the instruction is predicated.
 };
 
 template <int BN, int CG, class Epi>
@@ -129,7 +131,7 @@ struct StoreRing {
   static __device__ __forceinline__ void cta_init(const P&, uint8_t*, int, int) {}
   struct State { int seq; };
   static __device__ __forceinline__ uint8_t* acquire(const EpiCtx& c, State& st) {
-    if (c.lane == 0) tma_store_wait_read<1>();         // the store issued two chunks ago no longer reads its tile
+    if (c.el) tma_store_wait_read<1>();                // the store issued two chunks ago no longer reads its tile
     __syncwarp();
     return c.smem + (st.seq & 1) * 4096;
   }
@@ -137,7 +139,7 @@ struct StoreRing {
                                                  int row) {
     fence_proxy_async_smem();
     __syncwarp();
-    if (c.lane == 0) {
+    if (c.el) {
       tma_store_2d(map, tile, col, row);
       tma_store_commit();
     }
@@ -217,7 +219,7 @@ struct EpiStore : StoreRing {
     }
   }
   static __device__ __forceinline__ void end(const EpiCtx& c, State&) {
-    if (c.lane == 0) tma_store_wait_read<0>();
+    if (c.el) tma_store_wait_read<0>();
   }
 };
 
@@ -234,32 +236,43 @@ struct EpiStore : StoreRing {
 // kTrain: the training forward additionally keeps, for the backward, the branch output before the gate
 // (m = acc + bias, bf16 -> dgate = sum_t dx * m) and writes the updated stream to a second buffer (xmap_out), so that
 // the stream at every norm input stays available (RMSNorm Jacobian).
-template <int NX /*x tiles per warp*/, int PF /*prefetch distance in chunks*/, bool kTrain = false>
+template <int NXP /*pair buffers (2 x 4 KB x tiles each) per warp*/, int PFP /*prefetch distance in pairs*/, bool kTrain = false>
 struct EpiResidualT {
+  // The accumulator tile is walked in PAIRS of 32-column chunks (64 columns = 256 contiguous bytes of the fp32 stream per
+  // row, one 128-byte row of the bf16 operand): one barrier wait, one proxy fence and one bulk-store group per pair, two
+  // independent instruction streams for the scheduler to interleave.  Measured on the one-chunk-per-iteration version
+  // (clock64 stamps, profiles/r02_resid_trace.txt): ~2000 clk per chunk with NO wait for memory in it -- 420 clk in the
+  // lane-0 load issue (integer divisions of the tile coordinates + the ELECT / R2UR.BROADCAST / BRA.U.ANY loop nvcc wraps
+  // around a TMA instruction behind a single-lane branch), 240 clk in the store issue (same), 850 clk of dependent
+  // LDS -> FFMA -> STS chains with a lone warp per SM sub-partition.  Here every lane runs the control flow with
+  // incrementally updated (division-free) coordinates and only the TMA / mbarrier instructions are predicated on the
+  // elected lane.
   static constexpr int kWarps = 4;
   static constexpr int kCtaBytes = 0;
-  static constexpr int kNX = NX;
-  static constexpr int kPF = PF;
-  static_assert(PF + 2 <= NX, "a tile is reloaded PF chunks ahead while the stores of the last two chunks may still read theirs");
-  static constexpr int kXBytes = 4096, kABytesTile = 2048;
-  static constexpr int kMOff = kNX * kXBytes + 2 * kABytesTile;        // kTrain: two bf16 tiles for m
-  static constexpr int kVecOff = kMOff + (kTrain ? 2 * kABytesTile : 0);   // [3][256] floats: bias, gate, gnext of the tile
-  static constexpr int kWarpBytes = kVecOff + 4096;
-  static constexpr int kBars = kNX;
+  static constexpr int kNXP = NXP;
+  static constexpr int kPFP = PFP;
+  static_assert(PFP >= 1 && PFP + 1 <= NXP, "the buffer of pair p+PFP held pair p+PFP-NXP, whose store must have been waited for (pair <= p-1)");
+  static constexpr int kXBytes = 4096, kPairBytes = 2 * kXBytes, kATile = 4096;
+  static constexpr int kAOff = NXP * kPairBytes;                         // one bf16 tile [32 x 64] (128-byte rows) for anext
+  static constexpr int kMOff = kAOff + kATile;                           // kTrain: two bf16 tiles for m (double-buffered)
+  static constexpr int kVecOff = kMOff + (kTrain ? 2 * kATile : 0);      // [3][256] floats: bias, gate, gnext of the tile
+  static constexpr int kWarpBytes = kVecOff + 3072;
+  static constexpr int kBars = NXP;
   struct Params {
     CUtensorMap xmap;      // x [M, N] fp32: box {32, 32}, SWIZZLE_128B (loads)
     CUtensorMap xmap_out;  // where the updated x is stored (= xmap for the in-place inference path)
-    CUtensorMap amap;      // anext [M, N] bf16: box {32, 32}, SWIZZLE_64B (stores); unused when !has_anext
-    CUtensorMap mmap;      // kTrain: m [M, N] bf16, box {32, 32}, SWIZZLE_64B
+    CUtensorMap amap;      // anext [M, N] bf16: box {64, 32}, SWIZZLE_128B (stores); unused when !has_anext
+    CUtensorMap mmap;      // kTrain: m [M, N] bf16, box {64, 32}, SWIZZLE_128B
     const float* bias;     // [N]
     const float* gate;     // [B, gate_ld] or nullptr (=> 1)
     const float* gnext;    // [B, gnext_ld] (has_anext)
     float* ssq;            // [M, ss_slots] per-row partial sums of squares, or nullptr.  Slot = column/128 of the
                            // producing tile: no atomics, so the statistics are bit-reproducible.
     int gate_ld, gnext_ld, rows_per_sample, ss_slots, has_anext;
-    long long* trace;      // debug builds (-DLDMAE_GEMM_TRACE): [256 chunks][8] clock64 stamps of CTA 0, epilogue warp 0
+    long long* trace;      // debug builds (-DLDMAE_GEMM_TRACE): [256 pairs][8] clock64 stamps of CTA 0, epilogue warp 0
   };
-  struct State { int seq, pf_seq, pf_tile, pf_chunk; };
+  // every lane keeps the same copy of this state (warp-uniform control flow)
+  struct State { int seq, pf_seq, pf_tile, pf_pair, pf_mi, pf_ni, st_div, st_mod; };
 #ifdef LDMAE_GEMM_TRACE
 #define RES_STAMP(k) do { if (p.trace && blockIdx.x == 0 && s.wq == 0 && lane == 0 && st.seq < 256) p.trace[st.seq * 8 + (k)] = clock64(); } while (0)
 #else
@@ -273,25 +286,39 @@ struct EpiResidualT {
     if (p.has_anext) tma_prefetch_desc(&p.amap);
     if constexpr (kTrain) tma_prefetch_desc(&p.mmap);
   }
-  // issue the x loads of every chunk with sequence number <= upto (lane 0 only; buffers are known to be free)
+  // issue the x loads of every pair with sequence number <= upto (all lanes walk the schedule, the elected lane issues;
+  // the target buffers are known to be free)
   template <int BN>
   static __device__ __forceinline__ void pump(const Params& p, const GemmShape& g, const TileSched& s, const EpiCtx& c, State& st,
                                               int upto) {
     while (st.pf_seq <= upto && st.pf_tile < s.total) {
-      int row0, n0;
-      s.template coords<BN>(st.pf_tile, row0, n0);
-      const int nch = min(BN / 32, (g.N - n0 + 31) / 32);
-      const int b = st.pf_seq % kNX;
-      mbar_expect_tx(&c.bars[b], kXBytes);
-      tma_load_2d(&p.xmap, &c.bars[b], c.smem + b * kXBytes, n0 + st.pf_chunk * 32, row0);
+      const int row0 = (st.pf_mi * s.cg + s.cta_rank) * kBM + s.wq * 32;
+      const int n0 = st.pf_ni * BN;
+      const int npairs = min(BN / 64, (g.N - n0 + 63) / 64);
+      const int b = st.pf_seq % kNXP;
+      uint8_t* dst = c.smem + b * kPairBytes;
+      const int col = n0 + st.pf_pair * 64;
+      if (c.el) {
+        mbar_expect_tx(&c.bars[b], kPairBytes);
+        tma_load_2d(&p.xmap, &c.bars[b], dst, col, row0);
+        tma_load_2d(&p.xmap, &c.bars[b], dst + kXBytes, col + 32, row0);
+      }
       ++st.pf_seq;
-      if (++st.pf_chunk == nch) { st.pf_chunk = 0; st.pf_tile += s.stride; }
+      if (++st.pf_pair == npairs) {
+        st.pf_pair = 0;
+        st.pf_tile += s.stride;
+        st.pf_mi += st.st_div;
+        st.pf_ni += st.st_mod;
+        if (st.pf_ni >= s.n_tiles) { st.pf_ni -= s.n_tiles; ++st.pf_mi; }
+      }
     }
   }
   template <int BN>
   static __device__ __forceinline__ void begin(const Params& p, const GemmShape& g, const TileSched& s, const EpiCtx& c, State& st) {
-    st.seq = 0; st.pf_seq = 0; st.pf_tile = s.first; st.pf_chunk = 0;
-    if (c.lane == 0) pump<BN>(p, g, s, c, st, kPF - 1);
+    st.seq = 0; st.pf_seq = 0; st.pf_tile = s.first; st.pf_pair = 0;
+    st.pf_mi = s.first / s.n_tiles; st.pf_ni = s.first % s.n_tiles;
+    st.st_div = s.stride / s.n_tiles; st.st_mod = s.stride % s.n_tiles;
+    pump<BN>(p, g, s, c, st, kPFP - 1);
   }
   // one sample per warp (always true when rows_per_sample is a multiple of 32): the tile's column vectors are staged in
   // shared memory (kStaged); otherwise every thread reads its own sample's vectors from global memory.  Two
@@ -305,7 +332,7 @@ struct EpiResidualT {
   template <int BN, int GC, bool kStaged>
   static __device__ __forceinline__ void run_t(const Params& p, const GemmShape& g, const TileSched& s, const EpiCtx& c, State& st,
                                                uint32_t acc, int row0, int n0, int /*cbase*/) {
-    static_assert(GC == BN && BN <= 256, "the residual epilogue walks the whole tile width");
+    static_assert(GC == BN && BN <= 256 && BN % 64 == 0, "the residual epilogue walks the whole tile width in 64-column pairs");
     const int lane = c.lane;
     const int my_row = row0 + lane;
     const int my_b = (my_row < g.M ? my_row : g.M - 1) / p.rows_per_sample;
@@ -321,29 +348,22 @@ struct EpiResidualT {
       __syncwarp();
     }
     float ss = 0.f;
+    uint8_t* at = c.smem + kAOff;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = 0; c0 < BN; c0 += 64) {
       if (n0 + c0 >= g.N) break;
       RES_STAMP(0);
-      if (lane == 0) {
-        tma_store_wait_read<1>();                      // stores issued two chunks ago no longer read their tiles
-        RES_STAMP(1);
-        pump<BN>(p, g, s, c, st, st.seq + kPF);
-      }
-      __syncwarp();
-      RES_STAMP(2);
-      uint8_t* xt = c.smem + (st.seq % kNX) * kXBytes;
-      uint8_t* at = c.smem + kNX * kXBytes + (st.seq & 1) * kABytesTile;
-      uint8_t* mt = c.smem + kMOff + (st.seq & 1) * kABytesTile;
-      mbar_wait(&c.bars[st.seq % kNX], (st.seq / kNX) & 1, 500);
-      __syncwarp();
-      RES_STAMP(3);
-      float v[32];
+      uint8_t* xt = c.smem + (st.seq % kNXP) * kPairBytes;
+      uint8_t* mt = c.smem + kMOff + (st.seq & 1) * kATile;
+      mbar_wait(&c.bars[st.seq % kNXP], (st.seq / kNXP) & 1, 500);
+      RES_STAMP(1);
+      float v[64];
       tmem_ld32(acc + c0, v);
+      tmem_ld32(acc + c0 + 32, v + 32);
       tmem_ld_wait();
-      RES_STAMP(4);
+      RES_STAMP(2);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
+      for (int q = 0; q < 16; ++q) {
         const int col = n0 + c0 + 4 * q;
         float4 bi, gt = make_float4(1.f, 1.f, 1.f, 1.f);
         if constexpr (kStaged) {
@@ -353,13 +373,13 @@ struct EpiResidualT {
           bi = ldvec4(p.bias, col, g.N);
           if (gate != nullptr) gt = ldvec4(gate, col, g.N);
         }
-        uint8_t* xp = sw128_chunk(xt, lane, q);
+        uint8_t* xp = sw128_chunk(xt + (q >> 3) * kXBytes, lane, q & 7);
         const uint4 xr = ld_tile16(xp);
         float4 xn;
         const float m0 = v[4 * q] + bi.x, m1 = v[4 * q + 1] + bi.y, m2 = v[4 * q + 2] + bi.z, m3 = v[4 * q + 3] + bi.w;
         if constexpr (kTrain) {
-          // 4 bf16 = 8 bytes: half of 16-byte chunk q/2 of the SWIZZLE_64B tile
-          *reinterpret_cast<uint2*>(sw64_chunk(mt, lane, q >> 1) + (q & 1) * 8) = make_uint2(pack_bf16x2(m0, m1), pack_bf16x2(m2, m3));
+          // 4 bf16 = 8 bytes: half of 16-byte chunk q/2 of the 128-byte row
+          *reinterpret_cast<uint2*>(sw128_chunk(mt, lane, q >> 1) + (q & 1) * 8) = make_uint2(pack_bf16x2(m0, m1), pack_bf16x2(m2, m3));
         }
         xn.x = __uint_as_float(xr.x) + m0 * gt.x;
         xn.y = __uint_as_float(xr.y) + m1 * gt.y;
@@ -370,14 +390,21 @@ struct EpiResidualT {
         ss = fmaf(xn.x, xn.x, ss); ss = fmaf(xn.y, xn.y, ss); ss = fmaf(xn.z, xn.z, ss); ss = fmaf(xn.w, xn.w, ss);
         v[4 * q] = xn.x; v[4 * q + 1] = xn.y; v[4 * q + 2] = xn.z; v[4 * q + 3] = xn.w;
       }
+      RES_STAMP(3);
+      // every bulk store issued so far (pair seq-1 and older) has read its tiles: the anext tile and the pair buffer the
+      // next load goes into are free
+      if (c.el) tma_store_wait_read<0>();
+      __syncwarp();
+      pump<BN>(p, g, s, c, st, st.seq + kPFP);
+      RES_STAMP(4);
       if (p.has_anext) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 8; ++q) {
           const int col = n0 + c0 + 8 * q;
           float4 g0, g1;
           if constexpr (kStaged) { g0 = lds_f4(vgnext + c0 + 8 * q); g1 = lds_f4(vgnext + c0 + 8 * q + 4); }
           else { g0 = ldvec4(gnext, col, g.N); g1 = ldvec4(gnext, col + 4, g.N); }
-          st_tile16(sw64_chunk(at, lane, q),
+          st_tile16(sw128_chunk(at, lane, q),
                  make_uint4(pack_bf16x2(v[8 * q] * g0.x, v[8 * q + 1] * g0.y), pack_bf16x2(v[8 * q + 2] * g0.z, v[8 * q + 3] * g0.w),
                             pack_bf16x2(v[8 * q + 4] * g1.x, v[8 * q + 5] * g1.y), pack_bf16x2(v[8 * q + 6] * g1.z, v[8 * q + 7] * g1.w)));
         }
@@ -385,8 +412,9 @@ struct EpiResidualT {
       RES_STAMP(5);
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {
+      if (c.el) {
         tma_store_2d(&p.xmap_out, xt, n0 + c0, row0);
+        if (n0 + c0 + 32 < g.N) tma_store_2d(&p.xmap_out, xt + kXBytes, n0 + c0 + 32, row0);
         if (p.has_anext) tma_store_2d(&p.amap, at, n0 + c0, row0);
         if constexpr (kTrain) tma_store_2d(&p.mmap, mt, n0 + c0, row0);
         tma_store_commit();
@@ -401,13 +429,14 @@ struct EpiResidualT {
     }
   }
   static __device__ __forceinline__ void end(const EpiCtx& c, State&) {
-    if (c.lane == 0) tma_store_wait_read<0>();
+    if (c.el) tma_store_wait_read<0>();
+    __syncwarp();
   }
 };
 
-using EpiResidual = EpiResidualT<4, 2>;        // w3 (K = 4D/1.5: tensor-bound, keeps a 4-stage operand ring)
-using EpiResidualDeep = EpiResidualT<6, 4>;    // proj (K = D: HBM-bound, deeper residual prefetch, 3-stage operand ring)
-using EpiResidualTrain = EpiResidualT<4, 2, true>;   // training forward (keeps m and the per-norm stream copies)
+using EpiResidual = EpiResidualT<2, 1>;        // w3 (K = 4D/1.5: tensor-bound, keeps a 4-stage operand ring)
+using EpiResidualDeep = EpiResidualT<3, 2>;    // proj (K = D: HBM-bound, deeper residual prefetch, 3-stage operand ring)
+using EpiResidualTrain = EpiResidualT<2, 1, true>;   // training forward (keeps m and the per-norm stream copies)
 
 // QKV projection of LightningDiT attention (lightningdit.py:68-74) on the pre-scaled operand:
 //   v = acc * rsqrt(ssq[row]/D + eps) + cvec[b,col]        (= Linear(modulate(RMSNorm(x))) incl. bias)
@@ -425,7 +454,8 @@ struct EpiQKV : StoreRing {
     CUtensorMap rawmap;     // has_raw (training forward): q, k before the head norm [M, 2D] bf16, same box
     int has_raw;
     const float* ssq;       // [M, ss_slots] partial sums of squares of the residual-stream row (nullptr: no row scale)
-    const float* cvec;      // [B, 3D]  shift_b . W^T + bias
+    const float* cvec;      // [B, 3D] (row pitch cvec_ld)  shift_b . W^T + bias
+    int cvec_ld;
     const float* qw;        // [64] q_norm.weight or nullptr (no qk-norm)
     const float* kw;        // [64]
     const float* rope;      // [2, grid, 32] or nullptr
@@ -467,7 +497,7 @@ struct EpiQKV : StoreRing {
     const int my_b = my_row / p.rows_per_sample;
     const int tok = my_row % p.rows_per_sample;
     const float rinv = row_rinv(p.ssq, my_row, p.ss_slots, p.inv_D, p.eps_row);
-    const float* cv = p.cvec + static_cast<size_t>(my_b) * g.N;
+    const float* cv = p.cvec + static_cast<size_t>(my_b) * p.cvec_ld;
     const bool staged = kFast || warp_rows_one_sample(row0, g.M, p.rows_per_sample);
     float* vcv = reinterpret_cast<float*>(c.smem + kVecOff);       // [GC] cvec of this tile / group
     float* vnw = vcv + 256;                                        // [64 q_norm | 64 k_norm]
@@ -556,7 +586,7 @@ struct EpiQKV : StoreRing {
     }
   }
   static __device__ __forceinline__ void end(const EpiCtx& c, State&) {
-    if (c.lane == 0) tma_store_wait_read<0>();
+    if (c.el) tma_store_wait_read<0>();
   }
 };
 
@@ -570,7 +600,8 @@ struct EpiQKVWide : StoreRing {
     CUtensorMap rawmap;     // has_raw (training forward): q, k before the head norm [M, 2 * heads * 128] bf16, same box
     int has_raw;
     const float* ssq;       // [M, ss_slots]
-    const float* cvec;      // [B, N]
+    const float* cvec;      // [B, N] (row pitch cvec_ld)
+    int cvec_ld;
     const float* qw;        // [128] q_norm.weight zero-padded, or nullptr
     const float* kw;        // [128]
     const float* rope_cos;  // [T, hd] or nullptr
@@ -595,7 +626,7 @@ struct EpiQKVWide : StoreRing {
     const int my_b = my_row / p.rows_per_sample;
     const int tok = my_row % p.rows_per_sample;
     const float rinv = row_rinv(p.ssq, my_row, p.ss_slots, p.inv_D, p.eps_row);
-    const float* cv = p.cvec + static_cast<size_t>(my_b) * g.N;
+    const float* cv = p.cvec + static_cast<size_t>(my_b) * p.cvec_ld;
     const float inv_hd = 1.f / static_cast<float>(p.hd);
 #pragma unroll 1
     for (int c0 = cbase; c0 < cbase + GC; c0 += 128) {
@@ -675,7 +706,7 @@ struct EpiQKVWide : StoreRing {
     }
   }
   static __device__ __forceinline__ void end(const EpiCtx& c, State&) {
-    if (c.lane == 0) tma_store_wait_read<0>();
+    if (c.el) tma_store_wait_read<0>();
   }
 };
 
@@ -688,7 +719,8 @@ struct EpiSwiGLU : StoreRing {
     CUtensorMap premap;   // has_pre (training forward): pre-activation [M, 2H] bf16 (interleaved columns), same box
     int has_pre;
     const float* ssq;     // [M, ss_slots]
-    const float* cvec;    // [B, 2H] in the same interleaved column order
+    const float* cvec;    // [B, 2H] in the same interleaved column order (row pitch cvec_ld)
+    int cvec_ld;
     int rows_per_sample, ss_slots;
     float inv_D, eps_row;
   };
@@ -714,7 +746,7 @@ struct EpiSwiGLU : StoreRing {
     const int my_row = min(row0 + lane, g.M - 1);
     const int my_b = my_row / p.rows_per_sample;
     const float rinv = row_rinv(p.ssq, my_row, p.ss_slots, p.inv_D, p.eps_row);
-    const float* cv = p.cvec + static_cast<size_t>(my_b) * g.N;
+    const float* cv = p.cvec + static_cast<size_t>(my_b) * p.cvec_ld;
     float* vcv = reinterpret_cast<float*>(c.smem + kVecOff);
     if constexpr (kStaged) {
       stage_vec(vcv, cv, n0 + cbase, GC, g.N, lane);
@@ -761,7 +793,7 @@ struct EpiSwiGLU : StoreRing {
     }
   }
   static __device__ __forceinline__ void end(const EpiCtx& c, State&) {
-    if (c.lane == 0) tma_store_wait_read<0>();
+    if (c.el) tma_store_wait_read<0>();
   }
 };
 
@@ -883,7 +915,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // whole-warp control flow, elected issue (a single-lane branch around the loop makes nvcc wrap every TMA instruction in
+    // an ELECT / R2UR.BROADCAST / BRA.U.ANY convergence loop)
+    {
+      const bool issuer = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
@@ -895,16 +930,19 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
           void* da = smem_a + stage * Cfg::kABytes;
           void* db = smem_b + stage * Cfg::kBBytesPadded;
-          if constexpr (CG == 1) {
-            mbar_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::kBBytes);
-            tma_load_2d(&tmap_a, &full_bar[stage], da, kb * kBK, row_a);
-            tma_load_2d(&tmap_w, &full_bar[stage], db, kb * kBK, row_w);
-          } else {
-            if (leader) mbar_expect_tx(&full_bar[stage], 2 * (Cfg::kABytes + Cfg::kBBytes));
-            else mbar_arrive_cluster(&full_bar[stage], 0);
-            tma_load_2d_pair(&tmap_a, &full_bar[stage], da, kb * kBK, row_a);
-            tma_load_2d_pair(&tmap_w, &full_bar[stage], db, kb * kBK, row_w);
+          if (issuer) {
+            if constexpr (CG == 1) {
+              mbar_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::kBBytes);
+              tma_load_2d(&tmap_a, &full_bar[stage], da, kb * kBK, row_a);
+              tma_load_2d(&tmap_w, &full_bar[stage], db, kb * kBK, row_w);
+            } else {
+              if (leader) mbar_expect_tx(&full_bar[stage], 2 * (Cfg::kABytes + Cfg::kBBytes));
+              else mbar_arrive_cluster(&full_bar[stage], 0);
+              tma_load_2d_pair(&tmap_a, &full_bar[stage], da, kb * kBK, row_a);
+              tma_load_2d_pair(&tmap_w, &full_bar[stage], db, kb * kBK, row_w);
+            }
           }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -957,7 +995,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int wq = warp & 3;                                         // TMEM lane quarter of this warp
     const int grp = (warp - 4) / 4;                                  // column group of this warp
     const int ew = warp - 4;
-    const EpiCtx ctx{smem_epi + ew * Epi::kWarpBytes, smem_cta, epi_bar + ew * Epi::kBars, lane};
+    const EpiCtx ctx{smem_epi + ew * Epi::kWarpBytes, smem_cta, epi_bar + ew * Epi::kBars, lane, elect_one()};
     const TileSched sched{cluster_id, num_clusters, total_tiles, n_tiles, CG, static_cast<int>(cta_rank), wq};
     typename Epi::State est;
     Epi::template begin<BN>(ep, g, sched, ctx, est);
@@ -974,7 +1012,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       Epi::template run<BN, Cfg::kGroupCols>(ep, g, sched, ctx, est, acc, row0, n0, grp * Cfg::kGroupCols);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
+      if (ctx.el) {
         if constexpr (CG == 1) mbar_arrive(&tempty_bar[as]);
         else mbar_arrive_cluster(&tempty_bar[as], 0);
       }

@@ -47,7 +47,7 @@ struct EpiAccum : StoreRing {
                              __float_as_uint(v[4 * q + 2] * p.alpha), __float_as_uint(v[4 * q + 3] * p.alpha)));
       fence_proxy_async_smem();
       __syncwarp();
-      if (c.lane == 0) {
+      if (c.el) {
         tma_reduce_add_2d(&p.cmap, tile, n0 + c0, row0);
         tma_store_commit();
       }
@@ -135,7 +135,10 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_const
   const int num_clusters = gridDim.x / CG;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // whole-warp control flow, elected issue (see gemm_sm100.cuh: a single-lane branch makes nvcc wrap every TMA / MMA
+    // instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY convergence loop)
+    {
+      const bool issuer = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       for (int u = cluster_id; u < total_units; u += num_clusters) {
@@ -147,6 +150,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_const
           mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
           uint8_t* da = smem_a + stage * Cfg::kABytes;
           uint8_t* db = smem_b + stage * Cfg::kBBytes;
+          if (issuer) {
           if constexpr (CG == 1) {
             mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
 #pragma unroll
@@ -161,6 +165,8 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_const
 #pragma unroll
             for (int b = 0; b < Cfg::kLoadBN / 64; ++b) tma_load_2d_pair(&tmap_q, &full_bar[stage], db + b * 8192, col_q + b * 64, kb * kBK);
           }
+          }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -170,7 +176,8 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (leader && lane == 0) {
+    if (leader) {
+      const bool issuer = elect_one();
       constexpr uint32_t idesc = umma_idesc_bf16(kBM * CG, BN, true, true);
       int stage = 0;
       uint32_t phase = 0;
@@ -188,15 +195,18 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_const
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::kABytes);
           const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBBytes);
+          if (issuer) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            // 16 m-rows per instruction = two 8-row core groups (SBO 1024 B apart); 64-column atoms 8 KB apart (LBO)
-            const uint64_t ad = umma_smem_desc_sw128(a_addr + k * 2048, 1024, 8192);
-            const uint64_t bd = umma_smem_desc_sw128(b_addr + k * 2048, 1024, 8192);
-            umma_bf16<CG>(tmem_d, ad, bd, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+            for (int k = 0; k < kBK / 16; ++k) {
+              // 16 m-rows per instruction = two 8-row core groups (SBO 1024 B apart); 64-column atoms 8 KB apart (LBO)
+              const uint64_t ad = umma_smem_desc_sw128(a_addr + k * 2048, 1024, 8192);
+              const uint64_t bd = umma_smem_desc_sw128(b_addr + k * 2048, 1024, 8192);
+              umma_bf16<CG>(tmem_d, ad, bd, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+            }
+            umma_commit<CG>(&empty_bar[stage]);
+            if (kb == kb1 - 1) umma_commit<CG>(&tfull_bar[as]);
           }
-          umma_commit<CG>(&empty_bar[stage]);
-          if (kb == kb1 - 1) umma_commit<CG>(&tfull_bar[as]);
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -205,7 +215,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_const
     const int wq = warp & 3;
     const int grp = (warp - 4) / 4;
     const int ew = warp - 4;
-    const EpiCtx ctx{smem_epi + ew * EpiAccum::kWarpBytes, nullptr, nullptr, lane};
+    const EpiCtx ctx{smem_epi + ew * EpiAccum::kWarpBytes, nullptr, nullptr, lane, elect_one()};
     EpiAccum::State est;
     est.seq = 0;
     int it = 0;
@@ -222,12 +232,12 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_const
       if (row0 < g.N1) EpiAccum::run(ep, g.N2, ctx, est, acc, row0, n0, grp * Cfg::kGroupCols, Cfg::kGroupCols);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
+      if (ctx.el) {
         if constexpr (CG == 1) mbar_arrive(&tempty_bar[as]);
         else mbar_arrive_cluster(&tempty_bar[as], 0);
       }
     }
-    if (lane == 0) tma_store_wait_read<0>();
+    if (ctx.el) tma_store_wait_read<0>();
   }
 
   __syncwarp();

@@ -155,18 +155,19 @@ static int gemm_residual(const void* a, int lda, const void* w, int ldw, GemmSha
                          const float* gate, int gate_ld, const float* gnext, int gnext_ld, __nv_bfloat16* anext, float* ssq,
                          int ss_slots, int rows_per_sample, cudaStream_t st) {
   typename EpiResidual::Params ep;
+  LDMAE_REQUIRE(g.N % 64 == 0, "residual GEMM: N = %d must be a multiple of 64 (the epilogue walks the tile in 64-column pairs)", g.N);
   LDMAE_TRY(make_tmap_out_f32(&ep.xmap, x, g.M, g.N, ldx));
   ep.xmap_out = ep.xmap;
   ep.mmap = ep.xmap;
   ep.has_anext = anext != nullptr;
-  if (anext) LDMAE_TRY(make_tmap_2d(&ep.amap, anext, 2, g.M, g.N, ldx, 32, 32, 64));
+  if (anext) LDMAE_TRY(make_tmap_out_bf16(&ep.amap, anext, g.M, g.N, ldx));
   else ep.amap = ep.xmap;
   ep.bias = bias; ep.gate = gate; ep.gnext = gnext; ep.ssq = ssq;
   ep.gate_ld = gate_ld; ep.gnext_ld = gnext_ld; ep.rows_per_sample = rows_per_sample; ep.ss_slots = ss_slots;
   ep.trace = g_gemm_trace;
   static int deep = -1;
   if (deep < 0) { const char* e = getenv("LDMAE_RESID_DEEP"); deep = e ? atoi(e) : 1; }
-  if (deep && g.K <= 1024 && g.M > 128) {
+  if (((deep == 1 && g.K <= 1024) || deep == 2) && g.M > 128) {
     // short K: the epilogue's residual traffic, not the tensor core, bounds the kernel
     EpiResidualDeep::Params ed;
     memcpy(&ed, &ep, sizeof ed);
@@ -181,11 +182,12 @@ static int gemm_residual_train(const void* a, int lda, const void* w, int ldw, G
                                __nv_bfloat16* anext, float* ssq, int ss_slots, __nv_bfloat16* m_out, int rows_per_sample,
                                cudaStream_t st) {
   typename EpiResidualTrain::Params ep;
+  LDMAE_REQUIRE(g.N % 64 == 0, "residual GEMM: N = %d must be a multiple of 64 (the epilogue walks the tile in 64-column pairs)", g.N);
   LDMAE_TRY(make_tmap_out_f32(&ep.xmap, x_in, g.M, g.N, ldx));
   LDMAE_TRY(make_tmap_out_f32(&ep.xmap_out, x_out, g.M, g.N, ldx));
-  LDMAE_TRY(make_tmap_2d(&ep.mmap, m_out, 2, g.M, g.N, ldx, 32, 32, 64));
+  LDMAE_TRY(make_tmap_out_bf16(&ep.mmap, m_out, g.M, g.N, ldx));
   ep.has_anext = anext != nullptr;
-  if (anext) LDMAE_TRY(make_tmap_2d(&ep.amap, anext, 2, g.M, g.N, ldx, 32, 32, 64));
+  if (anext) LDMAE_TRY(make_tmap_out_bf16(&ep.amap, anext, g.M, g.N, ldx));
   else ep.amap = ep.mmap;
   ep.bias = bias; ep.gate = gate; ep.gnext = gnext; ep.ssq = ssq;
   ep.gate_ld = gate_ld; ep.gnext_ld = gnext_ld; ep.rows_per_sample = rows_per_sample; ep.ss_slots = ss_slots;
@@ -412,7 +414,13 @@ struct ldmae_dit {
   bool finalized = false;
   int debug_stop = -1;   // >= 0: dit_forward_impl returns after that many launch groups (ldmae_dit_debug_stop)
   // workspace (sized for maxB)
-  DevBuf<float> xres, ssq, cvec_c, th1, mods, gmul, cvec_qkv, cvec_12, cvec_f, vbuf, k1buf, xtmp;
+  DevBuf<float> xres, ssq, cvec_c, th1, mods, gmul, cvec_qkv, cvec_12, cvec_f, vbuf, k1buf, xtmp, cvec_all;
+  // inference: W_fused = W_linear . W_adaLN[shift slot] for every modulated Linear, so ONE GEMM on silu(c) yields all per-sample
+  // vectors shift_b . W^T + bias (dit_build_fused_shift); the training forward keeps the two-step route the backward differentiates
+  DevBuf<__nv_bfloat16> w_shf, shf_tmp, shf_btmp;
+  DevBuf<float> b_shf;
+  int Nsh = 0;
+  bool shf_valid = false;
   DevBuf<__nv_bfloat16> abuf, qkv, obuf, hbuf, sc, shift_bf16;
   DitTrain* tr = nullptr;   // activations kept by the training forward, backward workspace, gradients (dit_train.cuh)
   bool wT_valid = false;    // transposed bf16 weight copies (data-gradient GEMM operands) are current
@@ -455,6 +463,7 @@ static int dit_alloc_ws(ldmae_dit* h, int B) {
   LDMAE_TRY(h->cvec_qkv.alloc(static_cast<size_t>(h->c.depth) * B * 3 * h->QW));
   LDMAE_TRY(h->cvec_12.alloc(static_cast<size_t>(h->c.depth) * B * 2 * h->Hp));
   LDMAE_TRY(h->cvec_f.alloc(static_cast<size_t>(B) * h->Nf));
+  LDMAE_TRY(h->cvec_all.alloc(static_cast<size_t>(B) * h->Nsh));
   const size_t lat = static_cast<size_t>(B) * h->c.in_channels * h->c.input_size * h->c.input_size;
   LDMAE_TRY(h->vbuf.alloc(lat));
   LDMAE_TRY(h->k1buf.alloc(lat));
@@ -518,6 +527,7 @@ extern "C" int ldmae_dit_create(const ldmae_dit_config* cfg, ldmae_dit** out) {
     LDMAE_REQUIRE(hd == 64 || (hd > 64 && hd <= 128 && hd % 8 == 0),
                   "head_dim %d: built for 64 (tuned path) and for multiples of 8 in (64, 128] (XL: 72, inference only)", hd);
   }
+  LDMAE_REQUIRE(c.hidden_size % 64 == 0, "hidden_size %d must be a multiple of 64", c.hidden_size);
   LDMAE_REQUIRE(c.input_size % c.patch_size == 0, "input_size %% patch_size != 0");
   LDMAE_REQUIRE((c.in_channels * c.patch_size * c.patch_size) % 4 == 0, "C*p*p must be a multiple of 4");
   ldmae_dit* h = new ldmae_dit();
@@ -536,6 +546,7 @@ extern "C" int ldmae_dit_create(const ldmae_dit_config* cfg, ldmae_dit** out) {
   h->hd = c.hidden_size / c.num_heads;
   h->HW = h->hd == 64 ? 64 : 128;
   h->QW = c.num_heads * h->HW;
+  h->Nsh = c.depth * (3 * h->QW + 2 * ((c.mlp_hidden + 31) / 32 * 32));
   const int D = h->D;
   h->blk.resize(c.depth);
   int r = LDMAE_OK;
@@ -551,6 +562,7 @@ extern "C" int ldmae_dit_create(const ldmae_dit_config* cfg, ldmae_dit** out) {
   A(h->norm_w.alloc(static_cast<size_t>(h->S) * D));
   A(h->w_ada.alloc(static_cast<size_t>(h->Ntot) * D)); A(h->b_ada.alloc(h->Ntot));
   A(h->w_f.alloc(static_cast<size_t>(h->Nf) * D)); A(h->b_f.alloc(h->Nf)); A(h->w_f32.alloc(static_cast<size_t>(h->Nf) * D));
+  A(h->w_shf.alloc(static_cast<size_t>(h->Nsh) * D)); A(h->b_shf.alloc(h->Nsh)); A(h->shf_tmp.alloc(static_cast<size_t>(D) * D)); A(h->shf_btmp.alloc(D));
   for (auto& b : h->blk) {
     A(b.w_qkv.alloc(static_cast<size_t>(3 * h->QW) * D)); A(b.b_qkv.alloc(3 * h->QW, true));
     A(b.w_proj.alloc(static_cast<size_t>(D) * D)); A(b.b_proj.alloc(D));
@@ -676,6 +688,7 @@ extern "C" int ldmae_dit_load_tensor(ldmae_dit* h, const char* name, const float
   }
   if (rc == LDMAE_OK && std::find(h->loaded.begin(), h->loaded.end(), k) == h->loaded.end()) h->loaded.push_back(k);
   h->wT_valid = false;
+  h->shf_valid = false;
   return rc;
 }
 
@@ -750,6 +763,42 @@ struct DitTrain {
 };
 static void dit_train_free(DitTrain* t) { delete t; }
 
+// Pre-multiplied shift path of the inference forward.  For a modulated Linear  y = Linear(modulate(RMSNorm(x), shift_b, scale_b))
+// the per-sample vector is  cvec_b = shift_b . W^T + bias  with  shift_b = silu(c_b) . W_ada[slot]^T + b_ada[slot]
+// (lightningdit.py:239-250), i.e.  cvec_b = silu(c_b) . (W . W_ada[slot])^T + (W . b_ada[slot] + bias):  W_fused [Nsh, D] (bf16)
+// and b_fused [Nsh] are built once per weight upload with the library's own GEMM; rows follow the packed layouts of w_qkv / w12.
+static int transpose_bf16(__nv_bfloat16* dst, const __nv_bfloat16* src, int R, int C, cudaStream_t st);
+__global__ void f32_to_bf16_kernel(__nv_bfloat16* out, const float* in, size_t n);
+static int dit_build_fused_shift(ldmae_dit* h, cudaStream_t st) {
+  if (h->shf_valid) return LDMAE_OK;
+  const int D = h->D, per = 3 * h->QW + 2 * h->Hp;
+  for (int i = 0; i < h->c.depth; ++i) {
+    DitBlockW& b = h->blk[i];
+    for (int which = 0; which < 2; ++which) {
+      const int slot = 2 * i + which;
+      const int rows = which == 0 ? 3 * h->QW : 2 * h->Hp;
+      const __nv_bfloat16* W = which == 0 ? b.w_qkv.p : b.w12.p;
+      const float* bias = which == 0 ? b.b_qkv.p : b.b12.p;
+      const size_t r0 = static_cast<size_t>(i) * per + (which == 0 ? 0 : 3 * h->QW);
+      const int so = h->so_host[slot];
+      if (so < 0) {      // wo_shift: no shift term, the vector is the bias
+        LDMAE_CUDA(cudaMemsetAsync(h->w_shf.p + r0 * D, 0, static_cast<size_t>(rows) * D * sizeof(__nv_bfloat16), st));
+        LDMAE_CUDA(cudaMemcpyAsync(h->b_shf.p + r0, bias, rows * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        continue;
+      }
+      // F[n, k'] = sum_j W[n, j] * W_ada[so + j, k']  ==  TN GEMM of W against the transposed D x D slot
+      LDMAE_TRY(transpose_bf16(h->shf_tmp.p, h->w_ada.p + static_cast<size_t>(so) * D, D, D, st));
+      LDMAE_TRY((gemm_store<__nv_bfloat16, 0>(W, D, h->shf_tmp.p, D, GemmShape{rows, D, D}, h->w_shf.p + r0 * D, D, nullptr, st)));
+      // b_fused[n] = sum_j W[n, j] * bf16(b_ada[so + j]) + bias[n]   (the two-step route rounds the whole shift to bf16 as well)
+      f32_to_bf16_kernel<<<cdiv(D, 256), 256, 0, st>>>(h->shf_btmp.p, h->b_ada.p + so, static_cast<size_t>(D));
+      LDMAE_LAUNCH_CHECK();
+      LDMAE_TRY((gemm_store<float, 0>(h->shf_btmp.p, D, W, D, GemmShape{1, rows, D}, h->b_shf.p + r0, rows, bias, st)));
+    }
+  }
+  h->shf_valid = true;
+  return LDMAE_OK;
+}
+
 // One forward pass of cat-batch B (see header).  out: [B, Cstore, S, S].  tr != nullptr: training forward (keeps activations).
 static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float t_scalar, const int64_t* y, float* out,
                             int B, int src_mod, cudaStream_t st, DitTrain* tr = nullptr) {
@@ -816,16 +865,28 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
   }
   LDMAE_DBG_STAGE();   // 2
   // 3. per-sample vectors  shift_b . W^T + bias  for every modulated Linear
-  for (int i = 0; i < depth; ++i) {
+  const bool fused_shift = tr == nullptr;
+  if (fused_shift) {
+    // inference: one GEMM on silu(c) against the pre-multiplied matrices (dit_build_fused_shift)
     ProfScope ps(5, st);
-    DitBlockW& b = h->blk[i];
-    float* cq = h->cvec_qkv.p + static_cast<size_t>(i) * B * 3 * h->QW;
-    float* c12 = h->cvec_12.p + static_cast<size_t>(i) * B * 2 * h->Hp;
-    LDMAE_TRY((gemm_store<float, 0>(h->shift_bf16.p + static_cast<size_t>(2 * i) * B * D, D, b.w_qkv.p, D, GemmShape{B, 3 * h->QW, D},
-                                    cq, 3 * h->QW, b.b_qkv.p, st)));
-    LDMAE_TRY((gemm_store<float, 0>(h->shift_bf16.p + static_cast<size_t>(2 * i + 1) * B * D, D, b.w12.p, D,
-                                    GemmShape{B, 2 * h->Hp, D}, c12, 2 * h->Hp, b.b12.p, st)));
+    LDMAE_TRY(dit_build_fused_shift(h, st));
+    LDMAE_TRY((gemm_store<float, 0>(h->sc.p, D, h->w_shf.p, D, GemmShape{B, h->Nsh, D}, h->cvec_all.p, h->Nsh, h->b_shf.p, st)));
+  } else {
+    for (int i = 0; i < depth; ++i) {
+      ProfScope ps(5, st);
+      DitBlockW& b = h->blk[i];
+      float* cq = h->cvec_qkv.p + static_cast<size_t>(i) * B * 3 * h->QW;
+      float* c12 = h->cvec_12.p + static_cast<size_t>(i) * B * 2 * h->Hp;
+      LDMAE_TRY((gemm_store<float, 0>(h->shift_bf16.p + static_cast<size_t>(2 * i) * B * D, D, b.w_qkv.p, D, GemmShape{B, 3 * h->QW, D},
+                                      cq, 3 * h->QW, b.b_qkv.p, st)));
+      LDMAE_TRY((gemm_store<float, 0>(h->shift_bf16.p + static_cast<size_t>(2 * i + 1) * B * D, D, b.w12.p, D,
+                                      GemmShape{B, 2 * h->Hp, D}, c12, 2 * h->Hp, b.b12.p, st)));
+    }
   }
+  const int sh_per_blk = 3 * h->QW + 2 * h->Hp;
+  auto cvec_q = [&](int i) { return fused_shift ? h->cvec_all.p + static_cast<size_t>(i) * sh_per_blk : h->cvec_qkv.p + static_cast<size_t>(i) * B * 3 * h->QW; };
+  auto cvec_m = [&](int i) { return fused_shift ? h->cvec_all.p + static_cast<size_t>(i) * sh_per_blk + 3 * h->QW : h->cvec_12.p + static_cast<size_t>(i) * B * 2 * h->Hp; };
+  const int cvq_ld = fused_shift ? h->Nsh : 3 * h->QW, cvm_ld = fused_shift ? h->Nsh : 2 * h->Hp;
   {
     ProfScope ps(7, st);
     // final linear (N = p*p*C_out, e.g. 16): fp32 on CUDA cores straight from the shift columns of mods
@@ -868,7 +929,7 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
         eq.has_raw = 1;
         LDMAE_TRY(make_tmap_out_bf16(&eq.rawmap, tr->QKR.p + static_cast<size_t>(i) * M * 2 * D, M, 2 * D, 2 * D));
       }
-      eq.ssq = Ss(2 * i); eq.cvec = h->cvec_qkv.p + static_cast<size_t>(i) * B * 3 * D;
+      eq.ssq = Ss(2 * i); eq.cvec = cvec_q(i); eq.cvec_ld = cvq_ld;
       eq.qw = c.use_qknorm ? b.qw.p : nullptr; eq.kw = c.use_qknorm ? b.kw.p : nullptr;
       eq.rope = c.use_rope ? h->rope_tab.p : nullptr; eq.grid = h->G;
       eq.D = D; eq.rows_per_sample = T; eq.ss_slots = h->SS; eq.inv_D = 1.f / D; eq.eps_row = eps; eq.eps_head = eps;
@@ -892,7 +953,7 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
         eq.has_raw = 1;
         LDMAE_TRY(make_tmap_out_bf16(&eq.rawmap, tr->QKR.p + static_cast<size_t>(i) * M * 2 * h->QW, M, 2 * h->QW, 2 * h->QW));
       }
-      eq.ssq = Ss(2 * i); eq.cvec = h->cvec_qkv.p + static_cast<size_t>(i) * B * 3 * h->QW;
+      eq.ssq = Ss(2 * i); eq.cvec = cvec_q(i); eq.cvec_ld = cvq_ld;
       eq.qw = c.use_qknorm ? b.qw.p : nullptr; eq.kw = c.use_qknorm ? b.kw.p : nullptr;
       eq.rope_cos = c.use_rope ? h->rope_cos.p : nullptr; eq.rope_sin = c.use_rope ? h->rope_sin.p : nullptr;
       eq.section = h->QW; eq.hd = h->hd; eq.rows_per_sample = T; eq.ss_slots = h->SS;
@@ -925,7 +986,7 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
       es.has_pre = 1;
       LDMAE_TRY(make_tmap_out_bf16(&es.premap, tr->H12.p + static_cast<size_t>(i) * M * 2 * h->Hp, M, 2 * h->Hp, 2 * h->Hp));
     }
-    es.ssq = Ss(2 * i + 1); es.cvec = h->cvec_12.p + static_cast<size_t>(i) * B * 2 * h->Hp;
+    es.ssq = Ss(2 * i + 1); es.cvec = cvec_m(i); es.cvec_ld = cvm_ld;
     es.rows_per_sample = T; es.ss_slots = h->SS; es.inv_D = 1.f / D; es.eps_row = eps;
     { ProfScope ps(3, st); LDMAE_TRY((gemm_auto<EpiSwiGLU>(As(2 * i + 1), D, b.w12.p, D, GemmShape{M, 2 * h->Hp, D}, es, st))); }
     LDMAE_DBG_STAGE();
@@ -1427,7 +1488,7 @@ extern "C" int ldmae_gemm_residual(const void* a, const void* w, const float* bi
                                    float* x, void* anext, float* ssq, int32_t M, int32_t N, int32_t K, int32_t rows_per_sample,
                                    void* stream) {
   LDMAE_TRY(require_sm100());
-  LDMAE_REQUIRE(K % 8 == 0 && N % 4 == 0, "K must be a multiple of 8 and N of 4");
+  LDMAE_REQUIRE(K % 8 == 0 && N % 64 == 0, "K must be a multiple of 8 and N of 64");
   LDMAE_REQUIRE((anext == nullptr) == (gnext == nullptr), "anext and gnext go together");
   return gemm_residual(a, K, w, K, GemmShape{M, N, K}, x, N, bias, gate, N, gnext, N, static_cast<__nv_bfloat16*>(anext), ssq,
                        (N + 127) / 128, rows_per_sample, static_cast<cudaStream_t>(stream));

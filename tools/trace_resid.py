@@ -19,11 +19,11 @@ tr = torch.zeros(256, 8, dtype=torch.int64, device=dev)
 _lib.check(L.ldmae_gemm_trace(_lib.ptr(tr)))
 run(); torch.cuda.synchronize()
 tr = tr.cpu()
-names = ["wait_store_read", "pump", "wait_x", "ld_acc", "math+sts", "issue_store"]
+names = ["wait_x", "ld_acc", "math_x", "wait_store+pump", "math_a", "issue_store"]
 t0 = int(tr[0, 0])
 for sidx in list(range(0, 40)):
     st = [int(v) for v in tr[sidx]]
     if st[0] == 0: break
     d = [st[k + 1] - st[k] for k in range(6)]
     nxt = int(tr[sidx + 1, 0]) - st[6]
-    print(f"chunk {sidx:3d} start={st[0]-t0:8d} " + " ".join(f"{n}={v}" for n, v in zip(names, d)) + f" to_next={nxt}")
+    print(f"pair {sidx:3d} start={st[0]-t0:8d} " + " ".join(f"{n}={v}" for n, v in zip(names, d)) + f" to_next={nxt}")
