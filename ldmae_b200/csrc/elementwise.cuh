@@ -325,6 +325,56 @@ __global__ void layernorm_bf16_kernel(__nv_bfloat16* __restrict__ out, const flo
     out[static_cast<size_t>(row) * D + k] = __float2bfloat16((xr[k] - mean) * rstd * w[k] + bvec[k]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// LightningDiT fallback variants (use_rmsnorm=False and / or use_swiglu=False, reference lightningdit.py:195-224,257-272):
+// the norm is NOT folded into the neighbouring GEMM epilogues there (LayerNorm's mean has no such factorisation with the
+// shipped statistics), so the modulated operand is produced by one HBM pass:
+//   out[row, :] = bf16( norm(x[row, :]) * (1 + scale_b) + shift_b )
+//   norm = LayerNorm without affine (eps) when w == nullptr, else RMSNorm * w (models/rmsnorm.py:52-77); shift may be null.
+// One warp per row, 16-byte accesses.  D % 4 == 0.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+norm_modulate_bf16_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ x, const float* __restrict__ w,
+                          const float* __restrict__ scale, const float* __restrict__ shift, int mod_ld, int rows_per_sample,
+                          int M, int D, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* xr = x + static_cast<size_t>(row) * D;
+  const size_t b = static_cast<size_t>(row / rows_per_sample);
+  float s = 0.f, q = 0.f;
+  for (int k = lane * 4; k < D; k += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + k);
+    s += v.x + v.y + v.z + v.w;
+    q = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, q))));
+  }
+  s = warp_sum(s); q = warp_sum(q);
+  float mean = 0.f, rstd;
+  if (w == nullptr) {
+    mean = s / D;
+    float qc = 0.f;                                        // centred second pass (row is in L1/L2): no cancellation
+    for (int k = lane * 4; k < D; k += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(xr + k);
+      const float a0 = v.x - mean, a1 = v.y - mean, a2 = v.z - mean, a3 = v.w - mean;
+      qc = fmaf(a0, a0, fmaf(a1, a1, fmaf(a2, a2, fmaf(a3, a3, qc))));
+    }
+    rstd = rsqrtf(warp_sum(qc) / D + eps);
+  } else {
+    rstd = rsqrtf(q / D + eps);
+  }
+  for (int k = lane * 4; k < D; k += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + k);
+    float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (w != nullptr) g = *reinterpret_cast<const float4*>(w + k);
+    const float4 sc = *reinterpret_cast<const float4*>(scale + b * mod_ld + k);
+    float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (shift != nullptr) sh = *reinterpret_cast<const float4*>(shift + b * mod_ld + k);
+    const float y0 = (v.x - mean) * rstd * g.x * (1.f + sc.x) + sh.x, y1 = (v.y - mean) * rstd * g.y * (1.f + sc.y) + sh.y;
+    const float y2 = (v.z - mean) * rstd * g.z * (1.f + sc.z) + sh.z, y3 = (v.w - mean) * rstd * g.w * (1.f + sc.w) + sh.w;
+    *reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * D + k) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+  }
+}
+
 // latent [B,C,g,g] fp32 -> de-normalised tokens [B*g*g, Kpad] bf16 (zero padded):
 //   z' = z * std[c] / multiplier + mean[c]   (inference.py:291), 'b c h w -> b (h w) c' (models_mae.py:868)
 __global__ void latent_to_tokens_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ z,

@@ -458,6 +458,8 @@ struct EpiQKV : StoreRing {
     int cvec_ld;
     const float* qw;        // [64] q_norm.weight or nullptr (no qk-norm)
     const float* kw;        // [64]
+    const float* qb;        // [64] q_norm.bias: the head norm is nn.LayerNorm (use_rmsnorm=False, lightningdit.py:57-61); nullptr: RMSNorm
+    const float* kb;        // [64]
     const float* rope;      // [2, grid, 32] or nullptr
     int D, rows_per_sample, ss_slots, grid;
     float inv_D, eps_row, eps_head;
@@ -507,6 +509,9 @@ struct EpiQKV : StoreRing {
       const float mul = lane < 16 ? p.q_mul : 1.f;
       nw4.x *= mul; nw4.y *= mul; nw4.z *= mul; nw4.w *= mul;
       *reinterpret_cast<float4*>(vnw + lane * 4) = nw4;
+      if (p.qb != nullptr)
+        *reinterpret_cast<float4*>(vnw + 128 + lane * 4) =
+            lane < 16 ? __ldg(reinterpret_cast<const float4*>(p.qb) + lane) : __ldg(reinterpret_cast<const float4*>(p.kb) + lane - 16);
     }
     __syncwarp();
     const bool rsm = kFast || rope_in_smem(p);
@@ -547,13 +552,32 @@ struct EpiQKV : StoreRing {
         release(c, st, &p.rawmap, tile, colbase, row0);
         tile = acquire(c, st);
       }
-      if (which < 2 && p.qw != nullptr) {
+      if (which < 2 && p.qw != nullptr && p.qb == nullptr) {
         const float hs = rsqrtf(ms * (1.f / 64.f) + p.eps_head);
         const float* nw = vnw + which * 64;
 #pragma unroll
         for (int j = 0; j < 64; j += 4) {
           const float4 w4 = lds_f4(nw + j);
           v[j] *= hs * w4.x; v[j + 1] *= hs * w4.y; v[j + 2] *= hs * w4.z; v[j + 3] *= hs * w4.w;
+        }
+      }
+      if (which < 2 && p.qb != nullptr) {
+        // nn.LayerNorm(head_dim) with affine parameters (fallback variant): centred variance in registers
+        float sm = 0.f;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) sm += v[j];
+        const float mu = sm * (1.f / 64.f);
+        float var = 0.f;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) { const float d = v[j] - mu; var = fmaf(d, d, var); }
+        const float hs = rsqrtf(var * (1.f / 64.f) + p.eps_head);
+        const float* nw = vnw + which * 64;
+        const float* nb = vnw + 128 + which * 64;
+#pragma unroll
+        for (int j = 0; j < 64; j += 4) {
+          const float4 w4 = lds_f4(nw + j), b4 = lds_f4(nb + j);
+          v[j] = (v[j] - mu) * hs * w4.x + b4.x; v[j + 1] = (v[j + 1] - mu) * hs * w4.y + b4.y;
+          v[j + 2] = (v[j + 2] - mu) * hs * w4.z + b4.z; v[j + 3] = (v[j + 3] - mu) * hs * w4.w + b4.w;
         }
       }
       if (which < 2 && p.rope != nullptr) {
@@ -809,7 +833,8 @@ struct EpiFinal {
   struct Params {
     float* out;          // [B, Cstore, G*p, G*p]
     const float* ssq;    // [M, ss_slots]
-    const float* cvec;   // [B, N]
+    const float* cvec;   // [B, N] (row pitch cvec_ld; 0 = one vector for every sample)
+    int cvec_ld;
     int grid, patch, cout, cstore, rows_per_sample, ss_slots;
     float inv_D, eps_row;
   };
@@ -842,7 +867,7 @@ struct EpiFinal {
           const int pq = col / p.cout;
           const int pi = pq / p.patch, qi = pq % p.patch;
           if (ch < p.cstore) {
-            const float val = fmaf(v[j], rinv, __ldg(p.cvec + static_cast<size_t>(b) * g.N + col));
+            const float val = fmaf(v[j], rinv, __ldg(p.cvec + static_cast<size_t>(b) * p.cvec_ld + col));
             p.out[((static_cast<size_t>(b) * p.cstore + ch) * HW + (th * p.patch + pi)) * HW + tw * p.patch + qi] = val;
           }
         }

@@ -390,6 +390,8 @@ static int gemm_wgrad(const void* pm, int ldp, const void* qm, int ldq, float* c
 struct DitBlockW {
   DevBuf<__nv_bfloat16> w_qkv, w_proj, w12, w3;
   DevBuf<float> b_qkv, b_proj, b12, b3, qw, kw;
+  DevBuf<float> qb, kb;        // q_norm / k_norm bias: nn.LayerNorm head norm of the use_rmsnorm=False variant
+  // use_swiglu=False variant (timm Mlp, tanh GELU): fc1 lives in w12 / b12 (plain row order), fc2 in w3 / b3
   float attn_m0_log2 = -1.f;   // > 0: bound of |q.k| * scale * log2(e) from the q/k norm weights (constant-offset softmax)
 };
 
@@ -421,6 +423,7 @@ struct ldmae_dit {
   DevBuf<float> b_shf;
   int Nsh = 0;
   bool shf_valid = false;
+  bool fused = true;       // shipped recipe (RMSNorm + SwiGLU): norms folded into the GEMM epilogues; else the generic path
   DevBuf<__nv_bfloat16> abuf, qkv, obuf, hbuf, sc, shift_bf16;
   DitTrain* tr = nullptr;   // activations kept by the training forward, backward workspace, gradients (dit_train.cuh)
   bool wT_valid = false;    // transposed bf16 weight copies (data-gradient GEMM operands) are current
@@ -519,8 +522,9 @@ extern "C" int ldmae_dit_create(const ldmae_dit_config* cfg, ldmae_dit** out) {
   LDMAE_REQUIRE(cfg && out, "null argument");
   LDMAE_TRY(require_sm100());
   const ldmae_dit_config& c = *cfg;
-  LDMAE_REQUIRE(c.use_rmsnorm == 1, "LightningDiT without use_rmsnorm (LayerNorm variant) is not built yet");
-  LDMAE_REQUIRE(c.use_swiglu == 1, "LightningDiT without use_swiglu (GELU Mlp variant) is not built yet");
+  if (!(c.use_rmsnorm == 1 && c.use_swiglu == 1))
+    LDMAE_REQUIRE(c.hidden_size / std::max(1, c.num_heads) == 64,
+                  "the LayerNorm / GELU-Mlp variants (use_rmsnorm=False / use_swiglu=False) are built for head_dim 64");
   LDMAE_REQUIRE(c.num_heads > 0 && c.hidden_size % c.num_heads == 0, "hidden_size %% num_heads != 0");
   {
     const int hd = c.hidden_size / c.num_heads;
@@ -546,7 +550,8 @@ extern "C" int ldmae_dit_create(const ldmae_dit_config* cfg, ldmae_dit** out) {
   h->hd = c.hidden_size / c.num_heads;
   h->HW = h->hd == 64 ? 64 : 128;
   h->QW = c.num_heads * h->HW;
-  h->Nsh = c.depth * (3 * h->QW + 2 * ((c.mlp_hidden + 31) / 32 * 32));
+  h->fused = c.use_rmsnorm == 1 && c.use_swiglu == 1;
+  h->Nsh = h->fused ? c.depth * (3 * h->QW + 2 * ((c.mlp_hidden + 31) / 32 * 32)) : 4;
   const int D = h->D;
   h->blk.resize(c.depth);
   int r = LDMAE_OK;
@@ -566,9 +571,11 @@ extern "C" int ldmae_dit_create(const ldmae_dit_config* cfg, ldmae_dit** out) {
   for (auto& b : h->blk) {
     A(b.w_qkv.alloc(static_cast<size_t>(3 * h->QW) * D)); A(b.b_qkv.alloc(3 * h->QW, true));
     A(b.w_proj.alloc(static_cast<size_t>(D) * D)); A(b.b_proj.alloc(D));
-    A(b.w12.alloc(static_cast<size_t>(2 * h->Hp) * D)); A(b.b12.alloc(2 * h->Hp));
+    const int w12_rows = c.use_swiglu ? 2 * h->Hp : h->Hp;
+    A(b.w12.alloc(static_cast<size_t>(w12_rows) * D)); A(b.b12.alloc(w12_rows));
     A(b.w3.alloc(static_cast<size_t>(D) * h->Hp)); A(b.b3.alloc(D));
     A(b.qw.alloc(h->HW, true)); A(b.kw.alloc(h->HW, true));
+    A(b.qb.alloc(h->HW, true)); A(b.kb.alloc(h->HW, true));
   }
   // adaLN slot -> column offsets inside a mods row
   std::vector<int> so(h->S), sco(h->S);
@@ -670,6 +677,15 @@ extern "C" int ldmae_dit_load_tensor(ldmae_dit* h, const char* name, const float
     }
     else if (sub == "attn.q_norm.weight") rc = copy_f32(b.qw.p, data, numel, h->hd, name, st);
     else if (sub == "attn.k_norm.weight") rc = copy_f32(b.kw.p, data, numel, h->hd, name, st);
+    else if (sub == "attn.q_norm.bias" && !h->c.use_rmsnorm) rc = copy_f32(b.qb.p, data, numel, h->hd, name, st);
+    else if (sub == "attn.k_norm.bias" && !h->c.use_rmsnorm) rc = copy_f32(b.kb.p, data, numel, h->hd, name, st);
+    else if (sub == "mlp.fc1.weight" && !h->c.use_swiglu) rc = pack_bf16(b.w12.p, data, h->Hp, D, D, numel, name, st, 0, 0, h->H);
+    else if (sub == "mlp.fc1.bias" && !h->c.use_swiglu) {
+      LDMAE_CUDA(cudaMemsetAsync(b.b12.p, 0, h->Hp * sizeof(float), st));
+      rc = copy_f32(b.b12.p, data, numel, h->H, name, st);
+    }
+    else if (sub == "mlp.fc2.weight" && !h->c.use_swiglu) rc = pack_bf16(b.w3.p, data, D, h->H, h->Hp, numel, name, st);
+    else if (sub == "mlp.fc2.bias" && !h->c.use_swiglu) rc = copy_f32(b.b3.p, data, numel, D, name, st);
     else if (sub == "attn.proj.weight") rc = pack_bf16(b.w_proj.p, data, D, D, D, numel, name, st);
     else if (sub == "attn.proj.bias") rc = copy_f32(b.b_proj.p, data, numel, D, name, st);
     else if (sub == "mlp.w12.weight") rc = pack_bf16(b.w12.p, data, 2 * h->Hp, D, D, numel, name, st, 1, h->H, 2 * h->H);
@@ -696,7 +712,8 @@ extern "C" int ldmae_dit_finalize(ldmae_dit* h, void* stream) {
   LDMAE_REQUIRE(h, "null handle");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int expect = 8 + 5 + 12 * h->c.depth;   // without qk-norm / rope keys
-  if (h->c.use_qknorm) expect += 2 * h->c.depth;
+  if (!h->c.use_rmsnorm) expect -= 1 + 2 * h->c.depth;      // LayerNorm(elementwise_affine=False): no norm weights
+  if (h->c.use_qknorm) expect += (h->c.use_rmsnorm ? 2 : 4) * h->c.depth;   // nn.LayerNorm head norms carry a bias too
   if (h->c.use_rope) expect += 2;
   if ((int)h->loaded.size() != expect)
     return set_error(LDMAE_ERR_STATE, "LightningDiT weights incomplete: %d of %d tensors loaded", (int)h->loaded.size(), expect);
@@ -799,6 +816,88 @@ static int dit_build_fused_shift(ldmae_dit* h, cudaStream_t st) {
   return LDMAE_OK;
 }
 
+// The LightningDiT variants without the shipped RMSNorm + SwiGLU pair (reference lightningdit.py:195-224,257-272:
+// nn.LayerNorm(elementwise_affine=False, eps=1e-6) block / final norms, nn.LayerNorm(head_dim) q/k norms, timm Mlp with
+// tanh-GELU) -- inference only.  The norm is one HBM pass per modulated Linear (norm_modulate_bf16_kernel) instead of being
+// folded into the neighbouring GEMM epilogues; everything else runs on the same tcgen05 GEMM / attention kernels with the
+// row factor switched off (ssq = nullptr) and the Linear bias in the per-sample-vector slot (cvec_ld = 0).
+// Called by dit_forward_impl after the conditioning and the adaLN GEMM (h->mods is ready).
+static int dit_forward_generic(ldmae_dit* h, const float* x, float* out, int B, int src_mod, cudaStream_t st) {
+  const ldmae_dit_config& c = h->c;
+  const int D = h->D, T = h->T, depth = c.depth, M = B * T;
+  const float eps = 1e-6f;
+  LDMAE_REQUIRE(h->HW == 64, "LayerNorm / GELU variants need head_dim 64");
+  {
+    ProfScope ps(7, st);
+    dim3 grid(cdiv(T, 32), B);
+    const size_t sm = (32 * static_cast<size_t>(h->Kp) + 256) * sizeof(float);
+    patch_embed_kernel<<<grid, 256, sm, st>>>(h->xres.p, nullptr, nullptr, x, h->patch_w.p, h->patch_b.p, h->pos.p, nullptr,
+                                              c.in_channels, c.input_size, c.patch_size, D, src_mod, h->SS);
+    LDMAE_LAUNCH_CHECK();
+  }
+  auto norm_mod = [&](int slot) -> int {
+    ProfScope ps(7, st);
+    const float* w = c.use_rmsnorm ? h->norm_w.p + static_cast<size_t>(slot) * D : nullptr;
+    const float* sh = h->so_host[slot] >= 0 ? h->mods.p + h->so_host[slot] : nullptr;
+    norm_modulate_bf16_kernel<<<cdiv(M, 8), 256, 0, st>>>(h->abuf.p, h->xres.p, w, h->mods.p + h->sco_host[slot], sh, h->Ntot, T, M, D, eps);
+    LDMAE_LAUNCH_CHECK();
+    return LDMAE_OK;
+  };
+  for (int i = 0; i < depth; ++i) {
+    DitBlockW& b = h->blk[i];
+    const float* mods_i = h->mods.p + static_cast<size_t>(i) * h->nmod * D;
+    const float* gate_msa = mods_i + (c.wo_shift ? 1 : 2) * D;
+    const float* gate_mlp = mods_i + (c.wo_shift ? 3 : 5) * D;
+    LDMAE_TRY(norm_mod(2 * i));
+    EpiQKV::Params eq;
+    LDMAE_TRY(make_tmap_out_bf16(&eq.omap, h->qkv.p, M, 3 * D, 3 * D));
+    eq.has_raw = 0; eq.rawmap = eq.omap;
+    eq.ssq = nullptr; eq.cvec = b.b_qkv.p; eq.cvec_ld = 0;
+    eq.qw = c.use_qknorm ? b.qw.p : nullptr; eq.kw = c.use_qknorm ? b.kw.p : nullptr;
+    const bool ln_heads = c.use_qknorm && !c.use_rmsnorm;
+    eq.qb = ln_heads ? b.qb.p : nullptr; eq.kb = ln_heads ? b.kb.p : nullptr;
+    eq.rope = c.use_rope ? h->rope_tab.p : nullptr; eq.grid = h->G;
+    eq.D = D; eq.rows_per_sample = T; eq.ss_slots = h->SS; eq.inv_D = 1.f / D; eq.eps_row = eps;
+    eq.eps_head = ln_heads ? 1e-5f : eps;              // nn.LayerNorm default eps vs models/rmsnorm.py
+    eq.q_mul = 1.f;
+    { ProfScope ps(0, st); LDMAE_TRY((gemm_auto<EpiQKV>(h->abuf.p, D, b.w_qkv.p, D, GemmShape{M, 3 * D, D}, eq, st))); }
+    {
+      ProfScope ps(1, st);
+      // the score bound of finalize() holds for RMS-normed heads only; LayerNorm heads use the running-maximum kernel
+      const float m0 = (c.use_qknorm && c.use_rmsnorm) ? b.attn_m0_log2 : -1.f;
+      LDMAE_TRY(run_attention(h->qkv.p, 3 * D, h->obuf.p, D, B, T, c.num_heads, 0, D, 2 * D, 0.125f, st, nullptr, m0, false));
+    }
+    { ProfScope ps(2, st);
+      LDMAE_TRY(gemm_residual(h->obuf.p, D, b.w_proj.p, D, GemmShape{M, D, D}, h->xres.p, D, b.b_proj.p, gate_msa, h->Ntot, nullptr, 0,
+                              nullptr, nullptr, 0, T, st)); }
+    LDMAE_TRY(norm_mod(2 * i + 1));
+    if (c.use_swiglu) {
+      EpiSwiGLU::Params es;
+      LDMAE_TRY(make_tmap_out_bf16(&es.omap, h->hbuf.p, M, h->Hp, h->Hp));
+      es.has_pre = 0; es.premap = es.omap;
+      es.ssq = nullptr; es.cvec = b.b12.p; es.cvec_ld = 0;
+      es.rows_per_sample = T; es.ss_slots = h->SS; es.inv_D = 1.f / D; es.eps_row = eps;
+      ProfScope ps(3, st);
+      LDMAE_TRY((gemm_auto<EpiSwiGLU>(h->abuf.p, D, b.w12.p, D, GemmShape{M, 2 * h->Hp, D}, es, st)));
+    } else {
+      ProfScope ps(3, st);     // timm Mlp: fc1 + GELU(approximate="tanh")
+      LDMAE_TRY((gemm_store<__nv_bfloat16, 2>(h->abuf.p, D, b.w12.p, D, GemmShape{M, h->Hp, D}, h->hbuf.p, h->Hp, b.b12.p, st)));
+    }
+    { ProfScope ps(4, st);
+      LDMAE_TRY(gemm_residual(h->hbuf.p, h->Hp, b.w3.p, h->Hp, GemmShape{M, D, h->Hp}, h->xres.p, D, b.b3.p, gate_mlp, h->Ntot, nullptr, 0,
+                              nullptr, nullptr, 0, T, st)); }
+  }
+  LDMAE_TRY(norm_mod(2 * depth));
+  EpiFinal::Params ef;
+  ef.out = out; ef.ssq = nullptr; ef.cvec = h->b_f.p; ef.cvec_ld = 0; ef.grid = h->G; ef.patch = c.patch_size;
+  ef.cout = c.in_channels * (c.learn_sigma ? 2 : 1); ef.cstore = c.in_channels; ef.rows_per_sample = T; ef.ss_slots = h->SS;
+  ef.inv_D = 1.f / D; ef.eps_row = eps;
+  ProfScope ps(6, st);
+  LDMAE_TRY((launch_gemm<16, 1, EpiFinal>(h->abuf.p, D, h->w_f.p, D, GemmShape{M, h->Nf, D}, ef, st)));
+  ++g_launch_count;
+  return LDMAE_OK;
+}
+
 // One forward pass of cat-batch B (see header).  out: [B, Cstore, S, S].  tr != nullptr: training forward (keeps activations).
 static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float t_scalar, const int64_t* y, float* out,
                             int B, int src_mod, cudaStream_t st, DitTrain* tr = nullptr) {
@@ -858,6 +957,7 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
   {
     ProfScope ps(5, st);
     LDMAE_TRY((gemm_store<float, 0>(h->sc.p, D, h->w_ada.p, D, GemmShape{B, h->Ntot, D}, h->mods.p, h->Ntot, h->b_ada.p, st)));
+    if (!h->fused) return dit_forward_generic(h, x, out, B, src_mod, st);
     const size_t tot = static_cast<size_t>(h->S) * B * D;
     adaln_prep_kernel<<<cdiv(tot, 256), 256, 0, st>>>(h->shift_bf16.p, h->gmul.p, h->mods.p, h->norm_w.p,
                                                       h->slot_shift_off.p, h->slot_scale_off.p, B, D, h->Ntot, h->S);
@@ -930,7 +1030,7 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
         LDMAE_TRY(make_tmap_out_bf16(&eq.rawmap, tr->QKR.p + static_cast<size_t>(i) * M * 2 * D, M, 2 * D, 2 * D));
       }
       eq.ssq = Ss(2 * i); eq.cvec = cvec_q(i); eq.cvec_ld = cvq_ld;
-      eq.qw = c.use_qknorm ? b.qw.p : nullptr; eq.kw = c.use_qknorm ? b.kw.p : nullptr;
+      eq.qw = c.use_qknorm ? b.qw.p : nullptr; eq.kw = c.use_qknorm ? b.kw.p : nullptr; eq.qb = nullptr; eq.kb = nullptr;
       eq.rope = c.use_rope ? h->rope_tab.p : nullptr; eq.grid = h->G;
       eq.D = D; eq.rows_per_sample = T; eq.ss_slots = h->SS; eq.inv_D = 1.f / D; eq.eps_row = eps; eq.eps_head = eps;
       // inference forward of qk-normed heads: the softmax scale and log2(e) ride on q_norm.weight, the attention kernel takes
@@ -1005,7 +1105,7 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
   // 6. final layer + unpatchify
   {
     EpiFinal::Params ef;
-    ef.out = out; ef.ssq = Ss(2 * depth); ef.cvec = h->cvec_f.p; ef.grid = h->G; ef.patch = c.patch_size;
+    ef.out = out; ef.ssq = Ss(2 * depth); ef.cvec = h->cvec_f.p; ef.cvec_ld = h->Nf; ef.grid = h->G; ef.patch = c.patch_size;
     ef.cout = c.in_channels * (c.learn_sigma ? 2 : 1); ef.cstore = c.in_channels; ef.rows_per_sample = T; ef.ss_slots = h->SS;
     ef.inv_D = 1.f / D; ef.eps_row = eps;
     ProfScope ps(6, st);
@@ -1029,6 +1129,7 @@ extern "C" int ldmae_dit_debug_poison(ldmae_dit* h, int32_t byte, void* stream) 
   LDMAE_POISON(xres) LDMAE_POISON(ssq) LDMAE_POISON(cvec_c) LDMAE_POISON(th1) LDMAE_POISON(mods) LDMAE_POISON(gmul)
   LDMAE_POISON(cvec_qkv) LDMAE_POISON(cvec_12) LDMAE_POISON(cvec_f) LDMAE_POISON(vbuf) LDMAE_POISON(k1buf) LDMAE_POISON(xtmp)
   LDMAE_POISON(abuf) LDMAE_POISON(qkv) LDMAE_POISON(obuf) LDMAE_POISON(hbuf) LDMAE_POISON(sc) LDMAE_POISON(shift_bf16)
+  LDMAE_POISON(cvec_all)
 #undef LDMAE_POISON
   return LDMAE_OK;
 }

@@ -86,14 +86,25 @@ class _RopeBuffers(nn.Module):
 
 
 class _AttentionParams(nn.Module):
-    def __init__(self, dim, num_heads, qk_norm):
+    def __init__(self, dim, num_heads, qk_norm, use_rmsnorm=True):
         super().__init__()
         self.num_heads = num_heads
         self.head_dim = dim // num_heads
         self.qkv = nn.Linear(dim, dim * 3, bias=True)
-        self.q_norm = _RMSNormParams(self.head_dim) if qk_norm else nn.Identity()
-        self.k_norm = _RMSNormParams(self.head_dim) if qk_norm else nn.Identity()
+        # reference lightningdit.py:57-61: RMSNorm(head_dim) with use_rmsnorm, else nn.LayerNorm(head_dim) (affine, eps 1e-5)
+        norm = _RMSNormParams if use_rmsnorm else nn.LayerNorm
+        self.q_norm = norm(self.head_dim) if qk_norm else nn.Identity()
+        self.k_norm = norm(self.head_dim) if qk_norm else nn.Identity()
         self.proj = nn.Linear(dim, dim)
+
+
+class _MlpParams(nn.Module):
+    """timm Mlp parameter names (fc1, fc2); reference lightningdit.py:219-224 uses it with GELU(approximate='tanh')."""
+
+    def __init__(self, in_features, hidden_features):
+        super().__init__()
+        self.fc1 = nn.Linear(in_features, hidden_features, bias=True)
+        self.fc2 = nn.Linear(hidden_features, in_features, bias=True)
 
 
 class _SwiGLUParams(nn.Module):
@@ -103,21 +114,27 @@ class _SwiGLUParams(nn.Module):
         self.w3 = nn.Linear(hidden_features, in_features, bias=True)
 
 
+def _block_norm(hidden_size, use_rmsnorm):
+    """reference lightningdit.py:195-200,258-261: RMSNorm, or LayerNorm without affine parameters (eps 1e-6)."""
+    return _RMSNormParams(hidden_size) if use_rmsnorm else nn.LayerNorm(hidden_size, elementwise_affine=False, eps=1e-6)
+
+
 class _BlockParams(nn.Module):
-    def __init__(self, hidden_size, num_heads, mlp_ratio, use_qknorm, wo_shift):
+    def __init__(self, hidden_size, num_heads, mlp_ratio, use_qknorm, wo_shift, use_swiglu=True, use_rmsnorm=True):
         super().__init__()
-        self.norm1 = _RMSNormParams(hidden_size)
-        self.norm2 = _RMSNormParams(hidden_size)
-        self.attn = _AttentionParams(hidden_size, num_heads, use_qknorm)
-        self.mlp = _SwiGLUParams(hidden_size, int(2 / 3 * int(hidden_size * mlp_ratio)))
+        self.norm1 = _block_norm(hidden_size, use_rmsnorm)
+        self.norm2 = _block_norm(hidden_size, use_rmsnorm)
+        self.attn = _AttentionParams(hidden_size, num_heads, use_qknorm, use_rmsnorm)
+        mlp_hidden = int(hidden_size * mlp_ratio)
+        self.mlp = _SwiGLUParams(hidden_size, int(2 / 3 * mlp_hidden)) if use_swiglu else _MlpParams(hidden_size, mlp_hidden)
         self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(hidden_size, (4 if wo_shift else 6) * hidden_size))
         self.wo_shift = wo_shift
 
 
 class _FinalLayerParams(nn.Module):
-    def __init__(self, hidden_size, patch_size, out_channels):
+    def __init__(self, hidden_size, patch_size, out_channels, use_rmsnorm=True):
         super().__init__()
-        self.norm_final = _RMSNormParams(hidden_size)
+        self.norm_final = _block_norm(hidden_size, use_rmsnorm)
         self.linear = nn.Linear(hidden_size, patch_size * patch_size * out_channels, bias=True)
         self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(hidden_size, 2 * hidden_size))
 
@@ -130,11 +147,10 @@ class LightningDiT(nn.Module):
                  mlp_ratio=4.0, class_dropout_prob=0.1, num_classes=1000, learn_sigma=False, use_qknorm=False,
                  use_swiglu=False, use_rope=False, use_rmsnorm=False, wo_shift=False, use_checkpoint=False):
         super().__init__()
-        if not (use_swiglu and use_rmsnorm):
-            raise NotImplementedError(
-                "ldmae_b200 builds the shipped LightningDiT recipe (use_swiglu=True, use_rmsnorm=True; reference "
-                "configs/*/lightningdit_b_vmae_f8d16_cfg.yaml:28-34); the LayerNorm / GELU-Mlp fallbacks are not built")
         hd = hidden_size // num_heads
+        if not (use_swiglu and use_rmsnorm) and hd != 64:
+            raise NotImplementedError("the LayerNorm / GELU-Mlp variants (use_rmsnorm=False / use_swiglu=False; reference "
+                                      f"lightningdit.py:195-224) are built for head_dim 64, got {hd}")
         if not (hd == 64 or (64 < hd <= 128 and hd % 8 == 0)):
             raise NotImplementedError(f"ldmae_b200 attention is built for head_dim 64 (B, L, 1p0B, 1p6B: tuned kernels) and for "
                                       f"multiples of 8 in (64, 128] (XL, head_dim 72: 128-column head slots); got {hd}")
@@ -158,9 +174,9 @@ class LightningDiT(nn.Module):
         num_patches = self.x_embedder.num_patches
         self.pos_embed = nn.Parameter(torch.zeros(1, num_patches, hidden_size), requires_grad=False)
         self.feat_rope = _RopeBuffers(hidden_size // num_heads // 2, input_size // patch_size) if use_rope else None
-        self.blocks = nn.ModuleList([_BlockParams(hidden_size, num_heads, mlp_ratio, use_qknorm, wo_shift)
+        self.blocks = nn.ModuleList([_BlockParams(hidden_size, num_heads, mlp_ratio, use_qknorm, wo_shift, use_swiglu, use_rmsnorm)
                                      for _ in range(depth)])
-        self.final_layer = _FinalLayerParams(hidden_size, patch_size, self.out_channels)
+        self.final_layer = _FinalLayerParams(hidden_size, patch_size, self.out_channels, use_rmsnorm)
         self.initialize_weights()
         self._handle = None
         self._handle_sig = None
@@ -319,6 +335,10 @@ class LightningDiT(nn.Module):
         B = x.shape[0]
         h = self._ensure_handle(x.device, B)
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if not (self.use_swiglu and self.use_rmsnorm):
+                raise NotImplementedError("training (autograd through LightningDiT.forward) is built for the shipped recipe "
+                                          "(use_rmsnorm=True, use_swiglu=True); the LayerNorm / GELU-Mlp variants are "
+                                          "inference-only -- call under torch.no_grad()")
             # differentiable path (train_accum.py:215-230): the library keeps the activations, autograd sees one node whose
             # inputs are the trainable parameters, so .grad / DDP hooks / torch optimizers work as with the reference
             named = [(k, p) for k, p in self.named_parameters() if p.requires_grad]

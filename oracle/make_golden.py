@@ -134,7 +134,10 @@ def gen_dit_grads():
 def gen_dit_variants():
     """Config flags the API must accept (SURVEY section 8a tail): celeba (no qk-norm, 1 class -> no cfg
     embedding is NOT the case: class_dropout_prob stays 0.1 unless num_classes==1), wo_shift."""
-    for tag, flags in (("noqk", dict(use_qknorm=False)), ("woshift", dict(wo_shift=True))):
+    for tag, flags in (("noqk", dict(use_qknorm=False)), ("woshift", dict(wo_shift=True)),
+                       # fallbacks of lightningdit.py:195-224,257-261: LayerNorm block / head / final norms, timm Mlp + tanh-GELU
+                       ("ln_gelu", dict(use_rmsnorm=False, use_swiglu=False)), ("ln_swiglu", dict(use_rmsnorm=False)),
+                       ("rms_gelu", dict(use_swiglu=False)), ("ln_gelu_noqk", dict(use_rmsnorm=False, use_swiglu=False, use_qknorm=False))):
         spec, ref, sd = tiny_dit(1, **flags)
         g = torch.Generator().manual_seed(55)
         x = torch.randn(2, 16, 8, 8, generator=g); t = torch.rand(2, generator=g); y = torch.randint(0, 10, (2,), generator=g)
@@ -237,6 +240,9 @@ def gen_config1():
 if __name__ == "__main__":
     if "--config1-only" in sys.argv:
         gen_config1()
+        sys.exit(0)
+    if "--variants-only" in sys.argv:
+        gen_dit_variants()
         sys.exit(0)
     if "--grads-only" in sys.argv:
         gen_dit_grads()

@@ -33,7 +33,7 @@ def _tiny_model(patch, seed, **flags):
     spec = O.DiTSpec(depth=2, hidden_size=128, patch_size=patch, num_heads=2, input_size=8, in_channels=16,
                      num_classes=10, **flags)
     m = LightningDiT(input_size=8, patch_size=patch, in_channels=16, hidden_size=128, depth=2, num_heads=2, num_classes=10,
-                     use_qknorm=spec.use_qknorm, use_swiglu=True, use_rope=spec.use_rope, use_rmsnorm=True,
+                     use_qknorm=spec.use_qknorm, use_swiglu=spec.use_swiglu, use_rope=spec.use_rope, use_rmsnorm=spec.use_rmsnorm,
                      wo_shift=spec.wo_shift)
     sd = O.synth_dit_state(spec, seed)
     m.load_state_dict(sd, strict=True)
@@ -87,13 +87,34 @@ def test_sampler_euler_heun_vs_reference_golden(golden_dir, patch):
     assert torch.equal(z, torch.cat([x[:n], x[:n]], 0))
 
 
-@pytest.mark.parametrize("tag,flags", [("noqk", dict(use_qknorm=False)), ("woshift", dict(wo_shift=True))])
+@pytest.mark.parametrize("tag,flags", [("noqk", dict(use_qknorm=False)), ("woshift", dict(wo_shift=True)),
+                                      ("ln_gelu", dict(use_rmsnorm=False, use_swiglu=False)), ("ln_swiglu", dict(use_rmsnorm=False)),
+                                      ("rms_gelu", dict(use_swiglu=False)),
+                                      ("ln_gelu_noqk", dict(use_rmsnorm=False, use_swiglu=False, use_qknorm=False))])
 def test_dit_tiny_variants(golden_dir, tag, flags):
     from gpu_util import load_npz
     g = load_npz(golden_dir, f"dit_tiny_{tag}.npz")
     spec, sd, m = _tiny_model(1, int(g["seed"]), **flags)
-    out = m(torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["t"]).cuda(), torch.from_numpy(g["y"]).cuda())
-    assert _rel(out, g["out"]) < FWD_TOL
+    x, t, y = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["t"]).cuda(), torch.from_numpy(g["y"]).cuda()
+    out = m(x, t, y)
+    err = _rel(out, g["out"])
+    print(f"variant {tag}: velocity rel err {err:.3e}")
+    assert err < FWD_TOL
+    if not (spec.use_rmsnorm and spec.use_swiglu):
+        # the LayerNorm / GELU-Mlp fallbacks (lightningdit.py:195-224) run the generic path: CFG forward and sampler too
+        from ldmae_b200.transport import Sampler, create_transport
+        ycfg = torch.cat([y[:1], torch.full((1,), 10, device="cuda")])
+        z = torch.cat([x[:1], x[:1]], 0)
+        kw = dict(y=ycfg, cfg_scale=3.0, cfg_interval=True, cfg_interval_start=0.10)
+        fn = Sampler(create_transport("Linear", "velocity", None, None, None)).sample_ode(
+            sampling_method="euler", num_steps=5, atol=1e-6, rtol=1e-3, reverse=False, timestep_shift=0.3)
+        ours = fn(z, m.forward_with_cfg, **kw)[-1]
+        ref_fn = lambda xx, tt, **k: O.dit_forward_with_cfg(sd, spec, xx, tt, **k)
+        want = O.sample_ode(ref_fn, z.cpu(), sampling_method="euler", num_steps=5, timestep_shift=0.3,
+                            **{k: (v.cpu() if torch.is_tensor(v) else v) for k, v in kw.items()})[-1]
+        assert _rel(ours, want) < FINAL_TOL
+        with torch.enable_grad(), pytest.raises(NotImplementedError, match="inference-only"):
+            m(x, t, y)
 
 
 def test_dit_b1_forward_vs_reference_golden(golden_dir):
@@ -448,3 +469,35 @@ def test_uint8_nhwc_pack_bit_exact():
     assert torch.equal(u8, want)
     assert int((want == 0).sum()) > 0 and int((want == 255).sum()) > 0          # both clamps exercised
     assert np.array_equal(vae.decode_to_images(z), want.cpu().numpy())
+
+
+def test_dopri5_and_sde_through_the_generic_path_vs_oracle(golden_dir):
+    """The reference's default sampling_method ('dopri5', transport.py:401) and the SDE sampler (transport.py:336-396) drive the
+    model through its public forward_with_cfg, one library call per stage; compared with the same host loop around the oracle."""
+    from ldmae_b200.transport import Sampler, create_transport
+    from gpu_util import load_npz
+    g = load_npz(golden_dir, "dit_tiny_p1.npz")
+    spec, sd, m = _tiny_model(1, int(g["seed"]))
+    x = torch.from_numpy(g["x"])
+    n = x.shape[0] // 2
+    z = torch.cat([x[:n], x[:n]], 0)
+    ycfg = torch.from_numpy(g["ycfg"])
+    kw = dict(y=ycfg, cfg_scale=4.0, cfg_interval=True, cfg_interval_start=0.10)
+    kw_gpu = dict(kw, y=ycfg.cuda())
+    ref_model = lambda xx, tt, **k: O.dit_forward_with_cfg(sd, spec, xx, tt, **k)
+    smp = Sampler(create_transport("Linear", "velocity", None, None, None))
+    fn = smp.sample_ode(sampling_method="dopri5", num_steps=4, atol=1e-5, rtol=1e-3, reverse=False, timestep_shift=0.3)
+    ours, want = fn(z.cuda(), m.forward_with_cfg, **kw_gpu), fn(z, ref_model, **kw)
+    assert ours.shape == want.shape == (4,) + tuple(z.shape)
+    e = _rel(ours[-1][:n], want[-1][:n])
+    print(f"dopri5 (generic path) final state rel err {e:.3e}")
+    assert e < FINAL_TOL
+    fs = smp.sample_sde(sampling_method="Euler", diffusion_form="sigma", num_steps=6, last_step="Mean", last_step_size=0.04)
+    torch.manual_seed(5)
+    a = fs(z.cuda(), m.forward_with_cfg, **kw_gpu)
+    torch.manual_seed(5)                       # the noise is drawn on the host (integrators.py:30), so both runs see the same
+    b = fs(z, ref_model, **kw)
+    assert len(a) == len(b) == 6
+    e = _rel(a[-1][:n], b[-1][:n])
+    print(f"SDE Euler-Maruyama (generic path) final state rel err {e:.3e}")
+    assert e < FINAL_TOL

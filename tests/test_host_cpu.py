@@ -376,3 +376,56 @@ def test_fused_optimizer_state_round_trips_through_torch_adamw():
     assert load_adamw_state_dict(m, lay, ea2, es2, opt.state_dict()) == 7
     for k in lay.names:
         assert torch.equal(lay.view(ea2, k), lay.view(ea, k)) and torch.equal(lay.view(es2, k), lay.view(es, k))
+
+
+# ----------------------------------------------------------------------------- generic samplers (host-side loops)
+def test_generic_ode_solvers_on_analytic_problems():
+    """The loops that serve arbitrary model callables (transport.py:398-443 / integrators.py:77-126 with torchdiffeq restated):
+    fixed-grid Euler / Heun / midpoint / RK4 and adaptive dopri5 with dense output on dx/dt = -x and a rotation."""
+    import numpy as np
+    import torch
+    from ldmae_b200.transport.transport import Sampler, _dopri5_odeint, create_transport
+    A = torch.tensor([[0.0, 1.0], [-1.0, 0.0]])
+    t = torch.linspace(0, 1, 11)
+    sol = _dopri5_odeint(lambda tt, y: y @ A.T, torch.tensor([[1.0, 0.0], [0.0, 2.0]]), t, 1e-6, 1e-8)
+    want = torch.stack([torch.tensor([[np.cos(v), -np.sin(v)], [2 * np.sin(v), 2 * np.cos(v)]]) for v in t.numpy()]).float()
+    assert float((sol - want).abs().max()) < 2e-5
+    smp = Sampler(create_transport("Linear", "velocity", None, None, None))
+    model = lambda x, tt, **kw: -x
+    x0 = torch.randn(4, 3, 2, 2, generator=torch.Generator().manual_seed(0))
+    tol = {"dopri5": 3e-3, "rk4": 1e-6, "midpoint": 2e-3, "heun2": 2e-3, "heun": 2e-3, "euler": 6e-2}
+    for method, bound in tol.items():
+        fn = smp.sample_ode(sampling_method=method, num_steps=20, atol=1e-6, rtol=1e-3, reverse=False, timestep_shift=0.0)
+        out = fn(x0, model)
+        assert out.shape == (20, 4, 3, 2, 2) and torch.equal(out[0], x0)       # N grid points, every state returned
+        assert float((out[-1] - x0 * np.exp(-1.0)).abs().max()) < bound, method
+    with pytest.raises(AssertionError, match="forward time"):                      # the reference asserts the same (integrators.py:89)
+        smp.sample_ode(sampling_method="dopri5", num_steps=5, reverse=True)
+    with pytest.raises(NotImplementedError):
+        smp.sample_ode(sampling_method="bosh3")
+
+
+def test_sde_samplers_shapes_last_steps_and_zero_diffusion_limit():
+    """Sampler.sample_sde (transport.py:285-396): num_steps states, the four last-step rules, and with a vanishing diffusion
+    norm Euler-Maruyama reduces to the Euler ODE step on the same grid."""
+    import torch
+    from ldmae_b200.transport.transport import Sampler, create_transport
+    tr = create_transport("Linear", "velocity", None, None, None)
+    smp = Sampler(tr)
+    model = lambda x, tt, **kw: -x + 0.1
+    x0 = torch.randn(3, 2, 4, 4, generator=torch.Generator().manual_seed(1))
+    assert tr.check_interval(0, 0, sde=True, eval=True, last_step_size=0.04, diffusion_form="sigma") == (0, 0.96)
+    for method in ("Euler", "Heun"):
+        for last in ("Mean", "Tweedie", "Euler", None):
+            xs = smp.sample_sde(sampling_method=method, diffusion_form="sigma", num_steps=12, last_step=last)(x0, model)
+            assert len(xs) == 12
+            if last is not None:       # without a last step the grid ends at t = 1, where the score's variance vanishes (as upstream)
+                assert all(torch.isfinite(v).all() for v in xs)
+    xs = smp.sample_sde(sampling_method="Euler", diffusion_form="sigma", diffusion_norm=1e-12, num_steps=9, last_step=None)(x0, model)
+    grid = torch.linspace(0, 1, 9)
+    x = x0
+    for _ in grid[:-1]:
+        x = x + model(x, None) * (grid[1] - grid[0])
+    torch.testing.assert_close(xs[-2], x, rtol=1e-4, atol=1e-5)
+    with pytest.raises(NotImplementedError):
+        smp.sample_ode_likelihood()

@@ -60,7 +60,10 @@ def test_dit_tiny_forward_cfg_and_sampler(golden_dir, patch):
     torch.testing.assert_close(terms["loss"], _t(g["loss"]), **TOL)
 
 
-@pytest.mark.parametrize("tag,flags", [("noqk", dict(use_qknorm=False)), ("woshift", dict(wo_shift=True))])
+@pytest.mark.parametrize("tag,flags", [("noqk", dict(use_qknorm=False)), ("woshift", dict(wo_shift=True)),
+                                      ("ln_gelu", dict(use_rmsnorm=False, use_swiglu=False)), ("ln_swiglu", dict(use_rmsnorm=False)),
+                                      ("rms_gelu", dict(use_swiglu=False)),
+                                      ("ln_gelu_noqk", dict(use_rmsnorm=False, use_swiglu=False, use_qknorm=False))])
 def test_dit_tiny_variants(golden_dir, tag, flags):
     g = _load(golden_dir, f"dit_tiny_{tag}.npz")
     spec = _tiny_spec(1, **flags)
