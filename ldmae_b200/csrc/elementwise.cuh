@@ -175,7 +175,7 @@ __global__ void adaln_prep_kernel(__nv_bfloat16* __restrict__ shift_bf16, float*
   const int s = i / (static_cast<size_t>(D) * B);
   const float* row = mods + static_cast<size_t>(b) * Ntot;
   const int so = slot_shift_off[s];
-  shift_bf16[i] = __float2bfloat16(so >= 0 ? row[so + d] : 0.f);
+  if (shift_bf16 != nullptr) shift_bf16[i] = __float2bfloat16(so >= 0 ? row[so + d] : 0.f);   // nullptr: pre-multiplied shift path
   gmul[i] = norm_w[s * D + d] * (1.f + row[slot_scale_off[s] + d]);
 }
 
@@ -186,21 +186,58 @@ __global__ void adaln_prep_kernel(__nv_bfloat16* __restrict__ shift_bf16, float*
 //   anext[row,n]= bf16(x * gnext[b, n]);  ssq[row, 0] = sum_n x^2 (other slots 0)
 // src_mod: sample b reads latent (b % src_mod) -- forward_with_cfg feeds cat[half, half] (lightningdit.py:425-426).
 // ---------------------------------------------------------------------------------------------
+// Tensor-core route of the patch embedding (inference, token count a multiple of 128): the latent patches are split into
+// bf16 (hi | lo) pairs -- x = hi + lo to ~16 mantissa bits, so the fp32 latent is not rounded to bf16 -- and multiplied with
+// the doubled weight [W | W]; K = 2 * C * p * p still fits one 64-wide k-block for p = 1.
+//   out[row, 0:Kp] = bf16(x), out[row, Kp:2Kp] = bf16(x - float(bf16(x)))        row = sample b reading latent b % src_mod
+// Rows have a pitch of K2 >= 2 * Kp elements (a multiple of 64; the padding stays zero).
+__global__ void patchify_hilo_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ lat, int B, int C, int S, int p,
+                                     int src_mod, int K2) {
+  const int G = S / p, T = G * G, Kp = C * p * p;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(B) * T * Kp) return;
+  const int tok = i % T;                             // tokens fastest: coalesced reads of a (c, pi, qi) plane for p == 1
+  const int k = (i / T) % Kp;
+  const size_t b = i / (static_cast<size_t>(T) * Kp);
+  const int c = k / (p * p), pi = (k / p) % p, qi = k % p;
+  const float v = lat[(((b % src_mod) * C + c) * S + (tok / G) * p + pi) * S + (tok % G) * p + qi];
+  const __nv_bfloat16 hi = __float2bfloat16(v);
+  const size_t row = b * T + tok;
+  out[row * K2 + k] = hi;
+  out[row * K2 + Kp + k] = __float2bfloat16(v - __bfloat162float(hi));
+}
+// dst [D, K2] = [bf16(W) | bf16(W) | 0]
+__global__ void pack_dup_bf16_kernel(__nv_bfloat16* __restrict__ dst, const float* __restrict__ src, int D, int Kp, int K2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D * Kp) return;
+  const __nv_bfloat16 w = __float2bfloat16(src[i]);
+  const int n = i / Kp, k = i % Kp;
+  dst[static_cast<size_t>(n) * K2 + k] = w;
+  dst[static_cast<size_t>(n) * K2 + Kp + k] = w;
+}
+
+constexpr int kPeTokens = 64;     // tokens per block of patch_embed_kernel
+// shared memory of patch_embed_kernel: [64][Kp] patches, [8][64] partial sums, and (w_smem) the weight transposed [Kp][D + 4]
+inline size_t patch_embed_smem(int Kp, int D, bool w_smem) {
+  return (static_cast<size_t>(kPeTokens) * Kp + 8 * kPeTokens + (w_smem ? static_cast<size_t>(Kp) * (D + 4) : 0)) * sizeof(float);
+}
 __global__ void __launch_bounds__(256, 2)
 patch_embed_kernel(float* __restrict__ x, __nv_bfloat16* __restrict__ anext, float* __restrict__ ssq,
                    const float* __restrict__ lat /*[Bsrc, C, S, S]*/, const float* __restrict__ W /*[D, C*p*p]*/,
                    const float* __restrict__ bias, const float* __restrict__ pos /*[T, D]*/,
-                   const float* __restrict__ gnext /*[B, D]*/, int C, int S, int p, int D, int src_mod, int ss_slots) {
+                   const float* __restrict__ gnext /*[B, D]*/, int C, int S, int p, int D, int src_mod, int ss_slots, int w_smem) {
   extern __shared__ float sm[];
   const int G = S / p, T = G * G, Kp = C * p * p;
-  float* s_in = sm;                               // [32][Kp]
-  float* s_red = sm + 32 * Kp;                    // [8 warps][32 tokens] partial sums of squares (no atomics:
+  float* s_in = sm;                               // [64][Kp]
+  float* s_red = sm + kPeTokens * Kp;             // [8 warps][64 tokens] partial sums of squares (no atomics:
                                                   // fixed summation order => bit-reproducible statistics)
+  float* s_w = s_red + 8 * kPeTokens;             // w_smem: W transposed, s_w[k * (D + 4) + n]
+  const int wp = D + 4;
   const int b = blockIdx.y;
-  const int tok0 = blockIdx.x * 32;
+  const int tok0 = blockIdx.x * kPeTokens;
   const float* src = lat + static_cast<size_t>(b % src_mod) * C * S * S;
-  for (int i = threadIdx.x; i < 32 * Kp; i += blockDim.x) {
-    const int k = i / 32, tl = i % 32;            // tokens fastest -> coalesced for p == 1
+  for (int i = threadIdx.x; i < kPeTokens * Kp; i += blockDim.x) {
+    const int k = i / kPeTokens, tl = i % kPeTokens;   // tokens fastest -> coalesced for p == 1
     const int tok = tok0 + tl;
     float v = 0.f;
     if (tok < T) {
@@ -210,7 +247,18 @@ patch_embed_kernel(float* __restrict__ x, __nv_bfloat16* __restrict__ anext, flo
     }
     s_in[tl * Kp + k] = v;
   }
-  s_red[threadIdx.x] = 0.f;
+  if (w_smem) {
+    // W rows are 4 * Kp bytes apart: read straight from global memory, the 4 rows a thread needs per step are 32 separate
+    // lines per warp instruction (ncu, round 2: 1.39 ms for 2.4 GB written at Bf = 512 -- L1 wavefronts, not HBM).  Staged once
+    // per block, transposed, every later read is a conflict-free 16-byte shared-memory access.
+    const int k4n = Kp / 4;
+    for (int i = threadIdx.x; i < D * k4n; i += blockDim.x) {
+      const int n = i / k4n, k4 = i % k4n;
+      const float4 w = __ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(n) * Kp + 4 * k4));
+      s_w[(4 * k4 + 0) * wp + n] = w.x; s_w[(4 * k4 + 1) * wp + n] = w.y;
+      s_w[(4 * k4 + 2) * wp + n] = w.z; s_w[(4 * k4 + 3) * wp + n] = w.w;
+    }
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // thread = 4 consecutive output columns (16-byte stores of x, 8-byte stores of the bf16 operand; a warp writes 512
@@ -218,7 +266,7 @@ patch_embed_kernel(float* __restrict__ x, __nv_bfloat16* __restrict__ anext, flo
   // needs occupancy, not registers); the squares are summed per thread over its columns and reduced with ONE warp
   // reduction per token (fixed order => bit-reproducible statistics).  D % 128 == 0.
 #pragma unroll 1
-  for (int tg = 0; tg < 4; ++tg) {
+  for (int tg = 0; tg < kPeTokens / 8; ++tg) {
     float sq[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) sq[i] = 0.f;
@@ -232,15 +280,26 @@ patch_embed_kernel(float* __restrict__ x, __nv_bfloat16* __restrict__ anext, flo
       for (int i = 0; i < 8; ++i) { acc[i][0] = bn.x; acc[i][1] = bn.y; acc[i][2] = bn.z; acc[i][3] = bn.w; }
 #pragma unroll 1
       for (int k0 = 0; k0 < Kp; k0 += 4) {
-        float4 w[4];
+        float wk[4][4];                             // wk[kk][j] = W[n + j][k0 + kk]
+        if (w_smem) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) w[j] = __ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(n + j) * Kp + k0));
+          for (int kk = 0; kk < 4; ++kk) {
+            const float4 w4 = *reinterpret_cast<const float4*>(s_w + (k0 + kk) * wp + n);
+            wk[kk][0] = w4.x; wk[kk][1] = w4.y; wk[kk][2] = w4.z; wk[kk][3] = w4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(n + j) * Kp + k0));
+            wk[0][j] = w4.x; wk[1][j] = w4.y; wk[2][j] = w4.z; wk[3][j] = w4.w;
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float4 a = *reinterpret_cast<const float4*>(s_in + (tg * 8 + i) * Kp + k0);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            acc[i][j] = fmaf(w[j].x, a.x, fmaf(w[j].y, a.y, fmaf(w[j].z, a.z, fmaf(w[j].w, a.w, acc[i][j]))));
+            acc[i][j] = fmaf(wk[0][j], a.x, fmaf(wk[1][j], a.y, fmaf(wk[2][j], a.z, fmaf(wk[3][j], a.w, acc[i][j]))));
         }
       }
 #pragma unroll
@@ -260,15 +319,15 @@ patch_embed_kernel(float* __restrict__ x, __nv_bfloat16* __restrict__ anext, flo
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float t = warp_sum(sq[i]);
-      if (lane == 0) s_red[warp * 32 + tg * 8 + i] = t;
+      if (lane == 0) s_red[warp * kPeTokens + tg * 8 + i] = t;
     }
   }
   __syncthreads();
-  if (ssq != nullptr && threadIdx.x < 32 && tok0 + threadIdx.x < T) {
+  if (ssq != nullptr && threadIdx.x < kPeTokens && tok0 + threadIdx.x < T) {
     float* dst = ssq + (static_cast<size_t>(b) * T + tok0 + threadIdx.x) * ss_slots;   // slot 0 = whole row
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += s_red[w * 32 + threadIdx.x];
+    for (int w = 0; w < 8; ++w) s += s_red[w * kPeTokens + threadIdx.x];
     dst[0] = s;
     for (int j = 1; j < ss_slots; ++j) dst[j] = 0.f;
   }

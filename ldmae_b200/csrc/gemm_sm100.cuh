@@ -269,6 +269,8 @@ struct EpiResidualT {
     float* ssq;            // [M, ss_slots] per-row partial sums of squares, or nullptr.  Slot = column/128 of the
                            // producing tile: no atomics, so the statistics are bit-reproducible.
     int gate_ld, gnext_ld, rows_per_sample, ss_slots, has_anext;
+    int x_row_mod;         // > 0: the tile of x that is LOADED comes from row (row0 % x_row_mod) of xmap -- a [x_row_mod, N] table
+                           // added to every sample (patch embedding: x = patches . W^T + bias + pos_embed[token]); 0: row0
     long long* trace;      // debug builds (-DLDMAE_GEMM_TRACE): [256 pairs][8] clock64 stamps of CTA 0, epilogue warp 0
   };
   // every lane keeps the same copy of this state (warp-uniform control flow)
@@ -292,7 +294,8 @@ struct EpiResidualT {
   static __device__ __forceinline__ void pump(const Params& p, const GemmShape& g, const TileSched& s, const EpiCtx& c, State& st,
                                               int upto) {
     while (st.pf_seq <= upto && st.pf_tile < s.total) {
-      const int row0 = (st.pf_mi * s.cg + s.cta_rank) * kBM + s.wq * 32;
+      int row0 = (st.pf_mi * s.cg + s.cta_rank) * kBM + s.wq * 32;
+      if (p.x_row_mod > 0) row0 %= p.x_row_mod;
       const int n0 = st.pf_ni * BN;
       const int npairs = min(BN / 64, (g.N - n0 + 63) / 64);
       const int b = st.pf_seq % kNXP;

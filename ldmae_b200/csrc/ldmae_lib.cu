@@ -164,6 +164,7 @@ static int gemm_residual(const void* a, int lda, const void* w, int ldw, GemmSha
   else ep.amap = ep.xmap;
   ep.bias = bias; ep.gate = gate; ep.gnext = gnext; ep.ssq = ssq;
   ep.gate_ld = gate_ld; ep.gnext_ld = gnext_ld; ep.rows_per_sample = rows_per_sample; ep.ss_slots = ss_slots;
+  ep.x_row_mod = 0;
   ep.trace = g_gemm_trace;
   static int deep = -1;
   if (deep < 0) { const char* e = getenv("LDMAE_RESID_DEEP"); deep = e ? atoi(e) : 1; }
@@ -191,6 +192,7 @@ static int gemm_residual_train(const void* a, int lda, const void* w, int ldw, G
   else ep.amap = ep.mmap;
   ep.bias = bias; ep.gate = gate; ep.gnext = gnext; ep.ssq = ssq;
   ep.gate_ld = gate_ld; ep.gnext_ld = gnext_ld; ep.rows_per_sample = rows_per_sample; ep.ss_slots = ss_slots;
+  ep.x_row_mod = 0;
   ep.trace = nullptr;
   return gemm_auto<EpiResidualTrain>(a, lda, w, ldw, g, ep, st);
 }
@@ -405,6 +407,7 @@ static void dit_train_free(DitTrain* t);
 struct ldmae_dit {
   ldmae_dit_config c;
   int D, T, G, Kp, H, Hp, nmod, Ntot, S /*norm slots*/, Nf, maxB, SS /*ssq partial slots*/;
+  int K2 /*(hi | lo) patch row pitch of the tensor-core patch embedding: 2*Kp rounded up to 64*/;
   int hd /*real head_dim*/, HW /*head stride in the qkv buffer: 64, or 128 for wider heads*/, QW /*heads * HW*/;
   // weights
   DevBuf<float> pos, patch_w, patch_b, t_w0, t_b0, t_w2, t_b2, emb, rope_cos, rope_sin, rope_tab, norm_w, b_ada, b_f, w_f32;
@@ -420,6 +423,7 @@ struct ldmae_dit {
   // inference: W_fused = W_linear . W_adaLN[shift slot] for every modulated Linear, so ONE GEMM on silu(c) yields all per-sample
   // vectors shift_b . W^T + bias (dit_build_fused_shift); the training forward keeps the two-step route the backward differentiates
   DevBuf<__nv_bfloat16> w_shf, shf_tmp, shf_btmp;
+  DevBuf<__nv_bfloat16> patch_w2, tok2;     // tensor-core patch embedding: [D, 2Kp] doubled weight, [maxB*T, 2Kp] (hi | lo) patches
   DevBuf<float> b_shf;
   int Nsh = 0;
   bool shf_valid = false;
@@ -467,6 +471,7 @@ static int dit_alloc_ws(ldmae_dit* h, int B) {
   LDMAE_TRY(h->cvec_12.alloc(static_cast<size_t>(h->c.depth) * B * 2 * h->Hp));
   LDMAE_TRY(h->cvec_f.alloc(static_cast<size_t>(B) * h->Nf));
   LDMAE_TRY(h->cvec_all.alloc(static_cast<size_t>(B) * h->Nsh));
+  LDMAE_TRY(h->tok2.alloc(M * h->K2, true));
   const size_t lat = static_cast<size_t>(B) * h->c.in_channels * h->c.input_size * h->c.input_size;
   LDMAE_TRY(h->vbuf.alloc(lat));
   LDMAE_TRY(h->k1buf.alloc(lat));
@@ -540,6 +545,7 @@ extern "C" int ldmae_dit_create(const ldmae_dit_config* cfg, ldmae_dit** out) {
   h->G = c.input_size / c.patch_size;
   h->T = h->G * h->G;
   h->Kp = c.in_channels * c.patch_size * c.patch_size;
+  h->K2 = (2 * h->Kp + 63) / 64 * 64;
   h->H = c.mlp_hidden;
   h->Hp = (c.mlp_hidden + 31) / 32 * 32;
   h->nmod = c.wo_shift ? 4 : 6;
@@ -551,13 +557,14 @@ extern "C" int ldmae_dit_create(const ldmae_dit_config* cfg, ldmae_dit** out) {
   h->HW = h->hd == 64 ? 64 : 128;
   h->QW = c.num_heads * h->HW;
   h->fused = c.use_rmsnorm == 1 && c.use_swiglu == 1;
-  h->Nsh = h->fused ? c.depth * (3 * h->QW + 2 * ((c.mlp_hidden + 31) / 32 * 32)) : 4;
+  h->Nsh = h->fused ? c.depth * (3 * h->QW + 2 * ((c.mlp_hidden + 31) / 32 * 32)) + c.patch_size * c.patch_size * c.in_channels * (c.learn_sigma ? 2 : 1) : 4;
   const int D = h->D;
   h->blk.resize(c.depth);
   int r = LDMAE_OK;
   auto A = [&](int rc) { if (r == LDMAE_OK) r = rc; };
   A(h->pos.alloc(static_cast<size_t>(h->T) * D));
   A(h->patch_w.alloc(static_cast<size_t>(D) * h->Kp));
+  A(h->patch_w2.alloc(static_cast<size_t>(D) * h->K2, true));
   A(h->patch_b.alloc(D));
   A(h->t_w0.alloc(static_cast<size_t>(D) * 256)); A(h->t_b0.alloc(D));
   A(h->t_w2.alloc(static_cast<size_t>(D) * D)); A(h->t_b2.alloc(D));
@@ -639,7 +646,13 @@ extern "C" int ldmae_dit_load_tensor(ldmae_dit* h, const char* name, const float
     LDMAE_REQUIRE(bi >= 0 && bi < h->c.depth, "block index out of range in %s", name);
   }
   if (k == "pos_embed") rc = copy_f32(h->pos.p, data, numel, (int64_t)h->T * D, name, st);
-  else if (k == "x_embedder.proj.weight") rc = copy_f32(h->patch_w.p, data, numel, (int64_t)D * h->Kp, name, st);
+  else if (k == "x_embedder.proj.weight") {
+    rc = copy_f32(h->patch_w.p, data, numel, (int64_t)D * h->Kp, name, st);
+    if (rc == LDMAE_OK) {
+      pack_dup_bf16_kernel<<<cdiv(static_cast<size_t>(D) * h->Kp, 256), 256, 0, st>>>(h->patch_w2.p, data, D, h->Kp, h->K2);
+      LDMAE_LAUNCH_CHECK();
+    }
+  }
   else if (k == "x_embedder.proj.bias") rc = copy_f32(h->patch_b.p, data, numel, D, name, st);
   else if (k == "t_embedder.mlp.0.weight") rc = copy_f32(h->t_w0.p, data, numel, (int64_t)D * 256, name, st);
   else if (k == "t_embedder.mlp.0.bias") rc = copy_f32(h->t_b0.p, data, numel, D, name, st);
@@ -812,7 +825,57 @@ static int dit_build_fused_shift(ldmae_dit* h, cudaStream_t st) {
       LDMAE_TRY((gemm_store<float, 0>(h->shf_btmp.p, D, W, D, GemmShape{1, rows, D}, h->b_shf.p + r0, rows, bias, st)));
     }
   }
+  {
+    // final layer (lightningdit.py:267-272): rows of final_layer.linear against the final adaLN's shift slot
+    const size_t r0 = static_cast<size_t>(h->c.depth) * per;
+    const int so = h->so_host[2 * h->c.depth];
+    LDMAE_TRY(transpose_bf16(h->shf_tmp.p, h->w_ada.p + static_cast<size_t>(so) * D, D, D, st));
+    LDMAE_TRY((gemm_store<__nv_bfloat16, 0>(h->w_f.p, D, h->shf_tmp.p, D, GemmShape{h->Nf, D, D}, h->w_shf.p + r0 * D, D, nullptr, st)));
+    f32_to_bf16_kernel<<<cdiv(D, 256), 256, 0, st>>>(h->shf_btmp.p, h->b_ada.p + so, static_cast<size_t>(D));
+    LDMAE_LAUNCH_CHECK();
+    LDMAE_TRY((gemm_store<float, 0>(h->shf_btmp.p, D, h->w_f.p, D, GemmShape{1, h->Nf, D}, h->b_shf.p + r0, h->Nf, h->b_f.p, st)));
+  }
   h->shf_valid = true;
+  return LDMAE_OK;
+}
+
+// Patch embedding launch: the weight goes through shared memory (transposed) whenever it fits next to two resident blocks.
+static int launch_patch_embed(ldmae_dit* h, float* xs, __nv_bfloat16* as, float* ss, const float* x, const float* gmul, int B,
+                              int src_mod, cudaStream_t st, bool tensor_ok = true) {
+  const ldmae_dit_config& c = h->c;
+  static int tc = -1;
+  if (tc < 0) { const char* e = getenv("LDMAE_PATCH_TC"); tc = e ? atoi(e) : 1; }
+  if (tc && tensor_ok && h->T % 128 == 0 && h->Kp % 4 == 0 && h->D % 64 == 0) {
+    // tensor-core route: (hi | lo) bf16 patches . [W | W]^T through the residual epilogue, whose "x" tile is the pos_embed row
+    // of the token (x_row_mod = T): HBM-bound at 6 bytes per output element instead of CUDA-core bound
+    const int M = B * h->T, K2 = h->K2, D = h->D;
+    patchify_hilo_kernel<<<cdiv(static_cast<size_t>(M) * h->Kp, 256), 256, 0, st>>>(h->tok2.p, x, B, c.in_channels, c.input_size,
+                                                                                   c.patch_size, src_mod, K2);
+    LDMAE_LAUNCH_CHECK();
+    EpiResidualDeep::Params ep;
+    LDMAE_TRY(make_tmap_out_f32(&ep.xmap, h->pos.p, h->T, D, D));
+    LDMAE_TRY(make_tmap_out_f32(&ep.xmap_out, xs, M, D, D));
+    ep.mmap = ep.xmap;
+    ep.has_anext = as != nullptr;
+    if (as) LDMAE_TRY(make_tmap_out_bf16(&ep.amap, as, M, D, D));
+    else ep.amap = ep.xmap;
+    ep.bias = h->patch_b.p; ep.gate = nullptr; ep.gnext = gmul; ep.ssq = ss;
+    ep.gate_ld = 0; ep.gnext_ld = D; ep.rows_per_sample = h->T; ep.ss_slots = h->SS; ep.x_row_mod = h->T;
+    ep.trace = nullptr;
+    return gemm_auto<EpiResidualDeep>(h->tok2.p, K2, h->patch_w2.p, K2, GemmShape{M, D, K2}, ep, st);
+  }
+  const bool w_smem = patch_embed_smem(h->Kp, h->D, true) <= 100 * 1024;
+  const size_t sm = patch_embed_smem(h->Kp, h->D, w_smem);
+  static PerDeviceOnce attr;
+  if (attr.pending()) {
+    LDMAE_CUDA(cudaFuncSetAttribute(patch_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr.mark();
+  }
+  LDMAE_REQUIRE(sm <= 200 * 1024, "patch embed: patch vector of %d values does not fit shared memory", h->Kp);
+  dim3 grid(cdiv(h->T, kPeTokens), B);
+  patch_embed_kernel<<<grid, 256, sm, st>>>(xs, as, ss, x, h->patch_w.p, h->patch_b.p, h->pos.p, gmul, c.in_channels, c.input_size,
+                                            c.patch_size, h->D, src_mod, h->SS, w_smem ? 1 : 0);
+  LDMAE_LAUNCH_CHECK();
   return LDMAE_OK;
 }
 
@@ -829,11 +892,7 @@ static int dit_forward_generic(ldmae_dit* h, const float* x, float* out, int B, 
   LDMAE_REQUIRE(h->HW == 64, "LayerNorm / GELU variants need head_dim 64");
   {
     ProfScope ps(7, st);
-    dim3 grid(cdiv(T, 32), B);
-    const size_t sm = (32 * static_cast<size_t>(h->Kp) + 256) * sizeof(float);
-    patch_embed_kernel<<<grid, 256, sm, st>>>(h->xres.p, nullptr, nullptr, x, h->patch_w.p, h->patch_b.p, h->pos.p, nullptr,
-                                              c.in_channels, c.input_size, c.patch_size, D, src_mod, h->SS);
-    LDMAE_LAUNCH_CHECK();
+    LDMAE_TRY(launch_patch_embed(h, h->xres.p, nullptr, nullptr, x, nullptr, B, src_mod, st));
   }
   auto norm_mod = [&](int slot) -> int {
     ProfScope ps(7, st);
@@ -959,7 +1018,7 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
     LDMAE_TRY((gemm_store<float, 0>(h->sc.p, D, h->w_ada.p, D, GemmShape{B, h->Ntot, D}, h->mods.p, h->Ntot, h->b_ada.p, st)));
     if (!h->fused) return dit_forward_generic(h, x, out, B, src_mod, st);
     const size_t tot = static_cast<size_t>(h->S) * B * D;
-    adaln_prep_kernel<<<cdiv(tot, 256), 256, 0, st>>>(h->shift_bf16.p, h->gmul.p, h->mods.p, h->norm_w.p,
+    adaln_prep_kernel<<<cdiv(tot, 256), 256, 0, st>>>(tr ? h->shift_bf16.p : nullptr, h->gmul.p, h->mods.p, h->norm_w.p,
                                                       h->slot_shift_off.p, h->slot_scale_off.p, B, D, h->Ntot, h->S);
     LDMAE_LAUNCH_CHECK();
   }
@@ -987,7 +1046,7 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
   auto cvec_q = [&](int i) { return fused_shift ? h->cvec_all.p + static_cast<size_t>(i) * sh_per_blk : h->cvec_qkv.p + static_cast<size_t>(i) * B * 3 * h->QW; };
   auto cvec_m = [&](int i) { return fused_shift ? h->cvec_all.p + static_cast<size_t>(i) * sh_per_blk + 3 * h->QW : h->cvec_12.p + static_cast<size_t>(i) * B * 2 * h->Hp; };
   const int cvq_ld = fused_shift ? h->Nsh : 3 * h->QW, cvm_ld = fused_shift ? h->Nsh : 2 * h->Hp;
-  {
+  if (!fused_shift) {
     ProfScope ps(7, st);
     // final linear (N = p*p*C_out, e.g. 16): fp32 on CUDA cores straight from the shift columns of mods
     dim3 grid(cdiv(h->Nf, 64), cdiv(B, 16));
@@ -1000,11 +1059,7 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
   // 4. patch embed + pos embed -> residual stream, first operand, first row statistics
   {
     ProfScope ps(7, st);
-    dim3 grid(cdiv(T, 32), B);
-    const size_t sm = (32 * static_cast<size_t>(h->Kp) + 256) * sizeof(float);
-    patch_embed_kernel<<<grid, 256, sm, st>>>(Xs(0), As(0), Ss(0), x, h->patch_w.p, h->patch_b.p, h->pos.p,
-                                              h->gmul.p, c.in_channels, c.input_size, c.patch_size, D, src_mod, h->SS);
-    LDMAE_LAUNCH_CHECK();
+    LDMAE_TRY(launch_patch_embed(h, Xs(0), As(0), Ss(0), x, h->gmul.p, B, src_mod, st, tr == nullptr));
     if (tr) {
       LDMAE_REQUIRE(src_mod == B, "training forward takes a plain batch");
       patchify_bf16_kernel<<<cdiv(static_cast<size_t>(M) * h->Kp, 256), 256, 0, st>>>(tr->XTOK.p, x, B, c.in_channels, c.input_size, c.patch_size);
@@ -1105,7 +1160,9 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
   // 6. final layer + unpatchify
   {
     EpiFinal::Params ef;
-    ef.out = out; ef.ssq = Ss(2 * depth); ef.cvec = h->cvec_f.p; ef.cvec_ld = h->Nf; ef.grid = h->G; ef.patch = c.patch_size;
+    ef.out = out; ef.ssq = Ss(2 * depth); ef.grid = h->G; ef.patch = c.patch_size;
+    ef.cvec = fused_shift ? h->cvec_all.p + static_cast<size_t>(depth) * sh_per_blk : h->cvec_f.p;
+    ef.cvec_ld = fused_shift ? h->Nsh : h->Nf;
     ef.cout = c.in_channels * (c.learn_sigma ? 2 : 1); ef.cstore = c.in_channels; ef.rows_per_sample = T; ef.ss_slots = h->SS;
     ef.inv_D = 1.f / D; ef.eps_row = eps;
     ProfScope ps(6, st);

@@ -368,13 +368,13 @@ def test_b1_250_point_cfg10_sampler_vs_fp32_oracle_on_gpu():
 # ------------------------------------------------------------------------------------------------------------------
 # Index work must be bit-exact: patchify / token order / unpatchify (lightningdit.py:376-389,402) and the uint8 NHWC pack
 # ------------------------------------------------------------------------------------------------------------------
-def _index_model(patch):
+def _index_model(patch, S=8):
     """Tiny model whose forward is an exact function of the indices only: every adaLN matrix is zero (gates = 0: the blocks
     leave the stream untouched bit for bit; scale = shift = 0), the patch embedding and the final linear are one-hot
     selections, pos_embed and the biases are zero.  Then  out = unpatchify(patchify(x)) * r = x * r  for a single row factor r
     as long as every token's patch vector has the same sum of squares."""
     from ldmae_b200.models.lightningdit import LightningDiT
-    C, S, D = 16, 8, 128
+    C, D = 16, 128
     m = LightningDiT(input_size=S, patch_size=patch, in_channels=C, hidden_size=D, depth=2, num_heads=2, num_classes=10,
                      use_qknorm=True, use_swiglu=True, use_rope=True, use_rmsnorm=True)
     Kp = C * patch * patch
@@ -420,11 +420,11 @@ def _index_input(B, C, S, patch, Kp):
     return x
 
 
-@pytest.mark.parametrize("patch", [1, 2])
-def test_patchify_token_order_unpatchify_bit_exact(patch):
+@pytest.mark.parametrize("patch,S", [(1, 8), (2, 8), (1, 16), (2, 32)])     # T = 64, 16 (CUDA-core patch embed), 256, 256 (tensor-core route)
+def test_patchify_token_order_unpatchify_bit_exact(patch, S):
     from ldmae_b200 import _lib
-    m, Kp = _index_model(patch)
-    B, C, S, D = 3, 16, 8, 128
+    m, Kp = _index_model(patch, S)
+    B, C, D = 3, 16, 128
     G = S // patch
     T = G * G
     x = _index_input(B, C, S, patch, Kp).cuda()
