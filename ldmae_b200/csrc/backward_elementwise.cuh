@@ -55,14 +55,16 @@ struct ResidBwdParams {
 constexpr int kResidRows = 4;   // rows per warp (8 warps per CTA): 4 keeps the kernel at <= 85 registers, three CTAs per SM
 __global__ void __launch_bounds__(256, 3)
 resid_bwd_kernel(const ResidBwdParams p) {
-  extern __shared__ float s_acc[];              // [3][D]: dg, dgate, sdx
+  // [8 warps][3][D]: dg, dgate, sdx -- every warp visits every 128-column chunk exactly once, so its partial column sums go
+  // into a private row with plain conflict-free 16-byte stores (no shared atomics: 16 M bank-conflict cycles per launch in
+  // round 1's layout, ncu) and are summed over the warps at the end
+  extern __shared__ float s_all[];
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * (8 * kResidRows);
   const int nrows = min(8 * kResidRows, p.T - t0);
   const int D = p.D;
-  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) s_acc[i] = 0.f;
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* s_acc = s_all + static_cast<size_t>(warp) * 3 * D;
   const float* g = p.g + static_cast<size_t>(b) * D;
   const float* gate = p.gate ? p.gate + static_cast<size_t>(b) * p.gate_ld : nullptr;
   const size_t row0 = static_cast<size_t>(b) * p.T + t0 + warp * kResidRows;
@@ -125,18 +127,21 @@ resid_bwd_kernel(const ResidBwdParams p) {
         *reinterpret_cast<uint2*>(p.dy + off) = make_uint2(pack_bf16x2(dn[0] * gt[0], dn[1] * gt[1]), pack_bf16x2(dn[2] * gt[2], dn[3] * gt[3]));
       }
     }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      atomicAdd(&s_acc[c + q], a_dg[q]);
-      if (p.m_prev) atomicAdd(&s_acc[D + c + q], a_gt[q]);
-      if (p.sdx) atomicAdd(&s_acc[2 * D + c + q], a_sd[q]);
-    }
+    *reinterpret_cast<float4*>(s_acc + c) = make_float4(a_dg[0], a_dg[1], a_dg[2], a_dg[3]);
+    *reinterpret_cast<float4*>(s_acc + D + c) = make_float4(a_gt[0], a_gt[1], a_gt[2], a_gt[3]);
+    *reinterpret_cast<float4*>(s_acc + 2 * D + c) = make_float4(a_sd[0], a_sd[1], a_sd[2], a_sd[3]);
   }
   __syncthreads();
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    atomicAdd(p.dg + static_cast<size_t>(b) * D + c, s_acc[c]);
-    if (p.dgate) atomicAdd(p.dgate + static_cast<size_t>(b) * p.dgate_ld + c, s_acc[D + c]);
-    if (p.sdx) atomicAdd(p.sdx + static_cast<size_t>(b) * D + c, s_acc[2 * D + c]);
+    float t0s = 0.f, t1s = 0.f, t2s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const float* r = s_all + static_cast<size_t>(w) * 3 * D;
+      t0s += r[c]; t1s += r[D + c]; t2s += r[2 * D + c];
+    }
+    atomicAdd(p.dg + static_cast<size_t>(b) * D + c, t0s);
+    if (p.dgate) atomicAdd(p.dgate + static_cast<size_t>(b) * p.dgate_ld + c, t1s);
+    if (p.sdx) atomicAdd(p.sdx + static_cast<size_t>(b) * D + c, t2s);
   }
 }
 
@@ -168,108 +173,163 @@ __device__ __forceinline__ float half_warp_sum(float v) {   // sum over the 16 l
   return v;
 }
 
-// One warp = 4 rows x TWO 64-wide heads at a time: a half-warp per head, lane = 4 consecutive dims (two RoPE pairs, one
-// 8-byte access).  One CTA = 32 rows of a sample.
+__device__ __forceinline__ float oct_sum(float v) {   // sum over the 8 lanes that share a head (every lane takes part)
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
+
+// One warp = 4 rows x FOUR 64-wide heads at a time: 8 lanes per head, lane = 8 consecutive dims (four RoPE pairs, one
+// 16-byte access per row and array: half the memory instructions and 3-step instead of 4-step reductions compared with the
+// round-1 layout of 4 dims per lane, which ran at 43 % of the HBM peak -- profiles/r02_c_train_launches.txt).
+// One CTA = 32 rows of a sample.
 constexpr int kQkvRows = 4;     // rows per warp of qkv_bwd_kernel (32-row slab per CTA)
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 qkv_bwd_kernel(const QkvBwdParams p) {
-  extern __shared__ float s_acc[];          // [3D] column sums, then [128] dqw | dkw
+  // Column sums: every warp walks every column group exactly once, so it keeps a PRIVATE row of partial sums in shared
+  // memory, written with plain conflict-free 16-byte stores (two planes of 4 values per lane) and summed over the 8 warps at
+  // the end.  (Shared-memory atomics on a common row cost 43 M bank-conflict cycles per launch -- ncu, round 2 -- and were
+  // the kernel's bottleneck.)  Layout of a warp's row: [group g of 256 columns][plane 0..1][lane][4], then [128] dqw | dkw.
+  extern __shared__ float s_all[];
   const int D = p.D, N = 3 * D;
+  const int NG = (N + 255) / 256 * 256;     // columns rounded up to whole groups
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * (8 * kQkvRows);
   const int nrows = min(8 * kQkvRows, p.T - t0);
-  for (int i = threadIdx.x; i < N + 128; i += blockDim.x) s_acc[i] = 0.f;
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int hh = lane >> 4, l16 = lane & 15;
-  const int d0 = 4 * l16;                                    // first of this lane's 4 dims inside a head
+  float* s_acc = s_all + static_cast<size_t>(warp) * (NG + 128);
+  const int hh = lane >> 3, l8 = lane & 7;
+  const int d0 = 8 * l8;                                     // first of this lane's 8 dims inside a head
   const int heads3 = N / 64;
   const int myrows = max(0, min(kQkvRows, nrows - warp * kQkvRows));       // this warp owns kQkvRows consecutive rows of the slab
   const int tok0 = t0 + warp * kQkvRows;
   const size_t row0 = static_cast<size_t>(b) * p.T + tok0;
-  float rinv[kQkvRows], rc[kQkvRows][2], rs[kQkvRows][2];                         // row factor and this lane's two RoPE angles per row
+  float rinv[kQkvRows];
+  float4 rc[kQkvRows], rs[kQkvRows];                          // this lane's four RoPE angles per row
 #pragma unroll
   for (int i = 0; i < kQkvRows; ++i) {
-    rinv[i] = 0.f; rc[i][0] = rc[i][1] = 1.f; rs[i][0] = rs[i][1] = 0.f;
+    rinv[i] = 0.f; rc[i] = make_float4(1.f, 1.f, 1.f, 1.f); rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (i < myrows) {
       rinv[i] = row_rinv_g(p.ssq, row0 + i, p.slots, 1.f / D, p.eps_row);
       if (p.rope != nullptr) {
         const int axis = d0 >> 5, f = (d0 & 31) >> 1, tok = tok0 + i;     // dims 0..31: token row, 32..63: token column
         const int pos = axis == 0 ? tok / p.G : tok % p.G;
         const float* tab = p.rope + (static_cast<size_t>(axis) * p.G + pos) * 32;
-        rc[i][0] = __ldg(tab + f); rc[i][1] = __ldg(tab + f + 1);
-        rs[i][0] = __ldg(tab + 16 + f); rs[i][1] = __ldg(tab + 16 + f + 1);
+        rc[i] = __ldg(reinterpret_cast<const float4*>(tab + f));
+        rs[i] = __ldg(reinterpret_cast<const float4*>(tab + 16 + f));
       }
     }
   }
-  float wacc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};    // dq_norm.weight / dk_norm.weight partial sums (this lane's dims)
-  for (int hp = 0; hp < heads3; hp += 2) {
-    const int hc = hp + hh;                                  // this half-warp's head
+  float waq[8], wak[8];                                       // dq_norm.weight / dk_norm.weight partial sums (this lane's dims)
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { waq[q] = 0.f; wak[q] = 0.f; }
+  for (int hp = 0; hp < heads3; hp += 4) {
+    const int hc = hp + hh;                                  // this lane group's head
     const bool live = hc < heads3;
     const int col = hc * 64 + d0;
     const int which = live ? (hc * 64) / D : 2;              // 0 q, 1 k, 2 v
     const bool normed = which < 2 && p.qw != nullptr;
-    float wv[4] = {1.f, 1.f, 1.f, 1.f};
-    if (normed) { const float4 w4 = __ldg(reinterpret_cast<const float4*>((which == 0 ? p.qw : p.kw) + d0)); wv[0] = w4.x; wv[1] = w4.y; wv[2] = w4.z; wv[3] = w4.w; }
-    uint2 dyw[kQkvRows], xw[kQkvRows];
+    float wv[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+    if (normed) {
+      const float* wsrc = (which == 0 ? p.qw : p.kw) + d0;
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wsrc)), w1 = __ldg(reinterpret_cast<const float4*>(wsrc + 4));
+      wv[0] = w0.x; wv[1] = w0.y; wv[2] = w0.z; wv[3] = w0.w; wv[4] = w1.x; wv[5] = w1.y; wv[6] = w1.z; wv[7] = w1.w;
+    }
+    uint4 dyw[kQkvRows], xw[kQkvRows];
 #pragma unroll
     for (int i = 0; i < kQkvRows; ++i) {
-      dyw[i] = make_uint2(0u, 0u); xw[i] = make_uint2(0u, 0u);
+      dyw[i] = make_uint4(0u, 0u, 0u, 0u); xw[i] = make_uint4(0u, 0u, 0u, 0u);
       if (i < myrows && live) {
-        dyw[i] = *reinterpret_cast<const uint2*>(p.dqkv + (row0 + i) * N + col);
-        if (normed) xw[i] = *reinterpret_cast<const uint2*>(p.raw + (row0 + i) * 2 * D + col);
+        dyw[i] = *reinterpret_cast<const uint4*>(p.dqkv + (row0 + i) * N + col);
+        if (normed) xw[i] = *reinterpret_cast<const uint4*>(p.raw + (row0 + i) * 2 * D + col);
       }
     }
-    float cs[4] = {0.f, 0.f, 0.f, 0.f};
+    float cs[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) cs[q] = 0.f;
 #pragma unroll
     for (int i = 0; i < kQkvRows; ++i) {
-      const float2 a01 = bf2_to_f2(dyw[i].x), a23 = bf2_to_f2(dyw[i].y);
-      float dy[4] = {a01.x, a01.y, a23.x, a23.y};
+      const uint32_t dwd[4] = {dyw[i].x, dyw[i].y, dyw[i].z, dyw[i].w};
+      const uint32_t xwd[4] = {xw[i].x, xw[i].y, xw[i].z, xw[i].w};
+      const float cq[4] = {rc[i].x, rc[i].y, rc[i].z, rc[i].w}, sq[4] = {rs[i].x, rs[i].y, rs[i].z, rs[i].w};
+      float dy[8], x[8];
+#pragma unroll
+      for (int pr = 0; pr < 4; ++pr) {
+        const float2 a = bf2_to_f2(dwd[pr]), xx = bf2_to_f2(xwd[pr]);
+        dy[2 * pr] = a.x; dy[2 * pr + 1] = a.y; x[2 * pr] = xx.x; x[2 * pr + 1] = xx.y;
+      }
       if (which < 2 && p.rope != nullptr) {
 #pragma unroll
-        for (int pr = 0; pr < 2; ++pr) {                     // transpose of (a,b) -> (a c - b s, b c + a s)
-          const float a = dy[2 * pr] * rc[i][pr] + dy[2 * pr + 1] * rs[i][pr];
-          const float bb = dy[2 * pr + 1] * rc[i][pr] - dy[2 * pr] * rs[i][pr];
+        for (int pr = 0; pr < 4; ++pr) {                     // transpose of (a,b) -> (a c - b s, b c + a s)
+          const float a = dy[2 * pr] * cq[pr] + dy[2 * pr + 1] * sq[pr];
+          const float bb = dy[2 * pr + 1] * cq[pr] - dy[2 * pr] * sq[pr];
           dy[2 * pr] = a; dy[2 * pr + 1] = bb;
         }
       }
-      // head-norm Jacobian; the reductions run in every lane (the two half-warps may hold a normed and a plain head)
-      const float2 x01 = bf2_to_f2(xw[i].x), x23 = bf2_to_f2(xw[i].y);
-      const float x[4] = {x01.x, x01.y, x23.x, x23.y};
-      const float ms = half_warp_sum(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
-      const float hs = rsqrtf(ms * (1.f / 64.f) + p.eps_head);
-      float xh[4], u[4], dot = 0.f;
+      // head-norm Jacobian; the reductions run in every lane (the four lane groups may hold normed and plain heads)
+      float ssx = 0.f;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { xh[q] = x[q] * hs; u[q] = dy[q] * wv[q]; dot = fmaf(u[q], xh[q], dot); }
-      const float mu = half_warp_sum(dot) * (1.f / 64.f);
+      for (int q = 0; q < 8; ++q) ssx = fmaf(x[q], x[q], ssx);
+      const float ms = oct_sum(ssx);
+      const float hs = rsqrtf(ms * (1.f / 64.f) + p.eps_head);
+      float xh[8], u[8], dot = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { xh[q] = x[q] * hs; u[q] = dy[q] * wv[q]; dot = fmaf(u[q], xh[q], dot); }
+      const float mu = oct_sum(dot) * (1.f / 64.f);
       if (normed) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          wacc[which][q] = fmaf(dy[q], xh[q], wacc[which][q]);
+        for (int q = 0; q < 8; ++q) {
+          const float tq = dy[q] * xh[q];
+          waq[q] += which == 0 ? tq : 0.f;                   // (registers: no run-time indexed array)
+          wak[q] += which == 0 ? 0.f : tq;
           dy[q] = hs * (u[q] - xh[q] * mu);
         }
       }
       if (i < myrows && live) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) cs[q] += dy[q];
-        *reinterpret_cast<uint2*>(p.dqkv + (row0 + i) * N + col) =
-            make_uint2(pack_bf16x2(dy[0] * rinv[i], dy[1] * rinv[i]), pack_bf16x2(dy[2] * rinv[i], dy[3] * rinv[i]));
+        for (int q = 0; q < 8; ++q) cs[q] += dy[q];
+        const float r = rinv[i];
+        *reinterpret_cast<uint4*>(p.dqkv + (row0 + i) * N + col) =
+            make_uint4(pack_bf16x2(dy[0] * r, dy[1] * r), pack_bf16x2(dy[2] * r, dy[3] * r), pack_bf16x2(dy[4] * r, dy[5] * r),
+                       pack_bf16x2(dy[6] * r, dy[7] * r));
       }
     }
-    if (live) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) atomicAdd(&s_acc[col + q], cs[q]);
+    {
+      float* dst = s_acc + (hp / 4) * 256 + lane * 4;       // (dead lane groups of a ragged last group store their zeros)
+      *reinterpret_cast<float4*>(dst) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+      *reinterpret_cast<float4*>(dst + 128) = make_float4(cs[4], cs[5], cs[6], cs[7]);
     }
   }
   if (p.qw != nullptr) {
+    // the four lane groups hold partial sums for the same 64 dims: fold them, group 0 stores
 #pragma unroll
-    for (int w = 0; w < 2; ++w)
+    for (int q = 0; q < 8; ++q) {
+      waq[q] += __shfl_xor_sync(0xffffffffu, waq[q], 16); waq[q] += __shfl_xor_sync(0xffffffffu, waq[q], 8);
+      wak[q] += __shfl_xor_sync(0xffffffffu, wak[q], 16); wak[q] += __shfl_xor_sync(0xffffffffu, wak[q], 8);
+    }
+    if (hh == 0) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) atomicAdd(&s_acc[N + w * 64 + d0 + q], wacc[w][q]);
+      for (int q = 0; q < 8; ++q) { s_acc[NG + d0 + q] = waq[q]; s_acc[NG + 64 + d0 + q] = wak[q]; }
+    }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < N; c += blockDim.x) atomicAdd(p.dcvec + static_cast<size_t>(b) * N + c, s_acc[c]);
-  if (p.qw != nullptr && threadIdx.x < 128) atomicAdd((threadIdx.x < 64 ? p.dqw : p.dkw - 64) + threadIdx.x, s_acc[N + threadIdx.x]);
+  for (int i = threadIdx.x; i < NG; i += blockDim.x) {
+    const int g = i >> 8, plane = (i >> 7) & 1, ln = (i >> 2) & 31, j = i & 3;
+    const int c = g * 256 + (ln >> 3) * 64 + (ln & 7) * 8 + plane * 4 + j;
+    if (c < N) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += s_all[static_cast<size_t>(w) * (NG + 128) + i];
+      atomicAdd(p.dcvec + static_cast<size_t>(b) * N + c, t);
+    }
+  }
+  if (p.qw != nullptr && threadIdx.x < 128) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_all[static_cast<size_t>(w) * (NG + 128) + NG + threadIdx.x];
+    atomicAdd((threadIdx.x < 64 ? p.dqw : p.dkw - 64) + threadIdx.x, t);
+  }
 }
 
 // The same for heads in 128-column slots (head_dim hd <= 128, LightningDiT-XL: 72): lane = the adjacent pair (2 lane,
