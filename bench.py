@@ -620,8 +620,17 @@ def run_gpu(args, rank, world, local_rank):
 
     if fits("vmae_decode object", 5.0, not args.no_decode_extra):
         extras["vmae_decode"] = measure_decode(args, dev, vae, world)
-    ms_skip = None
-    if fits("cond_only_when_unguided object", t_job + 3.0, not args.no_cond_only_extra):
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        # required leg: runs even when the budget is tight (reserved above), on a bounded sample
+        threads = os.cpu_count() or 1
+        per_img, t_ode, t_dec, kind = cpu_job(args.cpu_images, args.cpu_points, threads)
+        cpu = {"value": 1.0 / per_img, "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": f"{args.cpu_images} images x {args.cpu_points - 1} CFG evaluations ({'the reference modules' if kind == 'reference' else 'fp32 oracle port of the reference'}, "
+                         f"{t_ode:.1f} s) + VMAE decode ({t_dec:.1f} s), scaled to 249 evaluations"}
+    # the cond-only extension is one more full job and comes last (it is never the headline)
+    run_cond_only = fits("cond_only_when_unguided object", t_job + 3.0 + 25.0 + 40.0, not args.no_cond_only_extra)
+    if run_cond_only:
         job2 = SamplingJob(model, vae, num_steps=args.num_steps, cfg_scale=10.0, cfg_interval_start=0.10, timestep_shift=0.3,
                            cond_only_when_unguided=True)
         z_dev, y_dev = z_host.to(dev), y_host.to(dev)
@@ -638,20 +647,12 @@ def run_gpu(args, rank, world, local_rank):
             "note": "extension, NOT the headline: steps with t < cfg_interval_start evaluate only the conditional half (its guided "
                     "velocity is its own prediction, lightningdit.py:436-439); images identical, 13.7% fewer FLOPs; rank 0's time"}
         del job2
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        # required leg: runs even when the budget is tight (reserved above), on a bounded sample
-        threads = os.cpu_count() or 1
-        per_img, t_ode, t_dec, kind = cpu_job(args.cpu_images, args.cpu_points, threads)
-        cpu = {"value": 1.0 / per_img, "unit": UNIT, "cores": threads, "kind": kind,
-               "sample": f"{args.cpu_images} images x {args.cpu_points - 1} CFG evaluations ({'the reference modules' if kind == 'reference' else 'fp32 oracle port of the reference'}, "
-                         f"{t_ode:.1f} s) + VMAE decode ({t_dec:.1f} s), scaled to 249 evaluations"}
     del job
     if fits("train object", 25.0, not args.no_train):
         extras["train"] = measure_train(args, dev, rank, world, model=model)
     del model, vae
     torch.cuda.empty_cache()
-    if fits("xl_512 object", 90.0, not args.no_xl_extra and world == 1 and args.model == "LightningDiT-B/1"):
+    if fits("xl_512 object", 40.0, not args.no_xl_extra and world == 1 and args.model == "LightningDiT-B/1"):
         extras["xl_512"] = measure_xl(args, dev)
     if rank != 0:
         if world > 1:

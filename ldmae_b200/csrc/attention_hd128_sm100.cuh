@@ -87,7 +87,11 @@ attn_fwd_hd128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn12
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, false, false);
-    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, false, true);
+    // The head occupies a 128-column slot but only its first `hd` columns are non-zero (XL: 72): the contraction of Q.K^T stops
+    // after ceil(hd / 16) of the 8 k-steps and P.V produces ceil(hd / 16) * 16 output columns -- exact (the skipped columns are
+    // zeros), 5/8 of the tensor-core work for head_dim 72.
+    const int ksteps = (p.hd + 15) / 16;
+    const uint32_t idesc_pv = umma_idesc_bf16(128, ksteps * 16, false, true);
     const bool issuer = elect_one();
     const uint64_t d_q0 = umma_smem_desc_sw128(smem_u32(sQ), 1024, 0);
     const uint64_t d_k0 = umma_smem_desc_sw128(smem_u32(sK), 1024, 0);
@@ -99,8 +103,9 @@ attn_fwd_hd128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn12
         for (int a = 0; a < 2; ++a)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16<1>(tmem_base, d_q0 + a * (kA128Atom >> 4) + 2 * k, dk + a * (kA128Atom >> 4) + 2 * k, idesc_qk,
-                         (a | k) != 0 ? 1u : 0u);
+            if (a * 4 + k < ksteps)
+              umma_bf16<1>(tmem_base, d_q0 + a * (kA128Atom >> 4) + 2 * k, dk + a * (kA128Atom >> 4) + 2 * k, idesc_qk,
+                           (a | k) != 0 ? 1u : 0u);
         umma_commit<1>(s_full);
       }
       __syncwarp();
