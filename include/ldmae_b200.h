@@ -81,6 +81,12 @@ int ldmae_dit_backward(ldmae_dit* h, const float* dout, int32_t B, void* stream)
  * re-allocation; ldmae_dit_backward fails with LDMAE_ERR_STATE when its forward is no longer the latest (the reference's
  * autograd graph would keep both alive, models/lightningdit.py:391-418 under train_accum.py:215-230). */
 long long ldmae_dit_generation(ldmae_dit* h);
+/* Batched forms of ldmae_dit_load_tensor / ldmae_dit_grad_read / ldmae_dit_grad_accumulate: n (name, pointer, numel) triples per
+ * call -- the fused trainer moves ~150 tensors each way per optimizer step. */
+int ldmae_dit_load_tensors(ldmae_dit* h, const char* const* names, const float* const* data, const int64_t* numels, int32_t n,
+                           void* stream);
+int ldmae_dit_grad_read_many(ldmae_dit* h, const char* const* names, float* const* dsts, const int64_t* numels, int32_t n,
+                             int32_t accumulate, void* stream);
 /* Class labels (reference nn.Embedding, lightningdit.py:146-169) outside the table are clamped and flagged on the device;
  * the flag is reported by the NEXT call on the handle, or right away by this call (which waits for `stream`). */
 int ldmae_dit_check_labels(ldmae_dit* h, void* stream);

@@ -42,6 +42,8 @@ SYMBOLS = {
     "ldmae_dit_train_forward": (C.c_int, [vp, vp, vp, vp, vp, i32, vp]),
     "ldmae_dit_backward": (C.c_int, [vp, vp, i32, vp]),
     "ldmae_dit_generation": (C.c_longlong, [vp]),
+    "ldmae_dit_load_tensors": (C.c_int, [vp, C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(i64), i32, vp]),
+    "ldmae_dit_grad_read_many": (C.c_int, [vp, C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(i64), i32, i32, vp]),
     "ldmae_dit_check_labels": (C.c_int, [vp, vp]),
     "ldmae_dit_grad_read": (C.c_int, [vp, C.c_char_p, vp, i64, vp]),
     "ldmae_dit_grad_accumulate": (C.c_int, [vp, C.c_char_p, vp, i64, vp]),

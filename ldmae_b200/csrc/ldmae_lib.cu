@@ -721,6 +721,14 @@ extern "C" int ldmae_dit_load_tensor(ldmae_dit* h, const char* name, const float
   return rc;
 }
 
+// n tensors in one call (weight re-upload after every fused optimizer step)
+extern "C" int ldmae_dit_load_tensors(ldmae_dit* h, const char* const* names, const float* const* data, const int64_t* numels,
+                                      int32_t n, void* stream) {
+  LDMAE_REQUIRE(h && names && data && numels && n >= 0, "bad argument");
+  for (int i = 0; i < n; ++i) LDMAE_TRY(ldmae_dit_load_tensor(h, names[i], data[i], numels[i], stream));
+  return LDMAE_OK;
+}
+
 extern "C" int ldmae_dit_finalize(ldmae_dit* h, void* stream) {
   LDMAE_REQUIRE(h, "null handle");
   cudaStream_t st = static_cast<cudaStream_t>(stream);

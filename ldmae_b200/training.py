@@ -119,6 +119,12 @@ class FusedTrainer:
         self.ema = self.flat.clone()                                   # train_accum.py:92 (deepcopy of the fresh model)
         self.step_count = 0
         self.device = dev
+        # (name, pointer, numel) arrays for the batched ABI calls: gradients land in / weights are re-packed from the flat buffers
+        n = len(self.names)
+        self._c_names = (C.c_char_p * n)(*[k.encode() for k in self.names])
+        self._c_numels = (C.c_int64 * n)(*[self.slices[k][1] for k in self.names])
+        self._c_grad_ptrs = (C.c_void_p * n)(*[self.grad.data_ptr() + 4 * self.slices[k][0] for k in self.names])
+        self._c_param_ptrs = (C.c_void_p * n)(*[self.flat.data_ptr() + 4 * self.slices[k][0] for k in self.names])
 
     # -- views ---------------------------------------------------------------------------------
     def grad_of(self, name):
@@ -225,11 +231,8 @@ class FusedTrainer:
             _lib.check(L.ldmae_flow_loss(_lib.ptr(out), _lib.ptr(ut), _lib.ptr(loss), _lib.ptr(dout), float(loss_scale), B,
                                          out[0].numel(), st), "flow_loss")
             _lib.check(L.ldmae_dit_backward(h, _lib.ptr(dout), B, st), "backward")
-            base = self.grad.data_ptr()
-            for k in self.names:
-                off, n, _ = self.slices[k]
-                fetch = L.ldmae_dit_grad_accumulate if accumulate else L.ldmae_dit_grad_read
-                _lib.check(fetch(h, k.encode(), C.c_void_p(base + 4 * off), n, st), f"grad {k}")
+            _lib.check(L.ldmae_dit_grad_read_many(h, self._c_names, self._c_grad_ptrs, self._c_numels, len(self.names),
+                                                  1 if accumulate else 0, st), "grad_read_many")
         return loss, out
 
     def optimizer_step(self):
@@ -241,7 +244,16 @@ class FusedTrainer:
                 _lib.ptr(self.flat), _lib.ptr(self.grad), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), _lib.ptr(self.ema),
                 self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count,
                 self.ema_decay, grad_scale, _lib.stream_ptr()), "adamw_ema_step")
-        self.model.mark_weights_dirty(self.names)                      # parameters changed behind torch's version counters
+        # parameters changed behind torch's version counters: re-pack the library's bf16 copies from the flat buffer in one call
+        m = self.model
+        if m._handle is not None and m._handle_dev == self.device and m._handle_sig is not None:
+            with torch.cuda.device(self.device):
+                st = _lib.stream_ptr()
+                _lib.check(_lib.lib().ldmae_dit_load_tensors(m._handle, self._c_names, self._c_param_ptrs, self._c_numels,
+                                                             len(self.names), st), "load_tensors")
+                _lib.check(_lib.lib().ldmae_dit_finalize(m._handle, st), "ldmae_dit_finalize")
+        else:
+            m.mark_weights_dirty(self.names)
 
     def step_from_moments(self, moments, moments_flip, y, *, latent_mean=None, latent_std=None, latent_multiplier=1.0,
                           flip=None, eps_post=None, t=None, x0=None):
