@@ -509,6 +509,23 @@ def measure_xl(args, dev):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def plan_steps(warmup, steps, t_elapsed, t_step, reserve, budget):
+    """Budget guard: how many warm-up / timed steps still fit after the first warm-up step took `t_step` seconds and
+    `t_elapsed` seconds have passed since process start.  Warm-up is cut first (never below min(warmup, 3)), then timed
+    steps (never below 1).  Returns (warmup, steps, notes)."""
+    notes = []
+    if warmup <= 0 or t_elapsed + (warmup - 1 + steps) * t_step + reserve <= budget:
+        return warmup, steps, notes
+    fit = int((budget - reserve - t_elapsed) // t_step)              # steps (remaining warm-up + timed) that still fit
+    w_new = max(min(warmup, 3), min(warmup, fit - steps + 1))
+    k_new = max(1, min(steps, fit - (w_new - 1)))
+    if w_new != warmup:
+        notes.append(f"{warmup - w_new} warm-up steps (kept {w_new})")
+    if k_new != steps:
+        notes.append(f"{steps - k_new} timed steps (kept {k_new})")
+    return w_new, k_new, notes
+
+
 def run_gpu(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -559,15 +576,8 @@ def run_gpu(args, rank, world, local_rank):
     if W > 0:
         job.run_host(z_host, y_host, out_host)
     t_first, t_el = agree([time.time() - t0, elapsed()])
-    if W > 0 and t_el + (W - 1 + K) * t_first + reserve > args.time_budget:
-        fit = int((args.time_budget - reserve - t_el) // t_first)           # steps (warm-up + timed) that still fit
-        W_new = max(min(W, 3), min(W, fit - K + 1))
-        K_new = max(1, min(K, fit - (W_new - 1)))
-        if W_new != W:
-            budget["skipped"].append(f"{W - W_new} warm-up steps (kept {W_new})")
-        if K_new != K:
-            budget["skipped"].append(f"{K - K_new} timed steps (kept {K_new})")
-        W, K = W_new, K_new
+    W, K, notes = plan_steps(W, K, t_el, t_first, reserve, args.time_budget)
+    budget["skipped"].extend(notes)
     for _ in range(max(0, W - 1)):
         job.run_host(z_host, y_host, out_host)
     barrier()

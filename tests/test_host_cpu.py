@@ -429,3 +429,20 @@ def test_sde_samplers_shapes_last_steps_and_zero_diffusion_limit():
     torch.testing.assert_close(xs[-2], x, rtol=1e-4, atol=1e-5)
     with pytest.raises(NotImplementedError):
         smp.sample_ode_likelihood()
+
+
+def test_bench_budget_guard_cuts_warmup_then_steps():
+    """bench.py's wall-clock budget (the driver's scaling harness allows 870 s per N): nothing is cut when the run fits; warm-up
+    goes first (never below 3), timed steps after that (never below 1)."""
+    import bench
+    assert bench.plan_steps(5, 20, 42.0, 28.0, 50.0, 810.0) == (5, 20, [])                 # 42 + 24*28 + 50 = 764
+    w, k, notes = bench.plan_steps(5, 20, 45.0, 32.0, 50.0, 810.0)                         # would need 863 s
+    assert (w, k) == (3, 20) and notes == ["2 warm-up steps (kept 3)"]
+    assert 45.0 + (w - 1 + k) * 32.0 + 50.0 <= 810.0
+    w, k, notes = bench.plan_steps(5, 20, 60.0, 60.0, 50.0, 810.0)                         # a box twice as slow
+    assert w == 3 and 1 <= k < 20 and 60.0 + (w - 1 + k) * 60.0 + 50.0 <= 810.0 and len(notes) == 2
+    assert bench.plan_steps(3, 2, 500.0, 400.0, 50.0, 810.0)[:2] == (3, 1)                 # never below one timed step
+    assert bench.plan_steps(0, 4, 10.0, 0.0, 0.0, 810.0) == (0, 4, [])
+    per_block, total = bench.dit_flops_per_sample_forward()
+    assert abs(total / 1e9 - 212.74) < 0.05                                                  # BASELINE.md section 3
+    assert abs(bench.vmae_decode_flops_per_image() / 1e9 - 20.70) < 0.05
