@@ -742,20 +742,18 @@ extern "C" int ldmae_dit_finalize(ldmae_dit* h, void* stream) {
     // compact axial table for the QKV epilogue + a check that the loaded [T, 64] buffers really have that structure
     float* maxdiff = h->rope_tab.p + static_cast<size_t>(2) * h->G * 32;
     float md = 0.f;
-    // (one retry after a full synchronisation: the check failed once in round 2, at the first upload of a process running under
-    //  `ncu --set full`, and never again in 300 plain and profiled uploads -- tools/stress_finalize.py)
-    for (int attempt = 0; attempt < 2; ++attempt) {
-      LDMAE_CUDA(cudaMemsetAsync(maxdiff, 0, sizeof(float), st));
-      rope_compact_kernel<<<cdiv(2 * h->G * 32, 128), 128, 0, st>>>(h->rope_tab.p, h->rope_cos.p, h->rope_sin.p, h->G);
-      LDMAE_LAUNCH_CHECK();
-      rope_check_kernel<<<cdiv(static_cast<size_t>(h->T) * 64, 256), 256, 0, st>>>(maxdiff, h->rope_tab.p, h->rope_cos.p, h->rope_sin.p, h->G);
-      LDMAE_LAUNCH_CHECK();
-      LDMAE_CUDA(cudaMemcpyAsync(&md, maxdiff, sizeof(float), cudaMemcpyDeviceToHost, st));
-      LDMAE_CUDA(cudaStreamSynchronize(st));
-      if (md <= 1e-6f) break;
-      LDMAE_CUDA(cudaDeviceSynchronize());
-    }
-    if (!(md <= 1e-6f))
+    LDMAE_CUDA(cudaMemsetAsync(maxdiff, 0, sizeof(float), st));
+    rope_compact_kernel<<<cdiv(2 * h->G * 32, 128), 128, 0, st>>>(h->rope_tab.p, h->rope_cos.p, h->rope_sin.p, h->G);
+    LDMAE_LAUNCH_CHECK();
+    rope_check_kernel<<<cdiv(static_cast<size_t>(h->T) * 64, 256), 256, 0, st>>>(maxdiff, h->rope_tab.p, h->rope_cos.p, h->rope_sin.p, h->G);
+    LDMAE_LAUNCH_CHECK();
+    LDMAE_CUDA(cudaMemcpyAsync(&md, maxdiff, sizeof(float), cudaMemcpyDeviceToHost, st));
+    LDMAE_CUDA(cudaStreamSynchronize(st));
+    // Tolerance: the buffers are computed by the HOST's cos / sin at model construction (models/pos_embed.py:96-133).  On most
+    // hosts equal angles give bit-equal values and the deviation is exactly 0; some GPU boxes of the pool produce tables whose
+    // repeated entries differ by up to 1.5e-4 (deterministically, round 2: bench.py aborted there with the former 1e-6 bound).
+    // That is far below the bf16 resolution of q and k (4e-3); a table with another layout deviates by O(1).
+    if (!(md <= 1e-3f))
       return set_error(LDMAE_ERR_INVALID, "feat_rope.freqs_cos/sin are not the 2-D axial table of models/pos_embed.py:96-133 "
                        "(max deviation %g): unsupported RoPE buffers", md);
   }
