@@ -501,3 +501,25 @@ def test_dopri5_and_sde_through_the_generic_path_vs_oracle(golden_dir):
     e = _rel(a[-1][:n], b[-1][:n])
     print(f"SDE Euler-Maruyama (generic path) final state rel err {e:.3e}")
     assert e < FINAL_TOL
+
+
+def test_benchmark_batch_is_sample_independent_bit_exactly():
+    """Size-independent property at BASELINE configs[1]'s batch (256 images, 512 sample-forwards per evaluation): samples never
+    interact, statistics use no atomics, so the job on the whole batch must equal the job on its two halves bit for bit -- every
+    persistent kernel then runs its many-tiles-per-CTA schedule exactly as in bench.py."""
+    from ldmae_b200.pipeline import SamplingJob, build_sampling_models
+    model, vae = build_sampling_models(torch.device("cuda"), seed=0)
+    job = SamplingJob(model, vae, num_steps=4, cfg_scale=10.0, cfg_interval_start=0.10, timestep_shift=0.3)
+    g = torch.Generator().manual_seed(3)
+    n = 256
+    z = torch.randn(n, 16, 32, 32, generator=g).cuda()
+    y = torch.randint(0, 1000, (n,), generator=g).cuda()
+    whole = job.run_device(z, y)
+    assert whole.shape == (n, 256, 256, 3) and whole.dtype == torch.uint8
+    assert float(whole.float().std()) > 1.0
+    a = job.run_device(z[:128], y[:128])
+    b = job.run_device(z[128:], y[128:])
+    assert torch.equal(whole[:128], a) and torch.equal(whole[128:], b)
+    lat = job.sample_latents(z, y)
+    assert torch.isfinite(lat).all()
+    assert torch.equal(lat[5:6], job.sample_latents(z[5:6], y[5:6]))     # batch of one: single-CTA tile paths, same bits
