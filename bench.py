@@ -500,9 +500,18 @@ def measure_xl(args, dev):
     pk = peaks()
     tfl = fwd * 2 * n * (pts - 1) / (ms / 1e3) / 1e12
     ok = bool(torch.isfinite(lat).all())
+    train = None
+    if args.xl_train:
+        # training step of the same model (BASELINE configs[4] names both): FusedTrainer on `--xl-train-batch` samples per GPU
+        import argparse as _ap
+        del job
+        targs = _ap.Namespace(**vars(args))
+        targs.model, targs.input_size, targs.train_batch, targs.train_steps = "LightningDiT-XL/1", 64, args.xl_train_batch, 3
+        train = measure_train(targs, dev, 0, 1, model=model)
+        job = None
     del job, model, vae
     torch.cuda.empty_cache()
-    return {"metric": "LightningDiT-XL/1 @512px sampling (short grid)", "batch": n, "evaluations": pts - 1, "ms": ms,
+    return {"metric": "LightningDiT-XL/1 @512px sampling (short grid)", "train": train, "batch": n, "evaluations": pts - 1, "ms": ms,
             "tflops_per_gpu": tfl, "frac_of_bf16_peak": tfl / pk["tflops"], "frac_of_bf16_burst_peak": tfl / pk["tflops_burst"] if pk["tflops_burst"] else None,
             "img_per_s_scaled_to_250_points": n / (ms / 1e3 / (pts - 1) * 249), "latents_finite": ok,
             "gpu_launches": _lib.launch_count() - launches0}
@@ -739,6 +748,8 @@ def main():
     ap.add_argument("--no-decode-extra", action="store_true", help="skip the VMAE decode object (BASELINE configs[3])")
     ap.add_argument("--no-cond-only-extra", action="store_true", help="skip the cond-only-below-interval extension (one more job)")
     ap.add_argument("--no-xl-extra", action="store_true", help="skip the short XL/1 @512px sampling run (BASELINE configs[4])")
+    ap.add_argument("--xl-train", action="store_true", help="also time XL/1 @512px training steps inside the xl_512 object (not in the default run)")
+    ap.add_argument("--xl-train-batch", type=int, default=8)
     ap.add_argument("--xl-batch", type=int, default=16)
     ap.add_argument("--xl-points", type=int, default=6)
     ap.add_argument("--cmp-evals", type=int, default=10, help="--impl torch-gpu: evaluations timed per variant")

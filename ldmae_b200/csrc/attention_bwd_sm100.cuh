@@ -195,7 +195,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
     // MMA issuer.  The whole warp runs the control flow (so that descriptors and TMEM addresses stay warp-uniform and live in
     // uniform registers); only the tcgen05 instructions themselves are issued by one elected lane.
     constexpr uint32_t idesc_ss = umma_idesc_bf16(128, 64, false, false);
-    constexpr uint32_t idesc_ts = umma_idesc_bf16(128, HD, false, true);    // B = column tile read MN-major (d contiguous)
+    // wide heads (HD = 128 slots, real head_dim p.hd, e.g. 72): the padding columns are zeros, so the contractions over the head
+    // dimension stop after ceil(hd / 16) k-steps and the accumulations produce ceil(hd / 16) * 16 columns -- exact, 5/8 of the
+    // tensor-core work for head_dim 72 (the epilogue never stores accumulator columns >= hd)
+    const int ksteps = HD == 64 ? 4 : (p.hd + 15) / 16;
+    const uint32_t idesc_ts = umma_idesc_bf16(128, HD == 64 ? 64 : ksteps * 16, false, true);    // B = column tile read MN-major (d contiguous)
     const bool issuer = elect_one();
     // one descriptor per tile; K-steps advance the 14-bit start-address field: +2 (32 B) K-major, +128 (2 KB) MN-major.
     // (The leading-dimension offset is unused in both forms: a single 64-wide swizzle atom along the other dimension.)
@@ -217,12 +221,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
           for (int a = 0; a < kAtoms; ++a)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16<1>(td, d_ra + a * (Geo::kRAtom >> 4) + 2 * k, d_ca + a * (Geo::kCAtom >> 4) + 2 * k, idesc_ss, (a | k) != 0 ? 1u : 0u);
+              if (a * 4 + k < ksteps)
+                umma_bf16<1>(td, d_ra + a * (Geo::kRAtom >> 4) + 2 * k, d_ca + a * (Geo::kCAtom >> 4) + 2 * k, idesc_ss, (a | k) != 0 ? 1u : 0u);
 #pragma unroll
           for (int a = 0; a < kAtoms; ++a)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16<1>(td + 64, d_rb + a * (Geo::kRAtom >> 4) + 2 * k, d_cb + a * (Geo::kCAtom >> 4) + 2 * k, idesc_ss, (a | k) != 0 ? 1u : 0u);
+              if (a * 4 + k < ksteps)
+                umma_bf16<1>(td + 64, d_rb + a * (Geo::kRAtom >> 4) + 2 * k, d_cb + a * (Geo::kCAtom >> 4) + 2 * k, idesc_ss, (a | k) != 0 ? 1u : 0u);
         }
         umma_commit<1>(&sd_full[buf]);
       }
