@@ -24,6 +24,8 @@ struct Attn128Params {
   int T, H, ldo, hd;      // hd = real head_dim (multiple of 8, <= 128)
   int q_col, k_col, v_col;
   float scale_log2;
+  float m0_log2;          // > 0: |score * scale_log2| <= m0_log2 is known (qk-normed heads): the constant replaces the running row
+                          // maximum -- no max pass, no rescaling of O (softmax is shift invariant); <= 0: running maximum
 };
 
 __global__ void __launch_bounds__(kA128Threads, 1)
@@ -165,11 +167,15 @@ attn_fwd_hd128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn12
         for (int i = 0; i < 128; ++i)
           if (i >= kvalid) s[i] = -INFINITY;
       }
-      float m_blk = s[0];
+      const bool fixed = p.m0_log2 > 0.f;                // warp-uniform
+      float m_new = m_used;
+      if (!fixed) {
+        float m_blk = s[0];
 #pragma unroll
-      for (int i = 1; i < 128; ++i) m_blk = fmaxf(m_blk, s[i]);
-      const float m_new = fmaxf(m_used, m_blk);
-      if (j > 0) {
+        for (int i = 1; i < 128; ++i) m_blk = fmaxf(m_blk, s[i]);
+        m_new = fmaxf(m_used, m_blk);
+      }
+      if (j > 0 && !fixed) {
         // O and l follow the running maximum (every block: this variant favours simplicity over the lazy rescale)
         mbar_wait(o_done, (j - 1) & 1, 32);
         __syncwarp();
@@ -190,7 +196,7 @@ attn_fwd_hd128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn12
         }
       }
       m_used = m_new;
-      const float neg = -m_used * p.scale_log2;
+      const float neg = fixed ? -p.m0_log2 : -m_used * p.scale_log2;
       const float2 neg2 = make_float2(neg, neg);
       float2 ls = make_float2(0.f, 0.f);
       uint32_t w[64];
@@ -215,7 +221,8 @@ attn_fwd_hd128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn12
     const float inv_l = 1.f / l_run;
     const int q_tok = qblk * 128 + wq * 32 + lane;
     if (p.lse2 != nullptr && q_tok < p.T)
-      p.lse2[(static_cast<size_t>(b) * p.H + head) * p.T + q_tok] = fmaf(m_used, p.scale_log2, log2f(l_run));
+      p.lse2[(static_cast<size_t>(b) * p.H + head) * p.T + q_tok] =
+          (p.m0_log2 > 0.f ? p.m0_log2 : m_used * p.scale_log2) + log2f(l_run);
     __nv_bfloat16* dst = p.out + static_cast<size_t>(row_base + min(q_tok, p.T - 1)) * p.ldo + head * p.hd;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {

@@ -266,7 +266,7 @@ static int run_attention(const void* qkv, int ldq, void* out, int ldo, int B, in
 
 // Heads stored with a 128-column stride (real head_dim hd <= 128): attention_hd128_sm100.cuh
 static int run_attention_hd128(const void* qkv, int ldq, void* out, int ldo, int B, int T, int H, int hd, int q_col, int k_col,
-                               int v_col, float scale, cudaStream_t st, float* lse2 = nullptr) {
+                               int v_col, float scale, cudaStream_t st, float* lse2 = nullptr, float m0_log2 = -1.f) {
   LDMAE_REQUIRE(hd > 0 && hd <= 128 && hd % 8 == 0, "wide attention: head_dim %d must be a multiple of 8 up to 128", hd);
   CUtensorMap tm;
   LDMAE_TRY(make_tmap_bf16(&tm, qkv, B * T, ldq, ldq, 128));
@@ -279,6 +279,7 @@ static int run_attention_hd128(const void* qkv, int ldq, void* out, int ldo, int
   p.out = static_cast<__nv_bfloat16*>(out); p.lse2 = lse2;
   p.T = T; p.H = H; p.ldo = ldo; p.hd = hd; p.q_col = q_col; p.k_col = k_col; p.v_col = v_col;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.m0_log2 = m0_log2;
   dim3 grid(cdiv(T, 128), H, B);
   attn_fwd_hd128_kernel<<<grid, kA128Threads, kA128SmemBytes, st>>>(tm, p);
   LDMAE_LAUNCH_CHECK();
@@ -762,19 +763,21 @@ extern "C" int ldmae_dit_finalize(ldmae_dit* h, void* stream) {
   for (auto& b : h->blk) b.attn_m0_log2 = -1.f;
   static int fixed = -1;
   if (fixed < 0) { const char* e = getenv("LDMAE_ATTN_FIXED_MAX"); fixed = e ? atoi(e) : 1; }
-  if (h->c.use_qknorm && fixed && h->HW == 64) {
-    const int depth = h->c.depth;
-    std::vector<float> w(static_cast<size_t>(depth) * 128);
+  if (h->c.use_qknorm && h->c.use_rmsnorm && fixed) {
+    // general head_dim: |q| <= sqrt(hd) max|q_norm.w| (RMS over hd, RoPE is a rotation), scale = 1 / sqrt(hd)
+    //   => |q.k| * scale * log2(e) <= sqrt(hd) * log2(e) * max|wq| * max|wk|     (8 * log2(e) ... for head_dim 64)
+    const int depth = h->c.depth, hdr = h->hd;
+    std::vector<float> w(static_cast<size_t>(depth) * 256);
     for (int i = 0; i < depth; ++i) {
-      LDMAE_CUDA(cudaMemcpyAsync(w.data() + i * 128, h->blk[i].qw.p, 64 * sizeof(float), cudaMemcpyDeviceToHost, st));
-      LDMAE_CUDA(cudaMemcpyAsync(w.data() + i * 128 + 64, h->blk[i].kw.p, 64 * sizeof(float), cudaMemcpyDeviceToHost, st));
+      LDMAE_CUDA(cudaMemcpyAsync(w.data() + i * 256, h->blk[i].qw.p, hdr * sizeof(float), cudaMemcpyDeviceToHost, st));
+      LDMAE_CUDA(cudaMemcpyAsync(w.data() + i * 256 + 128, h->blk[i].kw.p, hdr * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     LDMAE_CUDA(cudaStreamSynchronize(st));
     for (int i = 0; i < depth; ++i) {
       float mq = 0.f, mk = 0.f;
-      for (int j = 0; j < 64; ++j) { mq = std::max(mq, std::fabs(w[i * 128 + j])); mk = std::max(mk, std::fabs(w[i * 128 + 64 + j])); }
+      for (int j = 0; j < hdr; ++j) { mq = std::max(mq, std::fabs(w[i * 256 + j])); mk = std::max(mk, std::fabs(w[i * 256 + 128 + j])); }
       // 2 % head-room for the bf16 rounding of q and k; beyond 48 the exponent range [-2 m0, 0] gets uncomfortable
-      const float m0 = 8.f * 1.4426950408889634f * mq * mk * 1.02f;
+      const float m0 = std::sqrt(static_cast<float>(hdr)) * 1.4426950408889634f * mq * mk * 1.02f;
       if (m0 > 0.f && m0 <= 48.f) h->blk[i].attn_m0_log2 = m0;
     }
   }
@@ -1131,7 +1134,7 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
         ProfScope ps(1, st);
         float* lse = tr ? tr->LSE.p + static_cast<size_t>(i) * B * c.num_heads * T : nullptr;
         LDMAE_TRY(run_attention_hd128(qkv_i, 3 * h->QW, o_i, D, B, T, c.num_heads, h->hd, 0, h->QW, 2 * h->QW,
-                                      1.0f / sqrtf(static_cast<float>(h->hd)), st, lse));
+                                      1.0f / sqrtf(static_cast<float>(h->hd)), st, lse, c.use_qknorm ? b.attn_m0_log2 : -1.f));
       }
     }
     LDMAE_DBG_STAGE();
