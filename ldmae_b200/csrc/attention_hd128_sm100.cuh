@@ -16,7 +16,8 @@ constexpr int kA128Threads = 256;
 constexpr int kA128Stages = 2;
 constexpr int kA128Atom = 128 * 128;                 // 128 rows x 64 bf16
 constexpr int kA128Tile = 2 * kA128Atom;             // 128 rows x 128 bf16
-constexpr int kA128SmemBytes = 1024 + kA128Tile + 2 * kA128Stages * kA128Tile + 256;
+constexpr int kA128SmemBytes = 1024 + kA128Tile + 2 * kA128Stages * kA128Tile + 256 + 1024;   // + [2][128] partial row sums (kHalf)
+constexpr int kA128HalfThreads = 384;                // kHalf: eight softmax warps, two threads per query row
 
 struct Attn128Params {
   __nv_bfloat16* out;     // [B*T, ldo], head h at columns h*hd .. h*hd+hd
@@ -28,7 +29,13 @@ struct Attn128Params {
                           // maximum -- no max pass, no rescaling of O (softmax is shift invariant); <= 0: running maximum
 };
 
-__global__ void __launch_bounds__(kA128Threads, 1)
+// kHalf (needs the constant softmax offset, m0_log2 > 0): EIGHT softmax warps, two threads per query row -- warp w and w + 4
+// share the TMEM lanes of 32 rows and take 64 of the block's 128 score columns each.  Without a running maximum the two halves
+// of a row never talk to each other until the row sums are added at the end, and a second warp per SM sub-partition overlaps
+// one warp's tcgen05.ld / FMA / pack / tcgen05.st work with the other's MUFU queue (one warp per sub-partition left the
+// kernel at ~2.4x its MUFU floor).
+template <bool kHalf>
+__global__ void __launch_bounds__(kHalf ? kA128HalfThreads : kA128Threads, 1)
 attn_fwd_hd128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn128Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -46,6 +53,7 @@ attn_fwd_hd128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn12
   uint64_t* p_full = s_free + 1;
   uint64_t* o_done = p_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+  float* lsum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);      // [2][128] (kHalf)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -60,7 +68,7 @@ attn_fwd_hd128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn12
       mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
       mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
     }
-    mbar_init(s_full, 1); mbar_init(s_free, 4); mbar_init(p_full, 4); mbar_init(o_done, 1);
+    mbar_init(s_full, 1); mbar_init(s_free, kHalf ? 8 : 4); mbar_init(p_full, kHalf ? 8 : 4); mbar_init(o_done, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<1>(tmem_slot, 512);
@@ -143,6 +151,74 @@ attn_fwd_hd128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn12
       }
       __syncwarp();
       stage = nstage; phase = nphase;
+    }
+  } else if (kHalf && warp >= 4) {
+    const int wq = warp & 3, half = (warp - 4) >> 2;
+    const uint32_t lane_addr = static_cast<uint32_t>(wq * 32) << 16;
+    const uint32_t tS = tmem_base + lane_addr + half * 64, tP = tmem_base + lane_addr + 128 + half * 32, tO = tmem_base + lane_addr + 192;
+    const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+    const float2 neg2 = make_float2(-p.m0_log2, -p.m0_log2);
+    float l_run = 0.f;
+#pragma unroll 1
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(s_full, j & 1, 30);
+      __syncwarp();
+      tc_fence_after();
+      float s[64];
+      tmem_ld32(tS, s); tmem_ld32(tS + 32, s + 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);
+      const int kvalid = p.T - j * 128 - half * 64;
+      if (kvalid < 64) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i >= kvalid) s[i] = -INFINITY;
+      }
+      float2 ls = make_float2(0.f, 0.f);
+      uint32_t w[32];
+#pragma unroll
+      for (int i = 0; i < 64; i += 2) {
+        const float2 x = fma2(make_float2(s[i], s[i + 1]), sc2, neg2);
+        const float2 e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+        ls = add2(ls, e);
+        w[i >> 1] = pack_bf16x2(e.x, e.y);
+      }
+      l_run += ls.x + ls.y;
+      tmem_st32(tP, w);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    // row sum = the two halves' partial sums (shared memory, one named barrier over the eight softmax warps)
+    lsum[half * 128 + wq * 32 + lane] = l_run;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l_run = lsum[wq * 32 + lane] + lsum[128 + wq * 32 + lane];
+    mbar_wait(o_done, (nkv - 1) & 1, 34);
+    __syncwarp();
+    tc_fence_after();
+    const float inv_l = 1.f / l_run;
+    const int q_tok = qblk * 128 + wq * 32 + lane;
+    if (half == 0 && p.lse2 != nullptr && q_tok < p.T)
+      p.lse2[(static_cast<size_t>(b) * p.H + head) * p.T + q_tok] = p.m0_log2 + log2f(l_run);
+    __nv_bfloat16* dst = p.out + static_cast<size_t>(row_base + min(q_tok, p.T - 1)) * p.ldo + head * p.hd;
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c = half * 2 + cc;                     // this thread's 32-column chunks of O
+      float o[32];
+      tmem_ld32(tO + c * 32, o);
+      tmem_ld_wait();
+      if (q_tok < p.T) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (c * 32 + q * 8 < p.hd)
+            *reinterpret_cast<uint4*>(dst + c * 32 + q * 8) =
+                make_uint4(pack_bf16x2(o[8 * q] * inv_l, o[8 * q + 1] * inv_l), pack_bf16x2(o[8 * q + 2] * inv_l, o[8 * q + 3] * inv_l),
+                           pack_bf16x2(o[8 * q + 4] * inv_l, o[8 * q + 5] * inv_l), pack_bf16x2(o[8 * q + 6] * inv_l, o[8 * q + 7] * inv_l));
+        }
+      }
     }
   } else if (warp >= 4) {
     const int wq = warp & 3;

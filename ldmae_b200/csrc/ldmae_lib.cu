@@ -272,7 +272,8 @@ static int run_attention_hd128(const void* qkv, int ldq, void* out, int ldo, int
   LDMAE_TRY(make_tmap_bf16(&tm, qkv, B * T, ldq, ldq, 128));
   static PerDeviceOnce attr;
   if (attr.pending()) {
-    LDMAE_CUDA(cudaFuncSetAttribute(attn_fwd_hd128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kA128SmemBytes));
+    LDMAE_CUDA(cudaFuncSetAttribute(attn_fwd_hd128_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kA128SmemBytes));
+    LDMAE_CUDA(cudaFuncSetAttribute(attn_fwd_hd128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kA128SmemBytes));
     attr.mark();
   }
   Attn128Params p;
@@ -281,7 +282,10 @@ static int run_attention_hd128(const void* qkv, int ldq, void* out, int ldo, int
   p.scale_log2 = scale * 1.4426950408889634f;
   p.m0_log2 = m0_log2;
   dim3 grid(cdiv(T, 128), H, B);
-  attn_fwd_hd128_kernel<<<grid, kA128Threads, kA128SmemBytes, st>>>(tm, p);
+  static int half = -1;
+  if (half < 0) { const char* e = getenv("LDMAE_ATTN_WIDE_HALF"); half = e ? atoi(e) : 1; }
+  if (m0_log2 > 0.f && half) attn_fwd_hd128_kernel<true><<<grid, kA128HalfThreads, kA128SmemBytes, st>>>(tm, p);
+  else attn_fwd_hd128_kernel<false><<<grid, kA128Threads, kA128SmemBytes, st>>>(tm, p);
   LDMAE_LAUNCH_CHECK();
   return LDMAE_OK;
 }
