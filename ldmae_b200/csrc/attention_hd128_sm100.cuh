@@ -25,6 +25,7 @@ struct Attn128Params {
   int T, H, ldo, hd;      // hd = real head_dim (multiple of 8, <= 128)
   int q_col, k_col, v_col;
   float scale_log2;
+  int poly;               // kHalf: every 4th pair of exponentials on the FMA pipe (degree-3 polynomial) instead of the MUFU unit
   float m0_log2;          // > 0: |score * scale_log2| <= m0_log2 is known (qk-normed heads): the constant replaces the running row
                           // maximum -- no max pass, no rescaling of O (softmax is shift invariant); <= 0: running maximum
 };
@@ -158,6 +159,7 @@ attn_fwd_hd128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn12
     const uint32_t tS = tmem_base + lane_addr + half * 64, tP = tmem_base + lane_addr + 128 + half * 32, tO = tmem_base + lane_addr + 192;
     const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
     const float2 neg2 = make_float2(-p.m0_log2, -p.m0_log2);
+    const bool usepoly = p.poly != 0;
     float l_run = 0.f;
 #pragma unroll 1
     for (int j = 0; j < nkv; ++j) {
@@ -181,7 +183,8 @@ attn_fwd_hd128_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn12
 #pragma unroll
       for (int i = 0; i < 64; i += 2) {
         const float2 x = fma2(make_float2(s[i], s[i + 1]), sc2, neg2);
-        const float2 e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+        // a quarter of the exponentials on the FMA pipe (the MUFU unit, 16 / clk / SM, is the floor of this loop)
+        const float2 e = (usepoly && (i & 6) == 6) ? ex2_poly2(x) : make_float2(ex2_approx(x.x), ex2_approx(x.y));
         ls = add2(ls, e);
         w[i >> 1] = pack_bf16x2(e.x, e.y);
       }

@@ -281,6 +281,10 @@ static int run_attention_hd128(const void* qkv, int ldq, void* out, int ldo, int
   p.T = T; p.H = H; p.ldo = ldo; p.hd = hd; p.q_col = q_col; p.k_col = k_col; p.v_col = v_col;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.m0_log2 = m0_log2;
+  static int poly = -1;
+  // measured on XL/1 @512 (round 2): 741 vs 737 TFLOP/s with / without the polynomial quarter -- inside the noise, so off
+  if (poly < 0) { const char* e = getenv("LDMAE_ATTN_WIDE_POLY"); poly = e ? atoi(e) : 0; }
+  p.poly = poly;
   dim3 grid(cdiv(T, 128), H, B);
   static int half = -1;
   if (half < 0) { const char* e = getenv("LDMAE_ATTN_WIDE_HALF"); half = e ? atoi(e) : 1; }
