@@ -350,7 +350,7 @@ struct EpiResidualT {
       if (gnext != nullptr) stage_vec(vgnext, gnext, n0, BN, g.N, lane);
       __syncwarp();
     }
-    float ss = 0.f;
+    float2 ss2 = make_float2(0.f, 0.f);
     uint8_t* at = c.smem + kAOff;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 64) {
@@ -378,20 +378,21 @@ struct EpiResidualT {
         }
         uint8_t* xp = sw128_chunk(xt + (q >> 3) * kXBytes, lane, q & 7);
         const uint4 xr = ld_tile16(xp);
-        float4 xn;
-        const float m0 = v[4 * q] + bi.x, m1 = v[4 * q + 1] + bi.y, m2 = v[4 * q + 2] + bi.z, m3 = v[4 * q + 3] + bi.w;
+        // packed fp32x2 arithmetic: half the issue slots of the scalar form (this loop is issue/latency-bound with one warp
+        // per SM sub-partition); the row statistics accumulate in two lanes (even / odd columns), summed at the end
+        const float2 m01 = add2(make_float2(v[4 * q], v[4 * q + 1]), make_float2(bi.x, bi.y));
+        const float2 m23 = add2(make_float2(v[4 * q + 2], v[4 * q + 3]), make_float2(bi.z, bi.w));
         if constexpr (kTrain) {
           // 4 bf16 = 8 bytes: half of 16-byte chunk q/2 of the 128-byte row
-          *reinterpret_cast<uint2*>(sw128_chunk(mt, lane, q >> 1) + (q & 1) * 8) = make_uint2(pack_bf16x2(m0, m1), pack_bf16x2(m2, m3));
+          *reinterpret_cast<uint2*>(sw128_chunk(mt, lane, q >> 1) + (q & 1) * 8) = make_uint2(pack_bf16x2(m01.x, m01.y), pack_bf16x2(m23.x, m23.y));
         }
-        xn.x = __uint_as_float(xr.x) + m0 * gt.x;
-        xn.y = __uint_as_float(xr.y) + m1 * gt.y;
-        xn.z = __uint_as_float(xr.z) + m2 * gt.z;
-        xn.w = __uint_as_float(xr.w) + m3 * gt.w;
-        st_tile16(xp, make_uint4(__float_as_uint(xn.x), __float_as_uint(xn.y), __float_as_uint(xn.z), __float_as_uint(xn.w)));
+        const float2 x01 = fma2(m01, make_float2(gt.x, gt.y), make_float2(__uint_as_float(xr.x), __uint_as_float(xr.y)));
+        const float2 x23 = fma2(m23, make_float2(gt.z, gt.w), make_float2(__uint_as_float(xr.z), __uint_as_float(xr.w)));
+        st_tile16(xp, make_uint4(__float_as_uint(x01.x), __float_as_uint(x01.y), __float_as_uint(x23.x), __float_as_uint(x23.y)));
         // columns >= N hold zeros (TMA zero fill + zero bias/acc), so they do not disturb the statistics
-        ss = fmaf(xn.x, xn.x, ss); ss = fmaf(xn.y, xn.y, ss); ss = fmaf(xn.z, xn.z, ss); ss = fmaf(xn.w, xn.w, ss);
-        v[4 * q] = xn.x; v[4 * q + 1] = xn.y; v[4 * q + 2] = xn.z; v[4 * q + 3] = xn.w;
+        ss2 = fma2(x01, x01, ss2);
+        ss2 = fma2(x23, x23, ss2);
+        v[4 * q] = x01.x; v[4 * q + 1] = x01.y; v[4 * q + 2] = x23.x; v[4 * q + 3] = x23.y;
       }
       RES_STAMP(3);
       // every bulk store issued so far (pair seq-1 and older) has read its tiles: the anext tile and the pair buffer the
@@ -407,9 +408,12 @@ struct EpiResidualT {
           float4 g0, g1;
           if constexpr (kStaged) { g0 = lds_f4(vgnext + c0 + 8 * q); g1 = lds_f4(vgnext + c0 + 8 * q + 4); }
           else { g0 = ldvec4(gnext, col, g.N); g1 = ldvec4(gnext, col + 4, g.N); }
+          const float2 a0 = mul2(make_float2(v[8 * q], v[8 * q + 1]), make_float2(g0.x, g0.y));
+          const float2 a1 = mul2(make_float2(v[8 * q + 2], v[8 * q + 3]), make_float2(g0.z, g0.w));
+          const float2 a2 = mul2(make_float2(v[8 * q + 4], v[8 * q + 5]), make_float2(g1.x, g1.y));
+          const float2 a3 = mul2(make_float2(v[8 * q + 6], v[8 * q + 7]), make_float2(g1.z, g1.w));
           st_tile16(sw128_chunk(at, lane, q),
-                 make_uint4(pack_bf16x2(v[8 * q] * g0.x, v[8 * q + 1] * g0.y), pack_bf16x2(v[8 * q + 2] * g0.z, v[8 * q + 3] * g0.w),
-                            pack_bf16x2(v[8 * q + 4] * g1.x, v[8 * q + 5] * g1.y), pack_bf16x2(v[8 * q + 6] * g1.z, v[8 * q + 7] * g1.w)));
+                    make_uint4(pack_bf16x2(a0.x, a0.y), pack_bf16x2(a1.x, a1.y), pack_bf16x2(a2.x, a2.y), pack_bf16x2(a3.x, a3.y)));
         }
       }
       RES_STAMP(5);
@@ -427,7 +431,7 @@ struct EpiResidualT {
     }
     if (p.ssq != nullptr && my_row < g.M) {
       float* dst = p.ssq + static_cast<size_t>(my_row) * p.ss_slots + n0 / 128;
-      dst[0] = ss;
+      dst[0] = ss2.x + ss2.y;
       if (BN > 128 && n0 / 128 + 1 < p.ss_slots) dst[1] = 0.f;
     }
   }
