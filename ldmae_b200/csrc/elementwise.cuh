@@ -153,6 +153,29 @@ __global__ void rope_check_kernel(float* __restrict__ maxdiff, const float* __re
   atomicMax(reinterpret_cast<int*>(maxdiff), __float_as_int(e));
 }
 
+// The same for any head_dim with hd % 8 == 0 (wide heads, LightningDiT-XL's 72): tab[axis][pos][hd/4 x (cos, sin)] -- dims
+// [0, hd/2) rotate with the token's row, [hd/2, hd) with its column, adjacent pairs share an angle.
+__global__ void rope_compact_wide_kernel(float* __restrict__ tab, const float* __restrict__ cosf_, const float* __restrict__ sinf_, int G,
+                                         int hd) {
+  const int w = hd / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * G * w) return;
+  const int is_sin = i & 1, f = (i % w) / 2, pos = (i / w) % G, axis = i / (w * G);
+  const int tok = axis == 0 ? pos * G : pos;
+  tab[i] = (is_sin ? sinf_ : cosf_)[static_cast<size_t>(tok) * hd + axis * w + 2 * f];
+}
+__global__ void rope_check_wide_kernel(float* __restrict__ maxdiff, const float* __restrict__ tab, const float* __restrict__ cosf_,
+                                       const float* __restrict__ sinf_, int G, int hd) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(G) * G * hd) return;
+  const int w = hd / 2;
+  const int d = i % hd, tok = i / hd;
+  const int axis = d / w, pos = axis == 0 ? tok / G : tok % G, f = (d % w) / 2;
+  const float* row = tab + (static_cast<size_t>(axis) * G + pos) * w;
+  const float e = fmaxf(fabsf(cosf_[i] - row[2 * f]), fabsf(sinf_[i] - row[2 * f + 1]));
+  atomicMax(reinterpret_cast<int*>(maxdiff), __float_as_int(e));
+}
+
 // sc = bf16(silu(c))  -- operand of every adaLN_modulation Linear (lightningdit.py:228-236,263-266)
 __global__ void silu_to_bf16_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ in, size_t n) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;

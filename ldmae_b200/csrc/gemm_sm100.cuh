@@ -623,9 +623,15 @@ struct EpiQKV : StoreRing {
 
 // The same QKV epilogue for heads wider than 64 (LightningDiT-XL: head_dim 72): every head occupies 128 accumulator /
 // output columns, the real head_dim `hd` first and zeros behind (the packed weight and bias rows of the padding are zero,
-// so the padded accumulators are exactly 0 and take no part in the statistics).  Two passes over the head's two 64-column
-// halves: sum of squares, then normalise + RoPE + store.  RoPE angles come straight from the reference's [T, hd] tables.
+// so the padded accumulators are exactly 0 and take no part in the statistics).  Two passes over the head (128 fp32 values
+// per thread do not fit the register budget next to the rest of the kernel): sum of squares, then normalise + RoPE + store.
+// Only the 16-column groups of the second half that hold data are read from TMEM and worked on (hd 72: one of four); the
+// per-sample column vector and the norm weight are staged in shared memory; the RoPE angles come from a compact axial table
+// tab[axis][pos][hd/4 x (cos, sin)] (axis 0 = token row for dims < hd/2, axis 1 = token column) held in shared memory
+// -- derived from the reference's [T, hd] buffers and checked against them at load time (ldmae_dit_finalize); buffers without
+// that structure (rope_tab == nullptr) are read element by element from global memory.
 struct EpiQKVWide : StoreRing {
+  static constexpr int kCtaBytes = 10240;
   struct Params {
     CUtensorMap omap;       // out [M, 3 * heads * 128] bf16: box {64, 32}, SWIZZLE_128B
     CUtensorMap rawmap;     // has_raw (training forward): q, k before the head norm [M, 2 * heads * 128] bf16, same box
@@ -637,9 +643,23 @@ struct EpiQKVWide : StoreRing {
     const float* kw;        // [128]
     const float* rope_cos;  // [T, hd] or nullptr
     const float* rope_sin;
+    const float* rope_tab;  // [2, grid, hd/2] interleaved (cos, sin) per angle, or nullptr (hd % 8 != 0 or no axial structure)
+    int grid;
     int section, hd, rows_per_sample, ss_slots;     // section = heads * 128 = width of each of the q | k | v column ranges
     float inv_D, eps_row, eps_head;
   };
+  // row pitch (floats) of the table in shared memory: hd/2, plus 4 when that would put the 16-byte reads of 8 consecutive rows
+  // on the same banks
+  static __device__ __forceinline__ int rope_pitch(const Params& p) { return (p.hd / 2) + (((p.hd / 8) & 1) ? 0 : 4); }
+  static __device__ __forceinline__ bool rope_in_smem(const Params& p) {
+    return p.rope_tab != nullptr && 2 * p.grid * rope_pitch(p) * 4 <= kCtaBytes;
+  }
+  static __device__ __forceinline__ void cta_init(const Params& p, uint8_t* cta, int tid, int nthreads) {
+    if (!rope_in_smem(p)) return;
+    float* dst = reinterpret_cast<float*>(cta);
+    const int w = p.hd / 2, pitch = rope_pitch(p);
+    for (int i = tid; i < 2 * p.grid * w; i += nthreads) dst[(i / w) * pitch + (i % w)] = __ldg(p.rope_tab + i);
+  }
   static __device__ __forceinline__ void prefetch_maps(const Params& p) {
     tma_prefetch_desc(&p.omap);
     if (p.has_raw) tma_prefetch_desc(&p.rawmap);
@@ -647,6 +667,13 @@ struct EpiQKVWide : StoreRing {
   template <int BN>
   static __device__ __forceinline__ void begin(const Params&, const GemmShape&, const TileSched&, const EpiCtx&, State& st) {
     st.seq = 0;
+  }
+  static __device__ __forceinline__ void store_tile(uint8_t* tile, int lane, const float* v) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      st_tile16(sw128_chunk(tile, lane, q),
+                make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                           pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7])));
   }
   template <int BN, int GC>
   static __device__ __forceinline__ void run(const Params& p, const GemmShape& g, const TileSched&, const EpiCtx& c, State& st,
@@ -659,61 +686,127 @@ struct EpiQKVWide : StoreRing {
     const float rinv = row_rinv(p.ssq, my_row, p.ss_slots, p.inv_D, p.eps_row);
     const float* cv = p.cvec + static_cast<size_t>(my_b) * p.cvec_ld;
     const float inv_hd = 1.f / static_cast<float>(p.hd);
+    const bool staged = warp_rows_one_sample(row0, g.M, p.rows_per_sample);
+    float* vcv = reinterpret_cast<float*>(c.smem + kVecOff);       // [128] cvec of the head
+    float* vnw = vcv + 128;                                        // [128] q_norm / k_norm weight of the head
+    const int ng = (p.hd - 64 + 15) >> 4;                          // 16-column groups of the second half that hold data
+    // RoPE table rows of this thread's token: shared memory (pitch rope_pitch) or the global compact table (pitch hd/2)
+    const bool rsm = rope_in_smem(p);
+    const int F2 = p.hd / 2;                                       // floats per axis row = 2 x angles per axis
+    const int rpitch = rsm ? rope_pitch(p) : F2;
+    const float* rbase = rsm ? reinterpret_cast<const float*>(c.cta) : p.rope_tab;
+    const float* r_h = rbase ? rbase + static_cast<size_t>(tok / max(p.grid, 1)) * rpitch : nullptr;
+    const float* r_w = rbase ? rbase + static_cast<size_t>(p.grid + tok % max(p.grid, 1)) * rpitch : nullptr;
+    // angles of head dims d .. d+3 (two adjacent pairs): (cos a, sin a, cos a', sin a')
+    auto angles = [&](int d) -> float4 {
+      const int off = d - (d >= F2 ? F2 : 0);                      // 2 floats per angle, one angle per 2 dims: offset = dim within the axis
+      const float* src = (d >= F2 ? r_w : r_h) + off;
+      return rsm ? lds_f4(src) : __ldg(reinterpret_cast<const float4*>(src));
+    };
+    auto cvec4 = [&](int col_in_head, int colbase) -> float4 {
+      return staged ? lds_f4(vcv + col_in_head) : ldvec4(cv, colbase + col_in_head, g.N);
+    };
 #pragma unroll 1
     for (int c0 = cbase; c0 < cbase + GC; c0 += 128) {
       const int colbase = n0 + c0;
       if (colbase >= g.N) break;
       const int which = colbase / p.section;           // 0 q, 1 k, 2 v
       const bool normed = which < 2 && p.qw != nullptr;
+      const bool roped = which < 2 && p.rope_cos != nullptr;
+      __syncwarp();                                    // the previous head's readers of vcv / vnw are done
+      if (staged) stage_vec(vcv, cv, colbase, 128, g.N, lane);
+      if (normed) *reinterpret_cast<float4*>(vnw + 4 * lane) = __ldg(reinterpret_cast<const float4*>(which == 0 ? p.qw : p.kw) + lane);
+      __syncwarp();
       float hs = 1.f;
       if (normed) {
-        float ms = 0.f;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        float2 ms2 = make_float2(0.f, 0.f);
+        {
           float v[64];
-          tmem_ld32(acc + c0 + half * 64, v);
-          tmem_ld32(acc + c0 + half * 64 + 32, v + 32);
+          tmem_ld32(acc + c0, v);
+          tmem_ld32(acc + c0 + 32, v + 32);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 64; j += 4) {
-            const float4 cc = ldvec4(cv, colbase + half * 64 + j, g.N);
-            const float a0 = fmaf(v[j], rinv, cc.x), a1 = fmaf(v[j + 1], rinv, cc.y), a2 = fmaf(v[j + 2], rinv, cc.z), a3 = fmaf(v[j + 3], rinv, cc.w);
-            ms = fmaf(a0, a0, ms); ms = fmaf(a1, a1, ms); ms = fmaf(a2, a2, ms); ms = fmaf(a3, a3, ms);
+            const float4 cc = cvec4(j, colbase);
+            const float2 a01 = fma2(make_float2(v[j], v[j + 1]), make_float2(rinv, rinv), make_float2(cc.x, cc.y));
+            const float2 a23 = fma2(make_float2(v[j + 2], v[j + 3]), make_float2(rinv, rinv), make_float2(cc.z, cc.w));
+            ms2 = fma2(a01, a01, ms2);
+            ms2 = fma2(a23, a23, ms2);
           }
         }
-        hs = rsqrtf(ms * inv_hd + p.eps_head);
+#pragma unroll
+        for (int gi = 0; gi < 4; ++gi) {
+          if (gi < ng) {
+            float v[16];
+            tmem_ld16(acc + c0 + 64 + 16 * gi, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 cc = cvec4(64 + 16 * gi + j, colbase);
+              const float2 a01 = fma2(make_float2(v[j], v[j + 1]), make_float2(rinv, rinv), make_float2(cc.x, cc.y));
+              const float2 a23 = fma2(make_float2(v[j + 2], v[j + 3]), make_float2(rinv, rinv), make_float2(cc.z, cc.w));
+              ms2 = fma2(a01, a01, ms2);
+              ms2 = fma2(a23, a23, ms2);
+            }
+          }
+        }
+        hs = rsqrtf((ms2.x + ms2.y) * inv_hd + p.eps_head);
       }
-      const float* nw = which == 0 ? p.qw : p.kw;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint8_t* tile = acquire(c, st);
         float v[64];
-        tmem_ld32(acc + c0 + half * 64, v);
-        tmem_ld32(acc + c0 + half * 64 + 32, v + 32);
+        if (half == 0) {
+          tmem_ld32(acc + c0, v);
+          tmem_ld32(acc + c0 + 32, v + 32);
+        } else {
+#pragma unroll
+          for (int gi = 0; gi < 4; ++gi) {
+            if (gi < ng) tmem_ld16(acc + c0 + 64 + 16 * gi, v + 16 * gi);
+            else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[16 * gi + j] = 0.f;
+            }
+          }
+        }
         tmem_ld_wait();
+        const int live = half == 0 ? 64 : 16 * ng;     // columns of this half that can be non-zero
 #pragma unroll
         for (int j = 0; j < 64; j += 4) {
-          const float4 cc = ldvec4(cv, colbase + half * 64 + j, g.N);
-          v[j] = fmaf(v[j], rinv, cc.x); v[j + 1] = fmaf(v[j + 1], rinv, cc.y);
-          v[j + 2] = fmaf(v[j + 2], rinv, cc.z); v[j + 3] = fmaf(v[j + 3], rinv, cc.w);
+          if (j < live) {
+            const float4 cc = cvec4(half * 64 + j, colbase);
+            v[j] = fmaf(v[j], rinv, cc.x); v[j + 1] = fmaf(v[j + 1], rinv, cc.y);
+            v[j + 2] = fmaf(v[j + 2], rinv, cc.z); v[j + 3] = fmaf(v[j + 3], rinv, cc.w);
+          }
         }
         if (which < 2 && p.has_raw) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            st_tile16(sw128_chunk(tile, lane, q),
-                   make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                              pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7])));
+          store_tile(tile, lane, v);
           release(c, st, &p.rawmap, tile, colbase + half * 64, row0);
           tile = acquire(c, st);
         }
+        if (normed) {
 #pragma unroll
-        for (int j = 0; j < 64; j += 4) {
-          if (normed) {
-            const float4 w4 = __ldg(reinterpret_cast<const float4*>(nw + half * 64 + j));
-            v[j] *= hs * w4.x; v[j + 1] *= hs * w4.y; v[j + 2] *= hs * w4.z; v[j + 3] *= hs * w4.w;
+          for (int j = 0; j < 64; j += 4) {
+            if (j < live) {
+              const float4 w4 = lds_f4(vnw + half * 64 + j);
+              v[j] *= hs * w4.x; v[j + 1] *= hs * w4.y; v[j + 2] *= hs * w4.z; v[j + 3] *= hs * w4.w;
+            }
           }
         }
-        if (which < 2 && p.rope_cos != nullptr) {
+        if (roped && rbase != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 64; j += 4) {
+            const int d = half * 64 + j;
+            if (d < p.hd) {                                     // hd % 8 == 0 here: the four dims are inside or outside together
+              const float4 cs = angles(d);
+              const float a0 = v[j], b0 = v[j + 1], a1 = v[j + 2], b1 = v[j + 3];
+              v[j] = a0 * cs.x - b0 * cs.y;                    // t*cos + rotate_half(t)*sin, rotate: (x0,x1)->(-x1,x0)
+              v[j + 1] = b0 * cs.x + a0 * cs.y;
+              v[j + 2] = a1 * cs.z - b1 * cs.w;
+              v[j + 3] = b1 * cs.z + a1 * cs.w;
+            }
+          }
+        } else if (roped) {
           const float* rc = p.rope_cos + static_cast<size_t>(tok) * p.hd;
           const float* rs = p.rope_sin + static_cast<size_t>(tok) * p.hd;
 #pragma unroll
@@ -727,11 +820,7 @@ struct EpiQKVWide : StoreRing {
             }
           }
         }
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          st_tile16(sw128_chunk(tile, lane, q),
-                 make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                            pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7])));
+        store_tile(tile, lane, v);
         release(c, st, &p.omap, tile, colbase + half * 64, row0);
       }
     }

@@ -420,6 +420,7 @@ struct ldmae_dit {
   int hd /*real head_dim*/, HW /*head stride in the qkv buffer: 64, or 128 for wider heads*/, QW /*heads * HW*/;
   // weights
   DevBuf<float> pos, patch_w, patch_b, t_w0, t_b0, t_w2, t_b2, emb, rope_cos, rope_sin, rope_tab, norm_w, b_ada, b_f, w_f32;
+  bool rope_wide_ok = false;   // rope_tab holds the compact table of the wide-head QKV epilogue (checked in finalize)
   DevBuf<__nv_bfloat16> w_ada, w_f;
   std::vector<DitBlockW> blk;
   DevBuf<int> slot_shift_off, slot_scale_off;
@@ -579,7 +580,7 @@ extern "C" int ldmae_dit_create(const ldmae_dit_config* cfg, ldmae_dit** out) {
   A(h->t_w2.alloc(static_cast<size_t>(D) * D)); A(h->t_b2.alloc(D));
   A(h->emb.alloc(static_cast<size_t>(c.num_embeddings) * D));
   A(h->rope_cos.alloc(static_cast<size_t>(h->T) * h->hd)); A(h->rope_sin.alloc(static_cast<size_t>(h->T) * h->hd));
-  A(h->rope_tab.alloc(static_cast<size_t>(2) * h->G * 32 + 1));
+  A(h->rope_tab.alloc(static_cast<size_t>(2) * h->G * (h->hd > 64 ? h->hd / 2 : 32) + 1));
   A(h->norm_w.alloc(static_cast<size_t>(h->S) * D));
   A(h->w_ada.alloc(static_cast<size_t>(h->Ntot) * D)); A(h->b_ada.alloc(h->Ntot));
   A(h->w_f.alloc(static_cast<size_t>(h->Nf) * D)); A(h->b_f.alloc(h->Nf)); A(h->w_f32.alloc(static_cast<size_t>(h->Nf) * D));
@@ -765,6 +766,25 @@ extern "C" int ldmae_dit_finalize(ldmae_dit* h, void* stream) {
     if (!(md <= 1e-3f))
       return set_error(LDMAE_ERR_INVALID, "feat_rope.freqs_cos/sin are not the 2-D axial table of models/pos_embed.py:96-133 "
                        "(max deviation %g): unsupported RoPE buffers", md);
+  }
+  h->rope_wide_ok = false;
+  if (h->c.use_rope && h->HW == 128 && h->hd % 8 == 0) {
+    // wide heads: the same compact table (interleaved cos / sin); buffers without the axial structure keep the element-wise
+    // global reads of the epilogue instead of failing
+    const int w = h->hd / 2;
+    float* maxdiff = h->rope_tab.p + static_cast<size_t>(2) * h->G * w;
+    float md = 0.f;
+    LDMAE_CUDA(cudaMemsetAsync(maxdiff, 0, sizeof(float), st));
+    rope_compact_wide_kernel<<<cdiv(2 * h->G * w, 128), 128, 0, st>>>(h->rope_tab.p, h->rope_cos.p, h->rope_sin.p, h->G, h->hd);
+    LDMAE_LAUNCH_CHECK();
+    rope_check_wide_kernel<<<cdiv(static_cast<size_t>(h->T) * h->hd, 256), 256, 0, st>>>(maxdiff, h->rope_tab.p, h->rope_cos.p,
+                                                                                       h->rope_sin.p, h->G, h->hd);
+    LDMAE_LAUNCH_CHECK();
+    LDMAE_CUDA(cudaMemcpyAsync(&md, maxdiff, sizeof(float), cudaMemcpyDeviceToHost, st));
+    LDMAE_CUDA(cudaStreamSynchronize(st));
+    static int tab_on = -1;
+    if (tab_on < 0) { const char* e = getenv("LDMAE_ROPE_WIDE_TABLE"); tab_on = e ? atoi(e) : 1; }
+    h->rope_wide_ok = md <= 1e-3f && tab_on;
   }
   // Score bound of the qk-normed attention: |q| <= 8 max|q_norm.w|, |k| <= 8 max|k_norm.w| (RMSNorm over 64, RoPE is a
   // rotation), so |q.k| / 8 * log2(e) <= 8 * log2(e) * max|wq| * max|wk|.  Re-evaluated whenever weights are (re)loaded.
@@ -1134,6 +1154,7 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
       eq.ssq = Ss(2 * i); eq.cvec = cvec_q(i); eq.cvec_ld = cvq_ld;
       eq.qw = c.use_qknorm ? b.qw.p : nullptr; eq.kw = c.use_qknorm ? b.kw.p : nullptr;
       eq.rope_cos = c.use_rope ? h->rope_cos.p : nullptr; eq.rope_sin = c.use_rope ? h->rope_sin.p : nullptr;
+      eq.rope_tab = (c.use_rope && h->rope_wide_ok) ? h->rope_tab.p : nullptr; eq.grid = h->G;
       eq.section = h->QW; eq.hd = h->hd; eq.rows_per_sample = T; eq.ss_slots = h->SS;
       eq.inv_D = 1.f / D; eq.eps_row = eps; eq.eps_head = eps;
       { ProfScope ps(0, st); LDMAE_TRY((gemm_auto<EpiQKVWide>(As(2 * i), D, b.w_qkv.p, D, GemmShape{M, 3 * h->QW, D}, eq, st))); }
