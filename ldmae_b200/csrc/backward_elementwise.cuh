@@ -332,9 +332,9 @@ qkv_bwd_kernel(const QkvBwdParams p) {
   }
 }
 
-// The same for heads in 128-column slots (head_dim hd <= 128, LightningDiT-XL: 72): lane = the adjacent pair (2 lane,
-// 2 lane + 1) of each 64-column half of a head; statistics run over the real head_dim (padding columns are zero);
-// RoPE angles come from the reference's [T, hd] tables.
+// The same for heads in 128-column slots (head_dim hd <= 128, LightningDiT-XL: 72); statistics run over the real head_dim
+// (padding columns are zero in dqkv and raw, and are neither read nor written here); RoPE angles come from the reference's
+// [T, hd] tables, staged per row slab in shared memory as (cos, sin) pairs.
 struct QkvBwdWideParams {
   __nv_bfloat16* dqkv;                      // [M, 3 * QW]
   const __nv_bfloat16* raw;                 // [M, 2 * QW]
@@ -347,86 +347,141 @@ struct QkvBwdWideParams {
   float eps_row, eps_head;
 };
 
-__global__ void __launch_bounds__(256)
+// One CTA = a slab of 32 rows of one sample; the WARPS SPLIT THE HEADS, not the rows: warp w takes head pairs w, w + 8, ...
+// (two 128-column heads per pass, 16 lanes per head, lane = 8 consecutive dims, one 16-byte access per row and array) and
+// walks all 32 rows of the slab for them, four rows in flight.  A column therefore belongs to one lane of one warp: its sum
+// over the slab stays in registers and leaves with one global atomic per column and CTA -- no shared-memory accumulators.
+// (Round-2 first version: one warp = one head x one row at a time, 4-byte accesses, two 5-step reductions and scalar RoPE
+// loads per row; it took about two thirds of the XL step's element-wise backward time.)
+constexpr int kQkvWideRows = 32;
+__global__ void __launch_bounds__(256, 2)
 qkv_bwd_wide_kernel(const QkvBwdWideParams p) {
-  extern __shared__ float s_acc[];          // [3 * QW] column sums, then [256] dqw | dkw
+  __shared__ float s_rope[kQkvWideRows][128];   // (cos, sin) of the angle of dims (2a, 2a+1) at [row][2a], [row][2a+1]; identity beyond hd
+  __shared__ float s_rinv[kQkvWideRows];
+  __shared__ float s_w[256];                    // dq_norm.weight | dk_norm.weight partial sums of the CTA
   const int N = 3 * p.QW;
   const int b = blockIdx.y;
-  const int t0 = blockIdx.x * 64;
-  const int nrows = min(64, p.T - t0);
-  for (int i = threadIdx.x; i < N + 256; i += blockDim.x) s_acc[i] = 0.f;
-  __syncthreads();
+  const int t0 = blockIdx.x * kQkvWideRows;
+  const int nrows = min(kQkvWideRows, p.T - t0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t row0 = static_cast<size_t>(b) * p.T + t0;
+  for (int i = threadIdx.x; i < kQkvWideRows * 64; i += blockDim.x) {
+    const int r = i >> 6, a2 = (i & 63) * 2;
+    float cs = 1.f, sn = 0.f;
+    if (p.rope_cos != nullptr && r < nrows && a2 < p.hd) {
+      cs = __ldg(p.rope_cos + static_cast<size_t>(t0 + r) * p.hd + a2);
+      sn = __ldg(p.rope_sin + static_cast<size_t>(t0 + r) * p.hd + a2);
+    }
+    s_rope[r][a2] = cs; s_rope[r][a2 + 1] = sn;
+  }
+  if (threadIdx.x < kQkvWideRows)
+    s_rinv[threadIdx.x] = threadIdx.x < nrows ? row_rinv_g(p.ssq, row0 + threadIdx.x, p.slots, 1.f / p.D, p.eps_row) : 0.f;
+  s_w[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int hh = lane >> 4, l16 = lane & 15;
+  const int d0 = 8 * l16;                                    // first of this lane's 8 dims inside a head
+  const bool dims_live = d0 < p.hd;
   const int heads3 = N / 128;
-  const int myrows = max(0, min(8, nrows - warp * 8));
-  const int tok0 = t0 + warp * 8;
-  const size_t row0 = static_cast<size_t>(b) * p.T + tok0;
   const float inv_hd = 1.f / static_cast<float>(p.hd);
-  float wacc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-  for (int hc = 0; hc < heads3; ++hc) {
-    const int which = (hc * 128) / p.QW;                     // 0 q, 1 k, 2 v
+  float waq[8], wak[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { waq[q] = 0.f; wak[q] = 0.f; }
+  for (int hp = 2 * warp; hp < heads3; hp += 16) {
+    const int hc = hp + hh;                                  // this half-warp's head
+    const bool live = hc < heads3 && dims_live;
+    const int col = hc * 128 + d0;
+    const int which = hc < heads3 ? (hc * 128) / p.QW : 2;   // 0 q, 1 k, 2 v
     const bool normed = which < 2 && p.qw != nullptr;
-    const float* w = which == 0 ? p.qw : p.kw;
-    float wv[4] = {1.f, 1.f, 1.f, 1.f};
-    if (normed) { wv[0] = __ldg(w + lane * 2); wv[1] = __ldg(w + lane * 2 + 1); wv[2] = __ldg(w + 64 + lane * 2); wv[3] = __ldg(w + 65 + lane * 2); }
-    float cs[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int i = 0; i < myrows; ++i) {
-      const size_t row = row0 + i;
-      const int tok = tok0 + i;
-      const float rinv = row_rinv_g(p.ssq, row, p.slots, 1.f / p.D, p.eps_row);
-      __nv_bfloat16* dp = p.dqkv + row * N + hc * 128 + lane * 2;
-      const float2 d0 = bf2_to_f2(*reinterpret_cast<const uint32_t*>(dp));
-      const float2 d1 = bf2_to_f2(*reinterpret_cast<const uint32_t*>(dp + 64));
-      float dy[4] = {d0.x, d0.y, d1.x, d1.y};
-      if (which < 2) {
-        if (p.rope_cos != nullptr) {
+    const bool roped = which < 2 && p.rope_cos != nullptr;
+    float wv[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+    if (normed) {
+      const float* wsrc = (which == 0 ? p.qw : p.kw) + d0;
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wsrc)), w1 = __ldg(reinterpret_cast<const float4*>(wsrc + 4));
+      wv[0] = w0.x; wv[1] = w0.y; wv[2] = w0.z; wv[3] = w0.w; wv[4] = w1.x; wv[5] = w1.y; wv[6] = w1.z; wv[7] = w1.w;
+    }
+    float cs[8];
 #pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            const int d = hf * 64 + lane * 2;
-            if (d < p.hd) {
-              const float c = __ldg(p.rope_cos + static_cast<size_t>(tok) * p.hd + d), sn = __ldg(p.rope_sin + static_cast<size_t>(tok) * p.hd + d);
-              const float a = dy[2 * hf] * c + dy[2 * hf + 1] * sn;        // transpose of (a,b) -> (a c - b s, b c + a s)
-              const float bb = dy[2 * hf + 1] * c - dy[2 * hf] * sn;
-              dy[2 * hf] = a; dy[2 * hf + 1] = bb;
-            }
-          }
-        }
-        if (normed) {
-          const __nv_bfloat16* xp = p.raw + row * 2 * p.QW + hc * 128 + lane * 2;
-          const float2 x0 = bf2_to_f2(*reinterpret_cast<const uint32_t*>(xp));
-          const float2 x1 = bf2_to_f2(*reinterpret_cast<const uint32_t*>(xp + 64));
-          const float x[4] = {x0.x, x0.y, x1.x, x1.y};
-          const float ms = warp_sum(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
-          const float hs = rsqrtf(ms * inv_hd + p.eps_head);
-          float xh[4], u[4], dot = 0.f;
+    for (int q = 0; q < 8; ++q) cs[q] = 0.f;
+#pragma unroll 1
+    for (int rb = 0; rb < kQkvWideRows; rb += 4) {
+      uint4 dyw[4], xw[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) { xh[q] = x[q] * hs; u[q] = dy[q] * wv[q]; dot = fmaf(u[q], xh[q], dot); }
-          const float mu = warp_sum(dot) * inv_hd;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            wacc[which][q] = fmaf(dy[q], xh[q], wacc[which][q]);
-            dy[q] = hs * (u[q] - xh[q] * mu);
-          }
+      for (int i = 0; i < 4; ++i) {
+        dyw[i] = make_uint4(0u, 0u, 0u, 0u); xw[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (rb + i < nrows && live) {
+          dyw[i] = *reinterpret_cast<const uint4*>(p.dqkv + (row0 + rb + i) * N + col);
+          if (normed) xw[i] = *reinterpret_cast<const uint4*>(p.raw + (row0 + rb + i) * 2 * p.QW + col);
         }
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) cs[q] += dy[q];
-      *reinterpret_cast<uint32_t*>(dp) = pack_bf16x2(dy[0] * rinv, dy[1] * rinv);
-      *reinterpret_cast<uint32_t*>(dp + 64) = pack_bf16x2(dy[2] * rinv, dy[3] * rinv);
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t dwd[4] = {dyw[i].x, dyw[i].y, dyw[i].z, dyw[i].w};
+        const uint32_t xwd[4] = {xw[i].x, xw[i].y, xw[i].z, xw[i].w};
+        float dy[8], x[8];
+#pragma unroll
+        for (int pr = 0; pr < 4; ++pr) {
+          const float2 a = bf2_to_f2(dwd[pr]), xx = bf2_to_f2(xwd[pr]);
+          dy[2 * pr] = a.x; dy[2 * pr + 1] = a.y; x[2 * pr] = xx.x; x[2 * pr + 1] = xx.y;
+        }
+        if (roped) {
+          const float4 r0 = *reinterpret_cast<const float4*>(&s_rope[rb + i][d0]);
+          const float4 r1 = *reinterpret_cast<const float4*>(&s_rope[rb + i][d0 + 4]);
+          const float cq[4] = {r0.x, r0.z, r1.x, r1.z}, sq[4] = {r0.y, r0.w, r1.y, r1.w};
+#pragma unroll
+          for (int pr = 0; pr < 4; ++pr) {                   // transpose of (a,b) -> (a c - b s, b c + a s)
+            const float a = dy[2 * pr] * cq[pr] + dy[2 * pr + 1] * sq[pr];
+            const float bb = dy[2 * pr + 1] * cq[pr] - dy[2 * pr] * sq[pr];
+            dy[2 * pr] = a; dy[2 * pr + 1] = bb;
+          }
+        }
+        // head-norm Jacobian; the reductions run in every lane (the two half-warps may hold normed and plain heads)
+        float ssx = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) ssx = fmaf(x[q], x[q], ssx);
+        const float ms = half_warp_sum(ssx);
+        const float hs = rsqrtf(ms * inv_hd + p.eps_head);
+        float xh[8], u[8], dot = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { xh[q] = x[q] * hs; u[q] = dy[q] * wv[q]; dot = fmaf(u[q], xh[q], dot); }
+        const float mu = half_warp_sum(dot) * inv_hd;
+        if (normed) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float tq = dy[q] * xh[q];
+            waq[q] += which == 0 ? tq : 0.f;                 // (registers: no run-time indexed array)
+            wak[q] += which == 0 ? 0.f : tq;
+            dy[q] = hs * (u[q] - xh[q] * mu);
+          }
+        }
+        if (rb + i < nrows && live) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) cs[q] += dy[q];
+          const float r = s_rinv[rb + i];
+          *reinterpret_cast<uint4*>(p.dqkv + (row0 + rb + i) * N + col) =
+              make_uint4(pack_bf16x2(dy[0] * r, dy[1] * r), pack_bf16x2(dy[2] * r, dy[3] * r), pack_bf16x2(dy[4] * r, dy[5] * r),
+                         pack_bf16x2(dy[6] * r, dy[7] * r));
+        }
+      }
     }
-    atomicAdd(&s_acc[hc * 128 + lane * 2], cs[0]); atomicAdd(&s_acc[hc * 128 + lane * 2 + 1], cs[1]);
-    atomicAdd(&s_acc[hc * 128 + 64 + lane * 2], cs[2]); atomicAdd(&s_acc[hc * 128 + 65 + lane * 2], cs[3]);
+    if (live) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) atomicAdd(p.dcvec + static_cast<size_t>(b) * N + col + q, cs[q]);
+    }
   }
   if (p.qw != nullptr) {
+    // the two half-warps hold partial sums for the same 128 dims: fold them, then across the CTA's warps in shared memory
 #pragma unroll
-    for (int wch = 0; wch < 2; ++wch) {
-      atomicAdd(&s_acc[N + wch * 128 + lane * 2], wacc[wch][0]); atomicAdd(&s_acc[N + wch * 128 + lane * 2 + 1], wacc[wch][1]);
-      atomicAdd(&s_acc[N + wch * 128 + 64 + lane * 2], wacc[wch][2]); atomicAdd(&s_acc[N + wch * 128 + 65 + lane * 2], wacc[wch][3]);
+    for (int q = 0; q < 8; ++q) {
+      waq[q] += __shfl_xor_sync(0xffffffffu, waq[q], 16);
+      wak[q] += __shfl_xor_sync(0xffffffffu, wak[q], 16);
     }
+    if (hh == 0 && dims_live) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { atomicAdd(&s_w[d0 + q], waq[q]); atomicAdd(&s_w[128 + d0 + q], wak[q]); }
+    }
+    __syncthreads();
+    if ((threadIdx.x & 127) < p.hd) atomicAdd((threadIdx.x < 128 ? p.dqw : p.dkw - 128) + threadIdx.x, s_w[threadIdx.x]);
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < N; c += blockDim.x) atomicAdd(p.dcvec + static_cast<size_t>(b) * N + c, s_acc[c]);
-  if (p.qw != nullptr) atomicAdd((threadIdx.x < 128 ? p.dqw : p.dkw - 128) + threadIdx.x, s_acc[N + threadIdx.x]);
 }
 
 // dst[sec*nh*hd + h*hd + d, :] = src[sec*nh*hp + h*hp + d, :]  (gradient of a head-padded weight back to the reference rows)

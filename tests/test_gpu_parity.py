@@ -272,6 +272,20 @@ def test_dit_xl_head_dim_72_forward_and_sampler_vs_oracle():
     assert _rel(ours, want) < FINAL_TOL
 
 
+def test_dit_xl_rope_fallback_path_in_a_fresh_process():
+    """The wide-head QKV epilogue reads its RoPE angles from a compact axial table in shared memory; buffers without that
+    structure fall back to element-wise reads of the reference's [T, head_dim] tables.  LDMAE_ROPE_WIDE_TABLE=0 forces the
+    fallback (the switch is read once per process, hence the subprocess): the XL test above must pass on it as well."""
+    import os, subprocess, sys
+    env = dict(os.environ, LDMAE_ROPE_WIDE_TABLE="0")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "tests/test_gpu_parity.py", "-k",
+                        "test_dit_xl_head_dim_72_forward_and_sampler_vs_oracle"], cwd=root, env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "1 passed" in r.stdout
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # The benchmarked configuration itself (BASELINE.json configs[0] / configs[1]): B/1, cfg_scale 10, interval 0.10, shift 0.3
 # ------------------------------------------------------------------------------------------------------------------
