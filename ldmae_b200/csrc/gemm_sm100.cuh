@@ -675,6 +675,41 @@ struct EpiQKVWide : StoreRing {
                 make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
                            pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7])));
   }
+  // 16 live columns followed by 48 zero columns
+  static __device__ __forceinline__ void store_tile16z(uint8_t* tile, int lane, const float* v) {
+    st_tile16(sw128_chunk(tile, lane, 0), make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
+    st_tile16(sw128_chunk(tile, lane, 1), make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15])));
+#pragma unroll
+    for (int q = 2; q < 8; ++q) st_tile16(sw128_chunk(tile, lane, q), make_uint4(0u, 0u, 0u, 0u));
+  }
+  // v[0..NC) = v * rinv + cvec[col0 ..), returns the running (even, odd) sums of squares
+  template <int NC>
+  static __device__ __forceinline__ float2 add_cvec(float* v, const float* vcv, const float* cv, int colbase, int col0, int N, float rinv,
+                                                    bool staged, float2 ms2) {
+    const float2 r2 = make_float2(rinv, rinv);
+#pragma unroll
+    for (int j = 0; j < NC; j += 4) {
+      const float4 cc = staged ? lds_f4(vcv + col0 + j) : ldvec4(cv, colbase + col0 + j, N);
+      const float2 a01 = fma2(make_float2(v[j], v[j + 1]), r2, make_float2(cc.x, cc.y));
+      const float2 a23 = fma2(make_float2(v[j + 2], v[j + 3]), r2, make_float2(cc.z, cc.w));
+      ms2 = fma2(a01, a01, ms2);
+      ms2 = fma2(a23, a23, ms2);
+      v[j] = a01.x; v[j + 1] = a01.y; v[j + 2] = a23.x; v[j + 3] = a23.y;
+    }
+    return ms2;
+  }
+  // v[0..NC) *= hs * weight[col0 ..)
+  template <int NC>
+  static __device__ __forceinline__ void scale_w(float* v, const float* vnw, int col0, float hs) {
+    const float2 h2 = make_float2(hs, hs);
+#pragma unroll
+    for (int j = 0; j < NC; j += 4) {
+      const float4 w4 = lds_f4(vnw + col0 + j);
+      const float2 a01 = mul2(make_float2(v[j], v[j + 1]), mul2(h2, make_float2(w4.x, w4.y)));
+      const float2 a23 = mul2(make_float2(v[j + 2], v[j + 3]), mul2(h2, make_float2(w4.z, w4.w)));
+      v[j] = a01.x; v[j + 1] = a01.y; v[j + 2] = a23.x; v[j + 3] = a23.y;
+    }
+  }
   template <int BN, int GC>
   static __device__ __forceinline__ void run(const Params& p, const GemmShape& g, const TileSched&, const EpiCtx& c, State& st,
                                              uint32_t acc, int row0, int n0, int cbase) {
@@ -698,10 +733,18 @@ struct EpiQKVWide : StoreRing {
     const float* r_h = rbase ? rbase + static_cast<size_t>(tok / max(p.grid, 1)) * rpitch : nullptr;
     const float* r_w = rbase ? rbase + static_cast<size_t>(p.grid + tok % max(p.grid, 1)) * rpitch : nullptr;
     // angles of head dims d .. d+3 (two adjacent pairs): (cos a, sin a, cos a', sin a')
-    auto angles = [&](int d) -> float4 {
-      const int off = d - (d >= F2 ? F2 : 0);                      // 2 floats per angle, one angle per 2 dims: offset = dim within the axis
-      const float* src = (d >= F2 ? r_w : r_h) + off;
+    const float* r_w2 = r_w ? r_w - F2 : nullptr;                   // so that both axes are addressed by the head dim itself
+    auto angles = [&](int d) -> float4 {                           // 2 floats per angle, one angle per 2 dims: offset = dim within the axis
+      const float* src = (d >= F2 ? r_w2 : r_h) + d;
       return rsm ? lds_f4(src) : __ldg(reinterpret_cast<const float4*>(src));
+    };
+    auto rope4 = [&](float* v4, int d) {                           // dims d .. d+3 (two adjacent pairs)
+      const float4 cs = angles(d);
+      const float a0 = v4[0], b0 = v4[1], a1 = v4[2], b1 = v4[3];
+      v4[0] = a0 * cs.x - b0 * cs.y;                               // t*cos + rotate_half(t)*sin, rotate: (x0,x1)->(-x1,x0)
+      v4[1] = b0 * cs.x + a0 * cs.y;
+      v4[2] = a1 * cs.z - b1 * cs.w;
+      v4[3] = b1 * cs.z + a1 * cs.w;
     };
     auto cvec4 = [&](int col_in_head, int colbase) -> float4 {
       return staged ? lds_f4(vcv + col_in_head) : ldvec4(cv, colbase + col_in_head, g.N);
@@ -717,6 +760,43 @@ struct EpiQKVWide : StoreRing {
       if (staged) stage_vec(vcv, cv, colbase, 128, g.N, lane);
       if (normed) *reinterpret_cast<float4*>(vnw + 4 * lane) = __ldg(reinterpret_cast<const float4*>(which == 0 ? p.qw : p.kw) + lane);
       __syncwarp();
+      if (ng == 1 && (!roped || rbase != nullptr)) {
+        // head_dim <= 80 (XL: 72): the head's 80 live columns fit the registers -- ONE pass over the accumulator
+        float v[64], w[16];
+        tmem_ld32(acc + c0, v);
+        tmem_ld32(acc + c0 + 32, v + 32);
+        tmem_ld16(acc + c0 + 64, w);
+        tmem_ld_wait();
+        float2 ms2 = add_cvec<64>(v, vcv, cv, colbase, 0, g.N, rinv, staged, make_float2(0.f, 0.f));
+        ms2 = add_cvec<16>(w, vcv, cv, colbase, 64, g.N, rinv, staged, ms2);
+        if (which < 2 && p.has_raw) {
+          uint8_t* t0 = acquire(c, st);
+          store_tile(t0, lane, v);
+          release(c, st, &p.rawmap, t0, colbase, row0);
+          uint8_t* t1 = acquire(c, st);
+          store_tile16z(t1, lane, w);
+          release(c, st, &p.rawmap, t1, colbase + 64, row0);
+        }
+        if (normed) {
+          const float hs1 = rsqrtf((ms2.x + ms2.y) * inv_hd + p.eps_head);
+          scale_w<64>(v, vnw, 0, hs1);
+          scale_w<16>(w, vnw, 64, hs1);
+        }
+        if (roped) {
+#pragma unroll
+          for (int j = 0; j < 64; j += 4) rope4(v + j, j);
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            if (64 + j < p.hd) rope4(w + j, 64 + j);
+        }
+        uint8_t* t0 = acquire(c, st);
+        store_tile(t0, lane, v);
+        release(c, st, &p.omap, t0, colbase, row0);
+        uint8_t* t1 = acquire(c, st);
+        store_tile16z(t1, lane, w);
+        release(c, st, &p.omap, t1, colbase + 64, row0);
+        continue;
+      }
       float hs = 1.f;
       if (normed) {
         float2 ms2 = make_float2(0.f, 0.f);
@@ -797,14 +877,7 @@ struct EpiQKVWide : StoreRing {
 #pragma unroll
           for (int j = 0; j < 64; j += 4) {
             const int d = half * 64 + j;
-            if (d < p.hd) {                                     // hd % 8 == 0 here: the four dims are inside or outside together
-              const float4 cs = angles(d);
-              const float a0 = v[j], b0 = v[j + 1], a1 = v[j + 2], b1 = v[j + 3];
-              v[j] = a0 * cs.x - b0 * cs.y;                    // t*cos + rotate_half(t)*sin, rotate: (x0,x1)->(-x1,x0)
-              v[j + 1] = b0 * cs.x + a0 * cs.y;
-              v[j + 2] = a1 * cs.z - b1 * cs.w;
-              v[j + 3] = b1 * cs.z + a1 * cs.w;
-            }
+            if (d < p.hd) rope4(v + j, d);                      // hd % 8 == 0 here: the four dims are inside or outside together
           }
         } else if (roped) {
           const float* rc = p.rope_cos + static_cast<size_t>(tok) * p.hd;
