@@ -538,17 +538,21 @@ struct EpiQKV : StoreRing {
       tmem_ld32(acc + c0, v);
       tmem_ld32(acc + c0 + 32, v + 32);
       tmem_ld_wait();
-      float ms = 0.f;
+      // packed fp32x2 arithmetic (half the issue slots); the head's sum of squares runs in two lanes (even / odd columns)
+      float2 ms2 = make_float2(0.f, 0.f);
+      const float2 r2 = make_float2(rinv, rinv);
 #pragma unroll
       for (int j = 0; j < 64; j += 4) {
         float4 cc;
         if constexpr (kFast) cc = lds_f4(vcv + (c0 - cbase) + j);
         else cc = staged ? lds_f4(vcv + (c0 - cbase) + j) : ldvec4(cv, colbase + j, g.N);
-        v[j] = fmaf(v[j], rinv, cc.x); v[j + 1] = fmaf(v[j + 1], rinv, cc.y);
-        v[j + 2] = fmaf(v[j + 2], rinv, cc.z); v[j + 3] = fmaf(v[j + 3], rinv, cc.w);
-        ms = fmaf(v[j], v[j], ms); ms = fmaf(v[j + 1], v[j + 1], ms);
-        ms = fmaf(v[j + 2], v[j + 2], ms); ms = fmaf(v[j + 3], v[j + 3], ms);
+        const float2 a01 = fma2(make_float2(v[j], v[j + 1]), r2, make_float2(cc.x, cc.y));
+        const float2 a23 = fma2(make_float2(v[j + 2], v[j + 3]), r2, make_float2(cc.z, cc.w));
+        ms2 = fma2(a01, a01, ms2);
+        ms2 = fma2(a23, a23, ms2);
+        v[j] = a01.x; v[j + 1] = a01.y; v[j + 2] = a23.x; v[j + 3] = a23.y;
       }
+      const float ms = ms2.x + ms2.y;
       if (which < 2 && p.has_raw) {
         // the head-norm Jacobian of the backward needs the un-normed head
 #pragma unroll
@@ -561,11 +565,14 @@ struct EpiQKV : StoreRing {
       }
       if (which < 2 && p.qw != nullptr && p.qb == nullptr) {
         const float hs = rsqrtf(ms * (1.f / 64.f) + p.eps_head);
+        const float2 h2 = make_float2(hs, hs);
         const float* nw = vnw + which * 64;
 #pragma unroll
         for (int j = 0; j < 64; j += 4) {
           const float4 w4 = lds_f4(nw + j);
-          v[j] *= hs * w4.x; v[j + 1] *= hs * w4.y; v[j + 2] *= hs * w4.z; v[j + 3] *= hs * w4.w;
+          const float2 a01 = mul2(make_float2(v[j], v[j + 1]), mul2(h2, make_float2(w4.x, w4.y)));
+          const float2 a23 = mul2(make_float2(v[j + 2], v[j + 3]), mul2(h2, make_float2(w4.z, w4.w)));
+          v[j] = a01.x; v[j + 1] = a01.y; v[j + 2] = a23.x; v[j + 3] = a23.y;
         }
       }
       if (which < 2 && p.qb != nullptr) {
