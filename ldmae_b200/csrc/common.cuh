@@ -94,7 +94,9 @@ int launch_gemm(const void* a, int lda, const void* w, int ldw, GemmShape g, con
   LDMAE_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, "gemm: leading dimensions must be multiples of 8 (16-byte TMA strides)");
   CUtensorMap ta, tw;
   LDMAE_TRY(make_tmap_bf16(&ta, a, g.M, g.K, lda, kBM));
-  LDMAE_TRY(make_tmap_bf16(&tw, w, g.N, g.K, ldw, Cfg::kLoadBN));
+  LDMAE_REQUIRE(g.n_live == 0 || (g.n_live % 16 == 0 && g.n_live >= 16 && g.n_live <= Cfg::kLoadBN),
+                "gemm: n_live = %d must be a multiple of 16 up to %d", g.n_live, Cfg::kLoadBN);
+  LDMAE_TRY(make_tmap_bf16(&tw, w, g.N, g.K, ldw, g.n_live > 0 ? g.n_live : Cfg::kLoadBN));
   auto kern = gemm_tn_kernel<BN, CG, Epi>;
   static PerDeviceOnce attr_set;
   if (attr_set.pending()) {

@@ -31,6 +31,10 @@ constexpr int kSmemLimit = 232448;   // 227 KB opt-in shared memory per CTA
 
 struct GemmShape {
   int M, N, K;
+  // > 0: only the first n_live of the BN / CG weight rows each CTA owns in a tile are loaded and multiplied (the rest are known
+  // to be zero: head slots wider than the head).  The accumulator then holds CG * n_live columns: CTA r's rows at
+  // [r * n_live, (r + 1) * n_live).  Only epilogues that know about it (EpiQKVWide) may be launched this way.
+  int n_live = 0;
 };
 
 // which tiles this CTA works on, and where this epilogue warp's rows are
@@ -654,6 +658,8 @@ struct EpiQKVWide : StoreRing {
     int grid;
     int section, hd, rows_per_sample, ss_slots;     // section = heads * 128 = width of each of the q | k | v column ranges
     float inv_D, eps_row, eps_head;
+    int acc_stride;         // accumulator columns between consecutive heads of a tile: 128, or GemmShape::n_live when only the live
+                            // weight rows are multiplied
   };
   // row pitch (floats) of the table in shared memory: hd/2, plus 4 when that would put the 16-byte reads of 8 consecutive rows
   // on the same banks
@@ -760,6 +766,7 @@ struct EpiQKVWide : StoreRing {
     for (int c0 = cbase; c0 < cbase + GC; c0 += 128) {
       const int colbase = n0 + c0;
       if (colbase >= g.N) break;
+      const uint32_t hacc = acc + (c0 >> 7) * p.acc_stride;   // this head's accumulator columns
       const int which = colbase / p.section;           // 0 q, 1 k, 2 v
       const bool normed = which < 2 && p.qw != nullptr;
       const bool roped = which < 2 && p.rope_cos != nullptr;
@@ -770,9 +777,9 @@ struct EpiQKVWide : StoreRing {
       if (ng == 1 && (!roped || rbase != nullptr)) {
         // head_dim <= 80 (XL: 72): the head's 80 live columns fit the registers -- ONE pass over the accumulator
         float v[64], w[16];
-        tmem_ld32(acc + c0, v);
-        tmem_ld32(acc + c0 + 32, v + 32);
-        tmem_ld16(acc + c0 + 64, w);
+        tmem_ld32(hacc, v);
+        tmem_ld32(hacc + 32, v + 32);
+        tmem_ld16(hacc + 64, w);
         tmem_ld_wait();
         float2 ms2 = add_cvec<64>(v, vcv, cv, colbase, 0, g.N, rinv, staged, make_float2(0.f, 0.f));
         ms2 = add_cvec<16>(w, vcv, cv, colbase, 64, g.N, rinv, staged, ms2);
@@ -809,8 +816,8 @@ struct EpiQKVWide : StoreRing {
         float2 ms2 = make_float2(0.f, 0.f);
         {
           float v[64];
-          tmem_ld32(acc + c0, v);
-          tmem_ld32(acc + c0 + 32, v + 32);
+          tmem_ld32(hacc, v);
+          tmem_ld32(hacc + 32, v + 32);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 64; j += 4) {
@@ -825,7 +832,7 @@ struct EpiQKVWide : StoreRing {
         for (int gi = 0; gi < 4; ++gi) {
           if (gi < ng) {
             float v[16];
-            tmem_ld16(acc + c0 + 64 + 16 * gi, v);
+            tmem_ld16(hacc + 64 + 16 * gi, v);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
@@ -844,12 +851,12 @@ struct EpiQKVWide : StoreRing {
         uint8_t* tile = acquire(c, st);
         float v[64];
         if (half == 0) {
-          tmem_ld32(acc + c0, v);
-          tmem_ld32(acc + c0 + 32, v + 32);
+          tmem_ld32(hacc, v);
+          tmem_ld32(hacc + 32, v + 32);
         } else {
 #pragma unroll
           for (int gi = 0; gi < 4; ++gi) {
-            if (gi < ng) tmem_ld16(acc + c0 + 64 + 16 * gi, v + 16 * gi);
+            if (gi < ng) tmem_ld16(hacc + 64 + 16 * gi, v + 16 * gi);
             else {
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[16 * gi + j] = 0.f;
@@ -1120,6 +1127,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // an ELECT / R2UR.BROADCAST / BRA.U.ANY convergence loop)
     {
       const bool issuer = elect_one();
+      const uint32_t b_bytes = g.n_live > 0 ? static_cast<uint32_t>(g.n_live) * kBK * 2 : static_cast<uint32_t>(Cfg::kBBytes);
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
@@ -1133,11 +1141,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           void* db = smem_b + stage * Cfg::kBBytesPadded;
           if (issuer) {
             if constexpr (CG == 1) {
-              mbar_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::kBBytes);
+              mbar_expect_tx(&full_bar[stage], Cfg::kABytes + b_bytes);
               tma_load_2d(&tmap_a, &full_bar[stage], da, kb * kBK, row_a);
               tma_load_2d(&tmap_w, &full_bar[stage], db, kb * kBK, row_w);
             } else {
-              if (leader) mbar_expect_tx(&full_bar[stage], 2 * (Cfg::kABytes + Cfg::kBBytes));
+              if (leader) mbar_expect_tx(&full_bar[stage], 2 * (Cfg::kABytes + b_bytes));
               else mbar_arrive_cluster(&full_bar[stage], 0);
               tma_load_2d_pair(&tmap_a, &full_bar[stage], da, kb * kBK, row_a);
               tma_load_2d_pair(&tmap_w, &full_bar[stage], db, kb * kBK, row_w);
@@ -1161,7 +1169,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // margin of the tensor pipe's, ncu: 64-70 % active) -- the same finding as in the attention kernels.
     if (leader) {
       const bool issuer = elect_one();
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM * CG, BN);
+      const uint32_t idesc = umma_idesc_bf16(kBM * CG, g.n_live > 0 ? CG * g.n_live : BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;

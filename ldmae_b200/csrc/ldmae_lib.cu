@@ -1157,7 +1157,18 @@ static int dit_forward_impl(ldmae_dit* h, const float* x, const float* t, float 
       eq.rope_tab = (c.use_rope && h->rope_wide_ok) ? h->rope_tab.p : nullptr; eq.grid = h->G;
       eq.section = h->QW; eq.hd = h->hd; eq.rows_per_sample = T; eq.ss_slots = h->SS;
       eq.inv_D = 1.f / D; eq.eps_row = eps; eq.eps_head = eps;
-      { ProfScope ps(0, st); LDMAE_TRY((gemm_auto<EpiQKVWide>(As(2 * i), D, b.w_qkv.p, D, GemmShape{M, 3 * h->QW, D}, eq, st))); }
+      {
+        // multiply only the live rows of every 128-row head slot of the packed weight (the rest are zeros): 16 * ceil(hd / 16)
+        // of 128 -- the two-CTA tile (one head slot per CTA) then has N = 2 * n_live; LDMAE_QKV_WIDE_LIVE=0 keeps N = 256
+        static int live_on = -1;
+        if (live_on < 0) { const char* e = getenv("LDMAE_QKV_WIDE_LIVE"); live_on = e ? atoi(e) : 1; }
+        GemmShape gs{M, 3 * h->QW, D};
+        const bool two_cta = gemm_cg() == 2 && M > 128;
+        if (live_on && two_cta) gs.n_live = 16 * ((h->hd + 15) / 16);
+        eq.acc_stride = gs.n_live > 0 ? gs.n_live : 128;
+        ProfScope ps(0, st);
+        LDMAE_TRY((gemm_auto<EpiQKVWide>(As(2 * i), D, b.w_qkv.p, D, gs, eq, st)));
+      }
       LDMAE_DBG_STAGE();
       {
         ProfScope ps(1, st);
