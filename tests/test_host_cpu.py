@@ -405,6 +405,40 @@ def test_generic_ode_solvers_on_analytic_problems():
         smp.sample_ode(sampling_method="bosh3")
 
 
+def test_dopri5_restatement_against_scipy_rk45():
+    """torchdiffeq is un-vendored and absent here, so the adaptive solver is restated from the published algorithm (transport.py
+    docstring).  SciPy's RK45 is an independent implementation of the same Dormand-Prince 5(4) pair with the same RMS error norm,
+    Hairer initial step and 0.9 / 0.2 / 10 step controller (it differs only in when an accepted step may shrink and in its
+    dense-output polynomial): on a forced van der Pol system both must use about the same number of right-hand-side evaluations
+    and land equally far from a 1e-12 DOP853 solution, at the reference's default tolerances and at tight ones."""
+    import numpy as np
+    import torch
+    integrate = pytest.importorskip("scipy.integrate")
+    from ldmae_b200.transport.transport import _dopri5_odeint
+
+    def rhs_np(t, y):
+        y = y.reshape(2, 2)
+        return np.stack([y[:, 1], (1 - y[:, 0] ** 2) * y[:, 1] - y[:, 0] + np.sin(3 * t)], 1).reshape(-1)
+
+    calls = [0]
+
+    def rhs_t(t, y):
+        calls[0] += 1
+        return torch.stack([y[:, 1], (1 - y[:, 0] ** 2) * y[:, 1] - y[:, 0] + np.sin(3 * t)], 1)
+
+    y0 = torch.tensor([[1.0, 0.0], [-0.5, 2.0]], dtype=torch.float64)
+    t = torch.linspace(0, 4, 17, dtype=torch.float64)
+    exact = integrate.solve_ivp(rhs_np, (0, 4), y0.numpy().reshape(-1), method="DOP853", t_eval=t.numpy(), rtol=1e-12, atol=1e-14).y.T
+    for rtol, atol in ((1e-3, 1e-6), (1e-7, 1e-9)):           # (reference defaults transport.py:404-405, tight)
+        calls[0] = 0
+        ours = _dopri5_odeint(rhs_t, y0, t, rtol, atol).numpy().reshape(17, 4)
+        sp = integrate.solve_ivp(rhs_np, (0, 4), y0.numpy().reshape(-1), method="RK45", t_eval=t.numpy(), rtol=rtol, atol=atol)
+        assert abs(calls[0] - sp.nfev) <= 0.15 * sp.nfev, (calls[0], sp.nfev)
+        e_ours, e_sp = np.abs(ours - exact).max(), np.abs(sp.y.T - exact).max()
+        assert e_ours < 4 * e_sp + 1e-12 and e_ours < 60 * rtol, (rtol, e_ours, e_sp)
+        assert np.abs(ours - sp.y.T).max() < 40 * rtol
+
+
 def test_sde_samplers_shapes_last_steps_and_zero_diffusion_limit():
     """Sampler.sample_sde (transport.py:285-396): num_steps states, the four last-step rules, and with a vanishing diffusion
     norm Euler-Maruyama reduces to the Euler ODE step on the same grid."""
