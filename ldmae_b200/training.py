@@ -97,10 +97,36 @@ def reduce_gradients(grad, group=None):
     return 1.0 / world
 
 
+def clip_flat_gradient_(grad, max_norm, grad_scale=1.0):
+    """``accelerator.clip_grad_norm_(model.parameters(), max_grad_norm)`` of train_accum.py:235-238 (torch.nn.utils.clip_grad_norm_,
+    2-norm over all gradients, coefficient ``max_norm / (total + 1e-6)`` clamped to 1) on the flat gradient buffer, in place and
+    without a host sync.  ``grad`` holds the SUM over ranks and ``grad_scale`` the 1 / world the optimizer kernel applies when it
+    reads it, so the norm of the averaged gradient is ``grad_scale * |grad|`` (the 16-byte padding between slices is zero).
+    Returns the total norm (0-d tensor) like the reference call."""
+    total = torch.linalg.vector_norm(grad.float(), 2) * grad_scale
+    grad.mul_(torch.clamp(float(max_norm) / (total + 1e-6), max=1.0))
+    return total
+
+
+def cosine_loss_terms(out, ut, loss_scale=1.0):
+    """The optional cosine term of the reference's loss (transport.py:196-197, train_accum.py:216-223 with use_cosine_loss):
+    ``cos_loss = mean_flat(1 - cosine_similarity(out, ut, dim=1))`` per sample and the gradient of ``cos_loss.mean() *
+    loss_scale`` with respect to ``out`` (added to the MSE term's ``dout``).  No shipped config enables it, so it is host-side
+    PyTorch on the model output rather than part of the fused loss kernel."""
+    o = out.detach().requires_grad_(True)
+    with torch.enable_grad():
+        cos = torch.mean(1 - torch.nn.functional.cosine_similarity(o, ut, dim=1), dim=list(range(1, o.dim() - 1)))
+        g, = torch.autograd.grad(cos.mean() * loss_scale, o)
+    return cos.detach(), g
+
+
 class FusedTrainer:
     def __init__(self, model, *, lr=2e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.0, ema_decay=0.9999, transport=None,
-                 process_group=None):
+                 process_group=None, max_grad_norm=None):
         self.model = model
+        self.max_grad_norm = None if max_grad_norm is None else float(max_grad_norm)   # train_accum.py:235 (config: optimizer.max_grad_norm)
+        self.last_grad_norm = None
+        self.last_cos_loss = None
         self.lr, self.betas, self.eps, self.weight_decay, self.ema_decay = float(lr), betas, float(eps), float(weight_decay), float(ema_decay)
         self.transport = transport or create_transport("Linear", "velocity", None, None, None, use_cosine_loss=False,
                                                        use_lognorm=True)
@@ -230,6 +256,10 @@ class FusedTrainer:
             # loss = mean_flat((out - ut)^2); dout = d (mean(loss) * loss_scale) / d out  -- one pass (ldmae_flow_loss)
             _lib.check(L.ldmae_flow_loss(_lib.ptr(out), _lib.ptr(ut), _lib.ptr(loss), _lib.ptr(dout), float(loss_scale), B,
                                          out[0].numel(), st), "flow_loss")
+            if self.transport.use_cosine_loss:
+                # train_accum.py:216-218: loss = cos_loss.mean() + mse.mean(); the per-sample MSE stays what step() returns
+                self.last_cos_loss, dcos = cosine_loss_terms(out, ut, loss_scale)
+                dout.add_(dcos)
             _lib.check(L.ldmae_dit_backward(h, _lib.ptr(dout), B, st), "backward")
             _lib.check(L.ldmae_dit_grad_read_many(h, self._c_names, self._c_grad_ptrs, self._c_numels, len(self.names),
                                                   1 if accumulate else 0, st), "grad_read_many")
@@ -238,6 +268,8 @@ class FusedTrainer:
     def optimizer_step(self):
         """all-reduce (mean) + AdamW + EMA on the flat buffers; marks the library's bf16 weight copies stale."""
         grad_scale = reduce_gradients(self.grad, self.pg)
+        if self.max_grad_norm is not None:
+            self.last_grad_norm = clip_flat_gradient_(self.grad, self.max_grad_norm, grad_scale)
         self.step_count += 1
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().ldmae_adamw_ema_step(

@@ -378,6 +378,48 @@ def test_fused_optimizer_state_round_trips_through_torch_adamw():
         assert torch.equal(lay.view(ea2, k), lay.view(ea, k)) and torch.equal(lay.view(es2, k), lay.view(es, k))
 
 
+def test_flat_gradient_clipping_matches_torch_clip_grad_norm():
+    """FusedTrainer(max_grad_norm=...) (train_accum.py:235-238): clipping the flat SUM-over-ranks buffer with the 1/world factor
+    still pending equals torch.nn.utils.clip_grad_norm_ on the averaged per-parameter gradients, above and below the threshold."""
+    import torch
+    from ldmae_b200.training import FlatLayout, clip_flat_gradient_
+    torch.manual_seed(3)
+    m = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))           # 35 + 7 + 21 + 3: slices need padding
+    lay = FlatLayout(m)
+    world = 4
+    for max_norm in (0.05, 1e3):
+        for k in lay.names:
+            lay.view(lay.grad, k).copy_(torch.randn(lay.slices[k][2]))
+        ref_params = [torch.nn.Parameter(lay.view(lay.flat, k).clone()) for k in lay.names]
+        for p, k in zip(ref_params, lay.names):
+            p.grad = lay.view(lay.grad, k).clone() / world                             # what DDP would have left in .grad
+        want_norm = torch.nn.utils.clip_grad_norm_(ref_params, max_norm)
+        got_norm = clip_flat_gradient_(lay.grad, max_norm, 1.0 / world)
+        torch.testing.assert_close(got_norm, want_norm)
+        for p, k in zip(ref_params, lay.names):
+            torch.testing.assert_close(lay.view(lay.grad, k) / world, p.grad)
+        assert (float(want_norm) > max_norm) == (max_norm < 1.0)
+
+
+def test_cosine_loss_term_matches_reference_expression():
+    """use_cosine_loss (transport.py:196-197; train_accum.py:216-223): per-sample cos_loss and the extra d/d(out) the fused
+    trainer adds to the MSE kernel's dout, against autograd through the reference expression of the combined loss."""
+    import torch
+    from ldmae_b200.training import cosine_loss_terms
+    from ldmae_b200.transport.transport import mean_flat
+    g = torch.Generator().manual_seed(5)
+    out = torch.randn(3, 4, 6, 6, generator=g, requires_grad=True)
+    ut = torch.randn(3, 4, 6, 6, generator=g)
+    gas = 2
+    mse = mean_flat((out - ut) ** 2)
+    cos = mean_flat(1 - torch.nn.functional.cosine_similarity(out, ut, dim=1))
+    ((cos.mean() + mse.mean()) / gas).backward()
+    got_cos, dcos = cosine_loss_terms(out.detach(), ut, 1.0 / gas)
+    dmse = 2 * (out.detach() - ut) / out[0].numel() / out.shape[0] / gas                # what ldmae_flow_loss writes
+    torch.testing.assert_close(got_cos, cos.detach())
+    torch.testing.assert_close(dmse + dcos, out.grad)
+
+
 # ----------------------------------------------------------------------------- generic samplers (host-side loops)
 def test_generic_ode_solvers_on_analytic_problems():
     """The loops that serve arbitrary model callables (transport.py:398-443 / integrators.py:77-126 with torchdiffeq restated):
