@@ -241,6 +241,45 @@ def test_fused_trainer_step_matches_autograd_plus_torch_adamw():
     assert _rel(out, ref_out) < 1e-2
 
 
+def test_fused_trainer_cosine_loss_and_gradient_clipping():
+    """The loop's two optional terms (train_accum.py:216-218 with use_cosine_loss, :235-238 with optimizer.max_grad_norm):
+    the flat gradient of (cos_loss.mean() + mse.mean()) against oracle autograd, and the clipped gradient / reported norm
+    against torch.nn.utils.clip_grad_norm_ on the oracle's gradients."""
+    from ldmae_b200.training import FusedTrainer
+    from ldmae_b200.transport import create_transport
+    spec, sd, m = _tiny(1, 61)
+    g = torch.Generator().manual_seed(78)
+    B = 4
+    x1 = torch.randn(B, 16, 8, 8, generator=g); x0 = torch.randn(B, 16, 8, 8, generator=g)
+    t = torch.rand(B, generator=g); y = torch.randint(0, 10, (B,), generator=g)
+    leaves = {k: v.clone().requires_grad_(v.is_floating_point() and k != "pos_embed" and not k.startswith("feat_rope"))
+              for k, v in sd.items()}
+    terms = O.training_losses(lambda xt, tt, y: O.dit_forward(leaves, spec, xt, tt, y), x1, t, x0, y=y)
+    cos = (1 - torch.nn.functional.cosine_similarity(terms["pred"], terms["ut"], dim=1)).mean(dim=(1, 2))
+    (cos.mean() + terms["loss"].mean()).backward()
+    ref = {k: v.grad for k, v in leaves.items() if v.grad is not None}
+    tr = FusedTrainer(m, lr=1e-3, transport=create_transport("Linear", "velocity", None, None, None, use_cosine_loss=True,
+                                                             use_lognorm=True))
+    with torch.no_grad():
+        loss, _ = tr.loss_and_grad(x1.cuda(), y.cuda(), t.cuda(), x0.cuda())
+    torch.cuda.synchronize()
+    assert _rel(loss, terms["loss"].detach()) < 1e-2 and _rel(tr.last_cos_loss, cos.detach()) < 1e-2
+    _compare({k: tr.grad_of(k) for k in tr.names}, ref)
+    # clipping: threshold at half of the true norm
+    ref_params = [torch.nn.Parameter(sd[k].clone()) for k in ref]
+    for p_, k in zip(ref_params, ref):
+        p_.grad = ref[k].clone()
+    total = float(torch.nn.utils.clip_grad_norm_(ref_params, 1e9))
+    tr.max_grad_norm = 0.5 * total
+    before = {k: sd[k].clone() for k in tr.names}
+    tr.optimizer_step()
+    torch.cuda.synchronize()
+    assert abs(float(tr.last_grad_norm) - total) < 2e-2 * total
+    assert abs(float(tr.grad.norm()) - 0.5 * total) < 2e-2 * total           # the buffer was scaled in place
+    moved = max(float((dict(m.named_parameters())[k].detach().cpu() - before[k]).abs().max()) for k in tr.names)
+    assert 0 < moved <= 1e-3 * 1.001                                          # first AdamW step: |update| <= lr
+
+
 def test_gradient_accumulation_equals_the_full_batch():
     """FusedTrainer micro-batches (train_accum.py gradient_accumulation_steps): the accumulated flat gradient of 2 micro-batches
     equals the gradient of the full batch (same draws), up to fp32 summation order."""
