@@ -388,15 +388,34 @@ def measure_train(args, dev, rank, world, model=None):
     model.train()
     trainer = FusedTrainer(model, lr=2e-4, betas=(0.9, 0.95), weight_decay=0.0, ema_decay=0.9999)
     g = torch.Generator().manual_seed(100 + rank)
-    x_host = torch.randn(B, 16, args.input_size, args.input_size, generator=g).pin_memory()
+    S = args.input_size
     y_host = torch.randint(0, 1000, (B,), generator=g).pin_memory()
     loss_host = torch.empty(B).pin_memory()
+    if args.train_input == "moments":
+        # synthetic "extracted features" -- posterior moments of every image and of its flip (extract_features.py:
+        # 168-181); coin flip, posterior sample and per-channel normalisation (img_latent_dataset.py:76-94) run on the device
+        # inside the kernel that builds xt / ut
+        mom_host = (torch.randn(B, 32, S, S, generator=g) * 0.5).pin_memory()
+        momf_host = (torch.randn(B, 32, S, S, generator=g) * 0.5).pin_memory()
+        lat_mean = (torch.randn(1, 16, 1, 1, generator=g) * 0.1).to(dev)
+        lat_std = (1.0 + 0.1 * torch.rand(1, 16, 1, 1, generator=g)).to(dev)
+        h2d = (mom_host.numel() + momf_host.numel()) * 4 + y_host.numel() * 8
 
-    def one_step():
-        x = x_host.to(dev, non_blocking=True)
-        y = y_host.to(dev, non_blocking=True)
-        loss = trainer.step(x, y)
-        loss_host.copy_(loss, non_blocking=True)
+        def one_step():
+            mom = mom_host.to(dev, non_blocking=True)
+            momf = momf_host.to(dev, non_blocking=True)
+            y = y_host.to(dev, non_blocking=True)
+            loss = trainer.step_from_moments(mom, momf, y, latent_mean=lat_mean, latent_std=lat_std, latent_multiplier=1.0)
+            loss_host.copy_(loss, non_blocking=True)
+    else:
+        x_host = torch.randn(B, 16, S, S, generator=g).pin_memory()
+        h2d = x_host.numel() * 4 + y_host.numel() * 8
+
+        def one_step():
+            x = x_host.to(dev, non_blocking=True)
+            y = y_host.to(dev, non_blocking=True)
+            loss = trainer.step(x, y)
+            loss_host.copy_(loss, non_blocking=True)
 
     def barrier():
         if world > 1:
@@ -434,9 +453,11 @@ def measure_train(args, dev, rank, world, model=None):
             "tflops_per_gpu": tfl, "frac_of_bf16_peak": tfl / pk["tflops"], "flops_per_sample": 3 * fwd,
             "gpu_launches": launches, "final_loss": final_loss,
             "class_ms_per_step": {k: round(v[0] / args.train_steps, 3) for k, v in prof.items() if v[1] > 0},
-            "includes": "H2D of latents/labels, label dropout, forward, loss, backward, gradient all-reduce (N>1), fused AdamW+EMA, "
-                        "bf16 weight re-pack, D2H of per-sample losses",
-            "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": B * 4}
+            "input": ("posterior moments of each image and of its flip [B,32,S,S] (extract_features.py shard format); flip select, "
+                      "posterior sample, normalisation on the device" if args.train_input == "moments" else "ready latents [B,16,S,S]"),
+            "includes": "H2D of the stored features/labels, input pipeline, label dropout, transport draws, forward, loss, backward, "
+                        "gradient all-reduce (N>1), fused AdamW+EMA, bf16 weight re-pack, D2H of per-sample losses",
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * 4}
 
 
 def measure_decode(args, dev, vae, world):
@@ -643,19 +664,33 @@ def run_gpu(args, rank, world, local_rank):
             return False
         return True
 
+    def guarded(fn, *a, **k):
+        """The headline is already measured and validated at this point: on one GPU a failing extra is recorded in the line as
+        {"error": ...} instead of costing it.  Under torchrun exceptions propagate (a rank failing alone would leave the others
+        inside a collective; torchrun then ends the whole job)."""
+        if world > 1:
+            return fn(*a, **k)
+        try:
+            return fn(*a, **k)
+        except Exception as ex:                                             # noqa: BLE001
+            print(f"bench.py: extra object {getattr(fn, '__name__', fn)} failed: {type(ex).__name__}: {ex}", file=sys.stderr, flush=True)
+            return {"error": f"{type(ex).__name__}: {str(ex)[:300]}"}
+
     if fits("vmae_decode object", 5.0, not args.no_decode_extra):
-        extras["vmae_decode"] = measure_decode(args, dev, vae, world)
+        extras["vmae_decode"] = guarded(measure_decode, args, dev, vae, world)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         # required leg: runs even when the budget is tight (reserved above), on a bounded sample
-        threads = os.cpu_count() or 1
-        per_img, t_ode, t_dec, kind = cpu_job(args.cpu_images, args.cpu_points, threads)
-        cpu = {"value": 1.0 / per_img, "unit": UNIT, "cores": threads, "kind": kind,
-               "sample": f"{args.cpu_images} images x {args.cpu_points - 1} CFG evaluations ({'the reference modules' if kind == 'reference' else 'fp32 oracle port of the reference'}, "
-                         f"{t_ode:.1f} s) + VMAE decode ({t_dec:.1f} s), scaled to 249 evaluations"}
+        def cpu_leg():
+            threads = os.cpu_count() or 1
+            per_img, t_ode, t_dec, kind = cpu_job(args.cpu_images, args.cpu_points, threads)
+            return {"value": 1.0 / per_img, "unit": UNIT, "cores": threads, "kind": kind,
+                    "sample": f"{args.cpu_images} images x {args.cpu_points - 1} CFG evaluations ({'the reference modules' if kind == 'reference' else 'fp32 oracle port of the reference'}, "
+                              f"{t_ode:.1f} s) + VMAE decode ({t_dec:.1f} s), scaled to 249 evaluations"}
+        cpu = guarded(cpu_leg)
+
     # the cond-only extension is one more full job and comes last (it is never the headline)
-    run_cond_only = fits("cond_only_when_unguided object", t_job + 3.0 + 25.0 + 40.0, not args.no_cond_only_extra)
-    if run_cond_only:
+    def cond_only_leg():
         job2 = SamplingJob(model, vae, num_steps=args.num_steps, cfg_scale=10.0, cfg_interval_start=0.10, timestep_shift=0.3,
                            cond_only_when_unguided=True)
         z_dev, y_dev = z_host.to(dev), y_host.to(dev)
@@ -666,19 +701,20 @@ def run_gpu(args, rank, world, local_rank):
         s1.record()
         barrier()
         ms_skip = s0.elapsed_time(s1)
-        extras["cond_only_when_unguided"] = {
-            "value": world * n / (ms_skip / 1e3), "unit": UNIT, "ms_per_step": ms_skip, "steps": 1,
-            "sample_forwards_per_image": job2.sample_forwards_per_image,
-            "note": "extension, NOT the headline: steps with t < cfg_interval_start evaluate only the conditional half (its guided "
-                    "velocity is its own prediction, lightningdit.py:436-439); images identical, 13.7% fewer FLOPs; rank 0's time"}
-        del job2
+        return {"value": world * n / (ms_skip / 1e3), "unit": UNIT, "ms_per_step": ms_skip, "steps": 1,
+                "sample_forwards_per_image": job2.sample_forwards_per_image,
+                "note": "extension, NOT the headline: steps with t < cfg_interval_start evaluate only the conditional half (its guided "
+                        "velocity is its own prediction, lightningdit.py:436-439); images identical, 13.7% fewer FLOPs; rank 0's time"}
+
+    if fits("cond_only_when_unguided object", t_job + 3.0 + 25.0 + 40.0, not args.no_cond_only_extra):
+        extras["cond_only_when_unguided"] = guarded(cond_only_leg)
     del job
     if fits("train object", 25.0, not args.no_train):
-        extras["train"] = measure_train(args, dev, rank, world, model=model)
+        extras["train"] = guarded(measure_train, args, dev, rank, world, model=model)
     del model, vae
     torch.cuda.empty_cache()
     if fits("xl_512 object", 40.0, not args.no_xl_extra and world == 1 and args.model == "LightningDiT-B/1"):
-        extras["xl_512"] = measure_xl(args, dev)
+        extras["xl_512"] = guarded(measure_xl, args, dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -749,6 +785,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--train-batch", type=int, default=128, help="training samples per GPU per optimizer step")
     ap.add_argument("--train-steps", type=int, default=10)
+    ap.add_argument("--train-input", default="moments", choices=["moments", "latents"],
+                    help="training-step input: the stored posterior moments (SURVEY 8d C3; on-device input pipeline) or ready latents")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement (the `train` object)")
     ap.add_argument("--train-only", action="store_true", help="measure only the training step and print its object")
     ap.add_argument("--no-decode-extra", action="store_true", help="skip the VMAE decode object (BASELINE configs[3])")
