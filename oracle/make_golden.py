@@ -237,6 +237,32 @@ def gen_config1():
     print("config 1: latent absmax", lat.abs().max().item(), "std", lat.std().item(), "u8 mean", u8.mean())
 
 
+from oracle.make_golden_cases import SDE_CASES  # noqa: E402
+
+
+def gen_sde():
+    """The reference's OWN SDE samplers (transport.py:285-396, integrators.py:8-75 -- no torchdiffeq involved) on the tiny
+    reference LightningDiT: every state of a 6-point run per (method, diffusion form, norm, last step, last step size), with
+    the global torch RNG seeded right before the call (the noise draws `th.randn(x.size())` come from it in call order).
+    Not covered: diffusion_form "constant" (the reference's `th.sqrt(2 * diffusion)` raises TypeError on the Python float that
+    form returns, integrators.py:33,44) and the default "SBDM" (starts at t = sample_eps = 0 where 1/t is infinite)."""
+    spec, ref, sd = tiny_dit(1)
+    g = torch.Generator().manual_seed(321)
+    x = torch.randn(3, 16, 8, 8, generator=g)
+    y = torch.randint(0, 10, (3,), generator=g)
+    tr = create_transport("Linear", "velocity", None, None, None, use_cosine_loss=False, use_lognorm=True)
+    smp = Sampler(tr)
+    out = {}
+    for i, (method, form, norm, last, lsz) in enumerate(SDE_CASES):
+        fn = smp.sample_sde(sampling_method=method, diffusion_form=form, diffusion_norm=norm, last_step=last, last_step_size=lsz,
+                            num_steps=6)
+        torch.manual_seed(1000 + i)
+        xs = fn(x, ref.forward, y=y)
+        out[f"traj{i}"] = torch.stack(xs).numpy()
+        print("sde", method, form, last, "final absmax", xs[-1].abs().max().item())
+    np.savez_compressed(os.path.join(OUT, "sde_tiny.npz"), seed=12, checksum=O.state_checksum(sd), x=x.numpy(), y=y.numpy(), **out)
+
+
 if __name__ == "__main__":
     if "--config1-only" in sys.argv:
         gen_config1()
@@ -247,10 +273,14 @@ if __name__ == "__main__":
     if "--grads-only" in sys.argv:
         gen_dit_grads()
         sys.exit(0)
+    if "--sde-only" in sys.argv:
+        gen_sde()
+        sys.exit(0)
     gen_dit_tiny()
     gen_dit_grads()
     gen_dit_variants()
     gen_dit_b1()
     gen_vmae()
     gen_config1()
+    gen_sde()
     print("golden fixtures written to", OUT)

@@ -507,6 +507,32 @@ def test_sde_samplers_shapes_last_steps_and_zero_diffusion_limit():
         smp.sample_ode_likelihood()
 
 
+def test_sde_samplers_reproduce_the_reference_trajectories(golden_dir):
+    """Sampler.sample_sde against the reference's OWN SDE code (transport.py:285-396, integrators.py:8-75; no torchdiffeq in it),
+    run by oracle/make_golden.py on the tiny reference LightningDiT: same global-RNG seed, so the noise draws line up call by
+    call; every state of every case (Euler-Maruyama / Heun, four diffusion forms, Mean / Tweedie / Euler last steps)."""
+    import torch
+    from ldmae_b200.transport import Sampler, create_transport
+    from oracle import ldmae_oracle as O
+    from oracle.make_golden_cases import SDE_CASES
+    g = np.load(os.path.join(golden_dir, "sde_tiny.npz"))
+    spec = O.DiTSpec(depth=2, hidden_size=128, patch_size=1, num_heads=2, input_size=8, in_channels=16, num_classes=10)
+    sd = O.synth_dit_state(spec, int(g["seed"]))
+    assert O.state_checksum(sd) == pytest.approx(float(g["checksum"]), rel=1e-9)
+    x, y = torch.from_numpy(g["x"]), torch.from_numpy(g["y"])
+    model = lambda xx, tt, **kw: O.dit_forward(sd, spec, xx, tt, **kw)
+    smp = Sampler(create_transport("Linear", "velocity", None, None, None, use_cosine_loss=False, use_lognorm=True))
+    with torch.no_grad():
+        for i, (method, form, norm, last, lsz) in enumerate(SDE_CASES):
+            fn = smp.sample_sde(sampling_method=method, diffusion_form=form, diffusion_norm=norm, last_step=last, last_step_size=lsz,
+                                num_steps=6)
+            torch.manual_seed(1000 + i)
+            xs = torch.stack(fn(x, model, y=y))
+            want = torch.from_numpy(g[f"traj{i}"])
+            assert xs.shape == want.shape == (6, 3, 16, 8, 8)
+            torch.testing.assert_close(xs, want, rtol=1e-3, atol=1e-4, msg=lambda m: f"{(method, form, last)}: {m}")
+
+
 def test_bench_budget_guard_cuts_warmup_then_steps():
     """bench.py's wall-clock budget (the driver's scaling harness allows 870 s per N): nothing is cut when the run fits; warm-up
     goes first (never below 3), timed steps after that (never below 1)."""
