@@ -263,6 +263,47 @@ def gen_sde():
     np.savez_compressed(os.path.join(OUT, "sde_tiny.npz"), seed=12, checksum=O.state_checksum(sd), x=x.numpy(), y=y.numpy(), **out)
 
 
+def gen_dataset():
+    """The trainer's input format: two safetensors shards in the layout of extract_features.py:168-181 are written
+    under tests/golden/latent_shards/ and read back by the reference's OWN ImgLatentDataset (datasets/img_latent_dataset.py,
+    loaded by file path: a HuggingFace `datasets` package may shadow the name) with seeded global RNGs -- the cached statistics
+    and every item, for (latent_norm, sample, multiplier) = (True, True, 1.3) and (False, False, 1.0)."""
+    import importlib.util
+    import shutil
+    import tempfile
+    from safetensors.torch import save_file
+    spec_ = importlib.util.spec_from_file_location("ref_img_latent_dataset", os.path.join("/root/reference/LDMAE", "datasets", "img_latent_dataset.py"))
+    mod = importlib.util.module_from_spec(spec_)
+    spec_.loader.exec_module(mod)
+    shard_dir = os.path.join(OUT, "latent_shards")
+    shutil.rmtree(shard_dir, ignore_errors=True)
+    os.makedirs(shard_dir)
+    g = torch.Generator().manual_seed(77)
+    for shard, n in enumerate((3, 2)):
+        lat = torch.randn(n, 32, 4, 4, generator=g) * 0.5
+        flip = torch.randn(n, 32, 4, 4, generator=g) * 0.5
+        labels = torch.randint(0, 1000, (n,), generator=g)
+        save_file({"latents": lat, "latents_flip": flip, "labels": labels},                     # extract_features.py:168-181
+                  os.path.join(shard_dir, f"latents_rank00_shard{shard:03d}.safetensors"),
+                  metadata={"total_size": f"{n}", "dtype": f"{lat.dtype}", "device": f"{lat.device}"})
+    out = {}
+    for tag, (norm, sample, mult) in (("a", (True, True, 1.3)), ("b", (False, False, 1.0))):
+        with tempfile.TemporaryDirectory() as tmp:
+            for f in os.listdir(shard_dir):
+                shutil.copy(os.path.join(shard_dir, f), tmp)
+            np.random.seed(5); torch.manual_seed(5)
+            import contextlib, io
+            with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+                ds = mod.ImgLatentDataset(tmp, latent_norm=norm, latent_multiplier=mult, sample=sample)
+            items = [ds[i] for i in range(len(ds))]
+            out[f"{tag}_features"] = torch.stack([f for f, _ in items]).numpy()
+            out[f"{tag}_labels"] = torch.stack([l for _, l in items]).numpy()
+            if norm:
+                out[f"{tag}_mean"], out[f"{tag}_std"] = ds._latent_mean.numpy(), ds._latent_std.numpy()
+    np.savez_compressed(os.path.join(OUT, "dataset_items.npz"), **out)
+    print("dataset goldens:", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     if "--config1-only" in sys.argv:
         gen_config1()
@@ -276,6 +317,9 @@ if __name__ == "__main__":
     if "--sde-only" in sys.argv:
         gen_sde()
         sys.exit(0)
+    if "--dataset-only" in sys.argv:
+        gen_dataset()
+        sys.exit(0)
     gen_dit_tiny()
     gen_dit_grads()
     gen_dit_variants()
@@ -283,4 +327,5 @@ if __name__ == "__main__":
     gen_vmae()
     gen_config1()
     gen_sde()
+    gen_dataset()
     print("golden fixtures written to", OUT)

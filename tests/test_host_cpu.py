@@ -233,6 +233,46 @@ def test_img_latent_dataset_reads_the_extract_features_shard_format(tmp_path):
     assert torch.allclose(x3, 3.0 * mom[0][2]) or torch.allclose(x3, 3.0 * flip[0][2])
 
 
+def test_img_latent_dataset_reproduces_the_reference_items(golden_dir, tmp_path):
+    """The trainer's input format pinned to the reference's OWN ImgLatentDataset (datasets/img_latent_dataset.py:16-94, run by
+    oracle/make_golden.py:gen_dataset on the committed shards tests/golden/latent_shards/): with the same global RNG seeds the
+    cached statistics and every item are bit-identical (coin flip, posterior sample, normalisation, multiplier), and
+    write_latent_shard writes shard files with the same tensors and metadata (extract_features.py:168-181)."""
+    import shutil
+    import torch
+    from safetensors import safe_open
+    from safetensors.torch import load_file
+    from ldmae_b200.datasets import ImgLatentDataset
+    from ldmae_b200.datasets.img_latent_dataset import write_latent_shard
+    g = np.load(os.path.join(golden_dir, "dataset_items.npz"))
+    shard_dir = os.path.join(golden_dir, "latent_shards")
+    shards = sorted(os.listdir(shard_dir))
+    assert len(shards) == 2
+    for tag, (norm, sample, mult) in (("a", (True, True, 1.3)), ("b", (False, False, 1.0))):
+        d = tmp_path / tag
+        d.mkdir()
+        for f in shards:
+            shutil.copy(os.path.join(shard_dir, f), d)
+        np.random.seed(5); torch.manual_seed(5)
+        ds = ImgLatentDataset(str(d), latent_norm=norm, latent_multiplier=mult, sample=sample)
+        assert len(ds) == 5
+        items = [ds[i] for i in range(len(ds))]
+        assert torch.equal(torch.stack([f for f, _ in items]), torch.from_numpy(g[f"{tag}_features"]))
+        assert torch.equal(torch.stack([l for _, l in items]), torch.from_numpy(g[f"{tag}_labels"]))
+        if norm:
+            assert torch.equal(ds._latent_mean, torch.from_numpy(g["a_mean"])) and torch.equal(ds._latent_std, torch.from_numpy(g["a_std"]))
+            assert os.path.exists(d / "latents_stats.pt")                       # cached like the reference (:44-52)
+    for i, f in enumerate(shards):
+        t = load_file(os.path.join(shard_dir, f))
+        out = write_latent_shard(str(tmp_path / "w"), 0, i, t["latents"], t["latents_flip"], t["labels"])
+        assert os.path.basename(out) == f
+        # same tensors, dtypes and metadata (the header's metadata ORDER is a hash-map order in safetensors, not a format property)
+        with safe_open(out, framework="pt") as a, safe_open(os.path.join(shard_dir, f), framework="pt") as b:
+            assert a.metadata() == b.metadata() and sorted(a.keys()) == sorted(b.keys()) == ["labels", "latents", "latents_flip"]
+            for k in a.keys():
+                assert a.get_tensor(k).dtype == b.get_tensor(k).dtype and torch.equal(a.get_tensor(k), b.get_tensor(k))
+
+
 def test_prescaled_softmax_algebra_and_score_bound():
     """The inference forward folds softmax scale * log2(e) into q_norm.weight (EpiQKV::Params::q_mul) and the attention kernel
     takes p = 2^(q.k) with neither scale nor offset (attention_persist_sm100.cuh, kRaw).  Host-side statement of that algebra
