@@ -237,7 +237,7 @@ def gen_config1():
     print("config 1: latent absmax", lat.abs().max().item(), "std", lat.std().item(), "u8 mean", u8.mean())
 
 
-from oracle.make_golden_cases import SDE_CASES  # noqa: E402
+from oracle.make_golden_cases import SDE_CASES, state_fingerprint  # noqa: E402
 
 
 def gen_sde():
@@ -304,6 +304,52 @@ def gen_dataset():
     print("dataset goldens:", {k: v.shape for k, v in out.items()})
 
 
+def _ref_function(path, name):
+    """One top-level function of a reference driver script that cannot be imported as a whole (train_accum.py needs accelerate
+    and CUDA): its source segment is compiled on its own with torch in scope."""
+    import ast
+    from collections import OrderedDict
+    src = open(path).read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == name)
+    ns = {"torch": torch, "OrderedDict": OrderedDict}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    return ns[name]
+
+
+def gen_host_helpers():
+    """Host-side helpers pinned to the reference's own code: the image pre-processing of extract_features.py
+    (tokenizer/models_mae.py:85-103 center_crop_arr, :935-950 img_transform) on synthetic PIL images, and the trainer's
+    fine-tuning initialisation (train_accum.py:308-334 load_weights_with_shape_check) on tiny reference models."""
+    from PIL import Image
+    rng = np.random.RandomState(3)
+    out = {}
+    vae = ref_mae.mae_for_ldmae_f8d16_prev(ldmae_mode=True, no_cls=True, kl_loss_weight=True, smooth_output=True, img_size=64)
+    for i, (h, w) in enumerate(((75, 101), (300, 170), (64, 64))):          # plain resize, two BOX halvings first, identity
+        arr = rng.randint(0, 256, size=(h, w, 3), dtype=np.uint8)
+        out[f"img{i}"] = arr
+        out[f"crop{i}"] = np.array(ref_mae.center_crop_arr(Image.fromarray(arr), 64))
+        out[f"tensor{i}"] = vae.img_transform(p_hflip=0)(Image.fromarray(arr)).numpy()
+    # fine-tuning init: 16-channel checkpoint into a 32-channel model, one mismatched and one unknown tensor
+    load_ref = _ref_function("/root/reference/LDMAE/train_accum.py", "load_weights_with_shape_check")
+    mk = lambda c: LightningDiT(input_size=8, patch_size=1, in_channels=c, hidden_size=128, depth=2, num_heads=2, num_classes=10,
+                                use_qknorm=True, use_swiglu=True, use_rope=True, use_rmsnorm=True)
+    spec16 = O.DiTSpec(depth=2, hidden_size=128, patch_size=1, num_heads=2, input_size=8, in_channels=16, num_classes=10)
+    spec32 = O.DiTSpec(depth=2, hidden_size=128, patch_size=1, num_heads=2, input_size=8, in_channels=32, num_classes=10)
+    target = mk(32)
+    assert not load_into(target, O.synth_dit_state(spec32, 21))
+    ckpt = {"model": dict(O.synth_dit_state(spec16, 22))}
+    ckpt["model"]["blocks.0.attn.q_norm.weight"] = torch.ones(32)           # shape mismatch -> skipped
+    ckpt["model"]["not_a_parameter"] = torch.ones(3)                        # unknown -> skipped
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        load_ref(target, ckpt, rank=0)
+    keys, fp = state_fingerprint(target.state_dict())
+    out["load_keys"], out["load_fp"] = np.array(keys), fp
+    out["load_proj"] = target.state_dict()["x_embedder.proj.weight"].numpy()
+    np.savez_compressed(os.path.join(OUT, "host_helpers.npz"), **out)
+    print("host helper goldens:", {k: getattr(v, "shape", None) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     if "--config1-only" in sys.argv:
         gen_config1()
@@ -320,6 +366,9 @@ if __name__ == "__main__":
     if "--dataset-only" in sys.argv:
         gen_dataset()
         sys.exit(0)
+    if "--helpers-only" in sys.argv:
+        gen_host_helpers()
+        sys.exit(0)
     gen_dit_tiny()
     gen_dit_grads()
     gen_dit_variants()
@@ -328,4 +377,5 @@ if __name__ == "__main__":
     gen_config1()
     gen_sde()
     gen_dataset()
+    gen_host_helpers()
     print("golden fixtures written to", OUT)

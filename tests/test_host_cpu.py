@@ -394,6 +394,43 @@ def test_load_weights_with_shape_check_pads_patch_embedding(tmp_path):
     assert set(dst._ldmae_skipped_keys) == {"final_layer.linear.weight", "final_layer.linear.bias", "not_a_parameter"}
 
 
+def test_host_helpers_reproduce_the_reference_functions(golden_dir):
+    """Host helpers pinned to the reference's own code (oracle/make_golden.py:gen_host_helpers): centre crop + image transform of
+    extract_features.py (tokenizer/models_mae.py:85-103,935-950) bit for bit on three synthetic images (plain resize, two BOX
+    halvings first, identity), and load_weights_with_shape_check (train_accum.py:308-334) -- 16-channel checkpoint into a
+    32-channel model with one mismatched and one unknown tensor -- key by key."""
+    import torch
+    from PIL import Image
+    from ldmae_b200 import checkpoint as ck
+    from ldmae_b200.models.lightningdit import LightningDiT
+    from ldmae_b200.tokenizer import models_mae
+    from oracle import ldmae_oracle as O
+    from oracle.make_golden_cases import state_fingerprint
+    g = np.load(os.path.join(golden_dir, "host_helpers.npz"))
+    vae = models_mae.mae_for_ldmae_f8d16_prev(ldmae_mode=True, no_cls=True, kl_loss_weight=True, smooth_output=True, img_size=64)
+    for i in range(3):
+        img = Image.fromarray(g[f"img{i}"])
+        assert np.array_equal(np.array(models_mae.center_crop_arr(img, 64)), g[f"crop{i}"])
+        assert np.array_equal(vae.img_transform(p_hflip=0)(img).numpy(), g[f"tensor{i}"])
+    spec16 = O.DiTSpec(depth=2, hidden_size=128, patch_size=1, num_heads=2, input_size=8, in_channels=16, num_classes=10)
+    spec32 = O.DiTSpec(depth=2, hidden_size=128, patch_size=1, num_heads=2, input_size=8, in_channels=32, num_classes=10)
+    target = LightningDiT(input_size=8, patch_size=1, in_channels=32, hidden_size=128, depth=2, num_heads=2, num_classes=10,
+                          use_qknorm=True, use_swiglu=True, use_rope=True, use_rmsnorm=True)
+    target.load_state_dict(O.synth_dit_state(spec32, 21), strict=True)
+    ckpt = {"model": dict(O.synth_dit_state(spec16, 22))}
+    ckpt["model"]["blocks.0.attn.q_norm.weight"] = torch.ones(32)
+    ckpt["model"]["not_a_parameter"] = torch.ones(3)
+    ck.load_weights_with_shape_check(target, ckpt, rank=0, verbose=False)
+    # skipped like the reference: the planted mismatch, the unknown key, and the final layer (its output channels follow in_channels)
+    assert sorted(target._ldmae_skipped_keys) == ["blocks.0.attn.q_norm.weight", "final_layer.linear.bias", "final_layer.linear.weight",
+                                                  "not_a_parameter"]
+    keys, fp = state_fingerprint(target.state_dict())
+    assert keys == [str(k) for k in g["load_keys"]]
+    np.testing.assert_array_equal(fp, g["load_fp"])                                  # copies and zero padding: exact
+    assert np.array_equal(target.state_dict()["x_embedder.proj.weight"].numpy(), g["load_proj"])
+    assert float(np.abs(g["load_proj"][:, 16:]).max()) == 0.0 and float(np.abs(g["load_proj"][:, :16]).max()) > 0.0
+
+
 def test_fused_optimizer_state_round_trips_through_torch_adamw():
     """The flat moment buffers export to / import from torch.optim.AdamW(model.parameters()).state_dict() -- the 'opt' entry
     of the reference's checkpoints (frozen pos_embed keeps its parameter index and has no state)."""
