@@ -92,6 +92,29 @@ def test_training_losses_algebra():
     assert float(seen["t"].min()) > 0 and float(seen["t"].max()) < 1        # logit-normal times
 
 
+def test_transport_draws_reproduce_the_reference_rng_stream(golden_dir):
+    """Transport.sample (transport.py:113-166): with the same torch / numpy global seeds the mirror must draw the SAME x0
+    (randn_like) and logit-normal t (the reference goes through scipy.stats.norm.rvs, which consumes numpy's global stream
+    exactly like np.random.normal) as the unmodified reference did when oracle/make_golden.py recorded them, and the loss
+    through the oracle's forward then equals the reference's."""
+    from ldmae_b200.transport import create_transport
+    from oracle import ldmae_oracle as O
+    for patch in (1, 2):
+        g = np.load(os.path.join(golden_dir, f"dit_tiny_p{patch}.npz"))
+        x, y = torch.from_numpy(g["x"]), torch.from_numpy(g["y"])
+        tr = create_transport("Linear", "velocity", None, None, None, use_cosine_loss=False, use_lognorm=True)
+        torch.manual_seed(7); np.random.seed(7)
+        t, x0, x1 = tr.sample(x)
+        assert torch.equal(x0, torch.from_numpy(g["loss_x0"])) and torch.equal(x1, x)
+        torch.testing.assert_close(t, torch.from_numpy(g["loss_t"]), rtol=1e-6, atol=0)
+        spec = O.DiTSpec(depth=2, hidden_size=128, patch_size=patch, num_heads=2, input_size=8, in_channels=16, num_classes=10)
+        sd = O.synth_dit_state(spec, int(g["seed"]))
+        torch.manual_seed(7); np.random.seed(7)
+        with torch.no_grad():
+            terms = tr.training_losses(lambda xt, tt, y: O.dit_forward(sd, spec, xt, tt, y), x, dict(y=y))
+        torch.testing.assert_close(terms["loss"], torch.from_numpy(g["loss"]), rtol=2e-4, atol=2e-5)
+
+
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
