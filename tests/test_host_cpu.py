@@ -511,9 +511,10 @@ def test_cosine_loss_term_matches_reference_expression():
     out = torch.randn(3, 4, 6, 6, generator=g, requires_grad=True)
     ut = torch.randn(3, 4, 6, 6, generator=g)
     gas = 2
-    mse = mean_flat((out - ut) ** 2)
-    cos = mean_flat(1 - torch.nn.functional.cosine_similarity(out, ut, dim=1))
-    ((cos.mean() + mse.mean()) / gas).backward()
+    with torch.enable_grad():                               # other test modules switch autograd off process-wide
+        mse = mean_flat((out - ut) ** 2)
+        cos = mean_flat(1 - torch.nn.functional.cosine_similarity(out, ut, dim=1))
+        ((cos.mean() + mse.mean()) / gas).backward()
     got_cos, dcos = cosine_loss_terms(out.detach(), ut, 1.0 / gas)
     dmse = 2 * (out.detach() - ut) / out[0].numel() / out.shape[0] / gas                # what ldmae_flow_loss writes
     torch.testing.assert_close(got_cos, cos.detach())
