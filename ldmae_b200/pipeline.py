@@ -15,6 +15,8 @@ import torch
 
 from .transport import Sampler, create_transport
 
+__all__ = ["SamplingJob", "FeatureExtractionJob", "build_sampling_models"]
+
 
 class SamplingJob:
     """One rank's sampler + decoder with persistent device / pinned buffers for a fixed batch size."""
@@ -100,6 +102,71 @@ class SamplingJob:
             events[3].record()
         torch.cuda.current_stream(self.device).synchronize()
         return out_host
+
+
+class FeatureExtractionJob:
+    """One rank's body of the reference's feature-extraction loop (LDMAE/extract_features.py:140-188): images in [-1, 1]
+    -> VMAE encoder -> posterior moments of every image AND of its horizontal flip -> safetensors shards
+    ``latents_rankRR_shardSSS.safetensors`` of ``shard_images // batch_size`` batches each (10000 images in the reference),
+    the remainder in a last shard -- the files ``ImgLatentDataset`` / ``FusedTrainer.step_from_moments`` read.
+
+    The reference runs two DataLoaders (RandomHorizontalFlip p=0 and p=1) and two encoder calls per batch; here the flipped
+    batch is ``x.flip(-1)`` on the device (the flip commutes with ToTensor / Normalize, and the centre crop precedes it,
+    models_mae.py:935-950) and both halves go through ONE encoder call on the doubled batch.  ``sample=True`` stores the
+    moments ``tokenizer._encode(x)`` (configs with a ``data.sample`` key, extract_features.py:150-151), ``sample=False`` the
+    posterior mode (:153).  ``vae`` is any object with the tokenizer mirror's ``_encode`` / ``encode``."""
+
+    def __init__(self, vae, output_dir, *, rank=0, batch_size=256, shard_images=10000, sample=True, device=None):
+        if batch_size <= 0 or shard_images < batch_size:
+            raise ValueError(f"shard_images ({shard_images}) must hold at least one batch of {batch_size}")
+        self.vae, self.output_dir, self.rank = vae, output_dir, int(rank)
+        self.batches_per_shard = shard_images // batch_size            # extract_features.py:164
+        self.sample = bool(sample)
+        self.device = torch.device(device) if device is not None else None
+        self.latents, self.latents_flip, self.labels = [], [], []
+        self.saved_files, self.run_images, self.paths = 0, 0, []
+
+    def _encode(self, x):
+        if self.sample:
+            return self.vae._encode(x)
+        return self.vae.encode(x).latent_dist.mode().detach()
+
+    def add_batch(self, x, y, x_flip=None):
+        """x [B,3,H,W] in [-1,1] (host or device), y [B] labels; ``x_flip``: the separately loaded flipped batch of the
+        reference's second loader (default: flipped on the device).  Returns the shard path when this batch completed one."""
+        dev = self.device if self.device is not None else x.device
+        x = x.to(dev, non_blocking=True)
+        xf = x.flip(-1) if x_flip is None else x_flip.to(dev, non_blocking=True)
+        with torch.no_grad():
+            z = self._encode(torch.cat([x, xf], 0))
+        B = x.shape[0]
+        self.latents.append(z[:B]); self.latents_flip.append(z[B:]); self.labels.append(y.detach().cpu())
+        self.run_images += B
+        if len(self.latents) == self.batches_per_shard:
+            return self._flush()
+        return None
+
+    def finish(self):
+        """Writes the remainder (extract_features.py:189-206); returns the list of all shard paths."""
+        if self.latents:
+            self._flush()
+        return self.paths
+
+    def compute_stats(self):
+        """extract_features.py:213-216 (rank 0, after every rank has finished): constructing the dataset computes and caches
+        ``latents_stats.pt``.  Returns (mean, std) of shape [1, C', 1, 1]."""
+        from .datasets import ImgLatentDataset
+        ds = ImgLatentDataset(self.output_dir, latent_norm=True, sample=self.sample)
+        return ds._latent_mean, ds._latent_std
+
+    def _flush(self):
+        from .datasets.img_latent_dataset import write_latent_shard
+        path = write_latent_shard(self.output_dir, self.rank, self.saved_files, torch.cat(self.latents, 0),
+                                  torch.cat(self.latents_flip, 0), torch.cat(self.labels, 0))
+        self.latents, self.latents_flip, self.labels = [], [], []
+        self.saved_files += 1
+        self.paths.append(path)
+        return path
 
 
 def build_sampling_models(device, *, model_name="LightningDiT-B/1", input_size=32, in_channels=16, img_size=256, seed=0,

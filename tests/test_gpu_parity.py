@@ -193,6 +193,48 @@ def test_vmae_encode_vs_reference_golden(golden_dir, tag, img):
     assert rec.shape == pix.shape and torch.isfinite(rec).all()
 
 
+def test_feature_extraction_job_on_the_library_encoder(golden_dir, tmp_path):
+    """The extract_features.py loop (:140-216) through FeatureExtractionJob on the library-backed encoder: the stored moments of
+    every image and of its flip against the oracle's encoder (fp32 CPU), the doubled-batch encoder call against two separate
+    calls, and the shard read back by the trainer's dataset + on-device input pipeline shapes."""
+    from safetensors import safe_open
+    from ldmae_b200.datasets import ImgLatentDataset
+    from ldmae_b200.pipeline import FeatureExtractionJob
+    from ldmae_b200.tokenizer import models_mae
+    from gpu_util import load_npz
+    g = load_npz(golden_dir, "vmae_small.npz")
+    spec = O.VMAESpec(img_size=32)
+    vsd = O.synth_vmae_state(spec, int(g["seed"]), encoder=True)
+    vae = models_mae.mae_for_ldmae_f8d16_prev(ldmae_mode=True, no_cls=True, kl_loss_weight=True, smooth_output=True, img_size=32)
+    vae.load_state_dict(vsd, strict=True)
+    vae = vae.cuda().eval()
+    gen = torch.Generator().manual_seed(17)
+    imgs = torch.rand(5, 3, 32, 32, generator=gen) * 2 - 1
+    labels = torch.randint(0, 1000, (5,), generator=gen)
+    job = FeatureExtractionJob(vae, str(tmp_path), rank=0, batch_size=2, shard_images=4, sample=True, device="cuda")
+    for i in range(0, 5, 2):
+        job.add_batch(imgs[i:i + 2], labels[i:i + 2])
+    paths = job.finish()
+    assert len(paths) == 2
+    lat, flip, ys = [], [], []
+    for p_ in paths:
+        with safe_open(p_, framework="pt") as f:
+            assert f.metadata()["device"].startswith("cuda")                 # like the reference: device of the tensors before .cpu()
+            lat.append(f.get_tensor("latents")); flip.append(f.get_tensor("latents_flip")); ys.append(f.get_tensor("labels"))
+    lat, flip, ys = torch.cat(lat), torch.cat(flip), torch.cat(ys)
+    assert lat.shape == flip.shape == (5, 32, 4, 4) and torch.equal(ys, labels)
+    ref, ref_flip = O.vmae_encode_moments(vsd, spec, imgs), O.vmae_encode_moments(vsd, spec, imgs.flip(-1))
+    e1, e2 = _rel(lat, ref), _rel(flip, ref_flip)
+    print(f"feature extraction: moments rel err {e1:.3e} (images) {e2:.3e} (flips)")
+    assert e1 < FINAL_TOL and e2 < FINAL_TOL
+    sep = torch.cat([vae._encode(imgs.cuda()), vae._encode(imgs.flip(-1).cuda())]).cpu()
+    assert _rel(torch.cat([lat, flip]), sep) < 1e-3                          # one doubled-batch call vs two calls
+    mean, std = job.compute_stats()
+    ds = ImgLatentDataset(str(tmp_path), latent_norm=True, sample=True)
+    x, y = ds[4]
+    assert x.shape == (16, 4, 4) and int(y) == int(labels[4]) and torch.isfinite(x).all() and mean.shape == (1, 16, 1, 1)
+
+
 def test_cond_only_shortcut_is_bit_identical_for_the_kept_half(golden_dir):
     """Below the guidance interval only the conditional half is evaluated; the kept half must not change at all."""
     from ldmae_b200.transport import Sampler, create_transport

@@ -296,6 +296,59 @@ def test_img_latent_dataset_reproduces_the_reference_items(golden_dir, tmp_path)
                 assert a.get_tensor(k).dtype == b.get_tensor(k).dtype and torch.equal(a.get_tensor(k), b.get_tensor(k))
 
 
+def test_feature_extraction_job_writes_the_shards_the_dataset_reads(tmp_path):
+    """FeatureExtractionJob = the loop body of extract_features.py:140-216 around any encoder with the tokenizer's `_encode`:
+    shards of shard_images // batch_size batches, the remainder in a last shard, moments of every image and of its flip, the
+    cached statistics -- read back through ImgLatentDataset (the trainer's side of the format)."""
+    import torch
+    from safetensors import safe_open
+    from ldmae_b200.datasets import ImgLatentDataset
+    from ldmae_b200.pipeline import FeatureExtractionJob
+
+    class FakeVae:                                       # deterministic stand-in for the library-backed encoder
+        calls = 0
+
+        def _encode(self, x):
+            FakeVae.calls += 1
+            pooled = torch.nn.functional.avg_pool2d(x, 8)                               # [B, 3, 2, 2] for 16 x 16 images
+            return torch.cat([pooled, pooled * 2.0, pooled[:, :2] - 1.0], 1)            # "moments" [B, 8, 2, 2]
+
+    g = torch.Generator().manual_seed(4)
+    imgs = torch.rand(7, 3, 16, 16, generator=g) * 2 - 1
+    labels = torch.arange(7) * 3
+    job = FeatureExtractionJob(FakeVae(), str(tmp_path), rank=1, batch_size=2, shard_images=4, sample=True)
+    done = [job.add_batch(imgs[i:i + 2], labels[i:i + 2]) for i in range(0, 7, 2)]
+    paths = job.finish()
+    assert [os.path.basename(p) for p in paths] == [f"latents_rank01_shard{i:03d}.safetensors" for i in range(2)]
+    # like the reference the shard boundary counts BATCHES (len(latents) == 10000 // batch_size): the short last batch closes shard 1
+    assert done == [None, paths[0], None, paths[1]] and job.run_images == 7 and FakeVae.calls == 4   # one encoder call per batch
+    want, want_flip = FakeVae()._encode(imgs), FakeVae()._encode(imgs.flip(-1))
+    got, got_flip, got_y = [], [], []
+    for p_ in paths:
+        with safe_open(p_, framework="pt") as f:
+            got.append(f.get_tensor("latents")); got_flip.append(f.get_tensor("latents_flip")); got_y.append(f.get_tensor("labels"))
+    assert [t.shape[0] for t in got] == [4, 3]
+    assert torch.equal(torch.cat(got), want) and torch.equal(torch.cat(got_flip), want_flip) and torch.equal(torch.cat(got_y), labels)
+    # a remainder that does not complete a shard is written by finish() (extract_features.py:189-206)
+    job3 = FeatureExtractionJob(FakeVae(), str(tmp_path / "c"), batch_size=2, shard_images=4)
+    assert [job3.add_batch(imgs[i:i + 2], labels[i:i + 2]) is not None for i in (0, 2, 4)] == [False, True, False]
+    assert len(job3.paths) == 1 and len(job3.finish()) == 2
+    with safe_open(job3.paths[1], framework="pt") as f:
+        assert torch.equal(f.get_tensor("latents"), want[4:6])
+    # the reference's second loader delivers the flipped batch itself: same result
+    job2 = FeatureExtractionJob(FakeVae(), str(tmp_path / "b"), batch_size=7, shard_images=7)
+    job2.add_batch(imgs, labels, x_flip=imgs.flip(-1))
+    with safe_open(job2.finish()[0], framework="pt") as f:
+        assert torch.equal(f.get_tensor("latents_flip"), want_flip)
+    np.random.seed(0); torch.manual_seed(0)
+    mean, std = job.compute_stats()
+    assert mean.shape == (1, 4, 1, 1) and os.path.exists(tmp_path / "latents_stats.pt")
+    ds = ImgLatentDataset(str(tmp_path), latent_norm=True, sample=True)
+    assert len(ds) == 7 and ds[3][0].shape == (4, 2, 2) and int(ds[3][1]) == 9
+    with pytest.raises(ValueError):
+        FeatureExtractionJob(FakeVae(), str(tmp_path), batch_size=8, shard_images=4)
+
+
 def test_prescaled_softmax_algebra_and_score_bound():
     """The inference forward folds softmax scale * log2(e) into q_norm.weight (EpiQKV::Params::q_mul) and the attention kernel
     takes p = 2^(q.k) with neither scale nor offset (attention_persist_sm100.cuh, kRaw).  Host-side statement of that algebra
