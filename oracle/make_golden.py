@@ -350,6 +350,34 @@ def gen_host_helpers():
     print("host helper goldens:", {k: getattr(v, "shape", None) for k, v in out.items()})
 
 
+def gen_dit_hd72():
+    """The XL head geometry (head_dim 72 = hidden 1152 / 16 heads, lightningdit.py:509-515) at toy width: hidden 144, 2 heads,
+    so the RoPE tables ([T, 72], 18 frequencies per axis) and the per-head RMSNorm(72) of the reference pin the oracle for the
+    wide-head path too (the GPU tests of the XL kernels compare with the oracle)."""
+    spec = O.DiTSpec(depth=2, hidden_size=144, patch_size=1, num_heads=2, input_size=8, in_channels=16, num_classes=10)
+    ref = LightningDiT(input_size=8, patch_size=1, in_channels=16, hidden_size=144, depth=2, num_heads=2, num_classes=10,
+                       use_qknorm=True, use_swiglu=True, use_rope=True, use_rmsnorm=True)
+    ref_shapes = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    assert ref_shapes == O.dit_param_shapes(spec), set(ref_shapes) ^ set(O.dit_param_shapes(spec))
+    sd = O.synth_dit_state(spec, seed=72)
+    for k in ("pos_embed", "feat_rope.freqs_cos", "feat_rope.freqs_sin"):
+        assert torch.equal(sd[k], ref.state_dict()[k]), k
+    assert not load_into(ref, sd)
+    ref.eval()
+    g = torch.Generator().manual_seed(172)
+    n = 2
+    x = torch.randn(2 * n, 16, 8, 8, generator=g); t = torch.rand(2 * n, generator=g); y = torch.randint(0, 10, (2 * n,), generator=g)
+    out = ref(x, t, y)
+    ycfg = torch.cat([y[:n], torch.full((n,), 10)])
+    tr = create_transport("Linear", "velocity", None, None, None, use_cosine_loss=False, use_lognorm=True)
+    fn = Sampler(tr).sample_ode(sampling_method="euler", num_steps=5, atol=1e-6, rtol=1e-3, reverse=False, timestep_shift=0.3)
+    traj = fn(torch.cat([x[:n], x[:n]], 0), ref.forward_with_cfg, y=ycfg, cfg_scale=4.0, cfg_interval=True, cfg_interval_start=0.10)
+    np.savez_compressed(os.path.join(OUT, "dit_tiny_hd72.npz"), seed=72, checksum=O.state_checksum(sd), x=x.numpy(), t=t.numpy(),
+                        y=y.numpy(), ycfg=ycfg.numpy(), out=out.numpy(), traj_last=traj[-1].numpy(),
+                        rope_cos=ref.state_dict()["feat_rope.freqs_cos"].numpy())
+    print("dit hd72: out absmax", out.abs().max().item(), "rope table", tuple(ref.state_dict()["feat_rope.freqs_cos"].shape))
+
+
 if __name__ == "__main__":
     if "--config1-only" in sys.argv:
         gen_config1()
@@ -369,6 +397,9 @@ if __name__ == "__main__":
     if "--helpers-only" in sys.argv:
         gen_host_helpers()
         sys.exit(0)
+    if "--hd72-only" in sys.argv:
+        gen_dit_hd72()
+        sys.exit(0)
     gen_dit_tiny()
     gen_dit_grads()
     gen_dit_variants()
@@ -378,4 +409,5 @@ if __name__ == "__main__":
     gen_sde()
     gen_dataset()
     gen_host_helpers()
+    gen_dit_hd72()
     print("golden fixtures written to", OUT)

@@ -71,6 +71,23 @@ def test_dit_tiny_variants(golden_dir, tag, flags):
     torch.testing.assert_close(O.dit_forward(sd, spec, _t(g["x"]), _t(g["t"]), _t(g["y"])), _t(g["out"]), **TOL)
 
 
+def test_dit_head_dim_72_geometry(golden_dir):
+    """The XL head geometry (head_dim 72; lightningdit.py:509-515) at toy width against the reference: RoPE tables [T, 72],
+    per-head RMSNorm(72), forward and a guided Euler run -- the oracle the wide-head GPU kernels are compared with."""
+    g = _load(golden_dir, "dit_tiny_hd72.npz")
+    spec = O.DiTSpec(depth=2, hidden_size=144, patch_size=1, num_heads=2, input_size=8, in_channels=16, num_classes=10)
+    sd = O.synth_dit_state(spec, int(g["seed"]))
+    assert O.state_checksum(sd) == pytest.approx(float(g["checksum"]), rel=1e-9)
+    assert sd["feat_rope.freqs_cos"].shape == (64, 72) and np.array_equal(sd["feat_rope.freqs_cos"].numpy(), g["rope_cos"])
+    x, t, y, ycfg = _t(g["x"]), _t(g["t"]), _t(g["y"]), _t(g["ycfg"])
+    torch.testing.assert_close(O.dit_forward(sd, spec, x, t, y), _t(g["out"]), **TOL)
+    n = x.shape[0] // 2
+    fn = lambda xx, tt, **k: O.dit_forward_with_cfg(sd, spec, xx, tt, **k)
+    traj = O.sample_ode(fn, torch.cat([x[:n], x[:n]], 0), sampling_method="euler", num_steps=5, timestep_shift=0.3, y=ycfg,
+                        cfg_scale=4.0, cfg_interval=True, cfg_interval_start=0.10)
+    torch.testing.assert_close(traj[-1], _t(g["traj_last"]), rtol=1e-3, atol=1e-4)
+
+
 def test_dit_b1_forward(golden_dir):
     g = _load(golden_dir, "dit_b1_forward.npz")
     spec = O.DiTSpec.named("LightningDiT-B/1", input_size=32, in_channels=16)
