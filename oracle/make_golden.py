@@ -46,7 +46,7 @@ def tiny_dit(patch, **flags):
                      num_classes=10, **flags)
     ref = LightningDiT(input_size=8, patch_size=patch, in_channels=16, hidden_size=128, depth=2, num_heads=2,
                        num_classes=10, use_qknorm=spec.use_qknorm, use_swiglu=spec.use_swiglu,
-                       use_rope=spec.use_rope, use_rmsnorm=spec.use_rmsnorm, wo_shift=spec.wo_shift)
+                       use_rope=spec.use_rope, use_rmsnorm=spec.use_rmsnorm, wo_shift=spec.wo_shift, learn_sigma=spec.learn_sigma)
     # the reference's own state_dict must have exactly the keys/shapes the oracle lists
     ref_shapes = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
     assert ref_shapes == O.dit_param_shapes(spec), set(ref_shapes) ^ set(O.dit_param_shapes(spec))
@@ -137,12 +137,16 @@ def gen_dit_variants():
     for tag, flags in (("noqk", dict(use_qknorm=False)), ("woshift", dict(wo_shift=True)),
                        # fallbacks of lightningdit.py:195-224,257-261: LayerNorm block / head / final norms, timm Mlp + tanh-GELU
                        ("ln_gelu", dict(use_rmsnorm=False, use_swiglu=False)), ("ln_swiglu", dict(use_rmsnorm=False)),
-                       ("rms_gelu", dict(use_swiglu=False)), ("ln_gelu_noqk", dict(use_rmsnorm=False, use_swiglu=False, use_qknorm=False))):
-        spec, ref, sd = tiny_dit(1, **flags)
+                       ("rms_gelu", dict(use_swiglu=False)), ("ln_gelu_noqk", dict(use_rmsnorm=False, use_swiglu=False, use_qknorm=False)),
+                       # lightningdit.py:298,415-417: twice the output channels, the second half dropped by forward; no RoPE (:317-323)
+                       ("learnsigma", dict(learn_sigma=True)), ("learnsigma_p2", dict(learn_sigma=True, patch=2)), ("norope", dict(use_rope=False))):
+        flags = dict(flags)
+        patch = flags.pop("patch", 1)
+        spec, ref, sd = tiny_dit(patch, **flags)
         g = torch.Generator().manual_seed(55)
         x = torch.randn(2, 16, 8, 8, generator=g); t = torch.rand(2, generator=g); y = torch.randint(0, 10, (2,), generator=g)
         out = ref(x, t, y)
-        np.savez_compressed(os.path.join(OUT, f"dit_tiny_{tag}.npz"), seed=12, checksum=O.state_checksum(sd),
+        np.savez_compressed(os.path.join(OUT, f"dit_tiny_{tag}.npz"), seed=11 + patch, checksum=O.state_checksum(sd),
                             x=x.numpy(), t=t.numpy(), y=y.numpy(), out=out.numpy())
         print("dit variant", tag, out.abs().max().item())
 
@@ -351,11 +355,11 @@ def gen_host_helpers():
 
 
 def gen_dit_hd72():
-    """The XL head geometry (head_dim 72 = hidden 1152 / 16 heads, lightningdit.py:509-515) at toy width: hidden 144, 2 heads,
+    """The XL head geometry (head_dim 72 = hidden 1152 / 16 heads, lightningdit.py:509-515) at depth 2 (hidden 1152, 16 heads, 256 tokens),
     so the RoPE tables ([T, 72], 18 frequencies per axis) and the per-head RMSNorm(72) of the reference pin the oracle for the
     wide-head path too (the GPU tests of the XL kernels compare with the oracle)."""
-    spec = O.DiTSpec(depth=2, hidden_size=144, patch_size=1, num_heads=2, input_size=8, in_channels=16, num_classes=10)
-    ref = LightningDiT(input_size=8, patch_size=1, in_channels=16, hidden_size=144, depth=2, num_heads=2, num_classes=10,
+    spec = O.DiTSpec(depth=2, hidden_size=1152, patch_size=1, num_heads=16, input_size=16, in_channels=16, num_classes=10)
+    ref = LightningDiT(input_size=16, patch_size=1, in_channels=16, hidden_size=1152, depth=2, num_heads=16, num_classes=10,
                        use_qknorm=True, use_swiglu=True, use_rope=True, use_rmsnorm=True)
     ref_shapes = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
     assert ref_shapes == O.dit_param_shapes(spec), set(ref_shapes) ^ set(O.dit_param_shapes(spec))
@@ -366,7 +370,7 @@ def gen_dit_hd72():
     ref.eval()
     g = torch.Generator().manual_seed(172)
     n = 2
-    x = torch.randn(2 * n, 16, 8, 8, generator=g); t = torch.rand(2 * n, generator=g); y = torch.randint(0, 10, (2 * n,), generator=g)
+    x = torch.randn(2 * n, 16, 16, 16, generator=g); t = torch.rand(2 * n, generator=g); y = torch.randint(0, 10, (2 * n,), generator=g)
     out = ref(x, t, y)
     ycfg = torch.cat([y[:n], torch.full((n,), 10)])
     tr = create_transport("Linear", "velocity", None, None, None, use_cosine_loss=False, use_lognorm=True)

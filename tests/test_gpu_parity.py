@@ -34,7 +34,7 @@ def _tiny_model(patch, seed, **flags):
                      num_classes=10, **flags)
     m = LightningDiT(input_size=8, patch_size=patch, in_channels=16, hidden_size=128, depth=2, num_heads=2, num_classes=10,
                      use_qknorm=spec.use_qknorm, use_swiglu=spec.use_swiglu, use_rope=spec.use_rope, use_rmsnorm=spec.use_rmsnorm,
-                     wo_shift=spec.wo_shift)
+                     wo_shift=spec.wo_shift, learn_sigma=spec.learn_sigma)
     sd = O.synth_dit_state(spec, seed)
     m.load_state_dict(sd, strict=True)
     return spec, sd, m.cuda().eval()
@@ -90,11 +90,14 @@ def test_sampler_euler_heun_vs_reference_golden(golden_dir, patch):
 @pytest.mark.parametrize("tag,flags", [("noqk", dict(use_qknorm=False)), ("woshift", dict(wo_shift=True)),
                                       ("ln_gelu", dict(use_rmsnorm=False, use_swiglu=False)), ("ln_swiglu", dict(use_rmsnorm=False)),
                                       ("rms_gelu", dict(use_swiglu=False)),
-                                      ("ln_gelu_noqk", dict(use_rmsnorm=False, use_swiglu=False, use_qknorm=False))])
+                                      ("ln_gelu_noqk", dict(use_rmsnorm=False, use_swiglu=False, use_qknorm=False)),
+                                      ("learnsigma", dict(learn_sigma=True)), ("learnsigma_p2", dict(learn_sigma=True, patch=2)),
+                                      ("norope", dict(use_rope=False))])
 def test_dit_tiny_variants(golden_dir, tag, flags):
     from gpu_util import load_npz
     g = load_npz(golden_dir, f"dit_tiny_{tag}.npz")
-    spec, sd, m = _tiny_model(1, int(g["seed"]), **flags)
+    flags = dict(flags)
+    spec, sd, m = _tiny_model(flags.pop("patch", 1), int(g["seed"]), **flags)
     x, t, y = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["t"]).cuda(), torch.from_numpy(g["y"]).cuda()
     out = m(x, t, y)
     err = _rel(out, g["out"])
@@ -115,6 +118,30 @@ def test_dit_tiny_variants(golden_dir, tag, flags):
         assert _rel(ours, want) < FINAL_TOL
         with torch.enable_grad(), pytest.raises(NotImplementedError, match="inference-only"):
             m(x, t, y)
+
+
+def test_dit_head_dim_72_vs_reference_golden(golden_dir):
+    """The wide-head path (head_dim 72 in 128-column slots: EpiQKVWide, attention_hd128) against the unmodified reference at the XL
+    width (hidden 1152, 16 heads, depth 2, 256 tokens; tests/golden/dit_tiny_hd72.npz): forward and the last state of a guided Euler run."""
+    from ldmae_b200.models.lightningdit import LightningDiT
+    from ldmae_b200.transport import Sampler, create_transport
+    from gpu_util import load_npz
+    g = load_npz(golden_dir, "dit_tiny_hd72.npz")
+    spec = O.DiTSpec(depth=2, hidden_size=1152, patch_size=1, num_heads=16, input_size=16, in_channels=16, num_classes=10)
+    m = LightningDiT(input_size=16, patch_size=1, in_channels=16, hidden_size=1152, depth=2, num_heads=16, num_classes=10,
+                     use_qknorm=True, use_swiglu=True, use_rope=True, use_rmsnorm=True)
+    m.load_state_dict(O.synth_dit_state(spec, int(g["seed"])), strict=True)
+    m = m.cuda().eval()
+    x, t, y = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["t"]).cuda(), torch.from_numpy(g["y"]).cuda()
+    err = _rel(m(x, t, y), g["out"])
+    n = x.shape[0] // 2
+    fn = Sampler(create_transport("Linear", "velocity", None, None, None)).sample_ode(
+        sampling_method="euler", num_steps=5, atol=1e-6, rtol=1e-3, reverse=False, timestep_shift=0.3)
+    last = fn(torch.cat([x[:n], x[:n]], 0), m.forward_with_cfg, y=torch.from_numpy(g["ycfg"]).cuda(), cfg_scale=4.0,
+              cfg_interval=True, cfg_interval_start=0.10)[-1]
+    err2 = _rel(last, g["traj_last"])
+    print(f"head_dim 72 vs reference: velocity rel err {err:.3e}, final latent {err2:.3e}")
+    assert err < FWD_TOL and err2 < FINAL_TOL
 
 
 def test_dit_b1_forward_vs_reference_golden(golden_dir):

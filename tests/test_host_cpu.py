@@ -56,13 +56,13 @@ def test_constant_tables_equal_the_reference_for_both_head_widths(golden_dir):
     from ldmae_b200.models.lightningdit import LightningDiT
     from oracle import ldmae_oracle as O
     g = np.load(os.path.join(golden_dir, "dit_tiny_hd72.npz"))
-    m = LightningDiT(input_size=8, patch_size=1, in_channels=16, hidden_size=144, depth=2, num_heads=2, num_classes=10,
+    m = LightningDiT(input_size=16, patch_size=1, in_channels=16, hidden_size=1152, depth=2, num_heads=16, num_classes=10,
                      use_qknorm=True, use_swiglu=True, use_rope=True, use_rmsnorm=True)
     assert np.array_equal(m.feat_rope.freqs_cos.numpy(), g["rope_cos"])
-    for hidden in (128, 144):
-        spec = O.DiTSpec(depth=2, hidden_size=hidden, patch_size=1, num_heads=2, input_size=8, in_channels=16, num_classes=10)
+    for hidden, heads in ((128, 2), (1152, 16)):
+        spec = O.DiTSpec(depth=2, hidden_size=hidden, patch_size=1, num_heads=heads, input_size=16, in_channels=16, num_classes=10)
         sd = O.synth_dit_state(spec, 1)                     # the oracle's tables are asserted equal to the reference's in make_golden.py
-        mm = LightningDiT(input_size=8, patch_size=1, in_channels=16, hidden_size=hidden, depth=2, num_heads=2, num_classes=10,
+        mm = LightningDiT(input_size=16, patch_size=1, in_channels=16, hidden_size=hidden, depth=2, num_heads=heads, num_classes=10,
                           use_qknorm=True, use_swiglu=True, use_rope=True, use_rmsnorm=True)
         for k in ("pos_embed", "feat_rope.freqs_cos", "feat_rope.freqs_sin"):
             assert torch.equal(mm.state_dict()[k], sd[k]), (hidden, k)

@@ -63,22 +63,25 @@ def test_dit_tiny_forward_cfg_and_sampler(golden_dir, patch):
 @pytest.mark.parametrize("tag,flags", [("noqk", dict(use_qknorm=False)), ("woshift", dict(wo_shift=True)),
                                       ("ln_gelu", dict(use_rmsnorm=False, use_swiglu=False)), ("ln_swiglu", dict(use_rmsnorm=False)),
                                       ("rms_gelu", dict(use_swiglu=False)),
-                                      ("ln_gelu_noqk", dict(use_rmsnorm=False, use_swiglu=False, use_qknorm=False))])
+                                      ("ln_gelu_noqk", dict(use_rmsnorm=False, use_swiglu=False, use_qknorm=False)),
+                                      ("learnsigma", dict(learn_sigma=True)), ("learnsigma_p2", dict(learn_sigma=True, patch=2)),
+                                      ("norope", dict(use_rope=False))])
 def test_dit_tiny_variants(golden_dir, tag, flags):
     g = _load(golden_dir, f"dit_tiny_{tag}.npz")
-    spec = _tiny_spec(1, **flags)
+    flags = dict(flags)
+    spec = _tiny_spec(flags.pop("patch", 1), **flags)
     sd = O.synth_dit_state(spec, int(g["seed"]))
     torch.testing.assert_close(O.dit_forward(sd, spec, _t(g["x"]), _t(g["t"]), _t(g["y"])), _t(g["out"]), **TOL)
 
 
 def test_dit_head_dim_72_geometry(golden_dir):
-    """The XL head geometry (head_dim 72; lightningdit.py:509-515) at toy width against the reference: RoPE tables [T, 72],
+    """The XL head geometry (head_dim 72; lightningdit.py:509-515) at depth 2 against the reference: RoPE tables [T, 72],
     per-head RMSNorm(72), forward and a guided Euler run -- the oracle the wide-head GPU kernels are compared with."""
     g = _load(golden_dir, "dit_tiny_hd72.npz")
-    spec = O.DiTSpec(depth=2, hidden_size=144, patch_size=1, num_heads=2, input_size=8, in_channels=16, num_classes=10)
+    spec = O.DiTSpec(depth=2, hidden_size=1152, patch_size=1, num_heads=16, input_size=16, in_channels=16, num_classes=10)
     sd = O.synth_dit_state(spec, int(g["seed"]))
     assert O.state_checksum(sd) == pytest.approx(float(g["checksum"]), rel=1e-9)
-    assert sd["feat_rope.freqs_cos"].shape == (64, 72) and np.array_equal(sd["feat_rope.freqs_cos"].numpy(), g["rope_cos"])
+    assert sd["feat_rope.freqs_cos"].shape == (256, 72) and np.array_equal(sd["feat_rope.freqs_cos"].numpy(), g["rope_cos"])
     x, t, y, ycfg = _t(g["x"]), _t(g["t"]), _t(g["y"]), _t(g["ycfg"])
     torch.testing.assert_close(O.dit_forward(sd, spec, x, t, y), _t(g["out"]), **TOL)
     n = x.shape[0] // 2
