@@ -27,6 +27,17 @@ def test_library_exports_every_declared_symbol():
     assert lib.ldmae_version() >= 100
 
 
+def test_integration_doc_names_every_abi_symbol():
+    """INTEGRATION.md's table of entry points (which reference interface each one sits under) must not rot: every function the
+    header declares is named there."""
+    hdr = open(os.path.join(ROOT, "include", "ldmae_b200.h")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    declared = set(re.findall(r"\b(ldmae_[a-z0-9_]+)\s*\(", hdr))
+    groups = {m[:-1] for m in re.findall(r"ldmae_[a-z0-9_]*\*", doc)}                     # e.g. "ldmae_dit_debug_*"
+    missing = sorted(s for s in declared if s not in doc and not any(s.startswith(g) for g in groups))
+    assert not missing, missing
+
+
 def test_product_refuses_to_run_without_gpu():
     from ldmae_b200 import _lib
     from ldmae_b200.models.lightningdit import LightningDiT
