@@ -15,7 +15,30 @@ import torch
 
 from .transport import Sampler, create_transport
 
-__all__ = ["SamplingJob", "FeatureExtractionJob", "build_sampling_models"]
+__all__ = ["SamplingJob", "FeatureExtractionJob", "build_sampling_models", "rank_seed", "shard_plan", "output_indices"]
+
+
+# ----------------------------------------------------------------------------- multi-GPU sampling bookkeeping (no collective)
+def rank_seed(global_seed, world, rank):
+    """inference.py:87: every process seeds its own noise / label stream."""
+    return int(global_seed) * int(world) + int(rank)
+
+
+def shard_plan(num_samples, per_proc_batch, world):
+    """inference.py:194-205: a bit more than ``num_samples`` so that it divides evenly; returns (total_samples, iterations per
+    rank).  The batch is sharded by rank with no data-path collective: rank r produces images r, r + W, r + 2W, ... of every
+    global batch."""
+    import math
+    global_batch = int(per_proc_batch) * int(world)
+    total = int(math.ceil(num_samples / global_batch) * global_batch)
+    per_rank = total // world
+    assert total % world == 0 and per_rank % per_proc_batch == 0
+    return total, per_rank // per_proc_batch
+
+
+def output_indices(n, rank, world, total_so_far):
+    """inference.py:295-296: file index of the i-th image of this rank's batch = i * W + rank + total."""
+    return [i * world + rank + total_so_far for i in range(n)]
 
 
 class SamplingJob:
@@ -77,6 +100,29 @@ class SamplingJob:
 
     def run_device(self, z, y):
         return self.decode_u8(self.sample_latents(z, y))
+
+    def sample_shard(self, *, rank, world, global_seed, num_samples, per_proc_batch, num_classes, on_images, latent_size=None,
+                     done_samples=0):
+        """This rank's part of a ``num_samples`` job, as the reference's loop does it (inference.py:87,194-205,264-298): seed
+        ``global_seed * W + rank``, ``iterations`` batches of ``per_proc_batch`` images with z and y drawn ON THE DEVICE from
+        the seeded default generator, ``on_images(indices, uint8[n,H,W,3] numpy)`` per batch with the reference's file indices
+        ``i * W + rank + total``.  ``done_samples`` (images already on disk) skips finished iterations like the reference's
+        resume count (:204).  No collective: ranks never exchange data.  Returns the number of images produced."""
+        total_samples, iterations = shard_plan(num_samples, per_proc_batch, world)
+        torch.manual_seed(rank_seed(global_seed, world, rank))
+        S = latent_size if latent_size is not None else self.model.input_size
+        C, n = self.model.in_channels, per_proc_batch
+        done_iterations = (done_samples // world) // n
+        total, made = 0, 0
+        for it in range(iterations):
+            z = torch.randn(n, C, S, S, device=self.device)
+            y = torch.randint(0, num_classes, (n,), device=self.device)
+            if it >= done_iterations:                         # the draws above keep the RNG stream aligned with a fresh run
+                u8 = self.run_device(z, y)
+                on_images(output_indices(n, rank, world, total), u8.cpu().numpy())
+                made += n
+            total += n * world
+        return made
 
     # -- host-to-host path (what inference.py does per iteration) --------------------------------
     def run_host(self, z_host, y_host, out_host=None, events=None):

@@ -312,6 +312,31 @@ def test_sampling_job_vs_oracle():
     assert (diff <= 2).mean() > 0.98
 
 
+def test_sample_shard_walks_the_reference_plan_on_the_device():
+    """SamplingJob.sample_shard (inference.py:87,194-205,264-298) on the CUDA path: rank 1 of 2 produces the reference's file
+    indices, and its first batch is bit-identical to run_device on the z / y drawn from the rank's seed."""
+    from ldmae_b200.models.lightningdit import LightningDiT
+    from ldmae_b200.pipeline import SamplingJob, rank_seed
+    from ldmae_b200.tokenizer import models_mae
+    ds = O.DiTSpec(depth=2, hidden_size=128, patch_size=1, num_heads=2, input_size=16, in_channels=16, num_classes=10)
+    vs = O.VMAESpec(img_size=128)
+    m = LightningDiT(input_size=16, patch_size=1, in_channels=16, hidden_size=128, depth=2, num_heads=2, num_classes=10,
+                     use_qknorm=True, use_swiglu=True, use_rope=True, use_rmsnorm=True)
+    m.load_state_dict(O.synth_dit_state(ds, 3)); m = m.cuda().eval()
+    vae = models_mae.mae_for_ldmae_f8d16_prev(ldmae_mode=True, no_cls=True, kl_loss_weight=True, smooth_output=True, img_size=128)
+    vae.load_state_dict(O.synth_vmae_state(vs, 4), strict=False); vae = vae.cuda().eval()
+    job = SamplingJob(m, vae, num_steps=5, cfg_scale=4.0, cfg_interval_start=0.10, timestep_shift=0.3)
+    got = []
+    made = job.sample_shard(rank=1, world=2, global_seed=0, num_samples=8, per_proc_batch=2, num_classes=10,
+                            on_images=lambda idx, u8: got.append((idx, u8)))
+    assert made == 4 and [g_[0] for g_ in got] == [[1, 3], [5, 7]]
+    assert got[0][1].shape == (2, 128, 128, 3) and got[0][1].dtype == np.uint8 and got[0][1].std() > 1
+    torch.manual_seed(rank_seed(0, 2, 1))
+    z = torch.randn(2, 16, 16, 16, device="cuda"); y = torch.randint(0, 10, (2,), device="cuda")
+    assert np.array_equal(job.run_device(z, y).cpu().numpy(), got[0][1])
+    assert not np.array_equal(got[0][1], got[1][1])
+
+
 def test_dit_xl_head_dim_72_forward_and_sampler_vs_oracle():
     """LightningDiT-XL geometry (width 1152, 16 heads, head_dim 72; lightningdit.py:509-515) at depth 2: forward,
     forward_with_cfg and a short Euler sampler against the CPU oracle (the wide-head kernels; inference path)."""

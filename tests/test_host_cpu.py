@@ -181,6 +181,54 @@ def test_two_rank_sharding_over_gloo():
     assert g0 == g1 and abs(g0[0] - s0) < 1e-4 and abs(g0[1] - s1) < 1e-4
 
 
+def test_sampling_shard_bookkeeping_matches_inference_py():
+    """inference.py:87,194-205,295-296: per-rank seed, the rounded-up total, iterations per rank, and the file indices -- over all
+    ranks and iterations every index below the total is produced exactly once; SamplingJob.sample_shard walks that plan with
+    z / y drawn from the seeded default generator (run_device stubbed: the CUDA path is covered by the -m gpu tests)."""
+    from ldmae_b200.pipeline import SamplingJob, output_indices, rank_seed, shard_plan
+    assert rank_seed(0, 8, 3) == 3 and rank_seed(5, 8, 3) == 43
+    assert shard_plan(50000, 256, 8) == (51200, 25) and shard_plan(50000, 125, 4) == (50000, 100) and shard_plan(10, 4, 2) == (16, 2)
+    for num, n, W in ((50, 4, 2), (33, 3, 4), (8, 8, 1)):
+        total, iters = shard_plan(num, n, W)
+        seen = []
+        for r in range(W):
+            t = 0
+            for _ in range(iters):
+                seen += output_indices(n, r, W, t)
+                t += n * W
+        assert sorted(seen) == list(range(total)) and total >= num and total - num < n * W
+
+    class Stub(SamplingJob):
+        def __init__(self):
+            self.device = torch.device("cpu")
+            self.model = type("M", (), {"input_size": 4, "in_channels": 2})()
+            self.seen = []
+
+        def run_device(self, z, y):
+            self.seen.append((z.clone(), y.clone()))
+            return (z[:, :1].abs() * 40).clamp(0, 255).permute(0, 2, 3, 1).expand(-1, -1, -1, 3).to(torch.uint8)
+
+    got = {}
+    jobs = []
+    for r in range(2):
+        job = Stub()
+        made = job.sample_shard(rank=r, world=2, global_seed=3, num_samples=10, per_proc_batch=3, num_classes=7,
+                                on_images=lambda idx, u8: got.update({i: im for i, im in zip(idx, u8)}))
+        assert made == 6 and len(job.seen) == 2
+        jobs.append(job)
+    assert sorted(got) == list(range(12)) and got[0].shape == (4, 4, 3) and got[0].dtype == np.uint8
+    # the stream is the seeded default generator: rank 1's first batch is reproducible from its seed alone
+    torch.manual_seed(rank_seed(3, 2, 1))
+    z = torch.randn(3, 2, 4, 4); y = torch.randint(0, 7, (3,))
+    assert torch.equal(jobs[1].seen[0][0], z) and torch.equal(jobs[1].seen[0][1], y)
+    assert not torch.equal(jobs[0].seen[0][0], jobs[1].seen[0][0])
+    # resume: with the first global batch on disk only the second iteration is produced, from the same RNG position
+    job = Stub()
+    made = job.sample_shard(rank=1, world=2, global_seed=3, num_samples=10, per_proc_batch=3, num_classes=7,
+                            on_images=lambda idx, u8: None, done_samples=6)
+    assert made == 3 and torch.equal(job.seen[0][0], jobs[1].seen[1][0])
+
+
 # ----------------------------------------------------------------------------- training host logic (CPU)
 def test_flat_layout_makes_parameters_views_of_one_buffer():
     from ldmae_b200.models.lightningdit import LightningDiT
