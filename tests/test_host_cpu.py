@@ -77,6 +77,14 @@ def test_constant_tables_equal_the_reference_for_both_head_widths(golden_dir):
                           use_qknorm=True, use_swiglu=True, use_rope=True, use_rmsnorm=True)
         for k in ("pos_embed", "feat_rope.freqs_cos", "feat_rope.freqs_sin"):
             assert torch.equal(mm.state_dict()[k], sd[k]), (hidden, k)
+    # the tokenizer's tables come from float32 omega (tokenizer/util/pos_embed.py:20-67), unlike the DiT's float64 ones
+    from ldmae_b200.tokenizer import models_mae
+    for img in (32, 256):
+        vs = O.VMAESpec(img_size=img)
+        vsd = O.synth_vmae_state(vs, 1, encoder=True)        # asserted equal to the reference's tables in make_golden.py:gen_vmae
+        vae = models_mae.mae_for_ldmae_f8d16_prev(ldmae_mode=True, no_cls=True, kl_loss_weight=True, smooth_output=True, img_size=img)
+        for k in ("pos_embed", "decoder_pos_embed"):
+            assert torch.equal(vae.state_dict()[k], vsd[k]), (img, k)
 
 
 def test_time_grid_matches_oracle_and_counts():
