@@ -787,3 +787,39 @@ def test_bench_budget_guard_cuts_warmup_then_steps():
     per_block, total = bench.dit_flops_per_sample_forward()
     assert abs(total / 1e9 - 212.74) < 0.05
     assert abs(bench.vmae_decode_flops_per_image() / 1e9 - 20.70) < 0.05
+
+
+def test_budget_guard_and_shard_plan_properties():
+    """Property checks (hypothesis) of the two pure planners: bench.plan_steps never exceeds what was asked, never goes below its
+    floors, says what it cut, and its result fits the budget unless it is already at the floors; pipeline.shard_plan always
+    covers the request with whole global batches and less than one global batch of surplus."""
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+    import bench
+    from ldmae_b200.pipeline import shard_plan
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.integers(0, 10), st.integers(1, 40), st.floats(0, 900), st.floats(0.1, 400), st.floats(0, 100))
+    def plan(w, k, t_el, t_step, reserve):
+        W, K, notes = bench.plan_steps(w, k, t_el, t_step, reserve, 810.0)
+        assert 0 <= W <= w and 1 <= K <= k and W >= min(w, 3)
+        fits = lambda ww, kk: w <= 0 or t_el + (ww - 1 + kk) * t_step + reserve <= 810.0
+        if fits(w, k):
+            assert (W, K, notes) == (w, k, [])
+        elif (W, K) == (w, k):
+            assert w <= 3 and k == 1 and notes == []              # already at the floors: nothing left to cut
+        else:
+            assert notes                                          # whatever was cut is reported
+            assert fits(W, K) or (W == min(w, 3) and K == 1)      # fits now, or is down to the floors
+            if K < k:
+                assert W == min(w, 3)                             # timed steps are only cut after the warm-up is at its floor
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.integers(1, 100000), st.integers(1, 512), st.integers(1, 16))
+    def shards(num, n, world):
+        total, iters = shard_plan(num, n, world)
+        assert total >= num and total - num < n * world and total == iters * n * world
+
+    plan()
+    shards()
+
