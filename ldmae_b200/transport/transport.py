@@ -403,8 +403,12 @@ class Sampler:
         return _sample
 
     def sample_ode_likelihood(self, **_):
+        """Not built.  The reference's own version cannot run as written either: transport.py:481-489 constructs ``ode(...)``
+        without the required ``timestep_shift`` keyword (integrators.py:79-90), so ``Sampler.sample_ode_likelihood(...)`` raises
+        TypeError upstream (checked against the unmodified reference, tests/test_host_cpu.py)."""
         raise NotImplementedError("the likelihood ODE (transport.py:445-497) differentiates the model with respect to its input; "
-                                  "ldmae_b200's LightningDiT produces parameter gradients only -- outside the path")
+                                  "ldmae_b200's LightningDiT produces parameter gradients only -- outside the path (the reference's "
+                                  "own version raises TypeError: it omits ode()'s required timestep_shift argument)")
 
     def sample_ode(self, *, sampling_method="dopri5", num_steps=50, atol=1e-6, rtol=1e-3, reverse=False,
                    timestep_shift=0.0, keep_trajectory=None, cond_only_when_unguided=False):

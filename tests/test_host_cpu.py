@@ -772,6 +772,27 @@ def test_sde_samplers_reproduce_the_reference_trajectories(golden_dir):
             torch.testing.assert_close(xs, want, rtol=1e-3, atol=1e-4, msg=lambda m: f"{(method, form, last)}: {m}")
 
 
+def test_reference_likelihood_ode_raises_upstream_too():
+    """Sampler.sample_ode_likelihood is not built (NotImplementedError).  The unmodified reference's version cannot run either:
+    transport.py:481-489 calls ode(...) without its required timestep_shift keyword (integrators.py:79-90).  Checked in a
+    separate process against the staged / original reference files when they are present (skipped on a box without them)."""
+    import subprocess
+    from oracle import refshim
+    if not refshim.reference_available():
+        pytest.skip("reference files not present")
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from oracle import refshim; refshim.install()\n"
+            "from transport import create_transport, Sampler\n"
+            "try:\n"
+            "    Sampler(create_transport('Linear', 'velocity', None, None, None)).sample_ode_likelihood(sampling_method='euler', num_steps=5)\n"
+            "    print('RAN')\n"
+            "except TypeError as e:\n"
+            "    print('TypeError', e)\n") % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, TORCHDYNAMO_DISABLE="1")).stdout
+    assert "TypeError" in out and "timestep_shift" in out, out
+
+
 def test_bench_budget_guard_cuts_warmup_then_steps():
     """bench.py's wall-clock budget (the driver's scaling harness allows 870 s per N): nothing is cut when the run fits; warm-up
     goes first (never below 3), timed steps after that (never below 1)."""
