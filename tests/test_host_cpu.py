@@ -27,6 +27,33 @@ def test_library_exports_every_declared_symbol():
     assert lib.ldmae_version() >= 100
 
 
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """The drop-in boundary is a C ABI: include/ldmae_b200.h must compile as C99 (pedantic) and as C++, and a C program that only
+    includes it must link against libldmae_b200.so and call the introspection entry points (no compute without a GPU)."""
+    import shutil
+    import subprocess
+    from ldmae_b200 import build
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    hdr = os.path.join(ROOT, "include", "ldmae_b200.h")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr], check=True)
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr], check=True)
+    so = build.build()
+    src = tmp_path / "abi.c"
+    src.write_text('#include "ldmae_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) { ldmae_dit* h = 0; ldmae_dit_config cfg = {0};\n'
+                   '  int rc = ldmae_dit_create(&cfg, &h);   /* no device / bad config: must fail cleanly, not crash */\n'
+                   '  printf("%d %lld %d [%s]\\n", ldmae_version(), ldmae_launch_count(), rc, ldmae_last_error());\n'
+                   '  return rc == 0; }\n')
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", str(src), "-I", os.path.join(ROOT, "include"), "-o", str(exe), so,
+                    f"-Wl,-rpath,{os.path.dirname(so)}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, (out.stdout, out.stderr)
+    ver, launches, rc, msg = out.stdout.split(" ", 3)
+    assert int(ver) >= 100 and int(launches) == 0 and int(rc) < 0 and len(msg.strip()) > 2      # an error code and a message
+
+
 def test_integration_doc_names_every_abi_symbol():
     """INTEGRATION.md's table of entry points (which reference interface each one sits under) must not rot: every function the
     header declares is named there."""
